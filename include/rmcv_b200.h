@@ -1,0 +1,255 @@
+/*
+ * rmcv_b200 — C ABI of the B200-native rmcv detection hot path.
+ *
+ * Drop-in boundary for the three free functions the reference calls back to back at
+ * executable/main.cpp:172-176 (all citations relative to the reference tree):
+ *
+ *     rm::extract_color      include/imgproc.h:29       src/imgproc.cpp:50-75
+ *     rm::filter_lightblobs  include/objdetect.h:47-49  src/objdetect.cpp:55-87
+ *     rm::filter_armours     include/objdetect.h:70-71  src/objdetect.cpp:114-166
+ *     rm::lightblob / rm::armour ctors   include/core.h:89-130   src/core.cpp:9-49
+ *
+ * The reference has no FFI of its own (it is a static C++ library over OpenCV), so this header
+ * *is* the binding surface: plain pointers and sizes, POD structs, int status codes, no
+ * exceptions, no OpenCV and no torch types.  include/rmcv_gpu/rm_shim.hpp rebuilds the rm::
+ * signatures on top of it; INTEGRATION.md shows the reference-side wiring.
+ *
+ * Threading: one rmcv_ctx per host thread and GPU.  All device work of a ctx is stream-ordered;
+ * entry points documented "async" return before the GPU has finished — call rmcv_sync() (or a
+ * fetch/host entry point, which syncs) before reading outputs.
+ *
+ * There is no CPU fallback anywhere behind this ABI: without a CUDA device every entry point
+ * that needs one returns RMCV_ERR_CUDA / RMCV_ERR_NO_DEVICE.
+ */
+#ifndef RMCV_B200_H
+#define RMCV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMCV_B200_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------- */
+enum {
+    RMCV_OK = 0,
+    RMCV_ERR_INVALID_ARG = -1, /* null pointer, non-positive size, size above the ctx maxima ...  */
+    RMCV_ERR_CUDA = -2,        /* a CUDA runtime call failed; rmcv_last_error() has the text      */
+    RMCV_ERR_CAPACITY = -3,    /* a per-frame capacity (runs / blobs / armours) overflowed;       */
+                               /* the frames concerned carry RMCV_FRAME_OVERFLOW_* flags          */
+    RMCV_ERR_NO_DEVICE = -4,
+    RMCV_ERR_STATE = -5        /* call order violated (e.g. fetch before detect)                  */
+};
+
+/* rm::camp, include/core.h:20-23 */
+enum { RMCV_CAMP_RED = 0, RMCV_CAMP_BLUE = 1, RMCV_CAMP_GUIDELIGHT = 2, RMCV_CAMP_NEUTRAL = -1 };
+
+/* Daheng DX_PIXEL_COLOR_FILTER, hardware/include/daheng/DxImageProc.h:54-61 (the names give the
+ * colours of the first two pixels of row 0).  daheng::capture passes 4, or 2 when mirrored
+ * (hardware/src/daheng.cpp:81). */
+enum { RMCV_BAYER_RG = 1, RMCV_BAYER_GB = 2, RMCV_BAYER_GR = 3, RMCV_BAYER_BG = 4 };
+
+/* per-contour verdict of rm::filter_lightblobs (src/objdetect.cpp:64,82,83) */
+enum { RMCV_CONTOUR_SKIPPED = 0, RMCV_CONTOUR_POSITIVE = 1, RMCV_CONTOUR_NEGATIVE = 2 };
+
+/* which branch cv::fitEllipseDirect took for a contour */
+enum { RMCV_FIT_NONE = 0, RMCV_FIT_DIRECT = 1, RMCV_FIT_FALLBACK = 2 };
+
+enum {
+    RMCV_FRAME_OVERFLOW_RUNS = 1,
+    RMCV_FRAME_OVERFLOW_BLOBS = 2,
+    RMCV_FRAME_OVERFLOW_ARMOURS = 4
+};
+
+/* ---- PODs --------------------------------------------------------------------------------- */
+
+/* cv::RotatedRect as the reference consumes it (centre, size, angle in degrees), float32. */
+typedef struct rmcv_rotated_rect {
+    float cx, cy, w, h, angle;
+} rmcv_rotated_rect;
+
+/* rm::lightblob public fields, include/core.h:92-96.  56 bytes. */
+typedef struct rmcv_lightblob {
+    float angle;           /* 90 = upright                                                      */
+    int32_t target;        /* rm::camp                                                          */
+    float center[2];       /* x, y                                                              */
+    float vertices[4][2];  /* left-down, left-up, right-up, right-down (src/core.cpp:276-280)   */
+    float size[2];         /* width = short side, height = long side (src/core.cpp:18)          */
+} rmcv_lightblob;
+
+/* rm::armour public geometry, include/core.h:110-112, plus the pair that produced it and the
+ * gate quantities of rm::filter_armours (the reference keeps no score).  112 bytes. */
+typedef struct rmcv_armour {
+    float icon[4][2];
+    float vertices[4][2];
+    float bounding_box[4]; /* x, y, width, height (cv::Rect2f)                                   */
+    int32_t i, j;          /* indices into the frame's positive light-blob list, i < j           */
+    float gates[6];        /* |Δangle|, shear_i, shear_j, min/max height, |Δcy|, |Δcx|           */
+} rmcv_armour;
+
+/* One external contour (= one 8-connected component not nested in a hole), in the order
+ * cv::findContours returns them (reverse raster order of the first pixel).  72 bytes. */
+typedef struct rmcv_contour_info {
+    int32_t first_x, first_y;  /* raster-first pixel = contour[0]                                */
+    int32_t n_points;          /* contour.size() with CHAIN_APPROX_NONE (revisits counted)       */
+    int32_t status;            /* RMCV_CONTOUR_*                                                 */
+    int64_t area2;             /* 2 * cv::contourArea, exact                                     */
+    int32_t bbox[4];           /* x, y, width, height of the component                           */
+    rmcv_rotated_rect ellipse; /* cv::fitEllipseDirect; zero when status == SKIPPED              */
+    int32_t fit_branch;        /* RMCV_FIT_*                                                     */
+    float det0;                /* |det M| of the first direct-fit attempt (diagnostic)           */
+    int32_t blob_index;        /* index into the frame's positive list, or -1                    */
+} rmcv_contour_info;
+
+/* Per-frame counts and offsets into the dense result arrays of a batch.  32 bytes. */
+typedef struct rmcv_frame_info {
+    int32_t n_contours, n_positive, n_negative, n_armours;
+    int32_t contour_offset, blob_offset, armour_offset;
+    int32_t flags; /* RMCV_FRAME_* */
+} rmcv_frame_info;
+
+/* Parameters of the path; defaults = the literals at executable/main.cpp:172-176. */
+typedef struct rmcv_params {
+    int32_t target;      /* camp passed to extract_color / enemy passed to the filters           */
+    int32_t lower_bound; /* inRange lower bound                                                  */
+    float tilt_max;
+    float ratio_min, ratio_max;
+    double area_min, area_max;
+    float angle_difference_max;
+    float shear_max;
+    float lenght_ratio_max; /* sic (include/objdetect.h:68); acts as a minimum, SURVEY B.2        */
+} rmcv_params;
+
+typedef struct rmcv_config {
+    int32_t device;                /* CUDA ordinal                                               */
+    int32_t max_width, max_height; /* largest frame this ctx will see                            */
+    int32_t max_batch;             /* largest batch of one detect call                           */
+    int32_t chunk_frames;          /* frames per internal pipeline step; 0 = default             */
+    int32_t max_runs_per_frame;    /* 0 = default max(65536, W*H/64)                             */
+    int32_t max_blobs_per_frame;   /* components per frame; 0 = default 1024                     */
+    int32_t max_armours_per_frame; /* 0 = default 2048                                           */
+    int32_t flags;                 /* reserved, 0                                                */
+    void* stream;                  /* cudaStream_t for slot 0, or NULL for ctx-owned streams     */
+} rmcv_config;
+
+/* View of the results of the last detect call.  Pointers are ctx-owned pinned host memory, valid
+ * until the next detect call on the ctx.  Dense arrays are indexed through frames[f].*_offset. */
+typedef struct rmcv_results {
+    int32_t batch;
+    int32_t total_contours, total_blobs, total_armours;
+    const rmcv_frame_info* frames;
+    const rmcv_contour_info* contours;
+    const rmcv_lightblob* blobs;
+    const rmcv_armour* armours;
+} rmcv_results;
+
+typedef struct rmcv_ctx rmcv_ctx;
+
+/* ---- lifetime ----------------------------------------------------------------------------- */
+int rmcv_abi_version(void);
+const char* rmcv_status_string(int status);
+void rmcv_default_params(rmcv_params* p);                 /* main.cpp:172-176 literals */
+void rmcv_default_config(rmcv_config* c);
+int rmcv_device_count(int* count);
+int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out);
+int rmcv_ctx_destroy(rmcv_ctx* ctx);
+const char* rmcv_last_error(const rmcv_ctx* ctx);          /* text of the last failure on this ctx */
+
+/* ---- memory + stream helpers (so C / ctypes hosts need no CUDA toolkit) ---------------------- */
+int rmcv_device_alloc(rmcv_ctx* ctx, size_t bytes, void** dptr);
+int rmcv_device_free(rmcv_ctx* ctx, void* dptr);
+int rmcv_host_alloc(rmcv_ctx* ctx, size_t bytes, void** hptr);   /* pinned */
+int rmcv_host_free(rmcv_ctx* ctx, void* hptr);
+int rmcv_memcpy_h2d(rmcv_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on slot 0 */
+int rmcv_memcpy_d2h(rmcv_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on slot 0 */
+int rmcv_memset_d(rmcv_ctx* ctx, void* dst, int value, size_t bytes);         /* async on slot 0 */
+int rmcv_sync(rmcv_ctx* ctx);                                                 /* all ctx streams */
+void* rmcv_stream(rmcv_ctx* ctx);                                             /* slot-0 cudaStream_t */
+
+/* ---- a1: pixel stage of rm::extract_color (src/imgproc.cpp:52-69) --------------------------- */
+/* BGR interleaved u8 frames -> binary mask {0,255}.  Device pointers, async.
+ * frame f starts at d_bgr + f*frame_stride; rows are `pitch` bytes apart (cv::Mat::step).
+ * d_mask may be NULL when only the bit-packed mask (kept inside the ctx) is wanted. */
+int rmcv_extract_color_batch(rmcv_ctx* ctx, const uint8_t* d_bgr, size_t pitch, size_t frame_stride,
+                             int width, int height, int batch, int target, int lower_bound,
+                             uint8_t* d_mask, size_t mask_pitch, size_t mask_frame_stride);
+
+/* a0+a1: 8-bit Bayer mosaic -> (bilinear B,R) -> same pixel stage.  Stands in for
+ * DxRaw8toRGB24(RAW2RGB_NEIGHBOUR) of hardware/src/daheng.cpp:143-148 followed by extract_color. */
+int rmcv_bayer_extract_color_batch(rmcv_ctx* ctx, const uint8_t* d_raw, size_t pitch, size_t frame_stride,
+                                   int width, int height, int batch, int bayer_layout,
+                                   int target, int lower_bound,
+                                   uint8_t* d_mask, size_t mask_pitch, size_t mask_frame_stride);
+
+/* ---- a1..a5: the whole path, frames resident on the device ---------------------------------- */
+/* Async.  Results are read with rmcv_fetch_results().  d_mask may be NULL. */
+int rmcv_detect_batch(rmcv_ctx* ctx, const uint8_t* d_bgr, size_t pitch, size_t frame_stride,
+                      int width, int height, int batch, const rmcv_params* params,
+                      uint8_t* d_mask, size_t mask_pitch, size_t mask_frame_stride);
+
+int rmcv_bayer_detect_batch(rmcv_ctx* ctx, const uint8_t* d_raw, size_t pitch, size_t frame_stride,
+                            int width, int height, int batch, int bayer_layout, const rmcv_params* params,
+                            uint8_t* d_mask, size_t mask_pitch, size_t mask_frame_stride);
+
+/* The whole path from HOST frames (what a cv::Mat caller has): host->device copies, kernels and
+ * result read-back are pipelined chunk by chunk on the ctx's streams.  h_mask may be NULL.
+ * Synchronous: results are ready on return. */
+int rmcv_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, size_t frame_stride,
+                           int width, int height, int batch, const rmcv_params* params,
+                           uint8_t* h_mask, size_t mask_pitch, size_t mask_frame_stride,
+                           rmcv_results* out);
+
+/* Waits for the last detect call and exposes its results. */
+int rmcv_fetch_results(rmcv_ctx* ctx, rmcv_results* out);
+
+/* Ordered contour of external contour `contour_index` of frame `frame` of the last detect call
+ * (Suzuki border following, identical point sequence to cv::findContours).  xy receives up to
+ * `cap` (x,y) pairs; *n_points receives the full length.  Host pointer, synchronous. */
+int rmcv_get_contour(rmcv_ctx* ctx, int frame, int contour_index, int32_t* xy, int cap, int* n_points);
+
+/* int32 label map of frame `frame` of the last detect call: index of the external contour that
+ * owns each pixel, -1 for background and nested components.  Host pointer, synchronous. */
+int rmcv_get_label_map(rmcv_ctx* ctx, int frame, int32_t* labels, size_t pitch_elems);
+
+/* Bit-packed mask (1 bit per pixel, LSB = lowest x, rows padded to 32-pixel words) of frame
+ * `frame` of the last extract/detect call.  Host pointer, synchronous. */
+int rmcv_get_bitmask(rmcv_ctx* ctx, int frame, uint32_t* words, int words_per_row);
+
+/* ---- a2/a3 standalone: rm::filter_lightblobs on caller-supplied contours --------------------- */
+/* xy = concatenated (x,y) int32 pairs, offsets[n_contours+1] in points.  Host pointers,
+ * synchronous.  infos[n_contours] receives the verdicts in input order; blobs receives the
+ * positives in input order (up to blob_cap). */
+int rmcv_filter_lightblobs(rmcv_ctx* ctx, const int32_t* xy, const int32_t* offsets, int n_contours,
+                           const rmcv_params* params, rmcv_contour_info* infos,
+                           rmcv_lightblob* blobs, int blob_cap, int* n_blobs);
+
+/* ---- a4/a5 standalone: rm::filter_armours on caller-supplied light blobs ---------------------- */
+int rmcv_filter_armours(rmcv_ctx* ctx, const rmcv_lightblob* blobs, int n_blobs, const rmcv_params* params,
+                        rmcv_armour* armours, int armour_cap, int* n_armours);
+
+/* a3 standalone: rm::lightblob ctor from a RotatedRect (src/core.cpp:9-19) */
+int rmcv_make_lightblobs(rmcv_ctx* ctx, const rmcv_rotated_rect* boxes, int n, int target, rmcv_lightblob* out);
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+/* CUDA-event timing of the stages of detect/extract calls (on the stream that runs them). */
+enum {
+    RMCV_STAGE_PIXEL = 0,   /* fused diff/threshold/close kernel                                   */
+    RMCV_STAGE_RUNS = 1,    /* run extraction                                                     */
+    RMCV_STAGE_LABEL = 2,   /* union-find labelling (foreground + background gaps)                */
+    RMCV_STAGE_BLOB = 3,    /* per-component contour statistics + ellipse fit + gates             */
+    RMCV_STAGE_ARMOUR = 4,  /* ordering, pair gates, armour geometry, result write-out            */
+    RMCV_STAGE_COUNT = 5
+};
+int rmcv_profile_enable(rmcv_ctx* ctx, int on);
+/* accumulated milliseconds and launch counts per stage since the last reset */
+int rmcv_profile_read(rmcv_ctx* ctx, double ms[RMCV_STAGE_COUNT], int64_t launches[RMCV_STAGE_COUNT], int reset);
+/* number of kernels this library launched on the ctx since creation */
+int64_t rmcv_kernel_launches(const rmcv_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMCV_B200_H */

@@ -1,0 +1,416 @@
+"""Host-side mirror of the reference interface over the C ABI (include/rmcv_b200.h).
+
+The reference's API for this path is three free functions (include/imgproc.h:29, include/objdetect.h:47-49,
+70-71) returning the records of include/core.h:89-130.  This module binds librmcv_b200.so with ctypes and
+offers
+
+  * `Context` — one per host thread and GPU; batched device-resident calls (`detect_batch`,
+    `extract_color_batch`, ...) and the host-buffer end-to-end call (`detect_batch_host`);
+  * `extract_color`, `filter_lightblobs`, `filter_armours` — single-frame functions with the reference's
+    names, argument order and meaning, returning numpy/cv2-shaped values so the parity tests read like the
+    reference's call site at executable/main.cpp:172-176.
+
+There is no CPU fallback: if the CUDA library is missing or no device is present every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _abi as A
+
+_LIB_NAME = "librmcv_b200.so"
+_lib = None
+
+
+class RmcvError(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str = ""):
+        self.status = status
+        super().__init__(f"{where}: status {status} ({_status_string(status)}) {detail}".strip())
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+
+def load_library():
+    """Load librmcv_b200.so (built by __graft_entry__.build()).  Raises if it is missing: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found - run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+    lib = C.CDLL(path)
+    for name, (res, args) in A.PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.rmcv_abi_version() != A.ABI_VERSION:
+        raise RuntimeError("librmcv_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _status_string(s: int) -> str:
+    try:
+        return load_library().rmcv_status_string(s).decode()
+    except Exception:
+        return "?"
+
+
+def default_params(**over) -> A.Params:
+    p = A.Params()
+    load_library().rmcv_default_params(C.byref(p))
+    for k, v in over.items():
+        if k == "ratio_range":
+            p.ratio_min, p.ratio_max = v
+        elif k == "area_range":
+            p.area_min, p.area_max = v
+        else:
+            setattr(p, k, v)
+    return p
+
+
+# --------------------------------------------------------------------------------------------- records
+@dataclass
+class LightBlob:  # rm::lightblob, include/core.h:89-99
+    angle: float
+    target: int
+    center: Tuple[float, float]
+    vertices: np.ndarray  # 4x2 float32
+    size: Tuple[float, float]
+
+    @staticmethod
+    def from_c(b: A.LightBlob) -> "LightBlob":
+        v = np.array([[b.vertices[i][0], b.vertices[i][1]] for i in range(4)], np.float32)
+        return LightBlob(float(b.angle), int(b.target), (float(b.center[0]), float(b.center[1])), v,
+                         (float(b.size[0]), float(b.size[1])))
+
+    def to_c(self) -> A.LightBlob:
+        b = A.LightBlob()
+        b.angle, b.target = self.angle, self.target
+        b.center[0], b.center[1] = self.center
+        for i in range(4):
+            b.vertices[i][0], b.vertices[i][1] = float(self.vertices[i][0]), float(self.vertices[i][1])
+        b.size[0], b.size[1] = self.size
+        return b
+
+
+@dataclass
+class Armour:  # rm::armour public geometry, include/core.h:110-112
+    icon: np.ndarray
+    vertices: np.ndarray
+    bounding_box: Tuple[float, float, float, float]
+    i: int
+    j: int
+    gates: Tuple[float, ...]
+
+    @staticmethod
+    def from_c(a: A.Armour) -> "Armour":
+        ic = np.array([[a.icon[k][0], a.icon[k][1]] for k in range(4)], np.float32)
+        ve = np.array([[a.vertices[k][0], a.vertices[k][1]] for k in range(4)], np.float32)
+        return Armour(ic, ve, tuple(float(x) for x in a.bounding_box), int(a.i), int(a.j), tuple(float(g) for g in a.gates))
+
+
+@dataclass
+class ContourInfo:
+    first: Tuple[int, int]
+    n_points: int
+    status: int
+    area2: int
+    bbox: Tuple[int, int, int, int]
+    ellipse: Tuple[float, float, float, float, float]
+    fit_branch: int
+    det0: float
+    blob_index: int
+
+    @staticmethod
+    def from_c(c: A.ContourInfo) -> "ContourInfo":
+        e = c.ellipse
+        return ContourInfo((int(c.first_x), int(c.first_y)), int(c.n_points), int(c.status), int(c.area2),
+                           tuple(int(v) for v in c.bbox), (float(e.cx), float(e.cy), float(e.w), float(e.h), float(e.angle)),
+                           int(c.fit_branch), float(c.det0), int(c.blob_index))
+
+
+@dataclass
+class FrameDetections:
+    contours: List[ContourInfo]
+    positive: List[LightBlob]
+    armours: List[Armour]
+    n_negative: int
+    flags: int
+
+
+# --------------------------------------------------------------------------------------------- context
+class DeviceBuffer:
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        p = C.c_void_p()
+        ctx._check(ctx.lib.rmcv_device_alloc(ctx.h, self.nbytes, C.byref(p)), "rmcv_device_alloc")
+        self.ptr = p.value
+
+    def upload(self, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        self.ctx._check(self.ctx.lib.rmcv_memcpy_h2d(self.ctx.h, self.ptr, arr.ctypes.data, arr.nbytes), "rmcv_memcpy_h2d")
+        self.ctx.sync()
+
+    def download(self, shape, dtype=np.uint8) -> np.ndarray:
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        self.ctx._check(self.ctx.lib.rmcv_memcpy_d2h(self.ctx.h, out.ctypes.data, self.ptr, out.nbytes), "rmcv_memcpy_d2h")
+        self.ctx.sync()
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.ctx.lib.rmcv_device_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+
+class PinnedArray:
+    """numpy view over pinned host memory owned by the ctx."""
+
+    def __init__(self, ctx: "Context", shape, dtype=np.uint8):
+        self.ctx = ctx
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        ctx._check(ctx.lib.rmcv_host_alloc(ctx.h, n, C.byref(p)), "rmcv_host_alloc")
+        self.ptr = p.value
+        buf = (C.c_uint8 * n).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.ctx.lib.rmcv_host_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """rmcv_ctx wrapper.  One per host thread and GPU."""
+
+    def __init__(self, max_width=1280, max_height=1024, max_batch=64, device=0, chunk_frames=0, max_runs_per_frame=0,
+                 max_blobs_per_frame=0, max_armours_per_frame=0, stream: Optional[int] = None):
+        self.lib = load_library()
+        cfg = A.Config()
+        self.lib.rmcv_default_config(C.byref(cfg))
+        cfg.device, cfg.max_width, cfg.max_height, cfg.max_batch = device, max_width, max_height, max_batch
+        cfg.chunk_frames, cfg.max_runs_per_frame = chunk_frames, max_runs_per_frame
+        cfg.max_blobs_per_frame, cfg.max_armours_per_frame = max_blobs_per_frame, max_armours_per_frame
+        cfg.stream = stream
+        h = C.c_void_p()
+        rc = self.lib.rmcv_ctx_create(C.byref(cfg), C.byref(h))
+        if rc != A.RMCV_OK:
+            raise RmcvError(rc, "rmcv_ctx_create", "(is a CUDA device present? this library has no CPU path)")
+        self.h = h
+        self.cfg = cfg
+
+    # -- plumbing
+    def _check(self, rc: int, where: str):
+        if rc != A.RMCV_OK:
+            raise RmcvError(rc, where, self.lib.rmcv_last_error(self.h).decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rmcv_ctx_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._check(self.lib.rmcv_sync(self.h), "rmcv_sync")
+
+    def stream(self) -> int:
+        return int(self.lib.rmcv_stream(self.h) or 0)
+
+    def device_buffer(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def pinned(self, shape, dtype=np.uint8) -> PinnedArray:
+        return PinnedArray(self, shape, dtype)
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.rmcv_kernel_launches(self.h))
+
+    def profile(self, on=True):
+        self._check(self.lib.rmcv_profile_enable(self.h, 1 if on else 0), "rmcv_profile_enable")
+
+    def profile_read(self, reset=True):
+        ms = (C.c_double * 5)()
+        ln = (C.c_int64 * 5)()
+        self._check(self.lib.rmcv_profile_read(self.h, ms, ln, 1 if reset else 0), "rmcv_profile_read")
+        return {n: (ms[i], int(ln[i])) for i, n in enumerate(A.STAGE_NAMES)}
+
+    # -- device-resident batched calls (pointers are raw device addresses)
+    def extract_color_batch(self, d_bgr: int, width: int, height: int, batch: int, target: int, lower_bound: int,
+                            d_mask: Optional[int], pitch: Optional[int] = None, frame_stride: Optional[int] = None,
+                            mask_pitch: Optional[int] = None, mask_frame_stride: Optional[int] = None):
+        pitch = pitch or width * 3
+        frame_stride = frame_stride or pitch * height
+        mask_pitch = mask_pitch or width
+        mask_frame_stride = mask_frame_stride or mask_pitch * height
+        self._check(self.lib.rmcv_extract_color_batch(self.h, d_bgr, pitch, frame_stride, width, height, batch, target,
+                                                      lower_bound, d_mask, mask_pitch, mask_frame_stride),
+                    "rmcv_extract_color_batch")
+
+    def bayer_extract_color_batch(self, d_raw: int, width: int, height: int, batch: int, layout: int, target: int,
+                                  lower_bound: int, d_mask: Optional[int], pitch: Optional[int] = None,
+                                  frame_stride: Optional[int] = None):
+        pitch = pitch or width
+        frame_stride = frame_stride or pitch * height
+        self._check(self.lib.rmcv_bayer_extract_color_batch(self.h, d_raw, pitch, frame_stride, width, height, batch, layout,
+                                                            target, lower_bound, d_mask, width, width * height),
+                    "rmcv_bayer_extract_color_batch")
+
+    def detect_batch(self, d_bgr: int, width: int, height: int, batch: int, params: A.Params, d_mask: Optional[int] = None,
+                     pitch: Optional[int] = None, frame_stride: Optional[int] = None):
+        pitch = pitch or width * 3
+        frame_stride = frame_stride or pitch * height
+        self._check(self.lib.rmcv_detect_batch(self.h, d_bgr, pitch, frame_stride, width, height, batch, C.byref(params),
+                                               d_mask, width, width * height), "rmcv_detect_batch")
+
+    def bayer_detect_batch(self, d_raw: int, width: int, height: int, batch: int, layout: int, params: A.Params,
+                           d_mask: Optional[int] = None):
+        self._check(self.lib.rmcv_bayer_detect_batch(self.h, d_raw, width, width * height, width, height, batch, layout,
+                                                     C.byref(params), d_mask, width, width * height), "rmcv_bayer_detect_batch")
+
+    def fetch_results(self, allow_overflow=False) -> A.Results:
+        res = A.Results()
+        rc = self.lib.rmcv_fetch_results(self.h, C.byref(res))
+        if rc != A.RMCV_OK and not (allow_overflow and rc == A.RMCV_ERR_CAPACITY):
+            self._check(rc, "rmcv_fetch_results")
+        return res
+
+    def detect_batch_host(self, frames: np.ndarray, params: A.Params, masks: Optional[np.ndarray] = None) -> A.Results:
+        """frames: B×H×W×3 uint8 host array (pinned for full PCIe speed).  masks: optional B×H×W output."""
+        assert frames.dtype == np.uint8 and frames.ndim == 4 and frames.shape[3] == 3 and frames.flags.c_contiguous
+        B, H, W, _ = frames.shape
+        res = A.Results()
+        mptr = masks.ctypes.data if masks is not None else None
+        self._check(self.lib.rmcv_detect_batch_host(self.h, frames.ctypes.data, W * 3, W * 3 * H, W, H, B, C.byref(params),
+                                                    mptr, W, W * H, C.byref(res)), "rmcv_detect_batch_host")
+        return res
+
+    # -- result helpers
+    @staticmethod
+    def frame_detections(res: A.Results, f: int) -> FrameDetections:
+        fi = res.frames[f]
+        cs = [ContourInfo.from_c(res.contours[fi.contour_offset + k]) for k in range(fi.n_contours)]
+        bs = [LightBlob.from_c(res.blobs[fi.blob_offset + k]) for k in range(fi.n_positive)]
+        ar = [Armour.from_c(res.armours[fi.armour_offset + k]) for k in range(fi.n_armours)]
+        return FrameDetections(cs, bs, ar, int(fi.n_negative), int(fi.flags))
+
+    def get_contour(self, frame: int, index: int, cap: int = 1 << 16) -> np.ndarray:
+        n = C.c_int()
+        buf = np.empty((cap, 2), np.int32)
+        self._check(self.lib.rmcv_get_contour(self.h, frame, index, buf.ctypes.data, cap, C.byref(n)), "rmcv_get_contour")
+        if n.value > cap:
+            return self.get_contour(frame, index, n.value)
+        return buf[:n.value].copy()
+
+    def get_label_map(self, frame: int, width: int, height: int) -> np.ndarray:
+        out = np.empty((height, width), np.int32)
+        self._check(self.lib.rmcv_get_label_map(self.h, frame, out.ctypes.data, width), "rmcv_get_label_map")
+        return out
+
+    def get_bitmask(self, frame: int, width: int, height: int) -> np.ndarray:
+        wb = (width + 31) // 32
+        out = np.empty((height, wb), np.uint32)
+        self._check(self.lib.rmcv_get_bitmask(self.h, frame, out.ctypes.data, wb), "rmcv_get_bitmask")
+        return out
+
+    # -- standalone a2..a5
+    def filter_lightblobs_raw(self, contours: Sequence[np.ndarray], params: A.Params):
+        n = len(contours)
+        offs = np.zeros(n + 1, np.int32)
+        for i, c in enumerate(contours):
+            offs[i + 1] = offs[i] + len(c)
+        xy = (np.concatenate([np.asarray(c, np.int32).reshape(-1, 2) for c in contours]) if n and offs[-1] > 0
+              else np.zeros((0, 2), np.int32))
+        xy = np.ascontiguousarray(xy, np.int32)
+        infos = (A.ContourInfo * max(n, 1))()
+        blobs = (A.LightBlob * max(n, 1))()
+        nb = C.c_int()
+        self._check(self.lib.rmcv_filter_lightblobs(self.h, xy.ctypes.data if xy.size else None, offs.ctypes.data, n,
+                                                    C.byref(params), infos, blobs, max(n, 1), C.byref(nb)),
+                    "rmcv_filter_lightblobs")
+        return [ContourInfo.from_c(infos[i]) for i in range(n)], [LightBlob.from_c(blobs[i]) for i in range(nb.value)]
+
+    def filter_armours_raw(self, blobs: Sequence[LightBlob], params: A.Params, cap: int = 4096) -> List[Armour]:
+        n = len(blobs)
+        arr = (A.LightBlob * max(n, 1))(*[b.to_c() for b in blobs])
+        out = (A.Armour * cap)()
+        na = C.c_int()
+        self._check(self.lib.rmcv_filter_armours(self.h, arr, n, C.byref(params), out, cap, C.byref(na)), "rmcv_filter_armours")
+        return [Armour.from_c(out[i]) for i in range(na.value)]
+
+    def make_lightblobs(self, boxes: Sequence[Tuple[float, float, float, float, float]], target: int) -> List[LightBlob]:
+        n = len(boxes)
+        arr = (A.RotatedRect * max(n, 1))(*[A.RotatedRect(*b) for b in boxes])
+        out = (A.LightBlob * max(n, 1))()
+        self._check(self.lib.rmcv_make_lightblobs(self.h, arr, n, target, out), "rmcv_make_lightblobs")
+        return [LightBlob.from_c(out[i]) for i in range(n)]
+
+
+# --------------------------------------------------------------------------------------------- rm:: mirror
+_default_ctx: Optional[Context] = None
+
+
+def _ctx_for(width: int, height: int) -> Context:
+    global _default_ctx
+    c = _default_ctx
+    if c is None or c.cfg.max_width < width or c.cfg.max_height < height:
+        if c is not None:
+            c.close()
+        _default_ctx = c = Context(max_width=max(width, 1280), max_height=max(height, 1024), max_batch=1)
+    return c
+
+
+def extract_color(image: np.ndarray, target: int, lower_bound: int):
+    """rm::extract_color (include/imgproc.h:29) -> (contours, binary).  contours: list of N×2 int32 arrays in
+    cv::findContours order; binary: H×W uint8 {0,255}."""
+    assert image.dtype == np.uint8 and image.ndim == 3 and image.shape[2] == 3
+    image = np.ascontiguousarray(image)
+    H, W, _ = image.shape
+    ctx = _ctx_for(W, H)
+    p = default_params(target=target, lower_bound=lower_bound, area_range=(0.0, 1e300))
+    mask = np.empty((1, H, W), np.uint8)
+    res = ctx.detect_batch_host(image[None], p, mask)
+    n = res.frames[0].n_contours
+    contours = [ctx.get_contour(0, k) for k in range(n)]
+    return contours, mask[0]
+
+
+def filter_lightblobs(contours, tilt_max, ratio_range, area_range, enemy):
+    """rm::filter_lightblobs (include/objdetect.h:47-49) -> (positive, negative)."""
+    if len(contours) == 0:
+        return [], []
+    ctx = _ctx_for(1, 1) if _default_ctx is None else _default_ctx
+    p = default_params(target=enemy, tilt_max=tilt_max, ratio_range=ratio_range, area_range=area_range)
+    infos, blobs = ctx.filter_lightblobs_raw(contours, p)
+    negative = [c for c, i in zip(contours, infos) if i.status == A.CONTOUR_NEGATIVE]
+    return blobs, negative
+
+
+def filter_armours(lightblobs, angle_difference_max, shear_max, lenght_ratio_max, enemy):
+    """rm::filter_armours (include/objdetect.h:70-71)."""
+    ctx = _ctx_for(1, 1) if _default_ctx is None else _default_ctx
+    p = default_params(target=enemy, angle_difference_max=angle_difference_max, shear_max=shear_max,
+                       lenght_ratio_max=lenght_ratio_max)
+    return ctx.filter_armours_raw(lightblobs, p)

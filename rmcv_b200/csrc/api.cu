@@ -1,0 +1,696 @@
+// C ABI of rmcv_b200 (include/rmcv_b200.h): context, memory helpers, the batched entry points and the
+// chunked two-slot pipeline that overlaps copies and kernels.  No CPU fallback: every compute entry point
+// launches the CUDA kernels in pixel.cu / ccl.cu / blob.cu / armour.cu or fails with an error code.
+#include <stdlib.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace rmcv;
+
+namespace {
+
+struct ProfSet {
+    cudaEvent_t ev[RMCV_STAGE_COUNT + 1];
+    bool rec;
+};
+
+struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
+    std::vector<ProfSet> prof;
+    size_t prof_used = 0;
+    std::vector<void*> dev_allocs, host_allocs;
+    // scratch for the standalone entry points
+    void* tmp_dev = nullptr; size_t tmp_dev_bytes = 0;
+    void* tmp_host = nullptr; size_t tmp_host_bytes = 0;
+    int last_nchunks = 0;
+    int last_kind = 0;  // 0 none, 1 extract, 2 detect
+};
+
+CtxExtra* extra(rmcv_ctx* c) { return static_cast<CtxExtra*>(c->extra); }
+
+template <class T>
+cudaError_t dalloc(T** p, size_t count) { return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)); }
+
+int ensure_tmp(rmcv_ctx* ctx, size_t dev_bytes, size_t host_bytes) {
+    CtxExtra* ex = extra(ctx);
+    if (dev_bytes > ex->tmp_dev_bytes) {
+        if (ex->tmp_dev) cudaFree(ex->tmp_dev);
+        ex->tmp_dev = nullptr; ex->tmp_dev_bytes = 0;
+        RMCV_CUDA(ctx, cudaMalloc(&ex->tmp_dev, dev_bytes));
+        ex->tmp_dev_bytes = dev_bytes;
+    }
+    if (host_bytes > ex->tmp_host_bytes) {
+        if (ex->tmp_host) cudaFreeHost(ex->tmp_host);
+        ex->tmp_host = nullptr; ex->tmp_host_bytes = 0;
+        RMCV_CUDA(ctx, cudaMallocHost(&ex->tmp_host, host_bytes));
+        ex->tmp_host_bytes = host_bytes;
+    }
+    return RMCV_OK;
+}
+
+int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
+    const Geometry& g = ctx->cap;
+    const size_t CF = ctx->CF, H = g.H, WB = g.WB, R = g.R, C = g.C, A = g.A;
+    memset(&sb, 0, sizeof(sb));
+    RMCV_CUDA(ctx, dalloc(&sb.bits, CF * H * WB));
+    RMCV_CUDA(ctx, dalloc(&sb.hole, CF * H * WB));
+    RMCV_CUDA(ctx, cudaMemset(sb.hole, 0, CF * H * WB * sizeof(uint32_t)));
+    RMCV_CUDA(ctx, dalloc(&sb.row_off, CF * (H + 1)));
+    RMCV_CUDA(ctx, dalloc(&sb.run_x, CF * R));
+    RMCV_CUDA(ctx, dalloc(&sb.run_y, CF * R));
+    RMCV_CUDA(ctx, dalloc(&sb.parent, CF * R));
+    RMCV_CUDA(ctx, dalloc(&sb.gparent, CF * (R + 1)));
+    RMCV_CUDA(ctx, dalloc(&sb.rstat, CF * R));
+    RMCV_CUDA(ctx, dalloc(&sb.comp_root, CF * C));
+    RMCV_CUDA(ctx, dalloc(&sb.comps, CF * C));
+    RMCV_CUDA(ctx, dalloc(&sb.counters, CF));
+    RMCV_CUDA(ctx, cudaMemset(sb.counters, 0, CF * sizeof(FrameCounters)));
+    RMCV_CUDA(ctx, dalloc(&sb.s_contours, CF * C));
+    RMCV_CUDA(ctx, dalloc(&sb.s_blobs, CF * C));
+    RMCV_CUDA(ctx, dalloc(&sb.s_armours, CF * A));
+    if (first && ctx->cfg.stream) {
+        sb.stream = reinterpret_cast<cudaStream_t>(ctx->cfg.stream);
+        sb.own_stream = false;
+    } else {
+        RMCV_CUDA(ctx, cudaStreamCreateWithFlags(&sb.stream, cudaStreamNonBlocking));
+        sb.own_stream = true;
+    }
+    RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.done, cudaEventDisableTiming));
+    return RMCV_OK;
+}
+
+void free_slot(SlotBuffers& sb) {
+    cudaFree(sb.bits); cudaFree(sb.hole); cudaFree(sb.row_off); cudaFree(sb.run_x); cudaFree(sb.run_y);
+    cudaFree(sb.parent); cudaFree(sb.gparent); cudaFree(sb.rstat); cudaFree(sb.comp_root); cudaFree(sb.comps);
+    cudaFree(sb.counters); cudaFree(sb.s_contours); cudaFree(sb.s_blobs); cudaFree(sb.s_armours);
+    if (sb.frames) cudaFree(sb.frames);
+    if (sb.masks) cudaFree(sb.masks);
+    if (sb.own_stream && sb.stream) cudaStreamDestroy(sb.stream);
+    if (sb.done) cudaEventDestroy(sb.done);
+    memset(&sb, 0, sizeof(sb));
+}
+
+int check_geometry(rmcv_ctx* ctx, int width, int height, int batch) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    if (width <= 0 || height <= 0 || batch <= 0) return set_err(ctx, RMCV_ERR_INVALID_ARG, "width, height and batch must be positive");
+    if (width > ctx->cfg.max_width || height > ctx->cfg.max_height || batch > ctx->cfg.max_batch)
+        return set_err(ctx, RMCV_ERR_INVALID_ARG, "frame size or batch exceeds the ctx maxima");
+    if (width > 65535) return set_err(ctx, RMCV_ERR_INVALID_ARG, "width above 65535 is not supported");
+    return RMCV_OK;
+}
+
+Geometry call_geometry(const rmcv_ctx* ctx, int W, int H) {
+    Geometry g = ctx->cap;
+    g.W = W; g.H = H; g.WB = (W + 31) / 32;
+    return g;
+}
+
+ProfSet* prof_begin(rmcv_ctx* ctx, cudaStream_t st) {
+    if (!ctx->profiling) return nullptr;
+    CtxExtra* ex = extra(ctx);
+    if (ex->prof_used == ex->prof.size()) {
+        ProfSet ps;
+        for (int i = 0; i <= RMCV_STAGE_COUNT; ++i) cudaEventCreate(&ps.ev[i]);
+        ps.rec = false;
+        ex->prof.push_back(ps);
+    }
+    ProfSet* ps = &ex->prof[ex->prof_used++];
+    ps->rec = true;
+    cudaEventRecord(ps->ev[0], st);
+    return ps;
+}
+void prof_mark(ProfSet* ps, int stage, cudaStream_t st) {
+    if (ps) cudaEventRecord(ps->ev[stage + 1], st);
+}
+void prof_collect(rmcv_ctx* ctx) {  // after a sync
+    CtxExtra* ex = extra(ctx);
+    for (size_t i = 0; i < ex->prof_used; ++i) {
+        ProfSet& ps = ex->prof[i];
+        if (!ps.rec) continue;
+        for (int s = 0; s < RMCV_STAGE_COUNT; ++s) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ps.ev[s], ps.ev[s + 1]) == cudaSuccess) ctx->prof_ms[s] += ms;
+        }
+        ps.rec = false;
+    }
+    ex->prof_used = 0;
+    cudaGetLastError();
+}
+
+// Enqueue all stages for `frames` frames whose pixels are at `src` on slot `sb`.
+int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pitch, size_t frame_stride, int W, int H,
+                  int frames, int frame_base, int bayer_layout, const rmcv_params& prm, uint8_t* mask, size_t mask_pitch,
+                  size_t mask_frame_stride, bool full) {
+    cudaStream_t st = sb.stream;
+    ProfSet* ps = prof_begin(ctx, st);
+    int64_t l0 = ctx->kernel_launches;
+    PixelLaunch pl;
+    pl.src = src; pl.pitch = pitch; pl.frame_stride = frame_stride;
+    pl.mask = mask; pl.mask_pitch = mask_pitch; pl.mask_frame_stride = mask_frame_stride;
+    pl.bits = sb.bits; pl.W = W; pl.H = H; pl.batch = frames;
+    pl.target = prm.target; pl.lower_bound = prm.lower_bound; pl.bayer_layout = bayer_layout;
+    RMCV_CUDA(ctx, launch_pixel_stage(pl, ctx->sm_count, st, &ctx->kernel_launches));
+    prof_mark(ps, RMCV_STAGE_PIXEL, st);
+    ctx->prof_launches[RMCV_STAGE_PIXEL] += ctx->kernel_launches - l0; l0 = ctx->kernel_launches;
+    if (!full) {
+        for (int s = 1; s < RMCV_STAGE_COUNT; ++s) prof_mark(ps, s, st);
+        return RMCV_OK;
+    }
+    LabelLaunch ll;
+    ll.g = call_geometry(ctx, W, H); ll.frames = frames; ll.sb = &sb;
+    RMCV_CUDA(ctx, launch_runs(ll, st, &ctx->kernel_launches));
+    prof_mark(ps, RMCV_STAGE_RUNS, st);
+    ctx->prof_launches[RMCV_STAGE_RUNS] += ctx->kernel_launches - l0; l0 = ctx->kernel_launches;
+    RMCV_CUDA(ctx, launch_label(ll, st, &ctx->kernel_launches));
+    prof_mark(ps, RMCV_STAGE_LABEL, st);
+    ctx->prof_launches[RMCV_STAGE_LABEL] += ctx->kernel_launches - l0; l0 = ctx->kernel_launches;
+    RMCV_CUDA(ctx, launch_blobs(ll, prm, st, &ctx->kernel_launches));
+    RMCV_CUDA(ctx, launch_unpaint(ll, st, &ctx->kernel_launches));
+    prof_mark(ps, RMCV_STAGE_BLOB, st);
+    ctx->prof_launches[RMCV_STAGE_BLOB] += ctx->kernel_launches - l0; l0 = ctx->kernel_launches;
+    OutputLaunch ol;
+    ol.g = ll.g; ol.frames = frames; ol.sb = &sb; ol.frame_base = frame_base;
+    ol.o_frames = ctx->h_frames; ol.o_contours = ctx->h_contours; ol.o_blobs = ctx->h_blobs; ol.o_armours = ctx->h_armours;
+    ol.C_out = ctx->cap.C; ol.A_out = ctx->cap.A;
+    RMCV_CUDA(ctx, launch_armours(ol, prm, st, &ctx->kernel_launches));
+    prof_mark(ps, RMCV_STAGE_ARMOUR, st);
+    ctx->prof_launches[RMCV_STAGE_ARMOUR] += ctx->kernel_launches - l0;
+    return RMCV_OK;
+}
+
+int run_device_batch(rmcv_ctx* ctx, const uint8_t* d_src, size_t pitch, size_t frame_stride, int W, int H, int batch,
+                     int bayer_layout, const rmcv_params& prm, uint8_t* d_mask, size_t mask_pitch, size_t mask_frame_stride,
+                     bool full) {
+    int rc = check_geometry(ctx, W, H, batch);
+    if (rc != RMCV_OK) return rc;
+    if (!d_src) return set_err(ctx, RMCV_ERR_INVALID_ARG, "null frame pointer");
+    const size_t rowbytes = bayer_layout ? (size_t)W : (size_t)W * 3;
+    if (pitch < rowbytes) return set_err(ctx, RMCV_ERR_INVALID_ARG, "pitch smaller than a row");
+    if (d_mask && mask_pitch < (size_t)W) return set_err(ctx, RMCV_ERR_INVALID_ARG, "mask pitch smaller than a row");
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int CF = ctx->CF;
+    int nchunks = 0;
+    for (int f0 = 0; f0 < batch; f0 += CF, ++nchunks) {
+        SlotBuffers& sb = ctx->slot[nchunks & 1];
+        const int frames = batch - f0 < CF ? batch - f0 : CF;
+        rc = enqueue_chunk(ctx, sb, d_src + (size_t)f0 * frame_stride, pitch, frame_stride, W, H, frames, f0, bayer_layout,
+                           prm, d_mask ? d_mask + (size_t)f0 * mask_frame_stride : nullptr, mask_pitch, mask_frame_stride, full);
+        if (rc != RMCV_OK) return rc;
+    }
+    ctx->last_batch = batch; ctx->last_W = W; ctx->last_H = H;
+    ctx->have_results = full;
+    extra(ctx)->last_nchunks = nchunks;
+    extra(ctx)->last_kind = full ? 2 : 1;
+    return RMCV_OK;
+}
+
+int sync_all(rmcv_ctx* ctx) {
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(ctx->slot[0].stream));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(ctx->slot[1].stream));
+    prof_collect(ctx);
+    return RMCV_OK;
+}
+
+int fill_results(rmcv_ctx* ctx, rmcv_results* out) {
+    if (!ctx->have_results) return set_err(ctx, RMCV_ERR_STATE, "no detect call to fetch results from");
+    int flags = 0;
+    long long tc = 0, tb = 0, ta = 0;
+    for (int f = 0; f < ctx->last_batch; ++f) {
+        const rmcv_frame_info& fi = ctx->h_frames[f];
+        flags |= fi.flags; tc += fi.n_contours; tb += fi.n_positive; ta += fi.n_armours;
+    }
+    if (out) {
+        out->batch = ctx->last_batch;
+        out->total_contours = (int32_t)tc; out->total_blobs = (int32_t)tb; out->total_armours = (int32_t)ta;
+        out->frames = ctx->h_frames; out->contours = ctx->h_contours; out->blobs = ctx->h_blobs; out->armours = ctx->h_armours;
+    }
+    if (flags) return set_err(ctx, RMCV_ERR_CAPACITY, "a per-frame capacity overflowed; see rmcv_frame_info.flags");
+    return RMCV_OK;
+}
+
+// slot and local index of frame f of the last call, or null when its scratch has been recycled
+SlotBuffers* resident_slot(rmcv_ctx* ctx, int frame, int* local) {
+    if (frame < 0 || frame >= ctx->last_batch) return nullptr;
+    const int chunk = frame / ctx->CF;
+    if (chunk + 2 < extra(ctx)->last_nchunks) return nullptr;
+    *local = frame - chunk * ctx->CF;
+    return &ctx->slot[chunk & 1];
+}
+
+}  // namespace
+
+// =============================================================================================== ABI
+extern "C" {
+
+int rmcv_abi_version(void) { return RMCV_B200_ABI_VERSION; }
+
+const char* rmcv_status_string(int s) {
+    switch (s) {
+        case RMCV_OK: return "ok";
+        case RMCV_ERR_INVALID_ARG: return "invalid argument";
+        case RMCV_ERR_CUDA: return "CUDA error";
+        case RMCV_ERR_CAPACITY: return "per-frame capacity overflow";
+        case RMCV_ERR_NO_DEVICE: return "no CUDA device";
+        case RMCV_ERR_STATE: return "invalid call order";
+        default: return "unknown status";
+    }
+}
+
+void rmcv_default_params(rmcv_params* p) {  // executable/main.cpp:172-176
+    if (!p) return;
+    p->target = RMCV_CAMP_BLUE; p->lower_bound = 80; p->tilt_max = 70.f;
+    p->ratio_min = 1.5f; p->ratio_max = 80.f; p->area_min = 10.0; p->area_max = 99999.0;
+    p->angle_difference_max = 12.f; p->shear_max = 22.f; p->lenght_ratio_max = 0.4f;
+}
+
+void rmcv_default_config(rmcv_config* c) {
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    c->device = 0; c->max_width = 1280; c->max_height = 1024; c->max_batch = 64;
+}
+
+int rmcv_device_count(int* count) {
+    if (!count) return RMCV_ERR_INVALID_ARG;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    *count = (e == cudaSuccess) ? n : 0;
+    if (e != cudaSuccess) { cudaGetLastError(); return RMCV_ERR_NO_DEVICE; }
+    return RMCV_OK;
+}
+
+int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
+    if (!cfg || !out) return RMCV_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (cfg->max_width <= 0 || cfg->max_height <= 0 || cfg->max_batch <= 0 || cfg->max_width > 65535) return RMCV_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return RMCV_ERR_NO_DEVICE; }
+    if (cfg->device < 0 || cfg->device >= ndev) return RMCV_ERR_INVALID_ARG;
+    rmcv_ctx* ctx = static_cast<rmcv_ctx*>(calloc(1, sizeof(rmcv_ctx)));
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    ctx->cfg = *cfg;
+    ctx->device = cfg->device;
+    ctx->extra = new (std::nothrow) CtxExtra();
+    auto fail = [&](int code) {
+        static thread_local char keep[512];
+        snprintf(keep, sizeof(keep), "%s", ctx->err);
+        fprintf(stderr, "rmcv_ctx_create failed: %s\n", keep);
+        rmcv_ctx_destroy(ctx);
+        return code;
+    };
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "cudaSetDevice failed"); return fail(RMCV_ERR_CUDA); }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "cudaGetDeviceProperties failed"); return fail(RMCV_ERR_CUDA); }
+    ctx->sm_count = prop.multiProcessorCount;
+    Geometry& g = ctx->cap;
+    g.W = cfg->max_width; g.H = cfg->max_height; g.WB = (g.W + 31) / 32;
+    const long long px = (long long)g.W * g.H;
+    long long R = cfg->max_runs_per_frame > 0 ? cfg->max_runs_per_frame : (px / 64 > 65536 ? px / 64 : 65536);
+    if (R > px / 2 + g.H) R = px / 2 + g.H;
+    g.R = (int)R;
+    g.C = cfg->max_blobs_per_frame > 0 ? cfg->max_blobs_per_frame : 512;
+    g.A = cfg->max_armours_per_frame > 0 ? cfg->max_armours_per_frame : 1024;
+    int CF = cfg->chunk_frames;
+    if (CF <= 0) {
+        const long long frame_bytes = px * 3;
+        long long c = (512LL << 20) / frame_bytes;
+        CF = (int)(c < 1 ? 1 : (c > 128 ? 128 : c));
+    }
+    if (CF > cfg->max_batch) CF = cfg->max_batch;
+    ctx->CF = CF;
+    int rc = alloc_slot(ctx, ctx->slot[0], true);
+    if (rc == RMCV_OK) rc = alloc_slot(ctx, ctx->slot[1], false);
+    if (rc != RMCV_OK) return fail(rc);
+    const size_t B = cfg->max_batch;
+    const unsigned hflags = cudaHostAllocMapped | cudaHostAllocPortable;
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_frames), B * sizeof(rmcv_frame_info), hflags);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_contours), B * g.C * sizeof(rmcv_contour_info), hflags);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_blobs), B * g.C * sizeof(rmcv_lightblob), hflags);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_armours), B * g.A * sizeof(rmcv_armour), hflags);
+    if (e != cudaSuccess) {
+        snprintf(ctx->err, sizeof(ctx->err), "pinned result allocation failed: %s", cudaGetErrorString(e));
+        return fail(RMCV_ERR_CUDA);
+    }
+    memset(ctx->h_frames, 0, B * sizeof(rmcv_frame_info));
+    upload_luts();
+    if (cudaDeviceSynchronize() != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "device sync after init failed"); return fail(RMCV_ERR_CUDA); }
+    *out = ctx;
+    return RMCV_OK;
+}
+
+int rmcv_ctx_destroy(rmcv_ctx* ctx) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_slot(ctx->slot[0]);
+    free_slot(ctx->slot[1]);
+    if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
+    if (ctx->h_contours) cudaFreeHost(ctx->h_contours);
+    if (ctx->h_blobs) cudaFreeHost(ctx->h_blobs);
+    if (ctx->h_armours) cudaFreeHost(ctx->h_armours);
+    CtxExtra* ex = extra(ctx);
+    if (ex) {
+        for (auto& ps : ex->prof) for (int i = 0; i <= RMCV_STAGE_COUNT; ++i) cudaEventDestroy(ps.ev[i]);
+        for (void* p : ex->dev_allocs) cudaFree(p);
+        for (void* p : ex->host_allocs) cudaFreeHost(p);
+        if (ex->tmp_dev) cudaFree(ex->tmp_dev);
+        if (ex->tmp_host) cudaFreeHost(ex->tmp_host);
+        delete ex;
+    }
+    cudaGetLastError();
+    free(ctx);
+    return RMCV_OK;
+}
+
+const char* rmcv_last_error(const rmcv_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+
+int rmcv_device_alloc(rmcv_ctx* ctx, size_t bytes, void** dptr) {
+    if (!ctx || !dptr) return RMCV_ERR_INVALID_ARG;
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    RMCV_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 1));
+    extra(ctx)->dev_allocs.push_back(*dptr);
+    return RMCV_OK;
+}
+int rmcv_device_free(rmcv_ctx* ctx, void* dptr) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    auto& v = extra(ctx)->dev_allocs;
+    for (size_t i = 0; i < v.size(); ++i)
+        if (v[i] == dptr) { v.erase(v.begin() + i); break; }
+    RMCV_CUDA(ctx, cudaFree(dptr));
+    return RMCV_OK;
+}
+int rmcv_host_alloc(rmcv_ctx* ctx, size_t bytes, void** hptr) {
+    if (!ctx || !hptr) return RMCV_ERR_INVALID_ARG;
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    RMCV_CUDA(ctx, cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    extra(ctx)->host_allocs.push_back(*hptr);
+    return RMCV_OK;
+}
+int rmcv_host_free(rmcv_ctx* ctx, void* hptr) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    auto& v = extra(ctx)->host_allocs;
+    for (size_t i = 0; i < v.size(); ++i)
+        if (v[i] == hptr) { v.erase(v.begin() + i); break; }
+    RMCV_CUDA(ctx, cudaFreeHost(hptr));
+    return RMCV_OK;
+}
+int rmcv_memcpy_h2d(rmcv_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    RMCV_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->slot[0].stream));
+    return RMCV_OK;
+}
+int rmcv_memcpy_d2h(rmcv_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    RMCV_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->slot[0].stream));
+    return RMCV_OK;
+}
+int rmcv_memset_d(rmcv_ctx* ctx, void* dst, int value, size_t bytes) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    RMCV_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->slot[0].stream));
+    return RMCV_OK;
+}
+int rmcv_sync(rmcv_ctx* ctx) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    return sync_all(ctx);
+}
+void* rmcv_stream(rmcv_ctx* ctx) { return ctx ? reinterpret_cast<void*>(ctx->slot[0].stream) : nullptr; }
+
+int rmcv_extract_color_batch(rmcv_ctx* ctx, const uint8_t* d_bgr, size_t pitch, size_t frame_stride, int width, int height,
+                             int batch, int target, int lower_bound, uint8_t* d_mask, size_t mask_pitch,
+                             size_t mask_frame_stride) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    rmcv_params prm;
+    rmcv_default_params(&prm);
+    prm.target = target; prm.lower_bound = lower_bound;
+    return run_device_batch(ctx, d_bgr, pitch, frame_stride, width, height, batch, 0, prm, d_mask, mask_pitch, mask_frame_stride, false);
+}
+
+int rmcv_bayer_extract_color_batch(rmcv_ctx* ctx, const uint8_t* d_raw, size_t pitch, size_t frame_stride, int width,
+                                   int height, int batch, int bayer_layout, int target, int lower_bound, uint8_t* d_mask,
+                                   size_t mask_pitch, size_t mask_frame_stride) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    if (bayer_layout < RMCV_BAYER_RG || bayer_layout > RMCV_BAYER_BG) return set_err(ctx, RMCV_ERR_INVALID_ARG, "bad bayer layout");
+    if (width < 3 || height < 3) return set_err(ctx, RMCV_ERR_INVALID_ARG, "bayer frames must be at least 3x3");
+    rmcv_params prm;
+    rmcv_default_params(&prm);
+    prm.target = target; prm.lower_bound = lower_bound;
+    return run_device_batch(ctx, d_raw, pitch, frame_stride, width, height, batch, bayer_layout, prm, d_mask, mask_pitch,
+                            mask_frame_stride, false);
+}
+
+int rmcv_detect_batch(rmcv_ctx* ctx, const uint8_t* d_bgr, size_t pitch, size_t frame_stride, int width, int height, int batch,
+                      const rmcv_params* params, uint8_t* d_mask, size_t mask_pitch, size_t mask_frame_stride) {
+    if (!ctx || !params) return RMCV_ERR_INVALID_ARG;
+    return run_device_batch(ctx, d_bgr, pitch, frame_stride, width, height, batch, 0, *params, d_mask, mask_pitch, mask_frame_stride, true);
+}
+
+int rmcv_bayer_detect_batch(rmcv_ctx* ctx, const uint8_t* d_raw, size_t pitch, size_t frame_stride, int width, int height,
+                            int batch, int bayer_layout, const rmcv_params* params, uint8_t* d_mask, size_t mask_pitch,
+                            size_t mask_frame_stride) {
+    if (!ctx || !params) return RMCV_ERR_INVALID_ARG;
+    if (bayer_layout < RMCV_BAYER_RG || bayer_layout > RMCV_BAYER_BG) return set_err(ctx, RMCV_ERR_INVALID_ARG, "bad bayer layout");
+    if (width < 3 || height < 3) return set_err(ctx, RMCV_ERR_INVALID_ARG, "bayer frames must be at least 3x3");
+    return run_device_batch(ctx, d_raw, pitch, frame_stride, width, height, batch, bayer_layout, *params, d_mask, mask_pitch,
+                            mask_frame_stride, true);
+}
+
+int rmcv_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, size_t frame_stride, int width, int height,
+                           int batch, const rmcv_params* params, uint8_t* h_mask, size_t mask_pitch, size_t mask_frame_stride,
+                           rmcv_results* out) {
+    if (!ctx || !params || !h_bgr) return RMCV_ERR_INVALID_ARG;
+    int rc = check_geometry(ctx, width, height, batch);
+    if (rc != RMCV_OK) return rc;
+    const size_t rowbytes = (size_t)width * 3;
+    if (pitch < rowbytes) return set_err(ctx, RMCV_ERR_INVALID_ARG, "pitch smaller than a row");
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int CF = ctx->CF;
+    const size_t dev_frame = (size_t)height * rowbytes, dev_mask = (size_t)height * width;
+    int nchunks = 0;
+    for (int f0 = 0; f0 < batch; f0 += CF, ++nchunks) {
+        SlotBuffers& sb = ctx->slot[nchunks & 1];
+        const int frames = batch - f0 < CF ? batch - f0 : CF;
+        const size_t need = (size_t)CF * (size_t)ctx->cfg.max_height * ctx->cfg.max_width * 3;
+        if (sb.frames_bytes < need) {
+            if (sb.frames) cudaFree(sb.frames);
+            sb.frames = nullptr; sb.frames_bytes = 0;
+            RMCV_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&sb.frames), need));
+            sb.frames_bytes = need;
+        }
+        if (h_mask && sb.masks_bytes < need / 3) {
+            if (sb.masks) cudaFree(sb.masks);
+            sb.masks = nullptr; sb.masks_bytes = 0;
+            RMCV_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&sb.masks), need / 3));
+            sb.masks_bytes = need / 3;
+        }
+        const uint8_t* hsrc = h_bgr + (size_t)f0 * frame_stride;
+        if (pitch == rowbytes && frame_stride == dev_frame) {
+            RMCV_CUDA(ctx, cudaMemcpyAsync(sb.frames, hsrc, (size_t)frames * dev_frame, cudaMemcpyHostToDevice, sb.stream));
+        } else {
+            for (int f = 0; f < frames; ++f)
+                RMCV_CUDA(ctx, cudaMemcpy2DAsync(sb.frames + (size_t)f * dev_frame, rowbytes, hsrc + (size_t)f * frame_stride, pitch,
+                                                 rowbytes, height, cudaMemcpyHostToDevice, sb.stream));
+        }
+        rc = enqueue_chunk(ctx, sb, sb.frames, rowbytes, dev_frame, width, height, frames, f0, 0, *params,
+                           h_mask ? sb.masks : nullptr, width, dev_mask, true);
+        if (rc != RMCV_OK) return rc;
+        if (h_mask) {
+            uint8_t* hdst = h_mask + (size_t)f0 * mask_frame_stride;
+            if (mask_pitch == (size_t)width && mask_frame_stride == dev_mask) {
+                RMCV_CUDA(ctx, cudaMemcpyAsync(hdst, sb.masks, (size_t)frames * dev_mask, cudaMemcpyDeviceToHost, sb.stream));
+            } else {
+                for (int f = 0; f < frames; ++f)
+                    RMCV_CUDA(ctx, cudaMemcpy2DAsync(hdst + (size_t)f * mask_frame_stride, mask_pitch, sb.masks + (size_t)f * dev_mask,
+                                                     width, width, height, cudaMemcpyDeviceToHost, sb.stream));
+            }
+        }
+    }
+    ctx->last_batch = batch; ctx->last_W = width; ctx->last_H = height;
+    ctx->have_results = true;
+    extra(ctx)->last_nchunks = nchunks;
+    extra(ctx)->last_kind = 2;
+    rc = sync_all(ctx);
+    if (rc != RMCV_OK) return rc;
+    return fill_results(ctx, out);
+}
+
+int rmcv_fetch_results(rmcv_ctx* ctx, rmcv_results* out) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    int rc = sync_all(ctx);
+    if (rc != RMCV_OK) return rc;
+    return fill_results(ctx, out);
+}
+
+int rmcv_get_contour(rmcv_ctx* ctx, int frame, int contour_index, int32_t* xy, int cap, int* n_points) {
+    if (!ctx || !n_points || cap < 0 || (cap > 0 && !xy)) return RMCV_ERR_INVALID_ARG;
+    int rc = sync_all(ctx);
+    if (rc != RMCV_OK) return rc;
+    if (!ctx->have_results) return set_err(ctx, RMCV_ERR_STATE, "rmcv_get_contour needs a detect call first");
+    int local = 0;
+    SlotBuffers* sb = resident_slot(ctx, frame, &local);
+    if (!sb) return set_err(ctx, RMCV_ERR_STATE, "frame scratch no longer resident (only the last two chunks are kept)");
+    const rmcv_frame_info& fi = ctx->h_frames[frame];
+    if (contour_index < 0 || contour_index >= fi.n_contours) return set_err(ctx, RMCV_ERR_INVALID_ARG, "contour index out of range");
+    const rmcv_contour_info& ci = ctx->h_contours[fi.contour_offset + contour_index];
+    const size_t bytes = (size_t)(cap > 0 ? cap : 1) * 2 * sizeof(int32_t) + 16;
+    rc = ensure_tmp(ctx, bytes, bytes);
+    if (rc != RMCV_OK) return rc;
+    CtxExtra* ex = extra(ctx);
+    int32_t* d_n = reinterpret_cast<int32_t*>(ex->tmp_dev);
+    int32_t* d_xy = d_n + 4;
+    Geometry g = call_geometry(ctx, ctx->last_W, ctx->last_H);
+    cudaStream_t st = sb->stream;
+    RMCV_CUDA(ctx, launch_trace_contour(g, sb->bits + (size_t)local * g.H * g.WB, ci.first_x, ci.first_y, d_xy, cap, d_n, st,
+                                        &ctx->kernel_launches));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(ex->tmp_host, ex->tmp_dev, bytes, cudaMemcpyDeviceToHost, st));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(st));
+    const int32_t* h = reinterpret_cast<const int32_t*>(ex->tmp_host);
+    *n_points = h[0];
+    const int ncopy = h[0] < cap ? h[0] : cap;
+    if (ncopy > 0) memcpy(xy, h + 4, (size_t)ncopy * 2 * sizeof(int32_t));
+    return RMCV_OK;
+}
+
+int rmcv_get_label_map(rmcv_ctx* ctx, int frame, int32_t* labels, size_t pitch_elems) {
+    if (!ctx || !labels) return RMCV_ERR_INVALID_ARG;
+    int rc = sync_all(ctx);
+    if (rc != RMCV_OK) return rc;
+    if (!ctx->have_results) return set_err(ctx, RMCV_ERR_STATE, "rmcv_get_label_map needs a detect call first");
+    int local = 0;
+    SlotBuffers* sb = resident_slot(ctx, frame, &local);
+    if (!sb) return set_err(ctx, RMCV_ERR_STATE, "frame scratch no longer resident (only the last two chunks are kept)");
+    Geometry g = call_geometry(ctx, ctx->last_W, ctx->last_H);
+    if (pitch_elems < (size_t)g.W) return set_err(ctx, RMCV_ERR_INVALID_ARG, "label pitch smaller than a row");
+    const size_t bytes = (size_t)g.W * g.H * sizeof(int32_t);
+    rc = ensure_tmp(ctx, bytes, 0);
+    if (rc != RMCV_OK) return rc;
+    CtxExtra* ex = extra(ctx);
+    cudaStream_t st = sb->stream;
+    RMCV_CUDA(ctx, launch_label_map(g, sb, local, reinterpret_cast<int32_t*>(ex->tmp_dev), st, &ctx->kernel_launches));
+    RMCV_CUDA(ctx, cudaMemcpy2DAsync(labels, pitch_elems * sizeof(int32_t), ex->tmp_dev, (size_t)g.W * sizeof(int32_t),
+                                     (size_t)g.W * sizeof(int32_t), g.H, cudaMemcpyDeviceToHost, st));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(st));
+    return RMCV_OK;
+}
+
+int rmcv_get_bitmask(rmcv_ctx* ctx, int frame, uint32_t* words, int words_per_row) {
+    if (!ctx || !words) return RMCV_ERR_INVALID_ARG;
+    int rc = sync_all(ctx);
+    if (rc != RMCV_OK) return rc;
+    if (extra(ctx)->last_kind == 0) return set_err(ctx, RMCV_ERR_STATE, "no extract/detect call yet");
+    int local = 0;
+    SlotBuffers* sb = resident_slot(ctx, frame, &local);
+    if (!sb) return set_err(ctx, RMCV_ERR_STATE, "frame scratch no longer resident (only the last two chunks are kept)");
+    Geometry g = call_geometry(ctx, ctx->last_W, ctx->last_H);
+    if (words_per_row < g.WB) return set_err(ctx, RMCV_ERR_INVALID_ARG, "words_per_row too small");
+    RMCV_CUDA(ctx, cudaMemcpy2DAsync(words, (size_t)words_per_row * 4, sb->bits + (size_t)local * g.H * g.WB, (size_t)g.WB * 4,
+                                     (size_t)g.WB * 4, g.H, cudaMemcpyDeviceToHost, sb->stream));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(sb->stream));
+    return RMCV_OK;
+}
+
+int rmcv_filter_lightblobs(rmcv_ctx* ctx, const int32_t* xy, const int32_t* offsets, int n_contours, const rmcv_params* params,
+                           rmcv_contour_info* infos, rmcv_lightblob* blobs, int blob_cap, int* n_blobs) {
+    if (!ctx || !params || !offsets || n_contours < 0 || !n_blobs || (n_contours > 0 && !infos)) return RMCV_ERR_INVALID_ARG;
+    *n_blobs = 0;
+    if (n_contours == 0) return RMCV_OK;
+    const size_t npts = (size_t)offsets[n_contours];
+    if (npts > 0 && !xy) return RMCV_ERR_INVALID_ARG;
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    // device layout: xy | offsets | infos | blobs
+    const size_t b_xy = ((npts * 2 * 4) + 15) & ~(size_t)15, b_off = (((size_t)n_contours + 1) * 4 + 15) & ~(size_t)15;
+    const size_t b_info = (size_t)n_contours * sizeof(rmcv_contour_info), b_blob = (size_t)n_contours * sizeof(rmcv_lightblob);
+    int rc = ensure_tmp(ctx, b_xy + b_off + b_info + b_blob + 64, b_info + b_blob + 64);
+    if (rc != RMCV_OK) return rc;
+    CtxExtra* ex = extra(ctx);
+    uint8_t* d = reinterpret_cast<uint8_t*>(ex->tmp_dev);
+    cudaStream_t st = ctx->slot[0].stream;
+    if (npts) RMCV_CUDA(ctx, cudaMemcpyAsync(d, xy, npts * 2 * 4, cudaMemcpyHostToDevice, st));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(d + b_xy, offsets, ((size_t)n_contours + 1) * 4, cudaMemcpyHostToDevice, st));
+    rmcv_contour_info* d_info = reinterpret_cast<rmcv_contour_info*>(d + b_xy + b_off);
+    rmcv_lightblob* d_blob = reinterpret_cast<rmcv_lightblob*>(d + b_xy + b_off + b_info);
+    RMCV_CUDA(ctx, launch_filter_lightblobs(reinterpret_cast<const int32_t*>(d), reinterpret_cast<const int32_t*>(d + b_xy), n_contours,
+                                            *params, d_info, d_blob, st, &ctx->kernel_launches));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(ex->tmp_host, d_info, b_info + b_blob, cudaMemcpyDeviceToHost, st));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(st));
+    const rmcv_contour_info* h_info = reinterpret_cast<const rmcv_contour_info*>(ex->tmp_host);
+    const rmcv_lightblob* h_blob = reinterpret_cast<const rmcv_lightblob*>(reinterpret_cast<const uint8_t*>(ex->tmp_host) + b_info);
+    int nb = 0;
+    for (int i = 0; i < n_contours; ++i) {
+        infos[i] = h_info[i];
+        if (h_info[i].status == RMCV_CONTOUR_POSITIVE) {
+            infos[i].blob_index = nb;
+            if (blobs && nb < blob_cap) blobs[nb] = h_blob[i];
+            ++nb;
+        }
+    }
+    *n_blobs = nb;
+    return (blobs && nb > blob_cap) ? set_err(ctx, RMCV_ERR_CAPACITY, "blob_cap too small") : RMCV_OK;
+}
+
+int rmcv_filter_armours(rmcv_ctx* ctx, const rmcv_lightblob* blobs, int n_blobs, const rmcv_params* params, rmcv_armour* armours,
+                        int armour_cap, int* n_armours) {
+    if (!ctx || !params || n_blobs < 0 || !n_armours || armour_cap < 0 || (n_blobs > 0 && !blobs)) return RMCV_ERR_INVALID_ARG;
+    *n_armours = 0;
+    if (n_blobs < 2) return RMCV_OK;  // src/objdetect.cpp:120
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t b_blob = ((size_t)n_blobs * sizeof(rmcv_lightblob) + 15) & ~(size_t)15;
+    const size_t b_arm = (size_t)(armour_cap > 0 ? armour_cap : 1) * sizeof(rmcv_armour);
+    int rc = ensure_tmp(ctx, b_blob + b_arm + 64, b_arm + 64);
+    if (rc != RMCV_OK) return rc;
+    CtxExtra* ex = extra(ctx);
+    uint8_t* d = reinterpret_cast<uint8_t*>(ex->tmp_dev);
+    cudaStream_t st = ctx->slot[0].stream;
+    RMCV_CUDA(ctx, cudaMemcpyAsync(d, blobs, (size_t)n_blobs * sizeof(rmcv_lightblob), cudaMemcpyHostToDevice, st));
+    int32_t* d_count = reinterpret_cast<int32_t*>(d + b_blob);
+    rmcv_armour* d_arm = reinterpret_cast<rmcv_armour*>(d + b_blob + 16);
+    RMCV_CUDA(ctx, launch_filter_armours(reinterpret_cast<const rmcv_lightblob*>(d), n_blobs, *params, d_arm, armour_cap, d_count, st,
+                                         &ctx->kernel_launches));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(ex->tmp_host, d + b_blob, 16 + b_arm, cudaMemcpyDeviceToHost, st));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(st));
+    const int total = *reinterpret_cast<const int32_t*>(ex->tmp_host);
+    *n_armours = total;
+    const int ncopy = total < armour_cap ? total : armour_cap;
+    if (ncopy > 0 && armours) memcpy(armours, reinterpret_cast<const uint8_t*>(ex->tmp_host) + 16, (size_t)ncopy * sizeof(rmcv_armour));
+    return total > armour_cap ? set_err(ctx, RMCV_ERR_CAPACITY, "armour_cap too small") : RMCV_OK;
+}
+
+int rmcv_make_lightblobs(rmcv_ctx* ctx, const rmcv_rotated_rect* boxes, int n, int target, rmcv_lightblob* out) {
+    if (!ctx || n < 0 || (n > 0 && (!boxes || !out))) return RMCV_ERR_INVALID_ARG;
+    if (n == 0) return RMCV_OK;
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t b_in = ((size_t)n * sizeof(rmcv_rotated_rect) + 15) & ~(size_t)15, b_out = (size_t)n * sizeof(rmcv_lightblob);
+    int rc = ensure_tmp(ctx, b_in + b_out, b_out);
+    if (rc != RMCV_OK) return rc;
+    CtxExtra* ex = extra(ctx);
+    uint8_t* d = reinterpret_cast<uint8_t*>(ex->tmp_dev);
+    cudaStream_t st = ctx->slot[0].stream;
+    RMCV_CUDA(ctx, cudaMemcpyAsync(d, boxes, (size_t)n * sizeof(rmcv_rotated_rect), cudaMemcpyHostToDevice, st));
+    RMCV_CUDA(ctx, launch_make_lightblobs(reinterpret_cast<const rmcv_rotated_rect*>(d), n, target, reinterpret_cast<rmcv_lightblob*>(d + b_in),
+                                          st, &ctx->kernel_launches));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(ex->tmp_host, d + b_in, b_out, cudaMemcpyDeviceToHost, st));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(out, ex->tmp_host, b_out);
+    return RMCV_OK;
+}
+
+int rmcv_profile_enable(rmcv_ctx* ctx, int on) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    ctx->profiling = on != 0;
+    return RMCV_OK;
+}
+
+int rmcv_profile_read(rmcv_ctx* ctx, double ms[RMCV_STAGE_COUNT], int64_t launches[RMCV_STAGE_COUNT], int reset) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    for (int s = 0; s < RMCV_STAGE_COUNT; ++s) {
+        if (ms) ms[s] = ctx->prof_ms[s];
+        if (launches) launches[s] = ctx->prof_launches[s];
+        if (reset) { ctx->prof_ms[s] = 0.0; ctx->prof_launches[s] = 0; }
+    }
+    return RMCV_OK;
+}
+
+int64_t rmcv_kernel_launches(const rmcv_ctx* ctx) { return ctx ? ctx->kernel_launches : 0; }
+
+}  // extern "C"

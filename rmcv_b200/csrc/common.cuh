@@ -1,0 +1,164 @@
+// Shared declarations of the rmcv_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/rmcv_b200.h"
+
+namespace rmcv {
+
+// ------------------------------------------------------------------------------------------
+// Per-frame scratch layout.  One "slot" owns scratch for chunk_frames frames and one stream;
+// a detect call walks its batch chunk by chunk, alternating slots so that the copies of one
+// chunk overlap the kernels of the other.
+// ------------------------------------------------------------------------------------------
+struct CompRec {            // one 8-connected component after the blob kernel
+    int32_t firstkey;       // y*W + x of the raster-first pixel, -1 when not external
+    int32_t n_points;       // contour.size()
+    int64_t area2;          // 2*contourArea
+    int32_t bbox[4];        // x0, y0, x1, y1 (inclusive)
+    int32_t status;         // RMCV_CONTOUR_*, or -1 for nested / dropped components
+    int32_t fit_branch;
+    float det0;
+    rmcv_rotated_rect ellipse;
+    rmcv_lightblob blob;
+};
+
+struct RunStat {            // per run; meaningful at component roots after the flatten pass
+    int32_t x0, y0, x1, y1; // bounding box
+    int32_t firstkey;       // min over the component of y*W + xs
+};
+
+struct FrameCounters {      // device-side, one per frame in the chunk
+    int32_t n_runs;
+    int32_t n_comps;
+    int32_t n_holes;        // number of hole gaps (background runs not connected to the border)
+    int32_t flags;
+    int32_t n_contours, n_positive, n_negative, n_armours;
+};
+
+struct Geometry {           // frame geometry + derived sizes, shared by all kernels of a call
+    int W, H, WB;           // WB = 32-pixel words per row
+    int R;                  // run capacity per frame
+    int C;                  // component capacity per frame
+    int A;                  // armour capacity per frame
+};
+
+struct SlotBuffers {
+    // pixel stage outputs
+    uint32_t* bits;         // [CF][H][WB]   final mask, bit-packed
+    uint32_t* hole;         // [CF][H][WB]   hole background; all-zero between calls (invariant)
+    // runs
+    int32_t* row_off;       // [CF][H+1]     first run of each row (index into the frame's run arrays)
+    uint32_t* run_x;        // [CF][R]       xs | xe<<16
+    int32_t* run_y;         // [CF][R]
+    int32_t* parent;        // [CF][R]       union-find over foreground runs (8-connectivity)
+    int32_t* gparent;       // [CF][R+1]     union-find over interior background gaps, node 0 = outer
+    RunStat* rstat;         // [CF][R]
+    int32_t* comp_root;     // [CF][C]       root run of each component
+    CompRec* comps;         // [CF][C]
+    FrameCounters* counters;// [CF]
+    // ordered per-frame result slots (device) before dense write-out
+    rmcv_contour_info* s_contours; // [CF][C]
+    rmcv_lightblob* s_blobs;       // [CF][C]
+    rmcv_armour* s_armours;        // [CF][A]
+    // staging for host-input calls
+    uint8_t* frames;        // [CF][H][W*3] (allocated lazily)
+    uint8_t* masks;         // [CF][H][W]   (allocated lazily)
+    size_t frames_bytes, masks_bytes;
+    cudaStream_t stream;
+    bool own_stream;
+    cudaEvent_t done;       // recorded after the last kernel of a chunk
+};
+
+}  // namespace rmcv
+
+struct rmcv_ctx {
+    rmcv_config cfg;
+    int device;
+    int sm_count;
+    int CF;                 // chunk frames
+    rmcv::Geometry cap;     // capacities at max_width x max_height
+    rmcv::SlotBuffers slot[2];
+    // pinned, device-mapped result arrays for a whole batch
+    rmcv_frame_info* h_frames;      // [max_batch]
+    rmcv_contour_info* h_contours;  // [max_batch][C]  (chunk-dense)
+    rmcv_lightblob* h_blobs;        // [max_batch][C]
+    rmcv_armour* h_armours;         // [max_batch][A]
+    // last call
+    int last_batch, last_W, last_H;
+    bool have_results;
+    // profiling
+    bool profiling;
+    double prof_ms[RMCV_STAGE_COUNT];
+    int64_t prof_launches[RMCV_STAGE_COUNT];
+    int64_t kernel_launches;
+    void* extra;            // C++ side state (event sets, allocation lists), see api.cu
+    char err[512];
+};
+
+namespace rmcv {
+
+#define RMCV_CUDA(ctx, call)                                                                      \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s -> %s", __FILE__, __LINE__, #call, \
+                     cudaGetErrorString(e_));                                                     \
+            return RMCV_ERR_CUDA;                                                                 \
+        }                                                                                         \
+    } while (0)
+
+inline int set_err(rmcv_ctx* ctx, int code, const char* msg) {
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s", msg);
+    return code;
+}
+
+// ---- launchers implemented in the .cu files -----------------------------------------------
+struct PixelLaunch {
+    const uint8_t* src; size_t pitch, frame_stride;
+    uint8_t* mask; size_t mask_pitch, mask_frame_stride;
+    uint32_t* bits;     // [batch][H][WB]
+    int W, H, batch;
+    int target, lower_bound;
+    int bayer_layout;   // 0 = BGR input
+};
+cudaError_t launch_pixel_stage(const PixelLaunch& p, int sm_count, cudaStream_t st, int64_t* launches);
+
+struct LabelLaunch {
+    Geometry g; int frames; SlotBuffers* sb;
+};
+cudaError_t launch_runs(const LabelLaunch& p, cudaStream_t st, int64_t* launches);
+cudaError_t launch_label(const LabelLaunch& p, cudaStream_t st, int64_t* launches);
+cudaError_t launch_blobs(const LabelLaunch& p, const rmcv_params& prm, cudaStream_t st, int64_t* launches);
+cudaError_t launch_unpaint(const LabelLaunch& p, cudaStream_t st, int64_t* launches);
+
+struct OutputLaunch {
+    Geometry g; int frames; SlotBuffers* sb;
+    int frame_base;               // index of the chunk's first frame in the batch
+    rmcv_frame_info* o_frames;    // device-visible pointers of the pinned result arrays
+    rmcv_contour_info* o_contours;
+    rmcv_lightblob* o_blobs;
+    rmcv_armour* o_armours;
+    int C_out, A_out;             // per-frame strides of the pinned arrays
+};
+cudaError_t launch_armours(const OutputLaunch& p, const rmcv_params& prm, cudaStream_t st, int64_t* launches);
+
+cudaError_t launch_trace_contour(const Geometry& g, const uint32_t* bits, int x0, int y0, int32_t* d_xy, int cap,
+                                 int32_t* d_n, cudaStream_t st, int64_t* launches);
+cudaError_t launch_label_map(const Geometry& g, SlotBuffers* sb, int frame, int32_t* d_labels, cudaStream_t st,
+                             int64_t* launches);
+
+cudaError_t launch_filter_lightblobs(const int32_t* d_xy, const int32_t* d_off, int n, const rmcv_params& prm,
+                                     rmcv_contour_info* d_infos, rmcv_lightblob* d_blobs, cudaStream_t st,
+                                     int64_t* launches);
+cudaError_t launch_filter_armours(const rmcv_lightblob* d_blobs, int n, const rmcv_params& prm, rmcv_armour* d_out,
+                                  int cap, int32_t* d_count, cudaStream_t st, int64_t* launches);
+cudaError_t launch_make_lightblobs(const rmcv_rotated_rect* d_boxes, int n, int target, rmcv_lightblob* d_out,
+                                   cudaStream_t st, int64_t* launches);
+
+void upload_luts();  // copies the arc LUT to constant memory (once per process/device)
+
+}  // namespace rmcv

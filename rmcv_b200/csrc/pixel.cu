@@ -1,0 +1,510 @@
+// K1 — fused pixel stage of rm::extract_color (reference: src/imgproc.cpp:52-69):
+//   cv::split + saturating channel difference + inRange + 3x3 MORPH_CLOSE  ->  {0,255} byte mask
+//   (+ the same mask bit-packed, 1 bit/px, for the labelling stages).
+// and its Bayer front (reference: hardware/src/daheng.cpp:136-151, DxRaw8toRGB24 stand-in).
+//
+// HBM-bound streaming kernel, no tensor cores (nothing here is a contraction):
+//   * one CTA = one band of BH output rows of one frame, full image width (no x halo);
+//   * raw rows travel global -> shared with 1-D TMA bulk copies (cp.async.bulk, UBLKCP in SASS) through a
+//     S-stage ring guarded by mbarriers; a row band of a continuous frame is one contiguous copy;
+//   * per 16-pixel group a thread reads 48 B (3 conflict-free LDS.128), forms B-R-lb (or any channel pair)
+//     with 6 dp4a per 4 pixels and shifts the sign bits into a 16-bit threshold word;
+//   * dilate/erode run on the bit rows in shared memory (3 OR / 3 AND of shifted words), border rules of
+//     OpenCV's MORPH_CLOSE (dilate pads 0, erode pads 1);
+//   * every input byte is read from HBM once (band halo rows are re-read through L2), every mask byte is
+//     written once with 16-byte stores.
+#include "common.cuh"
+
+namespace rmcv {
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0, 16-B aligned).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
+// 4 mask bits -> 4 bytes of 0x00/0xFF: spread the bits to the byte MSBs, then PRMT sign-replicate.
+__device__ __forceinline__ uint32_t expand4(uint32_t nib) {
+    uint32_t x = nib * 0x10204080u;
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(x));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------ parameters
+struct PixelParams {
+    const uint8_t* src; size_t pitch, frame_stride;
+    uint8_t* mask; size_t mask_pitch, mask_frame_stride;
+    uint32_t* bits;
+    int W, H, WB;
+    int BH, bands;       // output rows per band, bands per frame
+    int RC, S;           // rows per TMA chunk, ring stages
+    int srow;            // shared-memory row stride in bytes
+    int gpr;             // 16-pixel groups per row (BGR) / per row (Bayer)
+    int halo;            // threshold-row halo: 2 (BGR), raw-row halo is halo+1 for Bayer
+    uint32_t coef[6];    // dp4a coefficient words (signed bytes) for the 4 pixels of a 12-byte group
+    int acc0;            // -lower_bound (or the constants that force all-0 / all-1)
+    int contiguous;      // pitch == row bytes: a chunk is one bulk copy
+    int mask_vec;        // mask rows allow 16-byte stores
+    uint32_t last_valid; // valid bits of the last word of a row
+    // Bayer only
+    int bayer;           // 0 = BGR
+    int px, py;          // parity (x&1, y&1) of the site that samples channel `plus`... see kernel
+    int plus_is_site;    // layout helpers, see bayer kernel
+    int lb;
+};
+
+struct Iter2D {  // walks idx = tid, tid+NT, ... over a [rows][cols] grid without divisions in the loop
+    int r, c, dr, dc, cols;
+    __device__ __forceinline__ Iter2D(int tid, int nt, int cols_) : cols(cols_) {
+        r = tid / cols_; c = tid - r * cols_;
+        dr = nt / cols_; dc = nt - dr * cols_;
+    }
+    __device__ __forceinline__ void next() {
+        r += dr; c += dc;
+        if (c >= cols) { c -= cols; ++r; }
+    }
+};
+
+// Shared-memory carve-up (bytes): [S stages][S mbarriers (padded to 16 B)][t rows][d rows]
+__host__ __device__ inline size_t pix_smem_bytes(int S, int RC, int srow, int BH, int WB, int halo_rows) {
+    size_t TW = (size_t)WB + 2;
+    size_t stage = (size_t)S * RC * srow;
+    size_t bars = ((size_t)S * 8 + 15) & ~(size_t)15;
+    size_t t = (size_t)(BH + 2 * halo_rows) * TW * 4;
+    size_t d = (size_t)(BH + 2) * TW * 4;
+    return stage + bars + t + d;
+}
+
+// ------------------------------------------------------------------------------------------ morphology + stores
+// t: (nout+4) x TW threshold words (row 0 <-> image row y0-2), zero outside the image.
+// Writes the final mask of rows [y0, y0+nout) to global as bytes and as bit words.
+__device__ __forceinline__ void close_and_store(const PixelParams& p, uint32_t* t, uint32_t* d, int frame, int y0,
+                                                int nout, int tid, int NT) {
+    const int WB = p.WB, TW = WB + 2, H = p.H;
+    const uint32_t valid = p.last_valid;
+    // ---- dilate: rows y0-1 .. y0+nout  (outside the image: all ones so that the erode ignores them)
+    for (Iter2D it(tid, NT, WB); it.r < nout + 2; it.next()) {
+        const int i = it.r, k = it.c;
+        const int y = y0 - 1 + i;
+        uint32_t dv = 0xFFFFFFFFu;
+        if (y >= 0 && y < H) {
+            const uint32_t* a = t + (size_t)i * TW + k;  // padded column k  <-> word k-1
+            uint32_t vm = a[0] | a[TW] | a[2 * TW];
+            uint32_t v0 = a[1] | a[TW + 1] | a[2 * TW + 1];
+            uint32_t vp = a[2] | a[TW + 2] | a[2 * TW + 2];
+            if (k == WB - 1) v0 &= valid;
+            if (k + 1 == WB - 1) vp &= valid;
+            dv = v0 | (v0 << 1) | (vm >> 31) | (v0 >> 1) | (vp << 31);
+            if (k == WB - 1) dv |= ~valid;
+        }
+        d[(size_t)i * TW + k + 1] = dv;
+        if (k == 0) d[(size_t)i * TW] = 0xFFFFFFFFu;
+        if (k == WB - 1) d[(size_t)i * TW + TW - 1] = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    // ---- erode: rows y0 .. y0+nout-1; result into t (compact [nout][WB]) and to the global bit mask
+    uint32_t* m = t;
+    uint32_t* gbits = p.bits + ((size_t)frame * H + y0) * WB;
+    for (Iter2D it(tid, NT, WB); it.r < nout; it.next()) {
+        const int j = it.r, k = it.c;
+        const uint32_t* a = d + (size_t)j * TW + k;
+        uint32_t am = a[0] & a[TW] & a[2 * TW];
+        uint32_t a0 = a[1] & a[TW + 1] & a[2 * TW + 1];
+        uint32_t ap = a[2] & a[TW + 2] & a[2 * TW + 2];
+        uint32_t mv = a0 & ((a0 << 1) | (am >> 31)) & ((a0 >> 1) | (ap << 31));
+        if (k == WB - 1) mv &= valid;
+        // t and m alias: every thread reads d only and writes m[j*WB+k]; t was last read before the barrier
+        m[(size_t)j * WB + k] = mv;
+        gbits[(size_t)j * WB + k] = mv;
+    }
+    if (p.mask == nullptr) return;
+    __syncthreads();
+    // ---- byte mask: one 16-byte store per 16 pixels
+    const uint16_t* m16 = reinterpret_cast<const uint16_t*>(m);
+    const int gpr16 = (p.W + 15) >> 4;
+    uint8_t* gmask = p.mask + (size_t)frame * p.mask_frame_stride + (size_t)y0 * p.mask_pitch;
+    for (Iter2D it(tid, NT, gpr16); it.r < nout; it.next()) {
+        const int j = it.r, g = it.c;
+        const uint32_t b = m16[(size_t)j * WB * 2 + g];
+        uint8_t* dst = gmask + (size_t)j * p.mask_pitch + (size_t)g * 16;
+        uint4 o;
+        o.x = expand4(b & 15u);
+        o.y = expand4((b >> 4) & 15u);
+        o.z = expand4((b >> 8) & 15u);
+        o.w = expand4(b >> 12);
+        if (p.mask_vec && g * 16 + 16 <= p.W) {
+            __stcs(reinterpret_cast<uint4*>(dst), o);
+        } else {
+            const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+            for (int q = 0; q < 16 && g * 16 + q < p.W; ++q) dst[q] = (uint8_t)(w[q >> 2] >> ((q & 3) * 8));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ BGR kernel
+template <bool kBulk>
+__global__ void __launch_bounds__(512) pixel_bgr_kernel(const PixelParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int frame = blockIdx.x / p.bands, band = blockIdx.x - frame * p.bands;
+    const int W = p.W, H = p.H, WB = p.WB, TW = WB + 2, BH = p.BH, RC = p.RC, S = p.S;
+    const int y0 = band * BH;
+    const int nout = min(BH, H - y0);
+    const int ty0 = y0 - 2;                               // image row of t row 0
+    const int cy0 = max(0, ty0), cy1 = min(H, y0 + nout + 2);
+    const int nchunks = (cy1 - cy0 + RC - 1) / RC;
+    const size_t stage_bytes = (size_t)RC * p.srow;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+    uint32_t* t = reinterpret_cast<uint32_t*>(smem + (size_t)S * stage_bytes + (((size_t)S * 8 + 15) & ~(size_t)15));
+    uint32_t* d = t + (size_t)(BH + 4) * TW;
+    uint16_t* t16 = reinterpret_cast<uint16_t*>(t);
+
+    for (int i = tid; i < (BH + 4) * TW; i += NT) t[i] = 0u;
+    if (!kBulk) {  // zero the row padding of the stage buffers once (generic widths)
+        for (int i = tid; i < (int)(S * stage_bytes / 4); i += NT) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+    }
+    if (kBulk && tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const uint8_t* fsrc = p.src + (size_t)frame * p.frame_stride;
+    const uint32_t rowbytes = (uint32_t)W * 3u;
+    auto issue = [&](int c) {  // one thread
+        const int s = c % S, r0 = cy0 + c * RC, nr = min(RC, cy1 - r0);
+        uint8_t* dst = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(&bars[s], (uint32_t)nr * rowbytes);
+        if (p.contiguous) {
+            bulk_g2s(dst, fsrc + (size_t)r0 * p.pitch, (uint32_t)nr * rowbytes, &bars[s]);
+        } else {
+            for (int r = 0; r < nr; ++r) bulk_g2s(dst + (size_t)r * p.srow, fsrc + (size_t)(r0 + r) * p.pitch, rowbytes, &bars[s]);
+        }
+    };
+    if (kBulk && tid == 0) {
+        for (int c = 0; c < S && c < nchunks; ++c) issue(c);
+    }
+
+    const int gpr = p.gpr;
+    const uint32_t c0 = p.coef[0], c1a = p.coef[1], c1b = p.coef[2], c2a = p.coef[3], c2b = p.coef[4], c3 = p.coef[5];
+    const int acc0 = p.acc0;
+    const Iter2D it0(tid, NT, gpr);
+
+    for (int c = 0; c < nchunks; ++c) {
+        const int s = c % S, r0 = cy0 + c * RC, nr = min(RC, cy1 - r0);
+        const uint8_t* stage = smem + (size_t)s * stage_bytes;
+        if (kBulk) {
+            mbar_wait(&bars[s], (uint32_t)((c / S) & 1));
+        } else {
+            uint8_t* wstage = smem + (size_t)s * stage_bytes;
+            for (int r = 0; r < nr; ++r) {
+                const uint8_t* g = fsrc + (size_t)(r0 + r) * p.pitch;
+                for (uint32_t i = tid; i < rowbytes; i += NT) wstage[(size_t)r * p.srow + i] = __ldg(g + i);
+            }
+            __syncthreads();
+        }
+        for (Iter2D it = it0; it.r < nr; it.next()) {
+            const uint4* q = reinterpret_cast<const uint4*>(stage + (size_t)it.r * p.srow + (size_t)it.c * 48);
+            const uint4 A = q[0], B = q[1], C = q[2];
+            const uint32_t w[12] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x, C.y, C.z, C.w};
+            uint32_t nb = 0;  // sign bits of (diff - lb), pixel 15 first so that pixel 0 lands in bit 0
+#pragma unroll
+            for (int grp = 3; grp >= 0; --grp) {
+                const uint32_t w0 = w[3 * grp], w1 = w[3 * grp + 1], w2 = w[3 * grp + 2];
+                const int v3 = dp4a_us(w2, c3, acc0);
+                const int v2 = dp4a_us(w1, c2a, dp4a_us(w2, c2b, acc0));
+                const int v1 = dp4a_us(w0, c1a, dp4a_us(w1, c1b, acc0));
+                const int v0 = dp4a_us(w0, c0, acc0);
+                nb = __funnelshift_l((uint32_t)v3, nb, 1);
+                nb = __funnelshift_l((uint32_t)v2, nb, 1);
+                nb = __funnelshift_l((uint32_t)v1, nb, 1);
+                nb = __funnelshift_l((uint32_t)v0, nb, 1);
+            }
+            const int ty = r0 + it.r - ty0;
+            t16[(size_t)ty * TW * 2 + 2 + it.c] = (uint16_t)(~nb);
+        }
+        __syncthreads();  // stage s fully consumed (and t rows of this chunk visible)
+        if (kBulk && tid == 0 && c + S < nchunks) issue(c + S);
+    }
+    close_and_store(p, t, d, frame, y0, nout, tid, NT);
+}
+
+// ------------------------------------------------------------------------------------------ Bayer kernel
+// Raw 8-bit mosaic, 1 B/px.  For the colour difference only two planes are needed; they are rebuilt with the
+// OpenCV bilinear rule: sample at its own site, (a+b+1)>>1 from two neighbours, (a+b+c+d+2)>>2
+// from four; then row 0 := row 1, row H-1 := row H-2, column 0 := column 1, column W-1 := column W-2, which on
+// threshold bits is a replicate of the neighbouring interior bit.
+struct BayerSite {  // which of the 4 interpolation patterns yields channel c at parity (py,px)
+    // 0 = own sample, 1 = horizontal pair, 2 = vertical pair, 3 = four diagonals, 4 = four plus-neighbours
+    uint8_t plus[2][2], minus[2][2];
+};
+
+__global__ void __launch_bounds__(512) pixel_bayer_kernel(const PixelParams p, const BayerSite site) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int frame = blockIdx.x / p.bands, band = blockIdx.x - frame * p.bands;
+    const int W = p.W, H = p.H, WB = p.WB, TW = WB + 2, BH = p.BH;
+    const int y0 = band * BH;
+    const int nout = min(BH, H - y0);
+    const int ty0 = y0 - 2;
+    // threshold rows needed: [y0-2, y0+nout+2) clipped; raw rows: one more on each side, clamped
+    const int cy0 = max(0, ty0), cy1 = min(H, y0 + nout + 2);
+    const int ry0 = max(0, cy0 - 2), ry1 = min(H, cy1 + 2);  // generous: border replicate may look 2 rows in
+    const int nraw = ry1 - ry0;
+    const size_t raw_bytes = ((size_t)(BH + 8) * p.srow + 15) & ~(size_t)15;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + raw_bytes);  // after the raw rows
+    uint32_t* t = reinterpret_cast<uint32_t*>(smem + raw_bytes + 16);
+    uint32_t* d = t + (size_t)(BH + 4) * TW;
+
+    for (int i = tid; i < (BH + 4) * TW; i += NT) t[i] = 0u;
+    const uint8_t* fsrc = p.src + (size_t)frame * p.frame_stride;
+    const bool bulk = p.contiguous >= 0 && (p.srow == W) && ((W & 15) == 0) && ((p.pitch & 15) == 0) &&
+                      ((((size_t)fsrc) & 15) == 0);
+    if (bulk) {
+        if (tid == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bars[0], (uint32_t)nraw * (uint32_t)W);
+            if (p.pitch == (size_t)W) {
+                // chunks of <= 32 KB keep every copy well inside the mbarrier tx-count range
+                int r = 0;
+                while (r < nraw) {
+                    int nr = min(nraw - r, max(1, 32768 / W));
+                    bulk_g2s(smem + (size_t)r * p.srow, fsrc + (size_t)(ry0 + r) * p.pitch, (uint32_t)nr * (uint32_t)W, &bars[0]);
+                    r += nr;
+                }
+            } else {
+                for (int r = 0; r < nraw; ++r)
+                    bulk_g2s(smem + (size_t)r * p.srow, fsrc + (size_t)(ry0 + r) * p.pitch, (uint32_t)W, &bars[0]);
+            }
+        }
+        mbar_wait(&bars[0], 0);
+    } else {
+        for (int r = 0; r < nraw; ++r) {
+            const uint8_t* g = fsrc + (size_t)(ry0 + r) * p.pitch;
+            for (int i = tid; i < W; i += NT) smem[(size_t)r * p.srow + i] = __ldg(g + i);
+        }
+        __syncthreads();
+    }
+    // threshold bits: one thread per (row, 32-pixel word); interior pixels by the bilinear rule, border
+    // pixels replicate the clamped interior coordinate.
+    const int lb = p.lb;
+    for (Iter2D it(tid, NT, WB); it.r < cy1 - cy0; it.next()) {
+        const int y = cy0 + it.r, k = it.c;
+        const int yc = min(max(y, 1), H - 2);          // row whose interior values this row shows
+        const uint8_t* rm = smem + (size_t)(yc - 1 - ry0) * p.srow;
+        const uint8_t* r0 = smem + (size_t)(yc - ry0) * p.srow;
+        const uint8_t* rp = smem + (size_t)(yc + 1 - ry0) * p.srow;
+        uint32_t wbits = 0;
+        const int xend = min(32, W - k * 32);
+        for (int b = 0; b < xend; ++b) {
+            const int x = k * 32 + b;
+            const int xc = min(max(x, 1), W - 2);
+            const int pyy = yc & 1, pxx = xc & 1;
+            int val[2];
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int mode = ch == 0 ? site.plus[pyy][pxx] : site.minus[pyy][pxx];
+                int v;
+                if (mode == 0) v = r0[xc];
+                else if (mode == 1) v = (r0[xc - 1] + r0[xc + 1] + 1) >> 1;
+                else if (mode == 2) v = (rm[xc] + rp[xc] + 1) >> 1;
+                else if (mode == 3) v = (rm[xc - 1] + rm[xc + 1] + rp[xc - 1] + rp[xc + 1] + 2) >> 2;
+                else v = (r0[xc - 1] + r0[xc + 1] + rm[xc] + rp[xc] + 2) >> 2;
+                val[ch] = v;
+            }
+            int diff = val[0] - val[1];
+            diff = diff < 0 ? 0 : diff;
+            wbits |= (uint32_t)(diff >= lb && diff <= 255) << b;
+        }
+        t[(size_t)(y - ty0) * TW + k + 1] = wbits;
+    }
+    __syncthreads();
+    close_and_store(p, t, d, frame, y0, nout, tid, NT);
+}
+
+// ------------------------------------------------------------------------------------------ host launcher
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t st, int64_t* launches) {
+    PixelParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = L.src; p.pitch = L.pitch; p.frame_stride = L.frame_stride;
+    p.mask = L.mask; p.mask_pitch = L.mask_pitch; p.mask_frame_stride = L.mask_frame_stride;
+    p.bits = L.bits;
+    p.W = L.W; p.H = L.H; p.WB = (L.W + 31) / 32;
+    p.last_valid = (L.W & 31) ? ((1u << (L.W & 31)) - 1u) : 0xFFFFFFFFu;
+    p.mask_vec = (L.mask != nullptr) && ((L.mask_pitch & 15) == 0) && ((L.mask_frame_stride & 15) == 0) &&
+                 ((((size_t)L.mask) & 15) == 0);
+    p.lb = L.lower_bound;
+    p.halo = 2;
+
+    // band height: tall bands amortise the 4 halo rows; small batches need more, shorter bands to fill 148 SMs
+    int BH = env_int("RMCV_PIX_BH", 0);
+    if (BH <= 0) {
+        BH = 32;
+        while (BH > 8 && (long long)L.batch * ((L.H + BH - 1) / BH) < 4LL * sm_count) BH >>= 1;
+    }
+    if (BH > L.H) BH = L.H;
+    p.BH = BH;
+    p.bands = (L.H + BH - 1) / BH;
+    const long long grid = (long long)L.batch * p.bands;
+    if (grid <= 0 || grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+
+    int dev = 0, max_smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+
+    if (L.bayer_layout == 0) {
+        // ---- BGR
+        int a, b;  // plus / minus channel (src/imgproc.cpp:56-65)
+        if (L.target == RMCV_CAMP_GUIDELIGHT) { a = 1; b = 2; }
+        else if (L.target == RMCV_CAMP_BLUE) { a = 0; b = 2; }
+        else { a = 2; b = 0; }
+        // byte k of a 12-byte group belongs to pixel k/3, channel k%3; coefficient words are per (pixel, word)
+        // order: c0 (px0,w0) c1a (px1,w0) c1b (px1,w1) c2a (px2,w1) c2b (px2,w2) c3 (px3,w2)
+        auto put = [&](int slot, int px, int word) {
+            uint32_t v = 0;
+            for (int lane = 0; lane < 4; ++lane) {
+                int k = word * 4 + lane;
+                if (k / 3 != px) continue;
+                int ch = k % 3;
+                int coef = (ch == a ? 1 : 0) - (ch == b ? 1 : 0);
+                v |= (uint32_t)(uint8_t)(int8_t)coef << (8 * lane);
+            }
+            p.coef[slot] = v;
+        };
+        put(0, 0, 0); put(1, 1, 0); put(2, 1, 1); put(3, 2, 1); put(4, 2, 2); put(5, 3, 2);
+        // v = diff + acc0 >= 0  <=>  sat_u8(diff) in [lb, 255].  The two-word pixels add acc0 once (inner dp4a).
+        if (L.lower_bound <= 0) { for (int i = 0; i < 6; ++i) p.coef[i] = 0; p.acc0 = 0; }
+        else if (L.lower_bound > 255) { for (int i = 0; i < 6; ++i) p.coef[i] = 0; p.acc0 = -1; }
+        else p.acc0 = -L.lower_bound;
+
+        p.gpr = (L.W + 15) / 16;
+        p.srow = p.gpr * 48;
+        const bool bulk = ((L.W & 15) == 0) && ((L.pitch & 15) == 0) && ((L.frame_stride & 15) == 0) &&
+                          ((((size_t)L.src) & 15) == 0) && env_int("RMCV_PIX_NOBULK", 0) == 0;
+        p.contiguous = (L.pitch == (size_t)L.W * 3) ? 1 : 0;
+        int RC = env_int("RMCV_PIX_RC", 0);
+        if (RC <= 0) RC = max(1, min(16, 24576 / p.srow));
+        if (RC > BH + 4) RC = BH + 4;
+        int S = env_int("RMCV_PIX_S", 3);
+        int NT = env_int("RMCV_PIX_NT", 0);
+        if (NT <= 0) {  // threads: minimise idle lanes in the per-chunk item loop
+            int items = RC * p.gpr, best = 256, best_waste = 1 << 30;
+            for (int nt = 192; nt <= 512; nt += 32) {
+                int waste = ((items + nt - 1) / nt) * nt - items;
+                // prefer exact fits, then sizes near 256
+                int score = waste * 1024 / items * 8 + abs(nt - 320) / 32;
+                if (score < best_waste) { best_waste = score; best = nt; }
+            }
+            NT = best;
+        }
+        p.RC = RC; p.S = S;
+        size_t smem = pix_smem_bytes(S, RC, p.srow, BH, p.WB, 2);
+        while (smem > (size_t)max_smem && p.S > 1) { --p.S; smem = pix_smem_bytes(p.S, RC, p.srow, BH, p.WB, 2); }
+        while (smem > (size_t)max_smem && p.RC > 1) { --p.RC; smem = pix_smem_bytes(p.S, p.RC, p.srow, BH, p.WB, 2); }
+        if (smem > (size_t)max_smem) return cudaErrorInvalidConfiguration;
+        cudaError_t e;
+        if (bulk) {
+            e = cudaFuncSetAttribute(pixel_bgr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            pixel_bgr_kernel<true><<<(unsigned)grid, NT, smem, st>>>(p);
+        } else {
+            e = cudaFuncSetAttribute(pixel_bgr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            pixel_bgr_kernel<false><<<(unsigned)grid, NT, smem, st>>>(p);
+        }
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    }
+
+    // ---- Bayer
+    BayerSite site;
+    {
+        // colour sampled at (y&1, x&1) for the Daheng layouts (0=B,1=G,2=R)
+        int ch[2][2];
+        switch (L.bayer_layout) {
+            case RMCV_BAYER_BG: ch[0][0] = 0; ch[0][1] = 1; ch[1][0] = 1; ch[1][1] = 2; break;
+            case RMCV_BAYER_GB: ch[0][0] = 1; ch[0][1] = 0; ch[1][0] = 2; ch[1][1] = 1; break;
+            case RMCV_BAYER_GR: ch[0][0] = 1; ch[0][1] = 2; ch[1][0] = 0; ch[1][1] = 1; break;
+            case RMCV_BAYER_RG: ch[0][0] = 2; ch[0][1] = 1; ch[1][0] = 1; ch[1][1] = 0; break;
+            default: return cudaErrorInvalidValue;
+        }
+        int a, b;
+        if (L.target == RMCV_CAMP_GUIDELIGHT) { a = 1; b = 2; }
+        else if (L.target == RMCV_CAMP_BLUE) { a = 0; b = 2; }
+        else { a = 2; b = 0; }
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                auto mode = [&](int c) -> uint8_t {
+                    int s = ch[py][px];
+                    if (s == c) return 0;
+                    if (c == 1) return 4;                     // green at a red/blue site: plus neighbours
+                    if (s == 1) return ch[py][px ^ 1] == c ? 1 : 2;  // at a green site: row or column pair
+                    return 3;                                 // opposite colour: diagonals
+                };
+                site.plus[py][px] = mode(a);
+                site.minus[py][px] = mode(b);
+            }
+    }
+    p.bayer = 1;
+    p.gpr = p.WB;
+    p.srow = (L.W + 15) & ~15;
+    if ((L.W & 15) == 0) p.srow = L.W;
+    p.contiguous = 0;
+    int NT = env_int("RMCV_PIX_NT", 256);
+    if (L.W < 3 || L.H < 3) return cudaErrorInvalidValue;
+    size_t raw_bytes = ((size_t)(BH + 8) * p.srow + 15) & ~(size_t)15;
+    size_t smem = raw_bytes + 16 + (size_t)(BH + 4) * (p.WB + 2) * 4 + (size_t)(BH + 2) * (p.WB + 2) * 4;
+    while (smem > (size_t)max_smem && p.BH > 1) {
+        p.BH = max(1, p.BH / 2); BH = p.BH;
+        p.bands = (L.H + BH - 1) / BH;
+        raw_bytes = ((size_t)(BH + 8) * p.srow + 15) & ~(size_t)15;
+        smem = raw_bytes + 16 + (size_t)(BH + 4) * (p.WB + 2) * 4 + (size_t)(BH + 2) * (p.WB + 2) * 4;
+    }
+    const long long grid2 = (long long)L.batch * p.bands;
+    cudaError_t e = cudaFuncSetAttribute(pixel_bayer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pixel_bayer_kernel<<<(unsigned)grid2, NT, smem, st>>>(p, site);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace rmcv

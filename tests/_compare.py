@@ -1,0 +1,191 @@
+"""Comparison of the GPU path's results with the oracle's, with the tolerances of SURVEY.md §8(c).
+
+Bit-exact: mask bytes, contour count, per-contour first pixel / point count / 2*area / bbox, ordered contour points,
+label map.  Float: ellipse centre <= 1e-3 px, axes <= 1e-5 relative (+1e-4 px), angle <= 1e-3 deg (mod 180, not
+compared for near-isotropic blobs); light-blob and armour vertices <= 2e-3 px; gate values <= 1e-3.
+Carve-outs (counted, returned in the report):
+  * `rng_band`: contours whose first direct-fit |det M| lies in [0.7e-10, 1e-10*(1+1e-6)]: cv::fitEllipseDirect
+    itself is non-deterministic there (jittered retry from the global RNG) -> loose tolerance
+    0.5 px / 0.5 % / 0.1 deg and no exact gate membership;
+  * `near_gate`: contours / pairs whose gate quantity is within tolerance of its threshold.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from oracle import rm_oracle as O
+
+TOL_CENTRE = 1e-3
+TOL_AXIS_REL = 1e-5
+TOL_AXIS_ABS = 1e-4
+TOL_ANGLE = 1e-3
+TOL_VERT = 2e-3
+TOL_GATE = 1e-3
+LOOSE = dict(centre=0.5, rel=5e-3, angle=0.1, vert=1.0)
+
+
+@dataclass
+class Report:
+    frames: int = 0
+    contours: int = 0
+    fitted: int = 0
+    direct: int = 0
+    fallback: int = 0
+    rng_band: int = 0
+    near_gate: int = 0
+    blobs: int = 0
+    armours: int = 0
+    worst_centre: float = 0.0
+    worst_axis_rel: float = 0.0
+    worst_angle: float = 0.0
+    worst_vertex: float = 0.0
+    notes: list = field(default_factory=list)
+
+    def merge(self, o: "Report"):
+        for k in ("frames", "contours", "fitted", "direct", "fallback", "rng_band", "near_gate", "blobs", "armours"):
+            setattr(self, k, getattr(self, k) + getattr(o, k))
+        for k in ("worst_centre", "worst_axis_rel", "worst_angle", "worst_vertex"):
+            setattr(self, k, max(getattr(self, k), getattr(o, k)))
+        self.notes += o.notes
+
+
+def angle_diff(a, b):
+    return abs(((a - b) + 90.0) % 180.0 - 90.0)
+
+
+def in_rng_band(det0: float) -> bool:
+    return 0.7e-10 <= det0 <= 1.0e-10 * (1 + 1e-6)
+
+
+def near_blob_gate(v: O.ContourVerdict, params) -> bool:
+    """Is the oracle's decision for this contour within float tolerance of flipping?"""
+    if v.status == O.STATUS_SKIPPED:
+        return False
+    r, t = v.ratio, v.tilt
+    rel = 1e-5
+    return (abs(r - params["ratio_range"][0]) <= rel * max(1, abs(r)) or abs(r - params["ratio_range"][1]) <= rel * max(1, abs(r))
+            or abs(t - params["tilt_max"]) <= TOL_ANGLE)
+
+
+def compare_frame(det, ref: O.FrameResult, params, where="") -> Report:
+    """det: rmcv_b200.FrameDetections; ref: oracle FrameResult."""
+    rep = Report(frames=1)
+    assert det.flags == 0, f"{where}: overflow flags {det.flags}"
+    assert len(det.contours) == len(ref.contours), f"{where}: contour count {len(det.contours)} != {len(ref.contours)}"
+    rep.contours = len(ref.contours)
+    loose_blob = {}   # oracle positive index -> loose?
+    flips = 0
+    pos_idx = 0
+    for k, (c, rc, v) in enumerate(zip(det.contours, ref.contours, ref.verdicts)):
+        w = f"{where} contour {k}"
+        assert c.first == (int(rc[0][0]), int(rc[0][1])), f"{w}: first pixel {c.first} != {tuple(rc[0])}"
+        assert c.n_points == v.n, f"{w}: n_points {c.n_points} != {v.n}"
+        assert c.area2 == int(round(2 * v.area)), f"{w}: area2 {c.area2} != {2 * v.area}"
+        xs, ys = rc[:, 0], rc[:, 1]
+        assert c.bbox == (int(xs.min()), int(ys.min()), int(xs.max() - xs.min() + 1), int(ys.max() - ys.min() + 1)), f"{w}: bbox"
+        if v.status == O.STATUS_SKIPPED:
+            assert c.status == 0, f"{w}: status {c.status} for a skipped contour"
+            continue
+        assert c.status != 0, f"{w}: GPU skipped a contour the oracle fitted"
+        rep.fitted += 1
+        band = in_rng_band(c.det0)
+        rep.rng_band += band
+        if c.fit_branch == 1:
+            rep.direct += 1
+        else:
+            rep.fallback += 1
+        e = v.ellipse
+        cx, cy, ew, eh, ea = c.ellipse
+        dc = max(abs(cx - e.cx), abs(cy - e.cy))
+        ds = max(abs(ew - e.w) / max(e.w, 1e-9), abs(eh - e.h) / max(e.h, 1e-9))
+        da = angle_diff(ea, e.angle) if e.h / max(e.w, 1e-9) >= 1 + 1e-4 else 0.0
+        if band:
+            assert dc <= LOOSE["centre"] and ds <= LOOSE["rel"] and da <= LOOSE["angle"], f"{w}: rng-band ellipse off: {c.ellipse} vs {e}"
+        else:
+            # tolerance floor: one fp32 ulp of the coordinate
+            ulp = float(np.spacing(np.float32(max(abs(e.cx), abs(e.cy), 1.0))))
+            assert dc <= max(TOL_CENTRE, 2 * ulp), f"{w}: centre off by {dc}: {c.ellipse} vs {e} det0={c.det0} branch={c.fit_branch}"
+            assert ds <= TOL_AXIS_REL + TOL_AXIS_ABS / max(e.w, 1e-9), f"{w}: axes off by {ds}: {c.ellipse} vs {e} det0={c.det0}"
+            assert da <= TOL_ANGLE, f"{w}: angle off by {da}: {c.ellipse} vs {e}"
+            rep.worst_centre = max(rep.worst_centre, dc)
+            rep.worst_axis_rel = max(rep.worst_axis_rel, ds)
+            rep.worst_angle = max(rep.worst_angle, da)
+        if c.status != v.status:
+            if band or near_blob_gate(v, params):
+                flips += 1
+                rep.near_gate += 1
+            else:
+                raise AssertionError(f"{w}: status {c.status} != oracle {v.status} (ratio {v.ratio}, tilt {v.tilt})")
+        if v.status == O.STATUS_POSITIVE:
+            loose_blob[pos_idx] = band
+            pos_idx += 1
+    if flips:
+        rep.notes.append(f"{where}: {flips} gate flips inside tolerance; blob/armour lists not compared")
+        return rep
+    # ---- light blobs
+    assert len(det.positive) == len(ref.positive), f"{where}: positive count"
+    assert det.n_negative == len(ref.negative), f"{where}: negative count"
+    rep.blobs = len(ref.positive)
+    for k, (b, rb) in enumerate(zip(det.positive, ref.positive)):
+        w = f"{where} blob {k}"
+        tol = LOOSE["vert"] if loose_blob.get(k) else TOL_VERT
+        assert b.target == rb.target
+        assert angle_diff(b.angle, rb.angle) <= (LOOSE["angle"] if loose_blob.get(k) else TOL_ANGLE), f"{w}: angle"
+        dv = float(np.max(np.abs(b.vertices - rb.vertices)))
+        assert dv <= tol, f"{w}: vertices off by {dv}\n{b.vertices}\n{rb.vertices}"
+        assert abs(b.size[0] - rb.size[0]) <= tol and abs(b.size[1] - rb.size[1]) <= tol, f"{w}: size"
+        if not loose_blob.get(k):
+            rep.worst_vertex = max(rep.worst_vertex, dv)
+    # ---- armours
+    ref_pairs = [(a.i, a.j) for a in ref.armours]
+    det_pairs = [(a.i, a.j) for a in det.armours]
+    if ref_pairs != det_pairs:
+        # allow differences only for pairs that sit on a gate threshold or involve a loose blob
+        diff = set(ref_pairs) ^ set(det_pairs)
+        for (i, j) in diff:
+            g = O.pair_gates(ref.positive[i], ref.positive[j])
+            near = (loose_blob.get(i) or loose_blob.get(j) or _near_pair_gate(g, params))
+            assert near, f"{where}: armour pair ({i},{j}) membership differs: gates {g}"
+            rep.near_gate += 1
+        rep.notes.append(f"{where}: {len(diff)} armour pairs differ inside tolerance")
+        common = [p for p in ref_pairs if p in set(det_pairs)]
+    else:
+        common = ref_pairs
+    rmap = {(a.i, a.j): a for a in ref.armours}
+    dmap = {(a.i, a.j): a for a in det.armours}
+    assert det_pairs == sorted(det_pairs), f"{where}: armours not in lexicographic (i,j) order"
+    rep.armours = len(common)
+    for p in common:
+        a, ra = dmap[p], rmap[p]
+        loose = loose_blob.get(p[0]) or loose_blob.get(p[1])
+        tol = LOOSE["vert"] * 2 if loose else TOL_VERT
+        assert float(np.max(np.abs(a.icon - ra.icon))) <= tol, f"{where}: armour {p} icon\n{a.icon}\n{ra.icon}"
+        assert float(np.max(np.abs(a.vertices - ra.vertices))) <= tol, f"{where}: armour {p} vertices"
+        if not loose:
+            for q in range(6):
+                assert abs(a.gates[q] - ra.gates[q]) <= TOL_GATE, f"{where}: armour {p} gate {q}: {a.gates} vs {ra.gates}"
+            # bounding box = floor of icon extents: exact unless an icon coordinate sits on an integer
+            if a.bounding_box != ra.bounding_box:
+                ic = ra.icon
+                near_int = np.min(np.abs(ic - np.round(ic))) <= TOL_VERT
+                assert near_int, f"{where}: armour {p} bounding_box {a.bounding_box} != {ra.bounding_box}"
+    return rep
+
+
+def _near_pair_gate(g, params) -> bool:
+    ad, si, sj, ratio, dy, dx, hsum = g
+    t = TOL_GATE
+    return (abs(ad - params["angle_difference_max"]) <= t or abs(si - params["shear_max"]) <= t or
+            abs(sj - params["shear_max"]) <= t or abs(ratio - params["lenght_ratio_max"]) <= 1e-5 or
+            abs(dy - hsum / 2) <= t or abs(dx - hsum * 2) <= t)
+
+
+def oracle_params(p=None):
+    from rmcv_b200 import synth
+    d = dict(synth.MAIN_PARAMS)
+    if p:
+        d.update(p)
+    return d

@@ -1,0 +1,48 @@
+// TEST INFRASTRUCTURE ONLY — never linked into librmcv_b200.so.
+// Compiles rmcv_b200/csrc/blob_math.cuh (the per-blob / per-pair device arithmetic) for the host so that the
+// numerics can be checked against the cv2 oracle in a GPU-less container (tests/test_hostmath.py).
+#include <cstring>
+#include "../../rmcv_b200/csrc/blob_math.cuh"
+
+using namespace rmcv;
+
+extern "C" {
+
+// Mirrors what the blob kernel does with a contour point multiset: mean, L1 spread, centred moments, direct fit,
+// fallback fit with float centring.  Returns the RMCV_FIT_* branch.
+int hm_fit_points(const int32_t* xy, int n, rmcv_rotated_rect* box, double* det0) {
+    double sx = 0, sy = 0;
+    for (int i = 0; i < n; ++i) { sx += xy[2 * i]; sy += xy[2 * i + 1]; }
+    const double cx = sx / n, cy = sy / n;
+    Moments m; moments_zero(m);
+    double s = 0;
+    for (int i = 0; i < n; ++i) {
+        const double dx = xy[2 * i] - cx, dy = xy[2 * i + 1] - cy;
+        s += fabs(dx) + fabs(dy);
+        moments_add(m, dx, dy);
+    }
+    double scale = 100.0 / (s > RMCV_FLT_EPSILON ? s : RMCV_FLT_EPSILON);
+    if (direct_fit(m, scale, cx, cy, box, det0)) return RMCV_FIT_DIRECT;
+    const float c32x = (float)sx / (float)n, c32y = (float)sy / (float)n;  // exact while sums < 2^24
+    moments_zero(m);
+    double s2 = 0;
+    for (int i = 0; i < n; ++i) {
+        const float fx = fsub((float)xy[2 * i], c32x), fy = fsub((float)xy[2 * i + 1], c32y);
+        s2 += (double)fadd(fabsf(fx), fabsf(fy));
+        moments_add(m, (double)fx, (double)fy);
+    }
+    scale = 100.0 / (s2 > RMCV_FLT_EPSILON ? s2 : RMCV_FLT_EPSILON);
+    nodirect_fit(m, scale, c32x, c32y, box);
+    return RMCV_FIT_FALLBACK;
+}
+
+void hm_make_lightblob(const rmcv_rotated_rect* box, int target, rmcv_lightblob* out) { make_lightblob(*box, target, out); }
+int hm_blob_gates(const rmcv_rotated_rect* e, const rmcv_params* p) { return blob_gates(*e, *p); }
+int hm_pair_gates(const rmcv_lightblob* a, const rmcv_lightblob* b, const rmcv_params* p, float* gates) {
+    return pair_gates(*a, *b, *p, gates) ? 1 : 0;
+}
+void hm_make_armour(const rmcv_lightblob* a, const rmcv_lightblob* b, rmcv_armour* out) {
+    memset(out, 0, sizeof(*out));
+    make_armour(*a, *b, out);
+}
+}

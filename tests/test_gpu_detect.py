@@ -1,0 +1,250 @@
+"""GPU parity of the whole path (extract_color -> filter_lightblobs -> filter_armours, executable/main.cpp:172-176)
+through the C ABI against the cv2 oracle: masks / contour discovery / contour statistics bit-exact, ellipse, light-blob
+and armour geometry within the tolerances of tests/_compare.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import rmcv_b200 as rb
+from oracle import rm_oracle as O
+from rmcv_b200 import synth
+from tests import _compare as CMP
+
+pytestmark = pytest.mark.gpu
+PRM = CMP.oracle_params()
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def oracle_kwargs(p):
+    return dict(target=p["target"], lower_bound=p["lower_bound"], tilt_max=p["tilt_max"], ratio_range=p["ratio_range"],
+                area_range=p["area_range"], angle_difference_max=p["angle_difference_max"], shear_max=p["shear_max"],
+                lenght_ratio_max=p["lenght_ratio_max"])
+
+
+def c_params(p):
+    return rb.default_params(target=p["target"], lower_bound=p["lower_bound"], tilt_max=p["tilt_max"], ratio_range=p["ratio_range"],
+                             area_range=p["area_range"], angle_difference_max=p["angle_difference_max"], shear_max=p["shear_max"],
+                             lenght_ratio_max=p["lenght_ratio_max"])
+
+
+def detect_and_compare(ctx, frames, p=PRM, check_points=True, check_labels=True, what=""):
+    B, H, W, _ = frames.shape
+    masks = np.empty((B, H, W), np.uint8)
+    res = ctx.detect_batch_host(frames, c_params(p), masks)
+    total = CMP.Report()
+    for f in range(B):
+        ref = O.detect_frame(frames[f], **oracle_kwargs(p))
+        bad = np.argwhere(masks[f] != ref.binary)
+        assert bad.size == 0, f"{what} frame {f}: {len(bad)} mask bytes differ"
+        det = ctx.frame_detections(res, f)
+        total.merge(CMP.compare_frame(det, ref, p, where=f"{what} frame {f}"))
+        resident = (f // ctx.cfg.chunk_frames if ctx.cfg.chunk_frames else 0)
+        if check_points:
+            try:
+                for k, rc in enumerate(ref.contours):
+                    pts = ctx.get_contour(f, k)
+                    assert np.array_equal(pts, rc), f"{what} frame {f} contour {k}: ordered points differ"
+            except rb.RmcvError as e:
+                assert e.status == rb.abi.RMCV_ERR_STATE
+        if check_labels:
+            try:
+                lab = ctx.get_label_map(f, W, H)
+                assert np.array_equal(lab, O.blob_label_map(ref.binary, ref.contours)), f"{what} frame {f}: label map (blob pixel sets) differs"
+            except rb.RmcvError as e:
+                assert e.status == rb.abi.RMCV_ERR_STATE
+    return total
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    with rb.Context(max_width=1280, max_height=1024, max_batch=16) as c:
+        yield c
+
+
+def mask_to_bgr(mask: np.ndarray) -> np.ndarray:
+    """BGR frame whose blue-minus-red difference is 200 on the mask (the 3x3 close still applies on both sides)."""
+    img = np.zeros(mask.shape + (3,), np.uint8)
+    img[..., 0] = np.where(mask, 200, 0)
+    return img
+
+
+def test_config1_single_frame(ctx):
+    """BASELINE config 1: seed 1, 8 plates, blue."""
+    frame = synth.make_frame(1, 1280, 1024, 8, blue=True)
+    rep = detect_and_compare(ctx, frame[None], what="config1")
+    assert rep.contours >= 16 and rep.blobs >= 16 and rep.armours >= 8
+
+
+def test_synthetic_batch_blue_and_red(ctx):
+    seeds = list(range(10, 22))
+    frames = np.stack([synth.make_frame(s, 1280, 1024, synth.plates_for_seed(s), blue=True) for s in seeds])
+    rep = detect_and_compare(ctx, frames, what="blue batch")
+    assert rep.direct > 0 and rep.fallback > 0, "both fitEllipseDirect branches must be exercised"
+    red = np.stack([synth.make_frame(s, 1280, 1024, synth.plates_for_seed(s), blue=False) for s in seeds[:4]])
+    p = CMP.oracle_params(dict(target=rb.CAMP_RED))
+    rep2 = detect_and_compare(ctx, red, p, what="red batch")
+    rep.merge(rep2)
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "parity_report.json"), "w") as fh:
+        json.dump({k: v for k, v in rep.__dict__.items()}, fh, indent=1)
+    assert rep.rng_band <= 0.05 * max(rep.fitted, 1)
+
+
+MICRO = {
+    "square3": (np.pad(np.ones((3, 3), bool), 3), 8, 8),            # 3x3 square -> 8 points, area 4 -> area2 8
+    "line5": (np.pad(np.ones((5, 1), bool), 3), 8, 0),              # 1x5 line -> 8 points (revisits), area 0
+    "pixel": (np.pad(np.ones((1, 1), bool), 3), 1, 0),
+    "diag3": (np.pad(np.eye(3, dtype=bool), 3), 4, 0),
+    "bar2x8": (np.pad(np.ones((2, 8), bool), 3), 16, 14),           # n=16, area 7
+}
+
+
+@pytest.mark.parametrize("name", sorted(MICRO))
+def test_micro_masks_known_answers(ctx, name):
+    """Hand-checkable masks.  They are built so that the 3x3 close leaves them unchanged."""
+    mask, n, area2 = MICRO[name]
+    frame = mask_to_bgr(mask)
+    ref = O.detect_frame(frame)
+    assert np.array_equal(ref.binary > 0, mask), "micro mask changed by the close; pick another"
+    p = c_params(PRM)
+    res = ctx.detect_batch_host(frame[None], p)
+    det = ctx.frame_detections(res, 0)
+    assert len(det.contours) == 1
+    assert det.contours[0].n_points == n and det.contours[0].area2 == area2
+    assert np.array_equal(ctx.get_contour(0, 0), ref.contours[0])
+
+
+def test_ring_with_nested_dot_and_corner_pixels(ctx):
+    m = np.zeros((24, 24), bool)
+    yy, xx = np.mgrid[0:24, 0:24]
+    r2 = (yy - 12) ** 2 + (xx - 12) ** 2
+    m[(r2 <= 81) & (r2 >= 36)] = True   # ring
+    m[11:14, 11:14] = True              # nested dot (must not be reported)
+    m[0, 0] = True; m[23, 23] = True    # corner pixels
+    frame = mask_to_bgr(m)
+    ref = O.detect_frame(frame)
+    assert len(ref.contours) == 3
+    rep = detect_and_compare(ctx, frame[None], what="ring")
+    assert rep.contours == 3
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_masks(ctx, seed):
+    """Random masks of random density incl. holes, nesting, border contact, thin parts (findContours semantics)."""
+    rng = np.random.default_rng(1000 + seed)
+    H, W = int(rng.integers(8, 90)), int(rng.integers(8, 140))
+    dens = rng.uniform(0.15, 0.75)
+    m = rng.random((H, W)) < dens
+    if seed % 3 == 1:   # blobby: smooth the noise so that components are large and have holes
+        import cv2
+        m = cv2.GaussianBlur(m.astype(np.float32), (0, 0), 2.0) > dens * 0.9
+    # wide area range so that small blobs are fitted too (degenerate fits are compared only when finite)
+    p = CMP.oracle_params(dict(area_range=(10.0, 99999.0)))
+    detect_and_compare(ctx, mask_to_bgr(m)[None], p, what=f"random {seed} {W}x{H}")
+
+
+def test_nested_levels(ctx):
+    """Component inside a hole inside a component inside a hole ...: only the outermost is external."""
+    m = np.zeros((60, 60), bool)
+    for k, r in enumerate(range(28, 2, -4)):
+        m[30 - r:30 + r, 30 - r:30 + r] = (k % 2 == 0)
+    detect_and_compare(ctx, mask_to_bgr(m)[None], what="nested squares")
+    # spiral / comb shapes whose background is connected to the border through long corridors
+    c = np.zeros((40, 64), bool)
+    c[2:38, 2:62] = True
+    for x in range(6, 60, 6):
+        c[2:30, x:x + 2] = False
+    detect_and_compare(ctx, mask_to_bgr(c)[None], what="comb")
+
+
+def test_multi_chunk_batch_and_device_api():
+    seeds = list(range(40, 51))
+    frames = np.stack([synth.make_frame(s, 640, 480, 5, blue=True) for s in seeds])
+    with rb.Context(max_width=640, max_height=480, max_batch=16, chunk_frames=3) as c:
+        rep = detect_and_compare(c, frames, check_points=True, what="multi-chunk host")
+        # device-resident entry point gives identical results
+        B, H, W, _ = frames.shape
+        d_in = c.device_buffer(frames.nbytes); d_mask = c.device_buffer(B * H * W)
+        d_in.upload(frames)
+        c.detect_batch(d_in.ptr, W, H, B, c_params(PRM), d_mask.ptr)
+        res = c.fetch_results()
+        masks = d_mask.download((B, H, W))
+        for f in range(B):
+            ref = O.detect_frame(frames[f])
+            assert np.array_equal(masks[f], ref.binary)
+            CMP.compare_frame(c.frame_detections(res, f), ref, PRM, where=f"device api frame {f}")
+        d_in.free(); d_mask.free()
+
+
+def test_standalone_filter_lightblobs_and_armours(ctx):
+    """rm::filter_lightblobs / rm::filter_armours on caller-supplied inputs (the reference's stage boundaries)."""
+    frame = synth.make_frame(3, 1280, 1024, 14)
+    ref = O.detect_frame(frame)
+    pos, neg = rb.filter_lightblobs(ref.contours, 70, (1.5, 80), (10, 99999), rb.CAMP_BLUE)
+    assert len(pos) == len(ref.positive) and len(neg) == len(ref.negative)
+    infos, _ = ctx.filter_lightblobs_raw(ref.contours, c_params(PRM))
+    pinfo = [i for i in infos if i.status == rb.CONTOUR_POSITIVE]
+    for b, rbk, inf in zip(pos, ref.positive, pinfo):
+        tol = CMP.LOOSE["vert"] if CMP.in_rng_band(inf.det0) else CMP.TOL_VERT
+        assert float(np.max(np.abs(b.vertices - rbk.vertices))) <= tol
+    for inf, v, rc in zip(infos, ref.verdicts, ref.contours):
+        assert inf.n_points == v.n and inf.area2 == int(round(2 * v.area)) and inf.first == (int(rc[0][0]), int(rc[0][1]))
+    for a, b in zip(neg, ref.negative):
+        assert np.array_equal(a, b)
+    # armours from the ORACLE's light blobs: identical inputs -> gates and geometry must agree to fp32 rounding
+    opos = [rb.LightBlob(b.angle, b.target, b.center, b.vertices, b.size) for b in ref.positive]
+    arm = rb.filter_armours(opos, 12, 22, 0.4, rb.CAMP_BLUE)
+    assert [(a.i, a.j) for a in arm] == [(a.i, a.j) for a in ref.armours]
+    for a, ra in zip(arm, ref.armours):
+        assert float(np.max(np.abs(a.icon - ra.icon))) <= 1e-4
+        assert float(np.max(np.abs(a.vertices - ra.vertices))) <= 1e-4
+        assert a.bounding_box == ra.bounding_box
+    # lightblob ctor from oracle ellipses: exact
+    boxes = [(v.ellipse.cx, v.ellipse.cy, v.ellipse.w, v.ellipse.h, v.ellipse.angle) for v in ref.verdicts if v.status == 1]
+    made = ctx.make_lightblobs(boxes, rb.CAMP_BLUE)
+    for b, rbk in zip(made, ref.positive):
+        assert np.array_equal(b.vertices, rbk.vertices) and b.angle == np.float32(rbk.angle) and b.size == rbk.size
+    # degenerate inputs of the reference (src/objdetect.cpp:120, :64)
+    assert rb.filter_armours(opos[:1], 12, 22, 0.4, rb.CAMP_BLUE) == []
+    assert rb.filter_lightblobs([], 70, (1.5, 80), (10, 99999), rb.CAMP_BLUE) == ([], [])
+    p2, n2 = rb.filter_lightblobs([np.array([[1, 1], [2, 1], [2, 2]], np.int32)], 70, (1.5, 80), (10, 99999), rb.CAMP_BLUE)
+    assert p2 == [] and n2 == []
+
+
+def test_rm_mirror_call_site(ctx):
+    """The reference's call site (executable/main.cpp:172-176) written against the mirror API."""
+    frame = synth.make_frame(8, 1280, 1024, 6)
+    contours, binary = rb.extract_color(frame, rb.CAMP_BLUE, 80)
+    positive, negative = rb.filter_lightblobs(contours, 70, (1.5, 80), (10, 99999), rb.CAMP_BLUE)
+    armours = rb.filter_armours(positive, 12, 22, 0.4, rb.CAMP_BLUE)
+    ref = O.detect_frame(frame)
+    assert np.array_equal(binary, ref.binary)
+    assert len(contours) == len(ref.contours) and all(np.array_equal(a, b) for a, b in zip(contours, ref.contours))
+    assert len(positive) == len(ref.positive) and len(negative) == len(ref.negative)
+    assert [(a.i, a.j) for a in armours] == [(a.i, a.j) for a in ref.armours]
+
+
+def test_capacity_overflow_is_reported():
+    frame = synth.make_frame(1, 640, 480, 6)
+    with rb.Context(max_width=640, max_height=480, max_batch=1, max_blobs_per_frame=4) as c:
+        with pytest.raises(rb.RmcvError) as ei:
+            c.detect_batch_host(frame[None], rb.default_params())
+        assert ei.value.status == rb.abi.RMCV_ERR_CAPACITY
+    with rb.Context(max_width=640, max_height=480, max_batch=1, max_runs_per_frame=16) as c:
+        with pytest.raises(rb.RmcvError) as ei:
+            c.detect_batch_host(frame[None], rb.default_params())
+        assert ei.value.status == rb.abi.RMCV_ERR_CAPACITY
+
+
+def test_hole_plane_invariant_and_repeatability(ctx):
+    """Frames with holes (annulus) processed twice give identical results (the hole plane is restored to zero)."""
+    frames = np.stack([synth.make_frame(s, 1280, 1024, 6) for s in (60, 61)])
+    a = ctx.detect_batch_host(frames, rb.default_params())
+    first = [(ctx.frame_detections(a, f)) for f in range(2)]
+    b = ctx.detect_batch_host(frames, rb.default_params())
+    second = [(ctx.frame_detections(b, f)) for f in range(2)]
+    for x, y in zip(first, second):
+        assert [c.__dict__ for c in x.contours] == [c.__dict__ for c in y.contours]
+        assert len(x.armours) == len(y.armours)

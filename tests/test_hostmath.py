@@ -1,0 +1,94 @@
+"""CPU: the per-blob / per-pair device arithmetic (rmcv_b200/csrc/blob_math.cuh) compiled for the host by
+tests/hostmath (test infrastructure, never part of the product library) against the cv2 oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import rm_oracle as O
+from rmcv_b200 import _abi as A
+from rmcv_b200 import synth
+
+LIB = os.path.join(os.path.dirname(__file__), "hostmath", "libhostmath.so")
+
+
+@pytest.fixture(scope="module")
+def hm():
+    return C.CDLL(LIB)
+
+
+def fit(hm, c):
+    xy = np.ascontiguousarray(c, np.int32)
+    box, det = A.RotatedRect(), C.c_double()
+    br = hm.hm_fit_points(xy.ctypes.data_as(C.c_void_p), len(xy), C.byref(box), C.byref(det))
+    return br, box, det.value
+
+
+def test_ellipse_lightblob_armour_math_matches_oracle(hm):
+    P = A.Params(1, 80, 70, 1.5, 80, 10, 99999, 12, 22, 0.4)
+    branches = {1: 0, 2: 0}
+    n_arm = 0
+    for seed in range(8):
+        img = synth.make_frame(seed, 1280, 1024, synth.plates_for_seed(seed))
+        fr = O.detect_frame(img)
+        blobs = []
+        for c, v in zip(fr.contours, fr.verdicts):
+            if v.status == 0:
+                continue
+            br, box, det = fit(hm, c)
+            branches[br] += 1
+            e = v.ellipse
+            if not (0.7e-10 <= det <= 1.0e-10 * (1 + 1e-6)):
+                assert max(abs(box.cx - e.cx), abs(box.cy - e.cy)) <= 1e-3
+                assert max(abs(box.w - e.w) / e.w, abs(box.h - e.h) / e.h) <= 1e-5
+                if e.h / e.w > 1.0001:
+                    assert abs(((box.angle - e.angle) + 90) % 180 - 90) <= 1e-3
+            rr = A.RotatedRect(e.cx, e.cy, e.w, e.h, e.angle)
+            assert hm.hm_blob_gates(C.byref(rr), C.byref(P)) == v.status
+            if v.status == 1:
+                ob = O.make_lightblob(e, 1)
+                lb = A.LightBlob()
+                hm.hm_make_lightblob(C.byref(rr), 1, C.byref(lb))
+                vv = np.array([[lb.vertices[i][0], lb.vertices[i][1]] for i in range(4)], np.float32)
+                assert np.array_equal(vv, ob.vertices) and lb.angle == np.float32(ob.angle)
+                assert (lb.size[0], lb.size[1]) == (np.float32(ob.size[0]), np.float32(ob.size[1]))
+                blobs.append((ob, lb))
+        oa = {(a.i, a.j): a for a in fr.armours}
+        for i in range(len(blobs)):
+            for j in range(i + 1, len(blobs)):
+                g = (C.c_float * 6)()
+                ok = hm.hm_pair_gates(C.byref(blobs[i][1]), C.byref(blobs[j][1]), C.byref(P), g)
+                assert bool(ok) == ((i, j) in oa)
+                og = O.pair_gates(blobs[i][0], blobs[j][0])
+                assert all(np.float32(g[k]) == np.float32(og[k]) for k in range(6))
+                if ok:
+                    n_arm += 1
+                    ar = A.Armour()
+                    hm.hm_make_armour(C.byref(blobs[i][1]), C.byref(blobs[j][1]), C.byref(ar))
+                    a = oa[(i, j)]
+                    ic = np.array([[ar.icon[k][0], ar.icon[k][1]] for k in range(4)], np.float32)
+                    ve = np.array([[ar.vertices[k][0], ar.vertices[k][1]] for k in range(4)], np.float32)
+                    assert np.array_equal(ic, a.icon) and np.array_equal(ve, a.vertices) and tuple(ar.bounding_box) == a.bounding_box
+    assert branches[1] > 50 and branches[2] > 5 and n_arm > 50
+
+
+def test_extend_cord_special_cases(hm):
+    """Vertical / horizontal cords take the exact branches of rm::utils::ExtendCord (src/core.cpp:298-331)."""
+    def blob(cx, verts):
+        b = A.LightBlob()
+        b.angle, b.target = 90.0, 1
+        b.center[0], b.center[1] = cx, 50.0
+        for i, (x, y) in enumerate(verts):
+            b.vertices[i][0], b.vertices[i][1] = x, y
+        b.size[0], b.size[1] = 10.0, 40.0
+        return b
+    L = blob(10.0, [(5, 70), (5, 30), (15, 30), (15, 70)])
+    Rr = blob(110.0, [(105, 70), (105, 30), (115, 30), (115, 70)])
+    ar = A.Armour()
+    hm.hm_make_armour(C.byref(L), C.byref(Rr), C.byref(ar))
+    ol = O.LightBlob(90.0, 1, (10.0, 50.0), np.array([(5, 70), (5, 30), (15, 30), (15, 70)], np.float32), (10.0, 40.0))
+    orr = O.LightBlob(90.0, 1, (110.0, 50.0), np.array([(105, 70), (105, 30), (115, 30), (115, 70)], np.float32), (10.0, 40.0))
+    a = O.make_armour(ol, orr)
+    ic = np.array([[ar.icon[k][0], ar.icon[k][1]] for k in range(4)], np.float32)
+    assert np.array_equal(ic, a.icon) and tuple(ar.bounding_box) == a.bounding_box

@@ -1,0 +1,216 @@
+"""CPU: pins the oracle.  (i) hand-checkable micro-masks and OpenCV semantics the restatement relies on,
+(ii) the order-free numpy restatements (the executable spec of the CUDA kernels) against cv2, (iii) golden fixtures."""
+import json
+import glob
+import os
+import zlib
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import cv_restate as R
+from oracle import rm_oracle as O
+from rmcv_b200 import synth
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.json")))
+
+
+def bgr_of(mask):
+    img = np.zeros(mask.shape + (3,), np.uint8)
+    img[..., 0] = np.where(mask, 200, 0)
+    return img
+
+
+def test_pixel_op_semantics():
+    # A.1: saturating subtract, inclusive inRange, all-ones 3x3 kernel
+    assert cv2.subtract(np.array([[10, 200, 0]], np.uint8), np.array([[20, 50, 0]], np.uint8)).tolist() == [[0, 150, 0]]
+    assert cv2.inRange(np.array([[79, 80, 81, 255]], np.uint8), 80, 255).tolist() == [[0, 255, 255, 255]]
+    assert cv2.getStructuringElement(cv2.MORPH_RECT, (3, 3)).min() == 1
+    assert O.channel_pair(O.CAMP_BLUE) == (0, 2) and O.channel_pair(O.CAMP_RED) == (2, 0)
+    assert O.channel_pair(O.CAMP_GUIDELIGHT) == (1, 2) and O.channel_pair(O.CAMP_NEUTRAL) == (2, 0)
+
+
+def test_close_rule_matches_morphologyex():
+    rng = np.random.default_rng(0)
+    for i in range(20):
+        t = rng.random((int(rng.integers(1, 40)), int(rng.integers(1, 60)))) < rng.uniform(0.1, 0.8)
+        m = cv2.morphologyEx((t * 255).astype(np.uint8), cv2.MORPH_CLOSE, cv2.getStructuringElement(cv2.MORPH_RECT, (3, 3)))
+        assert np.array_equal(m > 0, R.close3x3(t))
+
+
+def test_extract_color_mask_restatement():
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (50, 70, 3), dtype=np.uint8)
+    for target, lb in ((1, 80), (0, 30), (2, 10), (-1, 200), (1, 0), (1, 256)):
+        a, b = O.channel_pair(target)
+        ref = O.extract_color_mask(img, target, lb)
+        assert np.array_equal(ref > 0, R.close3x3(R.threshold_bits(img, a, b, lb)))
+
+
+MICRO = [  # mask, expected contour (cv2 order), contourArea
+    (np.pad(np.ones((3, 3), bool), 2), [(2, 2), (2, 3), (2, 4), (3, 4), (4, 4), (4, 3), (4, 2), (3, 2)], 4.0),
+    (np.pad(np.ones((5, 1), bool), 2), [(2, 2), (2, 3), (2, 4), (2, 5), (2, 6), (2, 5), (2, 4), (2, 3)], 0.0),
+    (np.pad(np.ones((1, 1), bool), 2), [(2, 2)], 0.0),
+    (np.pad(np.eye(3, dtype=bool), 1), [(1, 1), (2, 2), (3, 3), (2, 2)], 0.0),
+]
+
+
+@pytest.mark.parametrize("case", range(len(MICRO)))
+def test_findcontours_known_answers(case):
+    mask, pts, area = MICRO[case]
+    cs = O.find_external_contours((mask * 255).astype(np.uint8))
+    assert len(cs) == 1 and [tuple(p) for p in cs[0].tolist()] == pts
+    assert cv2.contourArea(cs[0].reshape(-1, 1, 2)) == area
+    st = R.contour_stats(mask)
+    assert len(st) == 1 and st[0]["n"] == len(pts) and st[0]["area2"] == int(2 * area) and st[0]["first"] == pts[0]
+
+
+def test_external_only_and_reverse_raster_order():
+    m = np.zeros((24, 24), bool)
+    yy, xx = np.mgrid[0:24, 0:24]
+    r2 = (yy - 12) ** 2 + (xx - 12) ** 2
+    m[(r2 <= 81) & (r2 >= 36)] = True
+    m[11:14, 11:14] = True
+    m[0, 0] = True; m[23, 23] = True
+    cs = O.find_external_contours((m * 255).astype(np.uint8))
+    n_cc, _ = cv2.connectedComponents((m * 255).astype(np.uint8), connectivity=8)
+    assert len(cs) == 3 and n_cc - 1 == 4  # the nested dot is a component but not an external contour
+    keys = [c[0][1] * 24 + c[0][0] for c in cs]
+    assert keys == sorted(keys, reverse=True)
+    lab = O.blob_label_map((m * 255).astype(np.uint8), cs)
+    assert lab[12, 12] == -1 and lab[0, 0] == 2 and lab[23, 23] == 0
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_arc_rule_equals_findcontours_on_random_masks(seed):
+    """A.3: the order-free arc rule (the CUDA blob kernel's algorithm) reproduces contour point multisets, sizes, areas."""
+    rng = np.random.default_rng(seed)
+    H, W = rng.integers(6, 48, 2)
+    t = rng.random((H, W)) < rng.uniform(0.15, 0.75)
+    if seed % 3 == 0:
+        t = R.close3x3(t)
+    cs = O.find_external_contours((t * 255).astype(np.uint8))
+    st = R.contour_stats(t)
+    assert len(cs) == len(st)
+    for c, s in zip(cs, st):
+        assert len(c) == s["n"]
+        assert int(round(2 * cv2.contourArea(c.reshape(-1, 1, 2)))) == s["area2"]
+        assert tuple(c[0]) == s["first"] and tuple(cv2.boundingRect(c.reshape(-1, 1, 2))) == s["bbox"]
+        assert sorted(map(tuple, c.tolist())) == sorted(map(tuple, s["points"].tolist()))
+
+
+def test_fit_ellipse_restatement_both_branches():
+    """A.6: moment-sum restatement of fitEllipseDirect (+ fallback) against cv2 on synthetic light bars."""
+    n_direct = n_fallback = 0
+    for seed in range(6):
+        img = synth.make_frame(seed, 1280, 1024, synth.plates_for_seed(seed))
+        cs, _ = O.extract_color(img, 1, 80)
+        for c in cs:
+            if len(c) < 6 or cv2.contourArea(c.reshape(-1, 1, 2)) < 10:
+                continue
+            e = O.fit_ellipse_direct(c)
+            r = R.fit_ellipse_direct(c)
+            if 0.7e-10 <= r["det0"] <= 1.0e-10:
+                continue  # cv2 itself is RNG dependent here
+            n_direct += r["branch"] == "direct"
+            n_fallback += r["branch"] == "fallback"
+            b = r["box"]
+            assert max(abs(b[0] - e.cx), abs(b[1] - e.cy)) <= 1e-3
+            assert max(abs(b[2] - e.w) / e.w, abs(b[3] - e.h) / e.h) <= 1e-5
+            if e.h / e.w > 1.0001:
+                assert abs(((b[4] - e.angle) + 90) % 180 - 90) <= 1e-3
+    assert n_direct > 50 and n_fallback > 5
+
+
+def test_fit_ellipse_direct_is_rng_dependent_only_inside_the_band():
+    """The oracle seeds cv::theRNG() before each fit; outside the band the result does not depend on the seed."""
+    img = synth.make_frame(2, 1280, 1024, 12)
+    cs, _ = O.extract_color(img, 1, 80)
+    for c in cs:
+        if len(c) < 6 or cv2.contourArea(c.reshape(-1, 1, 2)) < 10:
+            continue
+        r = R.fit_ellipse_direct(c)
+        if 0.5e-10 <= r["det0"] <= 1.5e-10:
+            continue
+        cv2.setRNGSeed(1)
+        a = cv2.fitEllipseDirect(c.reshape(-1, 1, 2))
+        cv2.setRNGSeed(12345)
+        b = cv2.fitEllipseDirect(c.reshape(-1, 1, 2))
+        assert a == b
+
+
+def test_box_points_and_bounding_rect():
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        cx, cy = rng.uniform(0, 1300, 2); w, h = rng.uniform(1, 200, 2); a = rng.uniform(-10, 190)
+        ref = cv2.boxPoints(((cx, cy), (w, h), a))
+        assert np.max(np.abs(R.box_points(cx, cy, w, h, a) - ref)) <= 2e-4
+        pts = rng.uniform(-5, 500, (4, 2)).astype(np.float32)
+        assert tuple(cv2.boundingRect(pts.reshape(-1, 1, 2))) == R.bounding_rect_f(pts)
+
+
+def test_lightblob_ctor_conventions():
+    # upright bar: fitEllipse angle 0 -> lightblob.angle 90 (include/core.h:92); size = (short, long)
+    m = np.zeros((120, 60), np.uint8)
+    cv2.ellipse(m, ((30, 60), (12, 80), 0), 255, -1)
+    c = O.find_external_contours(m)[0]
+    e = O.fit_ellipse_direct(c)
+    b = O.make_lightblob(e, O.CAMP_BLUE)
+    assert abs(b.angle - 90) < 1.0 and b.size[0] < b.size[1]
+    v = b.vertices  # left-down, left-up, right-up, right-down
+    assert v[0][0] < v[3][0] and v[1][0] < v[2][0] and v[0][1] > v[1][1] and v[3][1] > v[2][1]
+
+
+def test_filter_armours_gates_and_order():
+    img = synth.make_frame(1, 1280, 1024, 8)
+    fr = O.detect_frame(img)
+    pairs = [(a.i, a.j) for a in fr.armours]
+    assert pairs == sorted(pairs) and len(pairs) == 20 and len(fr.contours) == 27 and len(fr.positive) == 17
+    # reference quirks: a blob may appear in several armours (no dedupe); degenerate input gives []
+    assert O.filter_armours(fr.positive[:1], 12, 22, 0.4, 1) == []
+    # target mismatch never pairs (src/objdetect.cpp:124,128)
+    assert O.filter_armours(fr.positive, 12, 22, 0.4, O.CAMP_RED) == []
+
+
+def test_legacy_paths_run():
+    img = synth.make_frame(4, 640, 480, 4)
+    cs, _ = O.extract_color(img, 1, 80)
+    blobs = O.find_lightblobs_legacy(cs, 1.5, 80, 70, 10, 99999, img, fit_ellipse=True)
+    blobs_r = O.find_lightblobs_legacy(cs, 1.5, 80, 70, 10, 99999, img, fit_ellipse=False)
+    assert len(blobs) > 0 and all(b.target == O.CAMP_BLUE for b in blobs) and len(blobs_r) > 0
+    assert O.lightblob_overlap(blobs, 0, len(blobs)) is False  # one-past-end rejected (reference quirk B.7)
+
+
+def test_bayer_restatement_matches_cv2():
+    rng = np.random.default_rng(5)
+    for layout in (1, 2, 3, 4):
+        for shape in ((8, 10), (7, 9), (64, 96), (3, 3)):
+            raw = rng.integers(0, 256, shape, dtype=np.uint8)
+            assert np.array_equal(O.bayer_to_bgr(raw, layout), R.bayer_bilinear_bgr(raw, layout)), (layout, shape)
+    # the mosaic of a flat-colour image demosaics back to that colour
+    img = np.zeros((16, 16, 3), np.uint8); img[:] = (200, 100, 50)
+    assert np.array_equal(O.bayer_to_bgr(synth.bgr_to_bayer(img, 4), 4), img)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-5] for p in GOLDEN])
+def test_golden_fixtures(path):
+    """Oracle + generator against the committed fixtures (made by scripts/make_golden.py)."""
+    rec = json.load(open(path))
+    case = rec["case"]
+    img = synth.make_frame(case["seed"], case["width"], case["height"], case["plates"], blue=case["blue"])
+    assert zlib.crc32(img.tobytes()) == rec["frame_crc32"], "synthetic generator drifted"
+    p = dict(synth.MAIN_PARAMS); p["target"] = case["target"]
+    fr = O.detect_frame(img, **p)
+    assert zlib.crc32(fr.binary.tobytes()) == rec["mask_crc32"]
+    assert len(fr.contours) == len(rec["contours"]) and len(fr.positive) == len(rec["positive"]) and len(fr.armours) == len(rec["armours"])
+    for c, v, g in zip(fr.contours, fr.verdicts, rec["contours"]):
+        assert [int(c[0][0]), int(c[0][1])] == g["first"] and v.n == g["n"] and int(round(2 * v.area)) == g["area2"]
+        assert zlib.crc32(np.ascontiguousarray(c, np.int32).tobytes()) == g["points_crc32"] and v.status == g["status"]
+        if g["ellipse"] is not None:
+            e = v.ellipse
+            assert np.allclose([e.cx, e.cy, e.w, e.h, e.angle], g["ellipse"], rtol=1e-6, atol=1e-4)
+    for a, g in zip(fr.armours, rec["armours"]):
+        assert (a.i, a.j) == (g["i"], g["j"]) and np.allclose(a.icon, g["icon"], atol=1e-3) and list(a.bounding_box) == g["bounding_box"]
+    raw = synth.bgr_to_bayer(img, synth.BAYER_BG)
+    assert zlib.crc32(O.extract_color_mask(O.bayer_to_bgr(raw, 4), case["target"], 80).tobytes()) == rec["bayer_bg_mask_crc32"]
