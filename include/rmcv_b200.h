@@ -157,6 +157,7 @@ int rmcv_device_count(int* count);
 int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out);
 int rmcv_ctx_destroy(rmcv_ctx* ctx);
 const char* rmcv_last_error(const rmcv_ctx* ctx);          /* text of the last failure on this ctx */
+int rmcv_chunk_frames(const rmcv_ctx* ctx);                /* frames per internal pipeline step actually in use */
 
 /* ---- memory + stream helpers (so C / ctypes hosts need no CUDA toolkit) ---------------------- */
 int rmcv_device_alloc(rmcv_ctx* ctx, size_t bytes, void** dptr);
@@ -246,6 +247,10 @@ enum {
 int rmcv_profile_enable(rmcv_ctx* ctx, int on);
 /* accumulated milliseconds and launch counts per stage since the last reset */
 int rmcv_profile_read(rmcv_ctx* ctx, double ms[RMCV_STAGE_COUNT], int64_t launches[RMCV_STAGE_COUNT], int reset);
+/* Device-side stopwatch over ALL streams of the ctx: start records an event on every ctx stream, stop records again,
+ * synchronises and returns last-stop minus first-start in milliseconds (CUDA events on the launching streams). */
+int rmcv_timer_start(rmcv_ctx* ctx);
+int rmcv_timer_stop(rmcv_ctx* ctx, double* ms);
 /* number of kernels this library launched on the ctx since creation */
 int64_t rmcv_kernel_launches(const rmcv_ctx* ctx);
 

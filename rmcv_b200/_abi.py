@@ -74,6 +74,7 @@ PROTOTYPES = {
     "rmcv_ctx_create": (C.c_int, [C.POINTER(Config), C.POINTER(_vp)]),
     "rmcv_ctx_destroy": (C.c_int, [_vp]),
     "rmcv_last_error": (C.c_char_p, [_vp]),
+    "rmcv_chunk_frames": (C.c_int, [_vp]),
     "rmcv_device_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
     "rmcv_device_free": (C.c_int, [_vp, _vp]),
     "rmcv_host_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
@@ -98,5 +99,7 @@ PROTOTYPES = {
     "rmcv_make_lightblobs": (C.c_int, [_vp, _vp, _i, _i, _vp]),
     "rmcv_profile_enable": (C.c_int, [_vp, _i]),
     "rmcv_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), _i]),
+    "rmcv_timer_start": (C.c_int, [_vp]),
+    "rmcv_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "rmcv_kernel_launches": (C.c_int64, [_vp]),
 }

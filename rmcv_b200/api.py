@@ -210,6 +210,7 @@ class Context:
             raise RmcvError(rc, "rmcv_ctx_create", "(is a CUDA device present? this library has no CPU path)")
         self.h = h
         self.cfg = cfg
+        self.chunk_frames = int(self.lib.rmcv_chunk_frames(self.h))
 
     # -- plumbing
     def _check(self, rc: int, where: str):
@@ -247,6 +248,14 @@ class Context:
 
     def kernel_launches(self) -> int:
         return int(self.lib.rmcv_kernel_launches(self.h))
+
+    def timer_start(self):
+        self._check(self.lib.rmcv_timer_start(self.h), "rmcv_timer_start")
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._check(self.lib.rmcv_timer_stop(self.h, C.byref(ms)), "rmcv_timer_stop")
+        return ms.value
 
     def profile(self, on=True):
         self._check(self.lib.rmcv_profile_enable(self.h, 1 if on else 0), "rmcv_profile_enable")

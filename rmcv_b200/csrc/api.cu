@@ -26,6 +26,7 @@ struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
     void* tmp_host = nullptr; size_t tmp_host_bytes = 0;
     int last_nchunks = 0;
     int last_kind = 0;  // 0 none, 1 extract, 2 detect
+    cudaEvent_t t_start[2] = {nullptr, nullptr}, t_stop[2] = {nullptr, nullptr};
 };
 
 CtxExtra* extra(rmcv_ctx* c) { return static_cast<CtxExtra*>(c->extra); }
@@ -353,6 +354,7 @@ int rmcv_ctx_destroy(rmcv_ctx* ctx) {
     CtxExtra* ex = extra(ctx);
     if (ex) {
         for (auto& ps : ex->prof) for (int i = 0; i <= RMCV_STAGE_COUNT; ++i) cudaEventDestroy(ps.ev[i]);
+        for (int i = 0; i < 2; ++i) { if (ex->t_start[i]) cudaEventDestroy(ex->t_start[i]); if (ex->t_stop[i]) cudaEventDestroy(ex->t_stop[i]); }
         for (void* p : ex->dev_allocs) cudaFree(p);
         for (void* p : ex->host_allocs) cudaFreeHost(p);
         if (ex->tmp_dev) cudaFree(ex->tmp_dev);
@@ -365,6 +367,7 @@ int rmcv_ctx_destroy(rmcv_ctx* ctx) {
 }
 
 const char* rmcv_last_error(const rmcv_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+int rmcv_chunk_frames(const rmcv_ctx* ctx) { return ctx ? ctx->CF : 0; }
 
 int rmcv_device_alloc(rmcv_ctx* ctx, size_t bytes, void** dptr) {
     if (!ctx || !dptr) return RMCV_ERR_INVALID_ARG;
@@ -688,6 +691,35 @@ int rmcv_profile_read(rmcv_ctx* ctx, double ms[RMCV_STAGE_COUNT], int64_t launch
         if (launches) launches[s] = ctx->prof_launches[s];
         if (reset) { ctx->prof_ms[s] = 0.0; ctx->prof_launches[s] = 0; }
     }
+    return RMCV_OK;
+}
+
+int rmcv_timer_start(rmcv_ctx* ctx) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    CtxExtra* ex = extra(ctx);
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < 2; ++i) {
+        if (!ex->t_start[i]) { RMCV_CUDA(ctx, cudaEventCreate(&ex->t_start[i])); RMCV_CUDA(ctx, cudaEventCreate(&ex->t_stop[i])); }
+        RMCV_CUDA(ctx, cudaEventRecord(ex->t_start[i], ctx->slot[i].stream));
+    }
+    return RMCV_OK;
+}
+
+int rmcv_timer_stop(rmcv_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return RMCV_ERR_INVALID_ARG;
+    CtxExtra* ex = extra(ctx);
+    if (!ex->t_start[0]) return set_err(ctx, RMCV_ERR_STATE, "rmcv_timer_stop without rmcv_timer_start");
+    for (int i = 0; i < 2; ++i) RMCV_CUDA(ctx, cudaEventRecord(ex->t_stop[i], ctx->slot[i].stream));
+    int rc = sync_all(ctx);
+    if (rc != RMCV_OK) return rc;
+    float best = 0.f;
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) {
+            float t = 0.f;
+            RMCV_CUDA(ctx, cudaEventElapsedTime(&t, ex->t_start[i], ex->t_stop[j]));
+            if (t > best) best = t;
+        }
+    *ms = (double)best;
     return RMCV_OK;
 }
 

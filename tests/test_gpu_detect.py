@@ -40,7 +40,6 @@ def detect_and_compare(ctx, frames, p=PRM, check_points=True, check_labels=True,
         assert bad.size == 0, f"{what} frame {f}: {len(bad)} mask bytes differ"
         det = ctx.frame_detections(res, f)
         total.merge(CMP.compare_frame(det, ref, p, where=f"{what} frame {f}"))
-        resident = (f // ctx.cfg.chunk_frames if ctx.cfg.chunk_frames else 0)
         if check_points:
             try:
                 for k, rc in enumerate(ref.contours):
