@@ -211,6 +211,12 @@ int rmcv_fetch_results(rmcv_ctx* ctx, rmcv_results* out);
  * `cap` (x,y) pairs; *n_points receives the full length.  Host pointer, synchronous. */
 int rmcv_get_contour(rmcv_ctx* ctx, int frame, int contour_index, int32_t* xy, int cap, int* n_points);
 
+/* All external contours of frame `frame` in cv::findContours order, traced in one launch (one thread per contour).
+ * offsets[k]..offsets[k+1] delimit contour k inside xy ((x,y) int32 pairs); offsets needs n_contours+1 entries.
+ * *n_contours / *n_points always receive the full counts; RMCV_ERR_CAPACITY if a cap is too small. */
+int rmcv_get_contours(rmcv_ctx* ctx, int frame, int32_t* xy, int cap_points, int32_t* offsets, int cap_contours,
+                      int* n_contours, int* n_points);
+
 /* int32 label map of frame `frame` of the last detect call: index of the external contour that
  * owns each pixel, -1 for background and nested components.  Host pointer, synchronous. */
 int rmcv_get_label_map(rmcv_ctx* ctx, int frame, int32_t* labels, size_t pitch_elems);
@@ -237,12 +243,9 @@ int rmcv_make_lightblobs(rmcv_ctx* ctx, const rmcv_rotated_rect* boxes, int n, i
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* CUDA-event timing of the stages of detect/extract calls (on the stream that runs them). */
 enum {
-    RMCV_STAGE_PIXEL = 0,   /* fused diff/threshold/close kernel                                   */
-    RMCV_STAGE_RUNS = 1,    /* run extraction                                                     */
-    RMCV_STAGE_LABEL = 2,   /* union-find labelling (foreground + background gaps)                */
-    RMCV_STAGE_BLOB = 3,    /* per-component contour statistics + ellipse fit + gates             */
-    RMCV_STAGE_ARMOUR = 4,  /* ordering, pair gates, armour geometry, result write-out            */
-    RMCV_STAGE_COUNT = 5
+    RMCV_STAGE_PIXEL = 0,   /* fused diff/threshold/close kernel (+ run emission)                         */
+    RMCV_STAGE_FRAME = 1,   /* fused per-frame kernel: labelling, contour statistics, fits, gates, armours */
+    RMCV_STAGE_COUNT = 2
 };
 int rmcv_profile_enable(rmcv_ctx* ctx, int on);
 /* accumulated milliseconds and launch counts per stage since the last reset */

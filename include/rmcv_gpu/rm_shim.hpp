@@ -1,0 +1,305 @@
+// rm:: drop-in shim over the rmcv_b200 C ABI (include/rmcv_b200.h).
+//
+// Re-declares, with the reference's exact signatures, the three free functions the reference's only caller uses
+// (executable/main.cpp:172-176):
+//     rm::extract_color      include/imgproc.h:29       src/imgproc.cpp:50-75
+//     rm::filter_lightblobs  include/objdetect.h:47-49  src/objdetect.cpp:55-87
+//     rm::filter_armours     include/objdetect.h:70-71  src/objdetect.cpp:114-166
+// and routes them to librmcv_b200.so.  Two build modes:
+//
+//   * RMCV_SHIM_WITH_REFERENCE — inside the reference tree: includes the reference's own "core.h" (OpenCV types,
+//     rm::lightblob / rm::armour with their constructors).  Compile rm_shim.hpp's definitions INSTEAD OF the bodies in
+//     src/imgproc.cpp:50-75 and src/objdetect.cpp:55-87,114-166.  Light blobs and armours are
+//     rebuilt through the reference's public constructors from the GPU's cv::RotatedRect / blob pairs, so private
+//     members (Kalman filter, history) stay valid.
+//   * default (no OpenCV on this image) — a minimal `cv::`/`rm::` type set with the same public fields, enough to
+//     compile and run the call site (tests/cpp/call_site.cpp).
+//
+// Header-only; link with -lrmcv_b200.  One rm::gpu::context per host thread (thread_local default provided).
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../rmcv_b200.h"
+
+#if defined(RMCV_SHIM_WITH_REFERENCE)
+#include "core.h"  // the reference's include/core.h (pulls in OpenCV)
+#else
+namespace cv {
+struct Point { int x = 0, y = 0; };
+struct Point2f { float x = 0, y = 0; };
+struct Size2f { float width = 0, height = 0; };
+struct Rect2f { float x = 0, y = 0, width = 0, height = 0; };
+struct RotatedRect { Point2f center; Size2f size; float angle = 0; };
+// 8-bit image view/owner with cv::Mat's field names for the members the shim touches
+struct Mat {
+    int rows = 0, cols = 0, chans = 1;
+    size_t step = 0;
+    uint8_t* data = nullptr;
+    std::vector<uint8_t> storage;
+    Mat() = default;
+    Mat(int r, int c, int ch) : rows(r), cols(c), chans(ch), step((size_t)c * ch), storage((size_t)r * c * ch) { data = storage.data(); }
+    Mat(int r, int c, int ch, uint8_t* ext, size_t st) : rows(r), cols(c), chans(ch), step(st), data(ext) {}
+    int channels() const { return chans; }
+    bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+};
+using InputArray = const Mat&;
+}  // namespace cv
+
+namespace rm {
+enum camp { CAMP_RED = 0, CAMP_BLUE = 1, CAMP_GUIDELIGHT = 2, CAMP_NEUTRAL = -1 };  // include/core.h:20-23
+template <typename T>
+struct range {  // include/core.h:30-44
+    T lower_bound, upper_bound;
+    range(T lower, T upper) : lower_bound(lower), upper_bound(upper) {}
+    bool contains(T value) const { return value >= lower_bound && value <= upper_bound; }
+};
+typedef std::vector<cv::Point> contour;  // include/core.h:87
+class lightblob {  // public fields of include/core.h:89-99
+   public:
+    float angle = 0;
+    camp target = CAMP_NEUTRAL;
+    cv::Point2f center;
+    cv::Point2f vertices[4];
+    cv::Size2f size;
+};
+class armour {  // public geometry of include/core.h:101-130
+   public:
+    cv::Point2f icon[4];
+    cv::Point2f vertices[4];
+    cv::Rect2f bounding_box;
+    int64_t timestamp = 0;
+    int lost_count = 0;
+    int identity = -1;
+};
+}  // namespace rm
+#endif
+
+namespace rm {
+namespace gpu {
+
+struct error : std::runtime_error {
+    int status;
+    error(int s, const std::string& what) : std::runtime_error(what), status(s) {}
+};
+
+// Owns one rmcv_ctx sized for single-frame calls; grows on demand.
+class context {
+   public:
+    context() = default;
+    ~context() { if (ctx_) rmcv_ctx_destroy(ctx_); }
+    context(const context&) = delete;
+    context& operator=(const context&) = delete;
+
+    rmcv_ctx* get(int width, int height) {
+        if (!ctx_ || width > w_ || height > h_) {
+            if (ctx_) rmcv_ctx_destroy(ctx_);
+            ctx_ = nullptr;
+            rmcv_config cfg;
+            rmcv_default_config(&cfg);
+            w_ = width > w_ ? width : w_;
+            h_ = height > h_ ? height : h_;
+            cfg.max_width = w_ < 1280 ? 1280 : w_;
+            cfg.max_height = h_ < 1024 ? 1024 : h_;
+            cfg.max_batch = 1;
+            const int rc = rmcv_ctx_create(&cfg, &ctx_);
+            if (rc != RMCV_OK) throw error(rc, std::string("rmcv_ctx_create: ") + rmcv_status_string(rc) + " (no CPU fallback exists)");
+            w_ = cfg.max_width; h_ = cfg.max_height;
+        }
+        return ctx_;
+    }
+    void check(int rc, const char* where) {
+        if (rc != RMCV_OK) throw error(rc, std::string(where) + ": " + rmcv_status_string(rc) + " - " + (ctx_ ? rmcv_last_error(ctx_) : ""));
+    }
+
+   private:
+    rmcv_ctx* ctx_ = nullptr;
+    int w_ = 0, h_ = 0;
+};
+
+inline context& default_context() {
+    thread_local context c;
+    return c;
+}
+
+inline lightblob to_lightblob(const rmcv_lightblob& b, const rmcv_rotated_rect* box) {
+#if defined(RMCV_SHIM_WITH_REFERENCE)
+    // rebuild through the reference's own ctor (src/core.cpp:9-19) from the GPU's ellipse
+    (void)b;
+    return lightblob(cv::RotatedRect(cv::Point2f(box->cx, box->cy), cv::Size2f(box->w, box->h), box->angle), static_cast<camp>(b.target));
+#else
+    (void)box;
+    lightblob o;
+    o.angle = b.angle; o.target = static_cast<camp>(b.target);
+    o.center.x = b.center[0]; o.center.y = b.center[1];
+    for (int i = 0; i < 4; ++i) { o.vertices[i].x = b.vertices[i][0]; o.vertices[i].y = b.vertices[i][1]; }
+    o.size.width = b.size[0]; o.size.height = b.size[1];
+    return o;
+#endif
+}
+
+inline rmcv_lightblob from_lightblob(const lightblob& b) {
+    rmcv_lightblob o;
+    o.angle = b.angle; o.target = static_cast<int32_t>(b.target);
+    o.center[0] = b.center.x; o.center[1] = b.center.y;
+    for (int i = 0; i < 4; ++i) { o.vertices[i][0] = b.vertices[i].x; o.vertices[i][1] = b.vertices[i].y; }
+    o.size[0] = b.size.width; o.size[1] = b.size.height;
+    return o;
+}
+
+// The whole path in one call (not in the reference API; what a caller that does not need the contours should use).
+struct detection {
+    std::vector<lightblob> positive;
+    std::vector<armour> armours;
+    std::vector<rmcv_contour_info> contours;
+};
+
+}  // namespace gpu
+
+// ---------------------------------------------------------------------------------------------------------------
+// rm::extract_color — include/imgproc.h:29.  Returns the external contours (cv::findContours order, all points) and
+// the binary mask, exactly like src/imgproc.cpp:50-75.
+inline std::tuple<std::vector<contour>, cv::Mat> extract_color(cv::InputArray image_in, camp target, int lower_bound) {
+#if defined(RMCV_SHIM_WITH_REFERENCE)
+    cv::Mat image = image_in.getMat();
+    cv::Mat binary(image.rows, image.cols, CV_8UC1);
+    const size_t bstep = binary.step;
+#else
+    const cv::Mat& image = image_in;
+    cv::Mat binary(image.rows, image.cols, 1);
+    const size_t bstep = binary.step;
+#endif
+    gpu::context& gc = gpu::default_context();
+    rmcv_ctx* ctx = gc.get(image.cols, image.rows);
+    rmcv_params prm;
+    rmcv_default_params(&prm);
+    prm.target = static_cast<int32_t>(target);
+    prm.lower_bound = lower_bound;
+    rmcv_results res;
+    int rc = rmcv_detect_batch_host(ctx, image.data, image.step, image.step * (size_t)image.rows, image.cols, image.rows, 1, &prm,
+                                    binary.data, bstep, bstep * (size_t)image.rows, &res);
+    if (rc != RMCV_OK && rc != RMCV_ERR_CAPACITY) gc.check(rc, "rmcv_detect_batch_host");
+    int nc = 0, np = 0;
+    rc = rmcv_get_contours(ctx, 0, nullptr, 0, nullptr, 0, &nc, &np);
+    if (rc != RMCV_OK && rc != RMCV_ERR_CAPACITY) gc.check(rc, "rmcv_get_contours");
+    std::vector<int32_t> xy((size_t)np * 2 + 2), off((size_t)nc + 1);
+    if (nc > 0) gc.check(rmcv_get_contours(ctx, 0, xy.data(), np, off.data(), nc, &nc, &np), "rmcv_get_contours");
+    std::vector<contour> contours((size_t)nc);
+    for (int k = 0; k < nc; ++k) {
+        contours[k].resize((size_t)(off[k + 1] - off[k]));
+        for (int i = off[k]; i < off[k + 1]; ++i) { contours[k][i - off[k]].x = xy[2 * i]; contours[k][i - off[k]].y = xy[2 * i + 1]; }
+    }
+    return {contours, binary};
+}
+
+// rm::filter_lightblobs — include/objdetect.h:47-49, src/objdetect.cpp:55-87.
+inline auto filter_lightblobs(const std::vector<contour>& contours, const float tilt_max, const range<float> ratio_range,
+                              const range<double> area_range, camp enemy)
+    -> std::tuple<std::vector<lightblob>, std::vector<contour>> {
+    std::vector<lightblob> positive;
+    std::vector<contour> negative;
+    if (contours.empty()) return {positive, negative};
+    gpu::context& gc = gpu::default_context();
+    rmcv_ctx* ctx = gc.get(1, 1);
+    std::vector<int32_t> off(contours.size() + 1, 0);
+    for (size_t k = 0; k < contours.size(); ++k) off[k + 1] = off[k] + (int32_t)contours[k].size();
+    std::vector<int32_t> xy((size_t)off.back() * 2 + 2);
+    for (size_t k = 0; k < contours.size(); ++k)
+        for (size_t i = 0; i < contours[k].size(); ++i) { xy[2 * (off[k] + i)] = contours[k][i].x; xy[2 * (off[k] + i) + 1] = contours[k][i].y; }
+    rmcv_params prm;
+    rmcv_default_params(&prm);
+    prm.target = static_cast<int32_t>(enemy);
+    prm.tilt_max = tilt_max;
+    prm.ratio_min = ratio_range.lower_bound; prm.ratio_max = ratio_range.upper_bound;
+    prm.area_min = area_range.lower_bound; prm.area_max = area_range.upper_bound;
+    std::vector<rmcv_contour_info> infos(contours.size());
+    std::vector<rmcv_lightblob> blobs(contours.size());
+    int nb = 0;
+    gc.check(rmcv_filter_lightblobs(ctx, xy.data(), off.data(), (int)contours.size(), &prm, infos.data(), blobs.data(), (int)blobs.size(), &nb),
+             "rmcv_filter_lightblobs");
+    for (size_t k = 0; k < contours.size(); ++k) {
+        if (infos[k].status == RMCV_CONTOUR_NEGATIVE) negative.push_back(contours[k]);                       // :82
+        else if (infos[k].status == RMCV_CONTOUR_POSITIVE) positive.push_back(gpu::to_lightblob(blobs[infos[k].blob_index], &infos[k].ellipse));  // :83
+    }
+    return {positive, negative};
+}
+
+// rm::filter_armours — include/objdetect.h:70-71, src/objdetect.cpp:114-166.
+inline std::vector<armour> filter_armours(std::vector<lightblob>& lightblobs, const float angle_difference_max, const float shear_max,
+                                          const float lenght_ratio_max, const camp enemy) {
+    std::vector<armour> armours;
+    if (lightblobs.size() < 2) return armours;  // :120
+    gpu::context& gc = gpu::default_context();
+    rmcv_ctx* ctx = gc.get(1, 1);
+    std::vector<rmcv_lightblob> in(lightblobs.size());
+    for (size_t i = 0; i < lightblobs.size(); ++i) in[i] = gpu::from_lightblob(lightblobs[i]);
+    rmcv_params prm;
+    rmcv_default_params(&prm);
+    prm.target = static_cast<int32_t>(enemy);
+    prm.angle_difference_max = angle_difference_max; prm.shear_max = shear_max; prm.lenght_ratio_max = lenght_ratio_max;
+    int cap = 256, n = 0;
+    std::vector<rmcv_armour> out((size_t)cap);
+    int rc = rmcv_filter_armours(ctx, in.data(), (int)in.size(), &prm, out.data(), cap, &n);
+    if (rc == RMCV_ERR_CAPACITY) {
+        cap = n; out.resize((size_t)cap);
+        rc = rmcv_filter_armours(ctx, in.data(), (int)in.size(), &prm, out.data(), cap, &n);
+    }
+    gc.check(rc, "rmcv_filter_armours");
+    for (int k = 0; k < n; ++k) {
+#if defined(RMCV_SHIM_WITH_REFERENCE)
+        armours.push_back(armour({lightblobs[out[k].i], lightblobs[out[k].j]}));  // the reference's own ctor, :161
+#else
+        armour a;
+        for (int i = 0; i < 4; ++i) {
+            a.icon[i].x = out[k].icon[i][0]; a.icon[i].y = out[k].icon[i][1];
+            a.vertices[i].x = out[k].vertices[i][0]; a.vertices[i].y = out[k].vertices[i][1];
+        }
+        a.bounding_box.x = out[k].bounding_box[0]; a.bounding_box.y = out[k].bounding_box[1];
+        a.bounding_box.width = out[k].bounding_box[2]; a.bounding_box.height = out[k].bounding_box[3];
+        armours.push_back(a);
+#endif
+    }
+    return armours;
+}
+
+namespace gpu {
+// Fused single call: image -> positives + armours without materialising contours on the host.
+inline detection detect(const cv::Mat& image, const rmcv_params& prm, cv::Mat* binary = nullptr) {
+    context& gc = default_context();
+    rmcv_ctx* ctx = gc.get(image.cols, image.rows);
+    rmcv_results res;
+    const size_t bstep = binary ? (size_t)binary->step : 0;
+    gc.check(rmcv_detect_batch_host(ctx, image.data, image.step, image.step * (size_t)image.rows, image.cols, image.rows, 1, &prm,
+                                    binary ? binary->data : nullptr, bstep, bstep * (size_t)image.rows, &res),
+             "rmcv_detect_batch_host");
+    detection d;
+    const rmcv_frame_info& fi = res.frames[0];
+    d.contours.assign(res.contours + fi.contour_offset, res.contours + fi.contour_offset + fi.n_contours);
+    std::vector<const rmcv_rotated_rect*> boxes((size_t)fi.n_positive, nullptr);
+    for (const auto& c : d.contours)
+        if (c.blob_index >= 0) boxes[(size_t)c.blob_index] = &c.ellipse;
+    for (int k = 0; k < fi.n_positive; ++k) d.positive.push_back(to_lightblob(res.blobs[fi.blob_offset + k], boxes[(size_t)k]));
+    for (int k = 0; k < fi.n_armours; ++k) {
+        const rmcv_armour& o = res.armours[fi.armour_offset + k];
+#if defined(RMCV_SHIM_WITH_REFERENCE)
+        d.armours.push_back(armour({d.positive[o.i], d.positive[o.j]}));
+#else
+        armour a;
+        for (int i = 0; i < 4; ++i) {
+            a.icon[i].x = o.icon[i][0]; a.icon[i].y = o.icon[i][1];
+            a.vertices[i].x = o.vertices[i][0]; a.vertices[i].y = o.vertices[i][1];
+        }
+        a.bounding_box.x = o.bounding_box[0]; a.bounding_box.y = o.bounding_box[1];
+        a.bounding_box.width = o.bounding_box[2]; a.bounding_box.height = o.bounding_box[3];
+        d.armours.push_back(a);
+#endif
+    }
+    return d;
+}
+}  // namespace gpu
+}  // namespace rm

@@ -11,7 +11,7 @@ CAMP_RED, CAMP_BLUE, CAMP_GUIDELIGHT, CAMP_NEUTRAL = 0, 1, 2, -1
 BAYER_RG, BAYER_GB, BAYER_GR, BAYER_BG = 1, 2, 3, 4
 CONTOUR_SKIPPED, CONTOUR_POSITIVE, CONTOUR_NEGATIVE = 0, 1, 2
 FIT_NONE, FIT_DIRECT, FIT_FALLBACK = 0, 1, 2
-STAGE_NAMES = ("pixel", "runs", "label", "blob", "armour")
+STAGE_NAMES = ("pixel", "frame")
 
 
 class RotatedRect(C.Structure):
@@ -92,6 +92,7 @@ PROTOTYPES = {
                                          C.POINTER(Results)]),
     "rmcv_fetch_results": (C.c_int, [_vp, C.POINTER(Results)]),
     "rmcv_get_contour": (C.c_int, [_vp, _i, _i, _vp, _i, C.POINTER(C.c_int)]),
+    "rmcv_get_contours": (C.c_int, [_vp, _i, _vp, _i, _vp, _i, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rmcv_get_label_map": (C.c_int, [_vp, _i, _vp, _sz]),
     "rmcv_get_bitmask": (C.c_int, [_vp, _i, _vp, _i]),
     "rmcv_filter_lightblobs": (C.c_int, [_vp, _vp, _vp, _i, C.POINTER(Params), _vp, _vp, _i, C.POINTER(C.c_int)]),

@@ -261,8 +261,8 @@ class Context:
         self._check(self.lib.rmcv_profile_enable(self.h, 1 if on else 0), "rmcv_profile_enable")
 
     def profile_read(self, reset=True):
-        ms = (C.c_double * 5)()
-        ln = (C.c_int64 * 5)()
+        ms = (C.c_double * len(A.STAGE_NAMES))()
+        ln = (C.c_int64 * len(A.STAGE_NAMES))()
         self._check(self.lib.rmcv_profile_read(self.h, ms, ln, 1 if reset else 0), "rmcv_profile_read")
         return {n: (ms[i], int(ln[i])) for i, n in enumerate(A.STAGE_NAMES)}
 
@@ -333,6 +333,20 @@ class Context:
             return self.get_contour(frame, index, n.value)
         return buf[:n.value].copy()
 
+    def get_contours(self, frame: int) -> List[np.ndarray]:
+        """All external contours of a frame, traced in one launch (list of N×2 int32 arrays, cv::findContours order)."""
+        nc, npnt = C.c_int(), C.c_int()
+        rc = self.lib.rmcv_get_contours(self.h, frame, None, 0, None, 0, C.byref(nc), C.byref(npnt))
+        if rc not in (A.RMCV_OK, A.RMCV_ERR_CAPACITY):
+            self._check(rc, "rmcv_get_contours")
+        if nc.value == 0:
+            return []
+        xy = np.empty((max(npnt.value, 1), 2), np.int32)
+        offs = np.empty(nc.value + 1, np.int32)
+        self._check(self.lib.rmcv_get_contours(self.h, frame, xy.ctypes.data, npnt.value, offs.ctypes.data, nc.value,
+                                               C.byref(nc), C.byref(npnt)), "rmcv_get_contours")
+        return [xy[offs[k]:offs[k + 1]].copy() for k in range(nc.value)]
+
     def get_label_map(self, frame: int, width: int, height: int) -> np.ndarray:
         out = np.empty((height, width), np.int32)
         self._check(self.lib.rmcv_get_label_map(self.h, frame, out.ctypes.data, width), "rmcv_get_label_map")
@@ -401,9 +415,7 @@ def extract_color(image: np.ndarray, target: int, lower_bound: int):
     p = default_params(target=target, lower_bound=lower_bound, area_range=(0.0, 1e300))
     mask = np.empty((1, H, W), np.uint8)
     res = ctx.detect_batch_host(image[None], p, mask)
-    n = res.frames[0].n_contours
-    contours = [ctx.get_contour(0, k) for k in range(n)]
-    return contours, mask[0]
+    return ctx.get_contours(0), mask[0]
 
 
 def filter_lightblobs(contours, tilt_max, ratio_range, area_range, enemy):

@@ -56,18 +56,16 @@ int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
     const size_t CF = ctx->CF, H = g.H, WB = g.WB, R = g.R, C = g.C, A = g.A;
     memset(&sb, 0, sizeof(sb));
     RMCV_CUDA(ctx, dalloc(&sb.bits, CF * H * WB));
-    RMCV_CUDA(ctx, dalloc(&sb.hole, CF * H * WB));
-    RMCV_CUDA(ctx, cudaMemset(sb.hole, 0, CF * H * WB * sizeof(uint32_t)));
-    RMCV_CUDA(ctx, dalloc(&sb.row_off, CF * (H + 1)));
+    RMCV_CUDA(ctx, dalloc(&sb.rows, CF * H));
     RMCV_CUDA(ctx, dalloc(&sb.run_x, CF * R));
     RMCV_CUDA(ctx, dalloc(&sb.run_y, CF * R));
     RMCV_CUDA(ctx, dalloc(&sb.parent, CF * R));
     RMCV_CUDA(ctx, dalloc(&sb.gparent, CF * (R + 1)));
-    RMCV_CUDA(ctx, dalloc(&sb.rstat, CF * R));
+    RMCV_CUDA(ctx, dalloc(&sb.run_cid, CF * R));
     RMCV_CUDA(ctx, dalloc(&sb.comp_root, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.comps, CF * C));
-    RMCV_CUDA(ctx, dalloc(&sb.counters, CF));
-    RMCV_CUDA(ctx, cudaMemset(sb.counters, 0, CF * sizeof(FrameCounters)));
+    RMCV_CUDA(ctx, dalloc(&sb.counters, CF + 1));
+    RMCV_CUDA(ctx, cudaMemset(sb.counters, 0, (CF + 1) * sizeof(FrameCounters)));
     RMCV_CUDA(ctx, dalloc(&sb.s_contours, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.s_blobs, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.s_armours, CF * A));
@@ -83,8 +81,8 @@ int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
 }
 
 void free_slot(SlotBuffers& sb) {
-    cudaFree(sb.bits); cudaFree(sb.hole); cudaFree(sb.row_off); cudaFree(sb.run_x); cudaFree(sb.run_y);
-    cudaFree(sb.parent); cudaFree(sb.gparent); cudaFree(sb.rstat); cudaFree(sb.comp_root); cudaFree(sb.comps);
+    cudaFree(sb.bits); cudaFree(sb.rows); cudaFree(sb.run_x); cudaFree(sb.run_y);
+    cudaFree(sb.parent); cudaFree(sb.gparent); cudaFree(sb.run_cid); cudaFree(sb.comp_root); cudaFree(sb.comps);
     cudaFree(sb.counters); cudaFree(sb.s_contours); cudaFree(sb.s_blobs); cudaFree(sb.s_armours);
     if (sb.frames) cudaFree(sb.frames);
     if (sb.masks) cudaFree(sb.masks);
@@ -145,6 +143,7 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
                   int frames, int frame_base, int bayer_layout, const rmcv_params& prm, uint8_t* mask, size_t mask_pitch,
                   size_t mask_frame_stride, bool full) {
     cudaStream_t st = sb.stream;
+    if (full) RMCV_CUDA(ctx, cudaMemsetAsync(sb.counters, 0, (size_t)(frames + 1) * sizeof(FrameCounters), st));
     ProfSet* ps = prof_begin(ctx, st);
     int64_t l0 = ctx->kernel_launches;
     PixelLaunch pl;
@@ -152,32 +151,21 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
     pl.mask = mask; pl.mask_pitch = mask_pitch; pl.mask_frame_stride = mask_frame_stride;
     pl.bits = sb.bits; pl.W = W; pl.H = H; pl.batch = frames;
     pl.target = prm.target; pl.lower_bound = prm.lower_bound; pl.bayer_layout = bayer_layout;
+    pl.rows = full ? sb.rows : nullptr; pl.run_x = full ? sb.run_x : nullptr; pl.run_y = full ? sb.run_y : nullptr;
+    pl.counters = sb.counters; pl.R = ctx->cap.R;
     RMCV_CUDA(ctx, launch_pixel_stage(pl, ctx->sm_count, st, &ctx->kernel_launches));
     prof_mark(ps, RMCV_STAGE_PIXEL, st);
     ctx->prof_launches[RMCV_STAGE_PIXEL] += ctx->kernel_launches - l0; l0 = ctx->kernel_launches;
     if (!full) {
-        for (int s = 1; s < RMCV_STAGE_COUNT; ++s) prof_mark(ps, s, st);
+        prof_mark(ps, RMCV_STAGE_FRAME, st);
         return RMCV_OK;
     }
-    LabelLaunch ll;
-    ll.g = call_geometry(ctx, W, H); ll.frames = frames; ll.sb = &sb;
-    RMCV_CUDA(ctx, launch_runs(ll, st, &ctx->kernel_launches));
-    prof_mark(ps, RMCV_STAGE_RUNS, st);
-    ctx->prof_launches[RMCV_STAGE_RUNS] += ctx->kernel_launches - l0; l0 = ctx->kernel_launches;
-    RMCV_CUDA(ctx, launch_label(ll, st, &ctx->kernel_launches));
-    prof_mark(ps, RMCV_STAGE_LABEL, st);
-    ctx->prof_launches[RMCV_STAGE_LABEL] += ctx->kernel_launches - l0; l0 = ctx->kernel_launches;
-    RMCV_CUDA(ctx, launch_blobs(ll, prm, st, &ctx->kernel_launches));
-    RMCV_CUDA(ctx, launch_unpaint(ll, st, &ctx->kernel_launches));
-    prof_mark(ps, RMCV_STAGE_BLOB, st);
-    ctx->prof_launches[RMCV_STAGE_BLOB] += ctx->kernel_launches - l0; l0 = ctx->kernel_launches;
-    OutputLaunch ol;
-    ol.g = ll.g; ol.frames = frames; ol.sb = &sb; ol.frame_base = frame_base;
-    ol.o_frames = ctx->h_frames; ol.o_contours = ctx->h_contours; ol.o_blobs = ctx->h_blobs; ol.o_armours = ctx->h_armours;
-    ol.C_out = ctx->cap.C; ol.A_out = ctx->cap.A;
-    RMCV_CUDA(ctx, launch_armours(ol, prm, st, &ctx->kernel_launches));
-    prof_mark(ps, RMCV_STAGE_ARMOUR, st);
-    ctx->prof_launches[RMCV_STAGE_ARMOUR] += ctx->kernel_launches - l0;
+    FrameLaunch fl;
+    fl.g = call_geometry(ctx, W, H); fl.frames = frames; fl.sb = &sb; fl.frame_base = frame_base;
+    fl.o_frames = ctx->h_frames; fl.o_contours = ctx->h_contours; fl.o_blobs = ctx->h_blobs; fl.o_armours = ctx->h_armours;
+    RMCV_CUDA(ctx, launch_frames(fl, prm, ctx->max_smem_optin, st, &ctx->kernel_launches));
+    prof_mark(ps, RMCV_STAGE_FRAME, st);
+    ctx->prof_launches[RMCV_STAGE_FRAME] += ctx->kernel_launches - l0;
     return RMCV_OK;
 }
 
@@ -305,6 +293,7 @@ int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "cudaGetDeviceProperties failed"); return fail(RMCV_ERR_CUDA); }
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     Geometry& g = ctx->cap;
     g.W = cfg->max_width; g.H = cfg->max_height; g.WB = (g.W + 31) / 32;
     const long long px = (long long)g.W * g.H;
@@ -552,6 +541,50 @@ int rmcv_get_contour(rmcv_ctx* ctx, int frame, int contour_index, int32_t* xy, i
     *n_points = h[0];
     const int ncopy = h[0] < cap ? h[0] : cap;
     if (ncopy > 0) memcpy(xy, h + 4, (size_t)ncopy * 2 * sizeof(int32_t));
+    return RMCV_OK;
+}
+
+int rmcv_get_contours(rmcv_ctx* ctx, int frame, int32_t* xy, int cap_points, int32_t* offsets, int cap_contours, int* n_contours,
+                      int* n_points) {
+    if (!ctx || !n_contours || !n_points || cap_points < 0 || cap_contours < 0) return RMCV_ERR_INVALID_ARG;
+    int rc = sync_all(ctx);
+    if (rc != RMCV_OK) return rc;
+    if (!ctx->have_results) return set_err(ctx, RMCV_ERR_STATE, "rmcv_get_contours needs a detect call first");
+    int local = 0;
+    SlotBuffers* sb = resident_slot(ctx, frame, &local);
+    if (!sb) return set_err(ctx, RMCV_ERR_STATE, "frame scratch no longer resident (only the last two chunks are kept)");
+    const rmcv_frame_info& fi = ctx->h_frames[frame];
+    const int nc = fi.n_contours;
+    long long total = 0;
+    for (int k = 0; k < nc; ++k) total += ctx->h_contours[fi.contour_offset + k].n_points;
+    *n_contours = nc;
+    *n_points = (int)total;
+    if (nc > cap_contours || total > cap_points || (nc > 0 && (!offsets || !xy)))
+        return set_err(ctx, RMCV_ERR_CAPACITY, "rmcv_get_contours: caller buffers too small");
+    if (offsets) offsets[0] = 0;
+    if (nc == 0) return RMCV_OK;
+    const size_t b_meta = (((size_t)nc * 3 + 1) * 4 + 15) & ~(size_t)15, b_xy = (size_t)total * 8;
+    rc = ensure_tmp(ctx, b_meta + b_xy + 16, b_meta + b_xy + 16);
+    if (rc != RMCV_OK) return rc;
+    CtxExtra* ex = extra(ctx);
+    int32_t* h = reinterpret_cast<int32_t*>(ex->tmp_host);  // [offsets nc+1 | starts 2nc]
+    h[0] = 0;
+    for (int k = 0; k < nc; ++k) {
+        const rmcv_contour_info& ci = ctx->h_contours[fi.contour_offset + k];
+        h[k + 1] = h[k] + ci.n_points;
+        h[nc + 1 + 2 * k] = ci.first_x;
+        h[nc + 1 + 2 * k + 1] = ci.first_y;
+    }
+    for (int k = 0; k <= nc; ++k) offsets[k] = h[k];
+    uint8_t* d = reinterpret_cast<uint8_t*>(ex->tmp_dev);
+    cudaStream_t st = sb->stream;
+    Geometry g = call_geometry(ctx, ctx->last_W, ctx->last_H);
+    RMCV_CUDA(ctx, cudaMemcpyAsync(d, h, ((size_t)nc * 3 + 1) * 4, cudaMemcpyHostToDevice, st));
+    const int32_t* d_off = reinterpret_cast<const int32_t*>(d);
+    RMCV_CUDA(ctx, launch_trace_all(g, sb->bits + (size_t)local * g.H * g.WB, d_off + nc + 1, d_off, nc,
+                                    reinterpret_cast<int32_t*>(d + b_meta), st, &ctx->kernel_launches));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(xy, d + b_meta, b_xy, cudaMemcpyDeviceToHost, st));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(st));
     return RMCV_OK;
 }
 

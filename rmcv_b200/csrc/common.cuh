@@ -26,13 +26,14 @@ struct CompRec {            // one 8-connected component after the blob kernel
     rmcv_lightblob blob;
 };
 
-struct RunStat {            // per run; meaningful at component roots after the flatten pass
-    int32_t x0, y0, x1, y1; // bounding box
-    int32_t firstkey;       // min over the component of y*W + xs
+struct CompStat {           // per component, built in shared memory by the frame kernel
+    int32_t x0, y0, x1, y1; // bounding box (inclusive)
+    int32_t firstkey;       // min over the component of y*W + xs = raster-first pixel
+    int32_t root;           // root run index
 };
 
-struct FrameCounters {      // device-side, one per frame in the chunk
-    int32_t n_runs;
+struct FrameCounters {      // device-side, one per frame in the chunk (+1 trailing entry = chunk allocators)
+    int32_t n_runs;         // atomically grown by the pixel kernel's run emission (may exceed R: overflow)
     int32_t n_comps;
     int32_t n_holes;        // number of hole gaps (background runs not connected to the border)
     int32_t flags;
@@ -49,17 +50,16 @@ struct Geometry {           // frame geometry + derived sizes, shared by all ker
 struct SlotBuffers {
     // pixel stage outputs
     uint32_t* bits;         // [CF][H][WB]   final mask, bit-packed
-    uint32_t* hole;         // [CF][H][WB]   hole background; all-zero between calls (invariant)
-    // runs
-    int32_t* row_off;       // [CF][H+1]     first run of each row (index into the frame's run arrays)
+    // runs (emitted by the pixel kernel; rows of one band are contiguous, bands land in arrival order)
+    int2* rows;             // [CF][H]       (first run, one-past-last run) of each row
     uint32_t* run_x;        // [CF][R]       xs | xe<<16
-    int32_t* run_y;         // [CF][R]
-    int32_t* parent;        // [CF][R]       union-find over foreground runs (8-connectivity)
-    int32_t* gparent;       // [CF][R+1]     union-find over interior background gaps, node 0 = outer
-    RunStat* rstat;         // [CF][R]
+    uint16_t* run_y;        // [CF][R]
+    int32_t* parent;        // [CF][R]       flattened labels (root run index), written back by the frame kernel
+    int32_t* gparent;       // [CF][R+1]     background-gap forest; only used when a frame does not fit in shared memory
+    int16_t* run_cid;       // [CF][R]       component id per run; same remark
     int32_t* comp_root;     // [CF][C]       root run of each component
     CompRec* comps;         // [CF][C]
-    FrameCounters* counters;// [CF]
+    FrameCounters* counters;// [CF+1]        entry CF holds the chunk's dense-output allocators (n_runs,n_comps,n_holes)
     // ordered per-frame result slots (device) before dense write-out
     rmcv_contour_info* s_contours; // [CF][C]
     rmcv_lightblob* s_blobs;       // [CF][C]
@@ -79,6 +79,7 @@ struct rmcv_ctx {
     rmcv_config cfg;
     int device;
     int sm_count;
+    int max_smem_optin;
     int CF;                 // chunk frames
     rmcv::Geometry cap;     // capacities at max_width x max_height
     rmcv::SlotBuffers slot[2];
@@ -124,30 +125,26 @@ struct PixelLaunch {
     int W, H, batch;
     int target, lower_bound;
     int bayer_layout;   // 0 = BGR input
+    // run emission (null = mask only)
+    int2* rows; uint32_t* run_x; uint16_t* run_y; FrameCounters* counters; int R;
 };
 cudaError_t launch_pixel_stage(const PixelLaunch& p, int sm_count, cudaStream_t st, int64_t* launches);
 
-struct LabelLaunch {
-    Geometry g; int frames; SlotBuffers* sb;
-};
-cudaError_t launch_runs(const LabelLaunch& p, cudaStream_t st, int64_t* launches);
-cudaError_t launch_label(const LabelLaunch& p, cudaStream_t st, int64_t* launches);
-cudaError_t launch_blobs(const LabelLaunch& p, const rmcv_params& prm, cudaStream_t st, int64_t* launches);
-cudaError_t launch_unpaint(const LabelLaunch& p, cudaStream_t st, int64_t* launches);
-
-struct OutputLaunch {
+struct FrameLaunch {
     Geometry g; int frames; SlotBuffers* sb;
     int frame_base;               // index of the chunk's first frame in the batch
     rmcv_frame_info* o_frames;    // device-visible pointers of the pinned result arrays
     rmcv_contour_info* o_contours;
     rmcv_lightblob* o_blobs;
     rmcv_armour* o_armours;
-    int C_out, A_out;             // per-frame strides of the pinned arrays
 };
-cudaError_t launch_armours(const OutputLaunch& p, const rmcv_params& prm, cudaStream_t st, int64_t* launches);
+// everything after the pixel stage for one chunk: labelling, contour statistics, fits, gates, armours, write-out
+cudaError_t launch_frames(const FrameLaunch& p, const rmcv_params& prm, int max_smem_optin, cudaStream_t st, int64_t* launches);
 
 cudaError_t launch_trace_contour(const Geometry& g, const uint32_t* bits, int x0, int y0, int32_t* d_xy, int cap,
                                  int32_t* d_n, cudaStream_t st, int64_t* launches);
+cudaError_t launch_trace_all(const Geometry& g, const uint32_t* bits, const int32_t* d_starts, const int32_t* d_offsets,
+                             int n_contours, int32_t* d_xy, cudaStream_t st, int64_t* launches);
 cudaError_t launch_label_map(const Geometry& g, SlotBuffers* sb, int frame, int32_t* d_labels, cudaStream_t st,
                              int64_t* launches);
 

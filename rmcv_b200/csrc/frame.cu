@@ -1,0 +1,630 @@
+// K2 — everything after the pixel stage, one CTA per frame, run data resident in shared memory:
+//   * connected-component labelling of the runs the pixel kernel emitted (8-connected foreground) and of the background
+//     gaps between them (4-connected; node 0 = background connected to the image border) with a lock-free union-find
+//     (atomicMin on shared memory) — replaces the component discovery of cv::findContours(RETR_EXTERNAL)
+//     (reference: src/imgproc.cpp:71-72; semantics SURVEY A.2-A.5);
+//   * per component, one warp: contour.size(), cv::contourArea, bbox and the moment sums of the contour point multiset
+//     from the local 3x3 arc rule, cv::fitEllipseDirect incl. its fallback, the ratio/tilt gates and the
+//     rm::lightblob ctor (reference: src/objdetect.cpp:62-84, src/core.cpp:9-19) — the contour is never materialised;
+//   * ordering into cv::findContours order, the O(P^2) pair gates of rm::filter_armours and rm::armour geometry
+//     (reference: src/objdetect.cpp:114-166, src/core.cpp:21-49) with an order-preserving block compaction;
+//   * dense write-out straight into pinned, device-mapped host memory (space claimed with one atomicAdd per array), so
+//     results reach the host without a size-dependent cudaMemcpy.
+// Arcs whose background side is a hole are skipped, so hole borders never contribute and nested components end with
+// n == 0 (RETR_EXTERNAL).  Frames whose run count exceeds the shared-memory capacity run the same code on global arrays.
+#include "blob_math.cuh"
+#include "common.cuh"
+#include "pairs.cuh"
+
+namespace rmcv {
+
+// Arc table indexed by  NW | N<<1 | NE<<2 | W<<3 | E<<4 | SW<<5 | S<<6 | SE<<7  (bit set = foreground).
+// Entry: bits 0-2 arc count m; arc i at bits 3+5i: low 2 bits = 4-neighbour to test for "hole" (0=E,1=N,2=W,3=S),
+// high 3 bits = direction of the edge target q (0..7 = E,NE,N,NW,W,SW,S,SE); bit 31 = isolated pixel (no edge).
+__constant__ uint32_t c_arc_lut[256];
+__constant__ int8_t c_dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+__constant__ int8_t c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+
+void upload_luts() {
+    uint32_t lut[256];
+    for (int idx = 0; idx < 256; ++idx) {
+        int fg[8];  // un-permute to direction order E,NE,N,NW,W,SW,S,SE
+        fg[3] = (idx >> 0) & 1; fg[2] = (idx >> 1) & 1; fg[1] = (idx >> 2) & 1;
+        fg[4] = (idx >> 3) & 1; fg[0] = (idx >> 4) & 1;
+        fg[5] = (idx >> 5) & 1; fg[6] = (idx >> 6) & 1; fg[7] = (idx >> 7) & 1;
+        int any = 0;
+        for (int k = 0; k < 8; ++k) any |= fg[k];
+        if (!any) { lut[idx] = (1u << 31) | 1u; continue; }
+        int start = 0;
+        while (!fg[start]) ++start;
+        uint32_t v = 0; int m = 0;
+        int k = (start + 1) & 7, steps = 0;
+        while (steps < 8) {
+            if (!fg[k]) {
+                int four = -1;
+                while (!fg[k]) {
+                    if ((k & 1) == 0 && four < 0) four = k >> 1;
+                    k = (k + 1) & 7; ++steps;
+                }
+                if (four >= 0) { v |= (uint32_t)(four | (k << 2)) << (3 + 5 * m); ++m; }
+            } else {
+                k = (k + 1) & 7; ++steps;
+            }
+        }
+        lut[idx] = v | (uint32_t)m;
+    }
+    cudaMemcpyToSymbol(c_arc_lut, lut, sizeof(lut));
+}
+
+// ------------------------------------------------------------------------------------------ union-find
+__device__ __forceinline__ int uf_find(int32_t* parent, int x) {
+    // path halving with atomicMin: links only ever move towards smaller indices, so concurrent unions stay valid
+    while (true) {
+        const int p = *reinterpret_cast<volatile int32_t*>(parent + x);
+        if (p == x) return x;
+        const int gp = *reinterpret_cast<volatile int32_t*>(parent + p);
+        if (gp != p) atomicMin(parent + x, gp);
+        x = p;
+    }
+}
+
+__device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }  // a > b: hang a under b
+        const int old = atomicMin(parent + a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+struct Runs {  // run storage of one frame (shared or global memory, same code)
+    const int2* rows;      // per row: [first, end)
+    const uint32_t* run_x; // xs | xe<<16
+    const uint16_t* run_y;
+    int32_t* parent;
+    int32_t* gparent;      // node r+1 = gap to the left of run r; node 0 = outer background
+    int16_t* cid;
+    int n_runs, W, H;
+};
+
+// first run index in [lo,hi) with xe >= x
+__device__ __forceinline__ int lower_bound_xe(const uint32_t* run_x, int lo, int hi, int x) {
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)(run_x[mid] >> 16) < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// first run index in [lo,hi) with xs > x
+__device__ __forceinline__ int upper_bound_xs(const uint32_t* run_x, int lo, int hi, int x) {
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)(run_x[mid] & 0xffffu) <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Unions the interior gap node `gnode` = [a,b] with the 4-connected background gaps of row yy.
+__device__ __forceinline__ void gap_union_row(const Runs& f, int gnode, int a, int b, int yy) {
+    const int2 rr = f.rows[yy];
+    const int lo = rr.x, hi = rr.y;
+    for (int r = upper_bound_xs(f.run_x, lo, hi, a);; ++r) {
+        // gap between run r-1 and run r (r == lo: left border gap; r == hi: right border gap)
+        const int ga = (r == lo) ? 0 : (int)(f.run_x[r - 1] >> 16) + 1;
+        if (ga > b) break;
+        const int gb = (r == hi) ? f.W - 1 : (int)(f.run_x[r] & 0xffffu) - 1;
+        if (gb >= a && ga <= gb) {
+            const bool border = (r == lo) || (r == hi) || yy == 0 || yy == f.H - 1;
+            uf_union(f.gparent, gnode, border ? 0 : r + 1);
+        }
+        if (r == hi) break;
+    }
+}
+
+// Is background pixel (x,yy) part of a hole (background not connected to the image border)?
+__device__ __forceinline__ bool is_hole(const Runs& f, int x, int yy) {
+    if (x <= 0 || yy <= 0 || x >= f.W - 1 || yy >= f.H - 1) return false;
+    const int2 rr = f.rows[yy];
+    const int r = upper_bound_xs(f.run_x, rr.x, rr.y, x);  // the gap lies between run r-1 and run r
+    if (r == rr.x || r == rr.y) return false;                // touches the left / right border
+    return f.gparent[r + 1] != 0;
+}
+
+// ------------------------------------------------------------------------------------------ contour points
+__device__ __forceinline__ uint64_t window(const uint32_t* row, int k, int WB) {
+    const uint32_t w = __ldg(row + k);
+    const uint32_t prev = k > 0 ? (__ldg(row + k - 1) >> 31) : 0u;
+    const uint32_t next = k + 1 < WB ? (__ldg(row + k + 1) & 1u) : 0u;
+    return (uint64_t)prev | ((uint64_t)w << 1) | ((uint64_t)next << 33);
+}
+
+// Calls emit(x, y, dx, dy) for every contour point contributed by the run [xs,xe] of row y.
+template <class F>
+__device__ __forceinline__ void run_contour_points(const uint32_t* bits, const Runs& f, bool has_holes, int WB, int y, int xs,
+                                                   int xe, F&& emit) {
+    const int H = f.H;
+    const uint32_t* rc = bits + (size_t)y * WB;
+    const uint32_t* ru = bits + (size_t)(y - 1) * WB;
+    const uint32_t* rd = bits + (size_t)(y + 1) * WB;
+    for (int k = xs >> 5; k <= (xe >> 5); ++k) {
+        const int l = max(xs, k * 32) - k * 32, h = min(xe, k * 32 + 31) - k * 32;
+        const uint32_t runmask = (h == 31 ? 0xffffffffu : ((1u << (h + 1)) - 1u)) & ~((1u << l) - 1u);
+        const uint64_t cw = window(rc, k, WB);
+        const uint64_t uw = y > 0 ? window(ru, k, WB) : 0ull;
+        const uint64_t dw = y < H - 1 ? window(rd, k, WB) : 0ull;
+        // candidates: run pixels with a background 4-neighbour
+        uint32_t cand = runmask & ~((uint32_t)(uw >> 1) & (uint32_t)(dw >> 1) & (uint32_t)cw & (uint32_t)(cw >> 2));
+        while (cand) {
+            const int i = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const uint32_t u3 = (uint32_t)(uw >> i) & 7u, c3 = (uint32_t)(cw >> i) & 7u, d3 = (uint32_t)(dw >> i) & 7u;
+            const uint32_t idx = u3 | ((c3 & 1u) << 3) | ((c3 >> 2) << 4) | (d3 << 5);
+            const uint32_t ent = c_arc_lut[idx];
+            const int m = ent & 7;
+            const bool iso = (ent >> 31) != 0;
+            const int x = k * 32 + i;
+            for (int a = 0; a < m; ++a) {
+                const uint32_t arc = (ent >> (3 + 5 * a)) & 31u;
+                if (has_holes) {
+                    const int t4 = arc & 3u;  // 0=E,1=N,2=W,3=S
+                    const int tx = x + (t4 == 0) - (t4 == 2), tyy = y + (t4 == 3) - (t4 == 1);
+                    if (is_hole(f, tx, tyy)) continue;
+                }
+                const int q = arc >> 2;
+                emit(x, y, iso ? 0 : (int)c_dx[q], iso ? 0 : (int)c_dy[q]);
+            }
+        }
+    }
+}
+
+// Visits every run of component `root` inside its bbox rows, lanes striding over rows.
+template <class F>
+__device__ __forceinline__ void component_points(const uint32_t* bits, const Runs& f, bool has_holes, int WB, int root,
+                                                 const CompStat& st, int lane, F&& emit) {
+    for (int y = st.y0 + lane; y <= st.y1; y += 32) {
+        const int2 rr = f.rows[y];
+        for (int r = lower_bound_xe(f.run_x, rr.x, rr.y, st.x0); r < rr.y; ++r) {
+            const uint32_t rx = f.run_x[r];
+            const int xs = (int)(rx & 0xffffu), xe = (int)(rx >> 16);
+            if (xs > st.x1) break;
+            if (f.parent[r] != root) continue;
+            run_contour_points(bits, f, has_holes, WB, y, xs, xe, emit);
+        }
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum(long long v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void warp_sum(Moments& m) {
+    m.n = warp_sum(m.n);
+    m.x = warp_sum(m.x); m.y = warp_sum(m.y);
+    m.xx = warp_sum(m.xx); m.xy = warp_sum(m.xy); m.yy = warp_sum(m.yy);
+    m.xxx = warp_sum(m.xxx); m.xxy = warp_sum(m.xxy); m.xyy = warp_sum(m.xyy); m.yyy = warp_sum(m.yyy);
+    m.xxxx = warp_sum(m.xxxx); m.xxxy = warp_sum(m.xxxy); m.xxyy = warp_sum(m.xxyy);
+    m.xyyy = warp_sum(m.xyyy); m.yyyy = warp_sum(m.yyyy);
+}
+
+// Decision + fit shared by the detect path (points regenerated from the mask) and rm::filter_lightblobs on
+// caller-supplied contours.  `pass(fn)` must call fn(x, y) for every contour point (with multiplicity), partitioned
+// over the lanes of the warp.  All lanes return identical results.
+template <class PassFn>
+__device__ __forceinline__ void fit_and_gate(int n, long long sum_x, long long sum_y, long long cross, const rmcv_params& prm,
+                                             PassFn&& pass, int* status, int* branch, float* det0_out,
+                                             rmcv_rotated_rect* ell, rmcv_lightblob* blob) {
+    *status = RMCV_CONTOUR_SKIPPED;
+    *branch = RMCV_FIT_NONE;
+    *det0_out = 0.f;
+    ell->cx = ell->cy = ell->w = ell->h = ell->angle = 0.f;
+    const long long area2 = cross < 0 ? -cross : cross;
+    const double area = (double)area2 * 0.5;
+    if (n < 6 || !(area >= prm.area_min && area <= prm.area_max)) return;  // src/objdetect.cpp:64
+    // ---- direct branch (centre in double)
+    const double cx = (double)sum_x / (double)n, cy = (double)sum_y / (double)n;
+    Moments m;
+    moments_zero(m);
+    double s = 0.0;
+    pass([&](int x, int y) {
+        const double dx = (double)x - cx, dy = (double)y - cy;
+        s += fabs(dx) + fabs(dy);
+        moments_add(m, dx, dy);
+    });
+    s = warp_sum(s);
+    warp_sum(m);
+    double scale = 100.0 / (s > RMCV_FLT_EPSILON ? s : RMCV_FLT_EPSILON);
+    double det = 0.0;
+    const bool ok = direct_fit(m, scale, cx, cy, ell, &det);
+    *det0_out = (float)det;
+    if (ok) {
+        *branch = RMCV_FIT_DIRECT;
+    } else {
+        // ---- fallback branch: cv::fitEllipseNoDirect keeps the centre and the centred points in float
+        const float c32x = __fdiv_rn((float)sum_x, (float)n), c32y = __fdiv_rn((float)sum_y, (float)n);
+        moments_zero(m);
+        double s2 = 0.0;
+        pass([&](int x, int y) {
+            const float fx = __fsub_rn((float)x, c32x), fy = __fsub_rn((float)y, c32y);
+            s2 += (double)__fadd_rn(fabsf(fx), fabsf(fy));
+            moments_add(m, (double)fx, (double)fy);
+        });
+        s2 = warp_sum(s2);
+        warp_sum(m);
+        scale = 100.0 / (s2 > RMCV_FLT_EPSILON ? s2 : RMCV_FLT_EPSILON);
+        nodirect_fit(m, scale, c32x, c32y, ell);
+        *branch = RMCV_FIT_FALLBACK;
+    }
+    *status = blob_gates(*ell, prm);
+    if (*status == RMCV_CONTOUR_POSITIVE) make_lightblob(*ell, prm.target, blob);
+}
+
+// ------------------------------------------------------------------------------------------ the frame kernel
+struct FrameParams {
+    Geometry g;
+    SlotBuffers sb;
+    rmcv_params prm;
+    int frame_base;
+    rmcv_frame_info* o_frames;
+    rmcv_contour_info* o_contours;
+    rmcv_lightblob* o_blobs;
+    rmcv_armour* o_armours;
+    int Rs;      // run capacity of the shared-memory arrays
+    int frames;  // frames in this chunk (index of the allocator entry in sb.counters)
+};
+
+__host__ __device__ inline size_t frame_smem_bytes(int H, int Rs, int C) {
+    size_t b = 0;
+    b += (size_t)H * sizeof(int2);
+    b += (size_t)Rs * sizeof(uint32_t);            // run_x
+    b += (size_t)Rs * sizeof(int32_t);             // parent
+    b += ((size_t)Rs + 2) * sizeof(int32_t);       // gparent
+    b += (size_t)Rs * sizeof(uint16_t);            // run_y
+    b += (size_t)Rs * sizeof(int16_t);             // cid
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)C * sizeof(CompStat);
+    b += (size_t)C * 2 * sizeof(int32_t);          // keys, status
+    return b + 64;
+}
+
+__global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int sh_scan[33];
+    __shared__ int s_ncomp, s_nholes, s_np, s_nc, s_nn, s_flags, s_off[3];
+    const Geometry& g = p.g;
+    const int W = g.W, H = g.H, WB = g.WB, R = g.R, C = g.C, A = g.A, Rs = p.Rs;
+    const int frame = blockIdx.x;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+    const SlotBuffers& sb = p.sb;
+    FrameCounters& fc = sb.counters[frame];
+
+    // ---- carve shared memory
+    uint8_t* q = smem;
+    int2* s_rows = reinterpret_cast<int2*>(q); q += (size_t)H * sizeof(int2);
+    uint32_t* s_run_x = reinterpret_cast<uint32_t*>(q); q += (size_t)Rs * sizeof(uint32_t);
+    int32_t* s_parent = reinterpret_cast<int32_t*>(q); q += (size_t)Rs * sizeof(int32_t);
+    int32_t* s_gparent = reinterpret_cast<int32_t*>(q); q += ((size_t)Rs + 2) * sizeof(int32_t);
+    uint16_t* s_run_y = reinterpret_cast<uint16_t*>(q); q += (size_t)Rs * sizeof(uint16_t);
+    int16_t* s_cid = reinterpret_cast<int16_t*>(q); q += (size_t)Rs * sizeof(int16_t);
+    q = smem + (((size_t)(q - smem) + 15) & ~(size_t)15);
+    CompStat* s_stat = reinterpret_cast<CompStat*>(q); q += (size_t)C * sizeof(CompStat);
+    int32_t* s_keys = reinterpret_cast<int32_t*>(q); q += (size_t)C * sizeof(int32_t);
+    int32_t* s_status = reinterpret_cast<int32_t*>(q);
+
+    const int raw_runs = fc.n_runs;
+    const int n_runs = min(raw_runs, R);
+    const bool in_smem = n_runs <= Rs;
+    const uint32_t* g_run_x = sb.run_x + (size_t)frame * R;
+    const uint16_t* g_run_y = sb.run_y + (size_t)frame * R;
+    int32_t* g_parent = sb.parent + (size_t)frame * R;
+    const int2* g_rows = sb.rows + (size_t)frame * H;
+    const uint32_t* bits = sb.bits + (size_t)frame * H * WB;
+
+    Runs f;
+    f.rows = s_rows;
+    f.run_x = in_smem ? s_run_x : g_run_x;
+    f.run_y = in_smem ? s_run_y : g_run_y;
+    f.parent = in_smem ? s_parent : g_parent;
+    f.gparent = in_smem ? s_gparent : sb.gparent + (size_t)frame * (R + 1);
+    f.cid = in_smem ? s_cid : sb.run_cid + (size_t)frame * R;
+    f.n_runs = n_runs; f.W = W; f.H = H;
+
+    if (tid == 0) {
+        s_ncomp = 0; s_nholes = 0; s_np = 0; s_nc = 0; s_nn = 0;
+        s_flags = raw_runs > R ? RMCV_FRAME_OVERFLOW_RUNS : 0;
+    }
+    for (int y = tid; y < H; y += NT) {
+        int2 rr = g_rows[y];
+        rr.x = min(rr.x, n_runs); rr.y = min(rr.y, n_runs);
+        s_rows[y] = rr;
+    }
+    if (in_smem) {
+        for (int r = tid; r < n_runs; r += NT) { s_run_x[r] = g_run_x[r]; s_run_y[r] = g_run_y[r]; }
+    }
+    __syncthreads();
+    // ---- init forests
+    for (int r = tid; r < n_runs; r += NT) {
+        f.parent[r] = r;
+        const int y = f.run_y[r];
+        const bool outer = (r == s_rows[y].x) || y == 0 || y == H - 1;  // gap left of r touches the border
+        f.gparent[r + 1] = outer ? 0 : r + 1;
+    }
+    if (tid == 0) f.gparent[0] = 0;
+    __syncthreads();
+    // ---- unions
+    for (int r = tid; r < n_runs; r += NT) {
+        const uint32_t rx = f.run_x[r];
+        const int xs = (int)(rx & 0xffffu), xe = (int)(rx >> 16), y = f.run_y[r];
+        if (y > 0) {  // foreground, 8-connectivity: runs of row y-1 overlapping [xs-1, xe+1]
+            const int2 pr = s_rows[y - 1];
+            for (int pp = lower_bound_xe(f.run_x, pr.x, pr.y, xs - 1); pp < pr.y; ++pp) {
+                if ((int)(f.run_x[pp] & 0xffffu) > xe + 1) break;
+                uf_union(f.parent, r, pp);
+            }
+        }
+        if (r > s_rows[y].x && y > 0 && y < H - 1) {  // interior background gap to the left, 4-connectivity
+            const int a = (int)(f.run_x[r - 1] >> 16) + 1, b = xs - 1;
+            gap_union_row(f, r + 1, a, b, y - 1);
+            gap_union_row(f, r + 1, a, b, y + 1);
+        }
+    }
+    __syncthreads();
+    // ---- flatten, enumerate components
+    for (int r = tid; r < n_runs; r += NT) {
+        const int root = uf_find(f.parent, r);
+        if (root == r) {
+            const int c = atomicAdd(&s_ncomp, 1);
+            if (c < C) {
+                const uint32_t rx = f.run_x[r];
+                const int y = f.run_y[r];
+                CompStat st;
+                st.x0 = (int)(rx & 0xffffu); st.x1 = (int)(rx >> 16); st.y0 = y; st.y1 = y;
+                st.firstkey = y * W + st.x0; st.root = r;
+                s_stat[c] = st;
+                f.cid[r] = (int16_t)c;
+            } else {
+                f.cid[r] = -1;
+                atomicOr(&s_flags, RMCV_FRAME_OVERFLOW_BLOBS);
+            }
+        }
+        const int groot = uf_find(f.gparent, r + 1);
+        if (groot != 0) atomicAdd(&s_nholes, 1);
+    }
+    __syncthreads();
+    for (int r = tid; r < n_runs; r += NT) {
+        const int root = uf_find(f.parent, r);
+        f.parent[r] = root;                        // now a flat label
+        if (in_smem) g_parent[r] = root;           // kept for rmcv_get_label_map
+        f.gparent[r + 1] = uf_find(f.gparent, r + 1);
+    }
+    __syncthreads();
+    for (int r = tid; r < n_runs; r += NT) {
+        const int root = f.parent[r];
+        if (root == r) continue;
+        const int c = f.cid[root];
+        if (c < 0) continue;
+        const uint32_t rx = f.run_x[r];
+        const int xs = (int)(rx & 0xffffu), xe = (int)(rx >> 16), y = f.run_y[r];
+        CompStat* st = s_stat + c;
+        atomicMin(&st->x0, xs); atomicMax(&st->x1, xe);
+        atomicMin(&st->y0, y); atomicMax(&st->y1, y);
+        atomicMin(&st->firstkey, y * W + xs);
+    }
+    __syncthreads();
+    const int n_comps = min(s_ncomp, C);
+    const bool has_holes = s_nholes > 0;
+    CompRec* comps = sb.comps + (size_t)frame * C;
+    // ---- per component: contour statistics, fit, gates (one warp each)
+    for (int c = warp; c < n_comps; c += nwarps) {
+        const CompStat st = s_stat[c];
+        int n = 0;
+        long long sx = 0, sy = 0, cross = 0;
+        component_points(bits, f, has_holes, WB, st.root, st, lane, [&](int x, int y, int dx, int dy) {
+            ++n; sx += x; sy += y;
+            cross += (long long)x * dy - (long long)y * dx;
+        });
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        sx = warp_sum(sx); sy = warp_sum(sy); cross = warp_sum(cross);
+        CompRec rec;
+        rec.firstkey = n > 0 ? st.firstkey : -1;
+        rec.n_points = n;
+        rec.area2 = cross < 0 ? -cross : cross;
+        rec.bbox[0] = st.x0; rec.bbox[1] = st.y0; rec.bbox[2] = st.x1; rec.bbox[3] = st.y1;
+        rec.status = -1;
+        rec.fit_branch = RMCV_FIT_NONE;
+        rec.det0 = 0.f;
+        memset(&rec.blob, 0, sizeof(rec.blob));
+        memset(&rec.ellipse, 0, sizeof(rec.ellipse));
+        if (n > 0) {  // external component (warp-uniform)
+            auto pass = [&](auto&& fn) {
+                component_points(bits, f, has_holes, WB, st.root, st, lane, [&](int x, int y, int, int) { fn(x, y); });
+            };
+            fit_and_gate(n, sx, sy, cross, p.prm, pass, &rec.status, &rec.fit_branch, &rec.det0, &rec.ellipse, &rec.blob);
+        }
+        if (lane == 0) {
+            comps[c] = rec;
+            s_keys[c] = rec.firstkey;
+            s_status[c] = rec.status;
+            sb.comp_root[(size_t)frame * C + c] = st.root;
+        }
+    }
+    __syncthreads();
+    // ---- order: rank = number of external components with a larger first-pixel key (reverse raster order)
+    rmcv_contour_info* oc = sb.s_contours + (size_t)frame * C;
+    rmcv_lightblob* ob = sb.s_blobs + (size_t)frame * C;
+    rmcv_armour* oa = sb.s_armours + (size_t)frame * A;
+    for (int i = tid; i < n_comps; i += NT) {
+        const int key = s_keys[i];
+        if (key < 0) continue;
+        const int stt = s_status[i];
+        int rank = 0, prank = 0;
+        for (int j = 0; j < n_comps; ++j) {
+            if (s_keys[j] > key) { ++rank; prank += (s_status[j] == RMCV_CONTOUR_POSITIVE); }
+        }
+        const CompRec& c = comps[i];
+        rmcv_contour_info info;
+        info.first_x = key % W; info.first_y = key / W;
+        info.n_points = c.n_points;
+        info.status = stt;
+        info.area2 = c.area2;
+        info.bbox[0] = c.bbox[0]; info.bbox[1] = c.bbox[1];
+        info.bbox[2] = c.bbox[2] - c.bbox[0] + 1; info.bbox[3] = c.bbox[3] - c.bbox[1] + 1;
+        info.ellipse = c.ellipse;
+        info.fit_branch = c.fit_branch;
+        info.det0 = c.det0;
+        info.blob_index = stt == RMCV_CONTOUR_POSITIVE ? prank : -1;
+        oc[rank] = info;
+        atomicAdd(&s_nc, 1);
+        if (stt == RMCV_CONTOUR_POSITIVE) { ob[prank] = c.blob; atomicAdd(&s_np, 1); }
+        else if (stt == RMCV_CONTOUR_NEGATIVE) atomicAdd(&s_nn, 1);
+    }
+    __syncthreads();
+    // ---- pairs in lexicographic (i,j) order (src/objdetect.cpp:122-163)
+    const int P = s_np;
+    const long long npairs = (long long)P * (P - 1) / 2;
+    int base = 0;
+    for (long long k0 = 0; k0 < npairs; k0 += NT) {
+        const long long k = k0 + tid;
+        bool pass = false;
+        int i = 0, j = 0;
+        float gates[6];
+        if (k < npairs) {
+            pair_from_index(k, P, &i, &j);
+            pass = pair_gates(ob[i], ob[j], p.prm, gates);
+        }
+        int total;
+        const int pos = base + block_excl_scan(pass ? 1 : 0, &total, sh_scan);
+        if (pass) {
+            if (pos < A) {
+                rmcv_armour a;
+                make_armour(ob[i], ob[j], &a);
+                a.i = i; a.j = j;
+                for (int t = 0; t < 6; ++t) a.gates[t] = gates[t];
+                oa[pos] = a;
+            } else {
+                atomicOr(&s_flags, RMCV_FRAME_OVERFLOW_ARMOURS);
+            }
+        }
+        base += total;
+    }
+    const int n_arm = min(base, A);
+    // ---- claim dense space in the chunk's region of the pinned result arrays, write out
+    if (tid == 0) {
+        FrameCounters& al = sb.counters[p.frames];
+        s_off[0] = atomicAdd(&al.n_runs, s_nc);
+        s_off[1] = atomicAdd(&al.n_comps, P);
+        s_off[2] = atomicAdd(&al.n_holes, n_arm);
+        fc.n_comps = n_comps; fc.n_holes = s_nholes; fc.flags = s_flags;
+        fc.n_contours = s_nc; fc.n_positive = P; fc.n_negative = s_nn; fc.n_armours = n_arm;
+    }
+    __syncthreads();
+    const size_t base_c = (size_t)p.frame_base * C + s_off[0];
+    const size_t base_b = (size_t)p.frame_base * C + s_off[1];
+    const size_t base_a = (size_t)p.frame_base * A + s_off[2];
+    if (tid == 0) {
+        rmcv_frame_info fi;
+        fi.n_contours = s_nc; fi.n_positive = P; fi.n_negative = s_nn; fi.n_armours = n_arm;
+        fi.contour_offset = (int32_t)base_c; fi.blob_offset = (int32_t)base_b; fi.armour_offset = (int32_t)base_a;
+        fi.flags = s_flags;
+        p.o_frames[p.frame_base + frame] = fi;
+    }
+    copy_words(p.o_contours + base_c, oc, (size_t)s_nc * sizeof(rmcv_contour_info), tid, NT);
+    copy_words(p.o_blobs + base_b, ob, (size_t)P * sizeof(rmcv_lightblob), tid, NT);
+    copy_words(p.o_armours + base_a, oa, (size_t)n_arm * sizeof(rmcv_armour), tid, NT);
+}
+
+cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_smem_optin, cudaStream_t st, int64_t* launches) {
+    FrameParams p;
+    p.g = L.g; p.sb = *L.sb; p.prm = prm; p.frame_base = L.frame_base;
+    p.o_frames = L.o_frames; p.o_contours = L.o_contours; p.o_blobs = L.o_blobs; p.o_armours = L.o_armours;
+    p.frames = L.frames;
+    // shared-memory run capacity: aim at two CTAs per SM, never below 1024 runs
+    const char* env = getenv("RMCV_FRAME_RS");
+    int Rs = env ? atoi(env) : 4096;
+    if (Rs > L.g.R) Rs = L.g.R;
+    size_t smem = frame_smem_bytes(L.g.H, Rs, L.g.C);
+    while (smem > (size_t)max_smem_optin && Rs > 0) { Rs = Rs > 1024 ? Rs - 1024 : 0; smem = frame_smem_bytes(L.g.H, Rs, L.g.C); }
+    if (smem > (size_t)max_smem_optin) return cudaErrorInvalidConfiguration;
+    p.Rs = Rs;
+    cudaError_t e = cudaFuncSetAttribute(frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    frame_kernel<<<L.frames, 512, smem, st>>>(p);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------ standalone a2 / a3
+// rm::filter_lightblobs on caller-supplied ordered contours: one warp per contour.
+__global__ void __launch_bounds__(256) filter_lightblobs_kernel(const int32_t* xy, const int32_t* off, int n_contours,
+                                                                rmcv_params prm, rmcv_contour_info* infos,
+                                                                rmcv_lightblob* blobs) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= n_contours) return;
+    const int p0 = off[gw], p1 = off[gw + 1], n = p1 - p0;
+    const int32_t* pts = xy + 2 * (size_t)p0;
+    long long sx = 0, sy = 0, cross = 0;
+    int x0 = INT32_MAX, y0 = INT32_MAX, x1 = INT32_MIN, y1 = INT32_MIN;
+    for (int i = lane; i < n; i += 32) {
+        const int x = pts[2 * i], y = pts[2 * i + 1];
+        const int j = i == 0 ? n - 1 : i - 1;  // cv::contourArea: sum over (prev, cur)
+        const int px = pts[2 * j], py = pts[2 * j + 1];
+        sx += x; sy += y;
+        cross += (long long)px * y - (long long)py * x;
+        x0 = min(x0, x); y0 = min(y0, y); x1 = max(x1, x); y1 = max(y1, y);
+    }
+    sx = warp_sum(sx); sy = warp_sum(sy); cross = warp_sum(cross);
+    for (int o = 16; o > 0; o >>= 1) {
+        x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+        x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    rmcv_contour_info info;
+    memset(&info, 0, sizeof(info));
+    rmcv_lightblob blob;
+    memset(&blob, 0, sizeof(blob));
+    auto pass = [&](auto&& fn) {
+        for (int i = lane; i < n; i += 32) fn(pts[2 * i], pts[2 * i + 1]);
+    };
+    fit_and_gate(n, sx, sy, cross, prm, pass, &info.status, &info.fit_branch, &info.det0, &info.ellipse, &blob);
+    if (lane == 0) {
+        info.first_x = n > 0 ? pts[0] : 0; info.first_y = n > 0 ? pts[1] : 0;
+        info.n_points = n;
+        info.area2 = cross < 0 ? -cross : cross;
+        if (n > 0) { info.bbox[0] = x0; info.bbox[1] = y0; info.bbox[2] = x1 - x0 + 1; info.bbox[3] = y1 - y0 + 1; }
+        info.blob_index = -1;
+        infos[gw] = info;
+        blobs[gw] = blob;
+    }
+}
+
+__global__ void make_lightblobs_kernel(const rmcv_rotated_rect* boxes, int n, int target, rmcv_lightblob* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) make_lightblob(boxes[i], target, out + i);
+}
+
+cudaError_t launch_filter_lightblobs(const int32_t* d_xy, const int32_t* d_off, int n, const rmcv_params& prm,
+                                     rmcv_contour_info* d_infos, rmcv_lightblob* d_blobs, cudaStream_t st,
+                                     int64_t* launches) {
+    if (n <= 0) return cudaSuccess;
+    const int warps_per_block = 8;
+    filter_lightblobs_kernel<<<(n + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(d_xy, d_off, n, prm, d_infos,
+                                                                                          d_blobs);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_make_lightblobs(const rmcv_rotated_rect* d_boxes, int n, int target, rmcv_lightblob* d_out,
+                                   cudaStream_t st, int64_t* launches) {
+    if (n <= 0) return cudaSuccess;
+    make_lightblobs_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_boxes, n, target, d_out);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace rmcv

@@ -14,6 +14,7 @@
 //   * every input byte is read from HBM once (band halo rows are re-read through L2), every mask byte is
 //     written once with 16-byte stores.
 #include "common.cuh"
+#include "pairs.cuh"
 
 namespace rmcv {
 
@@ -76,6 +77,8 @@ struct PixelParams {
     int contiguous;      // pitch == row bytes: a chunk is one bulk copy
     int mask_vec;        // mask rows allow 16-byte stores
     uint32_t last_valid; // valid bits of the last word of a row
+    // run emission for the labelling stage (null = mask only)
+    int2* rows; uint32_t* run_x; uint16_t* run_y; FrameCounters* counters; int R;
     // Bayer only
     int bayer;           // 0 = BGR
     int px, py;          // parity (x&1, y&1) of the site that samples channel `plus`... see kernel
@@ -102,6 +105,7 @@ __host__ __device__ inline size_t pix_smem_bytes(int S, int RC, int srow, int BH
     size_t bars = ((size_t)S * 8 + 15) & ~(size_t)15;
     size_t t = (size_t)(BH + 2 * halo_rows) * TW * 4;
     size_t d = (size_t)(BH + 2) * TW * 4;
+    if (d < 256) d = 256;  // also used as scan scratch by the run emission
     return stage + bars + t + d;
 }
 
@@ -147,8 +151,62 @@ __device__ __forceinline__ void close_and_store(const PixelParams& p, uint32_t* 
         m[(size_t)j * WB + k] = mv;
         gbits[(size_t)j * WB + k] = mv;
     }
-    if (p.mask == nullptr) return;
     __syncthreads();
+    // ---- run emission: every maximal horizontal run of the band's final mask, in raster order inside the band.
+    // The band claims a contiguous range of the frame's run arrays with one atomicAdd; bands land in arrival order,
+    // rows[y] = (first, end) keeps every row addressable.  Start bits and end bits are ranked by one block scan.
+    if (p.run_x != nullptr) {
+        int* scratch = reinterpret_cast<int*>(d);  // d is dead after the erode
+        const int nwords = nout * WB;
+        const int per = (nwords + NT - 1) / NT;
+        const int w0 = min(nwords, tid * per), w1 = min(nwords, w0 + per);
+        int j0 = w0 / WB, k0 = w0 - j0 * WB;
+        int cnt = 0;
+        {
+            int k = k0;
+            for (int idx = w0; idx < w1; ++idx) {
+                const uint32_t w = m[idx];
+                const uint32_t prev = k > 0 ? (m[idx - 1] >> 31) : 0u;
+                cnt += __popc(w & ~((w << 1) | prev));
+                if (++k == WB) k = 0;
+            }
+        }
+        int total;
+        const int excl = block_excl_scan(cnt, &total, scratch);
+        if (tid == 0) scratch[40] = atomicAdd(&p.counters[frame].n_runs, total);
+        __syncthreads();
+        int rs = scratch[40] + excl;
+        const int R = p.R;
+        uint16_t* run_x16 = reinterpret_cast<uint16_t*>(p.run_x + (size_t)frame * R);
+        uint16_t* run_y = p.run_y + (size_t)frame * R;
+        int2* rows = p.rows + (size_t)frame * H;
+        int j = j0, k = k0;
+        for (int idx = w0; idx < w1; ++idx) {
+            const uint32_t w = m[idx];
+            const uint32_t prev = k > 0 ? (m[idx - 1] >> 31) : 0u;
+            const uint32_t next = k + 1 < WB ? (m[idx + 1] & 1u) : 0u;
+            uint32_t starts = w & ~((w << 1) | prev);
+            uint32_t ends = w & ~((w >> 1) | (next << 31));
+            int re = rs - (int)(prev & w & 1u);  // a run entering from the previous word is still open
+            const int y = y0 + j;
+            if (k == 0) rows[y].x = rs;
+            while (starts) {
+                const int b = __ffs(starts) - 1;
+                starts &= starts - 1;
+                if (rs < R) { run_x16[2 * rs] = (uint16_t)(k * 32 + b); run_y[rs] = (uint16_t)y; }
+                ++rs;
+            }
+            while (ends) {
+                const int b = __ffs(ends) - 1;
+                ends &= ends - 1;
+                if (re < R) run_x16[2 * re + 1] = (uint16_t)(k * 32 + b);
+                ++re;
+            }
+            if (k == WB - 1) rows[y].y = rs;
+            if (++k == WB) { k = 0; ++j; }
+        }
+    }
+    if (p.mask == nullptr) return;
     // ---- byte mask: one 16-byte store per 16 pixels
     const uint16_t* m16 = reinterpret_cast<const uint16_t*>(m);
     const int gpr16 = (p.W + 15) >> 4;
@@ -201,8 +259,8 @@ __global__ void __launch_bounds__(512) pixel_bgr_kernel(const PixelParams p) {
 
     const uint8_t* fsrc = p.src + (size_t)frame * p.frame_stride;
     const uint32_t rowbytes = (uint32_t)W * 3u;
-    auto issue = [&](int c) {  // one thread
-        const int s = c % S, r0 = cy0 + c * RC, nr = min(RC, cy1 - r0);
+    auto issue = [&](int c, int s) {  // one thread; chunk c into stage s
+        const int r0 = cy0 + c * RC, nr = min(RC, cy1 - r0);
         uint8_t* dst = smem + (size_t)s * stage_bytes;
         mbar_expect_tx(&bars[s], (uint32_t)nr * rowbytes);
         if (p.contiguous) {
@@ -212,7 +270,7 @@ __global__ void __launch_bounds__(512) pixel_bgr_kernel(const PixelParams p) {
         }
     };
     if (kBulk && tid == 0) {
-        for (int c = 0; c < S && c < nchunks; ++c) issue(c);
+        for (int c = 0; c < S && c < nchunks; ++c) issue(c, c);
     }
 
     const int gpr = p.gpr;
@@ -220,11 +278,13 @@ __global__ void __launch_bounds__(512) pixel_bgr_kernel(const PixelParams p) {
     const int acc0 = p.acc0;
     const Iter2D it0(tid, NT, gpr);
 
+    int s = 0;
+    uint32_t phase = 0;
     for (int c = 0; c < nchunks; ++c) {
-        const int s = c % S, r0 = cy0 + c * RC, nr = min(RC, cy1 - r0);
+        const int r0 = cy0 + c * RC, nr = min(RC, cy1 - r0);
         const uint8_t* stage = smem + (size_t)s * stage_bytes;
         if (kBulk) {
-            mbar_wait(&bars[s], (uint32_t)((c / S) & 1));
+            mbar_wait(&bars[s], phase);
         } else {
             uint8_t* wstage = smem + (size_t)s * stage_bytes;
             for (int r = 0; r < nr; ++r) {
@@ -254,7 +314,8 @@ __global__ void __launch_bounds__(512) pixel_bgr_kernel(const PixelParams p) {
             t16[(size_t)ty * TW * 2 + 2 + it.c] = (uint16_t)(~nb);
         }
         __syncthreads();  // stage s fully consumed (and t rows of this chunk visible)
-        if (kBulk && tid == 0 && c + S < nchunks) issue(c + S);
+        if (kBulk && tid == 0 && c + S < nchunks) issue(c + S, s);
+        if (++s == S) { s = 0; phase ^= 1u; }
     }
     close_and_store(p, t, d, frame, y0, nout, tid, NT);
 }
@@ -374,6 +435,7 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
                  ((((size_t)L.mask) & 15) == 0);
     p.lb = L.lower_bound;
     p.halo = 2;
+    p.rows = L.rows; p.run_x = L.run_x; p.run_y = L.run_y; p.counters = L.counters; p.R = L.R;
 
     // band height: tall bands amortise the 4 halo rows; small batches need more, shorter bands to fill 148 SMs
     int BH = env_int("RMCV_PIX_BH", 0);
@@ -422,19 +484,13 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
                           ((((size_t)L.src) & 15) == 0) && env_int("RMCV_PIX_NOBULK", 0) == 0;
         p.contiguous = (L.pitch == (size_t)L.W * 3) ? 1 : 0;
         int RC = env_int("RMCV_PIX_RC", 0);
-        if (RC <= 0) RC = max(1, min(16, 24576 / p.srow));
+        if (RC <= 0) RC = max(1, min(16, 16384 / p.srow));  // ~16 KB per TMA chunk (sweep: gpurun_out/sweep.log)
         if (RC > BH + 4) RC = BH + 4;
-        int S = env_int("RMCV_PIX_S", 3);
+        int S = env_int("RMCV_PIX_S", 4);
         int NT = env_int("RMCV_PIX_NT", 0);
-        if (NT <= 0) {  // threads: minimise idle lanes in the per-chunk item loop
-            int items = RC * p.gpr, best = 256, best_waste = 1 << 30;
-            for (int nt = 192; nt <= 512; nt += 32) {
-                int waste = ((items + nt - 1) / nt) * nt - items;
-                // prefer exact fits, then sizes near 256
-                int score = waste * 1024 / items * 8 + abs(nt - 320) / 32;
-                if (score < best_waste) { best_waste = score; best = nt; }
-            }
-            NT = best;
+        if (NT <= 0) {  // one 16-pixel group per thread per chunk, rounded up to whole warps
+            NT = ((RC * p.gpr + 31) / 32) * 32;
+            NT = max(128, min(512, NT));
         }
         p.RC = RC; p.S = S;
         size_t smem = pix_smem_bytes(S, RC, p.srow, BH, p.WB, 2);
@@ -492,12 +548,12 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
     int NT = env_int("RMCV_PIX_NT", 256);
     if (L.W < 3 || L.H < 3) return cudaErrorInvalidValue;
     size_t raw_bytes = ((size_t)(BH + 8) * p.srow + 15) & ~(size_t)15;
-    size_t smem = raw_bytes + 16 + (size_t)(BH + 4) * (p.WB + 2) * 4 + (size_t)(BH + 2) * (p.WB + 2) * 4;
+    size_t smem = raw_bytes + 16 + (size_t)(BH + 4) * (p.WB + 2) * 4 + (size_t)(BH + 2) * (p.WB + 2) * 4 + 256;
     while (smem > (size_t)max_smem && p.BH > 1) {
         p.BH = max(1, p.BH / 2); BH = p.BH;
         p.bands = (L.H + BH - 1) / BH;
         raw_bytes = ((size_t)(BH + 8) * p.srow + 15) & ~(size_t)15;
-        smem = raw_bytes + 16 + (size_t)(BH + 4) * (p.WB + 2) * 4 + (size_t)(BH + 2) * (p.WB + 2) * 4;
+        smem = raw_bytes + 16 + (size_t)(BH + 4) * (p.WB + 2) * 4 + (size_t)(BH + 2) * (p.WB + 2) * 4 + 256;
     }
     const long long grid2 = (long long)L.batch * p.bands;
     cudaError_t e = cudaFuncSetAttribute(pixel_bayer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
