@@ -468,13 +468,102 @@ RMCV_HD bool pair_gates(const rmcv_lightblob& bi, const rmcv_lightblob& bj, cons
     return true;
 }
 
-// The whole per-contour decision of rm::filter_lightblobs once n, area2 and the moment sums are known.
-struct FitInput {
-    int n;
-    int64_t area2;     // 2*contourArea (non-negative)
-    double cx, cy;     // mean in double (direct branch)
-    double s;          // sum |x-cx|+|y-cy| (direct branch)
-    Moments m;         // about (cx, cy)
+// ---------------------------------------------------------------------------------------------- integer contour sums
+// Everything cv::contourArea / cv::fitEllipseDirect need from a contour is a sum over its point multiset.  The kernels
+// accumulate them as EXACT integers (order-free, deterministic, atomics-friendly); the fit converts them to the centred
+// double sums the reference accumulates point by point.
+struct ContourSums {
+    long long n;                  // contour.size()
+    long long sx, sy;             // sum x, sum y (absolute pixel coordinates)
+    long long cross;              // shoelace sum: sum over contour edges p->q of x_p*y_q - x_q*y_p  (= +-2*contourArea)
+    long long xx, xy, yy;         // sums of dx^i dy^j with dx = x - ox, dy = y - oy
+    long long xxx, xxy, xyy, yyy;
+    long long xxxx, xxxy, xxyy, xyyy, yyyy;
+    long long s_int;              // sum |n*x - sx| + |n*y - sy|  (= n * sum(|x-cx|+|y-cy|), exact)
+    int ox, oy;                   // origin of the relative coordinates
 };
+
+RMCV_HD void sums_zero(ContourSums& c, int ox, int oy) {
+    c.n = c.sx = c.sy = c.cross = 0;
+    c.xx = c.xy = c.yy = c.xxx = c.xxy = c.xyy = c.yyy = 0;
+    c.xxxx = c.xxxy = c.xxyy = c.xyyy = c.yyyy = 0;
+    c.s_int = 0;
+    c.ox = ox; c.oy = oy;
+}
+
+RMCV_HD void sums_add_point(ContourSums& c, int x, int y) {
+    const long long dx = x - c.ox, dy = y - c.oy;
+    const long long xx = dx * dx, xy = dx * dy, yy = dy * dy;
+    c.n += 1; c.sx += x; c.sy += y;
+    c.xx += xx; c.xy += xy; c.yy += yy;
+    c.xxx += xx * dx; c.xxy += xx * dy; c.xyy += dx * yy; c.yyy += yy * dy;
+    c.xxxx += xx * xx; c.xxxy += xx * xy; c.xxyy += xx * yy; c.xyyy += xy * yy; c.yyyy += yy * yy;
+}
+
+// Moment sums about (ox + ax, oy + ay) from the exact sums about (ox, oy): binomial shift in double.
+RMCV_HD void centred_moments(const ContourSums& c, double ax, double ay, Moments* m) {
+    const double n = (double)c.n;
+    const double R10 = (double)(c.sx - c.n * c.ox), R01 = (double)(c.sy - c.n * c.oy);
+    const double R20 = (double)c.xx, R11 = (double)c.xy, R02 = (double)c.yy;
+    const double R30 = (double)c.xxx, R21 = (double)c.xxy, R12 = (double)c.xyy, R03 = (double)c.yyy;
+    const double R40 = (double)c.xxxx, R31 = (double)c.xxxy, R22 = (double)c.xxyy, R13 = (double)c.xyyy, R04 = (double)c.yyyy;
+    const double a = ax, b = ay, a2 = a * a, b2 = b * b, a3 = a2 * a, b3 = b2 * b, a4 = a2 * a2, b4 = b2 * b2;
+    m->n = n;
+    m->x = R10 - n * a;
+    m->y = R01 - n * b;
+    m->xx = R20 - 2.0 * a * R10 + n * a2;
+    m->yy = R02 - 2.0 * b * R01 + n * b2;
+    m->xy = R11 - a * R01 - b * R10 + n * a * b;
+    m->xxx = R30 - 3.0 * a * R20 + 3.0 * a2 * R10 - n * a3;
+    m->yyy = R03 - 3.0 * b * R02 + 3.0 * b2 * R01 - n * b3;
+    m->xxy = R21 - b * R20 - 2.0 * a * R11 + 2.0 * a * b * R10 + a2 * R01 - n * a2 * b;
+    m->xyy = R12 - a * R02 - 2.0 * b * R11 + 2.0 * a * b * R01 + b2 * R10 - n * a * b2;
+    m->xxxx = R40 - 4.0 * a * R30 + 6.0 * a2 * R20 - 4.0 * a3 * R10 + n * a4;
+    m->yyyy = R04 - 4.0 * b * R03 + 6.0 * b2 * R02 - 4.0 * b3 * R01 + n * b4;
+    m->xxxy = R31 - b * R30 - 3.0 * a * R21 + 3.0 * a * b * R20 + 3.0 * a2 * R11 - 3.0 * a2 * b * R10 - a3 * R01 + n * a3 * b;
+    m->xyyy = R13 - a * R03 - 3.0 * b * R12 + 3.0 * a * b * R02 + 3.0 * b2 * R11 - 3.0 * a * b2 * R01 - b3 * R10 + n * a * b3;
+    m->xxyy = R22 - 2.0 * a * R12 + a2 * R02 - 2.0 * b * R21 + 4.0 * a * b * R11 - 2.0 * a2 * b * R01 + b2 * R20 - 2.0 * a * b2 * R10 +
+              n * a2 * b2;
+}
+
+// Does this contour reach the fit at all?  (src/objdetect.cpp:64)
+RMCV_HD bool contour_is_fitted(long long n, long long cross, const rmcv_params& prm) {
+    const long long area2 = cross < 0 ? -cross : cross;
+    const double area = (double)area2 * 0.5;
+    return n >= 6 && area >= prm.area_min && area <= prm.area_max;
+}
+
+// Loop body of rm::filter_lightblobs (src/objdetect.cpp:62-84) from the integer sums of one contour.
+RMCV_HD void fit_contour(const ContourSums& c, const rmcv_params& prm, int* status, int* branch, float* det0_out,
+                         rmcv_rotated_rect* ell, rmcv_lightblob* blob) {
+    *status = RMCV_CONTOUR_SKIPPED;
+    *branch = RMCV_FIT_NONE;
+    *det0_out = 0.f;
+    ell->cx = ell->cy = ell->w = ell->h = ell->angle = 0.f;
+    if (!contour_is_fitted(c.n, c.cross, prm)) return;
+    const double n = (double)c.n;
+    // ---- cv::fitEllipseDirect, first attempt: centre and L1 spread in double
+    const double cx = (double)c.sx / n, cy = (double)c.sy / n;
+    const double s = (double)c.s_int / n;
+    double scale = 100.0 / (s > RMCV_FLT_EPSILON ? s : RMCV_FLT_EPSILON);
+    Moments m;
+    centred_moments(c, cx - (double)c.ox, cy - (double)c.oy, &m);
+    double det = 0.0;
+    const bool ok = direct_fit(m, scale, cx, cy, ell, &det);
+    *det0_out = (float)det;
+    if (ok) {
+        *branch = RMCV_FIT_DIRECT;
+    } else {
+        // ---- singular: the reference retries with RNG jitter and then returns cv::fitEllipseNoDirect, which keeps the
+        // centre as Point2f.  x - c32 is exact in fp32 for every blob whose extent is below its centroid's binade, so
+        // the float-centred sums are the same exact sums shifted to c32 (DESIGN.md "fallback centring").
+        const float c32x = fdiv((float)c.sx, (float)c.n), c32y = fdiv((float)c.sy, (float)c.n);
+        centred_moments(c, (double)c32x - (double)c.ox, (double)c32y - (double)c.oy, &m);
+        nodirect_fit(m, scale, c32x, c32y, ell);
+        *branch = RMCV_FIT_FALLBACK;
+    }
+    *status = blob_gates(*ell, prm);
+    if (*status == RMCV_CONTOUR_POSITIVE) make_lightblob(*ell, prm.target, blob);
+}
 
 }  // namespace rmcv

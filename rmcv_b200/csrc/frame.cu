@@ -277,7 +277,10 @@ struct FrameParams {
     rmcv_armour* o_armours;
     int Rs;      // run capacity of the shared-memory arrays
     int frames;  // frames in this chunk (index of the allocator entry in sb.counters)
+    long long* dbg_clock;  // optional [frames][16] phase timestamps (RMCV_FRAME_TIMING=1), else null
 };
+
+#define RMCV_PHASE(i) do { if (p.dbg_clock && tid == 0) p.dbg_clock[(size_t)frame * 16 + (i)] = clock64(); } while (0)
 
 __host__ __device__ inline size_t frame_smem_bytes(int H, int Rs, int C) {
     size_t b = 0;
@@ -335,6 +338,7 @@ __global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
     f.cid = in_smem ? s_cid : sb.run_cid + (size_t)frame * R;
     f.n_runs = n_runs; f.W = W; f.H = H;
 
+    RMCV_PHASE(0);
     if (tid == 0) {
         s_ncomp = 0; s_nholes = 0; s_np = 0; s_nc = 0; s_nn = 0;
         s_flags = raw_runs > R ? RMCV_FRAME_OVERFLOW_RUNS : 0;
@@ -348,6 +352,7 @@ __global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
         for (int r = tid; r < n_runs; r += NT) { s_run_x[r] = g_run_x[r]; s_run_y[r] = g_run_y[r]; }
     }
     __syncthreads();
+    RMCV_PHASE(1);
     // ---- init forests
     for (int r = tid; r < n_runs; r += NT) {
         f.parent[r] = r;
@@ -357,6 +362,7 @@ __global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
     }
     if (tid == 0) f.gparent[0] = 0;
     __syncthreads();
+    RMCV_PHASE(2);
     // ---- unions
     for (int r = tid; r < n_runs; r += NT) {
         const uint32_t rx = f.run_x[r];
@@ -375,6 +381,7 @@ __global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
         }
     }
     __syncthreads();
+    RMCV_PHASE(3);
     // ---- flatten, enumerate components
     for (int r = tid; r < n_runs; r += NT) {
         const int root = uf_find(f.parent, r);
@@ -417,6 +424,7 @@ __global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
         atomicMin(&st->firstkey, y * W + xs);
     }
     __syncthreads();
+    RMCV_PHASE(4);
     const int n_comps = min(s_ncomp, C);
     const bool has_holes = s_nholes > 0;
     CompRec* comps = sb.comps + (size_t)frame * C;
@@ -455,6 +463,7 @@ __global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
         }
     }
     __syncthreads();
+    RMCV_PHASE(5);
     // ---- order: rank = number of external components with a larger first-pixel key (reverse raster order)
     rmcv_contour_info* oc = sb.s_contours + (size_t)frame * C;
     rmcv_lightblob* ob = sb.s_blobs + (size_t)frame * C;
@@ -485,6 +494,7 @@ __global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
         else if (stt == RMCV_CONTOUR_NEGATIVE) atomicAdd(&s_nn, 1);
     }
     __syncthreads();
+    RMCV_PHASE(6);
     // ---- pairs in lexicographic (i,j) order (src/objdetect.cpp:122-163)
     const int P = s_np;
     const long long npairs = (long long)P * (P - 1) / 2;
@@ -514,6 +524,7 @@ __global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
         base += total;
     }
     const int n_arm = min(base, A);
+    RMCV_PHASE(7);
     // ---- claim dense space in the chunk's region of the pinned result arrays, write out
     if (tid == 0) {
         FrameCounters& al = sb.counters[p.frames];
@@ -537,6 +548,8 @@ __global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
     copy_words(p.o_contours + base_c, oc, (size_t)s_nc * sizeof(rmcv_contour_info), tid, NT);
     copy_words(p.o_blobs + base_b, ob, (size_t)P * sizeof(rmcv_lightblob), tid, NT);
     copy_words(p.o_armours + base_a, oa, (size_t)n_arm * sizeof(rmcv_armour), tid, NT);
+    __syncthreads();
+    RMCV_PHASE(8);
 }
 
 cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_smem_optin, cudaStream_t st, int64_t* launches) {
@@ -552,10 +565,29 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
     while (smem > (size_t)max_smem_optin && Rs > 0) { Rs = Rs > 1024 ? Rs - 1024 : 0; smem = frame_smem_bytes(L.g.H, Rs, L.g.C); }
     if (smem > (size_t)max_smem_optin) return cudaErrorInvalidConfiguration;
     p.Rs = Rs;
+    p.dbg_clock = nullptr;
+    static long long* dbg = nullptr;
+    const bool timing = getenv("RMCV_FRAME_TIMING") != nullptr;
+    if (timing) {
+        if (!dbg) cudaMalloc(reinterpret_cast<void**>(&dbg), sizeof(long long) * 16 * 4096);
+        p.dbg_clock = dbg;
+    }
     cudaError_t e = cudaFuncSetAttribute(frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     frame_kernel<<<L.frames, 512, smem, st>>>(p);
     if (launches) ++*launches;
+    if (timing) {  // debug aid: average cycles per phase over the chunk's frames
+        cudaStreamSynchronize(st);
+        static long long h[16 * 4096];
+        const int nf = L.frames < 4096 ? L.frames : 4096;
+        cudaMemcpy(h, dbg, sizeof(long long) * 16 * nf, cudaMemcpyDeviceToHost);
+        double acc[9] = {0};
+        for (int f = 0; f < nf; ++f)
+            for (int i = 1; i <= 8; ++i) acc[i] += (double)(h[f * 16 + i] - h[f * 16 + i - 1]);
+        fprintf(stderr, "[frame timing, cycles/frame] load %.0f init %.0f union %.0f flatten+stats %.0f blob %.0f order %.0f pairs %.0f out %.0f | total %.0f\n",
+                acc[1] / nf, acc[2] / nf, acc[3] / nf, acc[4] / nf, acc[5] / nf, acc[6] / nf, acc[7] / nf, acc[8] / nf,
+                (acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6] + acc[7] + acc[8]) / nf);
+    }
     return cudaGetLastError();
 }
 

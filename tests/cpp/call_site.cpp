@@ -1,0 +1,48 @@
+// The reference's call site (executable/main.cpp:172-176) compiled against include/rmcv_gpu/rm_shim.hpp in its
+// OpenCV-free mode.  Reads a raw BGR frame (W H then W*H*3 bytes) from argv[1], runs the three rm:: calls with the
+// reference's literal parameters and prints the results as JSON for tests/test_gpu_shim.py to compare with the oracle.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../include/rmcv_gpu/rm_shim.hpp"
+
+int main(int argc, char** argv) {
+    if (argc < 2) { fprintf(stderr, "usage: call_site frame.bin\n"); return 2; }
+    FILE* f = fopen(argv[1], "rb");
+    if (!f) { perror("open"); return 2; }
+    int wh[2];
+    if (fread(wh, sizeof(int), 2, f) != 2) return 2;
+    cv::Mat image(wh[1], wh[0], 3);
+    if (fread(image.data, 1, (size_t)wh[0] * wh[1] * 3, f) != (size_t)wh[0] * wh[1] * 3) return 2;
+    fclose(f);
+    try {
+        auto [contours, binary] = rm::extract_color(image, rm::CAMP_BLUE, 80);
+        auto [positive, negtive] = rm::filter_lightblobs(contours, 70, {1.5, 80}, {10, 99999}, rm::CAMP_BLUE);
+        auto armours = rm::filter_armours(positive, 12, 22, 0.4, rm::CAMP_BLUE);
+        // fused variant must agree with the three-call variant
+        rmcv_params prm;
+        rmcv_default_params(&prm);
+        auto det = rm::gpu::detect(image, prm);
+        unsigned long long fg = 0;
+        for (int y = 0; y < binary.rows; ++y)
+            for (int x = 0; x < binary.cols; ++x) fg += binary.data[(size_t)y * binary.step + x] == 255;
+        printf("{\"n_contours\": %zu, \"n_positive\": %zu, \"n_negative\": %zu, \"n_armours\": %zu, \"mask_fg\": %llu, "
+               "\"fused_positive\": %zu, \"fused_armours\": %zu,\n \"contour_sizes\": [",
+               contours.size(), positive.size(), negtive.size(), armours.size(), fg, det.positive.size(), det.armours.size());
+        for (size_t k = 0; k < contours.size(); ++k) printf("%s%zu", k ? "," : "", contours[k].size());
+        printf("],\n \"first_points\": [");
+        for (size_t k = 0; k < contours.size(); ++k) printf("%s[%d,%d]", k ? "," : "", contours[k][0].x, contours[k][0].y);
+        printf("],\n \"blob_centers\": [");
+        for (size_t k = 0; k < positive.size(); ++k) printf("%s[%.6f,%.6f,%.6f]", k ? "," : "", positive[k].center.x, positive[k].center.y, positive[k].angle);
+        printf("],\n \"armour_boxes\": [");
+        for (size_t k = 0; k < armours.size(); ++k)
+            printf("%s[%.1f,%.1f,%.1f,%.1f]", k ? "," : "", armours[k].bounding_box.x, armours[k].bounding_box.y, armours[k].bounding_box.width,
+                   armours[k].bounding_box.height);
+        printf("]}\n");
+    } catch (const rm::gpu::error& e) {
+        fprintf(stderr, "rm::gpu::error %d: %s\n", e.status, e.what());
+        return 3;
+    }
+    return 0;
+}

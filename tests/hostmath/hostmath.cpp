@@ -36,6 +36,25 @@ int hm_fit_points(const int32_t* xy, int n, rmcv_rotated_rect* box, double* det0
     return RMCV_FIT_FALLBACK;
 }
 
+// The integer-sum route the kernels take: exact sums about an origin, then fit_contour.
+int hm_fit_points_int(const int32_t* xy, int n, int ox, int oy, const rmcv_params* prm, rmcv_rotated_rect* box, double* det0, int* status) {
+    ContourSums c;
+    sums_zero(c, ox, oy);
+    for (int i = 0; i < n; ++i) {
+        sums_add_point(c, xy[2 * i], xy[2 * i + 1]);
+        const int j = i == 0 ? n - 1 : i - 1;
+        c.cross += (long long)xy[2 * j] * xy[2 * i + 1] - (long long)xy[2 * j + 1] * xy[2 * i];
+    }
+    for (int i = 0; i < n; ++i) {
+        const long long ax = c.n * xy[2 * i] - c.sx, ay = c.n * xy[2 * i + 1] - c.sy;
+        c.s_int += (ax < 0 ? -ax : ax) + (ay < 0 ? -ay : ay);
+    }
+    int branch; float d0; rmcv_lightblob blob;
+    fit_contour(c, *prm, status, &branch, &d0, box, &blob);
+    *det0 = (double)d0;
+    return branch;
+}
+
 void hm_make_lightblob(const rmcv_rotated_rect* box, int target, rmcv_lightblob* out) { make_lightblob(*box, target, out); }
 int hm_blob_gates(const rmcv_rotated_rect* e, const rmcv_params* p) { return blob_gates(*e, *p); }
 int hm_pair_gates(const rmcv_lightblob* a, const rmcv_lightblob* b, const rmcv_params* p, float* gates) {

