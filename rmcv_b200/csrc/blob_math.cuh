@@ -500,14 +500,13 @@ RMCV_HD void sums_add_point(ContourSums& c, int x, int y) {
     c.xxxx += xx * xx; c.xxxy += xx * xy; c.xxyy += xx * yy; c.xyyy += xy * yy; c.yyyy += yy * yy;
 }
 
-// Moment sums about (ox + ax, oy + ay) from the exact sums about (ox, oy): binomial shift in double.
-RMCV_HD void centred_moments(const ContourSums& c, double ax, double ay, Moments* m) {
-    const double n = (double)c.n;
-    const double R10 = (double)(c.sx - c.n * c.ox), R01 = (double)(c.sy - c.n * c.oy);
-    const double R20 = (double)c.xx, R11 = (double)c.xy, R02 = (double)c.yy;
-    const double R30 = (double)c.xxx, R21 = (double)c.xxy, R12 = (double)c.xyy, R03 = (double)c.yyy;
-    const double R40 = (double)c.xxxx, R31 = (double)c.xxxy, R22 = (double)c.xxyy, R13 = (double)c.xyyy, R04 = (double)c.yyyy;
-    const double a = ax, b = ay, a2 = a * a, b2 = b * b, a3 = a2 * a, b3 = b2 * b, a4 = a2 * a2, b4 = b2 * b2;
+// Moment sums about (O + (a, b)) from the sums R about O: binomial shift in double.
+RMCV_HD void shift_moments(const Moments& R, double a, double b, Moments* m) {
+    const double n = R.n;
+    const double R10 = R.x, R01 = R.y, R20 = R.xx, R11 = R.xy, R02 = R.yy;
+    const double R30 = R.xxx, R21 = R.xxy, R12 = R.xyy, R03 = R.yyy;
+    const double R40 = R.xxxx, R31 = R.xxxy, R22 = R.xxyy, R13 = R.xyyy, R04 = R.yyyy;
+    const double a2 = a * a, b2 = b * b, a3 = a2 * a, b3 = b2 * b, a4 = a2 * a2, b4 = b2 * b2;
     m->n = n;
     m->x = R10 - n * a;
     m->y = R01 - n * b;
@@ -526,6 +525,15 @@ RMCV_HD void centred_moments(const ContourSums& c, double ax, double ay, Moments
               n * a2 * b2;
 }
 
+// The exact integer sums about (ox, oy) as doubles (exact below 2^53, correctly rounded above).
+RMCV_HD void sums_to_moments(const ContourSums& c, Moments* R) {
+    R->n = (double)c.n;
+    R->x = (double)(c.sx - c.n * c.ox); R->y = (double)(c.sy - c.n * c.oy);
+    R->xx = (double)c.xx; R->xy = (double)c.xy; R->yy = (double)c.yy;
+    R->xxx = (double)c.xxx; R->xxy = (double)c.xxy; R->xyy = (double)c.xyy; R->yyy = (double)c.yyy;
+    R->xxxx = (double)c.xxxx; R->xxxy = (double)c.xxxy; R->xxyy = (double)c.xxyy; R->xyyy = (double)c.xyyy; R->yyyy = (double)c.yyyy;
+}
+
 // Does this contour reach the fit at all?  (src/objdetect.cpp:64)
 RMCV_HD bool contour_is_fitted(long long n, long long cross, const rmcv_params& prm) {
     const long long area2 = cross < 0 ? -cross : cross;
@@ -533,21 +541,24 @@ RMCV_HD bool contour_is_fitted(long long n, long long cross, const rmcv_params& 
     return n >= 6 && area >= prm.area_min && area <= prm.area_max;
 }
 
-// Loop body of rm::filter_lightblobs (src/objdetect.cpp:62-84) from the integer sums of one contour.
-RMCV_HD void fit_contour(const ContourSums& c, const rmcv_params& prm, int* status, int* branch, float* det0_out,
-                         rmcv_rotated_rect* ell, rmcv_lightblob* blob) {
+// Loop body of rm::filter_lightblobs (src/objdetect.cpp:62-84) once the sums of one contour are known:
+//   n, sum_x, sum_y, cross  exact integers in absolute pixel coordinates,
+//   R                       moment sums about the origin (Ox, Oy),
+//   s                       L1 spread  sum |x-cx| + |y-cy|  about the double mean.
+RMCV_HD void fit_from_moments(long long n_i, long long sum_x, long long sum_y, long long cross, const Moments& R, double Ox,
+                              double Oy, double s, const rmcv_params& prm, int* status, int* branch, float* det0_out,
+                              rmcv_rotated_rect* ell, rmcv_lightblob* blob) {
     *status = RMCV_CONTOUR_SKIPPED;
     *branch = RMCV_FIT_NONE;
     *det0_out = 0.f;
     ell->cx = ell->cy = ell->w = ell->h = ell->angle = 0.f;
-    if (!contour_is_fitted(c.n, c.cross, prm)) return;
-    const double n = (double)c.n;
+    if (!contour_is_fitted(n_i, cross, prm)) return;
+    const double n = (double)n_i;
     // ---- cv::fitEllipseDirect, first attempt: centre and L1 spread in double
-    const double cx = (double)c.sx / n, cy = (double)c.sy / n;
-    const double s = (double)c.s_int / n;
+    const double cx = (double)sum_x / n, cy = (double)sum_y / n;
     double scale = 100.0 / (s > RMCV_FLT_EPSILON ? s : RMCV_FLT_EPSILON);
     Moments m;
-    centred_moments(c, cx - (double)c.ox, cy - (double)c.oy, &m);
+    shift_moments(R, cx - Ox, cy - Oy, &m);
     double det = 0.0;
     const bool ok = direct_fit(m, scale, cx, cy, ell, &det);
     *det0_out = (float)det;
@@ -557,13 +568,22 @@ RMCV_HD void fit_contour(const ContourSums& c, const rmcv_params& prm, int* stat
         // ---- singular: the reference retries with RNG jitter and then returns cv::fitEllipseNoDirect, which keeps the
         // centre as Point2f.  x - c32 is exact in fp32 for every blob whose extent is below its centroid's binade, so
         // the float-centred sums are the same exact sums shifted to c32 (DESIGN.md "fallback centring").
-        const float c32x = fdiv((float)c.sx, (float)c.n), c32y = fdiv((float)c.sy, (float)c.n);
-        centred_moments(c, (double)c32x - (double)c.ox, (double)c32y - (double)c.oy, &m);
+        const float c32x = fdiv((float)sum_x, (float)n_i), c32y = fdiv((float)sum_y, (float)n_i);
+        shift_moments(R, (double)c32x - Ox, (double)c32y - Oy, &m);
         nodirect_fit(m, scale, c32x, c32y, ell);
         *branch = RMCV_FIT_FALLBACK;
     }
     *status = blob_gates(*ell, prm);
     if (*status == RMCV_CONTOUR_POSITIVE) make_lightblob(*ell, prm.target, blob);
+}
+
+// Same, from the exact integer sums.
+RMCV_HD void fit_contour(const ContourSums& c, const rmcv_params& prm, int* status, int* branch, float* det0_out,
+                         rmcv_rotated_rect* ell, rmcv_lightblob* blob) {
+    Moments R;
+    sums_to_moments(c, &R);
+    const double s = c.n > 0 ? (double)c.s_int / (double)c.n : 0.0;
+    fit_from_moments(c.n, c.sx, c.sy, c.cross, R, (double)c.ox, (double)c.oy, s, prm, status, branch, det0_out, ell, blob);
 }
 
 }  // namespace rmcv

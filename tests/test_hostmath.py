@@ -92,3 +92,40 @@ def test_extend_cord_special_cases(hm):
     a = O.make_armour(ol, orr)
     ic = np.array([[ar.icon[k][0], ar.icon[k][1]] for k in range(4)], np.float32)
     assert np.array_equal(ic, a.icon) and tuple(ar.bounding_box) == a.bounding_box
+
+
+def fit_int(hm, c, ox, oy, P):
+    xy = np.ascontiguousarray(c, np.int32)
+    box, det, status = A.RotatedRect(), C.c_double(), C.c_int()
+    br = hm.hm_fit_points_int(xy.ctypes.data_as(C.c_void_p), len(xy), int(ox), int(oy), C.byref(P), C.byref(box), C.byref(det),
+                              C.byref(status))
+    return br, box, det.value, status.value
+
+
+def test_integer_sum_route_matches_oracle_and_point_route(hm):
+    """The kernels accumulate exact integer sums about a per-component origin (the root run) and shift them to the
+    mean in double; this must agree with the oracle for any origin inside or near the blob."""
+    P = A.Params(1, 80, 70, 1.5, 80, 10, 99999, 12, 22, 0.4)
+    nfit = nband = 0
+    worst = [0.0, 0.0, 0.0]
+    for seed in range(8, 14):
+        img = synth.make_frame(seed, 1280, 1024, synth.plates_for_seed(seed))
+        fr = O.detect_frame(img)
+        for c, v in zip(fr.contours, fr.verdicts):
+            xs, ys = np.asarray(c)[:, 0], np.asarray(c)[:, 1]
+            for ox, oy in ((xs.min(), ys.min()), (xs.max(), ys.max()), (int(c[0][0]), int(c[0][1])), (xs.min() - 700, ys.max() + 700)):
+                br, box, det, status = fit_int(hm, c, ox, oy, P)
+                assert status == v.status
+                if v.status == 0:
+                    continue
+                e = v.ellipse
+                if 0.7e-10 <= det <= 1.0e-10 * (1 + 1e-6):
+                    nband += 1
+                    continue
+                nfit += 1
+                worst[0] = max(worst[0], abs(box.cx - e.cx), abs(box.cy - e.cy))
+                worst[1] = max(worst[1], abs(box.w - e.w) / e.w, abs(box.h - e.h) / e.h)
+                if e.h / e.w > 1.0001:
+                    worst[2] = max(worst[2], abs(((box.angle - e.angle) + 90) % 180 - 90))
+    assert nfit > 400
+    assert worst[0] <= 1e-3 and worst[1] <= 1e-5 and worst[2] <= 1e-3, worst
