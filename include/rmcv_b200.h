@@ -128,7 +128,7 @@ typedef struct rmcv_config {
     int32_t max_width, max_height; /* largest frame this ctx will see                            */
     int32_t max_batch;             /* largest batch of one detect call                           */
     int32_t chunk_frames;          /* frames per internal pipeline step; 0 = default             */
-    int32_t max_runs_per_frame;    /* 0 = default max(65536, W*H/64)                             */
+    int32_t max_runs_per_frame;    /* 0 = default max(16384, W*H/32)                             */
     int32_t max_blobs_per_frame;   /* components per frame; 0 = default 1024                     */
     int32_t max_armours_per_frame; /* 0 = default 2048                                           */
     int32_t flags;                 /* reserved, 0                                                */

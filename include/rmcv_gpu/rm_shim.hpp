@@ -45,6 +45,23 @@ struct Mat {
     Mat() = default;
     Mat(int r, int c, int ch) : rows(r), cols(c), chans(ch), step((size_t)c * ch), storage((size_t)r * c * ch) { data = storage.data(); }
     Mat(int r, int c, int ch, uint8_t* ext, size_t st) : rows(r), cols(c), chans(ch), step(st), data(ext) {}
+    // an owning Mat must re-point `data` at its own storage when copied or moved
+    Mat(const Mat& o) : rows(o.rows), cols(o.cols), chans(o.chans), step(o.step), data(o.data), storage(o.storage) {
+        if (!o.storage.empty()) data = storage.data();
+    }
+    Mat(Mat&& o) noexcept : rows(o.rows), cols(o.cols), chans(o.chans), step(o.step), data(o.data) {
+        const bool owning = !o.storage.empty();
+        storage = std::move(o.storage);
+        if (owning) data = storage.data();
+        o.data = nullptr; o.rows = o.cols = 0;
+    }
+    Mat& operator=(Mat o) {
+        rows = o.rows; cols = o.cols; chans = o.chans; step = o.step;
+        const bool owning = !o.storage.empty();
+        storage = std::move(o.storage);
+        data = owning ? storage.data() : o.data;
+        return *this;
+    }
     int channels() const { return chans; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
 };

@@ -60,8 +60,10 @@ int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
     RMCV_CUDA(ctx, dalloc(&sb.run_x, CF * R));
     RMCV_CUDA(ctx, dalloc(&sb.run_y, CF * R));
     RMCV_CUDA(ctx, dalloc(&sb.parent, CF * R));
-    RMCV_CUDA(ctx, dalloc(&sb.gparent, CF * (R + 1)));
+    RMCV_CUDA(ctx, dalloc(&sb.gparent, CF * (R + 2)));
     RMCV_CUDA(ctx, dalloc(&sb.run_cid, CF * R));
+    RMCV_CUDA(ctx, dalloc(&sb.sorted, CF * (R + 2)));
+    RMCV_CUDA(ctx, dalloc(&sb.acc, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.comp_root, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.comps, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.counters, CF + 1));
@@ -82,7 +84,7 @@ int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
 
 void free_slot(SlotBuffers& sb) {
     cudaFree(sb.bits); cudaFree(sb.rows); cudaFree(sb.run_x); cudaFree(sb.run_y);
-    cudaFree(sb.parent); cudaFree(sb.gparent); cudaFree(sb.run_cid); cudaFree(sb.comp_root); cudaFree(sb.comps);
+    cudaFree(sb.parent); cudaFree(sb.gparent); cudaFree(sb.run_cid); cudaFree(sb.sorted); cudaFree(sb.acc); cudaFree(sb.comp_root); cudaFree(sb.comps);
     cudaFree(sb.counters); cudaFree(sb.s_contours); cudaFree(sb.s_blobs); cudaFree(sb.s_armours);
     if (sb.frames) cudaFree(sb.frames);
     if (sb.masks) cudaFree(sb.masks);
@@ -96,7 +98,7 @@ int check_geometry(rmcv_ctx* ctx, int width, int height, int batch) {
     if (width <= 0 || height <= 0 || batch <= 0) return set_err(ctx, RMCV_ERR_INVALID_ARG, "width, height and batch must be positive");
     if (width > ctx->cfg.max_width || height > ctx->cfg.max_height || batch > ctx->cfg.max_batch)
         return set_err(ctx, RMCV_ERR_INVALID_ARG, "frame size or batch exceeds the ctx maxima");
-    if (width > 65535) return set_err(ctx, RMCV_ERR_INVALID_ARG, "width above 65535 is not supported");
+    if (width > 32767 || height > 32767) return set_err(ctx, RMCV_ERR_INVALID_ARG, "frames above 32767 px per side are not supported");
     return RMCV_OK;
 }
 
@@ -273,7 +275,7 @@ int rmcv_device_count(int* count) {
 int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
     if (!cfg || !out) return RMCV_ERR_INVALID_ARG;
     *out = nullptr;
-    if (cfg->max_width <= 0 || cfg->max_height <= 0 || cfg->max_batch <= 0 || cfg->max_width > 65535) return RMCV_ERR_INVALID_ARG;
+    if (cfg->max_width <= 0 || cfg->max_height <= 0 || cfg->max_batch <= 0 || cfg->max_width > 32767 || cfg->max_height > 32767) return RMCV_ERR_INVALID_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return RMCV_ERR_NO_DEVICE; }
     if (cfg->device < 0 || cfg->device >= ndev) return RMCV_ERR_INVALID_ARG;
@@ -297,16 +299,19 @@ int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
     Geometry& g = ctx->cap;
     g.W = cfg->max_width; g.H = cfg->max_height; g.WB = (g.W + 31) / 32;
     const long long px = (long long)g.W * g.H;
-    long long R = cfg->max_runs_per_frame > 0 ? cfg->max_runs_per_frame : (px / 64 > 65536 ? px / 64 : 65536);
+    long long R = cfg->max_runs_per_frame > 0 ? cfg->max_runs_per_frame : (px / 32 > 16384 ? px / 32 : 16384);
     if (R > px / 2 + g.H) R = px / 2 + g.H;
     g.R = (int)R;
     g.C = cfg->max_blobs_per_frame > 0 ? cfg->max_blobs_per_frame : 512;
     g.A = cfg->max_armours_per_frame > 0 ? cfg->max_armours_per_frame : 1024;
     int CF = cfg->chunk_frames;
     if (CF <= 0) {
+        // a chunk is one launch of each kernel: the frame kernel runs one CTA per frame, so a chunk should hold a few
+        // CTAs per SM; bounded so that the staging copy of a chunk of host frames stays below 2.5 GB
         const long long frame_bytes = px * 3;
-        long long c = (512LL << 20) / frame_bytes;
-        CF = (int)(c < 1 ? 1 : (c > 128 ? 128 : c));
+        long long c = (2560LL << 20) / frame_bytes;
+        const long long want = 4LL * ctx->sm_count;
+        CF = (int)(c < 1 ? 1 : (c > want ? want : c));
     }
     if (CF > cfg->max_batch) CF = cfg->max_batch;
     ctx->CF = CF;

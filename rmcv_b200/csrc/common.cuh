@@ -26,10 +26,16 @@ struct CompRec {            // one 8-connected component after the blob kernel
     rmcv_lightblob blob;
 };
 
-struct CompStat {           // per component, built in shared memory by the frame kernel
-    int32_t x0, y0, x1, y1; // bounding box (inclusive)
+struct CompAcc {            // exact integer sums over the contour point multiset of one component (frame kernel:
+                            // written by the warp that owns the component, read by the thread that fits it)
+    long long n, sx, sy;    // contour.size(), sum x, sum y (absolute pixel coordinates)
+    long long cross;        // shoelace sum = +-2*contourArea
+    long long xx, xy, yy, xxx, xxy, xyy, yyy, xxxx, xxxy, xxyy, xyyy, yyyy;  // moments about (ox, oy)
+    long long s_int;        // n * L1 spread about the mean
+    int32_t ox, oy;         // origin of the moments = first pixel of the root run
+    int32_t bbox[4];        // x0, y0, x1, y1 (inclusive)
     int32_t firstkey;       // min over the component of y*W + xs = raster-first pixel
-    int32_t root;           // root run index
+    int32_t fitted;         // passes the size / area gate of src/objdetect.cpp:64
 };
 
 struct FrameCounters {      // device-side, one per frame in the chunk (+1 trailing entry = chunk allocators)
@@ -55,8 +61,10 @@ struct SlotBuffers {
     uint32_t* run_x;        // [CF][R]       xs | xe<<16
     uint16_t* run_y;        // [CF][R]
     int32_t* parent;        // [CF][R]       flattened labels (root run index), written back by the frame kernel
-    int32_t* gparent;       // [CF][R+1]     background-gap forest; only used when a frame does not fit in shared memory
+    int32_t* gparent;       // [CF][R+2]     background-gap forest; only used when a frame does not fit in shared memory
     int16_t* run_cid;       // [CF][R]       component id per run; same remark
+    int32_t* sorted;        // [CF][R+2]     runs bucketed by component (and the gap join flags before that); same remark
+    CompAcc* acc;           // [CF][C]       integer contour sums per component
     int32_t* comp_root;     // [CF][C]       root run of each component
     CompRec* comps;         // [CF][C]
     FrameCounters* counters;// [CF+1]        entry CF holds the chunk's dense-output allocators (n_runs,n_comps,n_holes)

@@ -1,17 +1,22 @@
 // K2 — everything after the pixel stage, one CTA per frame, run data resident in shared memory:
-//   * connected-component labelling of the runs the pixel kernel emitted (8-connected foreground) and of the background
-//     gaps between them (4-connected; node 0 = background connected to the image border) with a lock-free union-find
-//     (atomicMin on shared memory) — replaces the component discovery of cv::findContours(RETR_EXTERNAL)
+//   * connected-component labelling of the runs the pixel kernel emitted (8-connected foreground): every run links to
+//     the first run it touches in the row above, the links are collapsed by pointer jumping (log2(depth) rounds, no
+//     atomics), and only the rare extra contacts (a run touching several runs above) go through a lock-free
+//     union-find — replaces the component discovery of cv::findContours(RETR_EXTERNAL)
 //     (reference: src/imgproc.cpp:71-72; semantics SURVEY A.2-A.5);
-//   * per component, one warp: contour.size(), cv::contourArea, bbox and the moment sums of the contour point multiset
-//     from the local 3x3 arc rule, cv::fitEllipseDirect incl. its fallback, the ratio/tilt gates and the
-//     rm::lightblob ctor (reference: src/objdetect.cpp:62-84, src/core.cpp:9-19) — the contour is never materialised;
+//   * holes: #holes = #components - #runs + #run contacts (Euler relation on the run graph).  Only frames that have a
+//     hole label the background gaps too (4-connected, same link + jump + union scheme; node 0 = background connected
+//     to the image border), so that arcs facing a hole are skipped and nested components end with n == 0;
+//   * runs are bucketed by component; one warp per component accumulates, as EXACT integers, contour.size(), the
+//     shoelace sum of cv::contourArea, bbox and the 14 moment sums of the contour point multiset from the local 3x3 arc
+//     rule — the contour is never materialised;
+//   * one thread per component: cv::fitEllipseDirect incl. its fallback, the ratio/tilt gates and the rm::lightblob
+//     ctor (reference: src/objdetect.cpp:62-84, src/core.cpp:9-19);
 //   * ordering into cv::findContours order, the O(P^2) pair gates of rm::filter_armours and rm::armour geometry
 //     (reference: src/objdetect.cpp:114-166, src/core.cpp:21-49) with an order-preserving block compaction;
 //   * dense write-out straight into pinned, device-mapped host memory (space claimed with one atomicAdd per array), so
 //     results reach the host without a size-dependent cudaMemcpy.
-// Arcs whose background side is a hole are skipped, so hole borders never contribute and nested components end with
-// n == 0 (RETR_EXTERNAL).  Frames whose run count exceeds the shared-memory capacity run the same code on global arrays.
+// Frames whose run count exceeds the shared-memory capacity run the same code on global arrays.
 #include "blob_math.cuh"
 #include "common.cuh"
 #include "pairs.cuh"
@@ -22,8 +27,10 @@ namespace rmcv {
 // Entry: bits 0-2 arc count m; arc i at bits 3+5i: low 2 bits = 4-neighbour to test for "hole" (0=E,1=N,2=W,3=S),
 // high 3 bits = direction of the edge target q (0..7 = E,NE,N,NW,W,SW,S,SE); bit 31 = isolated pixel (no edge).
 __constant__ uint32_t c_arc_lut[256];
-__constant__ int8_t c_dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-__constant__ int8_t c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+// direction q -> (dx, dy), two bits per direction holding d+1 (a register literal: divergent lanes would serialise on a
+// constant-memory table)
+__device__ __forceinline__ int dir_dx(int q) { return (int)((0x901Au >> (2 * q)) & 3u) - 1; }
+__device__ __forceinline__ int dir_dy(int q) { return (int)((0xA901u >> (2 * q)) & 3u) - 1; }
 
 void upload_luts() {
     uint32_t lut[256];
@@ -84,9 +91,12 @@ struct Runs {  // run storage of one frame (shared or global memory, same code)
     const int2* rows;      // per row: [first, end)
     const uint32_t* run_x; // xs | xe<<16
     const uint16_t* run_y;
-    int32_t* parent;
-    int32_t* gparent;      // node r+1 = gap to the left of run r; node 0 = outer background
-    int16_t* cid;
+    int32_t* link;         // foreground forest, then the flat label (root run) of every run
+    int32_t* glink;        // background-gap forest: node r+1 = gap to the left of run r; node 0 = outer background
+    int16_t* cid;          // first: "joined with the previous run of my row" flag; then the component id of the run
+    int32_t* sorted;       // run indices bucketed by component (shared-memory mode: aliases link once the labels are flat)
+    uint8_t* jp;           // gap node flags (alias the sorted/link region before the bucketing):
+    uint8_t* jo;           //   jp = joined with the previous gap of its row, jo = joined with the outer background
     int n_runs, W, H;
 };
 
@@ -107,20 +117,20 @@ __device__ __forceinline__ int upper_bound_xs(const uint32_t* run_x, int lo, int
     return lo;
 }
 
-// Unions the interior gap node `gnode` = [a,b] with the 4-connected background gaps of row yy.
-__device__ __forceinline__ void gap_union_row(const Runs& f, int gnode, int a, int b, int yy) {
-    const int2 rr = f.rows[yy];
-    const int lo = rr.x, hi = rr.y;
-    for (int r = upper_bound_xs(f.run_x, lo, hi, a);; ++r) {
-        // gap between run r-1 and run r (r == lo: left border gap; r == hi: right border gap)
-        const int ga = (r == lo) ? 0 : (int)(f.run_x[r - 1] >> 16) + 1;
-        if (ga > b) break;
-        const int gb = (r == hi) ? f.W - 1 : (int)(f.run_x[r] & 0xffffu) - 1;
-        if (gb >= a && ga <= gb) {
-            const bool border = (r == lo) || (r == hi) || yy == 0 || yy == f.H - 1;
-            uf_union(f.gparent, gnode, border ? 0 : r + 1);
+// Collapses a forest of links (every node points at an ancestor or at itself) until every node points at its root.
+// Block-wide; reads may see values written in the same round, which are ancestors too.
+__device__ __forceinline__ void pointer_jump(int32_t* link, int first, int end, int tid, int NT) {
+    volatile int32_t* v = link;
+    while (true) {
+        int changed = 0;
+        for (int r = first + tid; r < end; r += NT) {
+            const int l = v[r];
+            if (l != r) {
+                const int ll = v[l];
+                if (ll != l) { v[r] = ll; changed = 1; }
+            }
         }
-        if (r == hi) break;
+        if (!__syncthreads_or(changed)) break;
     }
 }
 
@@ -130,7 +140,7 @@ __device__ __forceinline__ bool is_hole(const Runs& f, int x, int yy) {
     const int2 rr = f.rows[yy];
     const int r = upper_bound_xs(f.run_x, rr.x, rr.y, x);  // the gap lies between run r-1 and run r
     if (r == rr.x || r == rr.y) return false;                // touches the left / right border
-    return f.gparent[r + 1] != 0;
+    return f.glink[r + 1] != 0;
 }
 
 // ------------------------------------------------------------------------------------------ contour points
@@ -143,7 +153,8 @@ __device__ __forceinline__ uint64_t window(const uint32_t* row, int k, int WB) {
 
 // Calls emit(x, y, dx, dy) for every contour point contributed by the run [xs,xe] of row y.
 template <class F>
-__device__ __forceinline__ void run_contour_points(const uint32_t* bits, const Runs& f, bool has_holes, int WB, int y, int xs,
+// `lut` is the arc table copied to shared memory (divergent indices); `test_holes` = this component has holes of its own.
+__device__ __forceinline__ void run_contour_points(const uint32_t* bits, const uint32_t* lut, const Runs& f, bool test_holes, int WB, int y, int xs,
                                                    int xe, F&& emit) {
     const int H = f.H;
     const uint32_t* rc = bits + (size_t)y * WB;
@@ -162,36 +173,20 @@ __device__ __forceinline__ void run_contour_points(const uint32_t* bits, const R
             cand &= cand - 1;
             const uint32_t u3 = (uint32_t)(uw >> i) & 7u, c3 = (uint32_t)(cw >> i) & 7u, d3 = (uint32_t)(dw >> i) & 7u;
             const uint32_t idx = u3 | ((c3 & 1u) << 3) | ((c3 >> 2) << 4) | (d3 << 5);
-            const uint32_t ent = c_arc_lut[idx];
+            const uint32_t ent = lut[idx];
             const int m = ent & 7;
             const bool iso = (ent >> 31) != 0;
             const int x = k * 32 + i;
             for (int a = 0; a < m; ++a) {
                 const uint32_t arc = (ent >> (3 + 5 * a)) & 31u;
-                if (has_holes) {
+                if (test_holes) {
                     const int t4 = arc & 3u;  // 0=E,1=N,2=W,3=S
                     const int tx = x + (t4 == 0) - (t4 == 2), tyy = y + (t4 == 3) - (t4 == 1);
                     if (is_hole(f, tx, tyy)) continue;
                 }
                 const int q = arc >> 2;
-                emit(x, y, iso ? 0 : (int)c_dx[q], iso ? 0 : (int)c_dy[q]);
+                emit(x, y, iso ? 0 : dir_dx(q), iso ? 0 : dir_dy(q));
             }
-        }
-    }
-}
-
-// Visits every run of component `root` inside its bbox rows, lanes striding over rows.
-template <class F>
-__device__ __forceinline__ void component_points(const uint32_t* bits, const Runs& f, bool has_holes, int WB, int root,
-                                                 const CompStat& st, int lane, F&& emit) {
-    for (int y = st.y0 + lane; y <= st.y1; y += 32) {
-        const int2 rr = f.rows[y];
-        for (int r = lower_bound_xe(f.run_x, rr.x, rr.y, st.x0); r < rr.y; ++r) {
-            const uint32_t rx = f.run_x[r];
-            const int xs = (int)(rx & 0xffffu), xe = (int)(rx >> 16);
-            if (xs > st.x1) break;
-            if (f.parent[r] != root) continue;
-            run_contour_points(bits, f, has_holes, WB, y, xs, xe, emit);
         }
     }
 }
@@ -281,29 +276,31 @@ struct FrameParams {
 };
 
 #define RMCV_PHASE(i) do { if (p.dbg_clock && tid == 0) p.dbg_clock[(size_t)frame * 16 + (i)] = clock64(); } while (0)
+#define RMCV_NPHASE 13
 
 __host__ __device__ inline size_t frame_smem_bytes(int H, int Rs, int C) {
     size_t b = 0;
     b += (size_t)H * sizeof(int2);
     b += (size_t)Rs * sizeof(uint32_t);            // run_x
-    b += (size_t)Rs * sizeof(int32_t);             // parent
-    b += ((size_t)Rs + 2) * sizeof(int32_t);       // gparent
+    b += (size_t)Rs * sizeof(int32_t);             // link / gap flags / sorted
+    b += ((size_t)Rs + 2) * sizeof(int32_t);       // glink
     b += (size_t)Rs * sizeof(uint16_t);            // run_y
     b += (size_t)Rs * sizeof(int16_t);             // cid
     b = (b + 15) & ~(size_t)15;
-    b += (size_t)C * sizeof(CompStat);
-    b += (size_t)C * 2 * sizeof(int32_t);          // keys, status
+    b += (size_t)C * 4 * sizeof(int32_t);          // root, cnt, keys, status
+    b += ((size_t)C + 1) * sizeof(int32_t);        // start
     return b + 64;
 }
 
-__global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
+__global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int sh_scan[33];
-    __shared__ int s_ncomp, s_nholes, s_np, s_nc, s_nn, s_flags, s_off[3];
+    __shared__ uint32_t s_lut[256];
+    __shared__ int s_ncomp, s_nadj, s_np, s_nc, s_nn, s_flags, s_next, s_off[3];
     const Geometry& g = p.g;
     const int W = g.W, H = g.H, WB = g.WB, R = g.R, C = g.C, A = g.A, Rs = p.Rs;
     const int frame = blockIdx.x;
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
     const SlotBuffers& sb = p.sb;
     FrameCounters& fc = sb.counters[frame];
 
@@ -311,14 +308,17 @@ __global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
     uint8_t* q = smem;
     int2* s_rows = reinterpret_cast<int2*>(q); q += (size_t)H * sizeof(int2);
     uint32_t* s_run_x = reinterpret_cast<uint32_t*>(q); q += (size_t)Rs * sizeof(uint32_t);
-    int32_t* s_parent = reinterpret_cast<int32_t*>(q); q += (size_t)Rs * sizeof(int32_t);
-    int32_t* s_gparent = reinterpret_cast<int32_t*>(q); q += ((size_t)Rs + 2) * sizeof(int32_t);
+    int32_t* s_link = reinterpret_cast<int32_t*>(q); q += (size_t)Rs * sizeof(int32_t);
+    int32_t* s_glink = reinterpret_cast<int32_t*>(q); q += ((size_t)Rs + 2) * sizeof(int32_t);
     uint16_t* s_run_y = reinterpret_cast<uint16_t*>(q); q += (size_t)Rs * sizeof(uint16_t);
     int16_t* s_cid = reinterpret_cast<int16_t*>(q); q += (size_t)Rs * sizeof(int16_t);
     q = smem + (((size_t)(q - smem) + 15) & ~(size_t)15);
-    CompStat* s_stat = reinterpret_cast<CompStat*>(q); q += (size_t)C * sizeof(CompStat);
+    int32_t* s_root = reinterpret_cast<int32_t*>(q); q += (size_t)C * sizeof(int32_t);
+    int32_t* s_cnt = reinterpret_cast<int32_t*>(q); q += (size_t)C * sizeof(int32_t);
     int32_t* s_keys = reinterpret_cast<int32_t*>(q); q += (size_t)C * sizeof(int32_t);
-    int32_t* s_status = reinterpret_cast<int32_t*>(q);
+    int32_t* s_status = reinterpret_cast<int32_t*>(q); q += (size_t)C * sizeof(int32_t);
+    int32_t* s_start = reinterpret_cast<int32_t*>(q);
+    int32_t* s_adj = s_keys;  // run contacts per component; consumed before the fit phase writes the keys
 
     const int raw_runs = fc.n_runs;
     const int n_runs = min(raw_runs, R);
@@ -333,14 +333,17 @@ __global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
     f.rows = s_rows;
     f.run_x = in_smem ? s_run_x : g_run_x;
     f.run_y = in_smem ? s_run_y : g_run_y;
-    f.parent = in_smem ? s_parent : g_parent;
-    f.gparent = in_smem ? s_gparent : sb.gparent + (size_t)frame * (R + 1);
+    f.link = in_smem ? s_link : g_parent;
+    f.glink = in_smem ? s_glink : sb.gparent + (size_t)frame * (R + 2);
     f.cid = in_smem ? s_cid : sb.run_cid + (size_t)frame * R;
+    f.sorted = in_smem ? s_link : sb.sorted + (size_t)frame * (R + 2);
+    f.jp = reinterpret_cast<uint8_t*>(f.sorted);
+    f.jo = f.jp + (size_t)n_runs + 2;
     f.n_runs = n_runs; f.W = W; f.H = H;
 
     RMCV_PHASE(0);
     if (tid == 0) {
-        s_ncomp = 0; s_nholes = 0; s_np = 0; s_nc = 0; s_nn = 0;
+        s_ncomp = 0; s_nadj = 0; s_np = 0; s_nc = 0; s_nn = 0; s_next = 0;
         s_flags = raw_runs > R ? RMCV_FRAME_OVERFLOW_RUNS : 0;
     }
     for (int y = tid; y < H; y += NT) {
@@ -348,122 +351,273 @@ __global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
         rr.x = min(rr.x, n_runs); rr.y = min(rr.y, n_runs);
         s_rows[y] = rr;
     }
-    if (in_smem) {
-        for (int r = tid; r < n_runs; r += NT) { s_run_x[r] = g_run_x[r]; s_run_y[r] = g_run_y[r]; }
+    for (int r = tid; r < n_runs; r += NT) {
+        if (in_smem) { s_run_x[r] = g_run_x[r]; s_run_y[r] = g_run_y[r]; }
+        f.cid[r] = 0;
     }
+    for (int i = tid; i < 256; i += NT) s_lut[i] = c_arc_lut[i];
     __syncthreads();
     RMCV_PHASE(1);
-    // ---- init forests
-    for (int r = tid; r < n_runs; r += NT) {
-        f.parent[r] = r;
-        const int y = f.run_y[r];
-        const bool outer = (r == s_rows[y].x) || y == 0 || y == H - 1;  // gap left of r touches the border
-        f.gparent[r + 1] = outer ? 0 : r + 1;
+    // ---- foreground links (8-connectivity): the first run of row y-1 overlapping [xs-1, xe+1] becomes the parent;
+    // every further touched run is flagged "joined with the run before it" (they are consecutive in their row)
+    {
+        int adj = 0;
+        for (int r = tid; r < n_runs; r += NT) {
+            const uint32_t rx = f.run_x[r];
+            const int xs = (int)(rx & 0xffffu), xe = (int)(rx >> 16), y = f.run_y[r];
+            int lk = r;
+            if (y > 0) {
+                const int2 pr = s_rows[y - 1];
+                const int p0 = lower_bound_xe(f.run_x, pr.x, pr.y, xs - 1);
+                int pp = p0;
+                while (pp < pr.y && (int)(f.run_x[pp] & 0xffffu) <= xe + 1) {
+                    if (pp > p0) f.cid[pp] = 1;
+                    ++pp;
+                }
+                if (pp > p0) { lk = p0; adj += pp - p0; }
+                f.glink[r + 1] = pp - p0;  // contacts of this run, summed per component below (glink is free until the gap phase)
+            } else {
+                f.glink[r + 1] = 0;
+            }
+            f.link[r] = lk;
+        }
+        if (adj) atomicAdd(&s_nadj, adj);
     }
-    if (tid == 0) f.gparent[0] = 0;
     __syncthreads();
     RMCV_PHASE(2);
-    // ---- unions
-    for (int r = tid; r < n_runs; r += NT) {
-        const uint32_t rx = f.run_x[r];
-        const int xs = (int)(rx & 0xffffu), xe = (int)(rx >> 16), y = f.run_y[r];
-        if (y > 0) {  // foreground, 8-connectivity: runs of row y-1 overlapping [xs-1, xe+1]
-            const int2 pr = s_rows[y - 1];
-            for (int pp = lower_bound_xe(f.run_x, pr.x, pr.y, xs - 1); pp < pr.y; ++pp) {
-                if ((int)(f.run_x[pp] & 0xffffu) > xe + 1) break;
-                uf_union(f.parent, r, pp);
-            }
-        }
-        if (r > s_rows[y].x && y > 0 && y < H - 1) {  // interior background gap to the left, 4-connectivity
-            const int a = (int)(f.run_x[r - 1] >> 16) + 1, b = xs - 1;
-            gap_union_row(f, r + 1, a, b, y - 1);
-            gap_union_row(f, r + 1, a, b, y + 1);
-        }
-    }
+    pointer_jump(f.link, 0, n_runs, tid, NT);
+    for (int r = tid; r < n_runs; r += NT)
+        if (f.cid[r]) uf_union(f.link, r, r - 1);
     __syncthreads();
     RMCV_PHASE(3);
     // ---- flatten, enumerate components
     for (int r = tid; r < n_runs; r += NT) {
-        const int root = uf_find(f.parent, r);
+        const int root = uf_find(f.link, r);
         if (root == r) {
             const int c = atomicAdd(&s_ncomp, 1);
             if (c < C) {
-                const uint32_t rx = f.run_x[r];
-                const int y = f.run_y[r];
-                CompStat st;
-                st.x0 = (int)(rx & 0xffffu); st.x1 = (int)(rx >> 16); st.y0 = y; st.y1 = y;
-                st.firstkey = y * W + st.x0; st.root = r;
-                s_stat[c] = st;
+                s_root[c] = r; s_cnt[c] = 0; s_adj[c] = 0;
                 f.cid[r] = (int16_t)c;
             } else {
                 f.cid[r] = -1;
                 atomicOr(&s_flags, RMCV_FRAME_OVERFLOW_BLOBS);
             }
+        } else {
+            f.link[r] = root;
         }
-        const int groot = uf_find(f.gparent, r + 1);
-        if (groot != 0) atomicAdd(&s_nholes, 1);
     }
     __syncthreads();
-    for (int r = tid; r < n_runs; r += NT) {
-        const int root = uf_find(f.parent, r);
-        f.parent[r] = root;                        // now a flat label
-        if (in_smem) g_parent[r] = root;           // kept for rmcv_get_label_map
-        f.gparent[r + 1] = uf_find(f.gparent, r + 1);
-    }
-    __syncthreads();
-    for (int r = tid; r < n_runs; r += NT) {
-        const int root = f.parent[r];
-        if (root == r) continue;
-        const int c = f.cid[root];
-        if (c < 0) continue;
-        const uint32_t rx = f.run_x[r];
-        const int xs = (int)(rx & 0xffffu), xe = (int)(rx >> 16), y = f.run_y[r];
-        CompStat* st = s_stat + c;
-        atomicMin(&st->x0, xs); atomicMax(&st->x1, xe);
-        atomicMin(&st->y0, y); atomicMax(&st->y1, y);
-        atomicMin(&st->firstkey, y * W + xs);
+    const int n_comps = min(s_ncomp, C);
+    const bool has_holes = s_ncomp - n_runs + s_nadj > 0;  // Euler relation on the run graph
+    for (int r0 = 0; r0 < n_runs; r0 += NT) {  // component id of every run + runs per component (warp-aggregated)
+        const int r = r0 + tid;
+        int c = -1, adj = 0;
+        if (r < n_runs) {
+            const int root = f.link[r];
+            c = f.cid[root];
+            adj = f.glink[r + 1];
+            if (root != r) f.cid[r] = (int16_t)c;
+            if (in_smem) g_parent[r] = root;       // kept for rmcv_get_label_map
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        adj = __reduce_add_sync(peers, adj);
+        if (c >= 0 && lane == __ffs(peers) - 1) { atomicAdd(&s_cnt[c], __popc(peers)); atomicAdd(&s_adj[c], adj); }
     }
     __syncthreads();
     RMCV_PHASE(4);
-    const int n_comps = min(s_ncomp, C);
-    const bool has_holes = s_nholes > 0;
-    CompRec* comps = sb.comps + (size_t)frame * C;
-    // ---- per component: contour statistics, fit, gates (one warp each)
-    for (int c = warp; c < n_comps; c += nwarps) {
-        const CompStat st = s_stat[c];
-        int n = 0;
+    // ---- background gaps (4-connectivity), only when the frame has a hole
+    if (has_holes) {
+        for (int i = tid; i < (2 * (n_runs + 2) + 3) / 4; i += NT) reinterpret_cast<uint32_t*>(f.jp)[i] = 0u;
+        if (tid == 0) f.glink[0] = 0;
+        __syncthreads();
+        for (int r = tid; r < n_runs; r += NT) {
+            const int y = f.run_y[r];
+            const int2 rr = s_rows[y];
+            if (r == rr.x || y == 0 || y == H - 1) { f.glink[r + 1] = 0; continue; }  // the gap touches the image border
+            const int a = (int)(f.run_x[r - 1] >> 16) + 1, b = (int)(f.run_x[r] & 0xffffu) - 1;
+            bool outer = false;
+            int first = -1;
+            {   // row above: every overlapped gap is connected to this one (and so to each other)
+                const int2 pr = s_rows[y - 1];
+                const int lo = pr.x, hi = pr.y;
+                bool prev_overlapped = false;
+                for (int k = upper_bound_xs(f.run_x, lo, hi, a);; ++k) {
+                    // gap k lies between run k-1 and run k (k == lo: left border gap; k == hi: right border gap)
+                    const int ga = (k == lo) ? 0 : (int)(f.run_x[k - 1] >> 16) + 1;
+                    if (ga > b) break;
+                    const int gb = (k == hi) ? W - 1 : (int)(f.run_x[k] & 0xffffu) - 1;
+                    if (gb >= a && ga <= gb) {
+                        if (k == lo || k == hi || y - 1 == 0) {
+                            outer = true;
+                        } else {
+                            if (first < 0) first = k + 1;
+                            if (prev_overlapped) f.jp[k + 1] = 1;  // node k (the gap before it) may alias the outer background
+                        }
+                        prev_overlapped = true;
+                    }
+                    if (k == hi) break;
+                }
+            }
+            {   // row below: its interior gaps look up themselves; only its border gaps have no node
+                const int2 nr = s_rows[y + 1];
+                if (nr.x == nr.y) {
+                    outer = true;
+                } else if (y + 1 == H - 1) {  // every gap of the last row is outer: connected unless one run covers [a,b]
+                    const int k = lower_bound_xe(f.run_x, nr.x, nr.y, a);
+                    const bool covered = k < nr.y && (int)(f.run_x[k] & 0xffffu) <= a && (int)(f.run_x[k] >> 16) >= b;
+                    if (!covered) outer = true;
+                } else if ((int)(f.run_x[nr.x] & 0xffffu) > a || (int)(f.run_x[nr.y - 1] >> 16) < b) {
+                    outer = true;
+                }
+            }
+            if (outer && first >= 0) f.jo[first] = 1;
+            f.glink[r + 1] = outer ? 0 : (first >= 0 ? first : r + 1);
+        }
+        __syncthreads();
+        pointer_jump(f.glink, 1, n_runs + 1, tid, NT);
+        for (int gnode = 1 + tid; gnode <= n_runs; gnode += NT) {
+            if (f.jp[gnode]) uf_union(f.glink, gnode, gnode - 1);
+            if (f.jo[gnode]) uf_union(f.glink, gnode, 0);
+        }
+        __syncthreads();
+        for (int gnode = 1 + tid; gnode <= n_runs; gnode += NT) f.glink[gnode] = uf_find(f.glink, gnode);
+        __syncthreads();
+    }
+    RMCV_PHASE(5);
+    // ---- bucket the runs by component: start = exclusive scan of the counts, then a warp-aggregated scatter
+    {
+        int carry = 0;
+        for (int c0 = 0; c0 < n_comps; c0 += NT) {
+            const int c = c0 + tid;
+            const int v = c < n_comps ? s_cnt[c] : 0;
+            int total;
+            const int ex = block_excl_scan(v, &total, sh_scan);
+            if (c < n_comps) {
+                s_start[c] = carry + ex;
+                s_status[c] = (1 - v + s_adj[c]) > 0;  // the component has holes of its own (Euler relation per component)
+                s_cnt[c] = 0;
+            }
+            carry += total;
+        }
+        if (tid == 0) s_start[n_comps] = carry;
+        __syncthreads();
+        for (int r0 = 0; r0 < n_runs; r0 += NT) {
+            const int r = r0 + tid;
+            const int c = r < n_runs ? (int)f.cid[r] : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, c);
+            int base = 0;
+            const int leader = __ffs(peers) - 1;
+            if (c >= 0 && lane == leader) base = atomicAdd(&s_cnt[c], __popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            // NOTE: in shared-memory mode `sorted` aliases `link`, which is dead here (labels live in cid / g_parent)
+            if (c >= 0) f.sorted[s_start[c] + base + __popc(peers & ((1u << lane) - 1u))] = r;
+        }
+    }
+    __syncthreads();
+    RMCV_PHASE(6);
+    // ---- per component (one warp each, claimed dynamically): exact integer sums over the contour point multiset
+    CompAcc* accs = sb.acc + (size_t)frame * C;
+    while (true) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&s_next, 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= n_comps) break;
+        const int base = s_start[c], cnt = s_start[c + 1] - base;
+        const int root = s_root[c];
+        const int ox = (int)(f.run_x[root] & 0xffffu), oy = (int)f.run_y[root];
+        // A component without holes faces ONE background region: outer (all arcs count) or a hole of another component
+        // (nested: RETR_EXTERNAL drops it).  The pixel above the first pixel of the root run is background of that region
+        // (a root run touches no run above).  Only components with holes of their own test every arc.
+        const bool own_holes = s_status[c] != 0;
+        const bool nested = has_holes && !own_holes && is_hole(f, ox, oy - 1);
+        const int ncnt = nested ? 0 : cnt;
+        int n = 0, x0 = INT32_MAX, y0 = INT32_MAX, x1 = -1, y1 = -1, fk = INT32_MAX;
         long long sx = 0, sy = 0, cross = 0;
-        component_points(bits, f, has_holes, WB, st.root, st, lane, [&](int x, int y, int dx, int dy) {
-            ++n; sx += x; sy += y;
-            cross += (long long)x * dy - (long long)y * dx;
-        });
-        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        long long m20 = 0, m11 = 0, m02 = 0, m30 = 0, m21 = 0, m12 = 0, m03 = 0, m40 = 0, m31 = 0, m22 = 0, m13 = 0, m04 = 0;
+        for (int i = lane; i < ncnt; i += 32) {
+            const int r = f.sorted[base + i];
+            const uint32_t rx = f.run_x[r];
+            const int xs = (int)(rx & 0xffffu), xe = (int)(rx >> 16), y = f.run_y[r];
+            x0 = min(x0, xs); x1 = max(x1, xe); y0 = min(y0, y); y1 = max(y1, y);
+            fk = min(fk, y * W + xs);
+            run_contour_points(bits, s_lut, f, own_holes, WB, y, xs, xe, [&](int x, int yy, int dx, int dy) {
+                ++n; sx += x; sy += yy;
+                cross += (long long)x * dy - (long long)yy * dx;
+                // relative coordinates stay below 2^15 (frames are at most 32767 px per side): 2nd-order products fit
+                // in int32 and every higher product is one 32x32->64 multiply-add
+                const int ex = x - ox, ey = yy - oy;
+                const int exx = ex * ex, exy = ex * ey, eyy = ey * ey;
+                m20 += exx; m11 += exy; m02 += eyy;
+                m30 += (long long)exx * ex; m21 += (long long)exx * ey; m12 += (long long)eyy * ex; m03 += (long long)eyy * ey;
+                m40 += (long long)exx * exx; m31 += (long long)exx * exy; m22 += (long long)exx * eyy;
+                m13 += (long long)exy * eyy; m04 += (long long)eyy * eyy;
+            });
+        }
+        n = __reduce_add_sync(0xffffffffu, n);
+        x0 = __reduce_min_sync(0xffffffffu, x0); y0 = __reduce_min_sync(0xffffffffu, y0);
+        x1 = __reduce_max_sync(0xffffffffu, x1); y1 = __reduce_max_sync(0xffffffffu, y1);
+        fk = __reduce_min_sync(0xffffffffu, fk);
         sx = warp_sum(sx); sy = warp_sum(sy); cross = warp_sum(cross);
+        long long s_int = 0;
+        const bool fitted = contour_is_fitted(n, cross, p.prm);  // warp-uniform
+        if (fitted) {
+            m20 = warp_sum(m20); m11 = warp_sum(m11); m02 = warp_sum(m02);
+            m30 = warp_sum(m30); m21 = warp_sum(m21); m12 = warp_sum(m12); m03 = warp_sum(m03);
+            m40 = warp_sum(m40); m31 = warp_sum(m31); m22 = warp_sum(m22); m13 = warp_sum(m13); m04 = warp_sum(m04);
+            // second pass: n * (L1 spread about the mean), exact
+            for (int i = lane; i < cnt; i += 32) {
+                const int r = f.sorted[base + i];
+                const uint32_t rx = f.run_x[r];
+                run_contour_points(bits, s_lut, f, own_holes, WB, f.run_y[r], (int)(rx & 0xffffu), (int)(rx >> 16), [&](int x, int yy, int, int) {
+                    s_int += llabs((long long)n * x - sx) + llabs((long long)n * yy - sy);
+                });
+            }
+            s_int = warp_sum(s_int);
+        }
+        if (lane == 0) {
+            CompAcc a;
+            a.n = n; a.sx = sx; a.sy = sy; a.cross = cross;
+            a.xx = m20; a.xy = m11; a.yy = m02; a.xxx = m30; a.xxy = m21; a.xyy = m12; a.yyy = m03;
+            a.xxxx = m40; a.xxxy = m31; a.xxyy = m22; a.xyyy = m13; a.yyyy = m04;
+            a.s_int = s_int;
+            a.ox = ox; a.oy = oy;
+            a.bbox[0] = x0; a.bbox[1] = y0; a.bbox[2] = x1; a.bbox[3] = y1;
+            a.firstkey = fk; a.fitted = fitted ? 1 : 0;
+            accs[c] = a;
+        }
+    }
+    __syncthreads();
+    RMCV_PHASE(7);
+    // ---- per component (one thread each): fit, gates, light blob
+    CompRec* comps = sb.comps + (size_t)frame * C;
+    for (int c = tid; c < n_comps; c += NT) {
+        const CompAcc& a = accs[c];
         CompRec rec;
-        rec.firstkey = n > 0 ? st.firstkey : -1;
+        const int n = (int)a.n;
+        rec.firstkey = n > 0 ? a.firstkey : -1;
         rec.n_points = n;
-        rec.area2 = cross < 0 ? -cross : cross;
-        rec.bbox[0] = st.x0; rec.bbox[1] = st.y0; rec.bbox[2] = st.x1; rec.bbox[3] = st.y1;
+        rec.area2 = a.cross < 0 ? -a.cross : a.cross;
+        rec.bbox[0] = a.bbox[0]; rec.bbox[1] = a.bbox[1]; rec.bbox[2] = a.bbox[2]; rec.bbox[3] = a.bbox[3];
         rec.status = -1;
         rec.fit_branch = RMCV_FIT_NONE;
         rec.det0 = 0.f;
         memset(&rec.blob, 0, sizeof(rec.blob));
         memset(&rec.ellipse, 0, sizeof(rec.ellipse));
-        if (n > 0) {  // external component (warp-uniform)
-            auto pass = [&](auto&& fn) {
-                component_points(bits, f, has_holes, WB, st.root, st, lane, [&](int x, int y, int, int) { fn(x, y); });
-            };
-            fit_and_gate(n, sx, sy, cross, p.prm, pass, &rec.status, &rec.fit_branch, &rec.det0, &rec.ellipse, &rec.blob);
+        if (n > 0) {  // external component
+            ContourSums cs;
+            cs.n = a.n; cs.sx = a.sx; cs.sy = a.sy; cs.cross = a.cross;
+            cs.xx = a.xx; cs.xy = a.xy; cs.yy = a.yy; cs.xxx = a.xxx; cs.xxy = a.xxy; cs.xyy = a.xyy; cs.yyy = a.yyy;
+            cs.xxxx = a.xxxx; cs.xxxy = a.xxxy; cs.xxyy = a.xxyy; cs.xyyy = a.xyyy; cs.yyyy = a.yyyy;
+            cs.s_int = a.s_int; cs.ox = a.ox; cs.oy = a.oy;
+            fit_contour(cs, p.prm, &rec.status, &rec.fit_branch, &rec.det0, &rec.ellipse, &rec.blob);
         }
-        if (lane == 0) {
-            comps[c] = rec;
-            s_keys[c] = rec.firstkey;
-            s_status[c] = rec.status;
-            sb.comp_root[(size_t)frame * C + c] = st.root;
-        }
+        comps[c] = rec;
+        s_keys[c] = rec.firstkey;
+        s_status[c] = rec.status;
+        sb.comp_root[(size_t)frame * C + c] = s_root[c];
     }
     __syncthreads();
-    RMCV_PHASE(5);
+    RMCV_PHASE(8);
     // ---- order: rank = number of external components with a larger first-pixel key (reverse raster order)
     rmcv_contour_info* oc = sb.s_contours + (size_t)frame * C;
     rmcv_lightblob* ob = sb.s_blobs + (size_t)frame * C;
@@ -494,7 +648,7 @@ __global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
         else if (stt == RMCV_CONTOUR_NEGATIVE) atomicAdd(&s_nn, 1);
     }
     __syncthreads();
-    RMCV_PHASE(6);
+    RMCV_PHASE(9);
     // ---- pairs in lexicographic (i,j) order (src/objdetect.cpp:122-163)
     const int P = s_np;
     const long long npairs = (long long)P * (P - 1) / 2;
@@ -524,14 +678,14 @@ __global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
         base += total;
     }
     const int n_arm = min(base, A);
-    RMCV_PHASE(7);
+    RMCV_PHASE(10);
     // ---- claim dense space in the chunk's region of the pinned result arrays, write out
     if (tid == 0) {
         FrameCounters& al = sb.counters[p.frames];
         s_off[0] = atomicAdd(&al.n_runs, s_nc);
         s_off[1] = atomicAdd(&al.n_comps, P);
         s_off[2] = atomicAdd(&al.n_holes, n_arm);
-        fc.n_comps = n_comps; fc.n_holes = s_nholes; fc.flags = s_flags;
+        fc.n_comps = n_comps; fc.n_holes = s_ncomp - n_runs + s_nadj; fc.flags = s_flags;
         fc.n_contours = s_nc; fc.n_positive = P; fc.n_negative = s_nn; fc.n_armours = n_arm;
     }
     __syncthreads();
@@ -549,7 +703,7 @@ __global__ void __launch_bounds__(512) frame_kernel(const FrameParams p) {
     copy_words(p.o_blobs + base_b, ob, (size_t)P * sizeof(rmcv_lightblob), tid, NT);
     copy_words(p.o_armours + base_a, oa, (size_t)n_arm * sizeof(rmcv_armour), tid, NT);
     __syncthreads();
-    RMCV_PHASE(8);
+    RMCV_PHASE(11);
 }
 
 cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_smem_optin, cudaStream_t st, int64_t* launches) {
@@ -557,7 +711,7 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
     p.g = L.g; p.sb = *L.sb; p.prm = prm; p.frame_base = L.frame_base;
     p.o_frames = L.o_frames; p.o_contours = L.o_contours; p.o_blobs = L.o_blobs; p.o_armours = L.o_armours;
     p.frames = L.frames;
-    // shared-memory run capacity: aim at two CTAs per SM, never below 1024 runs
+    // shared-memory run capacity: two CTAs per SM when the frame geometry allows it, never above the run capacity
     const char* env = getenv("RMCV_FRAME_RS");
     int Rs = env ? atoi(env) : 4096;
     if (Rs > L.g.R) Rs = L.g.R;
@@ -572,21 +726,25 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         if (!dbg) cudaMalloc(reinterpret_cast<void**>(&dbg), sizeof(long long) * 16 * 4096);
         p.dbg_clock = dbg;
     }
+    const char* envnt = getenv("RMCV_FRAME_NT");
+    int NT = envnt ? atoi(envnt) : 256;
+    if (NT < 32 || NT > 256 || (NT & 31)) NT = 256;
     cudaError_t e = cudaFuncSetAttribute(frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    frame_kernel<<<L.frames, 512, smem, st>>>(p);
+    frame_kernel<<<L.frames, NT, smem, st>>>(p);
     if (launches) ++*launches;
     if (timing) {  // debug aid: average cycles per phase over the chunk's frames
         cudaStreamSynchronize(st);
         static long long h[16 * 4096];
         const int nf = L.frames < 4096 ? L.frames : 4096;
         cudaMemcpy(h, dbg, sizeof(long long) * 16 * nf, cudaMemcpyDeviceToHost);
-        double acc[9] = {0};
-        for (int f = 0; f < nf; ++f)
-            for (int i = 1; i <= 8; ++i) acc[i] += (double)(h[f * 16 + i] - h[f * 16 + i - 1]);
-        fprintf(stderr, "[frame timing, cycles/frame] load %.0f init %.0f union %.0f flatten+stats %.0f blob %.0f order %.0f pairs %.0f out %.0f | total %.0f\n",
-                acc[1] / nf, acc[2] / nf, acc[3] / nf, acc[4] / nf, acc[5] / nf, acc[6] / nf, acc[7] / nf, acc[8] / nf,
-                (acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6] + acc[7] + acc[8]) / nf);
+        static const char* names[] = {"", "load", "links", "jump+union", "flatten+count", "gaps", "bucket", "sums", "fit", "order", "pairs", "out"};
+        double acc[16] = {0}, tot = 0;
+        for (int fi = 0; fi < nf; ++fi)
+            for (int i = 1; i <= 11; ++i) acc[i] += (double)(h[fi * 16 + i] - h[fi * 16 + i - 1]);
+        fprintf(stderr, "[frame timing, cycles/frame]");
+        for (int i = 1; i <= 11; ++i) { fprintf(stderr, " %s %.0f", names[i], acc[i] / nf); tot += acc[i] / nf; }
+        fprintf(stderr, " | total %.0f (smem %zu B, %d threads)\n", tot, smem, NT);
     }
     return cudaGetLastError();
 }
