@@ -61,7 +61,8 @@ enum { RMCV_FIT_NONE = 0, RMCV_FIT_DIRECT = 1, RMCV_FIT_FALLBACK = 2 };
 enum {
     RMCV_FRAME_OVERFLOW_RUNS = 1,
     RMCV_FRAME_OVERFLOW_BLOBS = 2,
-    RMCV_FRAME_OVERFLOW_ARMOURS = 4
+    RMCV_FRAME_OVERFLOW_ARMOURS = 4,
+    RMCV_FRAME_OVERFLOW_POINTS = 8  /* boundary pixels above 4 * max_runs_per_frame */
 };
 
 /* ---- PODs --------------------------------------------------------------------------------- */

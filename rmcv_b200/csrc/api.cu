@@ -53,7 +53,7 @@ int ensure_tmp(rmcv_ctx* ctx, size_t dev_bytes, size_t host_bytes) {
 
 int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
     const Geometry& g = ctx->cap;
-    const size_t CF = ctx->CF, H = g.H, WB = g.WB, R = g.R, C = g.C, A = g.A;
+    const size_t CF = ctx->CF, H = g.H, WB = g.WB, R = g.R, C = g.C, A = g.A, PC = g.PC, SC = g.SC;
     memset(&sb, 0, sizeof(sb));
     RMCV_CUDA(ctx, dalloc(&sb.bits, CF * H * WB));
     RMCV_CUDA(ctx, dalloc(&sb.rows, CF * H));
@@ -62,7 +62,8 @@ int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
     RMCV_CUDA(ctx, dalloc(&sb.parent, CF * R));
     RMCV_CUDA(ctx, dalloc(&sb.gparent, CF * (R + 2)));
     RMCV_CUDA(ctx, dalloc(&sb.run_cid, CF * R));
-    RMCV_CUDA(ctx, dalloc(&sb.sorted, CF * (R + 2)));
+    RMCV_CUDA(ctx, dalloc(&sb.sorted, CF * SC));
+    RMCV_CUDA(ctx, dalloc(&sb.recs, CF * PC));
     RMCV_CUDA(ctx, dalloc(&sb.acc, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.comp_root, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.comps, CF * C));
@@ -84,7 +85,7 @@ int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
 
 void free_slot(SlotBuffers& sb) {
     cudaFree(sb.bits); cudaFree(sb.rows); cudaFree(sb.run_x); cudaFree(sb.run_y);
-    cudaFree(sb.parent); cudaFree(sb.gparent); cudaFree(sb.run_cid); cudaFree(sb.sorted); cudaFree(sb.acc); cudaFree(sb.comp_root); cudaFree(sb.comps);
+    cudaFree(sb.parent); cudaFree(sb.gparent); cudaFree(sb.run_cid); cudaFree(sb.sorted); cudaFree(sb.recs); cudaFree(sb.acc); cudaFree(sb.comp_root); cudaFree(sb.comps);
     cudaFree(sb.counters); cudaFree(sb.s_contours); cudaFree(sb.s_blobs); cudaFree(sb.s_armours);
     if (sb.frames) cudaFree(sb.frames);
     if (sb.masks) cudaFree(sb.masks);
@@ -155,6 +156,7 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
     pl.target = prm.target; pl.lower_bound = prm.lower_bound; pl.bayer_layout = bayer_layout;
     pl.rows = full ? sb.rows : nullptr; pl.run_x = full ? sb.run_x : nullptr; pl.run_y = full ? sb.run_y : nullptr;
     pl.counters = sb.counters; pl.R = ctx->cap.R;
+    pl.recs = full ? sb.recs : nullptr; pl.PC = ctx->cap.PC;
     RMCV_CUDA(ctx, launch_pixel_stage(pl, ctx->sm_count, st, &ctx->kernel_launches));
     prof_mark(ps, RMCV_STAGE_PIXEL, st);
     ctx->prof_launches[RMCV_STAGE_PIXEL] += ctx->kernel_launches - l0; l0 = ctx->kernel_launches;
@@ -182,9 +184,10 @@ int run_device_batch(rmcv_ctx* ctx, const uint8_t* d_src, size_t pitch, size_t f
     if (d_mask && mask_pitch < (size_t)W) return set_err(ctx, RMCV_ERR_INVALID_ARG, "mask pitch smaller than a row");
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
     const int CF = ctx->CF;
+    static const bool serial = getenv("RMCV_SERIAL") != nullptr;  // debug aid: all chunks on one stream
     int nchunks = 0;
     for (int f0 = 0; f0 < batch; f0 += CF, ++nchunks) {
-        SlotBuffers& sb = ctx->slot[nchunks & 1];
+        SlotBuffers& sb = ctx->slot[serial ? 0 : (nchunks & 1)];
         const int frames = batch - f0 < CF ? batch - f0 : CF;
         rc = enqueue_chunk(ctx, sb, d_src + (size_t)f0 * frame_stride, pitch, frame_stride, W, H, frames, f0, bayer_layout,
                            prm, d_mask ? d_mask + (size_t)f0 * mask_frame_stride : nullptr, mask_pitch, mask_frame_stride, full);
@@ -302,6 +305,9 @@ int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
     long long R = cfg->max_runs_per_frame > 0 ? cfg->max_runs_per_frame : (px / 32 > 16384 ? px / 32 : 16384);
     if (R > px / 2 + g.H) R = px / 2 + g.H;
     g.R = (int)R;
+    g.PC = (int)(4 * R > px ? px : 4 * R);  // a boundary pixel is a foreground pixel
+    if (g.PC < 64) g.PC = 64;
+    g.SC = g.PC > g.R + 2 ? g.PC : g.R + 2;
     g.C = cfg->max_blobs_per_frame > 0 ? cfg->max_blobs_per_frame : 512;
     g.A = cfg->max_armours_per_frame > 0 ? cfg->max_armours_per_frame : 1024;
     int CF = cfg->chunk_frames;

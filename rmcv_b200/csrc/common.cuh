@@ -1,6 +1,7 @@
 // Shared declarations of the rmcv_b200 CUDA library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -39,11 +40,13 @@ struct CompAcc {            // exact integer sums over the contour point multise
 };
 
 struct FrameCounters {      // device-side, one per frame in the chunk (+1 trailing entry = chunk allocators)
-    int32_t n_runs;         // atomically grown by the pixel kernel's run emission (may exceed R: overflow)
+    int32_t n_runs;         // atomically grown by the pixel kernel's run emission (may exceed R: overflow) ...
+    int32_t n_recs;         // ... together with the boundary-pixel records (one packed 64-bit atomicAdd per band)
     int32_t n_comps;
-    int32_t n_holes;        // number of hole gaps (background runs not connected to the border)
+    int32_t n_holes;        // number of holes (Euler relation on the run graph)
     int32_t flags;
     int32_t n_contours, n_positive, n_negative, n_armours;
+    int32_t pad[3];
 };
 
 struct Geometry {           // frame geometry + derived sizes, shared by all kernels of a call
@@ -51,6 +54,8 @@ struct Geometry {           // frame geometry + derived sizes, shared by all ker
     int R;                  // run capacity per frame
     int C;                  // component capacity per frame
     int A;                  // armour capacity per frame
+    int PC;                 // boundary-pixel record capacity per frame
+    int SC;                 // entries per frame of the global bucket array (>= R+2 and >= PC)
 };
 
 struct SlotBuffers {
@@ -63,7 +68,9 @@ struct SlotBuffers {
     int32_t* parent;        // [CF][R]       flattened labels (root run index), written back by the frame kernel
     int32_t* gparent;       // [CF][R+2]     background-gap forest; only used when a frame does not fit in shared memory
     int16_t* run_cid;       // [CF][R]       component id per run; same remark
-    int32_t* sorted;        // [CF][R+2]     runs bucketed by component (and the gap join flags before that); same remark
+    uint2* recs;            // [CF][PC]      boundary pixels {x | y<<16, 8-neighbourhood | (component+1)<<8}, emitted by the pixel kernel
+    int32_t* sorted;        // [CF][SC]      record indices bucketed by component (and the gap join flags before that) when
+                            //               they do not fit in shared memory
     CompAcc* acc;           // [CF][C]       integer contour sums per component
     int32_t* comp_root;     // [CF][C]       root run of each component
     CompRec* comps;         // [CF][C]
@@ -135,6 +142,7 @@ struct PixelLaunch {
     int bayer_layout;   // 0 = BGR input
     // run emission (null = mask only)
     int2* rows; uint32_t* run_x; uint16_t* run_y; FrameCounters* counters; int R;
+    uint2* recs; int PC;  // boundary-pixel records (null = none)
 };
 cudaError_t launch_pixel_stage(const PixelLaunch& p, int sm_count, cudaStream_t st, int64_t* launches);
 

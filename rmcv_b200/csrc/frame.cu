@@ -94,8 +94,7 @@ struct Runs {  // run storage of one frame (shared or global memory, same code)
     int32_t* link;         // foreground forest, then the flat label (root run) of every run
     int32_t* glink;        // background-gap forest: node r+1 = gap to the left of run r; node 0 = outer background
     int16_t* cid;          // first: "joined with the previous run of my row" flag; then the component id of the run
-    int32_t* sorted;       // run indices bucketed by component (shared-memory mode: aliases link once the labels are flat)
-    uint8_t* jp;           // gap node flags (alias the sorted/link region before the bucketing):
+    uint8_t* jp;           // gap node flags (alias the link region / the global bucket array before the bucketing):
     uint8_t* jo;           //   jp = joined with the previous gap of its row, jo = joined with the outer background
     int n_runs, W, H;
 };
@@ -298,7 +297,7 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
     __shared__ uint32_t s_lut[256];
     __shared__ int s_ncomp, s_nadj, s_np, s_nc, s_nn, s_flags, s_next, s_off[3];
     const Geometry& g = p.g;
-    const int W = g.W, H = g.H, WB = g.WB, R = g.R, C = g.C, A = g.A, Rs = p.Rs;
+    const int W = g.W, H = g.H, R = g.R, C = g.C, A = g.A, Rs = p.Rs;
     const int frame = blockIdx.x;
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
     const SlotBuffers& sb = p.sb;
@@ -327,7 +326,6 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
     const uint16_t* g_run_y = sb.run_y + (size_t)frame * R;
     int32_t* g_parent = sb.parent + (size_t)frame * R;
     const int2* g_rows = sb.rows + (size_t)frame * H;
-    const uint32_t* bits = sb.bits + (size_t)frame * H * WB;
 
     Runs f;
     f.rows = s_rows;
@@ -336,8 +334,7 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
     f.link = in_smem ? s_link : g_parent;
     f.glink = in_smem ? s_glink : sb.gparent + (size_t)frame * (R + 2);
     f.cid = in_smem ? s_cid : sb.run_cid + (size_t)frame * R;
-    f.sorted = in_smem ? s_link : sb.sorted + (size_t)frame * (R + 2);
-    f.jp = reinterpret_cast<uint8_t*>(f.sorted);
+    f.jp = in_smem ? reinterpret_cast<uint8_t*>(s_link) : reinterpret_cast<uint8_t*>(sb.sorted + (size_t)frame * g.SC);
     f.jo = f.jp + (size_t)n_runs + 2;
     f.n_runs = n_runs; f.W = W; f.H = H;
 
@@ -484,38 +481,67 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
         __syncthreads();
     }
     RMCV_PHASE(5);
-    // ---- bucket the runs by component: start = exclusive scan of the counts, then a warp-aggregated scatter
+    // ---- boundary-pixel records -> components.  Count pass: the run that owns a record is found by binary search in
+    // its row (shared memory), its component id is stashed in the record; start = exclusive scan of the counts; then a
+    // warp-aggregated scatter of the record indices (16-bit in shared memory, 32-bit in global memory for huge frames).
+    const int raw_recs = fc.n_recs;
+    const int n_recs = min(raw_recs, g.PC);
+    uint2* recs = sb.recs + (size_t)frame * g.PC;
+    const bool idx16 = in_smem && n_recs <= 2 * Rs && n_recs <= 65536;
+    uint16_t* b16 = reinterpret_cast<uint16_t*>(s_link);            // link is dead: labels live in cid / g_parent
+    uint32_t* b32 = reinterpret_cast<uint32_t*>(sb.sorted + (size_t)frame * g.SC);
     {
+        if (tid == 0 && raw_recs > g.PC) atomicOr(&s_flags, RMCV_FRAME_OVERFLOW_POINTS);
+        // per-component hole flag from the Euler relation (1 - runs + contacts), then reuse cnt for the records
+        for (int c = tid; c < n_comps; c += NT) {
+            s_status[c] = (1 - s_cnt[c] + s_adj[c]) > 0;
+            s_cnt[c] = 0;
+        }
+        __syncthreads();
+        for (int i0 = 0; i0 < n_recs; i0 += NT) {
+            const int i = i0 + tid;
+            int c = -1;
+            if (i < n_recs) {
+                const uint2 rec = recs[i];
+                const int x = (int)(rec.x & 0xffffu), y = (int)(rec.x >> 16);
+                const int2 rr = s_rows[y];
+                const int r = lower_bound_xe(f.run_x, rr.x, rr.y, x);  // the run that contains x
+                c = r < rr.y ? (int)f.cid[r] : -1;
+                recs[i].y = (rec.y & 0xffu) | ((uint32_t)(c + 1) << 8);
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, c);
+            if (c >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[c], __popc(peers));
+        }
+        __syncthreads();
         int carry = 0;
         for (int c0 = 0; c0 < n_comps; c0 += NT) {
             const int c = c0 + tid;
             const int v = c < n_comps ? s_cnt[c] : 0;
             int total;
             const int ex = block_excl_scan(v, &total, sh_scan);
-            if (c < n_comps) {
-                s_start[c] = carry + ex;
-                s_status[c] = (1 - v + s_adj[c]) > 0;  // the component has holes of its own (Euler relation per component)
-                s_cnt[c] = 0;
-            }
+            if (c < n_comps) { s_start[c] = carry + ex; s_cnt[c] = 0; }
             carry += total;
         }
         if (tid == 0) s_start[n_comps] = carry;
         __syncthreads();
-        for (int r0 = 0; r0 < n_runs; r0 += NT) {
-            const int r = r0 + tid;
-            const int c = r < n_runs ? (int)f.cid[r] : -1;
+        for (int i0 = 0; i0 < n_recs; i0 += NT) {
+            const int i = i0 + tid;
+            const int c = i < n_recs ? (int)(recs[i].y >> 8) - 1 : -1;
             const unsigned peers = __match_any_sync(0xffffffffu, c);
             int base = 0;
             const int leader = __ffs(peers) - 1;
             if (c >= 0 && lane == leader) base = atomicAdd(&s_cnt[c], __popc(peers));
             base = __shfl_sync(0xffffffffu, base, leader);
-            // NOTE: in shared-memory mode `sorted` aliases `link`, which is dead here (labels live in cid / g_parent)
-            if (c >= 0) f.sorted[s_start[c] + base + __popc(peers & ((1u << lane) - 1u))] = r;
+            if (c >= 0) {
+                const int slot = s_start[c] + base + __popc(peers & ((1u << lane) - 1u));
+                if (idx16) b16[slot] = (uint16_t)i; else b32[slot] = (uint32_t)i;
+            }
         }
     }
     __syncthreads();
     RMCV_PHASE(6);
-    // ---- per component (one warp each, claimed dynamically): exact integer sums over the contour point multiset
+    // ---- per component (one warp each, claimed dynamically), lanes over its boundary pixels: exact integer sums over
+    // the contour point multiset.  A pixel contributes one contour point per arc of the 3x3 rule.
     CompAcc* accs = sb.acc + (size_t)frame * C;
     while (true) {
         int c = 0;
@@ -531,27 +557,46 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
         const bool own_holes = s_status[c] != 0;
         const bool nested = has_holes && !own_holes && is_hole(f, ox, oy - 1);
         const int ncnt = nested ? 0 : cnt;
+        // one record -> (multiplicity k, sum of the edge directions of its counted arcs)
+        auto arcs_of = [&](uint32_t nb, int x, int y, int* dxs, int* dys) -> int {
+            const uint32_t ent = s_lut[nb & 0xffu];
+            const int m = ent & 7;
+            const bool iso = (ent >> 31) != 0;
+            int k = 0, sdx = 0, sdy = 0;
+            for (int a = 0; a < m; ++a) {
+                const uint32_t arc = (ent >> (3 + 5 * a)) & 31u;
+                if (own_holes) {
+                    const int t4 = arc & 3u;  // 0=E,1=N,2=W,3=S
+                    if (is_hole(f, x + (t4 == 0) - (t4 == 2), y + (t4 == 3) - (t4 == 1))) continue;
+                }
+                ++k;
+                if (!iso) { sdx += dir_dx(arc >> 2); sdy += dir_dy(arc >> 2); }
+            }
+            *dxs = sdx; *dys = sdy;
+            return k;
+        };
         int n = 0, x0 = INT32_MAX, y0 = INT32_MAX, x1 = -1, y1 = -1, fk = INT32_MAX;
         long long sx = 0, sy = 0, cross = 0;
         long long m20 = 0, m11 = 0, m02 = 0, m30 = 0, m21 = 0, m12 = 0, m03 = 0, m40 = 0, m31 = 0, m22 = 0, m13 = 0, m04 = 0;
         for (int i = lane; i < ncnt; i += 32) {
-            const int r = f.sorted[base + i];
-            const uint32_t rx = f.run_x[r];
-            const int xs = (int)(rx & 0xffffu), xe = (int)(rx >> 16), y = f.run_y[r];
-            x0 = min(x0, xs); x1 = max(x1, xe); y0 = min(y0, y); y1 = max(y1, y);
-            fk = min(fk, y * W + xs);
-            run_contour_points(bits, s_lut, f, own_holes, WB, y, xs, xe, [&](int x, int yy, int dx, int dy) {
-                ++n; sx += x; sy += yy;
-                cross += (long long)x * dy - (long long)yy * dx;
-                // relative coordinates stay below 2^15 (frames are at most 32767 px per side): 2nd-order products fit
-                // in int32 and every higher product is one 32x32->64 multiply-add
-                const int ex = x - ox, ey = yy - oy;
-                const int exx = ex * ex, exy = ex * ey, eyy = ey * ey;
-                m20 += exx; m11 += exy; m02 += eyy;
-                m30 += (long long)exx * ex; m21 += (long long)exx * ey; m12 += (long long)eyy * ex; m03 += (long long)eyy * ey;
-                m40 += (long long)exx * exx; m31 += (long long)exx * exy; m22 += (long long)exx * eyy;
-                m13 += (long long)exy * eyy; m04 += (long long)eyy * eyy;
-            });
+            const uint2 rec = recs[idx16 ? (uint32_t)b16[base + i] : b32[base + i]];
+            const int x = (int)(rec.x & 0xffffu), y = (int)(rec.x >> 16);
+            x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y);
+            fk = min(fk, y * W + x);
+            int sdx, sdy;
+            const int k = arcs_of(rec.y, x, y, &sdx, &sdy);
+            n += k; sx += k * x; sy += k * y;
+            cross += (long long)x * sdy - (long long)y * sdx;
+            // relative coordinates stay below 2^15 (frames are at most 32767 px per side): 2nd-order products fit in
+            // int32 and every higher product is one 32x32->64 multiply-add
+            const int ex = x - ox, ey = y - oy;
+            const int exx = ex * ex, exy = ex * ey, eyy = ey * ey;
+            m20 += (long long)k * exx; m11 += (long long)k * exy; m02 += (long long)k * eyy;
+            const int kex = k * ex, key = k * ey;
+            m30 += (long long)exx * kex; m21 += (long long)exx * key; m12 += (long long)eyy * kex; m03 += (long long)eyy * key;
+            const long long q40 = (long long)exx * exx, q31 = (long long)exx * exy, q22 = (long long)exx * eyy,
+                            q13 = (long long)exy * eyy, q04 = (long long)eyy * eyy;
+            m40 += k * q40; m31 += k * q31; m22 += k * q22; m13 += k * q13; m04 += k * q04;
         }
         n = __reduce_add_sync(0xffffffffu, n);
         x0 = __reduce_min_sync(0xffffffffu, x0); y0 = __reduce_min_sync(0xffffffffu, y0);
@@ -565,12 +610,12 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
             m30 = warp_sum(m30); m21 = warp_sum(m21); m12 = warp_sum(m12); m03 = warp_sum(m03);
             m40 = warp_sum(m40); m31 = warp_sum(m31); m22 = warp_sum(m22); m13 = warp_sum(m13); m04 = warp_sum(m04);
             // second pass: n * (L1 spread about the mean), exact
-            for (int i = lane; i < cnt; i += 32) {
-                const int r = f.sorted[base + i];
-                const uint32_t rx = f.run_x[r];
-                run_contour_points(bits, s_lut, f, own_holes, WB, f.run_y[r], (int)(rx & 0xffffu), (int)(rx >> 16), [&](int x, int yy, int, int) {
-                    s_int += llabs((long long)n * x - sx) + llabs((long long)n * yy - sy);
-                });
+            for (int i = lane; i < ncnt; i += 32) {
+                const uint2 rec = recs[idx16 ? (uint32_t)b16[base + i] : b32[base + i]];
+                const int x = (int)(rec.x & 0xffffu), y = (int)(rec.x >> 16);
+                int sdx, sdy;
+                const int k = arcs_of(rec.y, x, y, &sdx, &sdy);
+                s_int += k * (llabs((long long)n * x - sx) + llabs((long long)n * y - sy));
             }
             s_int = warp_sum(s_int);
         }

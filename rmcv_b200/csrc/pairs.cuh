@@ -30,6 +30,32 @@ __device__ __forceinline__ int block_excl_scan(int v, int* total, int* sh) {
     return sh[warp] + incl - v;
 }
 
+// Same for a 64-bit value (two packed 32-bit counters).  sh: 34 long longs (272 bytes) of shared scratch.
+__device__ __forceinline__ long long block_excl_scan64(long long v, long long* total, long long* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    long long incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        long long w = lane < nwarps ? sh[lane] : 0;
+        long long i2 = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long u = __shfl_up_sync(0xffffffffu, i2, o);
+            if (lane >= o) i2 += u;
+        }
+        __syncwarp();
+        sh[lane] = i2 - w;
+        if (lane == 31) sh[32] = i2;
+    }
+    __syncthreads();
+    *total = sh[32];
+    return sh[warp] + incl - v;
+}
+
 // pair index k (row-major over i<j) -> (i, j): the order of the reference's double loop (src/objdetect.cpp:122-126)
 __device__ __forceinline__ void pair_from_index(long long k, int P, int* pi, int* pj) {
     const double b = 2.0 * P - 1.0;
