@@ -244,9 +244,13 @@ int rmcv_make_lightblobs(rmcv_ctx* ctx, const rmcv_rotated_rect* boxes, int n, i
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* CUDA-event timing of the stages of detect/extract calls (on the stream that runs them). */
 enum {
-    RMCV_STAGE_PIXEL = 0,   /* fused diff/threshold/close kernel (+ run emission)                         */
-    RMCV_STAGE_FRAME = 1,   /* fused per-frame kernel: labelling, contour statistics, fits, gates, armours */
-    RMCV_STAGE_COUNT = 2
+    RMCV_STAGE_PIXEL = 0,   /* fused diff/threshold/close kernel -> byte mask + bit mask                       */
+    RMCV_STAGE_EMIT = 1,    /* runs + boundary-pixel records from the bit mask                                 */
+    RMCV_STAGE_LABEL = 2,   /* connected components (+ holes) of the runs                                      */
+    RMCV_STAGE_CONTOUR = 3, /* per-component contour statistics (exact integer sums)                           */
+    RMCV_STAGE_FIT = 4,     /* ellipse fits, light-blob gates                                                  */
+    RMCV_STAGE_ORDER = 5,   /* cv::findContours order, armour pair gates, dense write-out                      */
+    RMCV_STAGE_COUNT = 6
 };
 int rmcv_profile_enable(rmcv_ctx* ctx, int on);
 /* accumulated milliseconds and launch counts per stage since the last reset */

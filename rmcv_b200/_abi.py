@@ -11,7 +11,7 @@ CAMP_RED, CAMP_BLUE, CAMP_GUIDELIGHT, CAMP_NEUTRAL = 0, 1, 2, -1
 BAYER_RG, BAYER_GB, BAYER_GR, BAYER_BG = 1, 2, 3, 4
 CONTOUR_SKIPPED, CONTOUR_POSITIVE, CONTOUR_NEGATIVE = 0, 1, 2
 FIT_NONE, FIT_DIRECT, FIT_FALLBACK = 0, 1, 2
-STAGE_NAMES = ("pixel", "frame")
+STAGE_NAMES = ("pixel", "emit", "label", "contour", "fit", "order")
 
 
 class RotatedRect(C.Structure):

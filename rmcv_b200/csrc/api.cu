@@ -12,9 +12,10 @@ using namespace rmcv;
 
 namespace {
 
-struct ProfSet {
-    cudaEvent_t ev[RMCV_STAGE_COUNT + 1];
-    bool rec;
+struct ProfSet {      // events of one chunk: pixel begin/end on the pixel stream, one mark per labelling stage on its stream
+    cudaEvent_t pix[2];
+    cudaEvent_t lab[RMCV_STAGE_COUNT];  // lab[0] = start of the labelling stages, lab[s] = end of stage s (s >= 1)
+    bool rec, full;
 };
 
 struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
@@ -26,7 +27,12 @@ struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
     void* tmp_host = nullptr; size_t tmp_host_bytes = 0;
     int last_nchunks = 0;
     int last_kind = 0;  // 0 none, 1 extract, 2 detect
-    cudaEvent_t t_start[2] = {nullptr, nullptr}, t_stop[2] = {nullptr, nullptr};
+    cudaEvent_t t_start[4] = {nullptr, nullptr, nullptr, nullptr}, t_stop[4] = {nullptr, nullptr, nullptr, nullptr};
+    // Streams of the ctx.  The pixel kernels of consecutive chunks run back to back on `pix`; the labelling kernels of
+    // chunk i run on the high-priority stream `lab` behind an event, so that they overlap the pixel kernel of chunk
+    // i+1; host<->device staging copies have their own streams (both copy engines stay busy).
+    cudaStream_t pix = nullptr, lab = nullptr, h2d = nullptr, d2h = nullptr;
+    bool own_pix = false;
 };
 
 CtxExtra* extra(rmcv_ctx* c) { return static_cast<CtxExtra*>(c->extra); }
@@ -64,33 +70,35 @@ int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
     RMCV_CUDA(ctx, dalloc(&sb.run_cid, CF * R));
     RMCV_CUDA(ctx, dalloc(&sb.sorted, CF * SC));
     RMCV_CUDA(ctx, dalloc(&sb.recs, CF * PC));
+    RMCV_CUDA(ctx, dalloc(&sb.recs2, CF * PC));
+    RMCV_CUDA(ctx, dalloc(&sb.comp_start, CF * (C + 1)));
     RMCV_CUDA(ctx, dalloc(&sb.acc, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.comp_root, CF * C));
+    RMCV_CUDA(ctx, dalloc(&sb.comp_cnt, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.comps, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.counters, CF + 1));
     RMCV_CUDA(ctx, cudaMemset(sb.counters, 0, (CF + 1) * sizeof(FrameCounters)));
     RMCV_CUDA(ctx, dalloc(&sb.s_contours, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.s_blobs, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.s_armours, CF * A));
-    if (first && ctx->cfg.stream) {
-        sb.stream = reinterpret_cast<cudaStream_t>(ctx->cfg.stream);
-        sb.own_stream = false;
-    } else {
-        RMCV_CUDA(ctx, cudaStreamCreateWithFlags(&sb.stream, cudaStreamNonBlocking));
-        sb.own_stream = true;
-    }
-    RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.done, cudaEventDisableTiming));
+    (void)first;
+    RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.ev_pix, cudaEventDisableTiming));
+    RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.ev_lab, cudaEventDisableTiming));
+    RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.ev_h2d, cudaEventDisableTiming));
+    RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.ev_d2h, cudaEventDisableTiming));
     return RMCV_OK;
 }
 
 void free_slot(SlotBuffers& sb) {
     cudaFree(sb.bits); cudaFree(sb.rows); cudaFree(sb.run_x); cudaFree(sb.run_y);
-    cudaFree(sb.parent); cudaFree(sb.gparent); cudaFree(sb.run_cid); cudaFree(sb.sorted); cudaFree(sb.recs); cudaFree(sb.acc); cudaFree(sb.comp_root); cudaFree(sb.comps);
+    cudaFree(sb.parent); cudaFree(sb.gparent); cudaFree(sb.run_cid); cudaFree(sb.sorted); cudaFree(sb.recs); cudaFree(sb.recs2); cudaFree(sb.comp_start); cudaFree(sb.acc); cudaFree(sb.comp_root); cudaFree(sb.comp_cnt); cudaFree(sb.comps);
     cudaFree(sb.counters); cudaFree(sb.s_contours); cudaFree(sb.s_blobs); cudaFree(sb.s_armours);
     if (sb.frames) cudaFree(sb.frames);
     if (sb.masks) cudaFree(sb.masks);
-    if (sb.own_stream && sb.stream) cudaStreamDestroy(sb.stream);
-    if (sb.done) cudaEventDestroy(sb.done);
+    if (sb.ev_pix) cudaEventDestroy(sb.ev_pix);
+    if (sb.ev_lab) cudaEventDestroy(sb.ev_lab);
+    if (sb.ev_h2d) cudaEventDestroy(sb.ev_h2d);
+    if (sb.ev_d2h) cudaEventDestroy(sb.ev_d2h);
     memset(&sb, 0, sizeof(sb));
 }
 
@@ -109,67 +117,72 @@ Geometry call_geometry(const rmcv_ctx* ctx, int W, int H) {
     return g;
 }
 
-ProfSet* prof_begin(rmcv_ctx* ctx, cudaStream_t st) {
+ProfSet* prof_begin(rmcv_ctx* ctx) {
     if (!ctx->profiling) return nullptr;
     CtxExtra* ex = extra(ctx);
     if (ex->prof_used == ex->prof.size()) {
         ProfSet ps;
-        for (int i = 0; i <= RMCV_STAGE_COUNT; ++i) cudaEventCreate(&ps.ev[i]);
-        ps.rec = false;
+        for (int i = 0; i < 2; ++i) cudaEventCreate(&ps.pix[i]);
+        for (int i = 0; i < RMCV_STAGE_COUNT; ++i) cudaEventCreate(&ps.lab[i]);
+        ps.rec = false; ps.full = false;
         ex->prof.push_back(ps);
     }
     ProfSet* ps = &ex->prof[ex->prof_used++];
-    ps->rec = true;
-    cudaEventRecord(ps->ev[0], st);
+    ps->rec = true; ps->full = false;
     return ps;
-}
-void prof_mark(ProfSet* ps, int stage, cudaStream_t st) {
-    if (ps) cudaEventRecord(ps->ev[stage + 1], st);
 }
 void prof_collect(rmcv_ctx* ctx) {  // after a sync
     CtxExtra* ex = extra(ctx);
     for (size_t i = 0; i < ex->prof_used; ++i) {
         ProfSet& ps = ex->prof[i];
         if (!ps.rec) continue;
-        for (int s = 0; s < RMCV_STAGE_COUNT; ++s) {
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, ps.ev[s], ps.ev[s + 1]) == cudaSuccess) ctx->prof_ms[s] += ms;
-        }
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ps.pix[0], ps.pix[1]) == cudaSuccess) ctx->prof_ms[RMCV_STAGE_PIXEL] += ms;
+        for (int s = 1; ps.full && s < RMCV_STAGE_COUNT; ++s)
+            if (cudaEventElapsedTime(&ms, ps.lab[s - 1], ps.lab[s]) == cudaSuccess) ctx->prof_ms[s] += ms;
         ps.rec = false;
     }
     ex->prof_used = 0;
     cudaGetLastError();
 }
 
-// Enqueue all stages for `frames` frames whose pixels are at `src` on slot `sb`.
+// Enqueue all stages for `frames` frames whose pixels are at `src`, using the scratch of slot `sb`.
 int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pitch, size_t frame_stride, int W, int H,
                   int frames, int frame_base, int bayer_layout, const rmcv_params& prm, uint8_t* mask, size_t mask_pitch,
                   size_t mask_frame_stride, bool full) {
-    cudaStream_t st = sb.stream;
-    if (full) RMCV_CUDA(ctx, cudaMemsetAsync(sb.counters, 0, (size_t)(frames + 1) * sizeof(FrameCounters), st));
-    ProfSet* ps = prof_begin(ctx, st);
-    int64_t l0 = ctx->kernel_launches;
+    CtxExtra* ex = extra(ctx);
+    cudaStream_t sp = ex->pix, sl = ex->lab;
+    // the slot's scratch is free once the labelling stages (and the mask download) of its previous chunk are done
+    RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, sb.ev_lab, 0));
+    RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, sb.ev_d2h, 0));
+    if (full) RMCV_CUDA(ctx, cudaMemsetAsync(sb.counters, 0, (size_t)(frames + 1) * sizeof(FrameCounters), sp));
+    ProfSet* ps = prof_begin(ctx);
+    if (ps) cudaEventRecord(ps->pix[0], sp);
+    const int64_t l0 = ctx->kernel_launches;
     PixelLaunch pl;
     pl.src = src; pl.pitch = pitch; pl.frame_stride = frame_stride;
     pl.mask = mask; pl.mask_pitch = mask_pitch; pl.mask_frame_stride = mask_frame_stride;
     pl.bits = sb.bits; pl.W = W; pl.H = H; pl.batch = frames;
     pl.target = prm.target; pl.lower_bound = prm.lower_bound; pl.bayer_layout = bayer_layout;
-    pl.rows = full ? sb.rows : nullptr; pl.run_x = full ? sb.run_x : nullptr; pl.run_y = full ? sb.run_y : nullptr;
-    pl.counters = sb.counters; pl.R = ctx->cap.R;
-    pl.recs = full ? sb.recs : nullptr; pl.PC = ctx->cap.PC;
-    RMCV_CUDA(ctx, launch_pixel_stage(pl, ctx->sm_count, st, &ctx->kernel_launches));
-    prof_mark(ps, RMCV_STAGE_PIXEL, st);
-    ctx->prof_launches[RMCV_STAGE_PIXEL] += ctx->kernel_launches - l0; l0 = ctx->kernel_launches;
-    if (!full) {
-        prof_mark(ps, RMCV_STAGE_FRAME, st);
-        return RMCV_OK;
-    }
+    RMCV_CUDA(ctx, launch_pixel_stage(pl, ctx->sm_count, sp, &ctx->kernel_launches));
+    if (ps) cudaEventRecord(ps->pix[1], sp);
+    RMCV_CUDA(ctx, cudaEventRecord(sb.ev_pix, sp));
+    ctx->prof_launches[RMCV_STAGE_PIXEL] += ctx->kernel_launches - l0;
+    if (!full) return RMCV_OK;
+    RMCV_CUDA(ctx, cudaStreamWaitEvent(sl, sb.ev_pix, 0));
+    if (ps) { ps->full = true; cudaEventRecord(ps->lab[0], sl); }
     FrameLaunch fl;
     fl.g = call_geometry(ctx, W, H); fl.frames = frames; fl.sb = &sb; fl.frame_base = frame_base;
     fl.o_frames = ctx->h_frames; fl.o_contours = ctx->h_contours; fl.o_blobs = ctx->h_blobs; fl.o_armours = ctx->h_armours;
-    RMCV_CUDA(ctx, launch_frames(fl, prm, ctx->max_smem_optin, st, &ctx->kernel_launches));
-    prof_mark(ps, RMCV_STAGE_FRAME, st);
-    ctx->prof_launches[RMCV_STAGE_FRAME] += ctx->kernel_launches - l0;
+    struct Mark { ProfSet* ps; rmcv_ctx* ctx; };
+    Mark mk{ps, ctx};
+    auto stage_done = [](void* arg, int stage, cudaStream_t s2) {
+        Mark* m = static_cast<Mark*>(arg);
+        if (m->ps) cudaEventRecord(m->ps->lab[stage], s2);
+        m->ctx->prof_launches[stage] += 1;
+    };
+    RMCV_CUDA(ctx, launch_frames(fl, prm, ctx->max_smem_optin, sl, &ctx->kernel_launches, stage_done, &mk));
+    RMCV_CUDA(ctx, cudaEventRecord(sb.ev_lab, sl));
     return RMCV_OK;
 }
 
@@ -184,10 +197,9 @@ int run_device_batch(rmcv_ctx* ctx, const uint8_t* d_src, size_t pitch, size_t f
     if (d_mask && mask_pitch < (size_t)W) return set_err(ctx, RMCV_ERR_INVALID_ARG, "mask pitch smaller than a row");
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
     const int CF = ctx->CF;
-    static const bool serial = getenv("RMCV_SERIAL") != nullptr;  // debug aid: all chunks on one stream
     int nchunks = 0;
     for (int f0 = 0; f0 < batch; f0 += CF, ++nchunks) {
-        SlotBuffers& sb = ctx->slot[serial ? 0 : (nchunks & 1)];
+        SlotBuffers& sb = ctx->slot[nchunks & 1];
         const int frames = batch - f0 < CF ? batch - f0 : CF;
         rc = enqueue_chunk(ctx, sb, d_src + (size_t)f0 * frame_stride, pitch, frame_stride, W, H, frames, f0, bayer_layout,
                            prm, d_mask ? d_mask + (size_t)f0 * mask_frame_stride : nullptr, mask_pitch, mask_frame_stride, full);
@@ -202,8 +214,11 @@ int run_device_batch(rmcv_ctx* ctx, const uint8_t* d_src, size_t pitch, size_t f
 
 int sync_all(rmcv_ctx* ctx) {
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
-    RMCV_CUDA(ctx, cudaStreamSynchronize(ctx->slot[0].stream));
-    RMCV_CUDA(ctx, cudaStreamSynchronize(ctx->slot[1].stream));
+    CtxExtra* ex = extra(ctx);
+    RMCV_CUDA(ctx, cudaStreamSynchronize(ex->h2d));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(ex->pix));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(ex->lab));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(ex->d2h));
     prof_collect(ctx);
     return RMCV_OK;
 }
@@ -321,6 +336,19 @@ int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
     }
     if (CF > cfg->max_batch) CF = cfg->max_batch;
     ctx->CF = CF;
+    {
+        CtxExtra* ex = extra(ctx);
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        cudaError_t se = cudaSuccess;
+        if (cfg->stream) { ex->pix = reinterpret_cast<cudaStream_t>(cfg->stream); ex->own_pix = false; }
+        else { se = cudaStreamCreateWithPriority(&ex->pix, cudaStreamNonBlocking, least); ex->own_pix = true; }
+        if (getenv("RMCV_SERIAL")) ex->lab = ex->pix;   // debug aid: every kernel on one stream
+        else if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&ex->lab, cudaStreamNonBlocking, greatest);
+        if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&ex->h2d, cudaStreamNonBlocking);
+        if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&ex->d2h, cudaStreamNonBlocking);
+        if (se != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "stream creation failed: %s", cudaGetErrorString(se)); return fail(RMCV_ERR_CUDA); }
+    }
     int rc = alloc_slot(ctx, ctx->slot[0], true);
     if (rc == RMCV_OK) rc = alloc_slot(ctx, ctx->slot[1], false);
     if (rc != RMCV_OK) return fail(rc);
@@ -353,8 +381,15 @@ int rmcv_ctx_destroy(rmcv_ctx* ctx) {
     if (ctx->h_armours) cudaFreeHost(ctx->h_armours);
     CtxExtra* ex = extra(ctx);
     if (ex) {
-        for (auto& ps : ex->prof) for (int i = 0; i <= RMCV_STAGE_COUNT; ++i) cudaEventDestroy(ps.ev[i]);
-        for (int i = 0; i < 2; ++i) { if (ex->t_start[i]) cudaEventDestroy(ex->t_start[i]); if (ex->t_stop[i]) cudaEventDestroy(ex->t_stop[i]); }
+        for (auto& ps : ex->prof) {
+            for (int i = 0; i < 2; ++i) cudaEventDestroy(ps.pix[i]);
+            for (int i = 0; i < RMCV_STAGE_COUNT; ++i) cudaEventDestroy(ps.lab[i]);
+        }
+        for (int i = 0; i < 4; ++i) { if (ex->t_start[i]) cudaEventDestroy(ex->t_start[i]); if (ex->t_stop[i]) cudaEventDestroy(ex->t_stop[i]); }
+        if (ex->lab && ex->lab != ex->pix) cudaStreamDestroy(ex->lab);
+        if (ex->pix && ex->own_pix) cudaStreamDestroy(ex->pix);
+        if (ex->h2d) cudaStreamDestroy(ex->h2d);
+        if (ex->d2h) cudaStreamDestroy(ex->d2h);
         for (void* p : ex->dev_allocs) cudaFree(p);
         for (void* p : ex->host_allocs) cudaFreeHost(p);
         if (ex->tmp_dev) cudaFree(ex->tmp_dev);
@@ -401,24 +436,24 @@ int rmcv_host_free(rmcv_ctx* ctx, void* hptr) {
 }
 int rmcv_memcpy_h2d(rmcv_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
-    RMCV_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->slot[0].stream));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, extra(ctx)->pix));
     return RMCV_OK;
 }
 int rmcv_memcpy_d2h(rmcv_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
-    RMCV_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->slot[0].stream));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, extra(ctx)->pix));
     return RMCV_OK;
 }
 int rmcv_memset_d(rmcv_ctx* ctx, void* dst, int value, size_t bytes) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
-    RMCV_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->slot[0].stream));
+    RMCV_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, extra(ctx)->pix));
     return RMCV_OK;
 }
 int rmcv_sync(rmcv_ctx* ctx) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
     return sync_all(ctx);
 }
-void* rmcv_stream(rmcv_ctx* ctx) { return ctx ? reinterpret_cast<void*>(ctx->slot[0].stream) : nullptr; }
+void* rmcv_stream(rmcv_ctx* ctx) { return ctx ? reinterpret_cast<void*>(extra(ctx)->pix) : nullptr; }
 
 int rmcv_extract_color_batch(rmcv_ctx* ctx, const uint8_t* d_bgr, size_t pitch, size_t frame_stride, int width, int height,
                              int batch, int target, int lower_bound, uint8_t* d_mask, size_t mask_pitch,
@@ -488,25 +523,32 @@ int rmcv_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, si
             sb.masks_bytes = need / 3;
         }
         const uint8_t* hsrc = h_bgr + (size_t)f0 * frame_stride;
+        CtxExtra* ex = extra(ctx);
+        // upload on the copy stream once the pixel kernel of the slot's previous chunk has read the staging buffer
+        RMCV_CUDA(ctx, cudaStreamWaitEvent(ex->h2d, sb.ev_pix, 0));
         if (pitch == rowbytes && frame_stride == dev_frame) {
-            RMCV_CUDA(ctx, cudaMemcpyAsync(sb.frames, hsrc, (size_t)frames * dev_frame, cudaMemcpyHostToDevice, sb.stream));
+            RMCV_CUDA(ctx, cudaMemcpyAsync(sb.frames, hsrc, (size_t)frames * dev_frame, cudaMemcpyHostToDevice, ex->h2d));
         } else {
             for (int f = 0; f < frames; ++f)
                 RMCV_CUDA(ctx, cudaMemcpy2DAsync(sb.frames + (size_t)f * dev_frame, rowbytes, hsrc + (size_t)f * frame_stride, pitch,
-                                                 rowbytes, height, cudaMemcpyHostToDevice, sb.stream));
+                                                 rowbytes, height, cudaMemcpyHostToDevice, ex->h2d));
         }
+        RMCV_CUDA(ctx, cudaEventRecord(sb.ev_h2d, ex->h2d));
+        RMCV_CUDA(ctx, cudaStreamWaitEvent(ex->pix, sb.ev_h2d, 0));
         rc = enqueue_chunk(ctx, sb, sb.frames, rowbytes, dev_frame, width, height, frames, f0, 0, *params,
                            h_mask ? sb.masks : nullptr, width, dev_mask, true);
         if (rc != RMCV_OK) return rc;
         if (h_mask) {
             uint8_t* hdst = h_mask + (size_t)f0 * mask_frame_stride;
+            RMCV_CUDA(ctx, cudaStreamWaitEvent(ex->d2h, sb.ev_pix, 0));
             if (mask_pitch == (size_t)width && mask_frame_stride == dev_mask) {
-                RMCV_CUDA(ctx, cudaMemcpyAsync(hdst, sb.masks, (size_t)frames * dev_mask, cudaMemcpyDeviceToHost, sb.stream));
+                RMCV_CUDA(ctx, cudaMemcpyAsync(hdst, sb.masks, (size_t)frames * dev_mask, cudaMemcpyDeviceToHost, ex->d2h));
             } else {
                 for (int f = 0; f < frames; ++f)
                     RMCV_CUDA(ctx, cudaMemcpy2DAsync(hdst + (size_t)f * mask_frame_stride, mask_pitch, sb.masks + (size_t)f * dev_mask,
-                                                     width, width, height, cudaMemcpyDeviceToHost, sb.stream));
+                                                     width, width, height, cudaMemcpyDeviceToHost, ex->d2h));
             }
+            RMCV_CUDA(ctx, cudaEventRecord(sb.ev_d2h, ex->d2h));
         }
     }
     ctx->last_batch = batch; ctx->last_W = width; ctx->last_H = height;
@@ -543,7 +585,7 @@ int rmcv_get_contour(rmcv_ctx* ctx, int frame, int contour_index, int32_t* xy, i
     int32_t* d_n = reinterpret_cast<int32_t*>(ex->tmp_dev);
     int32_t* d_xy = d_n + 4;
     Geometry g = call_geometry(ctx, ctx->last_W, ctx->last_H);
-    cudaStream_t st = sb->stream;
+    cudaStream_t st = extra(ctx)->lab;
     RMCV_CUDA(ctx, launch_trace_contour(g, sb->bits + (size_t)local * g.H * g.WB, ci.first_x, ci.first_y, d_xy, cap, d_n, st,
                                         &ctx->kernel_launches));
     RMCV_CUDA(ctx, cudaMemcpyAsync(ex->tmp_host, ex->tmp_dev, bytes, cudaMemcpyDeviceToHost, st));
@@ -588,7 +630,7 @@ int rmcv_get_contours(rmcv_ctx* ctx, int frame, int32_t* xy, int cap_points, int
     }
     for (int k = 0; k <= nc; ++k) offsets[k] = h[k];
     uint8_t* d = reinterpret_cast<uint8_t*>(ex->tmp_dev);
-    cudaStream_t st = sb->stream;
+    cudaStream_t st = extra(ctx)->lab;
     Geometry g = call_geometry(ctx, ctx->last_W, ctx->last_H);
     RMCV_CUDA(ctx, cudaMemcpyAsync(d, h, ((size_t)nc * 3 + 1) * 4, cudaMemcpyHostToDevice, st));
     const int32_t* d_off = reinterpret_cast<const int32_t*>(d);
@@ -613,7 +655,7 @@ int rmcv_get_label_map(rmcv_ctx* ctx, int frame, int32_t* labels, size_t pitch_e
     rc = ensure_tmp(ctx, bytes, 0);
     if (rc != RMCV_OK) return rc;
     CtxExtra* ex = extra(ctx);
-    cudaStream_t st = sb->stream;
+    cudaStream_t st = extra(ctx)->lab;
     RMCV_CUDA(ctx, launch_label_map(g, sb, local, reinterpret_cast<int32_t*>(ex->tmp_dev), st, &ctx->kernel_launches));
     RMCV_CUDA(ctx, cudaMemcpy2DAsync(labels, pitch_elems * sizeof(int32_t), ex->tmp_dev, (size_t)g.W * sizeof(int32_t),
                                      (size_t)g.W * sizeof(int32_t), g.H, cudaMemcpyDeviceToHost, st));
@@ -632,8 +674,8 @@ int rmcv_get_bitmask(rmcv_ctx* ctx, int frame, uint32_t* words, int words_per_ro
     Geometry g = call_geometry(ctx, ctx->last_W, ctx->last_H);
     if (words_per_row < g.WB) return set_err(ctx, RMCV_ERR_INVALID_ARG, "words_per_row too small");
     RMCV_CUDA(ctx, cudaMemcpy2DAsync(words, (size_t)words_per_row * 4, sb->bits + (size_t)local * g.H * g.WB, (size_t)g.WB * 4,
-                                     (size_t)g.WB * 4, g.H, cudaMemcpyDeviceToHost, sb->stream));
-    RMCV_CUDA(ctx, cudaStreamSynchronize(sb->stream));
+                                     (size_t)g.WB * 4, g.H, cudaMemcpyDeviceToHost, extra(ctx)->lab));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(extra(ctx)->lab));
     return RMCV_OK;
 }
 
@@ -652,7 +694,7 @@ int rmcv_filter_lightblobs(rmcv_ctx* ctx, const int32_t* xy, const int32_t* offs
     if (rc != RMCV_OK) return rc;
     CtxExtra* ex = extra(ctx);
     uint8_t* d = reinterpret_cast<uint8_t*>(ex->tmp_dev);
-    cudaStream_t st = ctx->slot[0].stream;
+    cudaStream_t st = extra(ctx)->pix;
     if (npts) RMCV_CUDA(ctx, cudaMemcpyAsync(d, xy, npts * 2 * 4, cudaMemcpyHostToDevice, st));
     RMCV_CUDA(ctx, cudaMemcpyAsync(d + b_xy, offsets, ((size_t)n_contours + 1) * 4, cudaMemcpyHostToDevice, st));
     rmcv_contour_info* d_info = reinterpret_cast<rmcv_contour_info*>(d + b_xy + b_off);
@@ -688,7 +730,7 @@ int rmcv_filter_armours(rmcv_ctx* ctx, const rmcv_lightblob* blobs, int n_blobs,
     if (rc != RMCV_OK) return rc;
     CtxExtra* ex = extra(ctx);
     uint8_t* d = reinterpret_cast<uint8_t*>(ex->tmp_dev);
-    cudaStream_t st = ctx->slot[0].stream;
+    cudaStream_t st = extra(ctx)->pix;
     RMCV_CUDA(ctx, cudaMemcpyAsync(d, blobs, (size_t)n_blobs * sizeof(rmcv_lightblob), cudaMemcpyHostToDevice, st));
     int32_t* d_count = reinterpret_cast<int32_t*>(d + b_blob);
     rmcv_armour* d_arm = reinterpret_cast<rmcv_armour*>(d + b_blob + 16);
@@ -712,7 +754,7 @@ int rmcv_make_lightblobs(rmcv_ctx* ctx, const rmcv_rotated_rect* boxes, int n, i
     if (rc != RMCV_OK) return rc;
     CtxExtra* ex = extra(ctx);
     uint8_t* d = reinterpret_cast<uint8_t*>(ex->tmp_dev);
-    cudaStream_t st = ctx->slot[0].stream;
+    cudaStream_t st = extra(ctx)->pix;
     RMCV_CUDA(ctx, cudaMemcpyAsync(d, boxes, (size_t)n * sizeof(rmcv_rotated_rect), cudaMemcpyHostToDevice, st));
     RMCV_CUDA(ctx, launch_make_lightblobs(reinterpret_cast<const rmcv_rotated_rect*>(d), n, target, reinterpret_cast<rmcv_lightblob*>(d + b_in),
                                           st, &ctx->kernel_launches));
@@ -742,9 +784,10 @@ int rmcv_timer_start(rmcv_ctx* ctx) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
     CtxExtra* ex = extra(ctx);
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
-    for (int i = 0; i < 2; ++i) {
+    cudaStream_t st[4] = {ex->pix, ex->lab, ex->h2d, ex->d2h};
+    for (int i = 0; i < 4; ++i) {
         if (!ex->t_start[i]) { RMCV_CUDA(ctx, cudaEventCreate(&ex->t_start[i])); RMCV_CUDA(ctx, cudaEventCreate(&ex->t_stop[i])); }
-        RMCV_CUDA(ctx, cudaEventRecord(ex->t_start[i], ctx->slot[i].stream));
+        RMCV_CUDA(ctx, cudaEventRecord(ex->t_start[i], st[i]));
     }
     return RMCV_OK;
 }
@@ -753,12 +796,13 @@ int rmcv_timer_stop(rmcv_ctx* ctx, double* ms) {
     if (!ctx || !ms) return RMCV_ERR_INVALID_ARG;
     CtxExtra* ex = extra(ctx);
     if (!ex->t_start[0]) return set_err(ctx, RMCV_ERR_STATE, "rmcv_timer_stop without rmcv_timer_start");
-    for (int i = 0; i < 2; ++i) RMCV_CUDA(ctx, cudaEventRecord(ex->t_stop[i], ctx->slot[i].stream));
+    cudaStream_t st[4] = {ex->pix, ex->lab, ex->h2d, ex->d2h};
+    for (int i = 0; i < 4; ++i) RMCV_CUDA(ctx, cudaEventRecord(ex->t_stop[i], st[i]));
     int rc = sync_all(ctx);
     if (rc != RMCV_OK) return rc;
     float best = 0.f;
-    for (int i = 0; i < 2; ++i)
-        for (int j = 0; j < 2; ++j) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
             float t = 0.f;
             RMCV_CUDA(ctx, cudaEventElapsedTime(&t, ex->t_start[i], ex->t_stop[j]));
             if (t > best) best = t;

@@ -68,11 +68,14 @@ struct SlotBuffers {
     int32_t* parent;        // [CF][R]       flattened labels (root run index), written back by the frame kernel
     int32_t* gparent;       // [CF][R+2]     background-gap forest; only used when a frame does not fit in shared memory
     int16_t* run_cid;       // [CF][R]       component id per run; same remark
-    uint2* recs;            // [CF][PC]      boundary pixels {x | y<<16, 8-neighbourhood | (component+1)<<8}, emitted by the pixel kernel
+    uint2* recs;            // [CF][PC]      boundary pixels {x | y<<16, 8-neighbourhood} in emission order (emit kernel)
+    uint2* recs2;           // [CF][PC]      the same records bucketed by component (label kernel)
+    int32_t* comp_start;    // [CF][C+1]     first record of each component in recs2
     int32_t* sorted;        // [CF][SC]      record indices bucketed by component (and the gap join flags before that) when
                             //               they do not fit in shared memory
     CompAcc* acc;           // [CF][C]       integer contour sums per component
     int32_t* comp_root;     // [CF][C]       root run of each component
+    int32_t* comp_cnt;      // [CF][C]       Euler term of each component; after the label kernel: has holes of its own
     CompRec* comps;         // [CF][C]
     FrameCounters* counters;// [CF+1]        entry CF holds the chunk's dense-output allocators (n_runs,n_comps,n_holes)
     // ordered per-frame result slots (device) before dense write-out
@@ -83,9 +86,11 @@ struct SlotBuffers {
     uint8_t* frames;        // [CF][H][W*3] (allocated lazily)
     uint8_t* masks;         // [CF][H][W]   (allocated lazily)
     size_t frames_bytes, masks_bytes;
-    cudaStream_t stream;
-    bool own_stream;
-    cudaEvent_t done;       // recorded after the last kernel of a chunk
+    // chunk i of a call uses slot i&1; the events order the ctx streams (api.cu) around the slot's scratch
+    cudaEvent_t ev_pix;     // pixel kernel done  (bits written; staging frames read)
+    cudaEvent_t ev_lab;     // labelling stages done (scratch free again)
+    cudaEvent_t ev_h2d;     // staging upload done
+    cudaEvent_t ev_d2h;     // mask download done
 };
 
 }  // namespace rmcv
@@ -140,9 +145,6 @@ struct PixelLaunch {
     int W, H, batch;
     int target, lower_bound;
     int bayer_layout;   // 0 = BGR input
-    // run emission (null = mask only)
-    int2* rows; uint32_t* run_x; uint16_t* run_y; FrameCounters* counters; int R;
-    uint2* recs; int PC;  // boundary-pixel records (null = none)
 };
 cudaError_t launch_pixel_stage(const PixelLaunch& p, int sm_count, cudaStream_t st, int64_t* launches);
 
@@ -154,8 +156,17 @@ struct FrameLaunch {
     rmcv_lightblob* o_blobs;
     rmcv_armour* o_armours;
 };
-// everything after the pixel stage for one chunk: labelling, contour statistics, fits, gates, armours, write-out
-cudaError_t launch_frames(const FrameLaunch& p, const rmcv_params& prm, int max_smem_optin, cudaStream_t st, int64_t* launches);
+// everything after the pixel stage for one chunk (five launches: emit, label, contour sums, fits, order/pairs/write-out);
+// stage_done(arg, RMCV_STAGE_*, stream) is called after each launch (profiling events), may be null
+cudaError_t launch_frames(const FrameLaunch& p, const rmcv_params& prm, int max_smem_optin, cudaStream_t st, int64_t* launches,
+                          void (*stage_done)(void*, int, cudaStream_t), void* stage_arg);
+
+struct EmitLaunch {
+    const uint32_t* bits; int W, H, batch;
+    int2* rows; uint32_t* run_x; uint16_t* run_y; FrameCounters* counters; int R;
+    uint2* recs; int PC;
+};
+cudaError_t launch_emit(const EmitLaunch& p, cudaStream_t st, int64_t* launches);
 
 cudaError_t launch_trace_contour(const Geometry& g, const uint32_t* bits, int x0, int y0, int32_t* d_xy, int cap,
                                  int32_t* d_n, cudaStream_t st, int64_t* launches);

@@ -1,22 +1,22 @@
-// K2 — everything after the pixel stage, one CTA per frame, run data resident in shared memory:
-//   * connected-component labelling of the runs the pixel kernel emitted (8-connected foreground): every run links to
-//     the first run it touches in the row above, the links are collapsed by pointer jumping (log2(depth) rounds, no
-//     atomics), and only the rare extra contacts (a run touching several runs above) go through a lock-free
-//     union-find — replaces the component discovery of cv::findContours(RETR_EXTERNAL)
-//     (reference: src/imgproc.cpp:71-72; semantics SURVEY A.2-A.5);
-//   * holes: #holes = #components - #runs + #run contacts (Euler relation on the run graph).  Only frames that have a
-//     hole label the background gaps too (4-connected, same link + jump + union scheme; node 0 = background connected
-//     to the image border), so that arcs facing a hole are skipped and nested components end with n == 0;
-//   * runs are bucketed by component; one warp per component accumulates, as EXACT integers, contour.size(), the
-//     shoelace sum of cv::contourArea, bbox and the 14 moment sums of the contour point multiset from the local 3x3 arc
-//     rule — the contour is never materialised;
-//   * one thread per component: cv::fitEllipseDirect incl. its fallback, the ratio/tilt gates and the rm::lightblob
-//     ctor (reference: src/objdetect.cpp:62-84, src/core.cpp:9-19);
-//   * ordering into cv::findContours order, the O(P^2) pair gates of rm::filter_armours and rm::armour geometry
-//     (reference: src/objdetect.cpp:114-166, src/core.cpp:21-49) with an order-preserving block compaction;
-//   * dense write-out straight into pinned, device-mapped host memory (space claimed with one atomicAdd per array), so
-//     results reach the host without a size-dependent cudaMemcpy.
-// Frames whose run count exceeds the shared-memory capacity run the same code on global arrays.
+// Labelling and measurement stages of the detection path (everything after the pixel kernel), one launch each per chunk:
+//   K_E  emit.cu   runs + boundary-pixel records from the bit mask;
+//   K_L  labelling, one CTA per frame in shared memory: every run links to the first run it touches in the row above
+//        (8-connected foreground), the links are collapsed by pointer jumping (log2(depth) rounds, no atomics) and only
+//        the rare extra contacts (a run touching several runs above) go through a lock-free union-find — replaces the
+//        component discovery of cv::findContours(RETR_EXTERNAL) (reference: src/imgproc.cpp:71-72).
+//        Holes: #holes = #components - #runs + #run contacts (Euler relation on the run graph); only frames that have a
+//        hole label the background gaps too (4-connected, same link + jump + union scheme; node 0 = background connected
+//        to the image border), so that arcs facing a hole are skipped and nested components end with n == 0;
+//   K_C  contour sums, one CTA per frame with little shared memory: the records are bucketed by component and one warp
+//        per component accumulates, as EXACT integers, contour.size(), the shoelace sum of cv::contourArea, bbox and
+//        the 14 moment sums of the contour point multiset from the local 3x3 arc rule — the contour is
+//        never materialised;
+//   K_F  one thread per component of the whole chunk: cv::fitEllipseDirect incl. its fallback, the ratio/tilt gates and
+//        the rm::lightblob ctor (reference: src/objdetect.cpp:62-84, src/core.cpp:9-19);
+//   K_O  one small CTA per frame: ordering into cv::findContours order, the O(P^2) pair gates of rm::filter_armours and
+//        rm::armour geometry (reference: src/objdetect.cpp:114-166, src/core.cpp:21-49) with an order-preserving block
+//        compaction, dense write-out straight into pinned, device-mapped host memory.
+// Each kernel has a homogeneous resource profile, so each fills the SMs on its own.
 #include "blob_math.cuh"
 #include "common.cuh"
 #include "pairs.cuh"
@@ -142,54 +142,6 @@ __device__ __forceinline__ bool is_hole(const Runs& f, int x, int yy) {
     return f.glink[r + 1] != 0;
 }
 
-// ------------------------------------------------------------------------------------------ contour points
-__device__ __forceinline__ uint64_t window(const uint32_t* row, int k, int WB) {
-    const uint32_t w = __ldg(row + k);
-    const uint32_t prev = k > 0 ? (__ldg(row + k - 1) >> 31) : 0u;
-    const uint32_t next = k + 1 < WB ? (__ldg(row + k + 1) & 1u) : 0u;
-    return (uint64_t)prev | ((uint64_t)w << 1) | ((uint64_t)next << 33);
-}
-
-// Calls emit(x, y, dx, dy) for every contour point contributed by the run [xs,xe] of row y.
-template <class F>
-// `lut` is the arc table copied to shared memory (divergent indices); `test_holes` = this component has holes of its own.
-__device__ __forceinline__ void run_contour_points(const uint32_t* bits, const uint32_t* lut, const Runs& f, bool test_holes, int WB, int y, int xs,
-                                                   int xe, F&& emit) {
-    const int H = f.H;
-    const uint32_t* rc = bits + (size_t)y * WB;
-    const uint32_t* ru = bits + (size_t)(y - 1) * WB;
-    const uint32_t* rd = bits + (size_t)(y + 1) * WB;
-    for (int k = xs >> 5; k <= (xe >> 5); ++k) {
-        const int l = max(xs, k * 32) - k * 32, h = min(xe, k * 32 + 31) - k * 32;
-        const uint32_t runmask = (h == 31 ? 0xffffffffu : ((1u << (h + 1)) - 1u)) & ~((1u << l) - 1u);
-        const uint64_t cw = window(rc, k, WB);
-        const uint64_t uw = y > 0 ? window(ru, k, WB) : 0ull;
-        const uint64_t dw = y < H - 1 ? window(rd, k, WB) : 0ull;
-        // candidates: run pixels with a background 4-neighbour
-        uint32_t cand = runmask & ~((uint32_t)(uw >> 1) & (uint32_t)(dw >> 1) & (uint32_t)cw & (uint32_t)(cw >> 2));
-        while (cand) {
-            const int i = __ffs(cand) - 1;
-            cand &= cand - 1;
-            const uint32_t u3 = (uint32_t)(uw >> i) & 7u, c3 = (uint32_t)(cw >> i) & 7u, d3 = (uint32_t)(dw >> i) & 7u;
-            const uint32_t idx = u3 | ((c3 & 1u) << 3) | ((c3 >> 2) << 4) | (d3 << 5);
-            const uint32_t ent = lut[idx];
-            const int m = ent & 7;
-            const bool iso = (ent >> 31) != 0;
-            const int x = k * 32 + i;
-            for (int a = 0; a < m; ++a) {
-                const uint32_t arc = (ent >> (3 + 5 * a)) & 31u;
-                if (test_holes) {
-                    const int t4 = arc & 3u;  // 0=E,1=N,2=W,3=S
-                    const int tx = x + (t4 == 0) - (t4 == 2), tyy = y + (t4 == 3) - (t4 == 1);
-                    if (is_hole(f, tx, tyy)) continue;
-                }
-                const int q = arc >> 2;
-                emit(x, y, iso ? 0 : dir_dx(q), iso ? 0 : dir_dy(q));
-            }
-        }
-    }
-}
-
 __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -259,65 +211,45 @@ __device__ __forceinline__ void fit_and_gate(int n, long long sum_x, long long s
     if (*status == RMCV_CONTOUR_POSITIVE) make_lightblob(*ell, prm.target, blob);
 }
 
-// ------------------------------------------------------------------------------------------ the frame kernel
-struct FrameParams {
+// ------------------------------------------------------------------------------------------ K_L: labelling
+// One CTA per frame; runs, links and labels live in shared memory (frames with more runs than fit use global arrays).
+struct LabelParams {
     Geometry g;
     SlotBuffers sb;
-    rmcv_params prm;
-    int frame_base;
-    rmcv_frame_info* o_frames;
-    rmcv_contour_info* o_contours;
-    rmcv_lightblob* o_blobs;
-    rmcv_armour* o_armours;
     int Rs;      // run capacity of the shared-memory arrays
-    int frames;  // frames in this chunk (index of the allocator entry in sb.counters)
-    long long* dbg_clock;  // optional [frames][16] phase timestamps (RMCV_FRAME_TIMING=1), else null
 };
 
-#define RMCV_PHASE(i) do { if (p.dbg_clock && tid == 0) p.dbg_clock[(size_t)frame * 16 + (i)] = clock64(); } while (0)
-#define RMCV_NPHASE 13
-
-__host__ __device__ inline size_t frame_smem_bytes(int H, int Rs, int C) {
-    size_t b = 0;
+__host__ __device__ inline size_t label_smem_bytes(int H, int Rs, int C) {
+    size_t b = ((size_t)2 * C + 2) * sizeof(int32_t);  // records per component, start offsets
     b += (size_t)H * sizeof(int2);
     b += (size_t)Rs * sizeof(uint32_t);            // run_x
-    b += (size_t)Rs * sizeof(int32_t);             // link / gap flags / sorted
+    b += (size_t)Rs * sizeof(int32_t);             // link / gap flags
     b += ((size_t)Rs + 2) * sizeof(int32_t);       // glink
     b += (size_t)Rs * sizeof(uint16_t);            // run_y
     b += (size_t)Rs * sizeof(int16_t);             // cid
-    b = (b + 15) & ~(size_t)15;
-    b += (size_t)C * 4 * sizeof(int32_t);          // root, cnt, keys, status
-    b += ((size_t)C + 1) * sizeof(int32_t);        // start
     return b + 64;
 }
 
-__global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
+__global__ void __launch_bounds__(256, 3) label_kernel(const LabelParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int sh_scan[33];
-    __shared__ uint32_t s_lut[256];
-    __shared__ int s_ncomp, s_nadj, s_np, s_nc, s_nn, s_flags, s_next, s_off[3];
+    __shared__ int s_ncomp, s_nadj, s_flags;
     const Geometry& g = p.g;
-    const int W = g.W, H = g.H, R = g.R, C = g.C, A = g.A, Rs = p.Rs;
+    const int W = g.W, H = g.H, R = g.R, C = g.C, Rs = p.Rs;
     const int frame = blockIdx.x;
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
     const SlotBuffers& sb = p.sb;
     FrameCounters& fc = sb.counters[frame];
 
-    // ---- carve shared memory
     uint8_t* q = smem;
+    int32_t* s_cnt = reinterpret_cast<int32_t*>(q); q += (size_t)C * sizeof(int32_t);
+    int32_t* s_start = reinterpret_cast<int32_t*>(q); q += ((size_t)C + 2) * sizeof(int32_t);
     int2* s_rows = reinterpret_cast<int2*>(q); q += (size_t)H * sizeof(int2);
     uint32_t* s_run_x = reinterpret_cast<uint32_t*>(q); q += (size_t)Rs * sizeof(uint32_t);
     int32_t* s_link = reinterpret_cast<int32_t*>(q); q += (size_t)Rs * sizeof(int32_t);
     int32_t* s_glink = reinterpret_cast<int32_t*>(q); q += ((size_t)Rs + 2) * sizeof(int32_t);
     uint16_t* s_run_y = reinterpret_cast<uint16_t*>(q); q += (size_t)Rs * sizeof(uint16_t);
-    int16_t* s_cid = reinterpret_cast<int16_t*>(q); q += (size_t)Rs * sizeof(int16_t);
-    q = smem + (((size_t)(q - smem) + 15) & ~(size_t)15);
-    int32_t* s_root = reinterpret_cast<int32_t*>(q); q += (size_t)C * sizeof(int32_t);
-    int32_t* s_cnt = reinterpret_cast<int32_t*>(q); q += (size_t)C * sizeof(int32_t);
-    int32_t* s_keys = reinterpret_cast<int32_t*>(q); q += (size_t)C * sizeof(int32_t);
-    int32_t* s_status = reinterpret_cast<int32_t*>(q); q += (size_t)C * sizeof(int32_t);
-    int32_t* s_start = reinterpret_cast<int32_t*>(q);
-    int32_t* s_adj = s_keys;  // run contacts per component; consumed before the fit phase writes the keys
+    int16_t* s_cid = reinterpret_cast<int16_t*>(q);
 
     const int raw_runs = fc.n_runs;
     const int n_runs = min(raw_runs, R);
@@ -325,36 +257,40 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
     const uint32_t* g_run_x = sb.run_x + (size_t)frame * R;
     const uint16_t* g_run_y = sb.run_y + (size_t)frame * R;
     int32_t* g_parent = sb.parent + (size_t)frame * R;
-    const int2* g_rows = sb.rows + (size_t)frame * H;
+    int32_t* g_glink = sb.gparent + (size_t)frame * (R + 2);
+    int16_t* g_cid = sb.run_cid + (size_t)frame * R;
+    int2* g_rows = sb.rows + (size_t)frame * H;
+    int32_t* g_comp_root = sb.comp_root + (size_t)frame * C;
+    int32_t* g_comp_cnt = sb.comp_cnt + (size_t)frame * C;     // runs per component, then (1 - runs + contacts) > 0
 
     Runs f;
     f.rows = s_rows;
     f.run_x = in_smem ? s_run_x : g_run_x;
     f.run_y = in_smem ? s_run_y : g_run_y;
     f.link = in_smem ? s_link : g_parent;
-    f.glink = in_smem ? s_glink : sb.gparent + (size_t)frame * (R + 2);
-    f.cid = in_smem ? s_cid : sb.run_cid + (size_t)frame * R;
+    f.glink = in_smem ? s_glink : g_glink;
+    f.cid = in_smem ? s_cid : g_cid;
     f.jp = in_smem ? reinterpret_cast<uint8_t*>(s_link) : reinterpret_cast<uint8_t*>(sb.sorted + (size_t)frame * g.SC);
     f.jo = f.jp + (size_t)n_runs + 2;
     f.n_runs = n_runs; f.W = W; f.H = H;
 
-    RMCV_PHASE(0);
     if (tid == 0) {
-        s_ncomp = 0; s_nadj = 0; s_np = 0; s_nc = 0; s_nn = 0; s_next = 0;
+        s_ncomp = 0; s_nadj = 0;
         s_flags = raw_runs > R ? RMCV_FRAME_OVERFLOW_RUNS : 0;
     }
     for (int y = tid; y < H; y += NT) {
         int2 rr = g_rows[y];
-        rr.x = min(rr.x, n_runs); rr.y = min(rr.y, n_runs);
+        if (rr.x > n_runs || rr.y > n_runs) {  // only after a run overflow: keep every later stage inside the arrays
+            rr.x = min(rr.x, n_runs); rr.y = min(rr.y, n_runs);
+            g_rows[y] = rr;
+        }
         s_rows[y] = rr;
     }
     for (int r = tid; r < n_runs; r += NT) {
         if (in_smem) { s_run_x[r] = g_run_x[r]; s_run_y[r] = g_run_y[r]; }
         f.cid[r] = 0;
     }
-    for (int i = tid; i < 256; i += NT) s_lut[i] = c_arc_lut[i];
     __syncthreads();
-    RMCV_PHASE(1);
     // ---- foreground links (8-connectivity): the first run of row y-1 overlapping [xs-1, xe+1] becomes the parent;
     // every further touched run is flagged "joined with the run before it" (they are consecutive in their row)
     {
@@ -381,19 +317,17 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
         if (adj) atomicAdd(&s_nadj, adj);
     }
     __syncthreads();
-    RMCV_PHASE(2);
     pointer_jump(f.link, 0, n_runs, tid, NT);
     for (int r = tid; r < n_runs; r += NT)
         if (f.cid[r]) uf_union(f.link, r, r - 1);
     __syncthreads();
-    RMCV_PHASE(3);
     // ---- flatten, enumerate components
     for (int r = tid; r < n_runs; r += NT) {
         const int root = uf_find(f.link, r);
         if (root == r) {
             const int c = atomicAdd(&s_ncomp, 1);
             if (c < C) {
-                s_root[c] = r; s_cnt[c] = 0; s_adj[c] = 0;
+                g_comp_root[c] = r; g_comp_cnt[c] = 1;   // the Euler term 1 - runs + contacts, accumulated below
                 f.cid[r] = (int16_t)c;
             } else {
                 f.cid[r] = -1;
@@ -405,23 +339,23 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
     }
     __syncthreads();
     const int n_comps = min(s_ncomp, C);
-    const bool has_holes = s_ncomp - n_runs + s_nadj > 0;  // Euler relation on the run graph
-    for (int r0 = 0; r0 < n_runs; r0 += NT) {  // component id of every run + runs per component (warp-aggregated)
+    const int n_holes = s_ncomp - n_runs + s_nadj;  // Euler relation on the run graph
+    const bool has_holes = n_holes > 0;
+    for (int r0 = 0; r0 < n_runs; r0 += NT) {  // component id of every run; per component: contacts - runs (warp-aggregated)
         const int r = r0 + tid;
         int c = -1, adj = 0;
         if (r < n_runs) {
             const int root = f.link[r];
             c = f.cid[root];
-            adj = f.glink[r + 1];
+            adj = f.glink[r + 1] - 1;
             if (root != r) f.cid[r] = (int16_t)c;
-            if (in_smem) g_parent[r] = root;       // kept for rmcv_get_label_map
+            if (in_smem) { g_parent[r] = root; g_cid[r] = (int16_t)c; }   // read by the contour kernel / rmcv_get_label_map
         }
         const unsigned peers = __match_any_sync(0xffffffffu, c);
         adj = __reduce_add_sync(peers, adj);
-        if (c >= 0 && lane == __ffs(peers) - 1) { atomicAdd(&s_cnt[c], __popc(peers)); atomicAdd(&s_adj[c], adj); }
+        if (c >= 0 && lane == __ffs(peers) - 1) atomicAdd(&g_comp_cnt[c], adj);
     }
     __syncthreads();
-    RMCV_PHASE(4);
     // ---- background gaps (4-connectivity), only when the frame has a hole
     if (has_holes) {
         for (int i = tid; i < (2 * (n_runs + 2) + 3) / 4; i += NT) reinterpret_cast<uint32_t*>(f.jp)[i] = 0u;
@@ -477,85 +411,133 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
             if (f.jo[gnode]) uf_union(f.glink, gnode, 0);
         }
         __syncthreads();
-        for (int gnode = 1 + tid; gnode <= n_runs; gnode += NT) f.glink[gnode] = uf_find(f.glink, gnode);
-        __syncthreads();
+        for (int gnode = tid; gnode <= n_runs; gnode += NT) {
+            const int root = gnode == 0 ? 0 : uf_find(f.glink, gnode);
+            f.glink[gnode] = root;
+            if (in_smem) g_glink[gnode] = root;  // read by the contour kernel's hole tests
+        }
     }
-    RMCV_PHASE(5);
-    // ---- boundary-pixel records -> components.  Count pass: the run that owns a record is found by binary search in
-    // its row (shared memory), its component id is stashed in the record; start = exclusive scan of the counts; then a
-    // warp-aggregated scatter of the record indices (16-bit in shared memory, 32-bit in global memory for huge frames).
+    __syncthreads();
+    for (int c = tid; c < n_comps; c += NT) { g_comp_cnt[c] = g_comp_cnt[c] > 0; s_cnt[c] = 0; }  // has holes of its own
+    // ---- boundary-pixel records -> components: the run that owns a record is found by binary search in its row; the
+    // records are counted per component, start = exclusive scan of the counts, and a warp-aggregated scatter writes them
+    // bucketed by component (so that the contour kernel streams each component's records linearly).
     const int raw_recs = fc.n_recs;
     const int n_recs = min(raw_recs, g.PC);
-    uint2* recs = sb.recs + (size_t)frame * g.PC;
-    const bool idx16 = in_smem && n_recs <= 2 * Rs && n_recs <= 65536;
-    uint16_t* b16 = reinterpret_cast<uint16_t*>(s_link);            // link is dead: labels live in cid / g_parent
-    uint32_t* b32 = reinterpret_cast<uint32_t*>(sb.sorted + (size_t)frame * g.SC);
+    const uint2* recs = sb.recs + (size_t)frame * g.PC;
+    uint2* recs2 = sb.recs2 + (size_t)frame * g.PC;
+    int32_t* g_start = sb.comp_start + (size_t)frame * (C + 1);
+    if (tid == 0 && raw_recs > g.PC) s_flags |= RMCV_FRAME_OVERFLOW_POINTS;
+    __syncthreads();
+    auto comp_of = [&](const uint2 rec) -> int {
+        const int x = (int)(rec.x & 0xffffu), y = (int)(rec.x >> 16);
+        const int2 rr = s_rows[y];
+        const int r = lower_bound_xe(f.run_x, rr.x, rr.y, x);  // the run that contains x
+        return r < rr.y ? (int)f.cid[r] : -1;
+    };
+    for (int i0 = 0; i0 < n_recs; i0 += NT) {
+        const int i = i0 + tid;
+        const int c = i < n_recs ? comp_of(recs[i]) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        if (c >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[c], __popc(peers));
+    }
+    __syncthreads();
     {
-        if (tid == 0 && raw_recs > g.PC) atomicOr(&s_flags, RMCV_FRAME_OVERFLOW_POINTS);
-        // per-component hole flag from the Euler relation (1 - runs + contacts), then reuse cnt for the records
-        for (int c = tid; c < n_comps; c += NT) {
-            s_status[c] = (1 - s_cnt[c] + s_adj[c]) > 0;
-            s_cnt[c] = 0;
-        }
-        __syncthreads();
-        for (int i0 = 0; i0 < n_recs; i0 += NT) {
-            const int i = i0 + tid;
-            int c = -1;
-            if (i < n_recs) {
-                const uint2 rec = recs[i];
-                const int x = (int)(rec.x & 0xffffu), y = (int)(rec.x >> 16);
-                const int2 rr = s_rows[y];
-                const int r = lower_bound_xe(f.run_x, rr.x, rr.y, x);  // the run that contains x
-                c = r < rr.y ? (int)f.cid[r] : -1;
-                recs[i].y = (rec.y & 0xffu) | ((uint32_t)(c + 1) << 8);
-            }
-            const unsigned peers = __match_any_sync(0xffffffffu, c);
-            if (c >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[c], __popc(peers));
-        }
-        __syncthreads();
         int carry = 0;
         for (int c0 = 0; c0 < n_comps; c0 += NT) {
             const int c = c0 + tid;
             const int v = c < n_comps ? s_cnt[c] : 0;
             int total;
             const int ex = block_excl_scan(v, &total, sh_scan);
-            if (c < n_comps) { s_start[c] = carry + ex; s_cnt[c] = 0; }
+            if (c < n_comps) { s_start[c] = carry + ex; g_start[c] = carry + ex; s_cnt[c] = 0; }
             carry += total;
         }
-        if (tid == 0) s_start[n_comps] = carry;
-        __syncthreads();
-        for (int i0 = 0; i0 < n_recs; i0 += NT) {
-            const int i = i0 + tid;
-            const int c = i < n_recs ? (int)(recs[i].y >> 8) - 1 : -1;
-            const unsigned peers = __match_any_sync(0xffffffffu, c);
-            int base = 0;
-            const int leader = __ffs(peers) - 1;
-            if (c >= 0 && lane == leader) base = atomicAdd(&s_cnt[c], __popc(peers));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (c >= 0) {
-                const int slot = s_start[c] + base + __popc(peers & ((1u << lane) - 1u));
-                if (idx16) b16[slot] = (uint16_t)i; else b32[slot] = (uint32_t)i;
-            }
-        }
+        if (tid == 0) g_start[n_comps] = carry;
     }
     __syncthreads();
-    RMCV_PHASE(6);
-    // ---- per component (one warp each, claimed dynamically), lanes over its boundary pixels: exact integer sums over
-    // the contour point multiset.  A pixel contributes one contour point per arc of the 3x3 rule.
+    for (int i0 = 0; i0 < n_recs; i0 += NT) {
+        const int i = i0 + tid;
+        uint2 rec = make_uint2(0u, 0u);
+        int c = -1;
+        if (i < n_recs) { rec = recs[i]; c = comp_of(rec); }
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        int base = 0;
+        const int leader = __ffs(peers) - 1;
+        if (c >= 0 && lane == leader) base = atomicAdd(&s_cnt[c], __popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (c >= 0) recs2[s_start[c] + base + __popc(peers & ((1u << lane) - 1u))] = rec;
+    }
+    if (tid == 0) { fc.n_comps = n_comps; fc.n_holes = n_holes; fc.flags = s_flags; }
+}
+
+// ------------------------------------------------------------------------------------------ K_C: contour sums
+// One warp per component over the whole chunk, lanes over its boundary-pixel records (bucketed by the label kernel):
+// accumulates, as exact integers, everything cv::contourArea / cv::fitEllipseDirect need.  No per-frame state in shared
+// memory, so tens of warps are resident per SM and the global-memory latency of the look-ups is hidden.
+struct ContourParams {
+    Geometry g;
+    SlotBuffers sb;
+    rmcv_params prm;
+};
+
+struct GRuns {  // read-only view of one frame's runs and gap labels in global memory
+    const int2* rows; const uint32_t* run_x; const int32_t* glink; int W, H;
+};
+__device__ __forceinline__ int g_lower_bound_xe(const uint32_t* run_x, int lo, int hi, int x) {
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)(__ldg(run_x + mid) >> 16) < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ bool g_is_hole(const GRuns& f, int x, int yy) {
+    if (x <= 0 || yy <= 0 || x >= f.W - 1 || yy >= f.H - 1) return false;
+    const int2 rr = __ldg(f.rows + yy);
+    int lo = rr.x, hi = rr.y;  // first run with xs > x: the gap lies between run r-1 and run r
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)(__ldg(f.run_x + mid) & 0xffffu) <= x) lo = mid + 1; else hi = mid;
+    }
+    if (lo == rr.x || lo == rr.y) return false;  // touches the left / right border
+    return __ldg(f.glink + lo + 1) != 0;
+}
+
+__global__ void __launch_bounds__(128) contour_kernel(const ContourParams p) {
+    __shared__ uint32_t s_lut[256];
+    const Geometry& g = p.g;
+    const int W = g.W, H = g.H, R = g.R, C = g.C;
+    const int frame = blockIdx.x;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+    const SlotBuffers& sb = p.sb;
+    const FrameCounters& fc = sb.counters[frame];
+    const int n_comps = fc.n_comps;
+    const bool has_holes = fc.n_holes > 0;
+    for (int i = tid; i < 256; i += NT) s_lut[i] = c_arc_lut[i];
+    __syncthreads();
+
+    GRuns f;
+    f.rows = sb.rows + (size_t)frame * H;
+    f.run_x = sb.run_x + (size_t)frame * R;
+    f.glink = sb.gparent + (size_t)frame * (R + 2);
+    f.W = W; f.H = H;
+    const uint16_t* run_y = sb.run_y + (size_t)frame * R;
+    const int32_t* comp_root = sb.comp_root + (size_t)frame * C;
+    const int32_t* comp_holes = sb.comp_cnt + (size_t)frame * C;
+    const int32_t* g_start = sb.comp_start + (size_t)frame * (C + 1);
+    const uint2* recs = sb.recs2 + (size_t)frame * g.PC;
+    // ---- per component (one warp each, claimed dynamically), lanes over its boundary pixels.  A pixel contributes one
+    // contour point per arc of the 3x3 rule.
     CompAcc* accs = sb.acc + (size_t)frame * C;
-    while (true) {
-        int c = 0;
-        if (lane == 0) c = atomicAdd(&s_next, 1);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        if (c >= n_comps) break;
-        const int base = s_start[c], cnt = s_start[c + 1] - base;
-        const int root = s_root[c];
-        const int ox = (int)(f.run_x[root] & 0xffffu), oy = (int)f.run_y[root];
+    const int warps_per_frame = gridDim.y * (NT >> 5);
+    for (int c = blockIdx.y * (NT >> 5) + (tid >> 5); c < n_comps; c += warps_per_frame) {
+        const int base = g_start[c], cnt = g_start[c + 1] - base;
+        const int root = comp_root[c];
+        const int ox = (int)(f.run_x[root] & 0xffffu), oy = (int)run_y[root];
         // A component without holes faces ONE background region: outer (all arcs count) or a hole of another component
         // (nested: RETR_EXTERNAL drops it).  The pixel above the first pixel of the root run is background of that region
         // (a root run touches no run above).  Only components with holes of their own test every arc.
-        const bool own_holes = s_status[c] != 0;
-        const bool nested = has_holes && !own_holes && is_hole(f, ox, oy - 1);
+        const bool own_holes = comp_holes[c] != 0;
+        const bool nested = has_holes && !own_holes && g_is_hole(f, ox, oy - 1);
         const int ncnt = nested ? 0 : cnt;
         // one record -> (multiplicity k, sum of the edge directions of its counted arcs)
         auto arcs_of = [&](uint32_t nb, int x, int y, int* dxs, int* dys) -> int {
@@ -567,7 +549,7 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
                 const uint32_t arc = (ent >> (3 + 5 * a)) & 31u;
                 if (own_holes) {
                     const int t4 = arc & 3u;  // 0=E,1=N,2=W,3=S
-                    if (is_hole(f, x + (t4 == 0) - (t4 == 2), y + (t4 == 3) - (t4 == 1))) continue;
+                    if (g_is_hole(f, x + (t4 == 0) - (t4 == 2), y + (t4 == 3) - (t4 == 1))) continue;
                 }
                 ++k;
                 if (!iso) { sdx += dir_dx(arc >> 2); sdy += dir_dy(arc >> 2); }
@@ -579,7 +561,7 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
         long long sx = 0, sy = 0, cross = 0;
         long long m20 = 0, m11 = 0, m02 = 0, m30 = 0, m21 = 0, m12 = 0, m03 = 0, m40 = 0, m31 = 0, m22 = 0, m13 = 0, m04 = 0;
         for (int i = lane; i < ncnt; i += 32) {
-            const uint2 rec = recs[idx16 ? (uint32_t)b16[base + i] : b32[base + i]];
+            const uint2 rec = recs[base + i];
             const int x = (int)(rec.x & 0xffffu), y = (int)(rec.x >> 16);
             x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y);
             fk = min(fk, y * W + x);
@@ -611,7 +593,7 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
             m40 = warp_sum(m40); m31 = warp_sum(m31); m22 = warp_sum(m22); m13 = warp_sum(m13); m04 = warp_sum(m04);
             // second pass: n * (L1 spread about the mean), exact
             for (int i = lane; i < ncnt; i += 32) {
-                const uint2 rec = recs[idx16 ? (uint32_t)b16[base + i] : b32[base + i]];
+                const uint2 rec = recs[base + i];
                 const int x = (int)(rec.x & 0xffffu), y = (int)(rec.x >> 16);
                 int sdx, sdy;
                 const int k = arcs_of(rec.y, x, y, &sdx, &sdy);
@@ -631,38 +613,78 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
             accs[c] = a;
         }
     }
-    __syncthreads();
-    RMCV_PHASE(7);
-    // ---- per component (one thread each): fit, gates, light blob
-    CompRec* comps = sb.comps + (size_t)frame * C;
-    for (int c = tid; c < n_comps; c += NT) {
-        const CompAcc& a = accs[c];
-        CompRec rec;
-        const int n = (int)a.n;
-        rec.firstkey = n > 0 ? a.firstkey : -1;
-        rec.n_points = n;
-        rec.area2 = a.cross < 0 ? -a.cross : a.cross;
-        rec.bbox[0] = a.bbox[0]; rec.bbox[1] = a.bbox[1]; rec.bbox[2] = a.bbox[2]; rec.bbox[3] = a.bbox[3];
-        rec.status = -1;
-        rec.fit_branch = RMCV_FIT_NONE;
-        rec.det0 = 0.f;
-        memset(&rec.blob, 0, sizeof(rec.blob));
-        memset(&rec.ellipse, 0, sizeof(rec.ellipse));
-        if (n > 0) {  // external component
-            ContourSums cs;
-            cs.n = a.n; cs.sx = a.sx; cs.sy = a.sy; cs.cross = a.cross;
-            cs.xx = a.xx; cs.xy = a.xy; cs.yy = a.yy; cs.xxx = a.xxx; cs.xxy = a.xxy; cs.xyy = a.xyy; cs.yyy = a.yyy;
-            cs.xxxx = a.xxxx; cs.xxxy = a.xxxy; cs.xxyy = a.xxyy; cs.xyyy = a.xyyy; cs.yyyy = a.yyyy;
-            cs.s_int = a.s_int; cs.ox = a.ox; cs.oy = a.oy;
-            fit_contour(cs, p.prm, &rec.status, &rec.fit_branch, &rec.det0, &rec.ellipse, &rec.blob);
-        }
-        comps[c] = rec;
-        s_keys[c] = rec.firstkey;
-        s_status[c] = rec.status;
-        sb.comp_root[(size_t)frame * C + c] = s_root[c];
+}
+
+// ------------------------------------------------------------------------------------------ K_F: fits
+// One thread per component over the whole chunk: cv::fitEllipseDirect incl. its fallback, the ratio/tilt gates and the
+// rm::lightblob ctor (reference: src/objdetect.cpp:62-84, src/core.cpp:9-19) from the integer sums.
+struct FitParams {
+    Geometry g;
+    SlotBuffers sb;
+    rmcv_params prm;
+};
+
+__global__ void __launch_bounds__(64) fit_kernel(const FitParams p) {
+    const int frame = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int C = p.g.C;
+    if (c >= p.sb.counters[frame].n_comps) return;
+    const CompAcc& a = p.sb.acc[(size_t)frame * C + c];
+    CompRec rec;
+    const int n = (int)a.n;
+    rec.firstkey = n > 0 ? a.firstkey : -1;
+    rec.n_points = n;
+    rec.area2 = a.cross < 0 ? -a.cross : a.cross;
+    rec.bbox[0] = a.bbox[0]; rec.bbox[1] = a.bbox[1]; rec.bbox[2] = a.bbox[2]; rec.bbox[3] = a.bbox[3];
+    rec.status = -1;
+    rec.fit_branch = RMCV_FIT_NONE;
+    rec.det0 = 0.f;
+    memset(&rec.blob, 0, sizeof(rec.blob));
+    memset(&rec.ellipse, 0, sizeof(rec.ellipse));
+    if (n > 0) {  // external component
+        ContourSums cs;
+        cs.n = a.n; cs.sx = a.sx; cs.sy = a.sy; cs.cross = a.cross;
+        cs.xx = a.xx; cs.xy = a.xy; cs.yy = a.yy; cs.xxx = a.xxx; cs.xxy = a.xxy; cs.xyy = a.xyy; cs.yyy = a.yyy;
+        cs.xxxx = a.xxxx; cs.xxxy = a.xxxy; cs.xxyy = a.xxyy; cs.xyyy = a.xyyy; cs.yyyy = a.yyyy;
+        cs.s_int = a.s_int; cs.ox = a.ox; cs.oy = a.oy;
+        fit_contour(cs, p.prm, &rec.status, &rec.fit_branch, &rec.det0, &rec.ellipse, &rec.blob);
     }
+    p.sb.comps[(size_t)frame * C + c] = rec;
+}
+
+// ------------------------------------------------------------------------------------------ K_O: order, pairs, output
+// One CTA per frame: ordering into cv::findContours order, the O(P^2) pair gates of rm::filter_armours and rm::armour
+// geometry (reference: src/objdetect.cpp:114-166, src/core.cpp:21-49) with an order-preserving block compaction, and
+// the dense write-out into pinned, device-mapped host memory (space claimed with one atomicAdd per array).
+struct OrderParams {
+    Geometry g;
+    SlotBuffers sb;
+    rmcv_params prm;
+    int frame_base;
+    rmcv_frame_info* o_frames;
+    rmcv_contour_info* o_contours;
+    rmcv_lightblob* o_blobs;
+    rmcv_armour* o_armours;
+    int frames;  // frames in this chunk (index of the allocator entry in sb.counters)
+};
+
+__global__ void __launch_bounds__(128) order_kernel(const OrderParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int sh_scan[33];
+    __shared__ int s_np, s_nc, s_nn, s_flags, s_off[3];
+    const Geometry& g = p.g;
+    const int W = g.W, C = g.C, A = g.A;
+    const int frame = blockIdx.x;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const SlotBuffers& sb = p.sb;
+    FrameCounters& fc = sb.counters[frame];
+    const int n_comps = fc.n_comps;
+    int32_t* s_keys = reinterpret_cast<int32_t*>(smem);
+    int32_t* s_status = s_keys + C;
+    const CompRec* comps = sb.comps + (size_t)frame * C;
+    if (tid == 0) { s_np = 0; s_nc = 0; s_nn = 0; s_flags = fc.flags; }
+    for (int c = tid; c < n_comps; c += NT) { s_keys[c] = comps[c].firstkey; s_status[c] = comps[c].status; }
     __syncthreads();
-    RMCV_PHASE(8);
     // ---- order: rank = number of external components with a larger first-pixel key (reverse raster order)
     rmcv_contour_info* oc = sb.s_contours + (size_t)frame * C;
     rmcv_lightblob* ob = sb.s_blobs + (size_t)frame * C;
@@ -693,7 +715,6 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
         else if (stt == RMCV_CONTOUR_NEGATIVE) atomicAdd(&s_nn, 1);
     }
     __syncthreads();
-    RMCV_PHASE(9);
     // ---- pairs in lexicographic (i,j) order (src/objdetect.cpp:122-163)
     const int P = s_np;
     const long long npairs = (long long)P * (P - 1) / 2;
@@ -723,14 +744,13 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
         base += total;
     }
     const int n_arm = min(base, A);
-    RMCV_PHASE(10);
     // ---- claim dense space in the chunk's region of the pinned result arrays, write out
     if (tid == 0) {
         FrameCounters& al = sb.counters[p.frames];
         s_off[0] = atomicAdd(&al.n_runs, s_nc);
         s_off[1] = atomicAdd(&al.n_comps, P);
         s_off[2] = atomicAdd(&al.n_holes, n_arm);
-        fc.n_comps = n_comps; fc.n_holes = s_ncomp - n_runs + s_nadj; fc.flags = s_flags;
+        fc.flags = s_flags;
         fc.n_contours = s_nc; fc.n_positive = P; fc.n_negative = s_nn; fc.n_armours = n_arm;
     }
     __syncthreads();
@@ -747,51 +767,77 @@ __global__ void __launch_bounds__(256, 2) frame_kernel(const FrameParams p) {
     copy_words(p.o_contours + base_c, oc, (size_t)s_nc * sizeof(rmcv_contour_info), tid, NT);
     copy_words(p.o_blobs + base_b, ob, (size_t)P * sizeof(rmcv_lightblob), tid, NT);
     copy_words(p.o_armours + base_a, oa, (size_t)n_arm * sizeof(rmcv_armour), tid, NT);
-    __syncthreads();
-    RMCV_PHASE(11);
 }
 
-cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_smem_optin, cudaStream_t st, int64_t* launches) {
-    FrameParams p;
-    p.g = L.g; p.sb = *L.sb; p.prm = prm; p.frame_base = L.frame_base;
-    p.o_frames = L.o_frames; p.o_contours = L.o_contours; p.o_blobs = L.o_blobs; p.o_armours = L.o_armours;
-    p.frames = L.frames;
-    // shared-memory run capacity: two CTAs per SM when the frame geometry allows it, never above the run capacity
-    const char* env = getenv("RMCV_FRAME_RS");
-    int Rs = env ? atoi(env) : 4096;
-    if (Rs > L.g.R) Rs = L.g.R;
-    size_t smem = frame_smem_bytes(L.g.H, Rs, L.g.C);
-    while (smem > (size_t)max_smem_optin && Rs > 0) { Rs = Rs > 1024 ? Rs - 1024 : 0; smem = frame_smem_bytes(L.g.H, Rs, L.g.C); }
-    if (smem > (size_t)max_smem_optin) return cudaErrorInvalidConfiguration;
-    p.Rs = Rs;
-    p.dbg_clock = nullptr;
-    static long long* dbg = nullptr;
-    const bool timing = getenv("RMCV_FRAME_TIMING") != nullptr;
-    if (timing) {
-        if (!dbg) cudaMalloc(reinterpret_cast<void**>(&dbg), sizeof(long long) * 16 * 4096);
-        p.dbg_clock = dbg;
+// Enqueues the labelling stages of one chunk.  stage_done(i) is called after each kernel (profiling events).
+cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_smem_optin, cudaStream_t st, int64_t* launches,
+                          void (*stage_done)(void*, int, cudaStream_t), void* stage_arg) {
+    cudaError_t e;
+    auto done = [&](int stage) { if (stage_done) stage_done(stage_arg, stage, st); };
+    {   // K_E
+        EmitLaunch el;
+        el.bits = L.sb->bits; el.W = L.g.W; el.H = L.g.H; el.batch = L.frames;
+        el.rows = L.sb->rows; el.run_x = L.sb->run_x; el.run_y = L.sb->run_y; el.counters = L.sb->counters; el.R = L.g.R;
+        el.recs = L.sb->recs; el.PC = L.g.PC;
+        e = launch_emit(el, st, launches);
+        if (e != cudaSuccess) return e;
+        done(RMCV_STAGE_EMIT);
     }
-    const char* envnt = getenv("RMCV_FRAME_NT");
-    int NT = envnt ? atoi(envnt) : 256;
-    if (NT < 32 || NT > 256 || (NT & 31)) NT = 256;
-    cudaError_t e = cudaFuncSetAttribute(frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    frame_kernel<<<L.frames, NT, smem, st>>>(p);
-    if (launches) ++*launches;
-    if (timing) {  // debug aid: average cycles per phase over the chunk's frames
-        cudaStreamSynchronize(st);
-        static long long h[16 * 4096];
-        const int nf = L.frames < 4096 ? L.frames : 4096;
-        cudaMemcpy(h, dbg, sizeof(long long) * 16 * nf, cudaMemcpyDeviceToHost);
-        static const char* names[] = {"", "load", "links", "jump+union", "flatten+count", "gaps", "bucket", "sums", "fit", "order", "pairs", "out"};
-        double acc[16] = {0}, tot = 0;
-        for (int fi = 0; fi < nf; ++fi)
-            for (int i = 1; i <= 11; ++i) acc[i] += (double)(h[fi * 16 + i] - h[fi * 16 + i - 1]);
-        fprintf(stderr, "[frame timing, cycles/frame]");
-        for (int i = 1; i <= 11; ++i) { fprintf(stderr, " %s %.0f", names[i], acc[i] / nf); tot += acc[i] / nf; }
-        fprintf(stderr, " | total %.0f (smem %zu B, %d threads)\n", tot, smem, NT);
+    {   // K_L
+        LabelParams p;
+        p.g = L.g; p.sb = *L.sb;
+        const char* env = getenv("RMCV_FRAME_RS");
+        int Rs = env ? atoi(env) : 3072;  // four CTAs per SM at 1280x1024 (gpurun_out/exp_rs*.json)
+        if (Rs > L.g.R) Rs = L.g.R;
+        size_t smem = label_smem_bytes(L.g.H, Rs, L.g.C);
+        while (smem > (size_t)max_smem_optin && Rs > 0) { Rs = Rs > 1024 ? Rs - 1024 : 0; smem = label_smem_bytes(L.g.H, Rs, L.g.C); }
+        if (smem > (size_t)max_smem_optin) return cudaErrorInvalidConfiguration;
+        p.Rs = Rs;
+        e = cudaFuncSetAttribute(label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        label_kernel<<<L.frames, 256, smem, st>>>(p);
+        if (launches) ++*launches;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        done(RMCV_STAGE_LABEL);
     }
-    return cudaGetLastError();
+    {   // K_C
+        ContourParams p;
+        p.g = L.g; p.sb = *L.sb; p.prm = prm;
+        const char* env = getenv("RMCV_CONTOUR_GY");
+        int gy = env ? atoi(env) : 8;                      // 8 blocks x 4 warps per frame
+        if (gy * 4 > L.g.C) gy = (L.g.C + 3) / 4;
+        if (gy < 1) gy = 1;
+        dim3 grid(L.frames, gy);
+        contour_kernel<<<grid, 128, 0, st>>>(p);
+        if (launches) ++*launches;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        done(RMCV_STAGE_CONTOUR);
+    }
+    {   // K_F
+        FitParams p;
+        p.g = L.g; p.sb = *L.sb; p.prm = prm;
+        dim3 grid((L.g.C + 63) / 64, L.frames);
+        fit_kernel<<<grid, 64, 0, st>>>(p);
+        if (launches) ++*launches;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        done(RMCV_STAGE_FIT);
+    }
+    {   // K_O
+        OrderParams p;
+        p.g = L.g; p.sb = *L.sb; p.prm = prm; p.frame_base = L.frame_base;
+        p.o_frames = L.o_frames; p.o_contours = L.o_contours; p.o_blobs = L.o_blobs; p.o_armours = L.o_armours;
+        p.frames = L.frames;
+        const size_t smem = (size_t)2 * L.g.C * 4 + 16;
+        if (smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        order_kernel<<<L.frames, 128, smem, st>>>(p);
+        if (launches) ++*launches;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        done(RMCV_STAGE_ORDER);
+    }
+    return cudaSuccess;
 }
 
 // ------------------------------------------------------------------------------------------ standalone a2 / a3

@@ -71,17 +71,12 @@ struct PixelParams {
     int RC, S;           // rows per TMA chunk, ring stages
     int srow;            // shared-memory row stride in bytes
     int gpr;             // 16-pixel groups per row (BGR) / per row (Bayer)
-    int halo;            // threshold-row halo: 2 for the close alone, 3 when boundary-pixel records are emitted too
-                         // (they need one final-mask row above and below the band)
+    int halo;            // threshold-row halo of the close: 2
     uint32_t coef[6];    // dp4a coefficient words (signed bytes) for the 4 pixels of a 12-byte group
     int acc0;            // -lower_bound (or the constants that force all-0 / all-1)
     int contiguous;      // pitch == row bytes: a chunk is one bulk copy
     int mask_vec;        // mask rows allow 16-byte stores
     uint32_t last_valid; // valid bits of the last word of a row
-    // run emission for the labelling stage (null = mask only)
-    int2* rows; uint32_t* run_x; uint16_t* run_y; FrameCounters* counters; int R;
-    // boundary-pixel records for the contour statistics (null = none): {x | y<<16, 8-neighbourhood}
-    uint2* recs; int PC;
     // Bayer only
     int bayer;           // 0 = BGR
     int px, py;          // parity (x&1, y&1) of the site that samples channel `plus`... see kernel
@@ -108,16 +103,13 @@ __host__ __device__ inline size_t pix_smem_bytes(int S, int RC, int srow, int BH
     size_t bars = ((size_t)S * 8 + 15) & ~(size_t)15;
     size_t t = (size_t)(BH + 2 * halo_rows) * TW * 4;
     size_t d = (size_t)(BH + 2 * halo_rows - 2) * TW * 4;
-    const size_t scan = (size_t)(96 + BH * WB) * 4;  // scan scratch + per-word prefix of the run / record emission
-    if (d < scan) d = scan;
     d += 16;
     return stage + bars + t + d;
 }
 
 // ------------------------------------------------------------------------------------------ morphology + stores
 // t: (nout+2*hl) x TW threshold words (row 0 <-> image row y0-hl), zero outside the image; hl = p.halo.
-// Writes the final mask of rows [y0, y0+nout) to global as bytes and as bit words, emits the runs and, with hl == 3,
-// the boundary-pixel records.
+// Writes the final mask of rows [y0, y0+nout) to global as bytes and as bit words (the labelling stages read the bits).
 __device__ __forceinline__ void close_and_store(const PixelParams& p, uint32_t* t, uint32_t* d, int frame, int y0,
                                                 int nout, int tid, int NT) {
     const int WB = p.WB, TW = WB + 2, H = p.H, hl = p.halo;
@@ -165,65 +157,6 @@ __device__ __forceinline__ void close_and_store(const PixelParams& p, uint32_t* 
         if (j >= e && j < nout + e) gbits[(size_t)(j - e) * WB + k] = mv;
     }
     __syncthreads();
-    // ---- emission for the labelling stage, in raster order inside the band:
-    //   runs     every maximal horizontal run of the band's final mask; rows[y] = (first, end) keeps every row addressable;
-    //   records  every foreground pixel with a background 4-neighbour, with its 3x3 neighbourhood.
-    // Both are counted per thread (a few consecutive words each), ranked by ONE block scan of the packed counts, and the
-    // band claims its ranges of the frame's arrays with ONE 64-bit atomicAdd (bands land in arrival order).  The atomic's
-    // round trip is hidden behind the byte-mask stores.  Records are then fetched balanced: every thread takes "its"
-    // candidates by binary search over the per-word prefix, so a blob cap does not serialise on one thread.
-    const bool emit = p.run_x != nullptr;
-    int* scratch = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(d) + 7) & ~(uintptr_t)7);  // d is dead after the erode
-    int* prefix = scratch + 80;                    // [nwords + 1] record prefix per word
-    const int nwords = nout * WB;
-    const int per = (nwords + NT - 1) / NT;
-    const int w0 = min(nwords, tid * per), w1 = min(nwords, w0 + per);
-    const int j0 = w0 / WB, k0 = w0 - j0 * WB;
-    auto boundary_word = [&](int j, int k) -> uint32_t {  // needs the halo rows of mm (hl == 3)
-        const uint32_t* c = m + (size_t)j * WB + k;
-        const uint32_t w = c[0];
-        if (w == 0u) return 0u;
-        const uint32_t prev = k > 0 ? (c[-1] >> 31) : 0u;
-        const uint32_t next = k + 1 < WB ? (c[1] & 1u) : 0u;
-        return w & ~(c[-WB] & c[WB] & ((w << 1) | prev) & ((w >> 1) | (next << 31)));
-    };
-    const bool want_recs = emit && p.recs != nullptr;
-    int run_excl = 0, rec_total = 0;
-    if (emit) {
-        int nrun = 0, nrec = 0;
-        {
-            int j = j0, k = k0;
-            for (int idx = w0; idx < w1; ++idx) {
-                const uint32_t w = m[idx];
-                if (w) {
-                    const uint32_t prev = k > 0 ? (m[idx - 1] >> 31) : 0u;
-                    nrun += __popc(w & ~((w << 1) | prev));
-                    if (want_recs) nrec += __popc(boundary_word(j, k));
-                }
-                if (++k == WB) { k = 0; ++j; }
-            }
-        }
-        long long total;
-        const long long excl = block_excl_scan64((long long)(unsigned)nrun | ((long long)nrec << 32), &total, reinterpret_cast<long long*>(scratch));
-        run_excl = (int)(excl & 0xffffffffll);
-        rec_total = (int)(total >> 32);
-        if (tid == 0) {
-            static_assert(offsetof(FrameCounters, n_recs) == offsetof(FrameCounters, n_runs) + 4, "n_runs/n_recs must pack into 64 bits");
-            const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(&p.counters[frame].n_runs),
-                                                     (unsigned long long)total);
-            scratch[72] = (int)(old & 0xffffffffull);
-            scratch[73] = (int)(old >> 32);
-        }
-        if (want_recs) {
-            int j = j0, k = k0, run = (int)(excl >> 32);
-            for (int idx = w0; idx < w1; ++idx) {
-                prefix[idx] = run;
-                if (m[idx]) run += __popc(boundary_word(j, k));
-                if (++k == WB) { k = 0; ++j; }
-            }
-            if (tid == 0) prefix[nwords] = rec_total;
-        }
-    }
     // ---- byte mask: one 16-byte store per 16 pixels
     if (p.mask != nullptr) {
         const uint16_t* m16 = reinterpret_cast<const uint16_t*>(m);
@@ -244,66 +177,6 @@ __device__ __forceinline__ void close_and_store(const PixelParams& p, uint32_t* 
                 const uint32_t w[4] = {o.x, o.y, o.z, o.w};
                 for (int q = 0; q < 16 && g * 16 + q < p.W; ++q) dst[q] = (uint8_t)(w[q >> 2] >> ((q & 3) * 8));
             }
-        }
-    }
-    if (!emit) return;
-    __syncthreads();  // claimed bases and the record prefix are visible
-    {
-        int rs = scratch[72] + run_excl;
-        const int R = p.R;
-        uint16_t* run_x16 = reinterpret_cast<uint16_t*>(p.run_x + (size_t)frame * R);
-        uint16_t* run_y = p.run_y + (size_t)frame * R;
-        int2* rows = p.rows + (size_t)frame * H;
-        int j = j0, k = k0;
-        for (int idx = w0; idx < w1; ++idx) {
-            const uint32_t w = m[idx];
-            const uint32_t prev = k > 0 ? (m[idx - 1] >> 31) : 0u;
-            const int y = y0 + j;
-            if (k == 0) rows[y].x = rs;
-            if (w) {
-                const uint32_t next = k + 1 < WB ? (m[idx + 1] & 1u) : 0u;
-                uint32_t starts = w & ~((w << 1) | prev);
-                uint32_t ends = w & ~((w >> 1) | (next << 31));
-                int re = rs - (int)(prev & w & 1u);  // a run entering from the previous word is still open
-                while (starts) {
-                    const int b = __ffs(starts) - 1;
-                    starts &= starts - 1;
-                    if (rs < R) { run_x16[2 * rs] = (uint16_t)(k * 32 + b); run_y[rs] = (uint16_t)y; }
-                    ++rs;
-                }
-                while (ends) {
-                    const int b = __ffs(ends) - 1;
-                    ends &= ends - 1;
-                    if (re < R) run_x16[2 * re + 1] = (uint16_t)(k * 32 + b);
-                    ++re;
-                }
-            }
-            if (k == WB - 1) rows[y].y = rs;
-            if (++k == WB) { k = 0; ++j; }
-        }
-    }
-    if (want_recs) {
-        const int base = scratch[73];
-        uint2* recs = p.recs + (size_t)frame * p.PC;
-        for (int q = tid; q < rec_total; q += NT) {
-            int lo = 0, hi = nwords;               // last word index with prefix <= q
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (prefix[mid] <= q) lo = mid; else hi = mid;
-            }
-            const int j = lo / WB, k = lo - j * WB;
-            uint32_t b = boundary_word(j, k);
-            for (int skip = q - prefix[lo]; skip > 0; --skip) b &= b - 1;
-            const int i = __ffs(b) - 1;
-            const uint32_t* c = m + (size_t)j * WB + k;
-            auto win = [&](const uint32_t* r) -> uint64_t {
-                const uint32_t prev = k > 0 ? (r[-1] >> 31) : 0u;
-                const uint32_t next = k + 1 < WB ? (r[1] & 1u) : 0u;
-                return (uint64_t)prev | ((uint64_t)r[0] << 1) | ((uint64_t)next << 33);
-            };
-            const uint32_t u3 = (uint32_t)(win(c - WB) >> i) & 7u, c3 = (uint32_t)(win(c) >> i) & 7u, d3 = (uint32_t)(win(c + WB) >> i) & 7u;
-            const uint32_t nb = u3 | ((c3 & 1u) << 3) | ((c3 >> 2) << 4) | (d3 << 5);
-            if (base + q < p.PC) recs[base + q] = make_uint2((uint32_t)(k * 32 + i) | ((uint32_t)(y0 + j) << 16), nb);
         }
     }
 }
@@ -515,9 +388,7 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
     p.mask_vec = (L.mask != nullptr) && ((L.mask_pitch & 15) == 0) && ((L.mask_frame_stride & 15) == 0) &&
                  ((((size_t)L.mask) & 15) == 0);
     p.lb = L.lower_bound;
-    p.rows = L.rows; p.run_x = L.run_x; p.run_y = L.run_y; p.counters = L.counters; p.R = L.R;
-    p.recs = L.recs; p.PC = L.PC;
-    p.halo = L.recs ? 3 : 2;
+    p.halo = 2;
     const int hl = p.halo;
 
     // band height: tall bands amortise the 4 halo rows; small batches need more, shorter bands to fill 148 SMs
@@ -569,12 +440,11 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
         int RC = env_int("RMCV_PIX_RC", 0);
         if (RC <= 0) RC = max(1, min(16, 16384 / p.srow));  // ~16 KB per TMA chunk (sweep: gpurun_out/sweep.log)
         if (RC > BH + 2 * hl) RC = BH + 2 * hl;
-        // with the emission tail a shallower ring and more resident CTAs win (gpurun_out/exp_*.json: S=2, 256 threads)
-        int S = env_int("RMCV_PIX_S", L.run_x ? 2 : 4);
+        int S = env_int("RMCV_PIX_S", 4);
         int NT = env_int("RMCV_PIX_NT", 0);
         if (NT <= 0) {  // one 16-pixel group per thread per chunk, rounded up to whole warps
             NT = ((RC * p.gpr + 31) / 32) * 32;
-            NT = max(128, min(L.run_x ? 256 : 512, NT));
+            NT = max(128, min(512, NT));
         }
         p.RC = RC; p.S = S;
         size_t smem = pix_smem_bytes(S, RC, p.srow, BH, p.WB, hl);
@@ -632,12 +502,12 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
     int NT = env_int("RMCV_PIX_NT", 256);
     if (L.W < 3 || L.H < 3) return cudaErrorInvalidValue;
     size_t raw_bytes = ((size_t)(BH + 2 * hl + 4) * p.srow + 15) & ~(size_t)15;
-    size_t smem = raw_bytes + 16 + (size_t)(BH + 2 * hl) * (p.WB + 2) * 4 + (size_t)(BH + 2 * hl - 2) * (p.WB + 2) * 4 + 640 + (size_t)BH * p.WB * 4;
+    size_t smem = raw_bytes + 16 + (size_t)(BH + 2 * hl) * (p.WB + 2) * 4 + (size_t)(BH + 2 * hl - 2) * (p.WB + 2) * 4 + 256;
     while (smem > (size_t)max_smem && p.BH > 1) {
         p.BH = max(1, p.BH / 2); BH = p.BH;
         p.bands = (L.H + BH - 1) / BH;
         raw_bytes = ((size_t)(BH + 2 * hl + 4) * p.srow + 15) & ~(size_t)15;
-        smem = raw_bytes + 16 + (size_t)(BH + 2 * hl) * (p.WB + 2) * 4 + (size_t)(BH + 2 * hl - 2) * (p.WB + 2) * 4 + 640 + (size_t)BH * p.WB * 4;
+        smem = raw_bytes + 16 + (size_t)(BH + 2 * hl) * (p.WB + 2) * 4 + (size_t)(BH + 2 * hl - 2) * (p.WB + 2) * 4 + 256;
     }
     const long long grid2 = (long long)L.batch * p.bands;
     cudaError_t e = cudaFuncSetAttribute(pixel_bayer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
