@@ -27,11 +27,11 @@ struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
     void* tmp_host = nullptr; size_t tmp_host_bytes = 0;
     int last_nchunks = 0;
     int last_kind = 0;  // 0 none, 1 extract, 2 detect
-    cudaEvent_t t_start[4] = {nullptr, nullptr, nullptr, nullptr}, t_stop[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t t_start[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, t_stop[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     // Streams of the ctx.  The pixel kernels of consecutive chunks run back to back on `pix`; the labelling kernels of
     // chunk i run on the high-priority stream `lab` behind an event, so that they overlap the pixel kernel of chunk
     // i+1; host<->device staging copies have their own streams (both copy engines stay busy).
-    cudaStream_t pix = nullptr, lab = nullptr, h2d = nullptr, d2h = nullptr;
+    cudaStream_t pix = nullptr, lab = nullptr, out = nullptr, h2d = nullptr, d2h = nullptr;
     bool own_pix = false;
 };
 
@@ -84,6 +84,7 @@ int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
     (void)first;
     RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.ev_pix, cudaEventDisableTiming));
     RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.ev_lab, cudaEventDisableTiming));
+    RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.ev_fit, cudaEventDisableTiming));
     RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.ev_h2d, cudaEventDisableTiming));
     RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.ev_d2h, cudaEventDisableTiming));
     return RMCV_OK;
@@ -97,6 +98,7 @@ void free_slot(SlotBuffers& sb) {
     if (sb.masks) cudaFree(sb.masks);
     if (sb.ev_pix) cudaEventDestroy(sb.ev_pix);
     if (sb.ev_lab) cudaEventDestroy(sb.ev_lab);
+    if (sb.ev_fit) cudaEventDestroy(sb.ev_fit);
     if (sb.ev_h2d) cudaEventDestroy(sb.ev_h2d);
     if (sb.ev_d2h) cudaEventDestroy(sb.ev_d2h);
     memset(&sb, 0, sizeof(sb));
@@ -173,6 +175,7 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
     if (ps) { ps->full = true; cudaEventRecord(ps->lab[0], sl); }
     FrameLaunch fl;
     fl.g = call_geometry(ctx, W, H); fl.frames = frames; fl.sb = &sb; fl.frame_base = frame_base;
+    fl.st_out = ex->out;
     fl.o_frames = ctx->h_frames; fl.o_contours = ctx->h_contours; fl.o_blobs = ctx->h_blobs; fl.o_armours = ctx->h_armours;
     struct Mark { ProfSet* ps; rmcv_ctx* ctx; };
     Mark mk{ps, ctx};
@@ -182,7 +185,7 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
         m->ctx->prof_launches[stage] += 1;
     };
     RMCV_CUDA(ctx, launch_frames(fl, prm, ctx->max_smem_optin, sl, &ctx->kernel_launches, stage_done, &mk));
-    RMCV_CUDA(ctx, cudaEventRecord(sb.ev_lab, sl));
+    RMCV_CUDA(ctx, cudaEventRecord(sb.ev_lab, ex->out));
     return RMCV_OK;
 }
 
@@ -218,6 +221,7 @@ int sync_all(rmcv_ctx* ctx) {
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->h2d));
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->pix));
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->lab));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(ex->out));
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->d2h));
     prof_collect(ctx);
     return RMCV_OK;
@@ -340,11 +344,18 @@ int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
         CtxExtra* ex = extra(ctx);
         int least = 0, greatest = 0;
         cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if (const char* pe = getenv("RMCV_PRIO")) {   // experiment: 1 = equal priorities, 2 = pixel stream first
+            if (atoi(pe) == 1) greatest = least;
+            else if (atoi(pe) == 2) { const int t = least; least = greatest; greatest = t; }
+        }
         cudaError_t se = cudaSuccess;
         if (cfg->stream) { ex->pix = reinterpret_cast<cudaStream_t>(cfg->stream); ex->own_pix = false; }
         else { se = cudaStreamCreateWithPriority(&ex->pix, cudaStreamNonBlocking, least); ex->own_pix = true; }
-        if (getenv("RMCV_SERIAL")) ex->lab = ex->pix;   // debug aid: every kernel on one stream
-        else if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&ex->lab, cudaStreamNonBlocking, greatest);
+        if (getenv("RMCV_SERIAL")) { ex->lab = ex->pix; ex->out = ex->pix; }   // debug aid: every kernel on one stream
+        else {
+            if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&ex->lab, cudaStreamNonBlocking, greatest);
+            if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&ex->out, cudaStreamNonBlocking, greatest);
+        }
         if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&ex->h2d, cudaStreamNonBlocking);
         if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&ex->d2h, cudaStreamNonBlocking);
         if (se != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "stream creation failed: %s", cudaGetErrorString(se)); return fail(RMCV_ERR_CUDA); }
@@ -385,8 +396,9 @@ int rmcv_ctx_destroy(rmcv_ctx* ctx) {
             for (int i = 0; i < 2; ++i) cudaEventDestroy(ps.pix[i]);
             for (int i = 0; i < RMCV_STAGE_COUNT; ++i) cudaEventDestroy(ps.lab[i]);
         }
-        for (int i = 0; i < 4; ++i) { if (ex->t_start[i]) cudaEventDestroy(ex->t_start[i]); if (ex->t_stop[i]) cudaEventDestroy(ex->t_stop[i]); }
+        for (int i = 0; i < 5; ++i) { if (ex->t_start[i]) cudaEventDestroy(ex->t_start[i]); if (ex->t_stop[i]) cudaEventDestroy(ex->t_stop[i]); }
         if (ex->lab && ex->lab != ex->pix) cudaStreamDestroy(ex->lab);
+        if (ex->out && ex->out != ex->pix) cudaStreamDestroy(ex->out);
         if (ex->pix && ex->own_pix) cudaStreamDestroy(ex->pix);
         if (ex->h2d) cudaStreamDestroy(ex->h2d);
         if (ex->d2h) cudaStreamDestroy(ex->d2h);
@@ -784,8 +796,8 @@ int rmcv_timer_start(rmcv_ctx* ctx) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
     CtxExtra* ex = extra(ctx);
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st[4] = {ex->pix, ex->lab, ex->h2d, ex->d2h};
-    for (int i = 0; i < 4; ++i) {
+    cudaStream_t st[5] = {ex->pix, ex->lab, ex->out, ex->h2d, ex->d2h};
+    for (int i = 0; i < 5; ++i) {
         if (!ex->t_start[i]) { RMCV_CUDA(ctx, cudaEventCreate(&ex->t_start[i])); RMCV_CUDA(ctx, cudaEventCreate(&ex->t_stop[i])); }
         RMCV_CUDA(ctx, cudaEventRecord(ex->t_start[i], st[i]));
     }
@@ -796,13 +808,13 @@ int rmcv_timer_stop(rmcv_ctx* ctx, double* ms) {
     if (!ctx || !ms) return RMCV_ERR_INVALID_ARG;
     CtxExtra* ex = extra(ctx);
     if (!ex->t_start[0]) return set_err(ctx, RMCV_ERR_STATE, "rmcv_timer_stop without rmcv_timer_start");
-    cudaStream_t st[4] = {ex->pix, ex->lab, ex->h2d, ex->d2h};
-    for (int i = 0; i < 4; ++i) RMCV_CUDA(ctx, cudaEventRecord(ex->t_stop[i], st[i]));
+    cudaStream_t st[5] = {ex->pix, ex->lab, ex->out, ex->h2d, ex->d2h};
+    for (int i = 0; i < 5; ++i) RMCV_CUDA(ctx, cudaEventRecord(ex->t_stop[i], st[i]));
     int rc = sync_all(ctx);
     if (rc != RMCV_OK) return rc;
     float best = 0.f;
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) {
+    for (int i = 0; i < 5; ++i)
+        for (int j = 0; j < 5; ++j) {
             float t = 0.f;
             RMCV_CUDA(ctx, cudaEventElapsedTime(&t, ex->t_start[i], ex->t_stop[j]));
             if (t > best) best = t;

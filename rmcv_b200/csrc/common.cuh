@@ -68,7 +68,7 @@ struct SlotBuffers {
     int32_t* parent;        // [CF][R]       flattened labels (root run index), written back by the frame kernel
     int32_t* gparent;       // [CF][R+2]     background-gap forest; only used when a frame does not fit in shared memory
     int16_t* run_cid;       // [CF][R]       component id per run; same remark
-    uint2* recs;            // [CF][PC]      boundary pixels {x | y<<16, 8-neighbourhood} in emission order (emit kernel)
+    uint2* recs;            // [CF][PC]      boundary pixels {x | y<<16, 8-neighbourhood | run<<8} in emission order (emit kernel)
     uint2* recs2;           // [CF][PC]      the same records bucketed by component (label kernel)
     int32_t* comp_start;    // [CF][C+1]     first record of each component in recs2
     int32_t* sorted;        // [CF][SC]      record indices bucketed by component (and the gap join flags before that) when
@@ -88,6 +88,7 @@ struct SlotBuffers {
     size_t frames_bytes, masks_bytes;
     // chunk i of a call uses slot i&1; the events order the ctx streams (api.cu) around the slot's scratch
     cudaEvent_t ev_pix;     // pixel kernel done  (bits written; staging frames read)
+    cudaEvent_t ev_fit;     // fit kernel done (the order kernel runs on its own stream behind it)
     cudaEvent_t ev_lab;     // labelling stages done (scratch free again)
     cudaEvent_t ev_h2d;     // staging upload done
     cudaEvent_t ev_d2h;     // mask download done
@@ -151,6 +152,7 @@ cudaError_t launch_pixel_stage(const PixelLaunch& p, int sm_count, cudaStream_t 
 struct FrameLaunch {
     Geometry g; int frames; SlotBuffers* sb;
     int frame_base;               // index of the chunk's first frame in the batch
+    cudaStream_t st_out;          // stream of the order/write-out kernel (null = same stream)
     rmcv_frame_info* o_frames;    // device-visible pointers of the pinned result arrays
     rmcv_contour_info* o_contours;
     rmcv_lightblob* o_blobs;

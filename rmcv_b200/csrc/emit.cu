@@ -6,7 +6,7 @@
 // One CTA = one band of BH rows of one frame, read from the bit mask the pixel kernel wrote (1/8 B per pixel, still in
 // L2), plus one row above and below.  In raster order inside the band:
 //   runs     every maximal horizontal run; rows[y] = (first, end) keeps every row addressable;
-//   records  {x | y<<16, 8-neighbourhood} of every boundary pixel.
+//   records  {x | y<<16, 8-neighbourhood | run index << 8} of every boundary pixel.
 // Foreground is sparse, so the band's non-zero words are first compacted (ballots) into a raster-ordered list and
 // everything else works on that list: run starts and boundary pixels are counted per entry, ranked by ONE block scan of
 // the packed counts, and the band claims its ranges of the frame's arrays with ONE 64-bit atomicAdd (bands land in
@@ -41,9 +41,10 @@ __global__ void __launch_bounds__(128) emit_kernel(const EmitParams p) {
     uint32_t* m = mm + WB;                                           // row 0 of m <-> image row y0
     uint16_t* list = reinterpret_cast<uint16_t*>(mm + (size_t)(p.BH + 2) * WB);  // [cap] non-zero words, raster order
     const uint32_t* gb = p.bits + (size_t)frame * H * WB;
-    for (int i = tid; i < (nout + 2) * WB; i += NT) {
-        const int y = y0 - 1 + i / WB;
-        mm[i] = (y >= 0 && y < H) ? __ldg(gb + (size_t)(y0 - 1) * WB + i) : 0u;
+    {   // rows y0-1 .. y0+nout are contiguous in the bit mask; rows outside the image read as background
+        const int lo_i = y0 > 0 ? 0 : WB, hi_i = y0 + nout < H ? (nout + 2) * WB : (nout + 1) * WB;
+        const long long off = ((long long)y0 - 1) * WB;
+        for (int i = tid; i < (nout + 2) * WB; i += NT) mm[i] = (i >= lo_i && i < hi_i) ? __ldg(gb + (off + i)) : 0u;
     }
     __syncthreads();
     // ---- the non-zero words of the band, in raster order (foreground is sparse: everything below works on this list)
@@ -163,7 +164,13 @@ __global__ void __launch_bounds__(128) emit_kernel(const EmitParams p) {
             };
             const uint32_t u3 = (uint32_t)(win(c - WB) >> i) & 7u, c3 = (uint32_t)(win(c) >> i) & 7u, d3 = (uint32_t)(win(c + WB) >> i) & 7u;
             const uint32_t nb = u3 | ((c3 & 1u) << 3) | ((c3 >> 2) << 4) | (d3 << 5);
-            if (rec_base + q < p.PC) recs[rec_base + q] = make_uint2((uint32_t)(k * 32 + i) | ((uint32_t)(y0 + j) << 16), nb);
+            // the run that owns the pixel: the last one started at or before bit i, else the one entering from the previous word
+            const uint32_t w = c[0];
+            const uint32_t pv = k > 0 ? (c[-1] >> 31) : 0u;
+            const uint32_t starts = w & ~((w << 1) | pv);
+            const int run = run_base + erun[lo] + __popc(starts & (0xffffffffu >> (31 - i))) - 1;
+            if (rec_base + q < p.PC)
+                recs[rec_base + q] = make_uint2((uint32_t)(k * 32 + i) | ((uint32_t)(y0 + j) << 16), nb | ((uint32_t)run << 8));
         }
     }
 }

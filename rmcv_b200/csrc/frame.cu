@@ -419,8 +419,8 @@ __global__ void __launch_bounds__(256, 3) label_kernel(const LabelParams p) {
     }
     __syncthreads();
     for (int c = tid; c < n_comps; c += NT) { g_comp_cnt[c] = g_comp_cnt[c] > 0; s_cnt[c] = 0; }  // has holes of its own
-    // ---- boundary-pixel records -> components: the run that owns a record is found by binary search in its row; the
-    // records are counted per component, start = exclusive scan of the counts, and a warp-aggregated scatter writes them
+    // ---- boundary-pixel records -> components (through the run each record is tagged with): the records are counted
+    // per component, start = exclusive scan of the counts, and a warp-aggregated scatter writes them
     // bucketed by component (so that the contour kernel streams each component's records linearly).
     const int raw_recs = fc.n_recs;
     const int n_recs = min(raw_recs, g.PC);
@@ -429,11 +429,9 @@ __global__ void __launch_bounds__(256, 3) label_kernel(const LabelParams p) {
     int32_t* g_start = sb.comp_start + (size_t)frame * (C + 1);
     if (tid == 0 && raw_recs > g.PC) s_flags |= RMCV_FRAME_OVERFLOW_POINTS;
     __syncthreads();
-    auto comp_of = [&](const uint2 rec) -> int {
-        const int x = (int)(rec.x & 0xffffu), y = (int)(rec.x >> 16);
-        const int2 rr = s_rows[y];
-        const int r = lower_bound_xe(f.run_x, rr.x, rr.y, x);  // the run that contains x
-        return r < rr.y ? (int)f.cid[r] : -1;
+    auto comp_of = [&](const uint2 rec) -> int {  // the emit kernel tagged the record with its run
+        const int r = (int)(rec.y >> 8);
+        return r < n_runs ? (int)f.cid[r] : -1;
     };
     for (int i0 = 0; i0 < n_recs; i0 += NT) {
         const int i = i0 + tid;
@@ -822,7 +820,13 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         done(RMCV_STAGE_FIT);
     }
-    {   // K_O
+    {   // K_O on its own stream: its write-out over PCIe stalls on store back-pressure while occupying almost no SM
+        // resources, so the next chunk's kernels need not queue behind it
+        cudaStream_t so = L.st_out ? L.st_out : st;
+        if (so != st) {
+            if ((e = cudaEventRecord(L.sb->ev_fit, st)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(so, L.sb->ev_fit, 0)) != cudaSuccess) return e;
+        }
         OrderParams p;
         p.g = L.g; p.sb = *L.sb; p.prm = prm; p.frame_base = L.frame_base;
         p.o_frames = L.o_frames; p.o_contours = L.o_contours; p.o_blobs = L.o_blobs; p.o_armours = L.o_armours;
@@ -832,10 +836,10 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
             e = cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        order_kernel<<<L.frames, 128, smem, st>>>(p);
+        order_kernel<<<L.frames, 128, smem, so>>>(p);
         if (launches) ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        done(RMCV_STAGE_ORDER);
+        if (stage_done) stage_done(stage_arg, RMCV_STAGE_ORDER, so);
     }
     return cudaSuccess;
 }

@@ -1,5 +1,2 @@
-run rs4096 A=1
-run rs3072 RMCV_FRAME_RS=3072
-run rs2048 RMCV_FRAME_RS=2048
-run rs3072serial RMCV_FRAME_RS=3072 RMCV_SERIAL=1
-run rs2048serial RMCV_FRAME_RS=2048 RMCV_SERIAL=1
+run base A=1
+run serial RMCV_SERIAL=1
