@@ -21,50 +21,100 @@ namespace rmcv {
 struct EmitParams {
     const uint32_t* bits;   // [frames][H][WB]
     int W, H, WB, BH, bands;
+    uint32_t inv_wb;        // floor(2^32 / WB) + 1: idx / WB == umulhi(idx, inv_wb) for idx < 2^20; 0 when WB == 1
     int2* rows; uint32_t* run_x; uint16_t* run_y; FrameCounters* counters; int R;
     uint2* recs; int PC;
 };
 
+// kVec: WB % 4 == 0 -> the band is loaded with 128-bit loads and the non-zero test rides on the load.
+template <bool kVec>
 __global__ void __launch_bounds__(128) emit_kernel(const EmitParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int s_wtot[32], s_base[2];
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
-    const int frame = blockIdx.x / p.bands, band = blockIdx.x - frame * p.bands;
+    __shared__ int s_wtot[4], s_base[2];
+    constexpr int NT = 128, nwarps = 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.y, band = blockIdx.x;
     const int H = p.H, WB = p.WB;
     const int y0 = band * p.BH;
     const int nout = min(p.BH, H - y0);
     const int nwords = nout * WB, cap = p.BH * WB;
+    auto row_of = [&](int idx) -> int { return p.inv_wb ? (int)__umulhi((uint32_t)idx, p.inv_wb) : idx; };  // idx / WB
     long long* scratch = reinterpret_cast<long long*>(smem);        // 34 long longs of scan scratch
     int* erun = reinterpret_cast<int*>(scratch + 36);                // [cap + 1] runs before entry e (exclusive prefix)
     int* erec = erun + cap + 1;                                      // [cap + 1] records before entry e
-    uint32_t* mm = reinterpret_cast<uint32_t*>(erec + cap + 1);      // [(BH+2)][WB] rows y0-1 .. y0+nout
+    uint32_t* mm = reinterpret_cast<uint32_t*>(erec + cap + 1 + ((2 * (cap + 1)) & 3 ? 4 - ((2 * (cap + 1)) & 3) : 0));
+                                                                     // [(BH+2)][WB] rows y0-1 .. y0+nout, 16-byte aligned
     uint32_t* m = mm + WB;                                           // row 0 of m <-> image row y0
     uint16_t* list = reinterpret_cast<uint16_t*>(mm + (size_t)(p.BH + 2) * WB);  // [cap] non-zero words, raster order
     const uint32_t* gb = p.bits + (size_t)frame * H * WB;
-    {   // rows y0-1 .. y0+nout are contiguous in the bit mask; rows outside the image read as background
-        const int lo_i = y0 > 0 ? 0 : WB, hi_i = y0 + nout < H ? (nout + 2) * WB : (nout + 1) * WB;
-        const long long off = ((long long)y0 - 1) * WB;
-        for (int i = tid; i < (nout + 2) * WB; i += NT) mm[i] = (i >= lo_i && i < hi_i) ? __ldg(gb + (off + i)) : 0u;
-    }
-    __syncthreads();
-    // ---- the non-zero words of the band, in raster order (foreground is sparse: everything below works on this list)
-    const int chunk = ((nwords + nwarps - 1) / nwarps + 31) & ~31;   // words per warp, whole ballots
-    const int c0 = min(nwords, warp * chunk), c1 = min(nwords, c0 + chunk);
-    int mine = 0;
-    for (int i = c0; i < c1; i += 32) {
-        const int idx = i + lane;
-        mine += __popc(__ballot_sync(0xffffffffu, idx < c1 && m[idx] != 0u));
-    }
-    if (lane == 0) s_wtot[warp] = mine;
-    __syncthreads();
+    // rows y0-1 .. y0+nout are contiguous in the bit mask; rows outside the image read as background
+    const int lo_i = y0 > 0 ? 0 : WB, hi_i = y0 + nout < H ? (nout + 2) * WB : (nout + 1) * WB;
+    const long long off = ((long long)y0 - 1) * WB;
     int pos = 0, n_ent = 0;
-    for (int w = 0; w < nwarps; ++w) { if (w < warp) pos += s_wtot[w]; n_ent += s_wtot[w]; }
-    for (int i = c0; i < c1; i += 32) {
-        const int idx = i + lane;
-        const bool nz = idx < c1 && m[idx] != 0u;
-        const unsigned bal = __ballot_sync(0xffffffffu, nz);
-        if (nz) list[pos + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)idx;
-        pos += __popc(bal);
+    if (kVec) {
+        // ---- load + the non-zero words of the band in raster order (foreground is sparse: everything below works on
+        // this list).  A warp owns a contiguous range of 16-byte groups; the non-zero nibbles stay in a register
+        // between the counting round and the writing round.
+        const uint4* src = reinterpret_cast<const uint4*>(gb + off);
+        uint4* dst = reinterpret_cast<uint4*>(mm);
+        const int nq = ((nout + 2) * WB) >> 2, lo_q = lo_i >> 2, hi_q = hi_i >> 2;
+        const int own_lo = WB >> 2, own_hi = ((nout + 1) * WB) >> 2;
+        const int per_w = (((nq + nwarps - 1) >> 2) + 31) & ~31;      // at most 256: eight rounds of nibbles
+        const int q0 = min(nq, warp * per_w), q1 = min(nq, q0 + per_w);
+        uint32_t nibs = 0;
+        int mine = 0, it = 0;
+        for (int i = q0 + lane; i < q1; i += 32, ++it) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (i >= lo_q && i < hi_q) v = __ldg(src + i);
+            dst[i] = v;
+            if (i >= own_lo && i < own_hi) {
+                const uint32_t nib = (v.x != 0u) | ((v.y != 0u) << 1) | ((v.z != 0u) << 2) | ((v.w != 0u) << 3);
+                nibs |= nib << (4 * it);
+                mine += __popc(nib);
+            }
+        }
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if (lane == 0) s_wtot[warp] = mine;
+        __syncthreads();
+        for (int w = 0; w < nwarps; ++w) { if (w < warp) pos += s_wtot[w]; n_ent += s_wtot[w]; }
+        it = 0;
+        for (int i0 = q0; i0 < q1; i0 += 32, ++it) {
+            uint32_t nib = (nibs >> (4 * it)) & 15u;
+            const int c = __popc(nib);
+            int incl = c;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            int at = pos + incl - c;
+            const int wbase = ((i0 + lane) << 2) - WB;   // word index relative to the band's first own row
+            while (nib) {
+                const int b = __ffs(nib) - 1;
+                nib &= nib - 1;
+                list[at++] = (uint16_t)(wbase + b);
+            }
+            pos += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    } else {
+        for (int i = tid; i < (nout + 2) * WB; i += NT) mm[i] = (i >= lo_i && i < hi_i) ? __ldg(gb + (off + i)) : 0u;
+        __syncthreads();
+        const int chunk = (((nwords + nwarps - 1) >> 2) + 31) & ~31;  // words per warp, whole ballots
+        const int c0 = min(nwords, warp * chunk), c1 = min(nwords, c0 + chunk);
+        int mine = 0;
+        for (int i = c0; i < c1; i += 32) {
+            const int idx = i + lane;
+            mine += __popc(__ballot_sync(0xffffffffu, idx < c1 && m[idx] != 0u));
+        }
+        if (lane == 0) s_wtot[warp] = mine;
+        __syncthreads();
+        for (int w = 0; w < nwarps; ++w) { if (w < warp) pos += s_wtot[w]; n_ent += s_wtot[w]; }
+        for (int i = c0; i < c1; i += 32) {
+            const int idx = i + lane;
+            const bool nz = idx < c1 && m[idx] != 0u;
+            const unsigned bal = __ballot_sync(0xffffffffu, nz);
+            if (nz) list[pos + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)idx;
+            pos += __popc(bal);
+        }
     }
     __syncthreads();
     auto boundary_word = [&](int idx, int k) -> uint32_t {
@@ -80,7 +130,7 @@ __global__ void __launch_bounds__(128) emit_kernel(const EmitParams p) {
         const int e = e0 + tid;
         long long v = 0;
         if (e < n_ent) {
-            const int idx = list[e], k = idx % WB;
+            const int idx = list[e], k = idx - row_of(idx) * WB;
             const uint32_t w = m[idx];
             const uint32_t prev = k > 0 ? (m[idx - 1] >> 31) : 0u;
             v = (long long)__popc(w & ~((w << 1) | prev)) | ((long long)__popc(boundary_word(idx, k)) << 32);
@@ -120,7 +170,7 @@ __global__ void __launch_bounds__(128) emit_kernel(const EmitParams p) {
         uint16_t* run_x16 = reinterpret_cast<uint16_t*>(p.run_x + (size_t)frame * R);
         uint16_t* run_y = p.run_y + (size_t)frame * R;
         for (int e = tid; e < n_ent; e += NT) {
-            const int idx = list[e], j = idx / WB, k = idx - j * WB;
+            const int idx = list[e], j = row_of(idx), k = idx - j * WB;
             const uint32_t w = m[idx];
             const uint32_t prev = k > 0 ? (m[idx - 1] >> 31) : 0u;
             const uint32_t next = k + 1 < WB ? (m[idx + 1] & 1u) : 0u;
@@ -152,7 +202,7 @@ __global__ void __launch_bounds__(128) emit_kernel(const EmitParams p) {
                 const int mid = (lo + hi) >> 1;
                 if (erec[mid] <= q) lo = mid; else hi = mid;
             }
-            const int idx = list[lo], j = idx / WB, k = idx - j * WB;
+            const int idx = list[lo], j = row_of(idx), k = idx - j * WB;
             uint32_t b = boundary_word(idx, k);
             for (int skip = q - erec[lo]; skip > 0; --skip) b &= b - 1;
             const int i = __ffs(b) - 1;
@@ -187,15 +237,19 @@ cudaError_t launch_emit(const EmitLaunch& L, cudaStream_t st, int64_t* launches)
     if (BH < 1) BH = 1;
     if (BH > L.H) BH = L.H;
     p.BH = BH; p.bands = (L.H + BH - 1) / BH;
-    const long long grid = (long long)L.batch * p.bands;
-    if (grid <= 0 || grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+    p.inv_wb = p.WB > 1 ? (uint32_t)((1ull << 32) / (unsigned)p.WB) + 1u : 0u;   // 0: WB == 1
+    if (L.batch <= 0 || L.batch > 65535) return cudaErrorInvalidValue;
     const size_t cap = (size_t)BH * p.WB;
-    const size_t smem = 36 * 8 + 2 * (cap + 1) * 4 + (size_t)(BH + 2) * p.WB * 4 + cap * 2 + 16;
+    const size_t smem = 36 * 8 + 2 * (cap + 1) * 4 + 16 + (size_t)(BH + 2) * p.WB * 4 + cap * 2 + 16;
+    const bool vec = (p.WB & 3) == 0;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = vec ? cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    emit_kernel<<<(unsigned)grid, 128, smem, st>>>(p);
+    dim3 grid(p.bands, L.batch);
+    if (vec) emit_kernel<true><<<grid, 128, smem, st>>>(p);
+    else emit_kernel<false><<<grid, 128, smem, st>>>(p);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
