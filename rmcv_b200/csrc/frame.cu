@@ -122,12 +122,15 @@ __device__ __forceinline__ void pointer_jump(int32_t* link, int first, int end, 
     volatile int32_t* v = link;
     while (true) {
         int changed = 0;
-        for (int r = first + tid; r < end; r += NT) {
-            const int l = v[r];
-            if (l != r) {
-                const int ll = v[l];
-                if (ll != l) { v[r] = ll; changed = 1; }
-            }
+        for (int r0 = first + tid; r0 < end; r0 += 4 * NT) {   // four independent chains per iteration (latency-bound)
+            int l[4], ll[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int r = r0 + u * NT; l[u] = r < end ? v[r] : -1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ll[u] = l[u] >= 0 ? v[l[u]] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (ll[u] != l[u]) { v[r0 + u * NT] = ll[u]; changed = 1; }
         }
         if (!__syncthreads_or(changed)) break;
     }
@@ -233,7 +236,7 @@ __host__ __device__ inline size_t label_smem_bytes(int H, int Rs, int C) {
 __global__ void __launch_bounds__(256, 3) label_kernel(const LabelParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int sh_scan[33];
-    __shared__ int s_ncomp, s_nadj, s_flags;
+    __shared__ int s_ncomp, s_nadj, s_flags, s_hb[4];
     const Geometry& g = p.g;
     const int W = g.W, H = g.H, R = g.R, C = g.C, Rs = p.Rs;
     const int frame = blockIdx.x;
@@ -358,14 +361,28 @@ __global__ void __launch_bounds__(256, 3) label_kernel(const LabelParams p) {
     __syncthreads();
     // ---- background gaps (4-connectivity), only when the frame has a hole
     if (has_holes) {
+        // A hole lies strictly inside the bounding box of the component that encloses it, so a gap that is not strictly
+        // inside the union of the bounding boxes of the components with holes is outer background without any search.
+        if (tid == 0) { s_hb[0] = INT32_MAX; s_hb[1] = INT32_MAX; s_hb[2] = -1; s_hb[3] = -1; f.glink[0] = 0; }
         for (int i = tid; i < (2 * (n_runs + 2) + 3) / 4; i += NT) reinterpret_cast<uint32_t*>(f.jp)[i] = 0u;
-        if (tid == 0) f.glink[0] = 0;
+        for (int c = tid; c < n_comps; c += NT) s_cnt[c] = g_comp_cnt[c];
         __syncthreads();
+        for (int r = tid; r < n_runs; r += NT) {
+            const int c = f.cid[r];
+            if (c >= 0 && s_cnt[c] > 0) {
+                const uint32_t rx = f.run_x[r];
+                atomicMin(&s_hb[0], (int)(rx & 0xffffu)); atomicMax(&s_hb[2], (int)(rx >> 16));
+                atomicMin(&s_hb[1], (int)f.run_y[r]); atomicMax(&s_hb[3], (int)f.run_y[r]);
+            }
+        }
+        __syncthreads();
+        const int hx0 = s_hb[0], hy0 = s_hb[1], hx1 = s_hb[2], hy1 = s_hb[3];
         for (int r = tid; r < n_runs; r += NT) {
             const int y = f.run_y[r];
             const int2 rr = s_rows[y];
-            if (r == rr.x || y == 0 || y == H - 1) { f.glink[r + 1] = 0; continue; }  // the gap touches the image border
+            if (r == rr.x || y <= hy0 || y >= hy1) { f.glink[r + 1] = 0; continue; }  // border gap, or outside the box
             const int a = (int)(f.run_x[r - 1] >> 16) + 1, b = (int)(f.run_x[r] & 0xffffu) - 1;
+            if (a <= hx0 || b >= hx1) { f.glink[r + 1] = 0; continue; }
             bool outer = false;
             int first = -1;
             {   // row above: every overlapped gap is connected to this one (and so to each other)
@@ -433,11 +450,16 @@ __global__ void __launch_bounds__(256, 3) label_kernel(const LabelParams p) {
         const int r = (int)(rec.y >> 8);
         return r < n_runs ? (int)f.cid[r] : -1;
     };
-    for (int i0 = 0; i0 < n_recs; i0 += NT) {
-        const int i = i0 + tid;
-        const int c = i < n_recs ? comp_of(recs[i]) : -1;
-        const unsigned peers = __match_any_sync(0xffffffffu, c);
-        if (c >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[c], __popc(peers));
+    for (int i0 = 0; i0 < n_recs; i0 += 4 * NT) {   // four loads in flight per thread
+        uint2 rec[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int i = i0 + u * NT + tid; rec[u] = i < n_recs ? recs[i] : make_uint2(0u, 0xffffff00u); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = comp_of(rec[u]);
+            const unsigned peers = __match_any_sync(0xffffffffu, c);
+            if (c >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[c], __popc(peers));
+        }
     }
     __syncthreads();
     {
@@ -453,17 +475,20 @@ __global__ void __launch_bounds__(256, 3) label_kernel(const LabelParams p) {
         if (tid == 0) g_start[n_comps] = carry;
     }
     __syncthreads();
-    for (int i0 = 0; i0 < n_recs; i0 += NT) {
-        const int i = i0 + tid;
-        uint2 rec = make_uint2(0u, 0u);
-        int c = -1;
-        if (i < n_recs) { rec = recs[i]; c = comp_of(rec); }
-        const unsigned peers = __match_any_sync(0xffffffffu, c);
-        int base = 0;
-        const int leader = __ffs(peers) - 1;
-        if (c >= 0 && lane == leader) base = atomicAdd(&s_cnt[c], __popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (c >= 0) recs2[s_start[c] + base + __popc(peers & ((1u << lane) - 1u))] = rec;
+    for (int i0 = 0; i0 < n_recs; i0 += 4 * NT) {
+        uint2 rec[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int i = i0 + u * NT + tid; rec[u] = i < n_recs ? recs[i] : make_uint2(0u, 0xffffff00u); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = comp_of(rec[u]);
+            const unsigned peers = __match_any_sync(0xffffffffu, c);
+            int base = 0;
+            const int leader = __ffs(peers) - 1;
+            if (c >= 0 && lane == leader) base = atomicAdd(&s_cnt[c], __popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (c >= 0) recs2[s_start[c] + base + __popc(peers & ((1u << lane) - 1u))] = rec[u];
+        }
     }
     if (tid == 0) { fc.n_comps = n_comps; fc.n_holes = n_holes; fc.flags = s_flags; }
 }
