@@ -18,7 +18,21 @@ struct ProfSet {      // events of one chunk: pixel begin/end on the pixel strea
     bool rec, full;
 };
 
+struct ResultSet {  // pinned, device-mapped result arrays of one detect call (two sets: two calls may be in flight)
+    rmcv_frame_info* frames = nullptr;      // [max_batch]
+    rmcv_contour_info* contours = nullptr;  // [max_batch][C]  (chunk-dense)
+    rmcv_lightblob* blobs = nullptr;        // [max_batch][C]
+    rmcv_armour* armours = nullptr;         // [max_batch][A]
+    int batch = 0;
+    bool pending = false;                   // enqueued, not fetched yet
+    long long call_id = -1;
+    cudaEvent_t done[2] = {nullptr, nullptr};  // recorded on the write-out stream and on the pixel stream
+};
+
 struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
+    ResultSet rs[2];
+    long long n_calls = 0;
+    int last_fetched = -1;
     std::vector<ProfSet> prof;
     size_t prof_used = 0;
     std::vector<void*> dev_allocs, host_allocs;
@@ -189,6 +203,23 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
     return RMCV_OK;
 }
 
+// A detect call writes into result set (call number & 1); the previous call's set stays readable, so the host can fetch
+// call n while call n+1 is already running (rmcv_fetch_results returns the oldest unfetched call).
+void begin_call(rmcv_ctx* ctx) {
+    CtxExtra* ex = extra(ctx);
+    ResultSet& r = ex->rs[ex->n_calls & 1];
+    r.pending = false;  // an unfetched call two calls back is dropped
+    ctx->h_frames = r.frames; ctx->h_contours = r.contours; ctx->h_blobs = r.blobs; ctx->h_armours = r.armours;
+}
+int end_call(rmcv_ctx* ctx, int batch) {
+    CtxExtra* ex = extra(ctx);
+    ResultSet& r = ex->rs[ex->n_calls & 1];
+    RMCV_CUDA(ctx, cudaEventRecord(r.done[0], ex->out));
+    RMCV_CUDA(ctx, cudaEventRecord(r.done[1], ex->pix));
+    r.batch = batch; r.pending = true; r.call_id = ex->n_calls++;
+    return RMCV_OK;
+}
+
 int run_device_batch(rmcv_ctx* ctx, const uint8_t* d_src, size_t pitch, size_t frame_stride, int W, int H, int batch,
                      int bayer_layout, const rmcv_params& prm, uint8_t* d_mask, size_t mask_pitch, size_t mask_frame_stride,
                      bool full) {
@@ -199,6 +230,7 @@ int run_device_batch(rmcv_ctx* ctx, const uint8_t* d_src, size_t pitch, size_t f
     if (pitch < rowbytes) return set_err(ctx, RMCV_ERR_INVALID_ARG, "pitch smaller than a row");
     if (d_mask && mask_pitch < (size_t)W) return set_err(ctx, RMCV_ERR_INVALID_ARG, "mask pitch smaller than a row");
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (full) begin_call(ctx);
     const int CF = ctx->CF;
     int nchunks = 0;
     for (int f0 = 0; f0 < batch; f0 += CF, ++nchunks) {
@@ -212,6 +244,7 @@ int run_device_batch(rmcv_ctx* ctx, const uint8_t* d_src, size_t pitch, size_t f
     ctx->have_results = full;
     extra(ctx)->last_nchunks = nchunks;
     extra(ctx)->last_kind = full ? 2 : 1;
+    if (full) return end_call(ctx, batch);
     return RMCV_OK;
 }
 
@@ -227,21 +260,39 @@ int sync_all(rmcv_ctx* ctx) {
     return RMCV_OK;
 }
 
-int fill_results(rmcv_ctx* ctx, rmcv_results* out) {
-    if (!ctx->have_results) return set_err(ctx, RMCV_ERR_STATE, "no detect call to fetch results from");
+int fill_results(rmcv_ctx* ctx, const ResultSet& r, rmcv_results* out) {
     int flags = 0;
     long long tc = 0, tb = 0, ta = 0;
-    for (int f = 0; f < ctx->last_batch; ++f) {
-        const rmcv_frame_info& fi = ctx->h_frames[f];
+    for (int f = 0; f < r.batch; ++f) {
+        const rmcv_frame_info& fi = r.frames[f];
         flags |= fi.flags; tc += fi.n_contours; tb += fi.n_positive; ta += fi.n_armours;
     }
     if (out) {
-        out->batch = ctx->last_batch;
+        out->batch = r.batch;
         out->total_contours = (int32_t)tc; out->total_blobs = (int32_t)tb; out->total_armours = (int32_t)ta;
-        out->frames = ctx->h_frames; out->contours = ctx->h_contours; out->blobs = ctx->h_blobs; out->armours = ctx->h_armours;
+        out->frames = r.frames; out->contours = r.contours; out->blobs = r.blobs; out->armours = r.armours;
     }
     if (flags) return set_err(ctx, RMCV_ERR_CAPACITY, "a per-frame capacity overflowed; see rmcv_frame_info.flags");
     return RMCV_OK;
+}
+
+// Waits for the oldest unfetched detect call (or re-exposes the last fetched one) and fills `out`.
+int fetch_oldest(rmcv_ctx* ctx, rmcv_results* out) {
+    CtxExtra* ex = extra(ctx);
+    int pick = -1;
+    for (int i = 0; i < 2; ++i)
+        if (ex->rs[i].pending && (pick < 0 || ex->rs[i].call_id < ex->rs[pick].call_id)) pick = i;
+    if (pick < 0) {
+        if (ex->last_fetched < 0) return set_err(ctx, RMCV_ERR_STATE, "no detect call to fetch results from");
+        return fill_results(ctx, ex->rs[ex->last_fetched], out);
+    }
+    ResultSet& r = ex->rs[pick];
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    RMCV_CUDA(ctx, cudaEventSynchronize(r.done[0]));
+    RMCV_CUDA(ctx, cudaEventSynchronize(r.done[1]));
+    r.pending = false;
+    ex->last_fetched = pick;
+    return fill_results(ctx, r, out);
 }
 
 // slot and local index of frame f of the last call, or null when its scratch has been recycled
@@ -365,15 +416,22 @@ int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
     if (rc != RMCV_OK) return fail(rc);
     const size_t B = cfg->max_batch;
     const unsigned hflags = cudaHostAllocMapped | cudaHostAllocPortable;
-    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_frames), B * sizeof(rmcv_frame_info), hflags);
-    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_contours), B * g.C * sizeof(rmcv_contour_info), hflags);
-    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_blobs), B * g.C * sizeof(rmcv_lightblob), hflags);
-    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_armours), B * g.A * sizeof(rmcv_armour), hflags);
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        ResultSet& r = extra(ctx)->rs[i];
+        e = cudaHostAlloc(reinterpret_cast<void**>(&r.frames), B * sizeof(rmcv_frame_info), hflags);
+        if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&r.contours), B * g.C * sizeof(rmcv_contour_info), hflags);
+        if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&r.blobs), B * g.C * sizeof(rmcv_lightblob), hflags);
+        if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&r.armours), B * g.A * sizeof(rmcv_armour), hflags);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.done[0], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.done[1], cudaEventDisableTiming);
+        if (e == cudaSuccess) memset(r.frames, 0, B * sizeof(rmcv_frame_info));
+    }
     if (e != cudaSuccess) {
         snprintf(ctx->err, sizeof(ctx->err), "pinned result allocation failed: %s", cudaGetErrorString(e));
         return fail(RMCV_ERR_CUDA);
     }
-    memset(ctx->h_frames, 0, B * sizeof(rmcv_frame_info));
+    begin_call(ctx);
     upload_luts();
     if (cudaDeviceSynchronize() != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "device sync after init failed"); return fail(RMCV_ERR_CUDA); }
     *out = ctx;
@@ -386,12 +444,16 @@ int rmcv_ctx_destroy(rmcv_ctx* ctx) {
     cudaDeviceSynchronize();
     free_slot(ctx->slot[0]);
     free_slot(ctx->slot[1]);
-    if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
-    if (ctx->h_contours) cudaFreeHost(ctx->h_contours);
-    if (ctx->h_blobs) cudaFreeHost(ctx->h_blobs);
-    if (ctx->h_armours) cudaFreeHost(ctx->h_armours);
     CtxExtra* ex = extra(ctx);
     if (ex) {
+        for (int i = 0; i < 2; ++i) {
+            ResultSet& r = ex->rs[i];
+            if (r.frames) cudaFreeHost(r.frames);
+            if (r.contours) cudaFreeHost(r.contours);
+            if (r.blobs) cudaFreeHost(r.blobs);
+            if (r.armours) cudaFreeHost(r.armours);
+            for (int k = 0; k < 2; ++k) if (r.done[k]) cudaEventDestroy(r.done[k]);
+        }
         for (auto& ps : ex->prof) {
             for (int i = 0; i < 2; ++i) cudaEventDestroy(ps.pix[i]);
             for (int i = 0; i < RMCV_STAGE_COUNT; ++i) cudaEventDestroy(ps.lab[i]);
@@ -515,6 +577,7 @@ int rmcv_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, si
     const size_t rowbytes = (size_t)width * 3;
     if (pitch < rowbytes) return set_err(ctx, RMCV_ERR_INVALID_ARG, "pitch smaller than a row");
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    begin_call(ctx);
     const int CF = ctx->CF;
     const size_t dev_frame = (size_t)height * rowbytes, dev_mask = (size_t)height * width;
     int nchunks = 0;
@@ -567,16 +630,19 @@ int rmcv_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, si
     ctx->have_results = true;
     extra(ctx)->last_nchunks = nchunks;
     extra(ctx)->last_kind = 2;
+    const int set = (int)(extra(ctx)->n_calls & 1);
+    rc = end_call(ctx, batch);
+    if (rc != RMCV_OK) return rc;
     rc = sync_all(ctx);
     if (rc != RMCV_OK) return rc;
-    return fill_results(ctx, out);
+    extra(ctx)->rs[set].pending = false;
+    extra(ctx)->last_fetched = set;
+    return fill_results(ctx, extra(ctx)->rs[set], out);
 }
 
 int rmcv_fetch_results(rmcv_ctx* ctx, rmcv_results* out) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
-    int rc = sync_all(ctx);
-    if (rc != RMCV_OK) return rc;
-    return fill_results(ctx, out);
+    return fetch_oldest(ctx, out);
 }
 
 int rmcv_get_contour(rmcv_ctx* ctx, int frame, int contour_index, int32_t* xy, int cap, int* n_points) {
@@ -784,6 +850,8 @@ int rmcv_profile_enable(rmcv_ctx* ctx, int on) {
 
 int rmcv_profile_read(rmcv_ctx* ctx, double ms[RMCV_STAGE_COUNT], int64_t launches[RMCV_STAGE_COUNT], int reset) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
+    const int rc0 = sync_all(ctx);  // collects the stage events of every finished call
+    if (rc0 != RMCV_OK) return rc0;
     for (int s = 0; s < RMCV_STAGE_COUNT; ++s) {
         if (ms) ms[s] = ctx->prof_ms[s];
         if (launches) launches[s] = ctx->prof_launches[s];

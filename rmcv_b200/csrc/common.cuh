@@ -104,7 +104,7 @@ struct rmcv_ctx {
     int CF;                 // chunk frames
     rmcv::Geometry cap;     // capacities at max_width x max_height
     rmcv::SlotBuffers slot[2];
-    // pinned, device-mapped result arrays for a whole batch
+    // pinned, device-mapped result arrays of the most recent detect call (one of the two sets kept in api.cu)
     rmcv_frame_info* h_frames;      // [max_batch]
     rmcv_contour_info* h_contours;  // [max_batch][C]  (chunk-dense)
     rmcv_lightblob* h_blobs;        // [max_batch][C]
