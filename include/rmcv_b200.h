@@ -14,9 +14,12 @@
  * exceptions, no OpenCV and no torch types.  include/rmcv_gpu/rm_shim.hpp rebuilds the rm::
  * signatures on top of it; INTEGRATION.md shows the reference-side wiring.
  *
- * Threading: one rmcv_ctx per host thread and GPU.  All device work of a ctx is stream-ordered;
- * entry points documented "async" return before the GPU has finished — call rmcv_sync() (or a
- * fetch/host entry point, which syncs) before reading outputs.
+ * Threading: one rmcv_ctx per host thread and GPU.  All device work of a ctx is ordered on the
+ * ctx's own streams (pixel kernels, labelling kernels, write-out and staging copies each have
+ * one); entry points documented "async" return before the GPU has finished — call rmcv_sync()
+ * (or a fetch/host entry point, which waits) before reading outputs.  Up to two detect calls may
+ * be in flight: results are double-buffered and rmcv_fetch_results() returns the oldest
+ * unfetched call, so call n+1 can be enqueued before call n is fetched.
  *
  * There is no CPU fallback anywhere behind this ABI: without a CUDA device every entry point
  * that needs one returns RMCV_ERR_CUDA / RMCV_ERR_NO_DEVICE.
@@ -133,11 +136,12 @@ typedef struct rmcv_config {
     int32_t max_blobs_per_frame;   /* components per frame; 0 = default 1024                     */
     int32_t max_armours_per_frame; /* 0 = default 2048                                           */
     int32_t flags;                 /* reserved, 0                                                */
-    void* stream;                  /* cudaStream_t for slot 0, or NULL for ctx-owned streams     */
+    void* stream;                  /* cudaStream_t to run the pixel kernels on, or NULL           */
 } rmcv_config;
 
-/* View of the results of the last detect call.  Pointers are ctx-owned pinned host memory, valid
- * until the next detect call on the ctx.  Dense arrays are indexed through frames[f].*_offset. */
+/* View of the results of one detect call.  Pointers are ctx-owned pinned host memory, valid
+ * until the second next detect call on the ctx (two result sets alternate).  Dense arrays are
+ * indexed through frames[f].*_offset. */
 typedef struct rmcv_results {
     int32_t batch;
     int32_t total_contours, total_blobs, total_armours;
@@ -165,11 +169,11 @@ int rmcv_device_alloc(rmcv_ctx* ctx, size_t bytes, void** dptr);
 int rmcv_device_free(rmcv_ctx* ctx, void* dptr);
 int rmcv_host_alloc(rmcv_ctx* ctx, size_t bytes, void** hptr);   /* pinned */
 int rmcv_host_free(rmcv_ctx* ctx, void* hptr);
-int rmcv_memcpy_h2d(rmcv_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on slot 0 */
-int rmcv_memcpy_d2h(rmcv_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on slot 0 */
-int rmcv_memset_d(rmcv_ctx* ctx, void* dst, int value, size_t bytes);         /* async on slot 0 */
+int rmcv_memcpy_h2d(rmcv_ctx* ctx, void* dst, const void* src, size_t bytes); /* async, pixel stream */
+int rmcv_memcpy_d2h(rmcv_ctx* ctx, void* dst, const void* src, size_t bytes); /* async, pixel stream */
+int rmcv_memset_d(rmcv_ctx* ctx, void* dst, int value, size_t bytes);         /* async, pixel stream */
 int rmcv_sync(rmcv_ctx* ctx);                                                 /* all ctx streams */
-void* rmcv_stream(rmcv_ctx* ctx);                                             /* slot-0 cudaStream_t */
+void* rmcv_stream(rmcv_ctx* ctx);                                             /* the pixel-kernel cudaStream_t */
 
 /* ---- a1: pixel stage of rm::extract_color (src/imgproc.cpp:52-69) --------------------------- */
 /* BGR interleaved u8 frames -> binary mask {0,255}.  Device pointers, async.
@@ -204,10 +208,13 @@ int rmcv_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, si
                            uint8_t* h_mask, size_t mask_pitch, size_t mask_frame_stride,
                            rmcv_results* out);
 
-/* Waits for the last detect call and exposes its results. */
+/* Waits for the oldest detect call whose results have not been fetched yet and exposes them
+ * (with one call in flight: the last call).  Without an unfetched call it re-exposes the
+ * results fetched last.  An unfetched call is dropped when a third call is enqueued. */
 int rmcv_fetch_results(rmcv_ctx* ctx, rmcv_results* out);
 
-/* Ordered contour of external contour `contour_index` of frame `frame` of the last detect call
+/* The on-demand getters below refer to the MOST RECENT detect call and wait for it.
+ * Ordered contour of external contour `contour_index` of frame `frame` of the last detect call
  * (Suzuki border following, identical point sequence to cv::findContours).  xy receives up to
  * `cap` (x,y) pairs; *n_points receives the full length.  Host pointer, synchronous. */
 int rmcv_get_contour(rmcv_ctx* ctx, int frame, int contour_index, int32_t* xy, int cap, int* n_points);
@@ -242,7 +249,7 @@ int rmcv_filter_armours(rmcv_ctx* ctx, const rmcv_lightblob* blobs, int n_blobs,
 int rmcv_make_lightblobs(rmcv_ctx* ctx, const rmcv_rotated_rect* boxes, int n, int target, rmcv_lightblob* out);
 
 /* ---- instrumentation ------------------------------------------------------------------------ */
-/* CUDA-event timing of the stages of detect/extract calls (on the stream that runs them). */
+/* CUDA-event timing of the stages of detect/extract calls (on the streams that run them). */
 enum {
     RMCV_STAGE_PIXEL = 0,   /* fused diff/threshold/close kernel -> byte mask + bit mask                       */
     RMCV_STAGE_EMIT = 1,    /* runs + boundary-pixel records from the bit mask                                 */
