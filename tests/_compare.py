@@ -7,7 +7,10 @@ Carve-outs (counted, returned in the report):
   * `rng_band`: contours whose first direct-fit |det M| lies in [0.7e-10, 1e-10*(1+1e-6)]: cv::fitEllipseDirect
     itself is non-deterministic there (jittered retry from the global RNG) -> loose tolerance
     0.5 px / 0.5 % / 0.1 deg and no exact gate membership;
-  * `near_gate`: contours / pairs whose gate quantity is within tolerance of its threshold.
+  * `near_gate`: contours / pairs whose gate quantity is within tolerance of its threshold;
+  * `degenerate`: contours whose oracle ellipse is thinner than 2 px (or not finite): the contour points lie on two
+    parallel lines, the conic through them is a line pair, cv::fitEllipse's least-squares systems are singular and its
+    answer is rounding noise (SURVEY A.6 "degenerate input warning") -> geometry and verdict not compared.
 """
 from __future__ import annotations
 
@@ -36,6 +39,7 @@ class Report:
     fallback: int = 0
     rng_band: int = 0
     near_gate: int = 0
+    degenerate: int = 0
     blobs: int = 0
     armours: int = 0
     worst_centre: float = 0.0
@@ -45,7 +49,7 @@ class Report:
     notes: list = field(default_factory=list)
 
     def merge(self, o: "Report"):
-        for k in ("frames", "contours", "fitted", "direct", "fallback", "rng_band", "near_gate", "blobs", "armours"):
+        for k in ("frames", "contours", "fitted", "direct", "fallback", "rng_band", "near_gate", "degenerate", "blobs", "armours"):
             setattr(self, k, getattr(self, k) + getattr(o, k))
         for k in ("worst_centre", "worst_axis_rel", "worst_angle", "worst_vertex"):
             setattr(self, k, max(getattr(self, k), getattr(o, k)))
@@ -99,6 +103,14 @@ def compare_frame(det, ref: O.FrameResult, params, where="") -> Report:
             rep.fallback += 1
         e = v.ellipse
         cx, cy, ew, eh, ea = c.ellipse
+        if not (math.isfinite(e.w) and math.isfinite(e.h) and math.isfinite(e.cx) and math.isfinite(e.cy)) or e.w < 2.0:
+            rep.degenerate += 1
+            if c.status != v.status:
+                flips += 1
+            if v.status == O.STATUS_POSITIVE:
+                loose_blob[pos_idx] = True
+                pos_idx += 1
+            continue
         dc = max(abs(cx - e.cx), abs(cy - e.cy))
         ds = max(abs(ew - e.w) / max(e.w, 1e-9), abs(eh - e.h) / max(e.h, 1e-9))
         da = angle_diff(ea, e.angle) if e.h / max(e.w, 1e-9) >= 1 + 1e-4 else 0.0
