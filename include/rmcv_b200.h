@@ -248,6 +248,30 @@ int rmcv_filter_armours(rmcv_ctx* ctx, const rmcv_lightblob* blobs, int n_blobs,
 /* a3 standalone: rm::lightblob ctor from a RotatedRect (src/core.cpp:9-19) */
 int rmcv_make_lightblobs(rmcv_ctx* ctx, const rmcv_rotated_rect* boxes, int n, int target, rmcv_lightblob* out);
 
+/* ---- a6 / a7 legacy rows, standalone ---------------------------------------------------------- */
+/* rm::MatchLightBlob (src/objdetect.cpp:9-28) on every caller-supplied contour: size/area gate, cv::fitEllipseDirect,
+ * box = the ellipse (fit_ellipse != 0) or cv::minAreaRect, ratio gate on the box, tilt gate on the ellipse.
+ * matched[k] = 1/0, boxes[k] = lightBlobBox (valid where matched).  Host pointers, synchronous. */
+int rmcv_match_lightblobs(rmcv_ctx* ctx, const int32_t* xy, const int32_t* offsets, int n_contours,
+                          float min_ratio, float max_ratio, float tilt_angle, float min_area, float max_area,
+                          int fit_ellipse, int32_t* matched, rmcv_rotated_rect* boxes);
+
+/* rm::FindLightBlobs (src/objdetect.cpp:30-53): MatchLightBlob + the camp vote from the mean colour of the contour's
+ * bounding rect in the 3-channel source image (G > B && G > R: guide light; else B > R ? blue : red) + the rm::lightblob
+ * ctor.  blobs receives the matches in input order (up to blob_cap); *n_blobs the full count. */
+int rmcv_find_lightblobs_legacy(rmcv_ctx* ctx, const int32_t* xy, const int32_t* offsets, int n_contours,
+                                float min_ratio, float max_ratio, float tilt_angle, float min_area, float max_area,
+                                const uint8_t* h_source_bgr, size_t pitch, int width, int height, int fit_ellipse,
+                                rmcv_lightblob* blobs, int blob_cap, int* n_blobs);
+
+/* cv::minAreaRect of every contour (convex hull + minimum-area enclosing rectangle; OpenCV 4.13 convention:
+ * angle in [-90, 0), width = extent along that direction).  Used by MatchLightBlob(fitEllipse = false). */
+int rmcv_min_area_rects(rmcv_ctx* ctx, const int32_t* xy, const int32_t* offsets, int n_contours, rmcv_rotated_rect* boxes);
+
+/* rm::LightBlobOverlap (src/objdetect.cpp:89-112).  *overlap = 1/0.  The reference's bound check admits
+ * right == n (one past the end, undefined behaviour in C++); here right >= n yields 0. */
+int rmcv_lightblob_overlap(rmcv_ctx* ctx, const rmcv_lightblob* blobs, int n_blobs, int left, int right, int* overlap);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* CUDA-event timing of the stages of detect/extract calls (on the streams that run them). */
 enum {

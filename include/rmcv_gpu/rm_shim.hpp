@@ -284,6 +284,80 @@ inline std::vector<armour> filter_armours(std::vector<lightblob>& lightblobs, co
     return armours;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Legacy functions (include/objdetect.h:22-37,62; src/objdetect.cpp:9-53,89-112), same signatures.
+namespace gpu {
+inline void pack_contours(const std::vector<contour>& contours, std::vector<int32_t>& xy, std::vector<int32_t>& off) {
+    off.assign(contours.size() + 1, 0);
+    for (size_t k = 0; k < contours.size(); ++k) off[k + 1] = off[k] + (int32_t)contours[k].size();
+    xy.resize((size_t)off.back() * 2 + 2);
+    for (size_t k = 0; k < contours.size(); ++k)
+        for (size_t i = 0; i < contours[k].size(); ++i) { xy[2 * (off[k] + i)] = contours[k][i].x; xy[2 * (off[k] + i) + 1] = contours[k][i].y; }
+}
+inline cv::RotatedRect to_rotated_rect(const rmcv_rotated_rect& b) {
+#if defined(RMCV_SHIM_WITH_REFERENCE)
+    return cv::RotatedRect(cv::Point2f(b.cx, b.cy), cv::Size2f(b.w, b.h), b.angle);
+#else
+    cv::RotatedRect r; r.center.x = b.cx; r.center.y = b.cy; r.size.width = b.w; r.size.height = b.h; r.angle = b.angle;
+    return r;
+#endif
+}
+}  // namespace gpu
+
+inline bool MatchLightBlob(const contour& c, float minRatio, float maxRatio, float tiltAngle, float minArea, float maxArea,
+                           cv::RotatedRect& lightBlobBox, bool fitEllipse = true) {
+    gpu::context& gc = gpu::default_context();
+    rmcv_ctx* ctx = gc.get(1, 1);
+    std::vector<int32_t> xy, off;
+    gpu::pack_contours({c}, xy, off);
+    int32_t matched = 0;
+    rmcv_rotated_rect box;
+    gc.check(rmcv_match_lightblobs(ctx, xy.data(), off.data(), 1, minRatio, maxRatio, tiltAngle, minArea, maxArea, fitEllipse ? 1 : 0,
+                                   &matched, &box), "rmcv_match_lightblobs");
+    if (matched) lightBlobBox = gpu::to_rotated_rect(box);
+    return matched != 0;
+}
+
+inline void FindLightBlobs(std::vector<contour>& contours, std::vector<lightblob>& lightBlobs, float minRatio, float maxRatio,
+                           float tiltAngle, float minArea, float maxArea, const cv::Mat& source, bool fitEllipse = true) {
+    lightBlobs.clear();
+    if (source.channels() != 3 || contours.empty()) return;   // src/objdetect.cpp:35
+    gpu::context& gc = gpu::default_context();
+    rmcv_ctx* ctx = gc.get(1, 1);
+    std::vector<int32_t> xy, off;
+    gpu::pack_contours(contours, xy, off);
+    std::vector<rmcv_lightblob> out(contours.size());
+    int nb = 0;
+    gc.check(rmcv_find_lightblobs_legacy(ctx, xy.data(), off.data(), (int)contours.size(), minRatio, maxRatio, tiltAngle, minArea, maxArea,
+                                         source.data, source.step, source.cols, source.rows, fitEllipse ? 1 : 0, out.data(),
+                                         (int)out.size(), &nb), "rmcv_find_lightblobs_legacy");
+    for (int k = 0; k < nb; ++k) {
+#if defined(RMCV_SHIM_WITH_REFERENCE)
+        // rebuild through the reference's ctor from the corner points' rectangle is not possible without the box; the
+        // C ABI returns the finished light blob, copy its public fields into a default-constructed-from-box object
+        lightblob lb(cv::RotatedRect(cv::Point2f(out[k].center[0], out[k].center[1]), cv::Size2f(out[k].size[0], out[k].size[1]), 0.f),
+                     static_cast<camp>(out[k].target));
+        lb.angle = out[k].angle;
+        for (int i = 0; i < 4; ++i) lb.vertices[i] = cv::Point2f(out[k].vertices[i][0], out[k].vertices[i][1]);
+        lb.size = cv::Size2f(out[k].size[0], out[k].size[1]);
+        lightBlobs.push_back(lb);
+#else
+        lightBlobs.push_back(gpu::to_lightblob(out[k], nullptr));
+#endif
+    }
+}
+
+inline bool LightBlobOverlap(const std::vector<lightblob>& lightBlobs, int leftIndex, int rightIndex) {
+    if (lightBlobs.empty()) return false;
+    gpu::context& gc = gpu::default_context();
+    rmcv_ctx* ctx = gc.get(1, 1);
+    std::vector<rmcv_lightblob> in(lightBlobs.size());
+    for (size_t i = 0; i < lightBlobs.size(); ++i) in[i] = gpu::from_lightblob(lightBlobs[i]);
+    int res = 0;
+    gc.check(rmcv_lightblob_overlap(ctx, in.data(), (int)in.size(), leftIndex, rightIndex, &res), "rmcv_lightblob_overlap");
+    return res != 0;
+}
+
 namespace gpu {
 // Fused single call: image -> positives + armours without materialising contours on the host.
 inline detection detect(const cv::Mat& image, const rmcv_params& prm, cv::Mat* binary = nullptr) {

@@ -98,6 +98,11 @@ PROTOTYPES = {
     "rmcv_filter_lightblobs": (C.c_int, [_vp, _vp, _vp, _i, C.POINTER(Params), _vp, _vp, _i, C.POINTER(C.c_int)]),
     "rmcv_filter_armours": (C.c_int, [_vp, _vp, _i, C.POINTER(Params), _vp, _i, C.POINTER(C.c_int)]),
     "rmcv_make_lightblobs": (C.c_int, [_vp, _vp, _i, _i, _vp]),
+    "rmcv_match_lightblobs": (C.c_int, [_vp, _vp, _vp, _i, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _i, _vp, _vp]),
+    "rmcv_find_lightblobs_legacy": (C.c_int, [_vp, _vp, _vp, _i, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                              _u8p, _sz, _i, _i, _i, _vp, _i, C.POINTER(C.c_int)]),
+    "rmcv_min_area_rects": (C.c_int, [_vp, _vp, _vp, _i, _vp]),
+    "rmcv_lightblob_overlap": (C.c_int, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_int)]),
     "rmcv_profile_enable": (C.c_int, [_vp, _i]),
     "rmcv_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), _i]),
     "rmcv_timer_start": (C.c_int, [_vp]),

@@ -391,6 +391,66 @@ class Context:
         return [LightBlob.from_c(out[i]) for i in range(n)]
 
 
+    # -- legacy rows (a6, a7)
+    @staticmethod
+    def _pack_contours(contours):
+        n = len(contours)
+        offs = np.zeros(n + 1, np.int32)
+        for i, c in enumerate(contours):
+            offs[i + 1] = offs[i] + len(c)
+        xy = (np.concatenate([np.asarray(c, np.int32).reshape(-1, 2) for c in contours]) if n and offs[-1] > 0
+              else np.zeros((0, 2), np.int32))
+        return np.ascontiguousarray(xy, np.int32), offs
+
+    def match_lightblobs(self, contours, min_ratio, max_ratio, tilt_angle, min_area, max_area, fit_ellipse=True):
+        """rm::MatchLightBlob on every contour -> list of (ok, (cx, cy, w, h, angle))."""
+        n = len(contours)
+        if n == 0:
+            return []
+        xy, offs = self._pack_contours(contours)
+        matched = np.zeros(n, np.int32)
+        boxes = (A.RotatedRect * n)()
+        self._check(self.lib.rmcv_match_lightblobs(self.h, xy.ctypes.data if xy.size else None, offs.ctypes.data, n, min_ratio,
+                                                   max_ratio, tilt_angle, min_area, max_area, 1 if fit_ellipse else 0,
+                                                   matched.ctypes.data, boxes), "rmcv_match_lightblobs")
+        return [(bool(matched[k]), (boxes[k].cx, boxes[k].cy, boxes[k].w, boxes[k].h, boxes[k].angle)) for k in range(n)]
+
+    def find_lightblobs_legacy(self, contours, min_ratio, max_ratio, tilt_angle, min_area, max_area, source, fit_ellipse=True):
+        """rm::FindLightBlobs (legacy) -> list of LightBlob (camp voted from the source image)."""
+        n = len(contours)
+        if n == 0 or source.ndim != 3 or source.shape[2] != 3:   # src/objdetect.cpp:35
+            return []
+        source = np.ascontiguousarray(source, np.uint8)
+        H, W, _ = source.shape
+        xy, offs = self._pack_contours(contours)
+        out = (A.LightBlob * n)()
+        nb = C.c_int()
+        self._check(self.lib.rmcv_find_lightblobs_legacy(self.h, xy.ctypes.data if xy.size else None, offs.ctypes.data, n,
+                                                         min_ratio, max_ratio, tilt_angle, min_area, max_area, source.ctypes.data,
+                                                         W * 3, W, H, 1 if fit_ellipse else 0, out, n, C.byref(nb)),
+                    "rmcv_find_lightblobs_legacy")
+        return [LightBlob.from_c(out[i]) for i in range(nb.value)]
+
+    def min_area_rects(self, contours):
+        """cv::minAreaRect of every contour -> list of (cx, cy, w, h, angle)."""
+        n = len(contours)
+        if n == 0:
+            return []
+        xy, offs = self._pack_contours(contours)
+        boxes = (A.RotatedRect * n)()
+        self._check(self.lib.rmcv_min_area_rects(self.h, xy.ctypes.data if xy.size else None, offs.ctypes.data, n, boxes),
+                    "rmcv_min_area_rects")
+        return [(boxes[k].cx, boxes[k].cy, boxes[k].w, boxes[k].h, boxes[k].angle) for k in range(n)]
+
+    def lightblob_overlap(self, blobs: Sequence[LightBlob], left: int, right: int) -> bool:
+        """rm::LightBlobOverlap."""
+        n = len(blobs)
+        arr = (A.LightBlob * max(n, 1))(*[b.to_c() for b in blobs])
+        out = C.c_int()
+        self._check(self.lib.rmcv_lightblob_overlap(self.h, arr, n, left, right, C.byref(out)), "rmcv_lightblob_overlap")
+        return bool(out.value)
+
+
 # --------------------------------------------------------------------------------------------- rm:: mirror
 _default_ctx: Optional[Context] = None
 

@@ -842,6 +842,107 @@ int rmcv_make_lightblobs(rmcv_ctx* ctx, const rmcv_rotated_rect* boxes, int n, i
     return RMCV_OK;
 }
 
+// shared by the three legacy contour entry points: upload, one launch, download
+static int run_legacy(rmcv_ctx* ctx, const int32_t* xy, const int32_t* offsets, int n, float min_ratio, float max_ratio,
+                      float tilt_angle, float min_area, float max_area, int fit_ellipse, const uint8_t* h_src, size_t pitch,
+                      int width, int height, int32_t* matched, rmcv_rotated_rect* boxes, int32_t* camps, rmcv_lightblob* blobs) {
+    if (!ctx || !offsets || n < 0) return RMCV_ERR_INVALID_ARG;
+    if (n == 0) return RMCV_OK;
+    const size_t npts = (size_t)offsets[n];
+    if (npts > 0 && !xy) return RMCV_ERR_INVALID_ARG;
+    if (h_src && (width <= 0 || height <= 0 || pitch < (size_t)width * 3)) return set_err(ctx, RMCV_ERR_INVALID_ARG, "bad source image geometry");
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    const size_t b_xy = up16(npts * 8 + 8), b_off = up16(((size_t)n + 1) * 4), b_hull = up16(npts * 8 + 8);
+    const size_t b_m = up16((size_t)n * 4), b_box = up16((size_t)n * sizeof(rmcv_rotated_rect)), b_c = up16((size_t)n * 4);
+    const size_t b_blob = up16((size_t)n * sizeof(rmcv_lightblob));
+    const size_t b_src = h_src ? up16((size_t)height * width * 3) : 0;
+    const size_t b_out = b_m + b_box + b_c + b_blob;
+    int rc = ensure_tmp(ctx, b_xy + b_off + b_hull + b_out + b_src + 64, b_out + 64);
+    if (rc != RMCV_OK) return rc;
+    CtxExtra* ex = extra(ctx);
+    uint8_t* d = reinterpret_cast<uint8_t*>(ex->tmp_dev);
+    cudaStream_t st = ex->pix;
+    if (npts) RMCV_CUDA(ctx, cudaMemcpyAsync(d, xy, npts * 8, cudaMemcpyHostToDevice, st));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(d + b_xy, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
+    uint8_t* d_out = d + b_xy + b_off + b_hull;
+    uint8_t* d_src = d_out + b_out;
+    if (h_src)
+        RMCV_CUDA(ctx, cudaMemcpy2DAsync(d_src, (size_t)width * 3, h_src, pitch, (size_t)width * 3, height, cudaMemcpyHostToDevice, st));
+    LegacyLaunch L;
+    L.xy = reinterpret_cast<const int32_t*>(d); L.off = reinterpret_cast<const int32_t*>(d + b_xy); L.n_contours = n;
+    L.min_ratio = min_ratio; L.max_ratio = max_ratio; L.tilt_angle = tilt_angle; L.min_area = min_area; L.max_area = max_area;
+    L.fit_ellipse = fit_ellipse;
+    L.src = h_src ? d_src : nullptr; L.pitch = (size_t)width * 3; L.W = width; L.H = height;
+    L.hull = reinterpret_cast<int32_t*>(d + b_xy + b_off);
+    L.matched = reinterpret_cast<int32_t*>(d_out);
+    L.boxes = reinterpret_cast<rmcv_rotated_rect*>(d_out + b_m);
+    L.camps = reinterpret_cast<int32_t*>(d_out + b_m + b_box);
+    L.blobs = reinterpret_cast<rmcv_lightblob*>(d_out + b_m + b_box + b_c);
+    if (fit_ellipse < 0) RMCV_CUDA(ctx, cudaMemsetAsync(d_out, 0, b_out, st));
+    RMCV_CUDA(ctx, launch_legacy(L, st, &ctx->kernel_launches));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(ex->tmp_host, d_out, b_out, cudaMemcpyDeviceToHost, st));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint8_t* h = reinterpret_cast<const uint8_t*>(ex->tmp_host);
+    if (matched) memcpy(matched, h, (size_t)n * 4);
+    if (boxes) memcpy(boxes, h + b_m, (size_t)n * sizeof(rmcv_rotated_rect));
+    if (camps) memcpy(camps, h + b_m + b_box, (size_t)n * 4);
+    if (blobs) memcpy(blobs, h + b_m + b_box + b_c, (size_t)n * sizeof(rmcv_lightblob));
+    return RMCV_OK;
+}
+
+int rmcv_match_lightblobs(rmcv_ctx* ctx, const int32_t* xy, const int32_t* offsets, int n_contours, float min_ratio,
+                          float max_ratio, float tilt_angle, float min_area, float max_area, int fit_ellipse, int32_t* matched,
+                          rmcv_rotated_rect* boxes) {
+    if (!matched || !boxes) return RMCV_ERR_INVALID_ARG;
+    return run_legacy(ctx, xy, offsets, n_contours, min_ratio, max_ratio, tilt_angle, min_area, max_area, fit_ellipse ? 1 : 0,
+                      nullptr, 0, 0, 0, matched, boxes, nullptr, nullptr);
+}
+
+int rmcv_find_lightblobs_legacy(rmcv_ctx* ctx, const int32_t* xy, const int32_t* offsets, int n_contours, float min_ratio,
+                                float max_ratio, float tilt_angle, float min_area, float max_area, const uint8_t* h_source_bgr,
+                                size_t pitch, int width, int height, int fit_ellipse, rmcv_lightblob* blobs, int blob_cap,
+                                int* n_blobs) {
+    if (!ctx || !n_blobs || !h_source_bgr || blob_cap < 0) return RMCV_ERR_INVALID_ARG;
+    *n_blobs = 0;
+    if (n_contours <= 0) return n_contours < 0 ? RMCV_ERR_INVALID_ARG : RMCV_OK;
+    std::vector<int32_t> matched((size_t)n_contours);
+    std::vector<rmcv_lightblob> all((size_t)n_contours);
+    int rc = run_legacy(ctx, xy, offsets, n_contours, min_ratio, max_ratio, tilt_angle, min_area, max_area, fit_ellipse ? 1 : 0,
+                        h_source_bgr, pitch, width, height, matched.data(), nullptr, nullptr, all.data());
+    if (rc != RMCV_OK) return rc;
+    int nb = 0;
+    for (int k = 0; k < n_contours; ++k)
+        if (matched[(size_t)k]) { if (blobs && nb < blob_cap) blobs[nb] = all[(size_t)k]; ++nb; }
+    *n_blobs = nb;
+    return (blobs && nb > blob_cap) ? set_err(ctx, RMCV_ERR_CAPACITY, "blob_cap too small") : RMCV_OK;
+}
+
+int rmcv_min_area_rects(rmcv_ctx* ctx, const int32_t* xy, const int32_t* offsets, int n_contours, rmcv_rotated_rect* boxes) {
+    if (!boxes) return RMCV_ERR_INVALID_ARG;
+    return run_legacy(ctx, xy, offsets, n_contours, 0.f, 0.f, 0.f, 0.f, 0.f, -1, nullptr, 0, 0, 0, nullptr, boxes, nullptr, nullptr);
+}
+
+int rmcv_lightblob_overlap(rmcv_ctx* ctx, const rmcv_lightblob* blobs, int n_blobs, int left, int right, int* overlap) {
+    if (!ctx || !overlap || n_blobs < 0 || (n_blobs > 0 && !blobs)) return RMCV_ERR_INVALID_ARG;
+    *overlap = 0;
+    if (n_blobs == 0) return RMCV_OK;
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t b_blob = ((size_t)n_blobs * sizeof(rmcv_lightblob) + 15) & ~(size_t)15;
+    int rc = ensure_tmp(ctx, b_blob + 64, 64);
+    if (rc != RMCV_OK) return rc;
+    CtxExtra* ex = extra(ctx);
+    uint8_t* d = reinterpret_cast<uint8_t*>(ex->tmp_dev);
+    cudaStream_t st = ex->pix;
+    RMCV_CUDA(ctx, cudaMemcpyAsync(d, blobs, (size_t)n_blobs * sizeof(rmcv_lightblob), cudaMemcpyHostToDevice, st));
+    int32_t* d_out = reinterpret_cast<int32_t*>(d + b_blob);
+    RMCV_CUDA(ctx, launch_overlap(reinterpret_cast<const rmcv_lightblob*>(d), n_blobs, left, right, d_out, st, &ctx->kernel_launches));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(ex->tmp_host, d_out, 4, cudaMemcpyDeviceToHost, st));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(st));
+    *overlap = *reinterpret_cast<const int32_t*>(ex->tmp_host);
+    return RMCV_OK;
+}
+
 int rmcv_profile_enable(rmcv_ctx* ctx, int on) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
     ctx->profiling = on != 0;

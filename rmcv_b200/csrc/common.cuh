@@ -185,6 +185,18 @@ cudaError_t launch_filter_armours(const rmcv_lightblob* d_blobs, int n, const rm
 cudaError_t launch_make_lightblobs(const rmcv_rotated_rect* d_boxes, int n, int target, rmcv_lightblob* d_out,
                                    cudaStream_t st, int64_t* launches);
 
+struct LegacyLaunch {   // rm::MatchLightBlob / rm::FindLightBlobs / cv::minAreaRect on caller-supplied contours (legacy.cu)
+    const int32_t* xy; const int32_t* off; int n_contours;
+    float min_ratio, max_ratio, tilt_angle, min_area, max_area;
+    int fit_ellipse;          // 1 = box from the ellipse, 0 = box from cv::minAreaRect, -1 = cv::minAreaRect only (no gates)
+    const uint8_t* src; size_t pitch; int W, H;   // device BGR image for the camp vote, or null
+    int32_t* hull;            // scratch, 2 ints per contour point
+    int32_t* matched; rmcv_rotated_rect* boxes; int32_t* camps; rmcv_lightblob* blobs;   // [n_contours] each
+};
+cudaError_t launch_legacy(const LegacyLaunch& p, cudaStream_t st, int64_t* launches);
+cudaError_t launch_overlap(const rmcv_lightblob* d_blobs, int n, int left, int right, int32_t* d_out, cudaStream_t st,
+                           int64_t* launches);
+
 void upload_luts();  // copies the arc LUT to constant memory (once per process/device)
 
 }  // namespace rmcv

@@ -24,12 +24,19 @@ int main(int argc, char** argv) {
         rmcv_params prm;
         rmcv_default_params(&prm);
         auto det = rm::gpu::detect(image, prm);
+        // legacy entry points (include/objdetect.h:22-37,62) over the same contours
+        std::vector<rm::lightblob> legacy;
+        rm::FindLightBlobs(contours, legacy, 1.5f, 80.f, 70.f, 10.f, 99999.f, image, false);   // box from cv::minAreaRect
+        cv::RotatedRect one;
+        const bool matched0 = !contours.empty() && rm::MatchLightBlob(contours[0], 1.5f, 80.f, 70.f, 10.f, 99999.f, one, true);
+        const bool overlap = legacy.size() >= 3 && rm::LightBlobOverlap(legacy, 0, (int)legacy.size() - 1);
         unsigned long long fg = 0;
         for (int y = 0; y < binary.rows; ++y)
             for (int x = 0; x < binary.cols; ++x) fg += binary.data[(size_t)y * binary.step + x] == 255;
         printf("{\"n_contours\": %zu, \"n_positive\": %zu, \"n_negative\": %zu, \"n_armours\": %zu, \"mask_fg\": %llu, "
-               "\"fused_positive\": %zu, \"fused_armours\": %zu,\n \"contour_sizes\": [",
-               contours.size(), positive.size(), negtive.size(), armours.size(), fg, det.positive.size(), det.armours.size());
+               "\"fused_positive\": %zu, \"fused_armours\": %zu, \"legacy_count\": %zu, \"legacy_blue\": %d, \"matched0\": %d, \"overlap\": %d,\n \"contour_sizes\": [",
+               contours.size(), positive.size(), negtive.size(), armours.size(), fg, det.positive.size(), det.armours.size(), legacy.size(),
+               (int)(legacy.empty() ? 0 : legacy[0].target == rm::CAMP_BLUE), (int)matched0, (int)overlap);
         for (size_t k = 0; k < contours.size(); ++k) printf("%s%zu", k ? "," : "", contours[k].size());
         printf("],\n \"first_points\": [");
         for (size_t k = 0; k < contours.size(); ++k) printf("%s[%d,%d]", k ? "," : "", contours[k][0].x, contours[k][0].y);

@@ -1,0 +1,111 @@
+"""GPU parity of the legacy rows of SURVEY §8 (a6 rm::MatchLightBlob / rm::FindLightBlobs incl. cv::minAreaRect and the
+bounding-rect camp vote, a7 rm::LightBlobOverlap) through the C ABI against the cv2 oracle."""
+import cv2
+import numpy as np
+import pytest
+
+import rmcv_b200 as rb
+from oracle import rm_oracle as O
+from rmcv_b200 import synth
+from tests import _compare as CMP
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    with rb.Context(max_width=1280, max_height=1024, max_batch=1) as c:
+        yield c
+
+
+def rect_equal(got, ref, tol=2e-3):
+    """Same rectangle: cv2 convention (angle in [-90, 0), width along it); near-square ties may swap the edge."""
+    (cx, cy, w, h, a), ((rx, ry), (rw, rh), ra) = got, ref
+    if max(abs(cx - rx), abs(cy - ry)) > tol * 10:
+        return False
+    if abs(w - rw) <= tol * max(1, rw) and abs(h - rh) <= tol * max(1, rh) and abs(a - ra) <= 0.02:
+        return True
+    return abs(w * h - rw * rh) <= 1e-5 * max(1.0, rw * rh)   # an equal-area tie between two hull edges
+
+
+def test_min_area_rect_matches_cv2(ctx):
+    n = ties = 0
+    for seed in range(4):
+        fr = O.detect_frame(synth.make_frame(400 + seed, 1280, 1024, synth.plates_for_seed(400 + seed)))
+        cs = [c for c in fr.contours if len(c) >= 3]
+        got = ctx.min_area_rects(cs)
+        for c, g in zip(cs, got):
+            ref = cv2.minAreaRect(c.reshape(-1, 1, 2).astype(np.int32))
+            if ref[1][0] * ref[1][1] == 0:
+                continue   # collinear points
+            assert rect_equal(g, ref), f"minAreaRect {g} vs cv2 {ref}"
+            exact = abs(g[2] - ref[1][0]) <= 2e-3 * max(1, ref[1][0]) and abs(g[4] - ref[2]) <= 0.02
+            ties += not exact
+            n += 1
+    assert n > 100 and ties <= 0.03 * n
+    # hand-checkable: an axis-aligned 20x100 block -> ((100, 20), -90) in OpenCV 4.13
+    ys, xs = np.mgrid[10:110, 30:50]
+    block = np.stack([xs.ravel(), ys.ravel()], 1).astype(np.int32)
+    (cx, cy, w, h, a), = ctx.min_area_rects([block])
+    assert (round(w), round(h), round(a)) == (99, 19, -90) and abs(cx - 39.5) < 1e-3 and abs(cy - 59.5) < 1e-3
+
+
+@pytest.mark.parametrize("fit_ellipse", [True, False])
+def test_match_and_find_lightblobs_legacy(ctx, fit_ellipse):
+    args = (1.5, 80.0, 70.0, 10.0, 99999.0)
+    nmatch = 0
+    for seed, blue in ((410, True), (411, False), (412, True)):
+        img = synth.make_frame(seed, 1280, 1024, synth.plates_for_seed(seed), blue=blue)
+        contours, _ = O.extract_color(img, rb.CAMP_BLUE if blue else rb.CAMP_RED, 80)
+        got = ctx.match_lightblobs(contours, *args, fit_ellipse=fit_ellipse)
+        keep = []
+        for c, (ok, box) in zip(contours, got):
+            rok, rbox = O.match_lightblob(c, *args, fit_ellipse=fit_ellipse)
+            v = O.classify_contour(c, 70.0, (1.5, 80.0), (10.0, 99999.0))
+            fragile = v.status != 0 and (v.ellipse.w < 2.0 or CMP.near_blob_gate(v, CMP.oracle_params()))
+            if not fragile:
+                assert ok == rok, f"seed {seed}: MatchLightBlob verdict {ok} != {rok}"
+            if ok and rok:
+                nmatch += 1
+                if fit_ellipse:
+                    assert abs(box[0] - rbox.cx) <= 0.5 and abs(box[1] - rbox.cy) <= 0.5   # rng-band tolerant; exact in test_gpu_detect
+                else:
+                    assert rect_equal(box, ((rbox.cx, rbox.cy), (rbox.w, rbox.h), rbox.angle))
+            keep.append(ok == rok)
+        if all(keep):
+            blobs = ctx.find_lightblobs_legacy(contours, *args, source=img, fit_ellipse=fit_ellipse)
+            ref = O.find_lightblobs_legacy(contours, *args, source=img, fit_ellipse=fit_ellipse)
+            assert [b.target for b in blobs] == [b.target for b in ref], "camp vote differs"
+            assert all(b.target == (rb.CAMP_BLUE if blue else rb.CAMP_RED) for b in blobs)
+            for b, r in zip(blobs, ref):
+                assert abs(b.center[0] - r.center[0]) <= 0.5 and abs(b.center[1] - r.center[1]) <= 0.5
+    assert nmatch > 30
+    # a non-3-channel source yields nothing (src/objdetect.cpp:35)
+    assert ctx.find_lightblobs_legacy(contours, *args, source=img[..., 0], fit_ellipse=fit_ellipse) == []
+
+
+def test_guide_light_vote(ctx):
+    """Green bars: G > B and G > R over the bounding rect -> CAMP_GUIDELIGHT."""
+    img = np.zeros((200, 300, 3), np.uint8)
+    cv2.ellipse(img, ((100, 100), (12, 70), 5), (40, 255, 60), -1)
+    cv2.ellipse(img, ((200, 100), (12, 70), -5), (40, 255, 60), -1)
+    contours, _ = O.extract_color(img, rb.CAMP_GUIDELIGHT, 80)
+    assert len(contours) == 2
+    blobs = ctx.find_lightblobs_legacy(contours, 1.5, 80.0, 70.0, 10.0, 99999.0, source=img)
+    ref = O.find_lightblobs_legacy(contours, 1.5, 80.0, 70.0, 10.0, 99999.0, source=img)
+    assert [b.target for b in blobs] == [b.target for b in ref] == [rb.CAMP_GUIDELIGHT, rb.CAMP_GUIDELIGHT]
+
+
+def test_lightblob_overlap(ctx):
+    fr = O.detect_frame(synth.make_frame(420, 1280, 1024, 12))
+    blobs = sorted(fr.positive, key=lambda b: b.center[0])
+    cb = [rb.LightBlob(b.angle, b.target, b.center, b.vertices, b.size) for b in blobs]
+    n = len(blobs)
+    seen = set()
+    for left in range(-1, n):
+        for right in range(left, n + 2):
+            got = ctx.lightblob_overlap(cb, left, right)
+            ref = O.lightblob_overlap(blobs, left, right)
+            assert got == ref, f"LightBlobOverlap({left},{right}) = {got}, oracle {ref}"
+            seen.add(ref)
+    assert seen == {True, False}

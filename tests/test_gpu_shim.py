@@ -33,6 +33,10 @@ def test_cpp_call_site_matches_oracle():
     assert got["n_negative"] == len(ref.negative) and got["n_armours"] == len(ref.armours)
     assert got["fused_positive"] == len(ref.positive) and got["fused_armours"] == len(ref.armours)
     assert got["mask_fg"] == int((ref.binary == 255).sum())
+    legacy = O.find_lightblobs_legacy(ref.contours, 1.5, 80.0, 70.0, 10.0, 99999.0, frame, fit_ellipse=False)
+    assert got["legacy_count"] == len(legacy) and got["legacy_blue"] == 1
+    assert got["matched0"] == int(O.match_lightblob(ref.contours[0], 1.5, 80.0, 70.0, 10.0, 99999.0, True)[0])
+    assert got["overlap"] == int(O.lightblob_overlap(legacy, 0, len(legacy) - 1))
     assert got["contour_sizes"] == [len(c) for c in ref.contours]
     assert got["first_points"] == [[int(c[0][0]), int(c[0][1])] for c in ref.contours]
     for g, b in zip(got["blob_centers"], ref.positive):
