@@ -42,6 +42,11 @@ W_, H_ = 1280, 1024
 ALG_BYTES_PER_FRAME = W_ * H_ * 4  # 3 B/px BGR read + 1 B/px mask written
 
 
+def workload_name(frames):
+    return (f"1280x1024 BGR full detect (extract_color+filter_lightblobs+filter_armours, main.cpp:172-176 parameters), "
+            f"{frames} synthetic frames per GPU per step (BASELINE config 3)")
+
+
 def env_rank():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -52,6 +57,16 @@ def measured_peak_gbs():
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_launch(frames_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the pixel kernel from the committed `ncu --set full` capture
+    (profiles/pixel_traffic.json, written by scripts/ncu_summary.py), scaled to this run's frames per launch."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "pixel_traffic.json")))
+        return d["dram_bytes_per_frame"] * frames_per_launch
+    except Exception:
+        return None
 
 
 def make_frames(n, seed0, out, threads=None):
@@ -151,7 +166,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"1280x1024 full detect (reference CPU path: OpenCV via the cv2 oracle; the C++ reference cannot be built here), {n} frames/step"},
+        "config": {"workload": workload_name(n), "frames_per_step": n,
+                   "note": "reference CPU path = the cv2 oracle (same OpenCV kernels as the C++ reference, which cannot be built on this image: no OpenCV C++)"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -224,7 +240,6 @@ def run_gpu(args):
     wall_ms = 1e3 * (time.perf_counter() - wall0)
     launches = ctx.kernel_launches() - launches0
     barrier()
-    clocks = sampler.stop()
     prof = ctx.profile_read(reset=True)
     ctx.profile(False)
     max_ms, units = shard.reduce_timing(dev_ms, B * args.steps, dist, device=None if dist is None else f"cuda:{local_rank}")
@@ -246,6 +261,11 @@ def run_gpu(args):
         if i >= 3:
             pix_ms.append(ms)
     pix_ms_med = statistics.median(pix_ms)
+    if (time.perf_counter() - wall0) < 0.35:   # keep the GPU under the same load until nvidia-smi has a few samples
+        while time.perf_counter() - wall0 < 0.35:
+            step_device()
+    clocks = sampler.stop()
+    clocks["note"] = "sampled every 100 ms from the start of the timed steps through the pixel-kernel roofline loop"
     chunk = ctx.chunk_frames
     n_chunks = -(-B // chunk)
     peak, peak_src = measured_peak_gbs()
@@ -268,6 +288,40 @@ def run_gpu(args):
     e2e_value = e2e_units / (e2e_max * 1e-3)
     d2h_bytes = 32 * B + 72 * n_contours + 56 * n_blobs + 112 * n_armours  # frame infos + dense records actually written
 
+    # ---- extras on rank 0: BASELINE config 5 (batch-1 latency) and config 2 (Bayer pixel stage)
+    extras = None
+    if rank == 0 and not args.no_extras:
+        extras = {}
+        lat = []
+        n_lat = 2000
+        for i in range(200 + n_lat):
+            t0 = time.perf_counter()
+            ctx.detect_batch(d_frames.ptr + (i % B) * H_ * W_ * 3, W_, H_, 1, params, d_mask.ptr)
+            ctx.fetch_results()
+            if i >= 200:
+                lat.append(1e6 * (time.perf_counter() - t0))
+        lat.sort()
+        extras["latency_batch1"] = {"p50_us": lat[len(lat) // 2], "p99_us": lat[int(len(lat) * 0.99)], "frames": n_lat,
+                                    "what": "1280x1024 frame resident in HBM; enqueue (6 launches) -> results readable in pinned host memory; host wall clock"}
+        WB_, HB_, NB_ = 1440, 1080, 64
+        raw = np.stack([synth.bgr_to_bayer(synth.make_frame(s, WB_, HB_, 10), synth.BAYER_BG) for s in range(8)] * (NB_ // 8))
+        ctxb = rb.Context(max_width=WB_, max_height=HB_, max_batch=NB_, device=dev_index)
+        d_raw = ctxb.device_buffer(raw.nbytes); d_mb = ctxb.device_buffer(NB_ * HB_ * WB_)
+        d_raw.upload(raw)
+        bms = []
+        for i in range(8):
+            ctxb.timer_start()
+            ctxb.bayer_extract_color_batch(d_raw.ptr, WB_, HB_, NB_, synth.BAYER_BG, params.target, params.lower_bound, d_mb.ptr)
+            ms = ctxb.timer_stop()
+            if i >= 3:
+                bms.append(ms)
+        bm = statistics.median(bms)
+        extras["bayer_pixel_stage"] = {"workload": "64 x 1440x1080 raw BGGR: debayer(B,R) + colour difference + threshold + 3x3 close (BASELINE config 2)",
+                                       "ms": bm, "algorithmic_bytes": NB_ * HB_ * WB_ * 2, "achieved_gbs": NB_ * HB_ * WB_ * 2 / (bm * 1e-3) / 1e9,
+                                       "frac_of_peak": NB_ * HB_ * WB_ * 2 / (bm * 1e-3) / 1e9 / peak,
+                                       "note": "199 MB working set, partly L2-resident between repetitions"}
+        d_raw.free(); d_mb.free(); ctxb.close()
+
     # ---- CPU baseline on rank 0 at N == 1
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -284,15 +338,17 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"1280x1024 BGR full detect (extract_color+filter_lightblobs+filter_armours), {B} frames per GPU per step, "
-                                   f"main.cpp:172-176 parameters, inputs resident in HBM ({B * H_ * W_ * 3 / 1e9:.1f} GB > 126 MB L2, no flush needed)",
+            "config": {"workload": workload_name(B),
+                       "inputs": f"resident in HBM ({B * H_ * W_ * 3 / 1e9:.1f} GB per GPU > 126 MB L2, no flush needed)",
                        "frames_per_gpu": B, "chunk_frames": chunk, "parallelism": f"frame-sharded x{world}, no collective",
                        "steps_in_flight": 1 if args.no_pipeline else 2,
                        "contours_per_frame": n_contours / B, "blobs_per_frame": n_blobs / B, "armours_per_frame": n_armours / B},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * H_ * W_ * 3, "d2h_bytes_per_step": d2h_bytes,
                     "steps": args.e2e_steps, "note": "rmcv_detect_batch_host from pinned host frames; wall clock; mask kept on device"},
             "gpu_launches": tot_launches,
-            "roofline": {"bound": "hbm", "achieved": ach_iso, "peak": peak, "unit": "GB/s", "frac": ach_iso / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach_iso, "peak": peak, "unit": "GB/s", "frac": ach_iso / peak,
+                         "traffic": ncu_traffic_per_launch(frames_per_launch),
+                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_FRAME * frames_per_launch,
                          "kernel": "pixel_bgr_kernel<true> (fused diff/threshold/close)", "peak_source": peak_src,
                          "launch_ms": pix_ms_med / n_chunks, "frames_per_launch": frames_per_launch,
                          "algorithmic_bytes_per_frame": ALG_BYTES_PER_FRAME,
@@ -300,6 +356,7 @@ def run_gpu(args):
                                          "note": "same kernel timed with CUDA events inside the timed steps, where it overlaps the other slot's labelling kernels"},
                          "full_path_frac": value / world * ALG_BYTES_PER_FRAME / 1e9 / peak},
             "cpu_baseline": cpu,
+            "extras": extras,
             "clocks": clocks,
             "stage_ms_per_step": stage_ms,
             "wall_ms_per_step": max_wall / args.steps,
@@ -323,6 +380,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=0, help="frame passes of the CPU baseline (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the latency (config 5) and Bayer (config 2) side measurements")
     ap.add_argument("--no-pipeline", action="store_true", help="fetch every step's results before enqueueing the next step")
     args = ap.parse_args()
     cores = os.cpu_count() or 1

@@ -748,6 +748,10 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         while (smem > (size_t)max_smem_optin && Rs > 0) { Rs = Rs > 1024 ? Rs - 1024 : 0; smem = label_smem_bytes(L.g.H, Rs, L.g.C); }
         if (smem > (size_t)max_smem_optin) return cudaErrorInvalidConfiguration;
         p.Rs = Rs;
+        if (const char* pad = getenv("RMCV_LABEL_MINSMEM")) {   // experiment: cap the CTAs per SM by padding shared memory
+            const size_t m = (size_t)atoi(pad);
+            if (m > smem && m <= (size_t)max_smem_optin) smem = m;
+        }
         e = cudaFuncSetAttribute(label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         label_kernel<<<L.frames, 256, smem, st>>>(p);

@@ -283,7 +283,23 @@ struct BayerSite {  // which of the 4 interpolation patterns yields channel c at
     uint8_t plus[2][2], minus[2][2];
 };
 
-__global__ void __launch_bounds__(512) pixel_bayer_kernel(const PixelParams p, const BayerSite site) {
+// The threshold test of one pixel as integer linear forms over its 3x3 raw neighbourhood.  With P = (Sp + rp) >> kp and
+// M = (Sm + rm) >> km (kp, km in {0,1,2}: own sample / pair / quad) the test sat(P - M) >= lb, lb >= 1, is
+//   km == 0:  Sp - (Sm << kp) + rp - (lb << kp) >= 0
+//   kp == 0:  (Sp << km) - Sm - c0 >= 0,             c0 = (lb << km) - (1 << km) + rm + 1
+//   else:     (((Sp + rp) >> kp) << km) - Sm - c0 >= 0
+// i.e.  V + ((Q + rq) >> kq << ks) >= 0  with V, Q linear in the nine bytes: three dp4a each (one per raw row), the
+// coefficient bytes placed where the pixel's neighbours sit in a word holding the bytes x-1 .. x+2 (even x) or
+// x-2 .. x+1 (odd x).
+struct BayerProg {
+    uint32_t vu, vc, vd;   // V coefficients (packed s8x4) for the rows y-1, y, y+1
+    uint32_t qu, qc, qd;   // Q coefficients; unused when kq == 0
+    int32_t v0;            // constant of V
+    int32_t rq, kq, ks;
+};
+struct BayerProgs { BayerProg g[2][2]; };  // [row parity][x parity]
+
+__global__ void __launch_bounds__(512) pixel_bayer_kernel(const PixelParams p, const BayerProgs progs) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, NT = blockDim.x;
     const int frame = blockIdx.x / p.bands, band = blockIdx.x - frame * p.bands;
@@ -294,39 +310,37 @@ __global__ void __launch_bounds__(512) pixel_bayer_kernel(const PixelParams p, c
     const int ty0 = y0 - hl;
     // threshold rows needed: [y0-hl, y0+nout+hl) clipped; raw rows: one more on each side, clamped
     const int cy0 = max(0, ty0), cy1 = min(H, y0 + nout + hl);
-    const int ry0 = max(0, cy0 - 2), ry1 = min(H, cy1 + 2);  // generous: border replicate may look 2 rows in
+    const int ry0 = max(0, min(cy0, H - 2) - 1), ry1 = min(H, max(cy1 - 1, 1) + 2);  // raw rows yc-1 .. yc+1, yc clamped to [1, H-2]
     const int nraw = ry1 - ry0;
-    const size_t raw_bytes = ((size_t)(BH + 2 * hl + 4) * p.srow + 15) & ~(size_t)15;
+    const size_t raw_bytes = ((size_t)(BH + 2 * hl + 2) * p.srow + 15) & ~(size_t)15;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + raw_bytes);  // after the raw rows
-    uint32_t* t = reinterpret_cast<uint32_t*>(smem + raw_bytes + 16);
+    uint32_t* t = reinterpret_cast<uint32_t*>(smem + raw_bytes + 128);   // room for 16 mbarriers (<= 128 raw rows)
     uint32_t* d = t + (size_t)(BH + 2 * hl) * TW;
 
     for (int i = tid; i < (BH + 2 * hl) * TW; i += NT) t[i] = 0u;
     const uint8_t* fsrc = p.src + (size_t)frame * p.frame_stride;
     const bool bulk = p.contiguous >= 0 && (p.srow == W) && ((W & 15) == 0) && ((p.pitch & 15) == 0) &&
                       ((((size_t)fsrc) & 15) == 0);
+    constexpr int kLoadRows = 8;   // raw rows per mbarrier: threshold rows start as soon as their three raw rows are in
+    const int nloads = (nraw + kLoadRows - 1) / kLoadRows;
     if (bulk) {
         if (tid == 0) {
-            mbar_init(&bars[0], 1);
+            for (int c = 0; c < nloads; ++c) mbar_init(&bars[c], 1);
             mbar_fence_init();
         }
         __syncthreads();
         if (tid == 0) {
-            mbar_expect_tx(&bars[0], (uint32_t)nraw * (uint32_t)W);
-            if (p.pitch == (size_t)W) {
-                // chunks of <= 32 KB keep every copy well inside the mbarrier tx-count range
-                int r = 0;
-                while (r < nraw) {
-                    int nr = min(nraw - r, max(1, 32768 / W));
-                    bulk_g2s(smem + (size_t)r * p.srow, fsrc + (size_t)(ry0 + r) * p.pitch, (uint32_t)nr * (uint32_t)W, &bars[0]);
-                    r += nr;
+            for (int c = 0; c < nloads; ++c) {
+                const int r = c * kLoadRows, nr = min(kLoadRows, nraw - r);
+                mbar_expect_tx(&bars[c], (uint32_t)nr * (uint32_t)W);
+                if (p.pitch == (size_t)W) {
+                    bulk_g2s(smem + (size_t)r * p.srow, fsrc + (size_t)(ry0 + r) * p.pitch, (uint32_t)nr * (uint32_t)W, &bars[c]);
+                } else {
+                    for (int q = 0; q < nr; ++q)
+                        bulk_g2s(smem + (size_t)(r + q) * p.srow, fsrc + (size_t)(ry0 + r + q) * p.pitch, (uint32_t)W, &bars[c]);
                 }
-            } else {
-                for (int r = 0; r < nraw; ++r)
-                    bulk_g2s(smem + (size_t)r * p.srow, fsrc + (size_t)(ry0 + r) * p.pitch, (uint32_t)W, &bars[0]);
             }
         }
-        mbar_wait(&bars[0], 0);
     } else {
         for (int r = 0; r < nraw; ++r) {
             const uint8_t* g = fsrc + (size_t)(ry0 + r) * p.pitch;
@@ -334,38 +348,66 @@ __global__ void __launch_bounds__(512) pixel_bayer_kernel(const PixelParams p, c
         }
         __syncthreads();
     }
-    // threshold bits: one thread per (row, 32-pixel word); interior pixels by the bilinear rule, border
-    // pixels replicate the clamped interior coordinate.
+    // threshold bits: one warp per row (the pixel programs depend on the row parity only), lanes over 16-pixel items;
+    // per pixel three dp4a (six at green sites) on funnel-shifted words.  Border rows replicate the neighbouring
+    // interior row (recomputed), border columns are fixed up afterwards.
     const int lb = p.lb;
-    for (Iter2D it(tid, NT, WB); it.r < cy1 - cy0; it.next()) {
-        const int y = cy0 + it.r, k = it.c;
+    const int nw = p.srow >> 2;  // 32-bit words per shared-memory row
+    const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+    const int items = (W + 15) >> 4;
+    uint16_t* t16 = reinterpret_cast<uint16_t*>(t);
+    for (int rr = warp; rr < cy1 - cy0; rr += nwarps) {
+        const int y = cy0 + rr;
         const int yc = min(max(y, 1), H - 2);          // row whose interior values this row shows
-        const uint8_t* rm = smem + (size_t)(yc - 1 - ry0) * p.srow;
-        const uint8_t* r0 = smem + (size_t)(yc - ry0) * p.srow;
-        const uint8_t* rp = smem + (size_t)(yc + 1 - ry0) * p.srow;
-        uint32_t wbits = 0;
-        const int xend = min(32, W - k * 32);
-        for (int b = 0; b < xend; ++b) {
-            const int x = k * 32 + b;
-            const int xc = min(max(x, 1), W - 2);
-            const int pyy = yc & 1, pxx = xc & 1;
-            int val[2];
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                const int mode = ch == 0 ? site.plus[pyy][pxx] : site.minus[pyy][pxx];
-                int v;
-                if (mode == 0) v = r0[xc];
-                else if (mode == 1) v = (r0[xc - 1] + r0[xc + 1] + 1) >> 1;
-                else if (mode == 2) v = (rm[xc] + rp[xc] + 1) >> 1;
-                else if (mode == 3) v = (rm[xc - 1] + rm[xc + 1] + rp[xc - 1] + rp[xc + 1] + 2) >> 2;
-                else v = (r0[xc - 1] + r0[xc + 1] + rm[xc] + rp[xc] + 2) >> 2;
-                val[ch] = v;
-            }
-            int diff = val[0] - val[1];
-            diff = diff < 0 ? 0 : diff;
-            wbits |= (uint32_t)(diff >= lb && diff <= 255) << b;
+        const uint32_t* rm = reinterpret_cast<const uint32_t*>(smem + (size_t)(yc - 1 - ry0) * p.srow);
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(smem + (size_t)(yc - ry0) * p.srow);
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(smem + (size_t)(yc + 1 - ry0) * p.srow);
+        const BayerProg pe = progs.g[yc & 1][0], po = progs.g[yc & 1][1];
+        uint16_t* trow = t16 + ((size_t)(y - ty0) * TW + 1) * 2;
+        if (bulk) {   // the loads that hold raw rows yc-1 .. yc+1
+            const int ca = (yc - 1 - ry0) / kLoadRows, cb = (yc + 1 - ry0) / kLoadRows;
+            mbar_wait(&bars[ca], 0);
+            if (cb != ca) mbar_wait(&bars[cb], 0);
         }
-        t[(size_t)(y - ty0) * TW + k + 1] = wbits;
+        for (int it = lane; it < items; it += 32) {
+            const int wi = it * 4;
+            const uint4 U = *reinterpret_cast<const uint4*>(rm + wi), Cc = *reinterpret_cast<const uint4*>(r0 + wi),
+                        D = *reinterpret_cast<const uint4*>(rp + wi);
+            const bool hasp = wi > 0, hasn = wi + 4 < nw;
+            const uint32_t u[6] = {hasp ? rm[wi - 1] : 0u, U.x, U.y, U.z, U.w, hasn ? rm[wi + 4] : 0u};
+            const uint32_t c[6] = {hasp ? r0[wi - 1] : 0u, Cc.x, Cc.y, Cc.z, Cc.w, hasn ? r0[wi + 4] : 0u};
+            const uint32_t d2[6] = {hasp ? rp[wi - 1] : 0u, D.x, D.y, D.z, D.w, hasn ? rp[wi + 4] : 0u};
+            uint32_t bits = 0;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                // words holding the bytes x-1 .. x+2 for x = 4m (pixels 4m, 4m+1) and for x = 4m+2 (pixels 4m+2, 4m+3)
+                const uint32_t ua = __funnelshift_l(u[m], u[m + 1], 8), ub = __funnelshift_r(u[m + 1], u[m + 2], 8);
+                const uint32_t ca = __funnelshift_l(c[m], c[m + 1], 8), cb = __funnelshift_r(c[m + 1], c[m + 2], 8);
+                const uint32_t da = __funnelshift_l(d2[m], d2[m + 1], 8), db = __funnelshift_r(d2[m + 1], d2[m + 2], 8);
+                auto pixel = [&](const BayerProg& g, uint32_t wu, uint32_t wc, uint32_t wd) -> uint32_t {
+                    int v = dp4a_us(wu, g.vu, dp4a_us(wc, g.vc, dp4a_us(wd, g.vd, g.v0)));
+                    if (g.kq) {   // warp-uniform (one row per warp)
+                        const int q = dp4a_us(wu, g.qu, dp4a_us(wc, g.qc, dp4a_us(wd, g.qd, g.rq)));
+                        v += (q >> g.kq) << g.ks;
+                    }
+                    return (uint32_t)v >> 31;   // 1 = below the threshold
+                };
+                bits |= pixel(pe, ua, ca, da) << (4 * m) | pixel(po, ua, ca, da) << (4 * m + 1) |
+                        pixel(pe, ub, cb, db) << (4 * m + 2) | pixel(po, ub, cb, db) << (4 * m + 3);
+            }
+            trow[it] = (uint16_t)(lb <= 0 ? 0xffffu : (lb > 255 ? 0u : ~bits));
+        }
+    }
+    __syncthreads();
+    // border columns: x = 0 shows x = 1, x = W-1 shows x = W-2 (after the row replicate, which the clamped row did)
+    for (int rr = tid; rr < cy1 - cy0; rr += NT) {
+        uint32_t* trow = t + (size_t)(cy0 + rr - ty0) * TW + 1;
+        uint32_t w0 = trow[0];
+        w0 = (w0 & ~1u) | ((w0 >> 1) & 1u);
+        trow[0] = w0;
+        const int xl = W - 1, xs = W - 2;
+        const uint32_t bit = (trow[xs >> 5] >> (xs & 31)) & 1u;
+        trow[xl >> 5] = (trow[xl >> 5] & ~(1u << (xl & 31))) | (bit << (xl & 31));
     }
     __syncthreads();
     close_and_store(p, t, d, frame, y0, nout, tid, NT);
@@ -494,6 +536,49 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
                 site.minus[py][px] = mode(b);
             }
     }
+    BayerProgs progs;
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            // weights of the interpolation patterns over (row -1/0/+1, column -1/0/+1), and their (shift, rounding)
+            auto weights = [](int mode, int w[3][3], int* k, int* r) {
+                for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) w[i][j] = 0;
+                switch (mode) {
+                    case 0: w[1][1] = 1; *k = 0; *r = 0; break;
+                    case 1: w[1][0] = w[1][2] = 1; *k = 1; *r = 1; break;
+                    case 2: w[0][1] = w[2][1] = 1; *k = 1; *r = 1; break;
+                    case 3: w[0][0] = w[0][2] = w[2][0] = w[2][2] = 1; *k = 2; *r = 2; break;
+                    default: w[1][0] = w[1][2] = w[0][1] = w[2][1] = 1; *k = 2; *r = 2; break;
+                }
+            };
+            int wp[3][3], wm[3][3], kp, rp, km, rm;
+            weights(site.plus[py][px], wp, &kp, &rp);
+            weights(site.minus[py][px], wm, &km, &rm);
+            const int lbv = L.lower_bound;
+            int V[3][3], Q[3][3];
+            BayerProg g;
+            memset(&g, 0, sizeof(g));
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { V[i][j] = 0; Q[i][j] = 0; }
+            if (km == 0) {
+                for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = wp[i][j] - (wm[i][j] << kp);
+                g.v0 = rp - (lbv << kp);
+            } else if (kp == 0) {
+                for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = (wp[i][j] << km) - wm[i][j];
+                g.v0 = -((lbv << km) - (1 << km) + rm + 1);
+            } else {
+                for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { V[i][j] = -wm[i][j]; Q[i][j] = wp[i][j]; }
+                g.v0 = -((lbv << km) - (1 << km) + rm + 1);
+                g.rq = rp; g.kq = kp; g.ks = km;
+            }
+            // byte lanes: even x sits at byte 1 of the shifted word (x-1, x, x+1, x+2), odd x at byte 2
+            auto pack = [&](const int row[3]) -> uint32_t {
+                uint32_t v = 0;
+                for (int j = 0; j < 3; ++j) v |= (uint32_t)(uint8_t)(int8_t)row[j] << (8 * (j + px));
+                return v;
+            };
+            g.vu = pack(V[0]); g.vc = pack(V[1]); g.vd = pack(V[2]);
+            g.qu = pack(Q[0]); g.qc = pack(Q[1]); g.qd = pack(Q[2]);
+            progs.g[py][px] = g;
+        }
     p.bayer = 1;
     p.gpr = p.WB;
     p.srow = (L.W + 15) & ~15;
@@ -501,18 +586,18 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
     p.contiguous = 0;
     int NT = env_int("RMCV_PIX_NT", 256);
     if (L.W < 3 || L.H < 3) return cudaErrorInvalidValue;
-    size_t raw_bytes = ((size_t)(BH + 2 * hl + 4) * p.srow + 15) & ~(size_t)15;
-    size_t smem = raw_bytes + 16 + (size_t)(BH + 2 * hl) * (p.WB + 2) * 4 + (size_t)(BH + 2 * hl - 2) * (p.WB + 2) * 4 + 256;
+    size_t raw_bytes = ((size_t)(BH + 2 * hl + 2) * p.srow + 15) & ~(size_t)15;
+    size_t smem = raw_bytes + 128 + (size_t)(BH + 2 * hl) * (p.WB + 2) * 4 + (size_t)(BH + 2 * hl - 2) * (p.WB + 2) * 4 + 256;
     while (smem > (size_t)max_smem && p.BH > 1) {
         p.BH = max(1, p.BH / 2); BH = p.BH;
         p.bands = (L.H + BH - 1) / BH;
-        raw_bytes = ((size_t)(BH + 2 * hl + 4) * p.srow + 15) & ~(size_t)15;
-        smem = raw_bytes + 16 + (size_t)(BH + 2 * hl) * (p.WB + 2) * 4 + (size_t)(BH + 2 * hl - 2) * (p.WB + 2) * 4 + 256;
+        raw_bytes = ((size_t)(BH + 2 * hl + 2) * p.srow + 15) & ~(size_t)15;
+        smem = raw_bytes + 128 + (size_t)(BH + 2 * hl) * (p.WB + 2) * 4 + (size_t)(BH + 2 * hl - 2) * (p.WB + 2) * 4 + 256;
     }
     const long long grid2 = (long long)L.batch * p.bands;
     cudaError_t e = cudaFuncSetAttribute(pixel_bayer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    pixel_bayer_kernel<<<(unsigned)grid2, NT, smem, st>>>(p, site);
+    pixel_bayer_kernel<<<(unsigned)grid2, NT, smem, st>>>(p, progs);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -6,7 +6,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -4 $OUT/pytest_gpu_$TAG.log
 python scripts/frame_timing.py > $OUT/frame_timing_$TAG.log 2>&1; echo "timing rc=$?"; tail -3 $OUT/frame_timing_$TAG.log
-python bench.py --steps 5 --warmup 3 --batch 1024 --no-cpu --e2e-steps 1 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"
+python bench.py --steps 5 --warmup 3 --batch 1024 --no-cpu --no-extras --e2e-steps 1 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"
 python - <<PY
 import json
 try:

@@ -2,7 +2,7 @@
 # experiment runner: each "run TAG [bench args --] ENV..." runs the short bench with that environment
 OUT=gpurun_out; mkdir -p $OUT
 run() { tag=$1; shift; extra=""; if [ "$1" = "--args" ]; then extra="$2"; shift 2; fi
-  env "$@" python bench.py --steps 5 --warmup 3 --batch 1024 --no-cpu --e2e-steps 1 $extra > $OUT/exp_$tag.json 2> $OUT/exp_$tag.err
+  env "$@" python bench.py --steps 5 --warmup 3 --batch 1024 --no-cpu --no-extras --e2e-steps 1 $extra > $OUT/exp_$tag.json 2> $OUT/exp_$tag.err
   python - <<PY
 import json
 try:

@@ -78,5 +78,25 @@ def full(path):
         print()
 
 
+def traffic(path, frames_per_launch):
+    """profiles/pixel_traffic.json for bench.py: DRAM bytes per frame of the pixel kernel from one `--set full` capture."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, r = rows[0], rows[1], rows[2]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    def val(name):
+        i = hdr.index(name)
+        return float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
+    rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    grid = r[hdr.index("Grid Size")]
+    print(json.dumps({"source": path, "kernel": r[hdr.index("Kernel Name")], "grid": grid, "frames_per_launch": int(frames_per_launch),
+                      "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_frame": (rd + wr) / float(frames_per_launch),
+                      "gpu_time_us": float(r[hdr.index("gpu__time_duration.sum")].replace(",", ""))}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
