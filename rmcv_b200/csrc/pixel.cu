@@ -297,7 +297,53 @@ struct BayerProg {
     int32_t v0;            // constant of V
     int32_t rq, kq, ks;
 };
-struct BayerProgs { BayerProg g[2][2]; };  // [row parity][x parity]
+// Shape of a pixel program, so that zero coefficient words cost nothing: 0 = V over all three rows, no Q (a sampled
+// site against the four diagonals); 1 = Q on the centre row, V on the rows above/below, pair rounding (kq = ks = 1: a
+// green site between two `plus` samples of its row); 2 = Q on the rows above/below, V on the centre row (a green site
+// between two `plus` samples of its column); 3 = generic.
+struct BayerProgs { BayerProg g[2][2]; int type[2][2]; };  // [row parity][x parity]
+
+template <int T>
+__device__ __forceinline__ int bayer_pixel(const BayerProg& g, uint32_t wu, uint32_t wc, uint32_t wd) {
+    if (T == 0) return dp4a_us(wu, g.vu, dp4a_us(wc, g.vc, dp4a_us(wd, g.vd, g.v0)));
+    if (T == 1) return dp4a_us(wu, g.vu, dp4a_us(wd, g.vd, g.v0)) + (dp4a_us(wc, g.qc, g.rq) & ~1);
+    if (T == 2) return dp4a_us(wc, g.vc, g.v0) + (dp4a_us(wu, g.qu, dp4a_us(wd, g.qd, g.rq)) & ~1);
+    int v = dp4a_us(wu, g.vu, dp4a_us(wc, g.vc, dp4a_us(wd, g.vd, g.v0)));
+    if (g.kq) v += (dp4a_us(wu, g.qu, dp4a_us(wc, g.qc, dp4a_us(wd, g.qd, g.rq))) >> g.kq) << g.ks;
+    return v;
+}
+
+// Threshold bits of one raw row: lanes over 16-pixel items.  Odd-x pixels sit at byte 1 of an aligned word (their
+// neighbours at bytes 0 and 2), even-x pixels at byte 2; the pixels at bytes 3 and 0 use the word shifted by 16 bits,
+// where they sit at bytes 1 and 2 again.  TE / TO = program shapes of the even-x / odd-x pixels.
+template <int TE, int TO>
+__device__ __forceinline__ void bayer_row(const uint32_t* rm, const uint32_t* r0, const uint32_t* rp, int nw, int items, int lane,
+                                          const BayerProg& pe, const BayerProg& po, uint16_t* trow, uint32_t force_or,
+                                          uint32_t force_and) {
+    for (int it = lane; it < items; it += 32) {
+        const int wi = it * 4;
+        const uint4 U = *reinterpret_cast<const uint4*>(rm + wi), C = *reinterpret_cast<const uint4*>(r0 + wi),
+                    D = *reinterpret_cast<const uint4*>(rp + wi);
+        const bool hasp = wi > 0, hasn = wi + 4 < nw;
+        const uint32_t u[6] = {hasp ? rm[wi - 1] : 0u, U.x, U.y, U.z, U.w, hasn ? rm[wi + 4] : 0u};
+        const uint32_t c[6] = {hasp ? r0[wi - 1] : 0u, C.x, C.y, C.z, C.w, hasn ? r0[wi + 4] : 0u};
+        const uint32_t d[6] = {hasp ? rp[wi - 1] : 0u, D.x, D.y, D.z, D.w, hasn ? rp[wi + 4] : 0u};
+        uint32_t nb = 0;  // sign bits (1 = below the threshold), pixel 15 first so that pixel 0 lands in bit 0
+#pragma unroll
+        for (int m = 3; m >= 0; --m) {
+            // su/sc/sd: bytes (w[m].2, w[m].3, w[m+1].0, w[m+1].1) -> pixel 4m+3 (odd x) and pixel 4m+4 (even x, next group)
+            const uint32_t su = __funnelshift_r(u[m + 1], u[m + 2], 16), sc = __funnelshift_r(c[m + 1], c[m + 2], 16),
+                           sd = __funnelshift_r(d[m + 1], d[m + 2], 16);
+            nb = __funnelshift_l((uint32_t)bayer_pixel<TO>(po, su, sc, sd), nb, 1);                    // pixel 4m+3
+            nb = __funnelshift_l((uint32_t)bayer_pixel<TE>(pe, u[m + 1], c[m + 1], d[m + 1]), nb, 1);  // pixel 4m+2
+            nb = __funnelshift_l((uint32_t)bayer_pixel<TO>(po, u[m + 1], c[m + 1], d[m + 1]), nb, 1);  // pixel 4m+1
+            const uint32_t tu = __funnelshift_r(u[m], u[m + 1], 16), tc = __funnelshift_r(c[m], c[m + 1], 16),
+                           td = __funnelshift_r(d[m], d[m + 1], 16);
+            nb = __funnelshift_l((uint32_t)bayer_pixel<TE>(pe, tu, tc, td), nb, 1);                    // pixel 4m
+        }
+        trow[it] = (uint16_t)((~nb | force_or) & force_and);
+    }
+}
 
 __global__ void __launch_bounds__(512) pixel_bayer_kernel(const PixelParams p, const BayerProgs progs) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -349,12 +395,13 @@ __global__ void __launch_bounds__(512) pixel_bayer_kernel(const PixelParams p, c
         __syncthreads();
     }
     // threshold bits: one warp per row (the pixel programs depend on the row parity only), lanes over 16-pixel items;
-    // per pixel three dp4a (six at green sites) on funnel-shifted words.  Border rows replicate the neighbouring
-    // interior row (recomputed), border columns are fixed up afterwards.
+    // per pixel three dp4a on aligned / 16-bit-shifted words.  Border rows replicate the neighbouring interior row
+    // (recomputed), border columns are fixed up afterwards.
     const int lb = p.lb;
     const int nw = p.srow >> 2;  // 32-bit words per shared-memory row
     const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
     const int items = (W + 15) >> 4;
+    const uint32_t force_or = lb <= 0 ? 0xffffu : 0u, force_and = lb > 255 ? 0u : 0xffffu;
     uint16_t* t16 = reinterpret_cast<uint16_t*>(t);
     for (int rr = warp; rr < cy1 - cy0; rr += nwarps) {
         const int y = cy0 + rr;
@@ -363,40 +410,19 @@ __global__ void __launch_bounds__(512) pixel_bayer_kernel(const PixelParams p, c
         const uint32_t* r0 = reinterpret_cast<const uint32_t*>(smem + (size_t)(yc - ry0) * p.srow);
         const uint32_t* rp = reinterpret_cast<const uint32_t*>(smem + (size_t)(yc + 1 - ry0) * p.srow);
         const BayerProg pe = progs.g[yc & 1][0], po = progs.g[yc & 1][1];
+        const int te = progs.type[yc & 1][0], to = progs.type[yc & 1][1];
         uint16_t* trow = t16 + ((size_t)(y - ty0) * TW + 1) * 2;
         if (bulk) {   // the loads that hold raw rows yc-1 .. yc+1
             const int ca = (yc - 1 - ry0) / kLoadRows, cb = (yc + 1 - ry0) / kLoadRows;
             mbar_wait(&bars[ca], 0);
             if (cb != ca) mbar_wait(&bars[cb], 0);
         }
-        for (int it = lane; it < items; it += 32) {
-            const int wi = it * 4;
-            const uint4 U = *reinterpret_cast<const uint4*>(rm + wi), Cc = *reinterpret_cast<const uint4*>(r0 + wi),
-                        D = *reinterpret_cast<const uint4*>(rp + wi);
-            const bool hasp = wi > 0, hasn = wi + 4 < nw;
-            const uint32_t u[6] = {hasp ? rm[wi - 1] : 0u, U.x, U.y, U.z, U.w, hasn ? rm[wi + 4] : 0u};
-            const uint32_t c[6] = {hasp ? r0[wi - 1] : 0u, Cc.x, Cc.y, Cc.z, Cc.w, hasn ? r0[wi + 4] : 0u};
-            const uint32_t d2[6] = {hasp ? rp[wi - 1] : 0u, D.x, D.y, D.z, D.w, hasn ? rp[wi + 4] : 0u};
-            uint32_t bits = 0;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                // words holding the bytes x-1 .. x+2 for x = 4m (pixels 4m, 4m+1) and for x = 4m+2 (pixels 4m+2, 4m+3)
-                const uint32_t ua = __funnelshift_l(u[m], u[m + 1], 8), ub = __funnelshift_r(u[m + 1], u[m + 2], 8);
-                const uint32_t ca = __funnelshift_l(c[m], c[m + 1], 8), cb = __funnelshift_r(c[m + 1], c[m + 2], 8);
-                const uint32_t da = __funnelshift_l(d2[m], d2[m + 1], 8), db = __funnelshift_r(d2[m + 1], d2[m + 2], 8);
-                auto pixel = [&](const BayerProg& g, uint32_t wu, uint32_t wc, uint32_t wd) -> uint32_t {
-                    int v = dp4a_us(wu, g.vu, dp4a_us(wc, g.vc, dp4a_us(wd, g.vd, g.v0)));
-                    if (g.kq) {   // warp-uniform (one row per warp)
-                        const int q = dp4a_us(wu, g.qu, dp4a_us(wc, g.qc, dp4a_us(wd, g.qd, g.rq)));
-                        v += (q >> g.kq) << g.ks;
-                    }
-                    return (uint32_t)v >> 31;   // 1 = below the threshold
-                };
-                bits |= pixel(pe, ua, ca, da) << (4 * m) | pixel(po, ua, ca, da) << (4 * m + 1) |
-                        pixel(pe, ub, cb, db) << (4 * m + 2) | pixel(po, ub, cb, db) << (4 * m + 3);
-            }
-            trow[it] = (uint16_t)(lb <= 0 ? 0xffffu : (lb > 255 ? 0u : ~bits));
-        }
+        // warp-uniform dispatch on the row's pair of program shapes
+        if (te == 0 && to == 1) bayer_row<0, 1>(rm, r0, rp, nw, items, lane, pe, po, trow, force_or, force_and);
+        else if (te == 1 && to == 0) bayer_row<1, 0>(rm, r0, rp, nw, items, lane, pe, po, trow, force_or, force_and);
+        else if (te == 2 && to == 0) bayer_row<2, 0>(rm, r0, rp, nw, items, lane, pe, po, trow, force_or, force_and);
+        else if (te == 0 && to == 2) bayer_row<0, 2>(rm, r0, rp, nw, items, lane, pe, po, trow, force_or, force_and);
+        else bayer_row<3, 3>(rm, r0, rp, nw, items, lane, pe, po, trow, force_or, force_and);
     }
     __syncthreads();
     // border columns: x = 0 shows x = 1, x = W-1 shows x = W-2 (after the row replicate, which the clamped row did)
@@ -569,15 +595,20 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
                 g.v0 = -((lbv << km) - (1 << km) + rm + 1);
                 g.rq = rp; g.kq = kp; g.ks = km;
             }
-            // byte lanes: even x sits at byte 1 of the shifted word (x-1, x, x+1, x+2), odd x at byte 2
+            // byte lanes: an odd-x pixel sits at byte 1 of its word (neighbours at bytes 0 and 2), an even-x pixel at byte 2
             auto pack = [&](const int row[3]) -> uint32_t {
                 uint32_t v = 0;
-                for (int j = 0; j < 3; ++j) v |= (uint32_t)(uint8_t)(int8_t)row[j] << (8 * (j + px));
+                for (int j = 0; j < 3; ++j) v |= (uint32_t)(uint8_t)(int8_t)row[j] << (8 * (j + (px == 0 ? 1 : 0)));
                 return v;
             };
             g.vu = pack(V[0]); g.vc = pack(V[1]); g.vd = pack(V[2]);
             g.qu = pack(Q[0]); g.qc = pack(Q[1]); g.qd = pack(Q[2]);
             progs.g[py][px] = g;
+            int type = 3;
+            if (g.kq == 0) type = 0;
+            else if (g.kq == 1 && g.ks == 1 && !g.vc && !g.qu && !g.qd) type = 1;
+            else if (g.kq == 1 && g.ks == 1 && !g.vu && !g.vd && !g.qc) type = 2;
+            progs.type[py][px] = type;
         }
     p.bayer = 1;
     p.gpr = p.WB;
