@@ -137,15 +137,6 @@ __device__ __forceinline__ void pointer_jump(int32_t* link, int first, int end, 
     }
 }
 
-// Is background pixel (x,yy) part of a hole (background not connected to the image border)?
-__device__ __forceinline__ bool is_hole(const Runs& f, int x, int yy) {
-    if (x <= 0 || yy <= 0 || x >= f.W - 1 || yy >= f.H - 1) return false;
-    const int2 rr = f.rows[yy];
-    const int r = upper_bound_xs(f.run_x, rr.x, rr.y, x);  // the gap lies between run r-1 and run r
-    if (r == rr.x || r == rr.y) return false;                // touches the left / right border
-    return f.glink[r + 1] != 0;
-}
-
 // ------------------------------------------------------------------------------------------ K_L: labelling
 // One CTA per frame; runs, links and labels live in shared memory (frames with more runs than fit use global arrays).
 struct LabelParams {
