@@ -72,6 +72,7 @@ struct PixelParams {
     int srow;            // shared-memory row stride in bytes
     int gpr;             // 16-pixel groups per row (BGR) / per row (Bayer)
     int halo;            // threshold-row halo of the close: 2
+    uint32_t inv_wb, inv_gpr16;  // floor(2^32 / n) + 1 for n = WB / ceil(W/16): slot / n == umulhi(slot, inv); 0 when n == 1
     uint32_t coef[6];    // dp4a coefficient words (signed bytes) for the 4 pixels of a 12-byte group
     int acc0;            // -lower_bound (or the constants that force all-0 / all-1)
     int contiguous;      // pitch == row bytes: a chunk is one bulk copy
@@ -108,74 +109,108 @@ __host__ __device__ inline size_t pix_smem_bytes(int S, int RC, int srow, int BH
 }
 
 // ------------------------------------------------------------------------------------------ morphology + stores
-// t: (nout+2*hl) x TW threshold words (row 0 <-> image row y0-hl), zero outside the image; hl = p.halo.
+// t: (nout+4) x TW threshold words (row 0 <-> image row y0-2), zero outside the image.
 // Writes the final mask of rows [y0, y0+nout) to global as bytes and as bit words (the labelling stages read the bits).
+// Both passes are separable (3x1 on the bit row, then 1x3 down the rows) and a thread walks DOWN one word column over a
+// segment of rows, so every word is loaded once and the row-combined value slides through three registers.
 __device__ __forceinline__ void close_and_store(const PixelParams& p, uint32_t* t, uint32_t* d, int frame, int y0,
                                                 int nout, int tid, int NT) {
-    const int WB = p.WB, TW = WB + 2, H = p.H, hl = p.halo;
-    const int e = hl - 2;  // rows of final mask kept above and below the band (0 or 1)
+    const int WB = p.WB, TW = WB + 2, H = p.H;
     const uint32_t valid = p.last_valid;
-    // ---- dilate: rows y0-hl+1 .. y0+nout+hl-2  (outside the image: all ones so that the erode ignores them)
-    for (Iter2D it(tid, NT, WB); it.r < nout + 2 * hl - 2; it.next()) {
-        const int i = it.r, k = it.c;
-        const int y = y0 - hl + 1 + i;
-        uint32_t dv = 0xFFFFFFFFu;
-        if (y >= 0 && y < H) {
-            const uint32_t* a = t + (size_t)i * TW + k;  // padded column k  <-> word k-1
-            uint32_t vm = a[0] | a[TW] | a[2 * TW];
-            uint32_t v0 = a[1] | a[TW + 1] | a[2 * TW + 1];
-            uint32_t vp = a[2] | a[TW + 2] | a[2 * TW + 2];
-            if (k == WB - 1) v0 &= valid;
-            if (k + 1 == WB - 1) vp &= valid;
-            dv = v0 | (v0 << 1) | (vm >> 31) | (v0 >> 1) | (vp << 31);
-            if (k == WB - 1) dv |= ~valid;
+    const int nseg = NT >= WB ? NT / WB : 1;      // row segments per word column
+    auto col_of = [&](int slot, int* seg) -> int {  // slot -> (segment, word column); one umulhi instead of a division
+        const int sg = p.inv_wb ? (int)__umulhi((uint32_t)slot, p.inv_wb) : slot;
+        *seg = sg;
+        return slot - sg * WB;
+    };
+    // ---- dilate: rows y0-1 .. y0+nout (outside the image: all ones so that the erode ignores them)
+    {
+        const int nd = nout + 2, per = (nd + nseg - 1) / nseg;
+        for (int slot = tid; slot < WB * nseg; slot += NT) {
+            int seg;
+            const int k = col_of(slot, &seg);
+            const int i0 = seg * per, i1 = min(nd, i0 + per);
+            if (i0 >= i1) continue;
+            const bool last = k == WB - 1, prelast = k + 1 == WB - 1;
+            auto hrow = [&](int ti) -> uint32_t {   // 3x1 OR of threshold row ti at word k (padded column k+1)
+                const uint32_t* a = t + (size_t)ti * TW + k;
+                uint32_t left = a[0], mid = a[1], right = a[2];
+                if (last) mid &= valid;
+                if (prelast) right &= valid;
+                return mid | (mid << 1) | (left >> 31) | (mid >> 1) | (right << 31);
+            };
+            uint32_t h0 = hrow(i0), h1 = hrow(i0 + 1);
+            uint32_t* dp = d + (size_t)i0 * TW + k + 1;
+            for (int i = i0; i < i1; ++i, dp += TW) {
+                const uint32_t h2 = hrow(i + 2);
+                const int y = y0 - 1 + i;
+                uint32_t dv = h0 | h1 | h2;
+                if (last) dv |= ~valid;
+                if (y < 0 || y >= H) dv = 0xFFFFFFFFu;
+                dp[0] = dv;
+                if (k == 0) dp[-1] = 0xFFFFFFFFu;
+                if (last) dp[1] = 0xFFFFFFFFu;
+                h0 = h1; h1 = h2;
+            }
         }
-        d[(size_t)i * TW + k + 1] = dv;
-        if (k == 0) d[(size_t)i * TW] = 0xFFFFFFFFu;
-        if (k == WB - 1) d[(size_t)i * TW + TW - 1] = 0xFFFFFFFFu;
     }
     __syncthreads();
-    // ---- erode: rows y0-e .. y0+nout-1+e; result into mm (compact [nout+2e][WB], zero outside the image); the band's
-    // own rows also go to the global bit mask
-    uint32_t* mm = t;
-    uint32_t* m = mm + (size_t)e * WB;  // row 0 of m <-> image row y0
-    uint32_t* gbits = p.bits + ((size_t)frame * H + y0) * WB;
-    for (Iter2D it(tid, NT, WB); it.r < nout + 2 * e; it.next()) {
-        const int j = it.r, k = it.c;
-        const int y = y0 - e + j;
-        uint32_t mv = 0u;
-        if (y >= 0 && y < H) {
-            const uint32_t* a = d + (size_t)j * TW + k;
-            uint32_t am = a[0] & a[TW] & a[2 * TW];
-            uint32_t a0 = a[1] & a[TW + 1] & a[2 * TW + 1];
-            uint32_t ap = a[2] & a[TW + 2] & a[2 * TW + 2];
-            mv = a0 & ((a0 << 1) | (am >> 31)) & ((a0 >> 1) | (ap << 31));
-            if (k == WB - 1) mv &= valid;
+    // ---- erode: rows y0 .. y0+nout-1; result into m (compact [nout][WB]) and to the global bit mask
+    uint32_t* m = t;   // t and m alias: every thread reads d only and writes m; t was last read before the barrier
+    {
+        uint32_t* gbits = p.bits + ((size_t)frame * H + y0) * WB;
+        const int per = (nout + nseg - 1) / nseg;
+        for (int slot = tid; slot < WB * nseg; slot += NT) {
+            int seg;
+            const int k = col_of(slot, &seg);
+            const int j0 = seg * per, j1 = min(nout, j0 + per);
+            if (j0 >= j1) continue;
+            const bool last = k == WB - 1;
+            auto hrow = [&](int di) -> uint32_t {   // 3x1 AND of dilated row di at word k
+                const uint32_t* a = d + (size_t)di * TW + k;
+                const uint32_t left = a[0], mid = a[1], right = a[2];
+                return mid & ((mid << 1) | (left >> 31)) & ((mid >> 1) | (right << 31));
+            };
+            uint32_t h0 = hrow(j0), h1 = hrow(j0 + 1);
+            uint32_t* mp = m + (size_t)j0 * WB + k;
+            uint32_t* gp = gbits + (size_t)j0 * WB + k;
+            for (int j = j0; j < j1; ++j, mp += WB, gp += WB) {
+                const uint32_t h2 = hrow(j + 2);
+                uint32_t mv = h0 & h1 & h2;
+                if (last) mv &= valid;
+                mp[0] = mv;
+                gp[0] = mv;
+                h0 = h1; h1 = h2;
+            }
         }
-        // t and mm alias: every thread reads d only and writes mm[j*WB+k]; t was last read before the barrier
-        mm[(size_t)j * WB + k] = mv;
-        if (j >= e && j < nout + e) gbits[(size_t)(j - e) * WB + k] = mv;
     }
     __syncthreads();
-    // ---- byte mask: one 16-byte store per 16 pixels
+    // ---- byte mask: one 16-byte store per 16 pixels, a thread walks down one 16-pixel column
     if (p.mask != nullptr) {
         const uint16_t* m16 = reinterpret_cast<const uint16_t*>(m);
         const int gpr16 = (p.W + 15) >> 4;
+        const int nsg = NT >= gpr16 ? NT / gpr16 : 1;
         uint8_t* gmask = p.mask + (size_t)frame * p.mask_frame_stride + (size_t)y0 * p.mask_pitch;
-        for (Iter2D it(tid, NT, gpr16); it.r < nout; it.next()) {
-            const int j = it.r, g = it.c;
-            const uint32_t b = m16[(size_t)j * WB * 2 + g];
-            uint8_t* dst = gmask + (size_t)j * p.mask_pitch + (size_t)g * 16;
-            uint4 o;
-            o.x = expand4(b & 15u);
-            o.y = expand4((b >> 4) & 15u);
-            o.z = expand4((b >> 8) & 15u);
-            o.w = expand4(b >> 12);
-            if (p.mask_vec && g * 16 + 16 <= p.W) {
-                __stcs(reinterpret_cast<uint4*>(dst), o);
-            } else {
-                const uint32_t w[4] = {o.x, o.y, o.z, o.w};
-                for (int q = 0; q < 16 && g * 16 + q < p.W; ++q) dst[q] = (uint8_t)(w[q >> 2] >> ((q & 3) * 8));
+        for (int slot = tid; slot < gpr16 * nsg; slot += NT) {
+            const int sg = p.inv_gpr16 ? (int)__umulhi((uint32_t)slot, p.inv_gpr16) : slot;
+            const int g = slot - sg * gpr16;
+            const bool vec = p.mask_vec && g * 16 + 16 <= p.W;
+            uint8_t* dst = gmask + (size_t)sg * p.mask_pitch + (size_t)g * 16;
+            const size_t dstep = (size_t)nsg * p.mask_pitch;
+            const uint16_t* src = m16 + (size_t)sg * WB * 2 + g;
+            for (int j = sg; j < nout; j += nsg, dst += dstep, src += (size_t)nsg * WB * 2) {
+                const uint32_t b = *src;
+                uint4 o;
+                o.x = expand4(b & 15u);
+                o.y = expand4((b >> 4) & 15u);
+                o.z = expand4((b >> 8) & 15u);
+                o.w = expand4(b >> 12);
+                if (vec) {
+                    __stcs(reinterpret_cast<uint4*>(dst), o);
+                } else {
+                    const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+                    for (int q = 0; q < 16 && g * 16 + q < p.W; ++q) dst[q] = (uint8_t)(w[q >> 2] >> ((q & 3) * 8));
+                }
             }
         }
     }
@@ -458,6 +493,11 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
     p.lb = L.lower_bound;
     p.halo = 2;
     const int hl = p.halo;
+    {
+        const unsigned g16 = (unsigned)((L.W + 15) / 16);
+        p.inv_wb = p.WB > 1 ? (uint32_t)((1ull << 32) / (unsigned)p.WB) + 1u : 0u;
+        p.inv_gpr16 = g16 > 1 ? (uint32_t)((1ull << 32) / g16) + 1u : 0u;
+    }
 
     // band height: tall bands amortise the 4 halo rows; small batches need more, shorter bands to fill 148 SMs
     int BH = env_int("RMCV_PIX_BH", 0);
