@@ -272,6 +272,26 @@ int rmcv_min_area_rects(rmcv_ctx* ctx, const int32_t* xy, const int32_t* offsets
  * right == n (one past the end, undefined behaviour in C++); here right >= n yields 0. */
 int rmcv_lightblob_overlap(rmcv_ctx* ctx, const rmcv_lightblob* blobs, int n_blobs, int left, int right, int* overlap);
 
+/* ---- f1 (next row): rm::solve_PnP per armour -------------------------------------------------- */
+/* Pose of one armour: cv::solvePnP(SOLVEPNP_IPPE_SQUARE) on armour.vertices against the canonical square of the given
+ * size (src/mobility.cpp:166-190), and tvec moved by the caller's 4x4 camera -> world transform (executable/main.cpp:
+ * 186-192; position == tvec when no transform is given).  88 bytes. */
+typedef struct rmcv_pose {
+    double rvec[3];       /* Rodrigues rotation vector                                         */
+    double tvec[3];       /* translation in the units of exact_w / exact_h                     */
+    double position[3];   /* cam2world * [tvec; 1]                                             */
+    double reproj_err;    /* sum of squared reprojection errors, normalised image coordinates  */
+    int32_t ok;           /* 0: the four image points are collinear                            */
+    int32_t pad;
+} rmcv_pose;
+
+/* camera_matrix: 3x3 row-major; dist_coeffs: k1, k2, p1, p2, k3 (NULL = none); exact_w must equal exact_h
+ * (IPPE_SQUARE); roi_x/roi_y are added to the image points (the reference's ROI offset); cam2world: 4x4 row-major
+ * or NULL.  Host pointers, synchronous. */
+int rmcv_solve_pnp(rmcv_ctx* ctx, const rmcv_armour* armours, int n_armours, const double camera_matrix[9],
+                   const double dist_coeffs[5], float exact_w, float exact_h, float roi_x, float roi_y,
+                   const double* cam2world, rmcv_pose* poses);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* CUDA-event timing of the stages of detect/extract calls (on the streams that run them). */
 enum {

@@ -358,6 +358,31 @@ inline bool LightBlobOverlap(const std::vector<lightblob>& lightBlobs, int leftI
     return res != 0;
 }
 
+#if defined(RMCV_SHIM_WITH_REFERENCE)
+// rm::solve_PnP — include/mobility.h:106-108, src/mobility.cpp:166-190 (needs cv::Mat of doubles: reference build only).
+inline std::tuple<cv::Mat, cv::Mat> solve_PnP(const cv::Point2f points_image[4], cv::InputArray cameraMatrix,
+                                              cv::InputArray distortionFactor, const cv::Size2f& exactSize,
+                                              const cv::Rect& ROI = {0, 0, 0, 0}) {
+    gpu::context& gc = gpu::default_context();
+    rmcv_ctx* ctx = gc.get(1, 1);
+    rmcv_armour a;
+    std::memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 4; ++i) { a.vertices[i][0] = points_image[i].x; a.vertices[i][1] = points_image[i].y; }
+    cv::Mat K, D;
+    cameraMatrix.getMat().convertTo(K, CV_64F);
+    distortionFactor.getMat().convertTo(D, CV_64F);
+    double dist[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < 5 && i < (int)D.total(); ++i) dist[i] = D.ptr<double>()[i];
+    cv::Mat Kc = K.isContinuous() ? K : K.clone();
+    rmcv_pose pose;
+    gc.check(rmcv_solve_pnp(ctx, &a, 1, Kc.ptr<double>(), dist, exactSize.width, exactSize.height, (float)ROI.x, (float)ROI.y,
+                            nullptr, &pose), "rmcv_solve_pnp");
+    cv::Mat rvec = (cv::Mat_<double>(3, 1) << pose.rvec[0], pose.rvec[1], pose.rvec[2]);
+    cv::Mat tvec = (cv::Mat_<double>(3, 1) << pose.tvec[0], pose.tvec[1], pose.tvec[2]);
+    return {rvec, tvec};
+}
+#endif
+
 namespace gpu {
 // Fused single call: image -> positives + armours without materialising contours on the host.
 inline detection detect(const cv::Mat& image, const rmcv_params& prm, cv::Mat* binary = nullptr) {

@@ -428,6 +428,36 @@ def lightblob_overlap(blobs: Sequence[LightBlob], left: int, right: int) -> bool
     return False
 
 
+# --------------------------------------------------------------------------- f1: rm::solve_PnP (next row)
+#: camera intrinsics of the reference's only caller, executable/main.cpp:8-14 (float literals stored into double Mats)
+MAIN_CAMMAT = np.array([[f32(1782.672144409928), 0.0, f32(598.8983414505224)],
+                        [0.0, f32(1783.860175007369), f32(523.4209809658056)],
+                        [0.0, 0.0, 1.0]], np.float64)
+MAIN_DISCOF = np.array([f32(-0.03436366268485048), f32(0.1953669264956857), f32(0.0001485060439399386),
+                        f32(-0.003814875777013483), f32(-0.3181808766352414)], np.float64)
+
+
+def solve_pnp(points_image, camera_matrix=MAIN_CAMMAT, dist_coeffs=MAIN_DISCOF, exact_size=(27.0, 27.0), roi=(0, 0)):
+    """rm::solve_PnP, src/mobility.cpp:166-190: cv::solvePnP(SOLVEPNP_IPPE_SQUARE) on the four armour vertices
+    (points 1, 2, 3, 0 against the canonical square).  Returns (rvec[3], tvec[3]) as float64."""
+    w, h = f32(exact_size[0]), f32(exact_size[1])
+    obj = np.array([[-w / f32(2), h / f32(2), 0], [w / f32(2), h / f32(2), 0],
+                    [w / f32(2), -h / f32(2), 0], [-w / f32(2), -h / f32(2), 0]], np.float32)
+    p = np.asarray(points_image, np.float32).reshape(4, 2)
+    off = np.array([f32(roi[0]), f32(roi[1])], np.float32)
+    coord = np.stack([p[1] + off, p[2] + off, p[3] + off, p[0] + off]).astype(np.float32)
+    ok, rvec, tvec = cv2.solvePnP(obj, coord, np.asarray(camera_matrix, np.float64), np.asarray(dist_coeffs, np.float64),
+                                  flags=cv2.SOLVEPNP_IPPE_SQUARE)
+    assert ok
+    return rvec.ravel().astype(np.float64), tvec.ravel().astype(np.float64)
+
+
+def camera_to_world(tvec, cam2world):
+    """executable/main.cpp:186-192: world = M * [tvec; 1] for a 4x4 homogeneous transform M."""
+    v = np.asarray(cam2world, np.float64).reshape(4, 4) @ np.array([tvec[0], tvec[1], tvec[2], 1.0])
+    return v[:3]
+
+
 # --------------------------------------------------------------------------- whole path + derived oracles
 @dataclass
 class FrameResult:

@@ -60,6 +60,12 @@ class Results(C.Structure):
                 ("blobs", C.POINTER(LightBlob)), ("armours", C.POINTER(Armour))]
 
 
+class Pose(C.Structure):
+    _fields_ = [("rvec", C.c_double * 3), ("tvec", C.c_double * 3), ("position", C.c_double * 3), ("reproj_err", C.c_double),
+                ("ok", C.c_int32), ("pad", C.c_int32)]
+
+
+assert C.sizeof(Pose) == 88
 assert C.sizeof(LightBlob) == 56 and C.sizeof(Armour) == 112 and C.sizeof(ContourInfo) == 72 and C.sizeof(FrameInfo) == 32
 
 _vp, _sz, _i, _u8p = C.c_void_p, C.c_size_t, C.c_int, C.c_void_p
@@ -103,6 +109,7 @@ PROTOTYPES = {
                                               _u8p, _sz, _i, _i, _i, _vp, _i, C.POINTER(C.c_int)]),
     "rmcv_min_area_rects": (C.c_int, [_vp, _vp, _vp, _i, _vp]),
     "rmcv_lightblob_overlap": (C.c_int, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_int)]),
+    "rmcv_solve_pnp": (C.c_int, [_vp, _vp, _i, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, _vp, _vp]),
     "rmcv_profile_enable": (C.c_int, [_vp, _i]),
     "rmcv_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), _i]),
     "rmcv_timer_start": (C.c_int, [_vp]),

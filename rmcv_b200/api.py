@@ -116,6 +116,18 @@ class Armour:  # rm::armour public geometry, include/core.h:110-112
         ve = np.array([[a.vertices[k][0], a.vertices[k][1]] for k in range(4)], np.float32)
         return Armour(ic, ve, tuple(float(x) for x in a.bounding_box), int(a.i), int(a.j), tuple(float(g) for g in a.gates))
 
+    def to_c(self) -> A.Armour:
+        a = A.Armour()
+        for k in range(4):
+            a.icon[k][0], a.icon[k][1] = float(self.icon[k][0]), float(self.icon[k][1])
+            a.vertices[k][0], a.vertices[k][1] = float(self.vertices[k][0]), float(self.vertices[k][1])
+        for k in range(4):
+            a.bounding_box[k] = float(self.bounding_box[k])
+        a.i, a.j = int(self.i), int(self.j)
+        for k in range(6):
+            a.gates[k] = float(self.gates[k]) if k < len(self.gates) else 0.0
+        return a
+
 
 @dataclass
 class ContourInfo:
@@ -449,6 +461,24 @@ class Context:
         out = C.c_int()
         self._check(self.lib.rmcv_lightblob_overlap(self.h, arr, n, left, right, C.byref(out)), "rmcv_lightblob_overlap")
         return bool(out.value)
+
+
+    # -- f1: rm::solve_PnP
+    def solve_pnp(self, armours: Sequence[Armour], camera_matrix, dist_coeffs, exact_size=(27.0, 27.0), roi=(0.0, 0.0),
+                  cam2world=None):
+        """rm::solve_PnP for every armour -> list of (rvec[3], tvec[3], position[3], ok)."""
+        n = len(armours)
+        if n == 0:
+            return []
+        arr = (A.Armour * n)(*[a.to_c() for a in armours])
+        K = np.ascontiguousarray(np.asarray(camera_matrix, np.float64).reshape(9))
+        D = None if dist_coeffs is None else np.ascontiguousarray(np.asarray(dist_coeffs, np.float64).reshape(5))
+        M = None if cam2world is None else np.ascontiguousarray(np.asarray(cam2world, np.float64).reshape(16))
+        out = (A.Pose * n)()
+        self._check(self.lib.rmcv_solve_pnp(self.h, arr, n, K.ctypes.data, None if D is None else D.ctypes.data,
+                                            float(exact_size[0]), float(exact_size[1]), float(roi[0]), float(roi[1]),
+                                            None if M is None else M.ctypes.data, out), "rmcv_solve_pnp")
+        return [(np.array(o.rvec[:]), np.array(o.tvec[:]), np.array(o.position[:]), bool(o.ok)) for o in out]
 
 
 # --------------------------------------------------------------------------------------------- rm:: mirror

@@ -943,6 +943,28 @@ int rmcv_lightblob_overlap(rmcv_ctx* ctx, const rmcv_lightblob* blobs, int n_blo
     return RMCV_OK;
 }
 
+int rmcv_solve_pnp(rmcv_ctx* ctx, const rmcv_armour* armours, int n_armours, const double camera_matrix[9],
+                   const double dist_coeffs[5], float exact_w, float exact_h, float roi_x, float roi_y, const double* cam2world,
+                   rmcv_pose* poses) {
+    if (!ctx || n_armours < 0 || !camera_matrix || (n_armours > 0 && (!armours || !poses))) return RMCV_ERR_INVALID_ARG;
+    if (exact_w != exact_h || !(exact_w > 0.f)) return set_err(ctx, RMCV_ERR_INVALID_ARG, "IPPE_SQUARE needs a square object of positive size");
+    if (n_armours == 0) return RMCV_OK;
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t b_in = ((size_t)n_armours * sizeof(rmcv_armour) + 15) & ~(size_t)15, b_out = (size_t)n_armours * sizeof(rmcv_pose);
+    int rc = ensure_tmp(ctx, b_in + b_out, b_out);
+    if (rc != RMCV_OK) return rc;
+    CtxExtra* ex = extra(ctx);
+    uint8_t* d = reinterpret_cast<uint8_t*>(ex->tmp_dev);
+    cudaStream_t st = ex->pix;
+    RMCV_CUDA(ctx, cudaMemcpyAsync(d, armours, (size_t)n_armours * sizeof(rmcv_armour), cudaMemcpyHostToDevice, st));
+    RMCV_CUDA(ctx, launch_pnp(reinterpret_cast<const rmcv_armour*>(d), n_armours, camera_matrix, dist_coeffs, exact_w, exact_h, roi_x,
+                              roi_y, cam2world, reinterpret_cast<rmcv_pose*>(d + b_in), st, &ctx->kernel_launches));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(ex->tmp_host, d + b_in, b_out, cudaMemcpyDeviceToHost, st));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(poses, ex->tmp_host, b_out);
+    return RMCV_OK;
+}
+
 int rmcv_profile_enable(rmcv_ctx* ctx, int on) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
     ctx->profiling = on != 0;

@@ -197,6 +197,9 @@ cudaError_t launch_legacy(const LegacyLaunch& p, cudaStream_t st, int64_t* launc
 cudaError_t launch_overlap(const rmcv_lightblob* d_blobs, int n, int left, int right, int32_t* d_out, cudaStream_t st,
                            int64_t* launches);
 
+cudaError_t launch_pnp(const rmcv_armour* d_armours, int n, const double K[9], const double dist[5], float w, float h,
+                       float roi_x, float roi_y, const double* cam2world, rmcv_pose* d_out, cudaStream_t st, int64_t* launches);
+
 void upload_luts();  // copies the arc LUT to constant memory (once per process/device)
 
 }  // namespace rmcv

@@ -3,6 +3,7 @@
 // numerics can be checked against the cv2 oracle in a GPU-less container (tests/test_hostmath.py).
 #include <cstring>
 #include "../../rmcv_b200/csrc/blob_math.cuh"
+#include "../../rmcv_b200/csrc/pnp_math.cuh"
 
 using namespace rmcv;
 
@@ -63,5 +64,11 @@ int hm_pair_gates(const rmcv_lightblob* a, const rmcv_lightblob* b, const rmcv_p
 void hm_make_armour(const rmcv_lightblob* a, const rmcv_lightblob* b, rmcv_armour* out) {
     memset(out, 0, sizeof(*out));
     make_armour(*a, *b, out);
+}
+int hm_solve_pnp(const float* pts, const double* K, const double* dist, float w, float h, float rx, float ry, double* rvec, double* tvec) {
+    PnpResult r;
+    const bool ok = solve_pnp_square(reinterpret_cast<const float (*)[2]>(pts), K, dist, w, h, rx, ry, &r);
+    for (int i = 0; i < 3; ++i) { rvec[i] = r.rvec[i]; tvec[i] = r.tvec[i]; }
+    return ok ? 1 : 0;
 }
 }

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def ctx():
-    with rb.Context(max_width=1280, max_height=1024, max_batch=1) as c:
+    with rb.Context(max_width=1280, max_height=1024, max_batch=2) as c:
         yield c
 
 
@@ -109,3 +109,29 @@ def test_lightblob_overlap(ctx):
             assert got == ref, f"LightBlobOverlap({left},{right}) = {got}, oracle {ref}"
             seen.add(ref)
     assert seen == {True, False}
+
+
+def test_solve_pnp_matches_cv2(ctx):
+    """f1 (next row): rm::solve_PnP per armour (src/mobility.cpp:166-190, executable/main.cpp:183-192) on the GPU
+    against cv2.solvePnP(SOLVEPNP_IPPE_SQUARE) with the reference's camera, plus the camera -> world transform."""
+    frames = np.stack([synth.make_frame(s, 1280, 1024, 10) for s in (430, 431)])
+    res = ctx.detect_batch_host(frames, rb.default_params())
+    M = np.array([[0.0007941130268316332, 0.009683274185178004, -0.9999528006788897, -27.25811584661768],
+                  [0.9989588796104363, 0.04560298009571095, 0.001234930707386894, -51.46996511920027],
+                  [0.04561278583864914, -0.9989127101040636, -0.009636978810429797, 77.11760876626687],
+                  [0.0, 0.0, 0.0, 1.0]])   # h_gripper2camera of executable/main.cpp:18-22
+    n = 0
+    for f in range(2):
+        arm = ctx.frame_detections(res, f).armours
+        poses = ctx.solve_pnp(arm, O.MAIN_CAMMAT, O.MAIN_DISCOF, (27.0, 27.0), cam2world=M)
+        assert len(poses) == len(arm) > 0
+        for a, (rvec, tvec, pos, ok) in zip(arm, poses):
+            rr, rt = O.solve_pnp(a.vertices)
+            assert ok
+            assert np.abs(rvec - rr).max() <= 1e-8 and (np.abs(tvec - rt) / np.abs(rt).max()).max() <= 1e-8
+            assert np.abs(pos - O.camera_to_world(rt, M)).max() <= 1e-6 * max(1.0, np.abs(rt).max())
+            n += 1
+    assert n >= 10
+    assert ctx.solve_pnp([], O.MAIN_CAMMAT, O.MAIN_DISCOF) == []
+    with pytest.raises(rb.RmcvError):
+        ctx.solve_pnp(arm[:1], O.MAIN_CAMMAT, O.MAIN_DISCOF, (27.0, 20.0))

@@ -129,3 +129,43 @@ def test_integer_sum_route_matches_oracle_and_point_route(hm):
                     worst[2] = max(worst[2], abs(((box.angle - e.angle) + 90) % 180 - 90))
     assert nfit > 400
     assert worst[0] <= 1e-3 and worst[1] <= 1e-5 and worst[2] <= 1e-3, worst
+
+
+def test_solve_pnp_ippe_square_matches_cv2(hm):
+    """rm::solve_PnP (src/mobility.cpp:166-190): the host build of pnp_math.cuh against cv2.solvePnP(IPPE_SQUARE) on
+    armours of synthetic frames and on random quadrilaterals, with the camera of executable/main.cpp:8-17."""
+    K = np.ascontiguousarray(O.MAIN_CAMMAT.ravel())
+    dist = np.ascontiguousarray(O.MAIN_DISCOF)
+
+    def mine(pts, size=(27.0, 27.0), roi=(0.0, 0.0)):
+        p = np.ascontiguousarray(np.asarray(pts, np.float32).reshape(4, 2))
+        rv, tv = np.zeros(3), np.zeros(3)
+        ok = hm.hm_solve_pnp(p.ctypes.data_as(C.c_void_p), K.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p),
+                             C.c_float(size[0]), C.c_float(size[1]), C.c_float(roi[0]), C.c_float(roi[1]),
+                             rv.ctypes.data_as(C.c_void_p), tv.ctypes.data_as(C.c_void_p))
+        return ok, rv, tv
+
+    worst_r = worst_t = 0.0
+    n = 0
+    quads = []
+    for seed in (500, 501):
+        fr = O.detect_frame(synth.make_frame(seed, 1280, 1024, 10))
+        quads += [(a.vertices, (27.0, 27.0), (0.0, 0.0)) for a in fr.armours]
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        cx, cy, s = rng.uniform(100, 1180), rng.uniform(100, 900), rng.uniform(15, 200)
+        q = np.array([[cx - s, cy - s], [cx - s, cy + s], [cx + s, cy + s], [cx + s, cy - s]], np.float32)
+        q += rng.uniform(-0.25 * s, 0.25 * s, (4, 2)).astype(np.float32)
+        quads.append((q, (float(rng.uniform(5, 60)), float(rng.uniform(5, 60))) if _ % 3 else (27.0, 27.0),
+                      (float(rng.integers(0, 50)), float(rng.integers(0, 50)))))
+    for q, size, roi in quads:
+        if size[0] != size[1]:
+            size = (size[0], size[0])          # IPPE_SQUARE asserts a square object
+        rv, tv = O.solve_pnp(q, exact_size=size, roi=roi)
+        ok, r2, t2 = mine(q, size, roi)
+        assert ok == 1
+        worst_r = max(worst_r, float(np.abs(rv - r2).max()))
+        worst_t = max(worst_t, float((np.abs(tv - t2) / np.abs(tv).max()).max()))
+        n += 1
+    assert n > 200
+    assert worst_r <= 1e-8 and worst_t <= 1e-8, (worst_r, worst_t)
