@@ -145,18 +145,28 @@ struct LabelParams {
     int Rs;      // run capacity of the shared-memory arrays
 };
 
+// Shared memory of the label kernel.  The "link" region is reused over the kernel's life: foreground links -> gap join
+// flags + per-component hole flags -> record counts / start offsets.
+__host__ __device__ inline size_t label_link_bytes(int Rs, int C) {
+    size_t a = (size_t)Rs * sizeof(int32_t);
+    const size_t b = (((size_t)2 * (Rs + 2) + 3) & ~(size_t)3) + (size_t)C * sizeof(int32_t) + 8;  // jp | jo | hole flags
+    const size_t c = ((size_t)2 * C + 2) * sizeof(int32_t);                                        // cnt | start
+    if (b > a) a = b;
+    if (c > a) a = c;
+    return (a + 15) & ~(size_t)15;
+}
 __host__ __device__ inline size_t label_smem_bytes(int H, int Rs, int C) {
-    size_t b = ((size_t)2 * C + 2) * sizeof(int32_t);  // records per component, start offsets
-    b += (size_t)H * sizeof(int2);
+    size_t b = 0;
+    b += ((size_t)H * sizeof(ushort2) + 15) & ~(size_t)15;  // rows (16-bit run indices: shared-memory mode only)
     b += (size_t)Rs * sizeof(uint32_t);            // run_x
-    b += (size_t)Rs * sizeof(int32_t);             // link / gap flags
+    b += label_link_bytes(Rs, C);                  // link / gap flags / record counts
     b += ((size_t)Rs + 2) * sizeof(int32_t);       // glink
     b += (size_t)Rs * sizeof(uint16_t);            // run_y
     b += (size_t)Rs * sizeof(int16_t);             // cid
     return b + 64;
 }
 
-__global__ void __launch_bounds__(256, 3) label_kernel(const LabelParams p) {
+__global__ void __launch_bounds__(256, 4) label_kernel(const LabelParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int sh_scan[33];
     __shared__ int s_ncomp, s_nadj, s_flags, s_hb[4];
@@ -168,11 +178,13 @@ __global__ void __launch_bounds__(256, 3) label_kernel(const LabelParams p) {
     FrameCounters& fc = sb.counters[frame];
 
     uint8_t* q = smem;
-    int32_t* s_cnt = reinterpret_cast<int32_t*>(q); q += (size_t)C * sizeof(int32_t);
-    int32_t* s_start = reinterpret_cast<int32_t*>(q); q += ((size_t)C + 2) * sizeof(int32_t);
-    int2* s_rows = reinterpret_cast<int2*>(q); q += (size_t)H * sizeof(int2);
+    ushort2* s_rows16 = reinterpret_cast<ushort2*>(q); q += ((size_t)H * sizeof(ushort2) + 15) & ~(size_t)15;
     uint32_t* s_run_x = reinterpret_cast<uint32_t*>(q); q += (size_t)Rs * sizeof(uint32_t);
-    int32_t* s_link = reinterpret_cast<int32_t*>(q); q += (size_t)Rs * sizeof(int32_t);
+    int32_t* s_link = reinterpret_cast<int32_t*>(q);
+    int32_t* s_hole = reinterpret_cast<int32_t*>(q + (((size_t)2 * (Rs + 2) + 3) & ~(size_t)3));  // per-component hole flags (gap phase)
+    int32_t* s_cnt = s_link;                       // record counts / start offsets (after the gap phase)
+    int32_t* s_start = s_link + C;
+    q += label_link_bytes(Rs, C);
     int32_t* s_glink = reinterpret_cast<int32_t*>(q); q += ((size_t)Rs + 2) * sizeof(int32_t);
     uint16_t* s_run_y = reinterpret_cast<uint16_t*>(q); q += (size_t)Rs * sizeof(uint16_t);
     int16_t* s_cid = reinterpret_cast<int16_t*>(q);
@@ -190,7 +202,12 @@ __global__ void __launch_bounds__(256, 3) label_kernel(const LabelParams p) {
     int32_t* g_comp_cnt = sb.comp_cnt + (size_t)frame * C;     // runs per component, then (1 - runs + contacts) > 0
 
     Runs f;
-    f.rows = s_rows;
+    f.rows = nullptr;
+    // rows[y] = (first, end) run of row y: 16-bit copies in shared memory when the runs live there, else the global array
+    auto row = [&](int y) -> int2 {
+        if (in_smem) { const ushort2 v = s_rows16[y]; return make_int2((int)v.x, (int)v.y); }
+        return g_rows[y];
+    };
     f.run_x = in_smem ? s_run_x : g_run_x;
     f.run_y = in_smem ? s_run_y : g_run_y;
     f.link = in_smem ? s_link : g_parent;
@@ -210,7 +227,7 @@ __global__ void __launch_bounds__(256, 3) label_kernel(const LabelParams p) {
             rr.x = min(rr.x, n_runs); rr.y = min(rr.y, n_runs);
             g_rows[y] = rr;
         }
-        s_rows[y] = rr;
+        if (in_smem) s_rows16[y] = make_ushort2((unsigned short)rr.x, (unsigned short)rr.y);
     }
     for (int r = tid; r < n_runs; r += NT) {
         if (in_smem) { s_run_x[r] = g_run_x[r]; s_run_y[r] = g_run_y[r]; }
@@ -226,7 +243,7 @@ __global__ void __launch_bounds__(256, 3) label_kernel(const LabelParams p) {
             const int xs = (int)(rx & 0xffffu), xe = (int)(rx >> 16), y = f.run_y[r];
             int lk = r;
             if (y > 0) {
-                const int2 pr = s_rows[y - 1];
+                const int2 pr = row(y - 1);
                 const int p0 = lower_bound_xe(f.run_x, pr.x, pr.y, xs - 1);
                 int pp = p0;
                 while (pp < pr.y && (int)(f.run_x[pp] & 0xffffu) <= xe + 1) {
@@ -288,11 +305,11 @@ __global__ void __launch_bounds__(256, 3) label_kernel(const LabelParams p) {
         // inside the union of the bounding boxes of the components with holes is outer background without any search.
         if (tid == 0) { s_hb[0] = INT32_MAX; s_hb[1] = INT32_MAX; s_hb[2] = -1; s_hb[3] = -1; f.glink[0] = 0; }
         for (int i = tid; i < (2 * (n_runs + 2) + 3) / 4; i += NT) reinterpret_cast<uint32_t*>(f.jp)[i] = 0u;
-        for (int c = tid; c < n_comps; c += NT) s_cnt[c] = g_comp_cnt[c];
+        for (int c = tid; c < n_comps; c += NT) s_hole[c] = g_comp_cnt[c];
         __syncthreads();
         for (int r = tid; r < n_runs; r += NT) {
             const int c = f.cid[r];
-            if (c >= 0 && s_cnt[c] > 0) {
+            if (c >= 0 && s_hole[c] > 0) {
                 const uint32_t rx = f.run_x[r];
                 atomicMin(&s_hb[0], (int)(rx & 0xffffu)); atomicMax(&s_hb[2], (int)(rx >> 16));
                 atomicMin(&s_hb[1], (int)f.run_y[r]); atomicMax(&s_hb[3], (int)f.run_y[r]);
@@ -302,14 +319,14 @@ __global__ void __launch_bounds__(256, 3) label_kernel(const LabelParams p) {
         const int hx0 = s_hb[0], hy0 = s_hb[1], hx1 = s_hb[2], hy1 = s_hb[3];
         for (int r = tid; r < n_runs; r += NT) {
             const int y = f.run_y[r];
-            const int2 rr = s_rows[y];
+            const int2 rr = row(y);
             if (r == rr.x || y <= hy0 || y >= hy1) { f.glink[r + 1] = 0; continue; }  // border gap, or outside the box
             const int a = (int)(f.run_x[r - 1] >> 16) + 1, b = (int)(f.run_x[r] & 0xffffu) - 1;
             if (a <= hx0 || b >= hx1) { f.glink[r + 1] = 0; continue; }
             bool outer = false;
             int first = -1;
             {   // row above: every overlapped gap is connected to this one (and so to each other)
-                const int2 pr = s_rows[y - 1];
+                const int2 pr = row(y - 1);
                 const int lo = pr.x, hi = pr.y;
                 bool prev_overlapped = false;
                 for (int k = upper_bound_xs(f.run_x, lo, hi, a);; ++k) {
@@ -330,7 +347,7 @@ __global__ void __launch_bounds__(256, 3) label_kernel(const LabelParams p) {
                 }
             }
             {   // row below: its interior gaps look up themselves; only its border gaps have no node
-                const int2 nr = s_rows[y + 1];
+                const int2 nr = row(y + 1);
                 if (nr.x == nr.y) {
                     outer = true;
                 } else if (y + 1 == H - 1) {  // every gap of the last row is outer: connected unless one run covers [a,b]
