@@ -230,10 +230,13 @@ cudaError_t launch_emit(const EmitLaunch& L, cudaStream_t st, int64_t* launches)
     p.bits = L.bits; p.W = L.W; p.H = L.H; p.WB = (L.W + 31) / 32;
     p.rows = L.rows; p.run_x = L.run_x; p.run_y = L.run_y; p.counters = L.counters; p.R = L.R;
     p.recs = L.recs; p.PC = L.PC;
-    int BH = 2048 / p.WB;                  // ~2048 words (8 KB of mask) per band; word indices must fit 16 bits
+    // band height: (BH + 2) * WB <= 4096 words keeps the per-warp nibble register within eight rounds and the word
+    // indices within 16 bits; taller bands amortise the scan / claim / row-table steps
+    const int bh_max = 4096 / p.WB - 2;
+    int BH = 32;
     const char* env = getenv("RMCV_EMIT_BH");
     if (env) BH = atoi(env);
-    if (BH > 32) BH = 32;
+    if (BH > bh_max) BH = bh_max;
     if (BH < 1) BH = 1;
     if (BH > L.H) BH = L.H;
     p.BH = BH; p.bands = (L.H + BH - 1) / BH;
