@@ -247,3 +247,55 @@ def test_hole_plane_invariant_and_repeatability(ctx):
     for x, y in zip(first, second):
         assert [c.__dict__ for c in x.contours] == [c.__dict__ for c in y.contours]
         assert len(x.armours) == len(y.armours)
+
+
+def test_empty_full_and_degenerate_frames(ctx):
+    """Edge cases of the path: no foreground at all, everything foreground, one-pixel-high / one-pixel-wide frames."""
+    p = CMP.oracle_params(dict(area_range=(0.0, 1e12)))
+    empty = np.zeros((1, 64, 96, 3), np.uint8)
+    res = ctx.detect_batch_host(empty, c_params(p))
+    assert res.total_contours == 0 and res.total_blobs == 0 and res.total_armours == 0
+    full = np.zeros((1, 40, 72, 3), np.uint8); full[..., 0] = 255
+    detect_and_compare(ctx, full, p, what="all foreground")
+    for shape in ((1, 50), (50, 1), (2, 2), (1, 1), (3, 200)):
+        rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+        m = rng.random(shape) < 0.6
+        detect_and_compare(ctx, mask_to_bgr(m)[None], p, what=f"thin {shape}")
+
+
+def test_all_targets_full_path(ctx):
+    """CAMP_RED and CAMP_GUIDELIGHT through the whole path (channel pairs of src/imgproc.cpp:56-65)."""
+    import cv2
+    img = synth.make_frame(70, 1280, 1024, 8, blue=False)
+    detect_and_compare(ctx, img[None], CMP.oracle_params(dict(target=rb.CAMP_RED)), what="red")
+    g = np.zeros((300, 400, 3), np.uint8)
+    for k, (x, a) in enumerate(((80, 5), (160, -4), (260, 8), (330, 0))):
+        cv2.ellipse(g, ((x, 150), (14, 90), a), (30, 250, 40), -1)
+    rep = detect_and_compare(ctx, g[None], CMP.oracle_params(dict(target=rb.CAMP_GUIDELIGHT)), what="guide light")
+    assert rep.blobs == 4 and rep.armours >= 1
+
+
+def test_pitched_device_frames_full_path(ctx):
+    """cv::Mat-style row pitch and frame stride larger than the payload, device-resident entry point."""
+    W, H, B = 300, 200, 3
+    frames = np.stack([synth.make_frame(80 + s, W, H, 3) for s in range(B)])
+    pitch, fstride = W * 3 + 52, (W * 3 + 52) * H + 4096
+    buf = np.zeros(B * fstride, np.uint8)
+    for f in range(B):
+        for y in range(H):
+            o = f * fstride + y * pitch
+            buf[o:o + W * 3] = frames[f, y].ravel()
+    mp, ms = W + 20, (W + 20) * H + 512
+    d_in = ctx.device_buffer(buf.nbytes); d_mask = ctx.device_buffer(B * ms)
+    d_in.upload(buf)
+    p = c_params(PRM)
+    import ctypes
+    ctx._check(ctx.lib.rmcv_detect_batch(ctx.h, d_in.ptr, pitch, fstride, W, H, B, ctypes.byref(p), d_mask.ptr, mp, ms), "rmcv_detect_batch")
+    res = ctx.fetch_results()
+    masks = d_mask.download((B * ms,))
+    for f in range(B):
+        ref = O.detect_frame(frames[f])
+        got = np.stack([masks[f * ms + y * mp: f * ms + y * mp + W] for y in range(H)])
+        assert np.array_equal(got, ref.binary)
+        CMP.compare_frame(ctx.frame_detections(res, f), ref, PRM, where=f"pitched frame {f}")
+    d_in.free(); d_mask.free()
