@@ -116,6 +116,11 @@ __global__ void __launch_bounds__(128) emit_kernel(const EmitParams p) {
             pos += __popc(bal);
         }
     }
+    if (n_ent == 0) {   // an empty band (block-uniform): its rows hold no runs, nothing to rank or claim
+        int2* rows = p.rows + (size_t)frame * H;
+        for (int j = tid; j < nout; j += NT) rows[y0 + j] = make_int2(0, 0);
+        return;
+    }
     __syncthreads();
     auto boundary_word = [&](int idx, int k) -> uint32_t {
         const uint32_t* c = m + idx;

@@ -1,5 +1,2 @@
-run bh32 RMCV_SERIAL=1
-run bh48 RMCV_SERIAL=1 RMCV_EMIT_BH=48
-run bh64 RMCV_SERIAL=1 RMCV_EMIT_BH=64
-run bh16 RMCV_SERIAL=1 RMCV_EMIT_BH=16
-run bh64p --args "--steps 20" RMCV_EMIT_BH=64
+run base --args "--steps 20" A=1
+run serial RMCV_SERIAL=1
