@@ -272,6 +272,18 @@ int rmcv_min_area_rects(rmcv_ctx* ctx, const int32_t* xy, const int32_t* offsets
  * right == n (one past the end, undefined behaviour in C++); here right >= n yields 0. */
 int rmcv_lightblob_overlap(rmcv_ctx* ctx, const rmcv_lightblob* blobs, int n_blobs, int left, int right, int* overlap);
 
+/* ---- f4 (next row): camera front-end variants ------------------------------------------------- */
+/* hardware/src/daheng.cpp:91-187 ahead of the demosaic: 10/12-bit samples in 16-bit containers are cut to bits 2..9 /
+ * 4..11 (DxRaw16toRaw8 DX_BIT_2_9 / DX_BIT_4_11), DxImageMirror(HORIZONTAL_MIRROR) and the flip argument of
+ * DxRaw8toRGB24 are folded into the index.  Device pointers, async (pixel stream).  bits: 8, 10 or 12; pitches and frame
+ * strides in bytes.  Run rmcv_bayer_* on d_raw8 with rmcv_frontend_layout(layout, width, height, 0, flip): daheng::capture
+ * already passes the post-mirror filter (2 instead of 4, daheng.cpp:81), so only the flip changes the layout. */
+int rmcv_raw_frontend_batch(rmcv_ctx* ctx, const void* d_raw, size_t pitch, size_t frame_stride, int width, int height,
+                            int batch, int bits, int mirror, int flip, uint8_t* d_raw8, size_t out_pitch,
+                            size_t out_frame_stride);
+/* Bayer layout (RMCV_BAYER_*) of a mosaic after a horizontal mirror and/or a vertical flip of a width x height frame. */
+int rmcv_frontend_layout(int layout, int width, int height, int mirror, int flip);
+
 /* ---- f1 (next row): rm::solve_PnP per armour -------------------------------------------------- */
 /* Pose of one armour: cv::solvePnP(SOLVEPNP_IPPE_SQUARE) on armour.vertices against the canonical square of the given
  * size (src/mobility.cpp:166-190), and tvec moved by the caller's 4x4 camera -> world transform (executable/main.cpp:

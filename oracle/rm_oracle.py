@@ -428,6 +428,21 @@ def lightblob_overlap(blobs: Sequence[LightBlob], left: int, right: int) -> bool
     return False
 
 
+# --------------------------------------------------------------------------- f4: camera front-end variants (next row)
+def daheng_process(raw: np.ndarray, bits: int, layout: int, flip: bool, mirror: bool) -> np.ndarray:
+    """hardware/src/daheng.cpp:91-187 (ProcessData) with the declared stand-ins for the closed SDK calls:
+    DxImageMirror(HORIZONTAL_MIRROR) = fliplr of the raw mosaic; DxRaw16toRaw8(DX_BIT_2_9 / DX_BIT_4_11) = bits 2..9 /
+    4..11; DxRaw8toRGB24(RAW2RGB_NEIGHBOUR, layout, flip) = cv2 bilinear demosaic with that layout, then flipud.
+    `layout` is what the caller passes to DxRaw8toRGB24, i.e. the layout of the mosaic AFTER the mirror (daheng.cpp:81)."""
+    r = np.asarray(raw)
+    if mirror:
+        r = r[:, ::-1]
+    if bits > 8:
+        r = ((r.astype(np.uint16) >> (4 if bits == 12 else 2)) & 0xFF).astype(np.uint8)
+    bgr = bayer_to_bgr(np.ascontiguousarray(r, np.uint8), layout)
+    return np.ascontiguousarray(bgr[::-1]) if flip else bgr
+
+
 # --------------------------------------------------------------------------- f1: rm::solve_PnP (next row)
 #: camera intrinsics of the reference's only caller, executable/main.cpp:8-14 (float literals stored into double Mats)
 MAIN_CAMMAT = np.array([[f32(1782.672144409928), 0.0, f32(598.8983414505224)],

@@ -109,6 +109,8 @@ PROTOTYPES = {
                                               _u8p, _sz, _i, _i, _i, _vp, _i, C.POINTER(C.c_int)]),
     "rmcv_min_area_rects": (C.c_int, [_vp, _vp, _vp, _i, _vp]),
     "rmcv_lightblob_overlap": (C.c_int, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_int)]),
+    "rmcv_raw_frontend_batch": (C.c_int, [_vp, _vp, _sz, _sz, _i, _i, _i, _i, _i, _i, _u8p, _sz, _sz]),
+    "rmcv_frontend_layout": (C.c_int, [_i, _i, _i, _i, _i]),
     "rmcv_solve_pnp": (C.c_int, [_vp, _vp, _i, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, _vp, _vp]),
     "rmcv_profile_enable": (C.c_int, [_vp, _i]),
     "rmcv_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), _i]),

@@ -463,6 +463,19 @@ class Context:
         return bool(out.value)
 
 
+    # -- f4: camera front-end variants (hardware/src/daheng.cpp:91-187)
+    def raw_frontend_batch(self, d_raw: int, width: int, height: int, batch: int, bits: int, mirror: bool, flip: bool,
+                           d_raw8: int, pitch: Optional[int] = None, frame_stride: Optional[int] = None):
+        bpp = 2 if bits > 8 else 1
+        pitch = width * bpp if pitch is None else pitch
+        frame_stride = pitch * height if frame_stride is None else frame_stride
+        self._check(self.lib.rmcv_raw_frontend_batch(self.h, d_raw, pitch, frame_stride, width, height, batch, bits,
+                                                     1 if mirror else 0, 1 if flip else 0, d_raw8, width, width * height),
+                    "rmcv_raw_frontend_batch")
+
+    def frontend_layout(self, layout: int, width: int, height: int, mirror: bool, flip: bool) -> int:
+        return int(self.lib.rmcv_frontend_layout(layout, width, height, 1 if mirror else 0, 1 if flip else 0))
+
     # -- f1: rm::solve_PnP
     def solve_pnp(self, armours: Sequence[Armour], camera_matrix, dist_coeffs, exact_size=(27.0, 27.0), roi=(0.0, 0.0),
                   cam2world=None):

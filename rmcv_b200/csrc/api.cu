@@ -943,6 +943,32 @@ int rmcv_lightblob_overlap(rmcv_ctx* ctx, const rmcv_lightblob* blobs, int n_blo
     return RMCV_OK;
 }
 
+int rmcv_raw_frontend_batch(rmcv_ctx* ctx, const void* d_raw, size_t pitch, size_t frame_stride, int width, int height, int batch,
+                            int bits, int mirror, int flip, uint8_t* d_raw8, size_t out_pitch, size_t out_frame_stride) {
+    if (!ctx || !d_raw || !d_raw8) return RMCV_ERR_INVALID_ARG;
+    if (width <= 0 || height <= 0 || batch <= 0) return set_err(ctx, RMCV_ERR_INVALID_ARG, "width, height and batch must be positive");
+    if (bits != 8 && bits != 10 && bits != 12) return set_err(ctx, RMCV_ERR_INVALID_ARG, "bits must be 8, 10 or 12");
+    const size_t rowbytes = (size_t)width * (bits > 8 ? 2 : 1);
+    if (pitch < rowbytes || out_pitch < (size_t)width) return set_err(ctx, RMCV_ERR_INVALID_ARG, "pitch smaller than a row");
+    if (bits > 8 && ((pitch | frame_stride | reinterpret_cast<size_t>(d_raw)) & 1)) return set_err(ctx, RMCV_ERR_INVALID_ARG, "16-bit rows must be 2-byte aligned");
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    RMCV_CUDA(ctx, launch_frontend(static_cast<const uint8_t*>(d_raw), pitch, frame_stride, d_raw8, out_pitch, out_frame_stride, width,
+                                   height, batch, bits, mirror ? 1 : 0, flip ? 1 : 0, extra(ctx)->pix, &ctx->kernel_launches));
+    return RMCV_OK;
+}
+
+int rmcv_frontend_layout(int layout, int width, int height, int mirror, int flip) {
+    // colour at (row parity, column parity): RG = [[R,G],[G,B]], GB = [[G,B],[R,G]], GR = [[G,R],[B,G]], BG = [[B,G],[G,R]]
+    if (layout < RMCV_BAYER_RG || layout > RMCV_BAYER_BG) return RMCV_ERR_INVALID_ARG;
+    // a mirror of an even-width frame swaps the two columns of the 2x2 cell, a flip of an even-height frame its rows
+    const bool swap_cols = mirror && (width % 2 == 0), swap_rows = flip && (height % 2 == 0);
+    static const int col_swapped[5] = {0, RMCV_BAYER_GR, RMCV_BAYER_BG, RMCV_BAYER_RG, RMCV_BAYER_GB};
+    static const int row_swapped[5] = {0, RMCV_BAYER_GB, RMCV_BAYER_RG, RMCV_BAYER_BG, RMCV_BAYER_GR};
+    if (swap_cols) layout = col_swapped[layout];
+    if (swap_rows) layout = row_swapped[layout];
+    return layout;
+}
+
 int rmcv_solve_pnp(rmcv_ctx* ctx, const rmcv_armour* armours, int n_armours, const double camera_matrix[9],
                    const double dist_coeffs[5], float exact_w, float exact_h, float roi_x, float roi_y, const double* cam2world,
                    rmcv_pose* poses) {

@@ -200,6 +200,10 @@ cudaError_t launch_overlap(const rmcv_lightblob* d_blobs, int n, int left, int r
 cudaError_t launch_pnp(const rmcv_armour* d_armours, int n, const double K[9], const double dist[5], float w, float h,
                        float roi_x, float roi_y, const double* cam2world, rmcv_pose* d_out, cudaStream_t st, int64_t* launches);
 
+cudaError_t launch_frontend(const uint8_t* d_src, size_t pitch, size_t frame_stride, uint8_t* d_dst, size_t dpitch,
+                            size_t dframe_stride, int W, int H, int batch, int bits, int mirror, int flip, cudaStream_t st,
+                            int64_t* launches);
+
 void upload_luts();  // copies the arc LUT to constant memory (once per process/device)
 
 }  // namespace rmcv

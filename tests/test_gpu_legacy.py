@@ -135,3 +135,38 @@ def test_solve_pnp_matches_cv2(ctx):
     assert ctx.solve_pnp([], O.MAIN_CAMMAT, O.MAIN_DISCOF) == []
     with pytest.raises(rb.RmcvError):
         ctx.solve_pnp(arm[:1], O.MAIN_CAMMAT, O.MAIN_DISCOF, (27.0, 20.0))
+
+
+@pytest.mark.parametrize("bits,mirror,flip", [(8, False, False), (8, True, False), (10, False, True), (12, True, True), (12, False, False)])
+def test_camera_frontend_variants(ctx, bits, mirror, flip):
+    """f4 (next row): 8/10/12-bit mosaics with mirror / flip (hardware/src/daheng.cpp:91-187) -> front-end kernel ->
+    Bayer pixel kernel, against the oracle's restatement of ProcessData followed by extract_color."""
+    W, H = 1280, 1024
+    scene = synth.make_frame(440 + bits, W, H, 8)
+    layout = rb.BAYER_GB if mirror else rb.BAYER_BG           # what daheng::capture passes (daheng.cpp:81)
+    # the camera delivers the mosaic BEFORE mirror/flip: build it so that ProcessData ends at `scene`'s orientation
+    pre = scene[::-1] if flip else scene
+    pre = pre[:, ::-1] if mirror else pre
+    sensor_layout = ctx.frontend_layout(layout, W, H, mirror, False)   # layout of the unmirrored sensor data
+    raw8 = synth.bgr_to_bayer(np.ascontiguousarray(pre), ctx.frontend_layout(sensor_layout, W, H, False, flip))
+    rng = np.random.default_rng(bits)
+    if bits > 8:
+        sh = 4 if bits == 12 else 2
+        raw = (raw8.astype(np.uint16) << sh) | rng.integers(0, 1 << sh, raw8.shape, dtype=np.uint16)
+    else:
+        raw = raw8
+    ref_bgr = O.daheng_process(raw, bits, layout, flip, mirror)
+    ref_mask = O.extract_color_mask(ref_bgr, rb.CAMP_BLUE, 80)
+    assert ref_mask.any()
+    d_raw = ctx.device_buffer(raw.nbytes); d_r8 = ctx.device_buffer(W * H); d_mask = ctx.device_buffer(W * H)
+    try:
+        d_raw.upload(np.ascontiguousarray(raw))
+        ctx.raw_frontend_batch(d_raw.ptr, W, H, 1, bits, mirror, flip, d_r8.ptr)
+        lay = ctx.frontend_layout(layout, W, H, False, flip)
+        ctx.bayer_extract_color_batch(d_r8.ptr, W, H, 1, lay, rb.CAMP_BLUE, 80, d_mask.ptr)
+        ctx.sync()
+        mask = d_mask.download((H, W))
+    finally:
+        d_raw.free(); d_r8.free(); d_mask.free()
+    bad = np.argwhere(mask != ref_mask)
+    assert bad.size == 0, f"bits {bits} mirror {mirror} flip {flip}: {len(bad)} mask bytes differ, first {bad[0]}"
