@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RMCV_B200_ABI_VERSION 1
+#define RMCV_B200_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -139,6 +139,18 @@ typedef struct rmcv_config {
     void* stream;                  /* cudaStream_t to run the pixel kernels on, or NULL           */
 } rmcv_config;
 
+/* Pose of one armour: cv::solvePnP(SOLVEPNP_IPPE_SQUARE) on armour.vertices against the canonical square of the given
+ * size (src/mobility.cpp:166-190), and tvec moved by the caller's 4x4 camera -> world transform (executable/main.cpp:
+ * 186-192; position == tvec when no transform is given).  88 bytes. */
+typedef struct rmcv_pose {
+    double rvec[3];       /* Rodrigues rotation vector                                         */
+    double tvec[3];       /* translation in the units of exact_w / exact_h                     */
+    double position[3];   /* cam2world * [tvec; 1]                                             */
+    double reproj_err;    /* sum of squared reprojection errors, normalised image coordinates  */
+    int32_t ok;           /* 0: the four image points are collinear                            */
+    int32_t pad;
+} rmcv_pose;
+
 /* View of the results of one detect call.  Pointers are ctx-owned pinned host memory, valid
  * until the second next detect call on the ctx (two result sets alternate).  Dense arrays are
  * indexed through frames[f].*_offset. */
@@ -149,6 +161,7 @@ typedef struct rmcv_results {
     const rmcv_contour_info* contours;
     const rmcv_lightblob* blobs;
     const rmcv_armour* armours;
+    const rmcv_pose* poses;   /* poses[k] belongs to armours[k]; NULL unless rmcv_set_camera() was called (f1) */
 } rmcv_results;
 
 typedef struct rmcv_ctx rmcv_ctx;
@@ -285,17 +298,12 @@ int rmcv_raw_frontend_batch(rmcv_ctx* ctx, const void* d_raw, size_t pitch, size
 int rmcv_frontend_layout(int layout, int width, int height, int mirror, int flip);
 
 /* ---- f1 (next row): rm::solve_PnP per armour -------------------------------------------------- */
-/* Pose of one armour: cv::solvePnP(SOLVEPNP_IPPE_SQUARE) on armour.vertices against the canonical square of the given
- * size (src/mobility.cpp:166-190), and tvec moved by the caller's 4x4 camera -> world transform (executable/main.cpp:
- * 186-192; position == tvec when no transform is given).  88 bytes. */
-typedef struct rmcv_pose {
-    double rvec[3];       /* Rodrigues rotation vector                                         */
-    double tvec[3];       /* translation in the units of exact_w / exact_h                     */
-    double position[3];   /* cam2world * [tvec; 1]                                             */
-    double reproj_err;    /* sum of squared reprojection errors, normalised image coordinates  */
-    int32_t ok;           /* 0: the four image points are collinear                            */
-    int32_t pad;
-} rmcv_pose;
+/* Fused variant: with a camera set, every detect call also solves the pose of every armour it finds (one more small
+ * kernel behind the write-out, executable/main.cpp:183-192 without the host round trip) and rmcv_results.poses is
+ * filled.  exact_w must equal exact_h; dist_coeffs and cam2world may be NULL.  rmcv_clear_camera() turns it off. */
+int rmcv_set_camera(rmcv_ctx* ctx, const double camera_matrix[9], const double dist_coeffs[5], float exact_w, float exact_h,
+                    const double* cam2world);
+int rmcv_clear_camera(rmcv_ctx* ctx);
 
 /* camera_matrix: 3x3 row-major; dist_coeffs: k1, k2, p1, p2, k3 (NULL = none); exact_w must equal exact_h
  * (IPPE_SQUARE); roi_x/roi_y are added to the image points (the reference's ROI offset); cam2world: 4x4 row-major

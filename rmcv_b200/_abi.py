@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 RMCV_OK = 0
 RMCV_ERR_INVALID_ARG, RMCV_ERR_CUDA, RMCV_ERR_CAPACITY, RMCV_ERR_NO_DEVICE, RMCV_ERR_STATE = -1, -2, -3, -4, -5
@@ -54,15 +54,15 @@ class Config(C.Structure):
                 ("stream", C.c_void_p)]
 
 
-class Results(C.Structure):
-    _fields_ = [("batch", C.c_int32), ("total_contours", C.c_int32), ("total_blobs", C.c_int32),
-                ("total_armours", C.c_int32), ("frames", C.POINTER(FrameInfo)), ("contours", C.POINTER(ContourInfo)),
-                ("blobs", C.POINTER(LightBlob)), ("armours", C.POINTER(Armour))]
-
-
 class Pose(C.Structure):
     _fields_ = [("rvec", C.c_double * 3), ("tvec", C.c_double * 3), ("position", C.c_double * 3), ("reproj_err", C.c_double),
                 ("ok", C.c_int32), ("pad", C.c_int32)]
+
+
+class Results(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("total_contours", C.c_int32), ("total_blobs", C.c_int32),
+                ("total_armours", C.c_int32), ("frames", C.POINTER(FrameInfo)), ("contours", C.POINTER(ContourInfo)),
+                ("blobs", C.POINTER(LightBlob)), ("armours", C.POINTER(Armour)), ("poses", C.POINTER(Pose))]
 
 
 assert C.sizeof(Pose) == 88
@@ -111,6 +111,8 @@ PROTOTYPES = {
     "rmcv_lightblob_overlap": (C.c_int, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_int)]),
     "rmcv_raw_frontend_batch": (C.c_int, [_vp, _vp, _sz, _sz, _i, _i, _i, _i, _i, _i, _u8p, _sz, _sz]),
     "rmcv_frontend_layout": (C.c_int, [_i, _i, _i, _i, _i]),
+    "rmcv_set_camera": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_float, _vp]),
+    "rmcv_clear_camera": (C.c_int, [_vp]),
     "rmcv_solve_pnp": (C.c_int, [_vp, _vp, _i, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, _vp, _vp]),
     "rmcv_profile_enable": (C.c_int, [_vp, _i]),
     "rmcv_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), _i]),

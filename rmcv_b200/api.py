@@ -156,6 +156,7 @@ class FrameDetections:
     armours: List[Armour]
     n_negative: int
     flags: int
+    poses: Optional[list] = None   # per armour (rvec, tvec, position, ok) when a camera is set (Context.set_camera)
 
 
 # --------------------------------------------------------------------------------------------- context
@@ -335,7 +336,13 @@ class Context:
         cs = [ContourInfo.from_c(res.contours[fi.contour_offset + k]) for k in range(fi.n_contours)]
         bs = [LightBlob.from_c(res.blobs[fi.blob_offset + k]) for k in range(fi.n_positive)]
         ar = [Armour.from_c(res.armours[fi.armour_offset + k]) for k in range(fi.n_armours)]
-        return FrameDetections(cs, bs, ar, int(fi.n_negative), int(fi.flags))
+        poses = None
+        if res.poses:
+            poses = []
+            for k in range(fi.n_armours):
+                o = res.poses[fi.armour_offset + k]
+                poses.append((np.array(o.rvec[:]), np.array(o.tvec[:]), np.array(o.position[:]), bool(o.ok)))
+        return FrameDetections(cs, bs, ar, int(fi.n_negative), int(fi.flags), poses)
 
     def get_contour(self, frame: int, index: int, cap: int = 1 << 16) -> np.ndarray:
         n = C.c_int()
@@ -477,6 +484,17 @@ class Context:
         return int(self.lib.rmcv_frontend_layout(layout, width, height, 1 if mirror else 0, 1 if flip else 0))
 
     # -- f1: rm::solve_PnP
+    def set_camera(self, camera_matrix, dist_coeffs=None, exact_size=(27.0, 27.0), cam2world=None):
+        """Fused rm::solve_PnP: every later detect call also fills Results.poses (executable/main.cpp:183-192)."""
+        K = np.ascontiguousarray(np.asarray(camera_matrix, np.float64).reshape(9))
+        D = None if dist_coeffs is None else np.ascontiguousarray(np.asarray(dist_coeffs, np.float64).reshape(5))
+        M = None if cam2world is None else np.ascontiguousarray(np.asarray(cam2world, np.float64).reshape(16))
+        self._check(self.lib.rmcv_set_camera(self.h, K.ctypes.data, None if D is None else D.ctypes.data, float(exact_size[0]),
+                                             float(exact_size[1]), None if M is None else M.ctypes.data), "rmcv_set_camera")
+
+    def clear_camera(self):
+        self._check(self.lib.rmcv_clear_camera(self.h), "rmcv_clear_camera")
+
     def solve_pnp(self, armours: Sequence[Armour], camera_matrix, dist_coeffs, exact_size=(27.0, 27.0), roi=(0.0, 0.0),
                   cam2world=None):
         """rm::solve_PnP for every armour -> list of (rvec[3], tvec[3], position[3], ok)."""

@@ -23,6 +23,8 @@ struct ResultSet {  // pinned, device-mapped result arrays of one detect call (t
     rmcv_contour_info* contours = nullptr;  // [max_batch][C]  (chunk-dense)
     rmcv_lightblob* blobs = nullptr;        // [max_batch][C]
     rmcv_armour* armours = nullptr;         // [max_batch][A]
+    rmcv_pose* poses = nullptr;             // [max_batch][A], allocated by the first rmcv_set_camera
+    bool with_poses = false;                // the call that filled this set had a camera
     int batch = 0;
     bool pending = false;                   // enqueued, not fetched yet
     long long call_id = -1;
@@ -47,6 +49,8 @@ struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
     // i+1; host<->device staging copies have their own streams (both copy engines stay busy).
     cudaStream_t pix = nullptr, lab = nullptr, out = nullptr, h2d = nullptr, d2h = nullptr;
     bool own_pix = false;
+    CameraSetup camera;      // f1 fused: pose of every armour behind the write-out kernel
+    bool have_camera = false;
 };
 
 CtxExtra* extra(rmcv_ctx* c) { return static_cast<CtxExtra*>(c->extra); }
@@ -95,6 +99,7 @@ int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
     RMCV_CUDA(ctx, dalloc(&sb.s_contours, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.s_blobs, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.s_armours, CF * A));
+    RMCV_CUDA(ctx, dalloc(&sb.arm_offset, CF));
     (void)first;
     RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.ev_pix, cudaEventDisableTiming));
     RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.ev_lab, cudaEventDisableTiming));
@@ -107,7 +112,7 @@ int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
 void free_slot(SlotBuffers& sb) {
     cudaFree(sb.bits); cudaFree(sb.rows); cudaFree(sb.run_x); cudaFree(sb.run_y);
     cudaFree(sb.parent); cudaFree(sb.gparent); cudaFree(sb.run_cid); cudaFree(sb.sorted); cudaFree(sb.recs); cudaFree(sb.recs2); cudaFree(sb.comp_start); cudaFree(sb.acc); cudaFree(sb.comp_root); cudaFree(sb.comp_cnt); cudaFree(sb.comps);
-    cudaFree(sb.counters); cudaFree(sb.s_contours); cudaFree(sb.s_blobs); cudaFree(sb.s_armours);
+    cudaFree(sb.counters); cudaFree(sb.s_contours); cudaFree(sb.s_blobs); cudaFree(sb.s_armours); cudaFree(sb.arm_offset);
     if (sb.frames) cudaFree(sb.frames);
     if (sb.masks) cudaFree(sb.masks);
     if (sb.ev_pix) cudaEventDestroy(sb.ev_pix);
@@ -191,6 +196,7 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
     fl.g = call_geometry(ctx, W, H); fl.frames = frames; fl.sb = &sb; fl.frame_base = frame_base;
     fl.st_out = ex->out;
     fl.o_frames = ctx->h_frames; fl.o_contours = ctx->h_contours; fl.o_blobs = ctx->h_blobs; fl.o_armours = ctx->h_armours;
+    fl.o_poses = ex->have_camera ? ctx->h_poses : nullptr; fl.camera = ex->have_camera ? &ex->camera : nullptr;
     struct Mark { ProfSet* ps; rmcv_ctx* ctx; };
     Mark mk{ps, ctx};
     auto stage_done = [](void* arg, int stage, cudaStream_t s2) {
@@ -210,6 +216,8 @@ void begin_call(rmcv_ctx* ctx) {
     ResultSet& r = ex->rs[ex->n_calls & 1];
     r.pending = false;  // an unfetched call two calls back is dropped
     ctx->h_frames = r.frames; ctx->h_contours = r.contours; ctx->h_blobs = r.blobs; ctx->h_armours = r.armours;
+    ctx->h_poses = r.poses;
+    r.with_poses = ex->have_camera && r.poses;
 }
 int end_call(rmcv_ctx* ctx, int batch) {
     CtxExtra* ex = extra(ctx);
@@ -271,6 +279,7 @@ int fill_results(rmcv_ctx* ctx, const ResultSet& r, rmcv_results* out) {
         out->batch = r.batch;
         out->total_contours = (int32_t)tc; out->total_blobs = (int32_t)tb; out->total_armours = (int32_t)ta;
         out->frames = r.frames; out->contours = r.contours; out->blobs = r.blobs; out->armours = r.armours;
+        out->poses = r.with_poses ? r.poses : nullptr;
     }
     if (flags) return set_err(ctx, RMCV_ERR_CAPACITY, "a per-frame capacity overflowed; see rmcv_frame_info.flags");
     return RMCV_OK;
@@ -452,6 +461,7 @@ int rmcv_ctx_destroy(rmcv_ctx* ctx) {
             if (r.contours) cudaFreeHost(r.contours);
             if (r.blobs) cudaFreeHost(r.blobs);
             if (r.armours) cudaFreeHost(r.armours);
+            if (r.poses) cudaFreeHost(r.poses);
             for (int k = 0; k < 2; ++k) if (r.done[k]) cudaEventDestroy(r.done[k]);
         }
         for (auto& ps : ex->prof) {
@@ -967,6 +977,34 @@ int rmcv_frontend_layout(int layout, int width, int height, int mirror, int flip
     if (swap_cols) layout = col_swapped[layout];
     if (swap_rows) layout = row_swapped[layout];
     return layout;
+}
+
+int rmcv_set_camera(rmcv_ctx* ctx, const double camera_matrix[9], const double dist_coeffs[5], float exact_w, float exact_h,
+                    const double* cam2world) {
+    if (!ctx || !camera_matrix) return RMCV_ERR_INVALID_ARG;
+    if (exact_w != exact_h || !(exact_w > 0.f)) return set_err(ctx, RMCV_ERR_INVALID_ARG, "IPPE_SQUARE needs a square object of positive size");
+    CtxExtra* ex = extra(ctx);
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < 2; ++i) {   // the pose arrays exist only for callers that ask for poses
+        ResultSet& r = ex->rs[i];
+        if (!r.poses)
+            RMCV_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&r.poses), (size_t)ctx->cfg.max_batch * ctx->cap.A * sizeof(rmcv_pose),
+                                         cudaHostAllocMapped | cudaHostAllocPortable));
+    }
+    CameraSetup& c = ex->camera;
+    for (int i = 0; i < 9; ++i) c.K[i] = camera_matrix[i];
+    for (int i = 0; i < 5; ++i) c.dist[i] = dist_coeffs ? dist_coeffs[i] : 0.0;
+    c.has_M = cam2world != nullptr;
+    for (int i = 0; i < 16; ++i) c.M[i] = cam2world ? cam2world[i] : 0.0;
+    c.w = exact_w; c.h = exact_h;
+    ex->have_camera = true;
+    return RMCV_OK;
+}
+
+int rmcv_clear_camera(rmcv_ctx* ctx) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    extra(ctx)->have_camera = false;
+    return RMCV_OK;
 }
 
 int rmcv_solve_pnp(rmcv_ctx* ctx, const rmcv_armour* armours, int n_armours, const double camera_matrix[9],

@@ -1,0 +1,296 @@
+// K1b — register-resident Bayer pixel stage (blue / red targets): the Bayer front (hardware/src/daheng.cpp:136-151,
+// cv2 bilinear stand-in for DxRaw8toRGB24) fused with rm::extract_color's difference / threshold / 3x3 close
+// (src/imgproc.cpp:52-69).  HBM-bound streaming kernel, no tensor cores, no shared-memory staging:
+//
+//   * a WARP owns a strip of 30 x 16 pixels (+ one halo lane each side) and walks down a segment of rows; a lane
+//     reads its 16 raw bytes of a row with one coalesced 128-bit load (the warp reads 512 contiguous bytes), two row
+//     pairs ahead of the arithmetic;
+//   * only the two sampled planes matter (B and R; green is never read).  Samples are unpacked into 16-bit lanes, two
+//     per register, the low lane for pixels 0..7 and the high lane for pixels 8..15 of the thread's group, so that
+//     horizontal neighbours are whole registers and the final bits fall in order.  Per raw row: the samples U and
+//     their horizontal pair sums H (+1).  Per output pixel the exact bilinear threshold test is one of
+//         sampled P, quad M :  4 P - (H_up + H_down) + 3 - 4 lb >= 0                 (M = (sum + 2) >> 2)
+//         quad P, sampled M :  (H_up + H_down) - 4 M - 4 lb     >= 0
+//         pair P, pair M    :  a - (b & ~1) - 2 lb              >= 0                 (P = a >> 1, M = b >> 1)
+//     evaluated on both lanes at once (IMAD / IADD3), biased by 2^(12 + x mod 4) so that the verdict of pixel x lands
+//     on its own bit of the lane: three bit-selects gather four pixels, nine instructions sixteen;
+//   * threshold words of the two neighbouring lanes arrive by warp shuffle; dilate and erode run on a 20-bit window in
+//     registers (OpenCV's MORPH_CLOSE borders: dilate pads 0, erode pads 1), rows slide through registers;
+//   * the byte mask leaves through a 256-entry bits -> 8 bytes table (the only shared memory, 2 KB) with one 16-byte
+//     streaming store per lane and row; the bit mask for the labelling stages as one 16-bit store.
+//
+// Border rule of cv2's demosaic: row 0 shows row 1, row H-1 row H-2, column 0 column 1, column W-1 column
+// W-2 — on threshold bits a replicate of the neighbouring interior bit.
+#include "common.cuh"
+
+namespace rmcv {
+
+namespace {
+
+struct StripParams {
+    const uint8_t* src; size_t pitch, frame_stride;
+    uint8_t* mask; size_t mask_pitch, mask_frame_stride;   // mask may be null
+    uint16_t* bits16;            // bit mask viewed as 16-bit words, [batch][H][WB2]
+    int W, H, NC, WB2;           // NC = W / 16 pixel groups per row, WB2 = 16-bit words per bit row
+    int seg, nseg, nwx;          // rows per segment (even), segments per frame, warps per strip row
+    int total_warps;
+    uint32_t kSP[4], kSM[4], kN[4];   // per-lane constants of the three tests, by x mod 4 (both lanes)
+    uint32_t force_or, force_and;     // lower_bound <= 0: all ones; > 255: all zeros
+};
+
+struct RowPrep {   // one raw row: samples U[j] = (x = 2j+s, x = 2j+8+s) and pair sums H[j] at the other x parity (+1)
+    uint32_t U[4], H[4];
+};
+
+constexpr uint32_t kOne2 = 0x00010001u;
+
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) { return (a & m) | (b & ~m); }
+
+// SX = x parity of the samples in this row
+template <int SX>
+__device__ __forceinline__ void prep_row(const uint4 w, RowPrep& r) {
+    uint32_t e0, e1, e2, e3;
+    if (SX == 0) { e0 = w.x & 0x00ff00ffu; e1 = w.y & 0x00ff00ffu; e2 = w.z & 0x00ff00ffu; e3 = w.w & 0x00ff00ffu; }
+    else { e0 = __byte_perm(w.x, 0, 0x4341); e1 = __byte_perm(w.y, 0, 0x4341); e2 = __byte_perm(w.z, 0, 0x4341); e3 = __byte_perm(w.w, 0, 0x4341); }
+    r.U[0] = __byte_perm(e0, e2, 0x5410);
+    r.U[1] = __byte_perm(e0, e2, 0x7632);
+    r.U[2] = __byte_perm(e1, e3, 0x5410);
+    r.U[3] = __byte_perm(e1, e3, 0x7632);
+    if (SX == 0) {   // H[j] at x = 2j+1: U(2j) + U(2j+2); the last one needs the right neighbour's first sample
+        const uint32_t rn = __shfl_down_sync(0xffffffffu, r.U[0], 1);
+        const uint32_t s3 = __funnelshift_r(r.U[0], rn, 16);    // (x = 8, x = 16)
+        r.H[0] = r.U[0] + r.U[1] + kOne2;
+        r.H[1] = r.U[1] + r.U[2] + kOne2;
+        r.H[2] = r.U[2] + r.U[3] + kOne2;
+        r.H[3] = r.U[3] + s3 + kOne2;
+    } else {         // H[j] at x = 2j: U(2j-1) + U(2j+1); the first one needs the left neighbour's last sample
+        const uint32_t ln = __shfl_up_sync(0xffffffffu, r.U[3], 1);
+        const uint32_t s0 = __funnelshift_l(ln, r.U[3], 16);    // (x = -1, x = 7)
+        r.H[0] = s0 + r.U[0] + kOne2;
+        r.H[1] = r.U[0] + r.U[1] + kOne2;
+        r.H[2] = r.U[1] + r.U[2] + kOne2;
+        r.H[3] = r.U[2] + r.U[3] + kOne2;
+    }
+}
+
+// Threshold word (16 pixels, bit x = pixel x of the group) of the row whose prep is C, rows above / below A and B.
+// PROW: C holds samples of the plus channel.  SXC = x parity of the samples in row C.
+template <bool PROW, int SXC>
+__device__ __forceinline__ uint32_t thr_row(const RowPrep& A, const RowPrep& C, const RowPrep& B, const StripParams& p) {
+    uint32_t sel[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int xs = 2 * (j & 1) + SXC, xn = 2 * (j & 1) + (1 - SXC);   // x mod 4 of the sampled / the other site
+        uint32_t ds, dn;
+        if (PROW) {
+            ds = C.U[j] * 4u + (p.kSP[xs] - A.H[j] - B.H[j]);
+            dn = C.H[j] + p.kN[xn] - ((A.U[j] + B.U[j] + kOne2) & 0xfffefffeu);
+        } else {
+            ds = (A.H[j] + B.H[j] + p.kSM[xs]) - C.U[j] * 4u;
+            dn = (A.U[j] + B.U[j] + kOne2) + p.kN[xn] - (C.H[j] & 0xfffefffeu);
+        }
+        sel[j] = bitsel(ds, dn, kOne2 << (12 + xs));
+    }
+    const uint32_t lo = bitsel(sel[0], sel[1], 0x30003000u);   // lanes: bits 12..15 = pixels 0..3 | 8..11
+    const uint32_t hi = bitsel(sel[2], sel[3], 0x30003000u);   //        bits 12..15 = pixels 4..7 | 12..15
+    const uint32_t z = bitsel(lo >> 4, hi, 0x0f000f00u);       // byte 1 = pixels 0..7, byte 3 = pixels 8..15
+    return (__byte_perm(z, 0, 0x4431) | p.force_or) & p.force_and;
+}
+
+// Per-thread state of the walk down a strip.
+struct Walk {
+    uint32_t h0, h1, e0, e1;     // sliding rows of the close: two horizontally dilated, two horizontally eroded rows
+    uint32_t inside;             // window bit i <-> x = 16c - 2 + i: the bits inside the image
+    uint32_t fix_mask, fix_rot;  // border columns: bit 0 of group 0 shows bit 1 (rotate right 1), bit 15 of the last group bit 14
+    const uint8_t* lp;           // raw row `lr` (clamped into the image) at the column of this lane
+    int lr;
+    uint8_t* mrow;               // byte-mask address of the next row to leave (or null)
+    uint16_t* brow;              // bit-mask address of the next row to leave
+    int H;
+    bool writer, tail16;
+};
+
+// One threshold row (row r) enters, the final row r-2 leaves (STORE: to memory).
+template <bool STORE, bool MASK>
+__device__ __forceinline__ void push_row(Walk& k, const StripParams& p, const uint2* lut, uint32_t t, int r) {
+    const uint32_t tl = __shfl_up_sync(0xffffffffu, t, 1), tr = __shfl_down_sync(0xffffffffu, t, 1);
+    const uint32_t w = ((tl >> 14) | (t << 2) | (tr << 18)) & k.inside;
+    const uint32_t h = w | (w << 1) | (w >> 1);
+    uint32_t d = k.h0 | k.h1 | h | ~k.inside;               // dilated row r-1; columns outside the image read as ones
+    k.h0 = k.h1; k.h1 = h;
+    if ((unsigned)(r - 1) >= (unsigned)k.H) d = 0xffffffffu;   // so do rows outside the image
+    const uint32_t e = d & (d << 1) & (d >> 1);
+    const uint32_t m = (k.e0 & k.e1 & e) >> 2 & 0xffffu;   // final row r-2
+    k.e0 = k.e1; k.e1 = e;
+    if (STORE) {
+        if (k.writer) {
+            k.brow[0] = (uint16_t)m;
+            if (k.tail16) k.brow[1] = 0;
+            if (MASK) {
+                const uint2 a = lut[m & 255u], b = lut[m >> 8];
+                __stcs(reinterpret_cast<uint4*>(k.mrow), make_uint4(a.x, a.y, b.x, b.y));
+            }
+        }
+        k.brow += p.WB2;
+        if (MASK) k.mrow += p.mask_pitch;
+    }
+}
+
+// Loads the next raw row (rows outside the image read the nearest row inside; their results are never used).
+__device__ __forceinline__ uint4 next_row(Walk& k, const StripParams& p) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(k.lp));
+    if ((unsigned)k.lr < (unsigned)(k.H - 1)) k.lp += p.pitch;
+    ++k.lr;
+    return v;
+}
+
+// Row pair (r, r+1), r even.  On entry A = prep(r-1), C = prep(r) and (ra, rb) hold the raw rows r+1, r+2.  On exit
+// B = prep(r+1), N = prep(r+2) are the (A, C) of the next pair and (ra, rb) hold the raw rows r+5, r+6.
+template <int PY, int PX, bool STORE, bool MASK>
+__device__ __forceinline__ void row_pair(Walk& k, const StripParams& p, const uint2* lut, const RowPrep& A, const RowPrep& C,
+                                         RowPrep& B, RowPrep& N, uint4& ra, uint4& rb, int r) {
+    constexpr bool kEvenIsP = PY == 0;
+    constexpr int kSxEven = kEvenIsP ? PX : 1 - PX, kSxOdd = 1 - kSxEven;   // x parity of the samples in even / odd rows
+    prep_row<kSxOdd>(ra, B);
+    prep_row<kSxEven>(rb, N);
+    ra = next_row(k, p);
+    rb = next_row(k, p);
+    uint32_t t0 = thr_row<kEvenIsP, kSxEven>(A, C, B, p);
+    uint32_t t1 = thr_row<!kEvenIsP, kSxOdd>(C, B, N, p);
+    if (r == 0) t0 = t1;                                 // row 0 shows row 1
+    if (r == k.H - 2) t1 = t0;                           // row H-1 shows row H-2
+    t0 = bitsel(__funnelshift_r(t0, t0, k.fix_rot), t0, k.fix_mask);   // column 0 shows column 1, column W-1 column W-2
+    t1 = bitsel(__funnelshift_r(t1, t1, k.fix_rot), t1, k.fix_mask);
+    if ((unsigned)r >= (unsigned)k.H) { t0 = 0u; t1 = 0u; }   // a pair is either inside or outside the image (r, H even)
+    push_row<STORE, MASK>(k, p, lut, t0, r);
+    push_row<STORE, MASK>(k, p, lut, t1, r + 1);
+}
+
+}  // namespace
+
+// PY, PX: parity of the rows / columns that sample the plus channel (the minus channel sits on the opposite diagonal)
+template <int PY, int PX, bool MASK>
+__global__ void __launch_bounds__(256) bayer_strip_kernel(const StripParams p) {
+    __shared__ uint2 s_lut[256];
+    {
+        const uint32_t i = threadIdx.x;
+        if (i < 256) {
+            auto expand4 = [](uint32_t nib) {   // 4 bits -> 4 bytes of 0x00 / 0xFF: bits to the byte MSBs, PRMT sign-replicate
+                uint32_t r;
+                asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(nib * 0x10204080u));
+                return r;
+            };
+            s_lut[i] = make_uint2(expand4(i & 15u), expand4(i >> 4));
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= p.total_warps) return;
+    const int wx = wid % p.nwx;
+    const int rest = wid / p.nwx;
+    const int seg = rest % p.nseg, frame = rest / p.nseg;
+    const int H = p.H, NC = p.NC;
+    const int c = wx * 30 - 1 + lane;                        // pixel group of this lane (lanes 0 and 31: halo only)
+    const int cc = min(max(c, 0), NC - 1);
+    const int y0 = seg * p.seg, y1 = min(H, y0 + p.seg);
+    Walk k;
+    k.h0 = k.h1 = 0u; k.e0 = k.e1 = 0u;
+    k.inside = 0xfffffu;
+    if (c <= 0) k.inside = c == 0 ? 0xffffcu : 0u;
+    if (c >= NC - 1) k.inside = c == NC - 1 ? (k.inside & 0x3ffffu) : 0u;
+    k.fix_mask = c == 0 ? 1u : (c == NC - 1 ? 0x8000u : 0u);
+    k.fix_rot = c == 0 ? 1u : 31u;
+    k.H = H;
+    k.writer = lane >= 1 && lane <= 30 && c < NC;
+    k.tail16 = k.writer && c == NC - 1 && (p.WB2 > NC);      // W % 32 == 16: the upper half of the last bit word is zero
+    k.mrow = MASK ? p.mask + (size_t)frame * p.mask_frame_stride + (size_t)y0 * p.mask_pitch + (size_t)cc * 16 : nullptr;
+    k.brow = p.bits16 + ((size_t)frame * H + y0) * p.WB2 + cc;
+
+    constexpr int kSxEven = PY == 0 ? PX : 1 - PX, kSxOdd = 1 - kSxEven;
+    RowPrep s0, s1, s2, s3;
+    int r = y0 - 2;
+    k.lr = r - 1;
+    k.lp = p.src + (size_t)frame * p.frame_stride + (size_t)min(max(k.lr, 0), H - 1) * p.pitch + (size_t)cc * 16;
+    prep_row<kSxOdd>(next_row(k, p), s0);
+    prep_row<kSxEven>(next_row(k, p), s1);
+    uint4 a0 = next_row(k, p), b0 = next_row(k, p);   // rows r+1, r+2
+    uint4 a1 = next_row(k, p), b1 = next_row(k, p);   // rows r+3, r+4; every pair then fetches the rows r+5, r+6
+    // rows y0-2 .. y0+1 fill the pipeline; from the pair at y0+2 on, every pair releases two final rows
+    row_pair<PY, PX, false, MASK>(k, p, s_lut, s0, s1, s2, s3, a0, b0, r);
+    row_pair<PY, PX, false, MASK>(k, p, s_lut, s2, s3, s0, s1, a1, b1, r + 2);
+    r += 4;
+    while (true) {                                          // the last pair starts at y1
+        row_pair<PY, PX, true, MASK>(k, p, s_lut, s0, s1, s2, s3, a0, b0, r);
+        r += 2;
+        if (r > y1) break;
+        row_pair<PY, PX, true, MASK>(k, p, s_lut, s2, s3, s0, s1, a1, b1, r);
+        r += 2;
+        if (r > y1) break;
+    }
+}
+
+// Fast path of the Bayer pixel stage; returns cudaErrorNotSupported when the call does not qualify (the caller then
+// runs the generic shared-memory kernel).
+cudaError_t launch_bayer_strip(const PixelLaunch& L, int sm_count, cudaStream_t st, int64_t* launches) {
+    if (L.target != RMCV_CAMP_BLUE && L.target != RMCV_CAMP_RED) return cudaErrorNotSupported;   // green needs the quincunx forms
+    if ((L.W & 15) || (L.H & 1) || L.W < 32 || L.H < 4) return cudaErrorNotSupported;
+    if ((L.pitch & 15) || (L.frame_stride & 15) || (((size_t)L.src) & 15)) return cudaErrorNotSupported;
+    if (L.mask && ((L.mask_pitch & 15) || (L.mask_frame_stride & 15) || (((size_t)L.mask) & 15))) return cudaErrorNotSupported;
+    int ch[2][2];   // colour sampled at (y&1, x&1): 0 = B, 1 = G, 2 = R
+    switch (L.bayer_layout) {
+        case RMCV_BAYER_BG: ch[0][0] = 0; ch[0][1] = 1; ch[1][0] = 1; ch[1][1] = 2; break;
+        case RMCV_BAYER_GB: ch[0][0] = 1; ch[0][1] = 0; ch[1][0] = 2; ch[1][1] = 1; break;
+        case RMCV_BAYER_GR: ch[0][0] = 1; ch[0][1] = 2; ch[1][0] = 0; ch[1][1] = 1; break;
+        case RMCV_BAYER_RG: ch[0][0] = 2; ch[0][1] = 1; ch[1][0] = 1; ch[1][1] = 0; break;
+        default: return cudaErrorInvalidValue;
+    }
+    const int plus = L.target == RMCV_CAMP_BLUE ? 0 : 2;   // src/imgproc.cpp:56-65: blue = B - R, otherwise R - B
+    int py = 0, px = 0;
+    for (int y = 0; y < 2; ++y) for (int x = 0; x < 2; ++x) if (ch[y][x] == plus) { py = y; px = x; }
+
+    StripParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = L.src; p.pitch = L.pitch; p.frame_stride = L.frame_stride;
+    p.mask = L.mask; p.mask_pitch = L.mask_pitch; p.mask_frame_stride = L.mask_frame_stride;
+    p.bits16 = reinterpret_cast<uint16_t*>(L.bits);
+    p.W = L.W; p.H = L.H; p.NC = L.W / 16; p.WB2 = 2 * ((L.W + 31) / 32);
+    p.nwx = (p.NC + 29) / 30;
+    // segment height: tall segments amortise the six halo rows; small batches need more, shorter segments
+    int seg = 64;
+    const char* es = getenv("RMCV_STRIP_SEG");
+    if (es && atoi(es) > 0) seg = atoi(es) & ~1;
+    else while (seg > 8 && (long long)L.batch * ((L.H + seg - 1) / seg) * p.nwx < 24LL * sm_count) seg >>= 1;
+    if (seg > L.H) seg = L.H;
+    if (seg < 2) seg = 2;
+    p.seg = seg; p.nseg = (L.H + seg - 1) / seg;
+    const long long total = (long long)L.batch * p.nseg * p.nwx;
+    if (total <= 0 || total > 0x7fffffffLL) return cudaErrorInvalidValue;
+    p.total_warps = (int)total;
+    const int lb = L.lower_bound < 1 ? 1 : (L.lower_bound > 255 ? 255 : L.lower_bound);
+    for (int x = 0; x < 4; ++x) {
+        const uint32_t bias = 1u << (12 + x);
+        p.kSP[x] = (bias + 3u - 4u * (uint32_t)lb) * kOne2;
+        p.kSM[x] = (bias - 4u * (uint32_t)lb) * kOne2;
+        p.kN[x] = (bias - 2u * (uint32_t)lb) * kOne2;
+    }
+    p.force_or = L.lower_bound <= 0 ? 0xffffu : 0u;
+    p.force_and = L.lower_bound > 255 ? 0u : 0xffffu;
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((total + wpb - 1) / wpb);
+    const int which = (py * 2 + px) * 2 + (L.mask ? 1 : 0);
+    switch (which) {
+        case 0: bayer_strip_kernel<0, 0, false><<<grid, wpb * 32, 0, st>>>(p); break;
+        case 1: bayer_strip_kernel<0, 0, true><<<grid, wpb * 32, 0, st>>>(p); break;
+        case 2: bayer_strip_kernel<0, 1, false><<<grid, wpb * 32, 0, st>>>(p); break;
+        case 3: bayer_strip_kernel<0, 1, true><<<grid, wpb * 32, 0, st>>>(p); break;
+        case 4: bayer_strip_kernel<1, 0, false><<<grid, wpb * 32, 0, st>>>(p); break;
+        case 5: bayer_strip_kernel<1, 0, true><<<grid, wpb * 32, 0, st>>>(p); break;
+        case 6: bayer_strip_kernel<1, 1, false><<<grid, wpb * 32, 0, st>>>(p); break;
+        default: bayer_strip_kernel<1, 1, true><<<grid, wpb * 32, 0, st>>>(p); break;
+    }
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace rmcv

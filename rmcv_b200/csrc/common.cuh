@@ -82,6 +82,7 @@ struct SlotBuffers {
     rmcv_contour_info* s_contours; // [CF][C]
     rmcv_lightblob* s_blobs;       // [CF][C]
     rmcv_armour* s_armours;        // [CF][A]
+    int32_t* arm_offset;           // [CF]  dense offset of the frame's armours in the result arrays (for the pose kernel)
     // staging for host-input calls
     uint8_t* frames;        // [CF][H][W*3] (allocated lazily)
     uint8_t* masks;         // [CF][H][W]   (allocated lazily)
@@ -109,6 +110,7 @@ struct rmcv_ctx {
     rmcv_contour_info* h_contours;  // [max_batch][C]  (chunk-dense)
     rmcv_lightblob* h_blobs;        // [max_batch][C]
     rmcv_armour* h_armours;         // [max_batch][A]
+    rmcv_pose* h_poses;             // [max_batch][A], null unless a camera is set (rmcv_set_camera)
     // last call
     int last_batch, last_W, last_H;
     bool have_results;
@@ -148,6 +150,10 @@ struct PixelLaunch {
     int bayer_layout;   // 0 = BGR input
 };
 cudaError_t launch_pixel_stage(const PixelLaunch& p, int sm_count, cudaStream_t st, int64_t* launches);
+// Bayer fast path (bayer_strip.cu); cudaErrorNotSupported when the call does not qualify for it
+cudaError_t launch_bayer_strip(const PixelLaunch& p, int sm_count, cudaStream_t st, int64_t* launches);
+
+struct CameraSetup { double K[9], dist[5], M[16]; int has_M; float w, h; };
 
 struct FrameLaunch {
     Geometry g; int frames; SlotBuffers* sb;
@@ -157,6 +163,8 @@ struct FrameLaunch {
     rmcv_contour_info* o_contours;
     rmcv_lightblob* o_blobs;
     rmcv_armour* o_armours;
+    rmcv_pose* o_poses;           // null unless a camera is set
+    const CameraSetup* camera;
 };
 // everything after the pixel stage for one chunk (five launches: emit, label, contour sums, fits, order/pairs/write-out);
 // stage_done(arg, RMCV_STAGE_*, stream) is called after each launch (profiling events), may be null
@@ -200,6 +208,9 @@ cudaError_t launch_overlap(const rmcv_lightblob* d_blobs, int n, int left, int r
 cudaError_t launch_pnp(const rmcv_armour* d_armours, int n, const double K[9], const double dist[5], float w, float h,
                        float roi_x, float roi_y, const double* cam2world, rmcv_pose* d_out, cudaStream_t st, int64_t* launches);
 
+// pose of every armour of a chunk, written next to the armours in the dense result array (pnp.cu)
+cudaError_t launch_chunk_poses(const SlotBuffers& sb, int frames, int A, rmcv_pose* o_poses, const CameraSetup& cam,
+                               cudaStream_t st, int64_t* launches);
 cudaError_t launch_frontend(const uint8_t* d_src, size_t pitch, size_t frame_stride, uint8_t* d_dst, size_t dpitch,
                             size_t dframe_stride, int W, int H, int batch, int bits, int mirror, int flip, cudaStream_t st,
                             int64_t* launches);

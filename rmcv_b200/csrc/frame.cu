@@ -726,6 +726,7 @@ __global__ void __launch_bounds__(128) order_kernel(const OrderParams p) {
         fi.contour_offset = (int32_t)base_c; fi.blob_offset = (int32_t)base_b; fi.armour_offset = (int32_t)base_a;
         fi.flags = s_flags;
         p.o_frames[p.frame_base + frame] = fi;
+        sb.arm_offset[frame] = (int32_t)base_a;
     }
     copy_words(p.o_contours + base_c, oc, (size_t)s_nc * sizeof(rmcv_contour_info), tid, NT);
     copy_words(p.o_blobs + base_b, ob, (size_t)P * sizeof(rmcv_lightblob), tid, NT);
@@ -808,6 +809,9 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         order_kernel<<<L.frames, 128, smem, so>>>(p);
         if (launches) ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (L.o_poses && L.camera) {   // f1 fused: rm::solve_PnP for every armour of the chunk
+            if ((e = launch_chunk_poses(*L.sb, L.frames, L.g.A, L.o_poses, *L.camera, so, launches)) != cudaSuccess) return e;
+        }
         if (stage_done) stage_done(stage_arg, RMCV_STAGE_ORDER, so);
     }
     return cudaSuccess;

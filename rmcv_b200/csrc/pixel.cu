@@ -573,7 +573,11 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
         return cudaGetLastError();
     }
 
-    // ---- Bayer
+    // ---- Bayer: blue / red targets on 16-pixel-aligned frames take the register-resident strip kernel (bayer_strip.cu)
+    if (env_int("RMCV_BAYER_GENERIC", 0) == 0) {
+        const cudaError_t se = launch_bayer_strip(L, sm_count, st, launches);
+        if (se != cudaErrorNotSupported) return se;
+    }
     BayerSite site;
     {
         // colour sampled at (y&1, x&1) for the Daheng layouts (0=B,1=G,2=R)

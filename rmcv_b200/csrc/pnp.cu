@@ -33,6 +33,48 @@ __global__ void __launch_bounds__(64) pnp_kernel(const PnpParams p) {
     p.out[i] = o;
 }
 
+// Fused variant: thread (frame, k) solves armour k of the frame straight from / into the dense result arrays.
+struct ChunkPoseParams {
+    const FrameCounters* counters; const int32_t* arm_offset;
+    const rmcv_armour* armours;   // [frames][A] device staging of the write-out kernel
+    rmcv_pose* poses;             // dense pinned result array
+    int A;
+    CameraSetup cam;
+};
+
+__global__ void __launch_bounds__(64) chunk_pose_kernel(const ChunkPoseParams p) {
+    const int frame = blockIdx.x;
+    const int n = p.counters[frame].n_armours;
+    const size_t base = (size_t)p.arm_offset[frame];
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const rmcv_armour& a = p.armours[(size_t)frame * p.A + k];
+        float pts[4][2];
+        for (int i = 0; i < 4; ++i) { pts[i][0] = a.vertices[i][0]; pts[i][1] = a.vertices[i][1]; }
+        PnpResult r;
+        rmcv_pose o;
+        memset(&o, 0, sizeof(o));
+        o.ok = solve_pnp_square(pts, p.cam.K, p.cam.dist, p.cam.w, p.cam.h, 0.f, 0.f, &r) ? 1 : 0;
+        if (o.ok) {
+            for (int i = 0; i < 3; ++i) { o.rvec[i] = r.rvec[i]; o.tvec[i] = r.tvec[i]; }
+            o.reproj_err = r.err;
+            for (int i = 0; i < 3; ++i)
+                o.position[i] = p.cam.has_M ? p.cam.M[4 * i] * r.tvec[0] + p.cam.M[4 * i + 1] * r.tvec[1] + p.cam.M[4 * i + 2] * r.tvec[2] + p.cam.M[4 * i + 3]
+                                            : r.tvec[i];
+        }
+        p.poses[base + k] = o;
+    }
+}
+
+cudaError_t launch_chunk_poses(const SlotBuffers& sb, int frames, int A, rmcv_pose* o_poses, const CameraSetup& cam,
+                               cudaStream_t st, int64_t* launches) {
+    if (frames <= 0) return cudaSuccess;
+    ChunkPoseParams p;
+    p.counters = sb.counters; p.arm_offset = sb.arm_offset; p.armours = sb.s_armours; p.poses = o_poses; p.A = A; p.cam = cam;
+    chunk_pose_kernel<<<frames, 64, 0, st>>>(p);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pnp(const rmcv_armour* d_armours, int n, const double K[9], const double dist[5], float w, float h,
                        float roi_x, float roi_y, const double* cam2world, rmcv_pose* d_out, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;

@@ -137,6 +137,37 @@ def test_solve_pnp_matches_cv2(ctx):
         ctx.solve_pnp(arm[:1], O.MAIN_CAMMAT, O.MAIN_DISCOF, (27.0, 20.0))
 
 
+def test_fused_poses_in_detect_results(ctx):
+    """f1 fused: with rmcv_set_camera every detect call also solves the pose of every armour it finds; poses[k] belongs
+    to armours[k] and equals the standalone rmcv_solve_pnp / cv2 result.  rmcv_clear_camera turns it off."""
+    frames = np.stack([synth.make_frame(s, 1280, 1024, 10 + s % 9) for s in range(440, 442)])
+    M = np.array([[0.0, 0.0, -1.0, -27.0], [1.0, 0.0, 0.0, -51.0], [0.0, -1.0, 0.0, 77.0], [0.0, 0.0, 0.0, 1.0]])
+    res = ctx.detect_batch_host(frames, rb.default_params())
+    assert not res.poses
+    ctx.set_camera(O.MAIN_CAMMAT, O.MAIN_DISCOF, (27.0, 27.0), cam2world=M)
+    try:
+        res = ctx.detect_batch_host(frames, rb.default_params())
+        assert res.poses
+        n = 0
+        for f in range(len(frames)):
+            det = ctx.frame_detections(res, f)
+            assert len(det.poses) == len(det.armours)
+            alone = ctx.solve_pnp(det.armours, O.MAIN_CAMMAT, O.MAIN_DISCOF, (27.0, 27.0), cam2world=M)
+            for a, (rvec, tvec, pos, ok), (rvec2, tvec2, pos2, ok2) in zip(det.armours, det.poses, alone):
+                assert ok and ok2
+                assert np.array_equal(rvec, rvec2) and np.array_equal(tvec, tvec2) and np.array_equal(pos, pos2)
+                rr, rt = O.solve_pnp(a.vertices)
+                assert np.abs(rvec - rr).max() <= 1e-8 and (np.abs(tvec - rt) / np.abs(rt).max()).max() <= 1e-8
+                n += 1
+        assert n >= 20
+        with pytest.raises(rb.RmcvError):
+            ctx.set_camera(O.MAIN_CAMMAT, O.MAIN_DISCOF, (27.0, 20.0))
+    finally:
+        ctx.clear_camera()
+    res = ctx.detect_batch_host(frames, rb.default_params())
+    assert not res.poses
+
+
 @pytest.mark.parametrize("bits,mirror,flip", [(8, False, False), (8, True, False), (10, False, True), (12, True, True), (12, False, False)])
 def test_camera_frontend_variants(ctx, bits, mirror, flip):
     """f4 (next row): 8/10/12-bit mosaics with mirror / flip (hardware/src/daheng.cpp:91-187) -> front-end kernel ->
