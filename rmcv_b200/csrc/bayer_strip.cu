@@ -28,8 +28,9 @@ namespace rmcv {
 namespace {
 
 struct StripParams {
-    const uint8_t* src; size_t pitch, frame_stride;
-    uint8_t* mask; size_t mask_pitch, mask_frame_stride;   // mask may be null
+    const uint8_t* src; size_t frame_stride;
+    uint8_t* mask; size_t mask_frame_stride;               // mask may be null
+    int pitch, mask_pitch;                                 // row pitches in bytes (< 2^31)
     uint16_t* bits16;            // bit mask viewed as 16-bit words, [batch][H][WB2]
     int W, H, NC, WB2;           // NC = W / 16 pixel groups per row, WB2 = 16-bit words per bit row
     int seg, nseg, nwx;          // rows per segment (even), segments per frame, warps per strip row
@@ -43,6 +44,27 @@ struct RowPrep {   // one raw row: samples U[j] = (x = 2j+s, x = 2j+8+s) and pai
 };
 
 constexpr uint32_t kOne2 = 0x00010001u;
+
+// Per-lane ring of raw rows in shared memory, filled by cp.async (LDGSTS): a lane only ever reads back the 16 bytes it
+// asked for itself, so the groups need no barrier, only cp.async.wait_group.
+constexpr int kStages = 4;                      // row pairs in flight per lane
+constexpr uint32_t kStageBytes = 2u * 32u * 16u;   // two rows x 32 lanes x 16 B per warp and stage
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint2 lds64(uint32_t saddr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) { return (a & m) | (b & ~m); }
 
@@ -104,15 +126,17 @@ struct Walk {
     uint32_t fix_mask, fix_rot;  // border columns: bit 0 of group 0 shows bit 1 (rotate right 1), bit 15 of the last group bit 14
     const uint8_t* lp;           // raw row `lr` (clamped into the image) at the column of this lane
     int lr;
+    uint32_t ring, stage;        // shared address of this lane's slot in stage 0; byte offset of the oldest stage
     uint8_t* mrow;               // byte-mask address of the next row to leave (or null)
     uint16_t* brow;              // bit-mask address of the next row to leave
+    uint32_t lut;                // shared address of the bits -> bytes table (2 KB aligned)
     int H;
-    bool writer, tail16;
+    int writer, tail16;          // this lane stores its group / also zeroes the odd 16-bit word that ends a W % 32 == 16 row
 };
 
 // One threshold row (row r) enters, the final row r-2 leaves (STORE: to memory).
 template <bool STORE, bool MASK>
-__device__ __forceinline__ void push_row(Walk& k, const StripParams& p, const uint2* lut, uint32_t t, int r) {
+__device__ __forceinline__ void push_row(Walk& k, const StripParams& p, uint32_t t, int r) {
     const uint32_t tl = __shfl_up_sync(0xffffffffu, t, 1), tr = __shfl_down_sync(0xffffffffu, t, 1);
     const uint32_t w = ((tl >> 14) | (t << 2) | (tr << 18)) & k.inside;
     const uint32_t h = w | (w << 1) | (w >> 1);
@@ -120,14 +144,14 @@ __device__ __forceinline__ void push_row(Walk& k, const StripParams& p, const ui
     k.h0 = k.h1; k.h1 = h;
     if ((unsigned)(r - 1) >= (unsigned)k.H) d = 0xffffffffu;   // so do rows outside the image
     const uint32_t e = d & (d << 1) & (d >> 1);
-    const uint32_t m = (k.e0 & k.e1 & e) >> 2 & 0xffffu;   // final row r-2
+    const uint32_t m = k.e0 & k.e1 & e;                     // final row r-2 in window bits 2..17
     k.e0 = k.e1; k.e1 = e;
     if (STORE) {
         if (k.writer) {
-            k.brow[0] = (uint16_t)m;
+            k.brow[0] = (uint16_t)(m >> 2);
             if (k.tail16) k.brow[1] = 0;
-            if (MASK) {
-                const uint2 a = lut[m & 255u], b = lut[m >> 8];
+            if (MASK) {   // table entries are 8 bytes: pixels 0..7 at (m >> 2 & 255) * 8, pixels 8..15 at (m >> 10 & 255) * 8
+                const uint2 a = lds64(((m << 1) & 0x7f8u) | k.lut), b = lds64(((m >> 7) & 0x7f8u) | k.lut);
                 __stcs(reinterpret_cast<uint4*>(k.mrow), make_uint4(a.x, a.y, b.x, b.y));
             }
         }
@@ -136,25 +160,33 @@ __device__ __forceinline__ void push_row(Walk& k, const StripParams& p, const ui
     }
 }
 
-// Loads the next raw row (rows outside the image read the nearest row inside; their results are never used).
-__device__ __forceinline__ uint4 next_row(Walk& k, const StripParams& p) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(k.lp));
-    if ((unsigned)k.lr < (unsigned)(k.H - 1)) k.lp += p.pitch;
+// Address of the next raw row (rows outside the image read the nearest row inside; their results are never used).
+__device__ __forceinline__ const uint8_t* next_row(Walk& k, const StripParams& p) {
+    const uint8_t* v = k.lp;
+    k.lp += (unsigned)k.lr < (unsigned)(k.H - 1) ? p.pitch : 0;
     ++k.lr;
     return v;
 }
+// Starts the copy of the next two raw rows into stage `off` of the lane's ring (one cp.async group).
+__device__ __forceinline__ void fetch_pair(Walk& k, const StripParams& p, uint32_t off) {
+    cp_async16(k.ring + off, next_row(k, p));
+    cp_async16(k.ring + off + 512u, next_row(k, p));
+    cp_commit();
+}
 
-// Row pair (r, r+1), r even.  On entry A = prep(r-1), C = prep(r) and (ra, rb) hold the raw rows r+1, r+2.  On exit
-// B = prep(r+1), N = prep(r+2) are the (A, C) of the next pair and (ra, rb) hold the raw rows r+5, r+6.
+// Row pair (r, r+1), r even.  On entry A = prep(r-1), C = prep(r) and the oldest stage of the ring holds the raw rows
+// r+1, r+2.  On exit B = prep(r+1), N = prep(r+2) are the (A, C) of the next pair and the stage is being refilled with the
+// rows r+1+2*kStages, r+2+2*kStages.
 template <int PY, int PX, bool STORE, bool MASK>
-__device__ __forceinline__ void row_pair(Walk& k, const StripParams& p, const uint2* lut, const RowPrep& A, const RowPrep& C,
-                                         RowPrep& B, RowPrep& N, uint4& ra, uint4& rb, int r) {
+__device__ __forceinline__ void row_pair(Walk& k, const StripParams& p, const RowPrep& A, const RowPrep& C,
+                                         RowPrep& B, RowPrep& N, int r) {
     constexpr bool kEvenIsP = PY == 0;
     constexpr int kSxEven = kEvenIsP ? PX : 1 - PX, kSxOdd = 1 - kSxEven;   // x parity of the samples in even / odd rows
-    prep_row<kSxOdd>(ra, B);
-    prep_row<kSxEven>(rb, N);
-    ra = next_row(k, p);
-    rb = next_row(k, p);
+    cp_wait<kStages - 1>();
+    prep_row<kSxOdd>(lds128(k.ring + k.stage), B);
+    prep_row<kSxEven>(lds128(k.ring + k.stage + 512u), N);
+    fetch_pair(k, p, k.stage);
+    k.stage = (k.stage + kStageBytes) & (kStages * kStageBytes - 1u);
     uint32_t t0 = thr_row<kEvenIsP, kSxEven>(A, C, B, p);
     uint32_t t1 = thr_row<!kEvenIsP, kSxOdd>(C, B, N, p);
     if (r == 0) t0 = t1;                                 // row 0 shows row 1
@@ -162,16 +194,18 @@ __device__ __forceinline__ void row_pair(Walk& k, const StripParams& p, const ui
     t0 = bitsel(__funnelshift_r(t0, t0, k.fix_rot), t0, k.fix_mask);   // column 0 shows column 1, column W-1 column W-2
     t1 = bitsel(__funnelshift_r(t1, t1, k.fix_rot), t1, k.fix_mask);
     if ((unsigned)r >= (unsigned)k.H) { t0 = 0u; t1 = 0u; }   // a pair is either inside or outside the image (r, H even)
-    push_row<STORE, MASK>(k, p, lut, t0, r);
-    push_row<STORE, MASK>(k, p, lut, t1, r + 1);
+    push_row<STORE, MASK>(k, p, t0, r);
+    push_row<STORE, MASK>(k, p, t1, r + 1);
 }
 
 }  // namespace
 
 // PY, PX: parity of the rows / columns that sample the plus channel (the minus channel sits on the opposite diagonal)
-template <int PY, int PX, bool MASK>
-__global__ void __launch_bounds__(256) bayer_strip_kernel(const StripParams p) {
-    __shared__ uint2 s_lut[256];
+template <int PY, int PX, bool MASK, int MINB>
+__global__ void __launch_bounds__(256, MINB) bayer_strip_kernel(const StripParams p) {
+    __shared__ __align__(16) uint2 s_lut_raw[512];   // the table is placed on a 2 KB boundary of the shared window, so
+                                                     // that index and base combine with OR
+    __shared__ __align__(16) uint8_t s_ring[8 * kStages * kStageBytes];   // 8 warps
     {
         const uint32_t i = threadIdx.x;
         if (i < 256) {
@@ -180,7 +214,8 @@ __global__ void __launch_bounds__(256) bayer_strip_kernel(const StripParams p) {
                 asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(nib * 0x10204080u));
                 return r;
             };
-            s_lut[i] = make_uint2(expand4(i & 15u), expand4(i >> 4));
+            const uint32_t base = ((uint32_t)__cvta_generic_to_shared(s_lut_raw) + 2047u) & ~2047u;
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(base + i * 8u), "r"(expand4(i & 15u)), "r"(expand4(i >> 4)) : "memory");
         }
     }
     __syncthreads();
@@ -204,6 +239,8 @@ __global__ void __launch_bounds__(256) bayer_strip_kernel(const StripParams p) {
     k.H = H;
     k.writer = lane >= 1 && lane <= 30 && c < NC;
     k.tail16 = k.writer && c == NC - 1 && (p.WB2 > NC);      // W % 32 == 16: the upper half of the last bit word is zero
+    asm volatile("" : "+r"(k.writer), "+r"(k.tail16));       // keep the flags in registers (no rematerialisation per row)
+    k.lut = ((uint32_t)__cvta_generic_to_shared(s_lut_raw) + 2047u) & ~2047u;
     k.mrow = MASK ? p.mask + (size_t)frame * p.mask_frame_stride + (size_t)y0 * p.mask_pitch + (size_t)cc * 16 : nullptr;
     k.brow = p.bits16 + ((size_t)frame * H + y0) * p.WB2 + cc;
 
@@ -212,19 +249,25 @@ __global__ void __launch_bounds__(256) bayer_strip_kernel(const StripParams p) {
     int r = y0 - 2;
     k.lr = r - 1;
     k.lp = p.src + (size_t)frame * p.frame_stride + (size_t)min(max(k.lr, 0), H - 1) * p.pitch + (size_t)cc * 16;
-    prep_row<kSxOdd>(next_row(k, p), s0);
-    prep_row<kSxEven>(next_row(k, p), s1);
-    uint4 a0 = next_row(k, p), b0 = next_row(k, p);   // rows r+1, r+2
-    uint4 a1 = next_row(k, p), b1 = next_row(k, p);   // rows r+3, r+4; every pair then fetches the rows r+5, r+6
+    k.ring = (uint32_t)__cvta_generic_to_shared(s_ring) + (threadIdx.x >> 5) * (kStages * kStageBytes) + lane * 16u;
+    k.stage = 0u;
+    {
+        const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(next_row(k, p)));
+        const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(next_row(k, p)));
+#pragma unroll
+        for (int st = 0; st < kStages; ++st) fetch_pair(k, p, st * kStageBytes);   // rows r+1 .. r+2*kStages
+        prep_row<kSxOdd>(w0, s0);
+        prep_row<kSxEven>(w1, s1);
+    }
     // rows y0-2 .. y0+1 fill the pipeline; from the pair at y0+2 on, every pair releases two final rows
-    row_pair<PY, PX, false, MASK>(k, p, s_lut, s0, s1, s2, s3, a0, b0, r);
-    row_pair<PY, PX, false, MASK>(k, p, s_lut, s2, s3, s0, s1, a1, b1, r + 2);
+    row_pair<PY, PX, false, MASK>(k, p, s0, s1, s2, s3, r);
+    row_pair<PY, PX, false, MASK>(k, p, s2, s3, s0, s1, r + 2);
     r += 4;
     while (true) {                                          // the last pair starts at y1
-        row_pair<PY, PX, true, MASK>(k, p, s_lut, s0, s1, s2, s3, a0, b0, r);
+        row_pair<PY, PX, true, MASK>(k, p, s0, s1, s2, s3, r);
         r += 2;
         if (r > y1) break;
-        row_pair<PY, PX, true, MASK>(k, p, s_lut, s2, s3, s0, s1, a1, b1, r);
+        row_pair<PY, PX, true, MASK>(k, p, s2, s3, s0, s1, r);
         r += 2;
         if (r > y1) break;
     }
@@ -251,16 +294,28 @@ cudaError_t launch_bayer_strip(const PixelLaunch& L, int sm_count, cudaStream_t 
 
     StripParams p;
     memset(&p, 0, sizeof(p));
-    p.src = L.src; p.pitch = L.pitch; p.frame_stride = L.frame_stride;
-    p.mask = L.mask; p.mask_pitch = L.mask_pitch; p.mask_frame_stride = L.mask_frame_stride;
+    if (L.pitch > 0x7fffffffu || L.mask_pitch > 0x7fffffffu) return cudaErrorNotSupported;
+    p.src = L.src; p.pitch = (int)L.pitch; p.frame_stride = L.frame_stride;
+    p.mask = L.mask; p.mask_pitch = (int)L.mask_pitch; p.mask_frame_stride = L.mask_frame_stride;
     p.bits16 = reinterpret_cast<uint16_t*>(L.bits);
     p.W = L.W; p.H = L.H; p.NC = L.W / 16; p.WB2 = 2 * ((L.W + 31) / 32);
     p.nwx = (p.NC + 29) / 30;
-    // segment height: tall segments amortise the six halo rows; small batches need more, shorter segments
-    int seg = 64;
+    // segment height: tall segments amortise the six halo rows, but the warps of a launch should fill whole waves of the
+    // resident warp slots (3 CTAs of 8 warps per SM): pick the even height with the least waves x (rows + halo)
+    int seg = 0;
+    const char* eb1 = getenv("RMCV_STRIP_MINB");
+    const int eb0 = eb1 ? atoi(eb1) : 3;
     const char* es = getenv("RMCV_STRIP_SEG");
     if (es && atoi(es) > 0) seg = atoi(es) & ~1;
-    else while (seg > 8 && (long long)L.batch * ((L.H + seg - 1) / seg) * p.nwx < 24LL * sm_count) seg >>= 1;
+    else {
+        const long long slots = (eb0 >= 4 ? 32LL : 24LL) * sm_count;
+        long long best = -1;
+        for (int sg = 16; sg <= 128; sg += 2) {
+            const long long warps = (long long)L.batch * ((L.H + sg - 1) / sg) * p.nwx;
+            const long long cost = ((warps + slots - 1) / slots) * (sg + 8);
+            if (best < 0 || cost < best) { best = cost; seg = sg; }
+        }
+    }
     if (seg > L.H) seg = L.H;
     if (seg < 2) seg = 2;
     p.seg = seg; p.nseg = (L.H + seg - 1) / seg;
@@ -279,16 +334,19 @@ cudaError_t launch_bayer_strip(const PixelLaunch& L, int sm_count, cudaStream_t 
     const int wpb = 8;
     const unsigned grid = (unsigned)((total + wpb - 1) / wpb);
     const int which = (py * 2 + px) * 2 + (L.mask ? 1 : 0);
+    const char* eb = getenv("RMCV_STRIP_MINB");
+    const int minb = eb ? atoi(eb) : 3;
+#define RMCV_STRIP_CASE(n, PY_, PX_, M_)                                                                     \
+    case n:                                                                                                  \
+        if (minb >= 4) bayer_strip_kernel<PY_, PX_, M_, 4><<<grid, wpb * 32, 0, st>>>(p);                    \
+        else bayer_strip_kernel<PY_, PX_, M_, 3><<<grid, wpb * 32, 0, st>>>(p);                              \
+        break;
     switch (which) {
-        case 0: bayer_strip_kernel<0, 0, false><<<grid, wpb * 32, 0, st>>>(p); break;
-        case 1: bayer_strip_kernel<0, 0, true><<<grid, wpb * 32, 0, st>>>(p); break;
-        case 2: bayer_strip_kernel<0, 1, false><<<grid, wpb * 32, 0, st>>>(p); break;
-        case 3: bayer_strip_kernel<0, 1, true><<<grid, wpb * 32, 0, st>>>(p); break;
-        case 4: bayer_strip_kernel<1, 0, false><<<grid, wpb * 32, 0, st>>>(p); break;
-        case 5: bayer_strip_kernel<1, 0, true><<<grid, wpb * 32, 0, st>>>(p); break;
-        case 6: bayer_strip_kernel<1, 1, false><<<grid, wpb * 32, 0, st>>>(p); break;
-        default: bayer_strip_kernel<1, 1, true><<<grid, wpb * 32, 0, st>>>(p); break;
+        RMCV_STRIP_CASE(0, 0, 0, false) RMCV_STRIP_CASE(1, 0, 0, true) RMCV_STRIP_CASE(2, 0, 1, false) RMCV_STRIP_CASE(3, 0, 1, true)
+        RMCV_STRIP_CASE(4, 1, 0, false) RMCV_STRIP_CASE(5, 1, 0, true) RMCV_STRIP_CASE(6, 1, 1, false) RMCV_STRIP_CASE(7, 1, 1, true)
+        default: return cudaErrorInvalidValue;
     }
+#undef RMCV_STRIP_CASE
     if (launches) ++*launches;
     return cudaGetLastError();
 }
