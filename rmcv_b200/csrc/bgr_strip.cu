@@ -1,0 +1,252 @@
+// K1 (fast path) — register-resident pixel stage of rm::extract_color on interleaved BGR frames (src/imgproc.cpp:52-69):
+// cv::split + saturating channel difference + inRange + 3x3 MORPH_CLOSE -> {0,255} byte mask and the same mask bit-packed
+// for the labelling stages.  HBM-bound streaming kernel, no tensor cores (nothing here is a contraction).
+//
+//   * pixel groups of 16 pixels (48 bytes) are numbered through the whole call: slot = (frame, row segment, group), group
+//     fastest.  A warp owns 30 consecutive slots (+ one halo lane each side) and every lane walks down its segment of rows;
+//     neighbouring lanes are neighbouring groups of the same rows except across an image edge, where the close pads anyway,
+//     so 30 of 32 lanes do useful work whatever the image width;
+//   * a lane copies its 48 bytes of a row with three cp.async (LDGSTS) into its own slice of a 3-row ring in shared
+//     memory, rows ahead of the arithmetic, and reads them back with three conflict-free LDS.128 — no barrier, a
+//     lane only reads what it asked for itself;
+//   * per 4 pixels 6 dp4a form c_a - c_b - lower_bound and funnel shifts collect the sign bits into a 16-bit threshold
+//     word; the close runs on a 20-bit window in registers (strip.cuh) and the byte mask leaves through the bits -> bytes
+//     table with one 16-byte streaming store per lane and row.
+//
+// About 6 thread instructions per pixel (the shared-memory band kernel in pixel.cu: 15.5), which leaves the issue slots of
+// an SM to the labelling kernels that run beside it.
+#include "strip.cuh"
+
+namespace rmcv {
+
+namespace {
+
+constexpr int kRows = 3;                       // rows in flight per lane (36 KB of ring per CTA)
+constexpr uint32_t kRowBytes = 32u * 48u;      // one row of a warp's ring
+constexpr int kWarps = 8;
+
+struct BgrStripParams {
+    const uint8_t* src; size_t frame_stride;
+    uint8_t* mask; size_t mask_frame_stride;   // mask may be null
+    int pitch, mask_pitch;                     // row pitches in bytes (< 2^31)
+    uint16_t* bits16;                          // bit mask viewed as 16-bit words, [batch][H][WB2]
+    int W, H, NC, WB2;                         // NC = W / 16 groups per row, WB2 = 16-bit words per bit row
+    int seg, nseg;                             // rows per segment, segments per frame
+    int total_slots, total_warps;
+    uint32_t coef[6];                          // dp4a coefficient words (signed bytes) for the 4 pixels of a 12-byte group
+    int acc0;                                  // -lower_bound (or the constants that force all-0 / all-1)
+    int* work_counter;                         // persistent launches: next work item (zeroed before the launch)
+};
+
+__device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
+
+// threshold word of 16 interleaved BGR pixels (bit x = pixel x passes)
+__device__ __forceinline__ uint32_t thr16(const uint4 A, const uint4 B, const uint4 C, const BgrStripParams& p) {
+    const uint32_t w[12] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x, C.y, C.z, C.w};
+    const uint32_t c0 = p.coef[0], c1a = p.coef[1], c1b = p.coef[2], c2a = p.coef[3], c2b = p.coef[4], c3 = p.coef[5];
+    const int acc0 = p.acc0;
+    uint32_t nb = 0;  // sign bits of (diff - lb), pixel 15 first so that pixel 0 lands in bit 0
+#pragma unroll
+    for (int grp = 3; grp >= 0; --grp) {
+        const uint32_t w0 = w[3 * grp], w1 = w[3 * grp + 1], w2 = w[3 * grp + 2];
+        const int v3 = dp4a_us(w2, c3, acc0);
+        const int v2 = dp4a_us(w1, c2a, dp4a_us(w2, c2b, acc0));
+        const int v1 = dp4a_us(w0, c1a, dp4a_us(w1, c1b, acc0));
+        const int v0 = dp4a_us(w0, c0, acc0);
+        nb = __funnelshift_l((uint32_t)v3, nb, 1);
+        nb = __funnelshift_l((uint32_t)v2, nb, 1);
+        nb = __funnelshift_l((uint32_t)v1, nb, 1);
+        nb = __funnelshift_l((uint32_t)v0, nb, 1);
+    }
+    return ~nb & 0xffffu;
+}
+
+struct Lane {
+    strip::CloseLane k;
+    const uint8_t* lp;       // raw row `lr` (clamped into the image) of this lane's group
+    int lr;
+    uint32_t ring, stage;    // shared address of the lane's slice of ring row 0; byte offset of the oldest row
+    int r;                   // image row of the threshold word that enters next
+    int left;                // rows this lane still has to store (0 for halo / idle lanes)
+    int tail16;
+};
+
+__device__ __forceinline__ void fetch_row(Lane& a, const BgrStripParams& p, uint32_t off) {
+    const uint8_t* g = a.lp;
+    a.lp += (unsigned)a.lr < (unsigned)(p.H - 1) ? p.pitch : 0;   // rows outside the image re-read the nearest row inside
+    ++a.lr;
+    strip::cp_async16_ca(a.ring + off, g);
+    strip::cp_async16_ca(a.ring + off + 16u, g + 16);
+    strip::cp_async16_ca(a.ring + off + 32u, g + 32);
+    strip::cp_commit();
+}
+
+template <bool STORE, bool MASK>
+__device__ __forceinline__ void one_row(Lane& a, const BgrStripParams& p) {
+    strip::cp_wait<kRows - 1>();
+    const uint32_t s = a.ring + a.stage;
+    const uint4 A = strip::lds128(s), B = strip::lds128(s + 16u), C = strip::lds128(s + 32u);
+    uint32_t t = thr16(A, B, C, p);
+    fetch_row(a, p, a.stage);
+    a.stage += kRowBytes;
+    if (a.stage == kRows * kRowBytes) a.stage = 0u;
+    if ((unsigned)a.r >= (unsigned)p.H) t = 0u;
+    strip::push_row<STORE, MASK>(a.k, p.WB2, p.mask_pitch, t, (unsigned)(a.r - 1) >= (unsigned)p.H, a.left > 0,
+                                 a.left > 0 && a.tail16);
+    if (STORE) --a.left;
+    ++a.r;
+}
+
+}  // namespace
+
+// One work item: 30 consecutive slots (+ halo lanes) walked down their row segments.
+template <bool MASK>
+__device__ __forceinline__ void walk_item(const BgrStripParams& p, int item, int lane, uint32_t ring, uint32_t lut) {
+    const int slot = item * 30 - 1 + lane;                   // lanes 0 and 31 only feed their neighbours
+    const bool valid = slot >= 0 && slot < p.total_slots;
+    const int sc = min(max(slot, 0), p.total_slots - 1);
+    const int c = sc % p.NC, q = sc / p.NC;
+    const int sg = q % p.nseg, frame = q / p.nseg;
+    const int y0 = sg * p.seg;
+    Lane a;
+    a.k.h0 = a.k.h1 = 0u; a.k.e0 = a.k.e1 = 0u;
+    uint32_t inside = 0xfffffu;
+    if (c == 0) inside &= 0xffffcu;
+    if (c == p.NC - 1) inside &= 0x3ffffu;
+    a.k.inside = valid ? inside : 0u;
+    a.k.lut = lut;
+    a.k.mrow = MASK ? p.mask + (size_t)frame * p.mask_frame_stride + (size_t)y0 * p.mask_pitch + (size_t)c * 16 : nullptr;
+    a.k.brow = p.bits16 + ((size_t)frame * p.H + y0) * p.WB2 + c;
+    const bool writer = valid && lane >= 1 && lane <= 30;
+    a.left = writer ? min(p.seg, p.H - y0) : 0;
+    a.tail16 = (c == p.NC - 1 && p.WB2 > p.NC) ? 1 : 0;      // W % 32 == 16: the upper half of the last bit word is zero
+    a.r = y0 - 2;
+    a.lr = a.r;
+    a.lp = p.src + (size_t)frame * p.frame_stride + (size_t)min(max(a.lr, 0), p.H - 1) * p.pitch + (size_t)c * 48;
+    a.ring = ring;
+    a.stage = 0u;
+#pragma unroll
+    for (int st = 0; st < kRows; ++st) fetch_row(a, p, st * kRowBytes);
+    // rows y0-2 .. y0+1 fill the pipeline; every later row releases one final row
+#pragma unroll
+    for (int i = 0; i < 4; ++i) one_row<false, MASK>(a, p);
+#pragma unroll 2
+    for (int i = 0; i < p.seg; ++i) one_row<true, MASK>(a, p);
+    strip::cp_wait<0>();                                      // the rows fetched past the segment: the ring is reused
+}
+
+// PERSIST: the grid is a fixed number of CTAs per SM and every warp draws work items from a counter until none is left
+// (the kernel then holds a fixed share of each SM while the labelling kernels of the previous chunk run beside it);
+// otherwise one item per warp.
+template <bool MASK, int MINB, bool PERSIST>
+__global__ void __launch_bounds__(kWarps * 32, MINB) bgr_strip_kernel(const BgrStripParams p) {
+    __shared__ __align__(16) uint8_t s_lut_raw[4096];
+    __shared__ __align__(16) uint8_t s_ring[kWarps * kRows * kRowBytes];
+    strip::lut_init(s_lut_raw, threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_ring) + (threadIdx.x >> 5) * (kRows * kRowBytes) + lane * 48u;
+    const uint32_t lut = strip::lut_base(s_lut_raw);
+    if (PERSIST) {
+        while (true) {
+            int item = 0;
+            if (lane == 0) item = atomicAdd(p.work_counter, 1);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= p.total_warps) break;
+            walk_item<MASK>(p, item, lane, ring, lut);
+        }
+    } else {
+        const int wid = blockIdx.x * kWarps + (threadIdx.x >> 5);
+        if (wid < p.total_warps) walk_item<MASK>(p, wid, lane, ring, lut);
+    }
+}
+
+// Fast path of the BGR pixel stage; cudaErrorNotSupported when the call does not qualify (the caller then runs the
+// shared-memory band kernel of pixel.cu).
+cudaError_t launch_bgr_strip(const PixelLaunch& L, int sm_count, cudaStream_t st, int64_t* launches) {
+    if ((L.W & 15) || L.W < 32 || L.H < 1) return cudaErrorNotSupported;
+    if ((L.pitch & 15) || (L.frame_stride & 15) || (((size_t)L.src) & 15)) return cudaErrorNotSupported;
+    if (L.mask && ((L.mask_pitch & 15) || (L.mask_frame_stride & 15) || (((size_t)L.mask) & 15))) return cudaErrorNotSupported;
+    if (L.pitch > 0x7fffffffu || L.mask_pitch > 0x7fffffffu) return cudaErrorNotSupported;
+    BgrStripParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = L.src; p.pitch = (int)L.pitch; p.frame_stride = L.frame_stride;
+    p.mask = L.mask; p.mask_pitch = (int)L.mask_pitch; p.mask_frame_stride = L.mask_frame_stride;
+    p.bits16 = reinterpret_cast<uint16_t*>(L.bits);
+    p.W = L.W; p.H = L.H; p.NC = L.W / 16; p.WB2 = 2 * ((L.W + 31) / 32);
+    {   // plus / minus channel (src/imgproc.cpp:56-65) as dp4a coefficient words: byte k of a 12-byte group belongs to pixel
+        // k/3, channel k%3; order: c0 (px0,w0) c1a (px1,w0) c1b (px1,w1) c2a (px2,w1) c2b (px2,w2) c3 (px3,w2)
+        int ca, cb;
+        if (L.target == RMCV_CAMP_GUIDELIGHT) { ca = 1; cb = 2; }
+        else if (L.target == RMCV_CAMP_BLUE) { ca = 0; cb = 2; }
+        else { ca = 2; cb = 0; }
+        auto put = [&](int slot, int px, int word) {
+            uint32_t v = 0;
+            for (int b = 0; b < 4; ++b) {
+                const int k = word * 4 + b;
+                if (k / 3 != px) continue;
+                const int ch = k % 3;
+                const int coef = (ch == ca ? 1 : 0) - (ch == cb ? 1 : 0);
+                v |= (uint32_t)(uint8_t)(int8_t)coef << (8 * b);
+            }
+            p.coef[slot] = v;
+        };
+        put(0, 0, 0); put(1, 1, 0); put(2, 1, 1); put(3, 2, 1); put(4, 2, 2); put(5, 3, 2);
+        // v = diff + acc0 >= 0  <=>  sat_u8(diff) in [lb, 255].  The two-word pixels add acc0 once (inner dp4a).
+        if (L.lower_bound <= 0) { for (int i = 0; i < 6; ++i) p.coef[i] = 0; p.acc0 = 0; }
+        else if (L.lower_bound > 255) { for (int i = 0; i < 6; ++i) p.coef[i] = 0; p.acc0 = -1; }
+        else p.acc0 = -L.lower_bound;
+    }
+    const char* eb = getenv("RMCV_STRIP_MINB");
+    const int minb = eb ? atoi(eb) : 3;
+    // segment height: tall segments amortise the four halo rows, but the warps of a launch should fill whole waves of the
+    // resident warp slots: the height with the least waves x (rows + halo)
+    int seg = 0;
+    const char* es = getenv("RMCV_STRIP_SEG");
+    if (es && atoi(es) > 0) seg = atoi(es);
+    else {
+        const long long slots = (long long)(minb >= 4 ? 4 : (minb <= 2 ? 2 : 3)) * kWarps * sm_count;
+        long long best = -1;
+        for (int sg = 16; sg <= 128; ++sg) {
+            const long long warps = ((long long)L.batch * ((L.H + sg - 1) / sg) * p.NC + 29) / 30;
+            const long long cost = ((warps + slots - 1) / slots) * (sg + 6);
+            if (best < 0 || cost < best) { best = cost; seg = sg; }
+        }
+    }
+    if (seg > L.H) seg = L.H;
+    if (seg < 1) seg = 1;
+    p.seg = seg; p.nseg = (L.H + seg - 1) / seg;
+    const long long total = (long long)L.batch * p.nseg * p.NC;
+    if (total <= 0 || total > 0x3fffffffLL) return cudaErrorNotSupported;
+    p.total_slots = (int)total;
+    p.total_warps = (int)((total + 29) / 30);
+    unsigned grid = (unsigned)((p.total_warps + kWarps - 1) / kWarps);
+    const char* ep = getenv("RMCV_PIX_PERSIST");
+    const int per_sm = ep ? atoi(ep) : 0;                  // CTAs per SM of a persistent launch (0: one item per warp)
+    const bool persist = per_sm > 0 && L.work_counter != nullptr && grid > (unsigned)(per_sm * sm_count);
+    if (persist) {
+        p.work_counter = L.work_counter;
+        cudaError_t e = cudaMemsetAsync(L.work_counter, 0, sizeof(int), st);
+        if (e != cudaSuccess) return e;
+        grid = (unsigned)(per_sm * sm_count);
+    }
+    const int which = (L.mask ? 1 : 0) + 2 * (minb >= 4 ? 2 : (minb <= 2 ? 0 : 1)) + (persist ? 6 : 0);
+    switch (which) {
+        case 0: bgr_strip_kernel<false, 2, false><<<grid, kWarps * 32, 0, st>>>(p); break;
+        case 1: bgr_strip_kernel<true, 2, false><<<grid, kWarps * 32, 0, st>>>(p); break;
+        case 2: bgr_strip_kernel<false, 3, false><<<grid, kWarps * 32, 0, st>>>(p); break;
+        case 3: bgr_strip_kernel<true, 3, false><<<grid, kWarps * 32, 0, st>>>(p); break;
+        case 4: bgr_strip_kernel<false, 4, false><<<grid, kWarps * 32, 0, st>>>(p); break;
+        case 5: bgr_strip_kernel<true, 4, false><<<grid, kWarps * 32, 0, st>>>(p); break;
+        case 6: case 8: case 10: bgr_strip_kernel<false, 3, true><<<grid, kWarps * 32, 0, st>>>(p); break;
+        default: bgr_strip_kernel<true, 3, true><<<grid, kWarps * 32, 0, st>>>(p); break;
+    }
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace rmcv

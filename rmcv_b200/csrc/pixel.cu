@@ -516,7 +516,13 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
 
     if (L.bayer_layout == 0) {
-        // ---- BGR
+        // ---- BGR.  The register-resident strip kernel (bgr_strip.cu) needs 2.5x fewer instructions per pixel but, with its
+        // many small copies in flight, it lengthens the memory latency the labelling kernels beside it see: the whole path
+        // is faster with the band kernel below.  RMCV_BGR_STRIP=1 selects the strip kernel.
+        if (env_int("RMCV_BGR_STRIP", 0) != 0) {
+            const cudaError_t se = launch_bgr_strip(L, sm_count, st, launches);
+            if (se != cudaErrorNotSupported) return se;
+        }
         int a, b;  // plus / minus channel (src/imgproc.cpp:56-65)
         if (L.target == RMCV_CAMP_GUIDELIGHT) { a = 1; b = 2; }
         else if (L.target == RMCV_CAMP_BLUE) { a = 0; b = 2; }
