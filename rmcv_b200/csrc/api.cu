@@ -100,7 +100,6 @@ int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
     RMCV_CUDA(ctx, dalloc(&sb.s_blobs, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.s_armours, CF * A));
     RMCV_CUDA(ctx, dalloc(&sb.arm_offset, CF));
-    RMCV_CUDA(ctx, dalloc(&sb.pix_counter, 4));
     (void)first;
     RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.ev_pix, cudaEventDisableTiming));
     RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.ev_lab, cudaEventDisableTiming));
@@ -113,7 +112,7 @@ int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
 void free_slot(SlotBuffers& sb) {
     cudaFree(sb.bits); cudaFree(sb.rows); cudaFree(sb.run_x); cudaFree(sb.run_y);
     cudaFree(sb.parent); cudaFree(sb.gparent); cudaFree(sb.run_cid); cudaFree(sb.sorted); cudaFree(sb.recs); cudaFree(sb.recs2); cudaFree(sb.comp_start); cudaFree(sb.acc); cudaFree(sb.comp_root); cudaFree(sb.comp_cnt); cudaFree(sb.comps);
-    cudaFree(sb.counters); cudaFree(sb.s_contours); cudaFree(sb.s_blobs); cudaFree(sb.s_armours); cudaFree(sb.arm_offset); cudaFree(sb.pix_counter);
+    cudaFree(sb.counters); cudaFree(sb.s_contours); cudaFree(sb.s_blobs); cudaFree(sb.s_armours); cudaFree(sb.arm_offset);
     if (sb.frames) cudaFree(sb.frames);
     if (sb.masks) cudaFree(sb.masks);
     if (sb.ev_pix) cudaEventDestroy(sb.ev_pix);
@@ -186,7 +185,6 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
     pl.mask = mask; pl.mask_pitch = mask_pitch; pl.mask_frame_stride = mask_frame_stride;
     pl.bits = sb.bits; pl.W = W; pl.H = H; pl.batch = frames;
     pl.target = prm.target; pl.lower_bound = prm.lower_bound; pl.bayer_layout = bayer_layout;
-    pl.work_counter = sb.pix_counter;
     RMCV_CUDA(ctx, launch_pixel_stage(pl, ctx->sm_count, sp, &ctx->kernel_launches));
     if (ps) cudaEventRecord(ps->pix[1], sp);
     RMCV_CUDA(ctx, cudaEventRecord(sb.ev_pix, sp));

@@ -35,7 +35,6 @@ struct BgrStripParams {
     int total_slots, total_warps;
     uint32_t coef[6];                          // dp4a coefficient words (signed bytes) for the 4 pixels of a 12-byte group
     int acc0;                                  // -lower_bound (or the constants that force all-0 / all-1)
-    int* work_counter;                         // persistent launches: next work item (zeroed before the launch)
 };
 
 __device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c) {
@@ -136,13 +135,10 @@ __device__ __forceinline__ void walk_item(const BgrStripParams& p, int item, int
     for (int i = 0; i < 4; ++i) one_row<false, MASK>(a, p);
 #pragma unroll 2
     for (int i = 0; i < p.seg; ++i) one_row<true, MASK>(a, p);
-    strip::cp_wait<0>();                                      // the rows fetched past the segment: the ring is reused
+    strip::cp_wait<0>();                                      // the rows fetched past the segment
 }
 
-// PERSIST: the grid is a fixed number of CTAs per SM and every warp draws work items from a counter until none is left
-// (the kernel then holds a fixed share of each SM while the labelling kernels of the previous chunk run beside it);
-// otherwise one item per warp.
-template <bool MASK, int MINB, bool PERSIST>
+template <bool MASK, int MINB>
 __global__ void __launch_bounds__(kWarps * 32, MINB) bgr_strip_kernel(const BgrStripParams p) {
     __shared__ __align__(16) uint8_t s_lut_raw[4096];
     __shared__ __align__(16) uint8_t s_ring[kWarps * kRows * kRowBytes];
@@ -150,19 +146,8 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) bgr_strip_kernel(const BgrS
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_ring) + (threadIdx.x >> 5) * (kRows * kRowBytes) + lane * 48u;
-    const uint32_t lut = strip::lut_base(s_lut_raw);
-    if (PERSIST) {
-        while (true) {
-            int item = 0;
-            if (lane == 0) item = atomicAdd(p.work_counter, 1);
-            item = __shfl_sync(0xffffffffu, item, 0);
-            if (item >= p.total_warps) break;
-            walk_item<MASK>(p, item, lane, ring, lut);
-        }
-    } else {
-        const int wid = blockIdx.x * kWarps + (threadIdx.x >> 5);
-        if (wid < p.total_warps) walk_item<MASK>(p, wid, lane, ring, lut);
-    }
+    const int wid = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (wid < p.total_warps) walk_item<MASK>(p, wid, lane, ring, strip::lut_base(s_lut_raw));
 }
 
 // Fast path of the BGR pixel stage; cudaErrorNotSupported when the call does not qualify (the caller then runs the
@@ -209,7 +194,7 @@ cudaError_t launch_bgr_strip(const PixelLaunch& L, int sm_count, cudaStream_t st
     const char* es = getenv("RMCV_STRIP_SEG");
     if (es && atoi(es) > 0) seg = atoi(es);
     else {
-        const long long slots = (long long)(minb >= 4 ? 4 : (minb <= 2 ? 2 : 3)) * kWarps * sm_count;
+        const long long slots = (long long)(minb >= 4 ? 4 : 3) * kWarps * sm_count;
         long long best = -1;
         for (int sg = 16; sg <= 128; ++sg) {
             const long long warps = ((long long)L.batch * ((L.H + sg - 1) / sg) * p.NC + 29) / 30;
@@ -224,26 +209,13 @@ cudaError_t launch_bgr_strip(const PixelLaunch& L, int sm_count, cudaStream_t st
     if (total <= 0 || total > 0x3fffffffLL) return cudaErrorNotSupported;
     p.total_slots = (int)total;
     p.total_warps = (int)((total + 29) / 30);
-    unsigned grid = (unsigned)((p.total_warps + kWarps - 1) / kWarps);
-    const char* ep = getenv("RMCV_PIX_PERSIST");
-    const int per_sm = ep ? atoi(ep) : 0;                  // CTAs per SM of a persistent launch (0: one item per warp)
-    const bool persist = per_sm > 0 && L.work_counter != nullptr && grid > (unsigned)(per_sm * sm_count);
-    if (persist) {
-        p.work_counter = L.work_counter;
-        cudaError_t e = cudaMemsetAsync(L.work_counter, 0, sizeof(int), st);
-        if (e != cudaSuccess) return e;
-        grid = (unsigned)(per_sm * sm_count);
-    }
-    const int which = (L.mask ? 1 : 0) + 2 * (minb >= 4 ? 2 : (minb <= 2 ? 0 : 1)) + (persist ? 6 : 0);
-    switch (which) {
-        case 0: bgr_strip_kernel<false, 2, false><<<grid, kWarps * 32, 0, st>>>(p); break;
-        case 1: bgr_strip_kernel<true, 2, false><<<grid, kWarps * 32, 0, st>>>(p); break;
-        case 2: bgr_strip_kernel<false, 3, false><<<grid, kWarps * 32, 0, st>>>(p); break;
-        case 3: bgr_strip_kernel<true, 3, false><<<grid, kWarps * 32, 0, st>>>(p); break;
-        case 4: bgr_strip_kernel<false, 4, false><<<grid, kWarps * 32, 0, st>>>(p); break;
-        case 5: bgr_strip_kernel<true, 4, false><<<grid, kWarps * 32, 0, st>>>(p); break;
-        case 6: case 8: case 10: bgr_strip_kernel<false, 3, true><<<grid, kWarps * 32, 0, st>>>(p); break;
-        default: bgr_strip_kernel<true, 3, true><<<grid, kWarps * 32, 0, st>>>(p); break;
+    const unsigned grid = (unsigned)((p.total_warps + kWarps - 1) / kWarps);
+    if (L.mask) {
+        if (minb >= 4) bgr_strip_kernel<true, 4><<<grid, kWarps * 32, 0, st>>>(p);
+        else bgr_strip_kernel<true, 3><<<grid, kWarps * 32, 0, st>>>(p);
+    } else {
+        if (minb >= 4) bgr_strip_kernel<false, 4><<<grid, kWarps * 32, 0, st>>>(p);
+        else bgr_strip_kernel<false, 3><<<grid, kWarps * 32, 0, st>>>(p);
     }
     if (launches) ++*launches;
     return cudaGetLastError();

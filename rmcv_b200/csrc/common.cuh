@@ -83,7 +83,6 @@ struct SlotBuffers {
     rmcv_lightblob* s_blobs;       // [CF][C]
     rmcv_armour* s_armours;        // [CF][A]
     int32_t* arm_offset;           // [CF]  dense offset of the frame's armours in the result arrays (for the pose kernel)
-    int32_t* pix_counter;          // work-item counter of a persistent pixel-kernel launch
     // staging for host-input calls
     uint8_t* frames;        // [CF][H][W*3] (allocated lazily)
     uint8_t* masks;         // [CF][H][W]   (allocated lazily)
@@ -149,7 +148,6 @@ struct PixelLaunch {
     int W, H, batch;
     int target, lower_bound;
     int bayer_layout;   // 0 = BGR input
-    int* work_counter;  // device int for persistent launches of the strip kernels, or null
 };
 cudaError_t launch_pixel_stage(const PixelLaunch& p, int sm_count, cudaStream_t st, int64_t* launches);
 // Bayer fast path (bayer_strip.cu); cudaErrorNotSupported when the call does not qualify for it

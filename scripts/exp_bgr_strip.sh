@@ -1,10 +1,5 @@
+# pipeline experiments with the opt-in BGR strip kernel (run on the GPU box): bench.py short runs
 run() { tag=$1; shift; env "$@" python bench.py --steps 6 --warmup 3 --batch 1024 --no-cpu --no-extras --e2e-steps 1 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$tag', round(d['value']), {k:round(v,3) for k,v in d['stage_ms_per_step'].items()}, round(d['roofline']['frac'],3))"; }
 run band A=1
 run strip RMCV_BGR_STRIP=1
-run p1 RMCV_BGR_STRIP=1 RMCV_PIX_PERSIST=1
-run p2 RMCV_BGR_STRIP=1 RMCV_PIX_PERSIST=2
-run p3 RMCV_BGR_STRIP=1 RMCV_PIX_PERSIST=3
-run p2s32 RMCV_BGR_STRIP=1 RMCV_PIX_PERSIST=2 RMCV_STRIP_SEG=32
-run p2s64 RMCV_BGR_STRIP=1 RMCV_PIX_PERSIST=2 RMCV_STRIP_SEG=64
-run s16 RMCV_BGR_STRIP=1 RMCV_STRIP_SEG=16
-run s32 RMCV_BGR_STRIP=1 RMCV_STRIP_SEG=32
+run strip_s32 RMCV_BGR_STRIP=1 RMCV_STRIP_SEG=32
