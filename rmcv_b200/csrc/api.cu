@@ -43,11 +43,11 @@ struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
     void* tmp_host = nullptr; size_t tmp_host_bytes = 0;
     int last_nchunks = 0;
     int last_kind = 0;  // 0 none, 1 extract, 2 detect
-    cudaEvent_t t_start[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, t_stop[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t t_start[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, t_stop[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // Streams of the ctx.  The pixel kernels of consecutive chunks run back to back on `pix`; the labelling kernels of
     // chunk i run on the high-priority stream `lab` behind an event, so that they overlap the pixel kernel of chunk
     // i+1; host<->device staging copies have their own streams (both copy engines stay busy).
-    cudaStream_t pix = nullptr, lab = nullptr, out = nullptr, h2d = nullptr, d2h = nullptr;
+    cudaStream_t pix = nullptr, lab = nullptr, lab2 = nullptr, out = nullptr, h2d = nullptr, d2h = nullptr;   // lab2: slot 1
     bool own_pix = false;
     CameraSetup camera;      // f1 fused: pose of every armour behind the write-out kernel
     bool have_camera = false;
@@ -172,7 +172,9 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
                   int frames, int frame_base, int bayer_layout, const rmcv_params& prm, uint8_t* mask, size_t mask_pitch,
                   size_t mask_frame_stride, bool full) {
     CtxExtra* ex = extra(ctx);
-    cudaStream_t sp = ex->pix, sl = ex->lab;
+    // each slot has its own labelling stream: the labelling kernels of consecutive chunks are latency-bound and overlap
+    // each other as well as the pixel kernels
+    cudaStream_t sp = ex->pix, sl = (&sb == &ctx->slot[1]) ? ex->lab2 : ex->lab;
     // the slot's scratch is free once the labelling stages (and the mask download) of its previous chunk are done
     RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, sb.ev_lab, 0));
     RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, sb.ev_d2h, 0));
@@ -262,6 +264,7 @@ int sync_all(rmcv_ctx* ctx) {
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->h2d));
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->pix));
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->lab));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(ex->lab2));
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->out));
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->d2h));
     prof_collect(ctx);
@@ -411,9 +414,12 @@ int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
         cudaError_t se = cudaSuccess;
         if (cfg->stream) { ex->pix = reinterpret_cast<cudaStream_t>(cfg->stream); ex->own_pix = false; }
         else { se = cudaStreamCreateWithPriority(&ex->pix, cudaStreamNonBlocking, least); ex->own_pix = true; }
-        if (getenv("RMCV_SERIAL")) { ex->lab = ex->pix; ex->out = ex->pix; }   // debug aid: every kernel on one stream
+        if (getenv("RMCV_SERIAL")) { ex->lab = ex->pix; ex->lab2 = ex->pix; ex->out = ex->pix; }   // debug aid: every kernel on one stream
         else {
             if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&ex->lab, cudaStreamNonBlocking, greatest);
+            const char* e1 = getenv("RMCV_LAB_STREAMS");
+            if (e1 && atoi(e1) == 1) ex->lab2 = ex->lab;
+            else if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&ex->lab2, cudaStreamNonBlocking, greatest);
             if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&ex->out, cudaStreamNonBlocking, greatest);
         }
         if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&ex->h2d, cudaStreamNonBlocking);
@@ -468,7 +474,8 @@ int rmcv_ctx_destroy(rmcv_ctx* ctx) {
             for (int i = 0; i < 2; ++i) cudaEventDestroy(ps.pix[i]);
             for (int i = 0; i < RMCV_STAGE_COUNT; ++i) cudaEventDestroy(ps.lab[i]);
         }
-        for (int i = 0; i < 5; ++i) { if (ex->t_start[i]) cudaEventDestroy(ex->t_start[i]); if (ex->t_stop[i]) cudaEventDestroy(ex->t_stop[i]); }
+        for (int i = 0; i < 6; ++i) { if (ex->t_start[i]) cudaEventDestroy(ex->t_start[i]); if (ex->t_stop[i]) cudaEventDestroy(ex->t_stop[i]); }
+        if (ex->lab2 && ex->lab2 != ex->pix && ex->lab2 != ex->lab) cudaStreamDestroy(ex->lab2);
         if (ex->lab && ex->lab != ex->pix) cudaStreamDestroy(ex->lab);
         if (ex->out && ex->out != ex->pix) cudaStreamDestroy(ex->out);
         if (ex->pix && ex->own_pix) cudaStreamDestroy(ex->pix);
@@ -1051,8 +1058,8 @@ int rmcv_timer_start(rmcv_ctx* ctx) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
     CtxExtra* ex = extra(ctx);
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st[5] = {ex->pix, ex->lab, ex->out, ex->h2d, ex->d2h};
-    for (int i = 0; i < 5; ++i) {
+    cudaStream_t st[6] = {ex->pix, ex->lab, ex->out, ex->h2d, ex->d2h, ex->lab2};
+    for (int i = 0; i < 6; ++i) {
         if (!ex->t_start[i]) { RMCV_CUDA(ctx, cudaEventCreate(&ex->t_start[i])); RMCV_CUDA(ctx, cudaEventCreate(&ex->t_stop[i])); }
         RMCV_CUDA(ctx, cudaEventRecord(ex->t_start[i], st[i]));
     }
@@ -1063,13 +1070,13 @@ int rmcv_timer_stop(rmcv_ctx* ctx, double* ms) {
     if (!ctx || !ms) return RMCV_ERR_INVALID_ARG;
     CtxExtra* ex = extra(ctx);
     if (!ex->t_start[0]) return set_err(ctx, RMCV_ERR_STATE, "rmcv_timer_stop without rmcv_timer_start");
-    cudaStream_t st[5] = {ex->pix, ex->lab, ex->out, ex->h2d, ex->d2h};
-    for (int i = 0; i < 5; ++i) RMCV_CUDA(ctx, cudaEventRecord(ex->t_stop[i], st[i]));
+    cudaStream_t st[6] = {ex->pix, ex->lab, ex->out, ex->h2d, ex->d2h, ex->lab2};
+    for (int i = 0; i < 6; ++i) RMCV_CUDA(ctx, cudaEventRecord(ex->t_stop[i], st[i]));
     int rc = sync_all(ctx);
     if (rc != RMCV_OK) return rc;
     float best = 0.f;
-    for (int i = 0; i < 5; ++i)
-        for (int j = 0; j < 5; ++j) {
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
             float t = 0.f;
             RMCV_CUDA(ctx, cudaEventElapsedTime(&t, ex->t_start[i], ex->t_stop[j]));
             if (t > best) best = t;

@@ -2,9 +2,12 @@
 // cv2 bilinear stand-in for DxRaw8toRGB24) fused with rm::extract_color's difference / threshold / 3x3 close
 // (src/imgproc.cpp:52-69).  HBM-bound streaming kernel, no tensor cores, no shared-memory staging:
 //
-//   * a WARP owns a strip of 30 x 16 pixels (+ one halo lane each side) and walks down a segment of rows; a lane
-//     reads its 16 raw bytes of a row with one coalesced 128-bit load (the warp reads 512 contiguous bytes), two row
-//     pairs ahead of the arithmetic;
+//   * pixel groups of 16 pixels are numbered through the whole call, slot = (frame, row segment, group), group fastest.
+//     A WARP owns 30 consecutive slots (+ one halo lane each side) and every lane walks down its segment of rows;
+//     neighbouring lanes are neighbouring groups of the same rows except across an image edge, where the close pads
+//     anyway, so 30 of 32 lanes work whatever the image width.  A lane copies its 16 raw bytes of a row with cp.async
+//     (LDGSTS; the warp's 512 contiguous bytes are one request) into its own slice of a 4-stage ring in shared memory,
+//     four row pairs ahead of the arithmetic — no barrier, a lane only reads back what it asked for itself;
 //   * only the two sampled planes matter (B and R; green is never read).  Samples are unpacked into 16-bit lanes, two
 //     per register, the low lane for pixels 0..7 and the high lane for pixels 8..15 of the thread's group, so that
 //     horizontal neighbours are whole registers and the final bits fall in order.  Per raw row: the samples U and
@@ -21,7 +24,7 @@
 //
 // Border rule of cv2's demosaic: row 0 shows row 1, row H-1 row H-2, column 0 column 1, column W-1 column
 // W-2 — on threshold bits a replicate of the neighbouring interior bit.
-#include "common.cuh"
+#include "strip.cuh"
 
 namespace rmcv {
 
@@ -33,8 +36,8 @@ struct StripParams {
     int pitch, mask_pitch;                                 // row pitches in bytes (< 2^31)
     uint16_t* bits16;            // bit mask viewed as 16-bit words, [batch][H][WB2]
     int W, H, NC, WB2;           // NC = W / 16 pixel groups per row, WB2 = 16-bit words per bit row
-    int seg, nseg, nwx;          // rows per segment (even), segments per frame, warps per strip row
-    int total_warps;
+    int seg, nseg;               // rows per segment (even), segments per frame
+    int total_slots, total_warps;   // slot = (frame, segment, group), group fastest; a warp owns 30 consecutive slots
     uint32_t kSP[4], kSM[4], kN[4];   // per-lane constants of the three tests, by x mod 4 (both lanes)
     uint32_t force_or, force_and;     // lower_bound <= 0: all ones; > 255: all zeros
 };
@@ -49,24 +52,11 @@ constexpr uint32_t kOne2 = 0x00010001u;
 // asked for itself, so the groups need no barrier, only cp.async.wait_group.
 constexpr int kStages = 4;                      // row pairs in flight per lane
 constexpr uint32_t kStageBytes = 2u * 32u * 16u;   // two rows x 32 lanes x 16 B per warp and stage
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ uint2 lds64(uint32_t saddr) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) { return (a & m) | (b & ~m); }
+using strip::bitsel;
+using strip::cp_async16;
+using strip::cp_commit;
+using strip::cp_wait;
+using strip::lds128;
 
 // SX = x parity of the samples in this row
 template <int SX>
@@ -119,51 +109,22 @@ __device__ __forceinline__ uint32_t thr_row(const RowPrep& A, const RowPrep& C, 
     return (__byte_perm(z, 0, 0x4431) | p.force_or) & p.force_and;
 }
 
-// Per-thread state of the walk down a strip.
+// Per-lane state of the walk down a row segment.
 struct Walk {
-    uint32_t h0, h1, e0, e1;     // sliding rows of the close: two horizontally dilated, two horizontally eroded rows
-    uint32_t inside;             // window bit i <-> x = 16c - 2 + i: the bits inside the image
+    strip::CloseLane k;
     uint32_t fix_mask, fix_rot;  // border columns: bit 0 of group 0 shows bit 1 (rotate right 1), bit 15 of the last group bit 14
-    const uint8_t* lp;           // raw row `lr` (clamped into the image) at the column of this lane
+    const uint8_t* lp;           // raw row `lr` (clamped into the image) at the group of this lane
     int lr;
     uint32_t ring, stage;        // shared address of this lane's slot in stage 0; byte offset of the oldest stage
-    uint8_t* mrow;               // byte-mask address of the next row to leave (or null)
-    uint16_t* brow;              // bit-mask address of the next row to leave
-    uint32_t lut;                // shared address of the bits -> bytes table (2 KB aligned)
-    int H;
-    int writer, tail16;          // this lane stores its group / also zeroes the odd 16-bit word that ends a W % 32 == 16 row
+    int r;                       // image row (even) of the pair that enters next
+    int left;                    // rows this lane still has to store (0 for halo / idle lanes)
+    int tail16;                  // also zero the odd 16-bit word that ends a W % 32 == 16 bit row
 };
-
-// One threshold row (row r) enters, the final row r-2 leaves (STORE: to memory).
-template <bool STORE, bool MASK>
-__device__ __forceinline__ void push_row(Walk& k, const StripParams& p, uint32_t t, int r) {
-    const uint32_t tl = __shfl_up_sync(0xffffffffu, t, 1), tr = __shfl_down_sync(0xffffffffu, t, 1);
-    const uint32_t w = ((tl >> 14) | (t << 2) | (tr << 18)) & k.inside;
-    const uint32_t h = w | (w << 1) | (w >> 1);
-    uint32_t d = k.h0 | k.h1 | h | ~k.inside;               // dilated row r-1; columns outside the image read as ones
-    k.h0 = k.h1; k.h1 = h;
-    if ((unsigned)(r - 1) >= (unsigned)k.H) d = 0xffffffffu;   // so do rows outside the image
-    const uint32_t e = d & (d << 1) & (d >> 1);
-    const uint32_t m = k.e0 & k.e1 & e;                     // final row r-2 in window bits 2..17
-    k.e0 = k.e1; k.e1 = e;
-    if (STORE) {
-        if (k.writer) {
-            k.brow[0] = (uint16_t)(m >> 2);
-            if (k.tail16) k.brow[1] = 0;
-            if (MASK) {   // table entries are 8 bytes: pixels 0..7 at (m >> 2 & 255) * 8, pixels 8..15 at (m >> 10 & 255) * 8
-                const uint2 a = lds64(((m << 1) & 0x7f8u) | k.lut), b = lds64(((m >> 7) & 0x7f8u) | k.lut);
-                __stcs(reinterpret_cast<uint4*>(k.mrow), make_uint4(a.x, a.y, b.x, b.y));
-            }
-        }
-        k.brow += p.WB2;
-        if (MASK) k.mrow += p.mask_pitch;
-    }
-}
 
 // Address of the next raw row (rows outside the image read the nearest row inside; their results are never used).
 __device__ __forceinline__ const uint8_t* next_row(Walk& k, const StripParams& p) {
     const uint8_t* v = k.lp;
-    k.lp += (unsigned)k.lr < (unsigned)(k.H - 1) ? p.pitch : 0;
+    k.lp += (unsigned)k.lr < (unsigned)(p.H - 1) ? p.pitch : 0;
     ++k.lr;
     return v;
 }
@@ -179,7 +140,7 @@ __device__ __forceinline__ void fetch_pair(Walk& k, const StripParams& p, uint32
 // rows r+1+2*kStages, r+2+2*kStages.
 template <int PY, int PX, bool STORE, bool MASK>
 __device__ __forceinline__ void row_pair(Walk& k, const StripParams& p, const RowPrep& A, const RowPrep& C,
-                                         RowPrep& B, RowPrep& N, int r) {
+                                         RowPrep& B, RowPrep& N) {
     constexpr bool kEvenIsP = PY == 0;
     constexpr int kSxEven = kEvenIsP ? PX : 1 - PX, kSxOdd = 1 - kSxEven;   // x parity of the samples in even / odd rows
     cp_wait<kStages - 1>();
@@ -187,15 +148,20 @@ __device__ __forceinline__ void row_pair(Walk& k, const StripParams& p, const Ro
     prep_row<kSxEven>(lds128(k.ring + k.stage + 512u), N);
     fetch_pair(k, p, k.stage);
     k.stage = (k.stage + kStageBytes) & (kStages * kStageBytes - 1u);
+    const int r = k.r;
     uint32_t t0 = thr_row<kEvenIsP, kSxEven>(A, C, B, p);
     uint32_t t1 = thr_row<!kEvenIsP, kSxOdd>(C, B, N, p);
     if (r == 0) t0 = t1;                                 // row 0 shows row 1
-    if (r == k.H - 2) t1 = t0;                           // row H-1 shows row H-2
+    if (r == p.H - 2) t1 = t0;                           // row H-1 shows row H-2
     t0 = bitsel(__funnelshift_r(t0, t0, k.fix_rot), t0, k.fix_mask);   // column 0 shows column 1, column W-1 column W-2
     t1 = bitsel(__funnelshift_r(t1, t1, k.fix_rot), t1, k.fix_mask);
-    if ((unsigned)r >= (unsigned)k.H) { t0 = 0u; t1 = 0u; }   // a pair is either inside or outside the image (r, H even)
-    push_row<STORE, MASK>(k, p, t0, r);
-    push_row<STORE, MASK>(k, p, t1, r + 1);
+    if ((unsigned)r >= (unsigned)p.H) { t0 = 0u; t1 = 0u; }   // a pair is either inside or outside the image (r, H even)
+    strip::push_row<STORE, MASK>(k.k, p.WB2, p.mask_pitch, t0, (unsigned)(r - 1) >= (unsigned)p.H, k.left > 0,
+                                 k.left > 0 && k.tail16);
+    strip::push_row<STORE, MASK>(k.k, p.WB2, p.mask_pitch, t1, (unsigned)r >= (unsigned)p.H, k.left > 1,
+                                 k.left > 1 && k.tail16);
+    if (STORE) k.left -= 2;
+    k.r = r + 2;
 }
 
 }  // namespace
@@ -203,52 +169,40 @@ __device__ __forceinline__ void row_pair(Walk& k, const StripParams& p, const Ro
 // PY, PX: parity of the rows / columns that sample the plus channel (the minus channel sits on the opposite diagonal)
 template <int PY, int PX, bool MASK, int MINB>
 __global__ void __launch_bounds__(256, MINB) bayer_strip_kernel(const StripParams p) {
-    __shared__ __align__(16) uint2 s_lut_raw[512];   // the table is placed on a 2 KB boundary of the shared window, so
-                                                     // that index and base combine with OR
+    __shared__ __align__(16) uint8_t s_lut_raw[4096];
     __shared__ __align__(16) uint8_t s_ring[8 * kStages * kStageBytes];   // 8 warps
-    {
-        const uint32_t i = threadIdx.x;
-        if (i < 256) {
-            auto expand4 = [](uint32_t nib) {   // 4 bits -> 4 bytes of 0x00 / 0xFF: bits to the byte MSBs, PRMT sign-replicate
-                uint32_t r;
-                asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(nib * 0x10204080u));
-                return r;
-            };
-            const uint32_t base = ((uint32_t)__cvta_generic_to_shared(s_lut_raw) + 2047u) & ~2047u;
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(base + i * 8u), "r"(expand4(i & 15u)), "r"(expand4(i >> 4)) : "memory");
-        }
-    }
+    strip::lut_init(s_lut_raw, threadIdx.x);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (wid >= p.total_warps) return;
-    const int wx = wid % p.nwx;
-    const int rest = wid / p.nwx;
-    const int seg = rest % p.nseg, frame = rest / p.nseg;
+    const int slot = wid * 30 - 1 + lane;                    // lanes 0 and 31 only feed their neighbours
+    const bool valid = slot >= 0 && slot < p.total_slots;
+    const int sc = min(max(slot, 0), p.total_slots - 1);
+    const int c = sc % p.NC, q = sc / p.NC;
+    const int sg = q % p.nseg, frame = q / p.nseg;
     const int H = p.H, NC = p.NC;
-    const int c = wx * 30 - 1 + lane;                        // pixel group of this lane (lanes 0 and 31: halo only)
-    const int cc = min(max(c, 0), NC - 1);
-    const int y0 = seg * p.seg, y1 = min(H, y0 + p.seg);
+    const int y0 = sg * p.seg;
     Walk k;
-    k.h0 = k.h1 = 0u; k.e0 = k.e1 = 0u;
-    k.inside = 0xfffffu;
-    if (c <= 0) k.inside = c == 0 ? 0xffffcu : 0u;
-    if (c >= NC - 1) k.inside = c == NC - 1 ? (k.inside & 0x3ffffu) : 0u;
+    k.k.h0 = k.k.h1 = 0u; k.k.e0 = k.k.e1 = 0u;
+    uint32_t inside = 0xfffffu;
+    if (c == 0) inside &= 0xffffcu;
+    if (c == NC - 1) inside &= 0x3ffffu;
+    k.k.inside = valid ? inside : 0u;
     k.fix_mask = c == 0 ? 1u : (c == NC - 1 ? 0x8000u : 0u);
     k.fix_rot = c == 0 ? 1u : 31u;
-    k.H = H;
-    k.writer = lane >= 1 && lane <= 30 && c < NC;
-    k.tail16 = k.writer && c == NC - 1 && (p.WB2 > NC);      // W % 32 == 16: the upper half of the last bit word is zero
-    asm volatile("" : "+r"(k.writer), "+r"(k.tail16));       // keep the flags in registers (no rematerialisation per row)
-    k.lut = ((uint32_t)__cvta_generic_to_shared(s_lut_raw) + 2047u) & ~2047u;
-    k.mrow = MASK ? p.mask + (size_t)frame * p.mask_frame_stride + (size_t)y0 * p.mask_pitch + (size_t)cc * 16 : nullptr;
-    k.brow = p.bits16 + ((size_t)frame * H + y0) * p.WB2 + cc;
+    const bool writer = valid && lane >= 1 && lane <= 30;
+    k.left = writer ? min(p.seg, H - y0) : 0;
+    k.tail16 = (c == NC - 1 && p.WB2 > NC) ? 1 : 0;          // W % 32 == 16: the upper half of the last bit word is zero
+    k.k.lut = strip::lut_base(s_lut_raw);
+    k.k.mrow = MASK ? p.mask + (size_t)frame * p.mask_frame_stride + (size_t)y0 * p.mask_pitch + (size_t)c * 16 : nullptr;
+    k.k.brow = p.bits16 + ((size_t)frame * H + y0) * p.WB2 + c;
 
     constexpr int kSxEven = PY == 0 ? PX : 1 - PX, kSxOdd = 1 - kSxEven;
     RowPrep s0, s1, s2, s3;
-    int r = y0 - 2;
-    k.lr = r - 1;
-    k.lp = p.src + (size_t)frame * p.frame_stride + (size_t)min(max(k.lr, 0), H - 1) * p.pitch + (size_t)cc * 16;
+    k.r = y0 - 2;
+    k.lr = k.r - 1;
+    k.lp = p.src + (size_t)frame * p.frame_stride + (size_t)min(max(k.lr, 0), H - 1) * p.pitch + (size_t)c * 16;
     k.ring = (uint32_t)__cvta_generic_to_shared(s_ring) + (threadIdx.x >> 5) * (kStages * kStageBytes) + lane * 16u;
     k.stage = 0u;
     {
@@ -260,17 +214,14 @@ __global__ void __launch_bounds__(256, MINB) bayer_strip_kernel(const StripParam
         prep_row<kSxEven>(w1, s1);
     }
     // rows y0-2 .. y0+1 fill the pipeline; from the pair at y0+2 on, every pair releases two final rows
-    row_pair<PY, PX, false, MASK>(k, p, s0, s1, s2, s3, r);
-    row_pair<PY, PX, false, MASK>(k, p, s2, s3, s0, s1, r + 2);
-    r += 4;
-    while (true) {                                          // the last pair starts at y1
-        row_pair<PY, PX, true, MASK>(k, p, s0, s1, s2, s3, r);
-        r += 2;
-        if (r > y1) break;
-        row_pair<PY, PX, true, MASK>(k, p, s2, s3, s0, s1, r);
-        r += 2;
-        if (r > y1) break;
+    row_pair<PY, PX, false, MASK>(k, p, s0, s1, s2, s3);
+    row_pair<PY, PX, false, MASK>(k, p, s2, s3, s0, s1);
+    for (int n = p.seg >> 1; n > 0; n -= 2) {               // seg / 2 storing pairs
+        row_pair<PY, PX, true, MASK>(k, p, s0, s1, s2, s3);
+        if (n == 1) break;
+        row_pair<PY, PX, true, MASK>(k, p, s2, s3, s0, s1);
     }
+    cp_wait<0>();
 }
 
 // Fast path of the Bayer pixel stage; returns cudaErrorNotSupported when the call does not qualify (the caller then
@@ -299,7 +250,6 @@ cudaError_t launch_bayer_strip(const PixelLaunch& L, int sm_count, cudaStream_t 
     p.mask = L.mask; p.mask_pitch = (int)L.mask_pitch; p.mask_frame_stride = L.mask_frame_stride;
     p.bits16 = reinterpret_cast<uint16_t*>(L.bits);
     p.W = L.W; p.H = L.H; p.NC = L.W / 16; p.WB2 = 2 * ((L.W + 31) / 32);
-    p.nwx = (p.NC + 29) / 30;
     // segment height: tall segments amortise the six halo rows, but the warps of a launch should fill whole waves of the
     // resident warp slots (3 CTAs of 8 warps per SM): pick the even height with the least waves x (rows + halo)
     int seg = 0;
@@ -311,7 +261,7 @@ cudaError_t launch_bayer_strip(const PixelLaunch& L, int sm_count, cudaStream_t 
         const long long slots = (eb0 >= 4 ? 32LL : 24LL) * sm_count;
         long long best = -1;
         for (int sg = 16; sg <= 128; sg += 2) {
-            const long long warps = (long long)L.batch * ((L.H + sg - 1) / sg) * p.nwx;
+            const long long warps = ((long long)L.batch * ((L.H + sg - 1) / sg) * p.NC + 29) / 30;
             const long long cost = ((warps + slots - 1) / slots) * (sg + 8);
             if (best < 0 || cost < best) { best = cost; seg = sg; }
         }
@@ -319,9 +269,11 @@ cudaError_t launch_bayer_strip(const PixelLaunch& L, int sm_count, cudaStream_t 
     if (seg > L.H) seg = L.H;
     if (seg < 2) seg = 2;
     p.seg = seg; p.nseg = (L.H + seg - 1) / seg;
-    const long long total = (long long)L.batch * p.nseg * p.nwx;
-    if (total <= 0 || total > 0x7fffffffLL) return cudaErrorInvalidValue;
-    p.total_warps = (int)total;
+    const long long total_slots = (long long)L.batch * p.nseg * p.NC;
+    if (total_slots <= 0 || total_slots > 0x3fffffffLL) return cudaErrorNotSupported;
+    p.total_slots = (int)total_slots;
+    p.total_warps = (int)((total_slots + 29) / 30);
+    const long long total = p.total_warps;
     const int lb = L.lower_bound < 1 ? 1 : (L.lower_bound > 255 ? 255 : L.lower_bound);
     for (int x = 0; x < 4; ++x) {
         const uint32_t bias = 1u << (12 + x);
