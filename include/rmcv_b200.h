@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RMCV_B200_ABI_VERSION 2
+#define RMCV_B200_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -311,6 +311,48 @@ int rmcv_clear_camera(rmcv_ctx* ctx);
 int rmcv_solve_pnp(rmcv_ctx* ctx, const rmcv_armour* armours, int n_armours, const double camera_matrix[9],
                    const double dist_coeffs[5], float exact_w, float exact_h, float roi_x, float roi_y,
                    const double* cam2world, rmcv_pose* poses);
+
+/* ---- f3 (next row): armour tracking — IoU association + 6-state Kalman filter + identity vote ------------------ */
+/* One tracked armour: the public tracking fields of rm::armour (include/core.h:103-122) and the state of its
+ * cv::KalmanFilter(6, 6, 0, CV_64F) observer (src/core.cpp:21,51-69).  As in the reference, bbox / position / identity
+ * are those of the armour that opened the track (rm::armour::update never refreshes them), lost_count is never
+ * cleared, and the first correct() runs against a zero errorCovPre (so it leaves the state at zero). */
+#define RMCV_TRACK_HIST 8
+typedef struct rmcv_track {
+    float bbox[4];                         /* bounding_box x, y, width, height                                   */
+    double position[3];
+    int64_t timestamp;                     /* ticks of the last update                                           */
+    int32_t lost_count;
+    int32_t identity;
+    int32_t initialized;
+    int32_t n_hist;                        /* identity_history (std::map<int,int>), sorted by identity           */
+    int32_t hist_id[RMCV_TRACK_HIST], hist_count[RMCV_TRACK_HIST];
+    double state_pre[6], state_post[6];    /* x, y, z, vx, vy, vz                                                */
+    double cov_pre[36], cov_post[36];      /* errorCovPre / errorCovPost, row-major                              */
+    double meas[6];                        /* measurement                                                        */
+    double q, r;                           /* processNoiseCov / measurementNoiseCov diagonal                     */
+} rmcv_track;
+
+typedef struct rmcv_tracker rmcv_tracker;  /* device-resident track list of one camera stream */
+int rmcv_tracker_create(rmcv_ctx* ctx, int capacity, rmcv_tracker** out);
+int rmcv_tracker_destroy(rmcv_ctx* ctx, rmcv_tracker* tracker);
+int rmcv_tracker_reset(rmcv_ctx* ctx, rmcv_tracker* tracker);
+/* One iteration of the reference's tracking loop (executable/main.cpp:57-88) for the armours of one frame, in the
+ * reference's order: for every track, rm::armour::max_IoU over the frame's remaining armours (src/core.cpp:145-161);
+ * IoU > 0.5: rm::armour::update(observation) (:71-106) and the armour leaves the list; otherwise lost_count++ > 25
+ * erases the track (and, like the reference's erase-in-a-for-loop, skips the one behind it), else update(timestamp)
+ * (:108-121); the armours left over open new tracks (rm::armour::reset(process_noise, measurement_noise, error),
+ * main.cpp:195).  An empty frame changes nothing; with no tracks the frame's armours become the tracks.
+ * positions: n x 3 world positions (rmcv_pose.position); identities: n class ids or NULL (-1).  A track list or an
+ * identity history that outgrows its capacity returns RMCV_ERR_CAPACITY (the list is then left as it was before the
+ * call).  Host pointers, synchronous; the track list itself stays on the device. */
+int rmcv_tracker_update(rmcv_ctx* ctx, rmcv_tracker* tracker, const rmcv_armour* armours, const double* positions,
+                        const int32_t* identities, int n_armours, int64_t timestamp, double tick_frequency,
+                        double process_noise, double measurement_noise, double error);
+/* Copies the track list to the host (up to cap tracks; *n_tracks = tracks alive). */
+int rmcv_tracker_read(rmcv_ctx* ctx, rmcv_tracker* tracker, rmcv_track* tracks, int cap, int* n_tracks);
+/* rm::armour::identity_max (src/core.cpp:123-143): softmax over the identity history of one track. */
+int rmcv_track_identity_max(const rmcv_track* track, int32_t* identity, double* probability);
 
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* CUDA-event timing of the stages of detect/extract calls (on the streams that run them). */

@@ -509,3 +509,126 @@ def blob_label_map(binary: np.ndarray, contours: Sequence[np.ndarray]) -> np.nda
         lut[labels[y, x]] = k
     lut[0] = -1
     return lut[labels]
+
+
+# --------------------------------------------------------------------------- f3 tracking (next row)
+class TrackedArmour:
+    """The tracking side of rm::armour (include/core.h:103-122): cv::KalmanFilter(6, 6, 0, CV_64F) observer, measurement,
+    identity_history, and the fields the tracking loop reads.  Restates src/core.cpp:51-161 through cv2.KalmanFilter."""
+
+    def __init__(self, bounding_box, position, identity, timestamp):
+        self.bounding_box = tuple(np.float32(v) for v in bounding_box)
+        self.position = np.asarray(position, np.float64).copy()
+        self.identity = int(identity)
+        self.timestamp = int(timestamp)
+        self.lost_count = 0
+        self.identity_history = {}
+        self.observer = cv2.KalmanFilter(6, 6, 0, cv2.CV_64F)   # src/core.cpp:21
+        self.measurement = np.zeros((6, 1), np.float64)
+        self.initialized = False
+
+    def reset(self, process_noise, measurement_noise, error):   # src/core.cpp:51-69
+        k = self.observer
+        k.measurementMatrix = np.eye(6)
+        k.processNoiseCov = np.eye(6) * process_noise
+        k.measurementNoiseCov = np.eye(6) * measurement_noise
+        k.errorCovPost = np.eye(6) * error
+        self.measurement = np.zeros((6, 1), np.float64)
+        F = np.eye(6)
+        F[0, 3] = F[1, 4] = F[2, 5] = 1.0
+        k.transitionMatrix = F
+        self.initialized = False
+
+    def _set_dt(self, dt):
+        F = self.observer.transitionMatrix.copy()
+        F[0, 3] = F[1, 4] = F[2, 5] = dt
+        self.observer.transitionMatrix = F
+
+    def update_observation(self, obs: "TrackedArmour", tick_frequency):   # src/core.cpp:71-106
+        self.identity_history[obs.identity] = self.identity_history.get(obs.identity, 0) + 1
+        if self.initialized:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                dt = np.float64(obs.timestamp - self.timestamp) / np.float64(tick_frequency)
+                self._set_dt(dt)
+                self.observer.predict()
+                self.measurement[3:6, 0] = (obs.position - self.measurement[0:3, 0]) / dt
+            self.measurement[0:3, 0] = obs.position
+            self.observer.correct(self.measurement)
+        else:
+            self.measurement[0:3, 0] = obs.position
+            self.observer.correct(self.measurement)
+            self.initialized = True
+        self.timestamp = obs.timestamp
+
+    def update_time(self, new_timestamp, tick_frequency):   # src/core.cpp:108-121
+        if not self.initialized:
+            return
+        self._set_dt(np.float64(new_timestamp - self.timestamp) / np.float64(tick_frequency))
+        self.observer.predict()
+
+    def identity_max(self):   # src/core.cpp:123-143
+        total = sum(np.exp(np.float64(c)) for c in self.identity_history.values())
+        best, best_id = 0.0, -1
+        for ident in sorted(self.identity_history):   # std::map iterates in key order
+            prob = np.exp(np.float64(self.identity_history[ident])) / total
+            if prob > best:
+                best, best_id = prob, ident
+        return best_id, best
+
+    def max_iou(self, armours):   # src/core.cpp:145-161
+        index, best = -1, np.float32(0)
+        for i, a in enumerate(armours):
+            v = rect_iou(self.bounding_box, a.bounding_box)
+            if v > best:
+                best, index = v, i
+        return index, best
+
+
+def rect_iou(a, b) -> np.float32:
+    """intersection.area() / (a.area() + b.area() - intersection.area()) on cv::Rect2f (src/core.cpp:151-154).  The
+    intersection restates cv::Rect_::operator&= of OpenCV 4.5+ (modules/core/include/opencv2/core/types.hpp); cv2 has no
+    binding for it, so this part of the oracle is not pinned by cv2 itself."""
+    f = np.float32
+    a = [f(v) for v in a]; b = [f(v) for v in b]
+    iw = ih = f(0)
+    if not (a[2] <= 0 or a[3] <= 0 or b[2] <= 0 or b[3] <= 0):
+        xmin, xmax = (a, b) if a[0] < b[0] else (b, a)
+        ymin, ymax = (a, b) if a[1] < b[1] else (b, a)
+        apart = (xmin[0] < 0 and f(xmin[0] + xmin[2]) < xmax[0]) or (ymin[1] < 0 and f(ymin[1] + ymin[3]) < ymax[1])
+        if not apart:
+            iw = min(f(xmin[2] - f(xmax[0] - xmin[0])), xmax[2])
+            ih = min(f(ymin[3] - f(ymax[1] - ymin[1])), ymax[3])
+            if iw <= 0 or ih <= 0:
+                iw = ih = f(0)
+    inter = f(iw * ih)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return f(inter / f(f(f(a[2] * a[3]) + f(b[2] * b[3])) - inter))
+
+
+def tracking_step(tracking: list, armours: list, tick_frequency, noise=(5e-5, 0.5, 0.05)) -> list:
+    """One iteration of the tracking thread's loop, executable/main.cpp:60-85, including its erase-inside-a-for-loop
+    (the track behind an erased one is skipped).  `armours`: TrackedArmour observations of one frame; they are reset() like
+    process_function does (main.cpp:195) when they enter the list."""
+    armours = list(armours)
+    if not armours:
+        return tracking
+    for a in armours:
+        a.reset(*noise)
+    if not tracking:
+        return armours
+    i = 0
+    while i < len(tracking):
+        index, iou = tracking[i].max_iou(armours)
+        if iou > 0.5:
+            tracking[i].update_observation(armours[index], tick_frequency)
+            del armours[index]
+        else:
+            lost = tracking[i].lost_count
+            tracking[i].lost_count += 1
+            if lost > 25:
+                del tracking[i]
+            else:
+                tracking[i].update_time(tracking[i].timestamp, tick_frequency)
+        i += 1
+    tracking.extend(armours)
+    return tracking

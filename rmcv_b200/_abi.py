@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 RMCV_OK = 0
 RMCV_ERR_INVALID_ARG, RMCV_ERR_CUDA, RMCV_ERR_CAPACITY, RMCV_ERR_NO_DEVICE, RMCV_ERR_STATE = -1, -2, -3, -4, -5
@@ -65,6 +65,17 @@ class Results(C.Structure):
                 ("blobs", C.POINTER(LightBlob)), ("armours", C.POINTER(Armour)), ("poses", C.POINTER(Pose))]
 
 
+TRACK_HIST = 8
+
+
+class Track(C.Structure):
+    _fields_ = [("bbox", C.c_float * 4), ("position", C.c_double * 3), ("timestamp", C.c_int64), ("lost_count", C.c_int32),
+                ("identity", C.c_int32), ("initialized", C.c_int32), ("n_hist", C.c_int32),
+                ("hist_id", C.c_int32 * TRACK_HIST), ("hist_count", C.c_int32 * TRACK_HIST),
+                ("state_pre", C.c_double * 6), ("state_post", C.c_double * 6), ("cov_pre", C.c_double * 36),
+                ("cov_post", C.c_double * 36), ("meas", C.c_double * 6), ("q", C.c_double), ("r", C.c_double)]
+
+
 assert C.sizeof(Pose) == 88
 assert C.sizeof(LightBlob) == 56 and C.sizeof(Armour) == 112 and C.sizeof(ContourInfo) == 72 and C.sizeof(FrameInfo) == 32
 
@@ -114,6 +125,12 @@ PROTOTYPES = {
     "rmcv_set_camera": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_float, _vp]),
     "rmcv_clear_camera": (C.c_int, [_vp]),
     "rmcv_solve_pnp": (C.c_int, [_vp, _vp, _i, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, _vp, _vp]),
+    "rmcv_tracker_create": (C.c_int, [_vp, _i, C.POINTER(_vp)]),
+    "rmcv_tracker_destroy": (C.c_int, [_vp, _vp]),
+    "rmcv_tracker_reset": (C.c_int, [_vp, _vp]),
+    "rmcv_tracker_update": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "rmcv_tracker_read": (C.c_int, [_vp, _vp, _vp, _i, C.POINTER(C.c_int)]),
+    "rmcv_track_identity_max": (C.c_int, [C.POINTER(Track), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     "rmcv_profile_enable": (C.c_int, [_vp, _i]),
     "rmcv_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), _i]),
     "rmcv_timer_start": (C.c_int, [_vp]),

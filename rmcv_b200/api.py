@@ -512,6 +512,48 @@ class Context:
         return [(np.array(o.rvec[:]), np.array(o.tvec[:]), np.array(o.position[:]), bool(o.ok)) for o in out]
 
 
+class Tracker:
+    """f3: device-resident track list of one camera stream (executable/main.cpp:57-88, src/core.cpp:51-161)."""
+
+    def __init__(self, ctx: "Context", capacity: int = 64):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._check(ctx.lib.rmcv_tracker_create(ctx.h, capacity, C.byref(h)), "rmcv_tracker_create")
+        self.h, self.capacity = h, capacity
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.rmcv_tracker_destroy(self.ctx.h, self.h)
+            self.h = None
+
+    def reset(self):
+        self.ctx._check(self.ctx.lib.rmcv_tracker_reset(self.ctx.h, self.h), "rmcv_tracker_reset")
+
+    def update(self, armours: Sequence[Armour], positions, identities, timestamp: int, tick_frequency: float,
+               process_noise=5e-5, measurement_noise=0.5, error=0.05):
+        """One iteration of the tracking loop for the armours of one frame (noise defaults: main.cpp:195)."""
+        n = len(armours)
+        arr = (A.Armour * max(n, 1))(*[a.to_c() for a in armours])
+        pos = np.ascontiguousarray(np.asarray(positions, np.float64).reshape(n, 3)) if n else np.zeros((1, 3))
+        ids = None if identities is None else np.ascontiguousarray(np.asarray(identities, np.int32).reshape(n))
+        self.ctx._check(self.ctx.lib.rmcv_tracker_update(self.ctx.h, self.h, arr, pos.ctypes.data,
+                                                         None if ids is None or n == 0 else ids.ctypes.data, n, int(timestamp),
+                                                         float(tick_frequency), float(process_noise), float(measurement_noise),
+                                                         float(error)), "rmcv_tracker_update")
+
+    def read(self) -> list:
+        out = (A.Track * self.capacity)()
+        n = C.c_int()
+        self.ctx._check(self.ctx.lib.rmcv_tracker_read(self.ctx.h, self.h, out, self.capacity, C.byref(n)), "rmcv_tracker_read")
+        return [out[i] for i in range(n.value)]
+
+    def identity_max(self, track) -> tuple:
+        ident, prob = C.c_int32(), C.c_double()
+        self.ctx._check(self.ctx.lib.rmcv_track_identity_max(C.byref(track), C.byref(ident), C.byref(prob)),
+                        "rmcv_track_identity_max")
+        return ident.value, prob.value
+
+
 # --------------------------------------------------------------------------------------------- rm:: mirror
 _default_ctx: Optional[Context] = None
 

@@ -1,6 +1,7 @@
 // C ABI of rmcv_b200 (include/rmcv_b200.h): context, memory helpers, the batched entry points and the
 // chunked two-slot pipeline that overlaps copies and kernels.  No CPU fallback: every compute entry point
 // launches the CUDA kernels in pixel.cu / ccl.cu / blob.cu / armour.cu or fails with an error code.
+#include <math.h>
 #include <stdlib.h>
 
 #include <new>
@@ -1033,6 +1034,116 @@ int rmcv_solve_pnp(rmcv_ctx* ctx, const rmcv_armour* armours, int n_armours, con
     RMCV_CUDA(ctx, cudaMemcpyAsync(ex->tmp_host, d + b_in, b_out, cudaMemcpyDeviceToHost, st));
     RMCV_CUDA(ctx, cudaStreamSynchronize(st));
     memcpy(poses, ex->tmp_host, b_out);
+    return RMCV_OK;
+}
+
+// ---- f3: tracking ----------------------------------------------------------------------------------------------------
+}  // extern "C"
+struct rmcv_tracker {
+    int cap;
+    rmcv_track* tracks; rmcv_track* backup;   // [cap] each, device
+    int32_t* n_tracks; int32_t* status;       // device
+};
+extern "C" {
+
+int rmcv_tracker_create(rmcv_ctx* ctx, int capacity, rmcv_tracker** out) {
+    if (!ctx || !out || capacity <= 0) return RMCV_ERR_INVALID_ARG;
+    *out = nullptr;
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    rmcv_tracker* t = new (std::nothrow) rmcv_tracker();
+    if (!t) return set_err(ctx, RMCV_ERR_CUDA, "out of host memory");
+    t->cap = capacity; t->tracks = t->backup = nullptr; t->n_tracks = t->status = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&t->tracks), (size_t)capacity * sizeof(rmcv_track));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->backup), (size_t)capacity * sizeof(rmcv_track));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->n_tracks), 2 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemset(t->n_tracks, 0, 2 * sizeof(int32_t));
+    if (e != cudaSuccess) {
+        cudaFree(t->tracks); cudaFree(t->backup); cudaFree(t->n_tracks);
+        delete t;
+        snprintf(ctx->err, sizeof(ctx->err), "tracker allocation failed: %s", cudaGetErrorString(e));
+        return RMCV_ERR_CUDA;
+    }
+    t->status = t->n_tracks + 1;
+    *out = t;
+    return RMCV_OK;
+}
+
+int rmcv_tracker_destroy(rmcv_ctx* ctx, rmcv_tracker* t) {
+    if (!ctx || !t) return RMCV_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(extra(ctx)->pix);
+    cudaFree(t->tracks); cudaFree(t->backup); cudaFree(t->n_tracks);
+    delete t;
+    return RMCV_OK;
+}
+
+int rmcv_tracker_reset(rmcv_ctx* ctx, rmcv_tracker* t) {
+    if (!ctx || !t) return RMCV_ERR_INVALID_ARG;
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    RMCV_CUDA(ctx, cudaMemsetAsync(t->n_tracks, 0, 2 * sizeof(int32_t), extra(ctx)->pix));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(extra(ctx)->pix));
+    return RMCV_OK;
+}
+
+int rmcv_tracker_update(rmcv_ctx* ctx, rmcv_tracker* t, const rmcv_armour* armours, const double* positions, const int32_t* identities,
+                        int n_armours, int64_t timestamp, double tick_frequency, double process_noise, double measurement_noise,
+                        double error) {
+    if (!ctx || !t || n_armours < 0 || (n_armours > 0 && (!armours || !positions))) return RMCV_ERR_INVALID_ARG;
+    if (!(tick_frequency > 0.0)) return set_err(ctx, RMCV_ERR_INVALID_ARG, "tick_frequency must be positive");
+    if (n_armours == 0) return RMCV_OK;   // executable/main.cpp:63: an empty frame changes nothing
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)n_armours;
+    const size_t b_arm = (n * sizeof(rmcv_armour) + 15) & ~(size_t)15, b_pos = (n * 3 * sizeof(double) + 15) & ~(size_t)15,
+                 b_id = (n * sizeof(int32_t) + 15) & ~(size_t)15;
+    int rc = ensure_tmp(ctx, b_arm + b_pos + 2 * b_id, b_arm + b_pos + b_id + 16);
+    if (rc != RMCV_OK) return rc;
+    CtxExtra* ex = extra(ctx);
+    uint8_t* h = reinterpret_cast<uint8_t*>(ex->tmp_host);
+    uint8_t* d = reinterpret_cast<uint8_t*>(ex->tmp_dev);
+    memcpy(h, armours, n * sizeof(rmcv_armour));
+    memcpy(h + b_arm, positions, n * 3 * sizeof(double));
+    if (identities) memcpy(h + b_arm + b_pos, identities, n * sizeof(int32_t));
+    cudaStream_t st = ex->pix;
+    RMCV_CUDA(ctx, cudaMemcpyAsync(d, h, b_arm + b_pos + b_id, cudaMemcpyHostToDevice, st));
+    RMCV_CUDA(ctx, launch_track_update(t->tracks, t->n_tracks, t->cap, t->backup, reinterpret_cast<const rmcv_armour*>(d),
+                                       reinterpret_cast<const double*>(d + b_arm),
+                                       identities ? reinterpret_cast<const int32_t*>(d + b_arm + b_pos) : nullptr, n_armours,
+                                       reinterpret_cast<int32_t*>(d + b_arm + b_pos + b_id), (long long)timestamp, tick_frequency,
+                                       process_noise, measurement_noise, error, t->status, st, &ctx->kernel_launches));
+    int32_t* hs = reinterpret_cast<int32_t*>(h + b_arm + b_pos + b_id);
+    RMCV_CUDA(ctx, cudaMemcpyAsync(hs, t->status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(st));
+    if (*hs == 1) return set_err(ctx, RMCV_ERR_CAPACITY, "track list capacity exceeded");
+    if (*hs == 2) return set_err(ctx, RMCV_ERR_CAPACITY, "identity history of a track exceeded RMCV_TRACK_HIST");
+    return RMCV_OK;
+}
+
+int rmcv_tracker_read(rmcv_ctx* ctx, rmcv_tracker* t, rmcv_track* tracks, int cap, int* n_tracks) {
+    if (!ctx || !t || !n_tracks || cap < 0 || (cap > 0 && !tracks)) return RMCV_ERR_INVALID_ARG;
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = extra(ctx)->pix;
+    int32_t n = 0;
+    RMCV_CUDA(ctx, cudaMemcpyAsync(&n, t->n_tracks, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(st));
+    *n_tracks = n;
+    const int m = n < cap ? n : cap;
+    if (m > 0) {
+        RMCV_CUDA(ctx, cudaMemcpyAsync(tracks, t->tracks, (size_t)m * sizeof(rmcv_track), cudaMemcpyDeviceToHost, st));
+        RMCV_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return RMCV_OK;
+}
+
+int rmcv_track_identity_max(const rmcv_track* track, int32_t* identity, double* probability) {
+    if (!track || !identity || !probability) return RMCV_ERR_INVALID_ARG;
+    double sum = 0.0;                                            // src/core.cpp:123-143
+    for (int i = 0; i < track->n_hist; ++i) sum += exp((double)track->hist_count[i]);
+    double best = 0.0; int32_t id = -1;
+    for (int i = 0; i < track->n_hist; ++i) {
+        const double prob = exp((double)track->hist_count[i]) / sum;
+        if (prob > best) { best = prob; id = track->hist_id[i]; }
+    }
+    *identity = id; *probability = best;
     return RMCV_OK;
 }
 

@@ -1,29 +1,28 @@
-// K1 (fast path) — register-resident pixel stage of rm::extract_color on interleaved BGR frames (src/imgproc.cpp:52-69):
-// cv::split + saturating channel difference + inRange + 3x3 MORPH_CLOSE -> {0,255} byte mask and the same mask bit-packed
-// for the labelling stages.  HBM-bound streaming kernel, no tensor cores (nothing here is a contraction).
+// K1 (alternative, opt-in: RMCV_BGR_STRIP=1) — register-resident pixel stage of rm::extract_color on interleaved BGR
+// frames (src/imgproc.cpp:52-69): cv::split + saturating channel difference + inRange + 3x3 MORPH_CLOSE -> {0,255} byte mask
+// and the same mask bit-packed for the labelling stages.  HBM-bound streaming kernel, no tensor cores.
 //
-//   * pixel groups of 16 pixels (48 bytes) are numbered through the whole call: slot = (frame, row segment, group), group
-//     fastest.  A warp owns 30 consecutive slots (+ one halo lane each side) and every lane walks down its segment of rows;
-//     neighbouring lanes are neighbouring groups of the same rows except across an image edge, where the close pads anyway,
-//     so 30 of 32 lanes do useful work whatever the image width;
-//   * a lane copies its 48 bytes of a row with three cp.async (LDGSTS) into its own slice of a 3-row ring in shared
-//     memory, rows ahead of the arithmetic, and reads them back with three conflict-free LDS.128 — no barrier, a
-//     lane only reads what it asked for itself;
+//   * a WARP owns a strip of 30 groups of 16 pixels (+ one halo lane each side) of one frame and walks down a segment of
+//     rows.  The warp's 1536 bytes of a row travel global -> shared with three fully coalesced cp.async (LDGSTS)
+//     instructions (lane l copies the 16-byte chunks l, l+32, l+64) into a 4-stage ring, three rows ahead of the
+//     arithmetic; after cp.async.wait_group + __syncwarp a lane reads its own 48 bytes back with three conflict-free
+//     LDS.128;
 //   * per 4 pixels 6 dp4a form c_a - c_b - lower_bound and funnel shifts collect the sign bits into a 16-bit threshold
 //     word; the close runs on a 20-bit window in registers (strip.cuh) and the byte mask leaves through the bits -> bytes
 //     table with one 16-byte streaming store per lane and row.
 //
-// About 6 thread instructions per pixel (the shared-memory band kernel in pixel.cu: 15.5), which leaves the issue slots of
-// an SM to the labelling kernels that run beside it.
+// About 7 thread instructions per pixel (the shared-memory band kernel in pixel.cu: 15.5).
 #include "strip.cuh"
 
 namespace rmcv {
 
 namespace {
 
-constexpr int kRows = 3;                       // rows in flight per lane (36 KB of ring per CTA)
+constexpr int kRows = 3;                       // rows in flight per warp
+constexpr int kRing = kRows + 1;               // ring stages: the stage read in the previous row is the one being refilled
 constexpr uint32_t kRowBytes = 32u * 48u;      // one row of a warp's ring
 constexpr int kWarps = 8;
+constexpr size_t kSmemBytes = 4096 + (size_t)kWarps * kRing * kRowBytes;   // table + rings (dynamic shared memory)
 
 struct BgrStripParams {
     const uint8_t* src; size_t frame_stride;
@@ -31,8 +30,8 @@ struct BgrStripParams {
     int pitch, mask_pitch;                     // row pitches in bytes (< 2^31)
     uint16_t* bits16;                          // bit mask viewed as 16-bit words, [batch][H][WB2]
     int W, H, NC, WB2;                         // NC = W / 16 groups per row, WB2 = 16-bit words per bit row
-    int seg, nseg;                             // rows per segment, segments per frame
-    int total_slots, total_warps;
+    int seg, nseg, nwx;                        // rows per segment, segments per frame, warps per strip row
+    int total_warps;
     uint32_t coef[6];                          // dp4a coefficient words (signed bytes) for the 4 pixels of a 12-byte group
     int acc0;                                  // -lower_bound (or the constants that force all-0 / all-1)
 };
@@ -66,33 +65,39 @@ __device__ __forceinline__ uint32_t thr16(const uint4 A, const uint4 B, const ui
 
 struct Lane {
     strip::CloseLane k;
-    const uint8_t* lp;       // raw row `lr` (clamped into the image) of this lane's group
+    const uint8_t* gp;       // chunk 0 of this lane in raw row `lr` (clamped into the image); chunks 1, 2 at +512, +1024
     int lr;
-    uint32_t ring, stage;    // shared address of the lane's slice of ring row 0; byte offset of the oldest row
+    uint32_t cmask;          // which of the lane's three chunks lie inside the row
+    uint32_t wring;          // shared address of the warp's ring + lane * 16 (copy side)
+    uint32_t rring;          // shared address of the warp's ring + lane * 48 (read side)
+    uint32_t stage, fill;    // byte offsets of the stage read next / refilled next
     int r;                   // image row of the threshold word that enters next
     int left;                // rows this lane still has to store (0 for halo / idle lanes)
     int tail16;
 };
 
+// Starts the copy of the next raw row of the warp's strip into stage `off` (one cp.async group, possibly empty).
 __device__ __forceinline__ void fetch_row(Lane& a, const BgrStripParams& p, uint32_t off) {
-    const uint8_t* g = a.lp;
-    a.lp += (unsigned)a.lr < (unsigned)(p.H - 1) ? p.pitch : 0;   // rows outside the image re-read the nearest row inside
+    const uint8_t* g = a.gp;
+    a.gp += (unsigned)a.lr < (unsigned)(p.H - 1) ? p.pitch : 0;   // rows outside the image re-read the nearest row inside
     ++a.lr;
-    strip::cp_async16_ca(a.ring + off, g);
-    strip::cp_async16_ca(a.ring + off + 16u, g + 16);
-    strip::cp_async16_ca(a.ring + off + 32u, g + 32);
+    if (a.cmask & 1u) strip::cp_async16(a.wring + off, g);
+    if (a.cmask & 2u) strip::cp_async16(a.wring + off + 512u, g + 512);
+    if (a.cmask & 4u) strip::cp_async16(a.wring + off + 1024u, g + 1024);
     strip::cp_commit();
 }
 
 template <bool STORE, bool MASK>
 __device__ __forceinline__ void one_row(Lane& a, const BgrStripParams& p) {
     strip::cp_wait<kRows - 1>();
-    const uint32_t s = a.ring + a.stage;
+    __syncwarp();             // every lane's chunks of this row have landed, and every lane is done with the previous stage
+    const uint32_t s = a.rring + a.stage;
     const uint4 A = strip::lds128(s), B = strip::lds128(s + 16u), C = strip::lds128(s + 32u);
-    uint32_t t = thr16(A, B, C, p);
-    fetch_row(a, p, a.stage);
+    fetch_row(a, p, a.fill);
+    a.fill = a.stage;
     a.stage += kRowBytes;
-    if (a.stage == kRows * kRowBytes) a.stage = 0u;
+    if (a.stage == kRing * kRowBytes) a.stage = 0u;
+    uint32_t t = thr16(A, B, C, p);
     if ((unsigned)a.r >= (unsigned)p.H) t = 0u;
     strip::push_row<STORE, MASK>(a.k, p.WB2, p.mask_pitch, t, (unsigned)(a.r - 1) >= (unsigned)p.H, a.left > 0,
                                  a.left > 0 && a.tail16);
@@ -102,14 +107,19 @@ __device__ __forceinline__ void one_row(Lane& a, const BgrStripParams& p) {
 
 }  // namespace
 
-// One work item: 30 consecutive slots (+ halo lanes) walked down their row segments.
-template <bool MASK>
-__device__ __forceinline__ void walk_item(const BgrStripParams& p, int item, int lane, uint32_t ring, uint32_t lut) {
-    const int slot = item * 30 - 1 + lane;                   // lanes 0 and 31 only feed their neighbours
-    const bool valid = slot >= 0 && slot < p.total_slots;
-    const int sc = min(max(slot, 0), p.total_slots - 1);
-    const int c = sc % p.NC, q = sc / p.NC;
-    const int sg = q % p.nseg, frame = q / p.nseg;
+template <bool MASK, int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB) bgr_strip_kernel(const BgrStripParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];         // [4 KB table area][kWarps rings]
+    strip::lut_init(smem, threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wid = blockIdx.x * kWarps + warp;
+    if (wid >= p.total_warps) return;
+    const int wx = wid % p.nwx, rest = wid / p.nwx;
+    const int sg = rest % p.nseg, frame = rest / p.nseg;
+    const int c = wx * 30 - 1 + lane;                        // pixel group of this lane (lanes 0 and 31: halo only)
+    const bool valid = c >= 0 && c < p.NC;
+    const int cc = min(max(c, 0), p.NC - 1);
     const int y0 = sg * p.seg;
     Lane a;
     a.k.h0 = a.k.h1 = 0u; a.k.e0 = a.k.e1 = 0u;
@@ -117,17 +127,24 @@ __device__ __forceinline__ void walk_item(const BgrStripParams& p, int item, int
     if (c == 0) inside &= 0xffffcu;
     if (c == p.NC - 1) inside &= 0x3ffffu;
     a.k.inside = valid ? inside : 0u;
-    a.k.lut = lut;
-    a.k.mrow = MASK ? p.mask + (size_t)frame * p.mask_frame_stride + (size_t)y0 * p.mask_pitch + (size_t)c * 16 : nullptr;
-    a.k.brow = p.bits16 + ((size_t)frame * p.H + y0) * p.WB2 + c;
+    a.k.lut = strip::lut_base(smem);
+    a.k.mrow = MASK ? p.mask + (size_t)frame * p.mask_frame_stride + (size_t)y0 * p.mask_pitch + (size_t)cc * 16 : nullptr;
+    a.k.brow = p.bits16 + ((size_t)frame * p.H + y0) * p.WB2 + cc;
     const bool writer = valid && lane >= 1 && lane <= 30;
     a.left = writer ? min(p.seg, p.H - y0) : 0;
     a.tail16 = (c == p.NC - 1 && p.WB2 > p.NC) ? 1 : 0;      // W % 32 == 16: the upper half of the last bit word is zero
     a.r = y0 - 2;
     a.lr = a.r;
-    a.lp = p.src + (size_t)frame * p.frame_stride + (size_t)min(max(a.lr, 0), p.H - 1) * p.pitch + (size_t)c * 48;
-    a.ring = ring;
+    // byte offset in the row of this lane's chunk j: (wx * 30 - 1) * 48 + (j * 32 + lane) * 16
+    const int x0 = (wx * 30 - 1) * 48 + lane * 16, rowbytes = p.W * 3;
+    a.cmask = (x0 >= 0 && x0 < rowbytes ? 1u : 0u) | (x0 + 512 >= 0 && x0 + 512 < rowbytes ? 2u : 0u) |
+              (x0 + 1024 >= 0 && x0 + 1024 < rowbytes ? 4u : 0u);
+    a.gp = p.src + (size_t)frame * p.frame_stride + (size_t)min(max(a.lr, 0), p.H - 1) * p.pitch + (ptrdiff_t)x0;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem + 4096) + warp * (kRing * kRowBytes);
+    a.wring = ring + lane * 16u;
+    a.rring = ring + lane * 48u;
     a.stage = 0u;
+    a.fill = kRows * kRowBytes;
 #pragma unroll
     for (int st = 0; st < kRows; ++st) fetch_row(a, p, st * kRowBytes);
     // rows y0-2 .. y0+1 fill the pipeline; every later row releases one final row
@@ -135,19 +152,7 @@ __device__ __forceinline__ void walk_item(const BgrStripParams& p, int item, int
     for (int i = 0; i < 4; ++i) one_row<false, MASK>(a, p);
 #pragma unroll 2
     for (int i = 0; i < p.seg; ++i) one_row<true, MASK>(a, p);
-    strip::cp_wait<0>();                                      // the rows fetched past the segment
-}
-
-template <bool MASK, int MINB>
-__global__ void __launch_bounds__(kWarps * 32, MINB) bgr_strip_kernel(const BgrStripParams p) {
-    __shared__ __align__(16) uint8_t s_lut_raw[4096];
-    __shared__ __align__(16) uint8_t s_ring[kWarps * kRows * kRowBytes];
-    strip::lut_init(s_lut_raw, threadIdx.x);
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_ring) + (threadIdx.x >> 5) * (kRows * kRowBytes) + lane * 48u;
-    const int wid = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    if (wid < p.total_warps) walk_item<MASK>(p, wid, lane, ring, strip::lut_base(s_lut_raw));
+    strip::cp_wait<0>();
 }
 
 // Fast path of the BGR pixel stage; cudaErrorNotSupported when the call does not qualify (the caller then runs the
@@ -163,6 +168,7 @@ cudaError_t launch_bgr_strip(const PixelLaunch& L, int sm_count, cudaStream_t st
     p.mask = L.mask; p.mask_pitch = (int)L.mask_pitch; p.mask_frame_stride = L.mask_frame_stride;
     p.bits16 = reinterpret_cast<uint16_t*>(L.bits);
     p.W = L.W; p.H = L.H; p.NC = L.W / 16; p.WB2 = 2 * ((L.W + 31) / 32);
+    p.nwx = (p.NC + 29) / 30;
     {   // plus / minus channel (src/imgproc.cpp:56-65) as dp4a coefficient words: byte k of a 12-byte group belongs to pixel
         // k/3, channel k%3; order: c0 (px0,w0) c1a (px1,w0) c1b (px1,w1) c2a (px2,w1) c2b (px2,w2) c3 (px3,w2)
         int ca, cb;
@@ -197,7 +203,7 @@ cudaError_t launch_bgr_strip(const PixelLaunch& L, int sm_count, cudaStream_t st
         const long long slots = (long long)(minb >= 4 ? 4 : 3) * kWarps * sm_count;
         long long best = -1;
         for (int sg = 16; sg <= 128; ++sg) {
-            const long long warps = ((long long)L.batch * ((L.H + sg - 1) / sg) * p.NC + 29) / 30;
+            const long long warps = (long long)L.batch * ((L.H + sg - 1) / sg) * p.nwx;
             const long long cost = ((warps + slots - 1) / slots) * (sg + 6);
             if (best < 0 || cost < best) { best = cost; seg = sg; }
         }
@@ -205,18 +211,20 @@ cudaError_t launch_bgr_strip(const PixelLaunch& L, int sm_count, cudaStream_t st
     if (seg > L.H) seg = L.H;
     if (seg < 1) seg = 1;
     p.seg = seg; p.nseg = (L.H + seg - 1) / seg;
-    const long long total = (long long)L.batch * p.nseg * p.NC;
-    if (total <= 0 || total > 0x3fffffffLL) return cudaErrorNotSupported;
-    p.total_slots = (int)total;
-    p.total_warps = (int)((total + 29) / 30);
+    const long long total = (long long)L.batch * p.nseg * p.nwx;
+    if (total <= 0 || total > 0x7fffffffLL) return cudaErrorNotSupported;
+    p.total_warps = (int)total;
     const unsigned grid = (unsigned)((p.total_warps + kWarps - 1) / kWarps);
-    if (L.mask) {
-        if (minb >= 4) bgr_strip_kernel<true, 4><<<grid, kWarps * 32, 0, st>>>(p);
-        else bgr_strip_kernel<true, 3><<<grid, kWarps * 32, 0, st>>>(p);
-    } else {
-        if (minb >= 4) bgr_strip_kernel<false, 4><<<grid, kWarps * 32, 0, st>>>(p);
-        else bgr_strip_kernel<false, 3><<<grid, kWarps * 32, 0, st>>>(p);
-    }
+    cudaError_t e = cudaSuccess;
+#define RMCV_BGR_LAUNCH(M_, B_)                                                                                         \
+    do {                                                                                                                \
+        e = cudaFuncSetAttribute(bgr_strip_kernel<M_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes); \
+        if (e == cudaSuccess) bgr_strip_kernel<M_, B_><<<grid, kWarps * 32, kSmemBytes, st>>>(p);                        \
+    } while (0)
+    if (L.mask) { if (minb >= 4) RMCV_BGR_LAUNCH(true, 4); else RMCV_BGR_LAUNCH(true, 3); }
+    else { if (minb >= 4) RMCV_BGR_LAUNCH(false, 4); else RMCV_BGR_LAUNCH(false, 3); }
+#undef RMCV_BGR_LAUNCH
+    if (e != cudaSuccess) return e;
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -217,6 +217,11 @@ cudaError_t launch_frontend(const uint8_t* d_src, size_t pitch, size_t frame_str
                             size_t dframe_stride, int W, int H, int batch, int bits, int mirror, int flip, cudaStream_t st,
                             int64_t* launches);
 
+// f3: one iteration of the tracking loop (track.cu)
+cudaError_t launch_track_update(rmcv_track* d_tracks, int32_t* d_n_tracks, int cap, rmcv_track* d_backup, const rmcv_armour* d_armours,
+                                const double* d_positions, const int32_t* d_identities, int n, int32_t* d_remaining, long long timestamp,
+                                double freq, double q, double r, double err, int32_t* d_status, cudaStream_t st, int64_t* launches);
+
 void upload_luts();  // copies the arc LUT to constant memory (once per process/device)
 
 }  // namespace rmcv

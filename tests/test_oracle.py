@@ -214,3 +214,30 @@ def test_golden_fixtures(path):
         assert (a.i, a.j) == (g["i"], g["j"]) and np.allclose(a.icon, g["icon"], atol=1e-3) and list(a.bounding_box) == g["bounding_box"]
     raw = synth.bgr_to_bayer(img, synth.BAYER_BG)
     assert zlib.crc32(O.extract_color_mask(O.bayer_to_bgr(raw, 4), case["target"], 80).tobytes()) == rec["bayer_bg_mask_crc32"]
+
+
+def test_tracking_loop_restatement_semantics():
+    """f3 oracle (executable/main.cpp:57-88 through cv2.KalmanFilter): the reference's quirks are kept — the first
+    correct() runs against a zero errorCovPre and leaves the state at zero; a track keeps the bounding box it was opened
+    with; lost_count is never cleared and the 27th miss erases the track, skipping the track behind it."""
+    a = lambda box, pos, ident, ts: O.TrackedArmour(box, pos, ident, ts)
+    tr = O.tracking_step([], [a((0, 0, 10, 10), (1, 2, 3), 1, 0), a((100, 0, 10, 10), (4, 5, 6), 2, 0)], 1e9)
+    assert len(tr) == 2 and not tr[0].initialized
+    tr = O.tracking_step(tr, [a((1, 0, 10, 10), (2, 2, 3), 1, 1_000_000)], 1e9)
+    assert tr[0].initialized and np.all(tr[0].observer.statePost == 0) and np.all(tr[0].observer.errorCovPost == 0)
+    assert tr[0].bounding_box == tuple(np.float32(v) for v in (0, 0, 10, 10)) and tr[1].lost_count == 1
+    tr = O.tracking_step(tr, [a((1, 0, 10, 10), (3, 2, 3), 1, 2_000_000)], 1e9)
+    assert tr[0].observer.statePost[0, 0] > 0 and tr[0].identity_max()[0] == 1
+    # third track far away keeps matching; track 1 misses until it is erased, and the erase skips the track behind it
+    tr = O.tracking_step(tr, [a((1, 0, 10, 10), (3, 2, 3), 1, 3_000_000), a((500, 500, 10, 10), (0, 0, 0), 3, 3_000_000)], 1e9)
+    assert len(tr) == 3
+    for n in range(40):
+        before = [t.lost_count for t in tr]
+        tr = O.tracking_step(tr, [a((1, 0, 10, 10), (3, 2, 3), 1, 4_000_000 + n)], 1e9)
+        if len(tr) == 2:
+            assert before[1] == 26 and tr[1].lost_count == before[2], "the track behind the erased one must be skipped"
+            break
+    else:
+        raise AssertionError("track was never erased")
+    assert float(O.rect_iou((0, 0, 10, 10), (5, 5, 10, 10))) == pytest.approx(25 / 175)
+    assert np.isnan(O.rect_iou((0, 0, 0, 0), (0, 0, 0, 0)))
