@@ -312,6 +312,42 @@ int rmcv_solve_pnp(rmcv_ctx* ctx, const rmcv_armour* armours, int n_armours, con
                    const double dist_coeffs[5], float exact_w, float exact_h, float roi_x, float roi_y,
                    const double* cam2world, rmcv_pose* poses);
 
+/* ---- f2 (next row, first half): the icon crop that feeds the SVM ------------------------------------------------ */
+/* rm::affine_correction (src/imgproc.cpp:9-35) + rm::utils::flatten_image (src/core.cpp:202-216) for every armour of a
+ * frame that is resident in device memory (d_bgr: height x width x 3, interleaved, row pitch in bytes): the icon vertices
+ * are clamped into the frame IN PLACE like the reference does (armours[k].icon is updated), the bounding box of the rounded
+ * vertices is warped by cv::getAffineTransform / cv::warpAffine (bilinear, constant border 0) and resized (bilinear) to
+ * out_w x out_h.  icons: n x out_h x out_w x 3 bytes (bit-exact against OpenCV); rows: the same values as float32, one
+ * row of out_w * out_h * 3 per armour (the SVM's input, executable/main.cpp:180-181), or NULL.  armours / icons / rows are
+ * host pointers; synchronous.  The SVM itself is not part of the library (the reference ships no svm.xml). */
+int rmcv_icon_batch(rmcv_ctx* ctx, const uint8_t* d_bgr, size_t pitch, int width, int height, rmcv_armour* armours,
+                    int n_armours, int out_w, int out_h, uint8_t* icons, float* rows);
+
+/* ---- f2 (next row, second half): cv::ml::SVM::predict for the model the reference trains --------------------------- */
+/* A trained C_SVC model with the LINEAR kernel (executable/svm/optimizer.cpp:18-21), as cv::ml::SVM holds it after
+ * training / SVM::load: the (compressed) support vectors, and per one-vs-one decision function (class i against class j,
+ * i < j, in that order) its rho and its (alpha, support-vector index) pairs.  From Python:
+ * svm.getSupportVectors(), svm.getDecisionFunction(k) -> (rho, alpha, svidx).  Host pointers. */
+typedef struct rmcv_svm_model {
+    int32_t var_count;               /* features per sample (out_w * out_h * 3 = 1200 for the 20 x 20 icons)          */
+    int32_t class_count;             /* <= 32                                                                         */
+    int32_t sv_total;
+    const float* support_vectors;    /* sv_total x var_count                                                          */
+    const int32_t* class_labels;     /* class_count labels, ascending (the sorted distinct training responses)        */
+    const double* rho;               /* class_count * (class_count - 1) / 2                                           */
+    const int32_t* df_ofs;           /* decision function k uses entries df_ofs[k] .. df_ofs[k+1]-1 of the next two   */
+    const double* df_alpha;
+    const int32_t* df_index;
+} rmcv_svm_model;
+/* labels[s] = (int)svm->predict(rows[s]) for n rows of var_count floats (OpenCV's summation order and one-vs-one vote,
+ * modules/ml/src/svm.cpp).  Host pointers, synchronous. */
+int rmcv_svm_predict(rmcv_ctx* ctx, const rmcv_svm_model* model, const float* rows, int n, int32_t* labels);
+/* executable/main.cpp:178-181 in one call: icon crop (out_w x out_h, out_w * out_h * 3 == model->var_count) and SVM
+ * identity of every armour of a device-resident frame, without the host round trip between the two; armours[k].icon is
+ * clamped in place as in rmcv_icon_batch. */
+int rmcv_identify_batch(rmcv_ctx* ctx, const uint8_t* d_bgr, size_t pitch, int width, int height, rmcv_armour* armours,
+                        int n_armours, int out_w, int out_h, const rmcv_svm_model* model, int32_t* identities);
+
 /* ---- f3 (next row): armour tracking — IoU association + 6-state Kalman filter + identity vote ------------------ */
 /* One tracked armour: the public tracking fields of rm::armour (include/core.h:103-122) and the state of its
  * cv::KalmanFilter(6, 6, 0, CV_64F) observer (src/core.cpp:21,51-69).  As in the reference, bbox / position / identity

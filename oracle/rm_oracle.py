@@ -511,6 +511,31 @@ def blob_label_map(binary: np.ndarray, contours: Sequence[np.ndarray]) -> np.nda
     return lut[labels]
 
 
+# --------------------------------------------------------------------------- f2 icon crop (next row, first half)
+def affine_correction(source: np.ndarray, vertices: np.ndarray, out_size=(20, 20)):
+    """rm::affine_correction, src/imgproc.cpp:9-35, through the same OpenCV calls.  Returns (calibration, vertices clamped
+    in place like the reference does)."""
+    v = np.asarray(vertices, np.float32).copy()
+    rows, cols = source.shape[:2]
+    v[:, 0] = np.maximum(np.float32(0), np.minimum(v[:, 0], np.float32(cols) - np.float32(1)))   # :11-15
+    v[:, 1] = np.maximum(np.float32(0), np.minimum(v[:, 1], np.float32(rows) - np.float32(1)))
+    pts = np.rint(v).astype(np.int32)            # std::vector<cv::Point>(Point2f...): cvRound
+    x, y, w, h = cv2.boundingRect(pts.reshape(-1, 1, 2))   # :17
+    src = np.float32([[v[1, 0] - np.float32(x), v[1, 1] - np.float32(y)], [v[2, 0] - np.float32(x), v[2, 1] - np.float32(y)],
+                      [v[0, 0] - np.float32(x), v[0, 1] - np.float32(y)]])
+    dst = np.float32([[0, 0], [w, 0], [0, h]])
+    warp = cv2.getAffineTransform(src, dst)      # :28
+    roi = source[y:y + h, x:x + w]
+    calibration = cv2.warpAffine(roi, warp, (w, h))   # :31 (an empty dsize means the source size)
+    calibration = cv2.resize(calibration, tuple(out_size))   # :32
+    return calibration, v
+
+
+def flatten_image(image: np.ndarray) -> np.ndarray:
+    """rm::utils::flatten_image(input, CV_32FC1), src/core.cpp:202-216 (no resize)."""
+    return image.reshape(1, -1).astype(np.float32)
+
+
 # --------------------------------------------------------------------------- f3 tracking (next row)
 class TrackedArmour:
     """The tracking side of rm::armour (include/core.h:103-122): cv::KalmanFilter(6, 6, 0, CV_64F) observer, measurement,

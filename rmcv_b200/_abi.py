@@ -65,6 +65,12 @@ class Results(C.Structure):
                 ("blobs", C.POINTER(LightBlob)), ("armours", C.POINTER(Armour)), ("poses", C.POINTER(Pose))]
 
 
+class SvmModel(C.Structure):
+    _fields_ = [("var_count", C.c_int32), ("class_count", C.c_int32), ("sv_total", C.c_int32), ("support_vectors", C.c_void_p),
+                ("class_labels", C.c_void_p), ("rho", C.c_void_p), ("df_ofs", C.c_void_p), ("df_alpha", C.c_void_p),
+                ("df_index", C.c_void_p)]
+
+
 TRACK_HIST = 8
 
 
@@ -125,6 +131,9 @@ PROTOTYPES = {
     "rmcv_set_camera": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_float, _vp]),
     "rmcv_clear_camera": (C.c_int, [_vp]),
     "rmcv_solve_pnp": (C.c_int, [_vp, _vp, _i, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, _vp, _vp]),
+    "rmcv_icon_batch": (C.c_int, [_vp, _u8p, _sz, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "rmcv_svm_predict": (C.c_int, [_vp, C.POINTER(SvmModel), _vp, _i, _vp]),
+    "rmcv_identify_batch": (C.c_int, [_vp, _u8p, _sz, _i, _i, _vp, _i, _i, _i, C.POINTER(SvmModel), _vp]),
     "rmcv_tracker_create": (C.c_int, [_vp, _i, C.POINTER(_vp)]),
     "rmcv_tracker_destroy": (C.c_int, [_vp, _vp]),
     "rmcv_tracker_reset": (C.c_int, [_vp, _vp]),

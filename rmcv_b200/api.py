@@ -495,6 +495,39 @@ class Context:
     def clear_camera(self):
         self._check(self.lib.rmcv_clear_camera(self.h), "rmcv_clear_camera")
 
+    def icon_batch(self, d_bgr: int, width: int, height: int, armours: Sequence[Armour], out_size=(20, 20), pitch: Optional[int] = None):
+        """rm::affine_correction + flatten_image for every armour of a device-resident frame ->
+        (icons uint8 n x h x w x 3, rows float32 n x (w*h*3), armours with their icon vertices clamped into the frame)."""
+        n = len(armours)
+        ow, oh = int(out_size[0]), int(out_size[1])
+        icons = np.zeros((n, oh, ow, 3), np.uint8)
+        rows = np.zeros((n, ow * oh * 3), np.float32)
+        if n == 0:
+            return icons, rows, []
+        arr = (A.Armour * n)(*[a.to_c() for a in armours])
+        self._check(self.lib.rmcv_icon_batch(self.h, d_bgr, pitch or width * 3, width, height, arr, n, ow, oh, icons.ctypes.data,
+                                             rows.ctypes.data), "rmcv_icon_batch")
+        return icons, rows, [Armour.from_c(arr[i]) for i in range(n)]
+
+    def svm_predict(self, model: "SvmModel", rows: np.ndarray) -> np.ndarray:
+        """labels[s] = int(svm.predict(rows[s])) (cv::ml::SVM, C_SVC + LINEAR)."""
+        rows = np.ascontiguousarray(rows, np.float32).reshape(-1, model.sv.shape[1])
+        out = np.zeros(len(rows), np.int32)
+        if len(rows):
+            self._check(self.lib.rmcv_svm_predict(self.h, C.byref(model.c), rows.ctypes.data, len(rows), out.ctypes.data), "rmcv_svm_predict")
+        return out
+
+    def identify_batch(self, d_bgr: int, width: int, height: int, armours: Sequence[Armour], model: "SvmModel", out_size=(20, 20),
+                       pitch: Optional[int] = None) -> np.ndarray:
+        """executable/main.cpp:178-181: icon crop + SVM identity of every armour of a device-resident frame."""
+        n = len(armours)
+        out = np.zeros(n, np.int32)
+        if n:
+            arr = (A.Armour * n)(*[a.to_c() for a in armours])
+            self._check(self.lib.rmcv_identify_batch(self.h, d_bgr, pitch or width * 3, width, height, arr, n, int(out_size[0]),
+                                                     int(out_size[1]), C.byref(model.c), out.ctypes.data), "rmcv_identify_batch")
+        return out
+
     def solve_pnp(self, armours: Sequence[Armour], camera_matrix, dist_coeffs, exact_size=(27.0, 27.0), roi=(0.0, 0.0),
                   cam2world=None):
         """rm::solve_PnP for every armour -> list of (rvec[3], tvec[3], position[3], ok)."""
@@ -510,6 +543,34 @@ class Context:
                                             float(exact_size[0]), float(exact_size[1]), float(roi[0]), float(roi[1]),
                                             None if M is None else M.ctypes.data, out), "rmcv_solve_pnp")
         return [(np.array(o.rvec[:]), np.array(o.tvec[:]), np.array(o.position[:]), bool(o.ok)) for o in out]
+
+
+class SvmModel:
+    """A trained cv::ml::SVM (C_SVC, LINEAR kernel) as plain arrays: support_vectors (sv_total x var_count float32),
+    class_labels (ascending), and per one-vs-one decision function rho and (alpha, support-vector index) lists.
+    From cv2: SvmModel.from_cv2(svm, class_labels)."""
+
+    def __init__(self, support_vectors, class_labels, rho, alphas, indices):
+        self.sv = np.ascontiguousarray(support_vectors, np.float32)
+        self.labels = np.ascontiguousarray(class_labels, np.int32)
+        self.rho = np.ascontiguousarray(rho, np.float64)
+        ofs = [0]
+        for a in alphas:
+            ofs.append(ofs[-1] + len(a))
+        self.ofs = np.ascontiguousarray(ofs, np.int32)
+        self.alpha = np.ascontiguousarray(np.concatenate([np.asarray(a, np.float64).reshape(-1) for a in alphas]), np.float64)
+        self.index = np.ascontiguousarray(np.concatenate([np.asarray(i, np.int32).reshape(-1) for i in indices]), np.int32)
+        c = A.SvmModel()
+        c.var_count, c.class_count, c.sv_total = self.sv.shape[1], len(self.labels), self.sv.shape[0]
+        c.support_vectors, c.class_labels, c.rho = self.sv.ctypes.data, self.labels.ctypes.data, self.rho.ctypes.data
+        c.df_ofs, c.df_alpha, c.df_index = self.ofs.ctypes.data, self.alpha.ctypes.data, self.index.ctypes.data
+        self.c = c
+
+    @staticmethod
+    def from_cv2(svm, class_labels) -> "SvmModel":
+        k = len(class_labels)
+        dfs = [svm.getDecisionFunction(i) for i in range(k * (k - 1) // 2)]
+        return SvmModel(svm.getSupportVectors(), sorted(class_labels), [d[0] for d in dfs], [d[1] for d in dfs], [d[2] for d in dfs])
 
 
 class Tracker:

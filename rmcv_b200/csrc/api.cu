@@ -1037,6 +1037,133 @@ int rmcv_solve_pnp(rmcv_ctx* ctx, const rmcv_armour* armours, int n_armours, con
     return RMCV_OK;
 }
 
+int rmcv_icon_batch(rmcv_ctx* ctx, const uint8_t* d_bgr, size_t pitch, int width, int height, rmcv_armour* armours, int n_armours,
+                    int out_w, int out_h, uint8_t* icons, float* rows) {
+    if (!ctx || !d_bgr || n_armours < 0 || (n_armours > 0 && (!armours || !icons))) return RMCV_ERR_INVALID_ARG;
+    if (width <= 0 || height <= 0 || out_w <= 0 || out_h <= 0 || out_w > 4096 || out_h > 4096 || pitch < (size_t)width * 3)
+        return set_err(ctx, RMCV_ERR_INVALID_ARG, "bad frame or icon geometry");
+    if (n_armours == 0) return RMCV_OK;
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)n_armours, npx = (size_t)out_w * out_h * 3;
+    const size_t b_arm = (n * sizeof(rmcv_armour) + 15) & ~(size_t)15, b_icon = (n * npx + 15) & ~(size_t)15,
+                 b_rows = rows ? n * npx * sizeof(float) : 0;
+    int rc = ensure_tmp(ctx, b_arm + b_icon + b_rows, b_arm + b_icon + b_rows);
+    if (rc != RMCV_OK) return rc;
+    CtxExtra* ex = extra(ctx);
+    uint8_t* h = reinterpret_cast<uint8_t*>(ex->tmp_host);
+    uint8_t* d = reinterpret_cast<uint8_t*>(ex->tmp_dev);
+    memcpy(h, armours, n * sizeof(rmcv_armour));
+    cudaStream_t st = ex->pix;
+    RMCV_CUDA(ctx, cudaMemcpyAsync(d, h, n * sizeof(rmcv_armour), cudaMemcpyHostToDevice, st));
+    RMCV_CUDA(ctx, launch_icons(d_bgr, pitch, width, height, reinterpret_cast<rmcv_armour*>(d), n_armours, out_w, out_h, d + b_arm,
+                                rows ? reinterpret_cast<float*>(d + b_arm + b_icon) : nullptr, st, &ctx->kernel_launches));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(h, d, b_arm + b_icon + b_rows, cudaMemcpyDeviceToHost, st));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(armours, h, n * sizeof(rmcv_armour));
+    memcpy(icons, h + b_arm, n * npx);
+    if (rows) memcpy(rows, h + b_arm + b_icon, n * npx * sizeof(float));
+    return RMCV_OK;
+}
+
+namespace {
+struct SvmDevice {   // model arrays inside one device allocation
+    const float* sv; const double* rho; const int32_t* df_ofs; const double* df_alpha; const int32_t* df_index; const int32_t* labels;
+    size_t bytes;
+};
+int check_svm_model(rmcv_ctx* ctx, const rmcv_svm_model* m) {
+    if (!m || !m->support_vectors || !m->class_labels || !m->rho || !m->df_ofs || !m->df_alpha || !m->df_index)
+        return set_err(ctx, RMCV_ERR_INVALID_ARG, "incomplete svm model");
+    if (m->var_count <= 0 || m->class_count < 2 || m->class_count > 32 || m->sv_total <= 0)
+        return set_err(ctx, RMCV_ERR_INVALID_ARG, "bad svm model sizes");
+    const int ndf = m->class_count * (m->class_count - 1) / 2;
+    for (int k = 0; k < ndf; ++k) if (m->df_ofs[k + 1] < m->df_ofs[k] || m->df_ofs[k] < 0) return set_err(ctx, RMCV_ERR_INVALID_ARG, "bad svm decision function offsets");
+    for (int k = m->df_ofs[0]; k < m->df_ofs[ndf]; ++k)
+        if (m->df_index[k] < 0 || m->df_index[k] >= m->sv_total) return set_err(ctx, RMCV_ERR_INVALID_ARG, "svm support vector index out of range");
+    return RMCV_OK;
+}
+// lays the model out at d (device) through the staging area h (pinned host); returns the device views
+SvmDevice stage_svm_model(const rmcv_svm_model* m, uint8_t* h, uint8_t* d, bool copy) {
+    const int ndf = m->class_count * (m->class_count - 1) / 2, nk = m->df_ofs[ndf];
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    size_t o = 0;
+    SvmDevice v;
+    const size_t b_sv = (size_t)m->sv_total * m->var_count * sizeof(float);
+    v.sv = reinterpret_cast<const float*>(d + o); if (copy) memcpy(h + o, m->support_vectors, b_sv); o = al(o + b_sv);
+    v.rho = reinterpret_cast<const double*>(d + o); if (copy) memcpy(h + o, m->rho, ndf * sizeof(double)); o = al(o + ndf * sizeof(double));
+    v.df_alpha = reinterpret_cast<const double*>(d + o); if (copy) memcpy(h + o, m->df_alpha, nk * sizeof(double)); o = al(o + nk * sizeof(double));
+    v.df_ofs = reinterpret_cast<const int32_t*>(d + o); if (copy) memcpy(h + o, m->df_ofs, (ndf + 1) * sizeof(int32_t)); o = al(o + (ndf + 1) * sizeof(int32_t));
+    v.df_index = reinterpret_cast<const int32_t*>(d + o); if (copy) memcpy(h + o, m->df_index, nk * sizeof(int32_t)); o = al(o + nk * sizeof(int32_t));
+    v.labels = reinterpret_cast<const int32_t*>(d + o); if (copy) memcpy(h + o, m->class_labels, m->class_count * sizeof(int32_t)); o = al(o + m->class_count * sizeof(int32_t));
+    v.bytes = o;
+    return v;
+}
+}  // namespace
+
+int rmcv_svm_predict(rmcv_ctx* ctx, const rmcv_svm_model* model, const float* rows, int n, int32_t* labels) {
+    if (!ctx || n < 0 || (n > 0 && (!rows || !labels))) return RMCV_ERR_INVALID_ARG;
+    int rc = check_svm_model(ctx, model);
+    if (rc != RMCV_OK) return rc;
+    if (n == 0) return RMCV_OK;
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t b_model = stage_svm_model(model, nullptr, nullptr, false).bytes;
+    const size_t b_rows = ((size_t)n * model->var_count * sizeof(float) + 15) & ~(size_t)15;
+    const size_t b_k = ((size_t)n * model->sv_total * sizeof(float) + 15) & ~(size_t)15, b_lab = ((size_t)n * sizeof(int32_t) + 15) & ~(size_t)15;
+    rc = ensure_tmp(ctx, b_model + b_rows + b_k + b_lab, b_model + b_rows + b_lab);
+    if (rc != RMCV_OK) return rc;
+    CtxExtra* ex = extra(ctx);
+    uint8_t* h = reinterpret_cast<uint8_t*>(ex->tmp_host);
+    uint8_t* d = reinterpret_cast<uint8_t*>(ex->tmp_dev);
+    const SvmDevice v = stage_svm_model(model, h, d, true);
+    memcpy(h + b_model, rows, (size_t)n * model->var_count * sizeof(float));
+    cudaStream_t st = ex->pix;
+    RMCV_CUDA(ctx, cudaMemcpyAsync(d, h, b_model + b_rows, cudaMemcpyHostToDevice, st));
+    int32_t* d_lab = reinterpret_cast<int32_t*>(d + b_model + b_rows + b_k);
+    RMCV_CUDA(ctx, launch_svm_predict(reinterpret_cast<const float*>(d + b_model), n, v.sv, model->sv_total, model->var_count, v.rho, v.df_ofs,
+                                      v.df_alpha, v.df_index, v.labels, model->class_count, reinterpret_cast<float*>(d + b_model + b_rows),
+                                      d_lab, st, &ctx->kernel_launches));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(h, d_lab, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(labels, h, (size_t)n * sizeof(int32_t));
+    return RMCV_OK;
+}
+
+int rmcv_identify_batch(rmcv_ctx* ctx, const uint8_t* d_bgr, size_t pitch, int width, int height, rmcv_armour* armours, int n_armours,
+                        int out_w, int out_h, const rmcv_svm_model* model, int32_t* identities) {
+    if (!ctx || !d_bgr || n_armours < 0 || (n_armours > 0 && (!armours || !identities))) return RMCV_ERR_INVALID_ARG;
+    int rc = check_svm_model(ctx, model);
+    if (rc != RMCV_OK) return rc;
+    if (width <= 0 || height <= 0 || out_w <= 0 || out_h <= 0 || pitch < (size_t)width * 3 || (long long)out_w * out_h * 3 != model->var_count)
+        return set_err(ctx, RMCV_ERR_INVALID_ARG, "icon size does not match the model's var_count");
+    if (n_armours == 0) return RMCV_OK;
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)n_armours, npx = (size_t)model->var_count;
+    const size_t b_model = stage_svm_model(model, nullptr, nullptr, false).bytes;
+    const size_t b_arm = (n * sizeof(rmcv_armour) + 15) & ~(size_t)15, b_icon = (n * npx + 15) & ~(size_t)15, b_rows = n * npx * sizeof(float);
+    const size_t b_k = (n * model->sv_total * sizeof(float) + 15) & ~(size_t)15, b_lab = (n * sizeof(int32_t) + 15) & ~(size_t)15;
+    rc = ensure_tmp(ctx, b_model + b_arm + b_icon + b_rows + b_k + b_lab, b_model + b_arm + b_lab);
+    if (rc != RMCV_OK) return rc;
+    CtxExtra* ex = extra(ctx);
+    uint8_t* h = reinterpret_cast<uint8_t*>(ex->tmp_host);
+    uint8_t* d = reinterpret_cast<uint8_t*>(ex->tmp_dev);
+    const SvmDevice v = stage_svm_model(model, h, d, true);
+    memcpy(h + b_model, armours, n * sizeof(rmcv_armour));
+    cudaStream_t st = ex->pix;
+    RMCV_CUDA(ctx, cudaMemcpyAsync(d, h, b_model + b_arm, cudaMemcpyHostToDevice, st));
+    rmcv_armour* d_arm = reinterpret_cast<rmcv_armour*>(d + b_model);
+    float* d_rows = reinterpret_cast<float*>(d + b_model + b_arm + b_icon);
+    int32_t* d_lab = reinterpret_cast<int32_t*>(d + b_model + b_arm + b_icon + b_rows + b_k);
+    RMCV_CUDA(ctx, launch_icons(d_bgr, pitch, width, height, d_arm, n_armours, out_w, out_h, d + b_model + b_arm, d_rows, st, &ctx->kernel_launches));
+    RMCV_CUDA(ctx, launch_svm_predict(d_rows, n_armours, v.sv, model->sv_total, model->var_count, v.rho, v.df_ofs, v.df_alpha, v.df_index, v.labels,
+                                      model->class_count, reinterpret_cast<float*>(d + b_model + b_arm + b_icon + b_rows), d_lab, st,
+                                      &ctx->kernel_launches));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(h, d_arm, n * sizeof(rmcv_armour), cudaMemcpyDeviceToHost, st));
+    RMCV_CUDA(ctx, cudaMemcpyAsync(h + b_arm, d_lab, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RMCV_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(armours, h, n * sizeof(rmcv_armour));
+    memcpy(identities, h + b_arm, n * sizeof(int32_t));
+    return RMCV_OK;
+}
+
 // ---- f3: tracking ----------------------------------------------------------------------------------------------------
 }  // extern "C"
 struct rmcv_tracker {

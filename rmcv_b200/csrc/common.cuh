@@ -217,6 +217,12 @@ cudaError_t launch_frontend(const uint8_t* d_src, size_t pitch, size_t frame_str
                             size_t dframe_stride, int W, int H, int batch, int bits, int mirror, int flip, cudaStream_t st,
                             int64_t* launches);
 
+// f2: icon crops of the armours of one frame (icon.cu)
+cudaError_t launch_icons(const uint8_t* d_bgr, size_t pitch, int W, int H, rmcv_armour* d_armours, int n, int ow, int oh,
+                         uint8_t* d_icons, float* d_rows, cudaStream_t st, int64_t* launches);
+cudaError_t launch_svm_predict(const float* d_rows, int n, const float* d_sv, int sv_total, int var_count, const double* d_rho,
+                               const int32_t* d_df_ofs, const double* d_df_alpha, const int32_t* d_df_index, const int32_t* d_class_labels,
+                               int class_count, float* d_kbuf, int32_t* d_labels, cudaStream_t st, int64_t* launches);
 // f3: one iteration of the tracking loop (track.cu)
 cudaError_t launch_track_update(rmcv_track* d_tracks, int32_t* d_n_tracks, int cap, rmcv_track* d_backup, const rmcv_armour* d_armours,
                                 const double* d_positions, const int32_t* d_identities, int n, int32_t* d_remaining, long long timestamp,
