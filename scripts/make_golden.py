@@ -29,7 +29,8 @@ def record(case):
     p = dict(synth.MAIN_PARAMS)
     p["target"] = case["target"]
     fr = O.detect_frame(img, **p)
-    rec = dict(case=case, frame_crc32=zlib.crc32(img.tobytes()), mask_crc32=zlib.crc32(fr.binary.tobytes()),
+    rec = dict(case=case, camera=dict(matrix=O.MAIN_CAMMAT.tolist(), dist=O.MAIN_DISCOF.tolist(), exact_size=[27.0, 27.0]),
+               frame_crc32=zlib.crc32(img.tobytes()), mask_crc32=zlib.crc32(fr.binary.tobytes()),
                mask_foreground=int((fr.binary > 0).sum()), contours=[], positive=[], armours=[])
     for c, v in zip(fr.contours, fr.verdicts):
         e = v.ellipse
@@ -40,8 +41,20 @@ def record(case):
     for b in fr.positive:
         rec["positive"].append(dict(angle=b.angle, center=list(b.center), size=list(b.size), vertices=b.vertices.tolist()))
     for a in fr.armours:
+        rvec, tvec = O.solve_pnp(a.vertices)                                    # next row f1
+        icon, _ = O.affine_correction(img, a.icon)                              # next row f2
         rec["armours"].append(dict(i=a.i, j=a.j, icon=a.icon.tolist(), vertices=a.vertices.tolist(), bounding_box=list(a.bounding_box),
-                                   gates=list(a.gates)))
+                                   gates=list(a.gates), rvec=rvec.tolist(), tvec=tvec.tolist(),
+                                   icon20_crc32=zlib.crc32(np.ascontiguousarray(icon).tobytes())))
+    # next row f3: the frame's armours drifting by (2, 1) px per frame through the tracking loop, 6 frames at 125 Hz
+    tracking = []
+    for n in range(6):
+        obs = [O.TrackedArmour((a.bounding_box[0] + 2 * n, a.bounding_box[1] + n, a.bounding_box[2], a.bounding_box[3]),
+                               O.solve_pnp(a.vertices)[1] + n, k % 7, 1000 + 8_000_000 * n) for k, a in enumerate(fr.armours)]
+        tracking = O.tracking_step(tracking, obs, 1e9)
+    rec["tracking"] = [dict(lost_count=t.lost_count, timestamp=t.timestamp, history=sorted(t.identity_history.items()),
+                            state_post=t.observer.statePost.ravel().tolist(), cov_post_diag=np.diag(t.observer.errorCovPost).tolist())
+                       for t in tracking]
     # Bayer stand-in (config 2 front): mosaic -> cv2 bilinear -> pixel stage
     raw = synth.bgr_to_bayer(img, synth.BAYER_BG)
     bmask = O.extract_color_mask(O.bayer_to_bgr(raw, 4), case["target"], 80)

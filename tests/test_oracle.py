@@ -212,6 +212,20 @@ def test_golden_fixtures(path):
             assert np.allclose([e.cx, e.cy, e.w, e.h, e.angle], g["ellipse"], rtol=1e-6, atol=1e-4)
     for a, g in zip(fr.armours, rec["armours"]):
         assert (a.i, a.j) == (g["i"], g["j"]) and np.allclose(a.icon, g["icon"], atol=1e-3) and list(a.bounding_box) == g["bounding_box"]
+        rvec, tvec = O.solve_pnp(a.vertices)
+        assert np.allclose(rvec, g["rvec"], rtol=1e-9, atol=1e-9) and np.allclose(tvec, g["tvec"], rtol=1e-9, atol=1e-9)
+        assert zlib.crc32(np.ascontiguousarray(O.affine_correction(img, a.icon)[0]).tobytes()) == g["icon20_crc32"]
+    tracking = []
+    for n in range(6):
+        obs = [O.TrackedArmour((a.bounding_box[0] + 2 * n, a.bounding_box[1] + n, a.bounding_box[2], a.bounding_box[3]),
+                               O.solve_pnp(a.vertices)[1] + n, k % 7, 1000 + 8_000_000 * n) for k, a in enumerate(fr.armours)]
+        tracking = O.tracking_step(tracking, obs, 1e9)
+    assert len(tracking) == len(rec["tracking"])
+    for t, g in zip(tracking, rec["tracking"]):
+        assert t.lost_count == g["lost_count"] and t.timestamp == g["timestamp"]
+        assert sorted(t.identity_history.items()) == [tuple(x) for x in g["history"]]
+        assert np.allclose(t.observer.statePost.ravel(), g["state_post"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(np.diag(t.observer.errorCovPost), g["cov_post_diag"], rtol=1e-9, atol=1e-15)
     raw = synth.bgr_to_bayer(img, synth.BAYER_BG)
     assert zlib.crc32(O.extract_color_mask(O.bayer_to_bgr(raw, 4), case["target"], 80).tobytes()) == rec["bayer_bg_mask_crc32"]
 
