@@ -332,6 +332,26 @@ def run_gpu(args):
                                        "launches_per_timed_window": rep_b,
                                        "note": "average launch duration over back-to-back launches; 199 MB working set, partly L2-resident between repetitions"}
         d_raw.free(); d_mb.free(); ctxb.close()
+        # the whole path from raw Bayer frames at the size of config 3 (1024 x 1280x1024 mosaics, two calls in flight)
+        WF_, HF_, NF_ = 1280, 1024, 1024
+        rawf = np.stack([synth.bgr_to_bayer(pinned.array[i], synth.BAYER_BG) for i in range(64)] * (NF_ // 64))
+        ctxf = rb.Context(max_width=WF_, max_height=HF_, max_batch=NF_, device=dev_index)
+        d_rf = ctxf.device_buffer(rawf.nbytes); d_mf = ctxf.device_buffer(NF_ * HF_ * WF_)
+        d_rf.upload(rawf)
+        for _ in range(3):
+            ctxf.bayer_detect_batch(d_rf.ptr, WF_, HF_, NF_, synth.BAYER_BG, params, d_mf.ptr); fres = ctxf.fetch_results()
+        fsteps = 6
+        ctxf.timer_start()
+        ctxf.bayer_detect_batch(d_rf.ptr, WF_, HF_, NF_, synth.BAYER_BG, params, d_mf.ptr)
+        for _ in range(1, fsteps):
+            ctxf.bayer_detect_batch(d_rf.ptr, WF_, HF_, NF_, synth.BAYER_BG, params, d_mf.ptr); fres = ctxf.fetch_results()
+        fres = ctxf.fetch_results()
+        fms = ctxf.timer_stop() / fsteps
+        extras["bayer_full_detect"] = {"workload": "1024 x 1280x1024 raw BGGR frames: Bayer front + full detection, two calls in flight",
+                                       "ms_per_step": fms, "frames_per_s": NF_ / (fms * 1e-3), "blobs_per_frame": fres.total_blobs / NF_,
+                                       "full_path_frac_of_hbm_peak": NF_ * HF_ * WF_ * 2 / (fms * 1e-3) / 1e9 / peak,
+                                       "note": "2 B/px algorithmic (1 raw in, 1 mask out)"}
+        d_rf.free(); d_mf.free(); ctxf.close()
         # BASELINE config 4: 4096x3072 stress frames (250 plates -> ~500 light blobs, ~125k pairs per frame), batch 16
         WS_, HS_, NS_ = 4096, 3072, 16
         sframes = np.stack([synth.make_stress_frame(s, WS_, HS_, 250) for s in range(4)] * (NS_ // 4))

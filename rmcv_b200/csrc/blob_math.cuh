@@ -468,6 +468,28 @@ RMCV_HD bool pair_gates(const rmcv_lightblob& bi, const rmcv_lightblob& bj, cons
     return true;
 }
 
+// The verdict of pair_gates alone, cheap comparisons first: the double-precision atan2 behind the shear gate is only
+// evaluated for pairs that pass every other gate (the verdict is a conjunction of the same comparisons, so the order in
+// which they are tried does not change it).  The O(P^2) loops call this and build the gate values for the few survivors.
+RMCV_HD bool pair_passes(const rmcv_lightblob& bi, const rmcv_lightblob& bj, const rmcv_params& prm) {
+    if (bi.target != prm.target || bj.target != prm.target) return false;
+    if (fabsf(fsub(bi.angle, bj.angle)) > prm.angle_difference_max) return false;
+    const float hi = bi.size[1], hj = bj.size[1];
+    if (fdiv(fminf(hi, hj), fmaxf(hi, hj)) < prm.lenght_ratio_max) return false;
+    const float hsum = fadd(hi, hj);
+    const float y = fabsf(fsub(bi.center[1], bj.center[1]));
+    if (y > fdiv(hsum, 2.f)) return false;
+    const float x = fabsf(fsub(bi.center[0], bj.center[0]));
+    if (x > fmul(hsum, 2.f)) return false;
+    const float pif = 3.14159274101257324f;
+    const float rect_angle = (float)(atan2((double)y, (double)x) * 180.0 / (double)pif);
+    const float si = fabsf(bi.angle > 90.f ? fsub(fabsf(fsub(bi.angle, rect_angle)), 90.f)
+                                           : fsub(fabsf(fsub(fsub(180.f, bi.angle), rect_angle)), 90.f));
+    const float sj = fabsf(bj.angle > 90.f ? fsub(fabsf(fsub(bj.angle, rect_angle)), 90.f)
+                                           : fsub(fabsf(fsub(fsub(180.f, bj.angle), rect_angle)), 90.f));
+    return !(si > prm.shear_max || sj > prm.shear_max);
+}
+
 // ---------------------------------------------------------------------------------------------- integer contour sums
 // Everything cv::contourArea / cv::fitEllipseDirect need from a contour is a sum over its point multiset.  The kernels
 // accumulate them as EXACT integers (order-free, deterministic, atomics-friendly); the fit converts them to the centred

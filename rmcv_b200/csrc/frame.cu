@@ -166,7 +166,11 @@ __host__ __device__ inline size_t label_smem_bytes(int H, int Rs, int C) {
     return b + 64;
 }
 
-__global__ void __launch_bounds__(256, 4) label_kernel(const LabelParams p) {
+// NTMAX / MINB: 256 threads, four CTAs per SM for ordinary frames (the runs fit in shared memory); 1024 threads, one CTA per
+// SM for frames whose run arrays stay in global memory (4096x3072 stress frames), where the phases are bound by L2 latency
+// and more threads per frame mean more loads in flight.
+template <int NTMAX, int MINB>
+__global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int sh_scan[33];
     __shared__ int s_ncomp, s_nadj, s_flags, s_hb[4];
@@ -631,7 +635,10 @@ struct OrderParams {
     int frames;  // frames in this chunk (index of the allocator entry in sb.counters)
 };
 
-__global__ void __launch_bounds__(128) order_kernel(const OrderParams p) {
+// NTMAX: 128 threads for ordinary frames; 512 for frames with large capacities (stress frames: hundreds of blobs, ~125k
+// pairs, ~130 KB of records to post over PCIe per frame from a handful of CTAs).
+template <int NTMAX>
+__global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int sh_scan[33];
     __shared__ int s_np, s_nc, s_nn, s_flags, s_off[3];
@@ -680,31 +687,91 @@ __global__ void __launch_bounds__(128) order_kernel(const OrderParams p) {
     __syncthreads();
     // ---- pairs in lexicographic (i,j) order (src/objdetect.cpp:122-163)
     const int P = s_np;
+    const rmcv_lightblob* sblob = ob;            // ordinary frames: ~25 positives, read in place (L1/L2)
+    if (NTMAX > 128) {                           // large capacities: staged in shared memory for the O(P^2) loops
+        rmcv_lightblob* st = reinterpret_cast<rmcv_lightblob*>(s_status + C);
+        copy_words(st, ob, (size_t)P * sizeof(rmcv_lightblob), tid, NT);
+        sblob = st;
+        __syncthreads();
+    }
     const long long npairs = (long long)P * (P - 1) / 2;
     int base = 0;
-    for (long long k0 = 0; k0 < npairs; k0 += NT) {
-        const long long k = k0 + tid;
-        bool pass = false;
-        int i = 0, j = 0;
-        float gates[6];
-        if (k < npairs) {
-            pair_from_index(k, P, &i, &j);
-            pass = pair_gates(ob[i], ob[j], p.prm, gates);
+    if (npairs <= 8 * NT) {
+        // few pairs (an ordinary frame): one pair per thread and round, order-preserving block compaction
+        for (long long k0 = 0; k0 < npairs; k0 += NT) {
+            const long long k = k0 + tid;
+            bool pass = false;
+            int i = 0, j = 0;
+            float gates[6];
+            if (k < npairs) {
+                pair_from_index(k, P, &i, &j);
+                pass = pair_passes(sblob[i], sblob[j], p.prm);
+                if (pass) pair_gates(sblob[i], sblob[j], p.prm, gates);
+            }
+            int total;
+            const int pos = base + block_excl_scan(pass ? 1 : 0, &total, sh_scan);
+            if (pass) {
+                if (pos < A) {
+                    rmcv_armour a;
+                    make_armour(sblob[i], sblob[j], &a);
+                    a.i = i; a.j = j;
+                    for (int t = 0; t < 6; ++t) a.gates[t] = gates[t];
+                    oa[pos] = a;
+                } else {
+                    atomicOr(&s_flags, RMCV_FRAME_OVERFLOW_ARMOURS);
+                }
+            }
+            base += total;
         }
-        int total;
-        const int pos = base + block_excl_scan(pass ? 1 : 0, &total, sh_scan);
-        if (pass) {
-            if (pos < A) {
-                rmcv_armour a;
-                make_armour(ob[i], ob[j], &a);
-                a.i = i; a.j = j;
-                for (int t = 0; t < 6; ++t) a.gates[t] = gates[t];
-                oa[pos] = a;
-            } else {
-                atomicOr(&s_flags, RMCV_FRAME_OVERFLOW_ARMOURS);
+    } else {
+        // many pairs (stress frames, ~125k): no barrier inside the O(P^2) loop.  Rows i and P-2-i of the pair triangle go to
+        // the same thread (P-1 pairs per unit); pass 1 counts the pairs of a row that pass the gates, a scan of the counts
+        // gives every row its first output slot, pass 2 builds the armours there.
+        int* s_rowpos = s_keys;                  // the ordering keys are no longer needed
+        const int nrows = P - 1, nunits = (nrows + 1) / 2;
+        for (int u = tid; u < nunits; u += NT) {
+            for (int half = 0; half < 2; ++half) {
+                const int i = half == 0 ? u : nrows - 1 - u;
+                if (half == 1 && i == u) break;
+                const rmcv_lightblob bi = sblob[i];
+                int cnt = 0;
+                for (int j = i + 1; j < P; ++j) cnt += pair_passes(bi, sblob[j], p.prm) ? 1 : 0;
+                s_rowpos[i] = cnt;
             }
         }
-        base += total;
+        __syncthreads();
+        for (int r0 = 0; r0 < nrows; r0 += NT) {
+            const int r = r0 + tid;
+            const int v = r < nrows ? s_rowpos[r] : 0;
+            int total;
+            const int ex = block_excl_scan(v, &total, sh_scan);
+            if (r < nrows) s_rowpos[r] = base + ex;
+            base += total;
+        }
+        __syncthreads();
+        for (int u = tid; u < nunits; u += NT) {
+            for (int half = 0; half < 2; ++half) {
+                const int i = half == 0 ? u : nrows - 1 - u;
+                if (half == 1 && i == u) break;
+                const rmcv_lightblob bi = sblob[i];
+                float gates[6];
+                int pos = s_rowpos[i];
+                for (int j = i + 1; j < P; ++j) {
+                    if (!pair_passes(bi, sblob[j], p.prm)) continue;
+                    pair_gates(bi, sblob[j], p.prm, gates);
+                    if (pos < A) {
+                        rmcv_armour a;
+                        make_armour(bi, sblob[j], &a);
+                        a.i = i; a.j = j;
+                        for (int t = 0; t < 6; ++t) a.gates[t] = gates[t];
+                        oa[pos] = a;
+                    } else {
+                        atomicOr(&s_flags, RMCV_FRAME_OVERFLOW_ARMOURS);
+                    }
+                    ++pos;
+                }
+            }
+        }
     }
     const int n_arm = min(base, A);
     // ---- claim dense space in the chunk's region of the pinned result arrays, write out
@@ -761,9 +828,16 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
             const size_t m = (size_t)atoi(pad);
             if (m > smem && m <= (size_t)max_smem_optin) smem = m;
         }
-        e = cudaFuncSetAttribute(label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        label_kernel<<<L.frames, 256, smem, st>>>(p);
+        const bool big = L.g.R > 65535 && !getenv("RMCV_LABEL_SMALL");   // run indices beyond 16 bits: global-memory mode
+        if (big) {
+            e = cudaFuncSetAttribute(label_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            label_kernel<1024, 1><<<L.frames, 1024, smem, st>>>(p);
+        } else {
+            e = cudaFuncSetAttribute(label_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            label_kernel<256, 4><<<L.frames, 256, smem, st>>>(p);
+        }
         if (launches) ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         done(RMCV_STAGE_LABEL);
@@ -801,12 +875,15 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         p.g = L.g; p.sb = *L.sb; p.prm = prm; p.frame_base = L.frame_base;
         p.o_frames = L.o_frames; p.o_contours = L.o_contours; p.o_blobs = L.o_blobs; p.o_armours = L.o_armours;
         p.frames = L.frames;
-        const size_t smem = (size_t)2 * L.g.C * 4 + 16;
+        const bool big = L.g.R > 65535 || L.g.C > 512;
+        const size_t smem = (size_t)2 * L.g.C * 4 + 16 + (big ? (size_t)L.g.C * sizeof(rmcv_lightblob) : 0);   // keys, status (+ staged blobs)
         if (smem > 48 * 1024) {
-            e = cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = big ? cudaFuncSetAttribute(order_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                    : cudaFuncSetAttribute(order_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        order_kernel<<<L.frames, 128, smem, so>>>(p);
+        if (big) order_kernel<512><<<L.frames, 512, smem, so>>>(p);
+        else order_kernel<128><<<L.frames, 128, smem, so>>>(p);
         if (launches) ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (L.o_poses && L.camera) {   // f1 fused: rm::solve_PnP for every armour of the chunk

@@ -70,7 +70,15 @@ __device__ __forceinline__ void pair_from_index(long long k, int P, int* pi, int
 }
 
 __device__ __forceinline__ void copy_words(void* dst, const void* src, size_t bytes, int tid, int nt) {
-    const uint64_t* s = reinterpret_cast<const uint64_t*>(src);  // records are multiples of 8 bytes, 8-byte aligned
+    // records are multiples of 8 bytes, 8-byte aligned; 16-byte words when both ends allow (fewer, larger PCIe writes)
+    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | bytes) & 15) == 0) {
+        const uint4* s = reinterpret_cast<const uint4*>(src);
+        uint4* d = reinterpret_cast<uint4*>(dst);
+        const size_t n = bytes / 16;
+        for (size_t i = tid; i < n; i += nt) d[i] = s[i];
+        return;
+    }
+    const uint64_t* s = reinterpret_cast<const uint64_t*>(src);
     uint64_t* d = reinterpret_cast<uint64_t*>(dst);
     const size_t n = bytes / 8;
     for (size_t i = tid; i < n; i += nt) d[i] = s[i];
