@@ -805,6 +805,8 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
                           void (*stage_done)(void*, int, cudaStream_t), void* stage_arg) {
     cudaError_t e;
     auto done = [&](int stage) { if (stage_done) stage_done(stage_arg, stage, st); };
+    const char* esb = getenv("RMCV_SMALL_BATCH");
+    const int small_batch = esb ? atoi(esb) : 16;   // at most this many frames: per-frame kernels take their wide variants
     {   // K_E
         EmitLaunch el;
         el.bits = L.sb->bits; el.W = L.g.W; el.H = L.g.H; el.batch = L.frames;
@@ -828,7 +830,9 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
             const size_t m = (size_t)atoi(pad);
             if (m > smem && m <= (size_t)max_smem_optin) smem = m;
         }
-        const bool big = L.g.R > 65535 && !getenv("RMCV_LABEL_SMALL");   // run indices beyond 16 bits: global-memory mode
+        // 1024 threads: frames whose runs stay in global memory (run indices beyond 16 bits), and small batches, where a
+        // frame's latency matters and the SMs are idle anyway
+        const bool big = (L.g.R > 65535 || L.frames <= small_batch) && !getenv("RMCV_LABEL_SMALL");
         if (big) {
             e = cudaFuncSetAttribute(label_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
@@ -875,7 +879,7 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         p.g = L.g; p.sb = *L.sb; p.prm = prm; p.frame_base = L.frame_base;
         p.o_frames = L.o_frames; p.o_contours = L.o_contours; p.o_blobs = L.o_blobs; p.o_armours = L.o_armours;
         p.frames = L.frames;
-        const bool big = L.g.R > 65535 || L.g.C > 512;
+        const bool big = L.g.R > 65535 || L.g.C > 512 || L.frames <= small_batch;
         const size_t smem = (size_t)2 * L.g.C * 4 + 16 + (big ? (size_t)L.g.C * sizeof(rmcv_lightblob) : 0);   // keys, status (+ staged blobs)
         if (smem > 48 * 1024) {
             e = big ? cudaFuncSetAttribute(order_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
