@@ -100,7 +100,7 @@ int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
     RMCV_CUDA(ctx, dalloc(&sb.s_contours, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.s_blobs, CF * C));
     RMCV_CUDA(ctx, dalloc(&sb.s_armours, CF * A));
-    RMCV_CUDA(ctx, dalloc(&sb.arm_offset, CF));
+    RMCV_CUDA(ctx, dalloc(&sb.arm_offset, CF * 4));
     (void)first;
     RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.ev_pix, cudaEventDisableTiming));
     RMCV_CUDA(ctx, cudaEventCreateWithFlags(&sb.ev_lab, cudaEventDisableTiming));

@@ -475,12 +475,12 @@ RMCV_HD bool pair_passes(const rmcv_lightblob& bi, const rmcv_lightblob& bj, con
     if (bi.target != prm.target || bj.target != prm.target) return false;
     if (fabsf(fsub(bi.angle, bj.angle)) > prm.angle_difference_max) return false;
     const float hi = bi.size[1], hj = bj.size[1];
-    if (fdiv(fminf(hi, hj), fmaxf(hi, hj)) < prm.lenght_ratio_max) return false;
     const float hsum = fadd(hi, hj);
     const float y = fabsf(fsub(bi.center[1], bj.center[1]));
-    if (y > fdiv(hsum, 2.f)) return false;
+    if (y > fmul(hsum, 0.5f)) return false;                      // hsum / 2.f: halving is exact
     const float x = fabsf(fsub(bi.center[0], bj.center[0]));
     if (x > fmul(hsum, 2.f)) return false;
+    if (fdiv(fminf(hi, hj), fmaxf(hi, hj)) < prm.lenght_ratio_max) return false;
     const float pif = 3.14159274101257324f;
     const float rect_angle = (float)(atan2((double)y, (double)x) * 180.0 / (double)pif);
     const float si = fabsf(bi.angle > 90.f ? fsub(fabsf(fsub(bi.angle, rect_angle)), 90.f)

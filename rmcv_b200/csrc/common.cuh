@@ -82,7 +82,8 @@ struct SlotBuffers {
     rmcv_contour_info* s_contours; // [CF][C]
     rmcv_lightblob* s_blobs;       // [CF][C]
     rmcv_armour* s_armours;        // [CF][A]
-    int32_t* arm_offset;           // [CF]  dense offset of the frame's armours in the result arrays (for the pose kernel)
+    int32_t* arm_offset;           // [CF][4] dense offsets of the frame's armours, contours, blobs in the result arrays
+                                   //         (for the pose kernel and the grid-wide write-out of large frames)
     // staging for host-input calls
     uint8_t* frames;        // [CF][H][W*3] (allocated lazily)
     uint8_t* masks;         // [CF][H][W]   (allocated lazily)

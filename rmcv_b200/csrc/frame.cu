@@ -633,6 +633,7 @@ struct OrderParams {
     rmcv_lightblob* o_blobs;
     rmcv_armour* o_armours;
     int frames;  // frames in this chunk (index of the allocator entry in sb.counters)
+    int defer_copy;  // the records are posted by writeout_kernel (large frames: many CTAs per frame share the PCIe writes)
 };
 
 // NTMAX: 128 threads for ordinary frames; 512 for frames with large capacities (stress frames: hundreds of blobs, ~125k
@@ -724,19 +725,24 @@ __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
             base += total;
         }
     } else {
-        // many pairs (stress frames, ~125k): no barrier inside the O(P^2) loop.  Rows i and P-2-i of the pair triangle go to
-        // the same thread (P-1 pairs per unit); pass 1 counts the pairs of a row that pass the gates, a scan of the counts
-        // gives every row its first output slot, pass 2 builds the armours there.
+        // many pairs (stress frames, ~125k): no barrier inside the O(P^2) loop.  A warp takes rows i and P-2-i of the pair
+        // triangle together (P-1 pairs per unit) with its lanes over j; pass 1 counts the pairs of a row that pass the gates,
+        // a scan of the counts gives every row its first output slot, pass 2 records the passing pairs there in j order.
         int* s_rowpos = s_keys;                  // the ordering keys are no longer needed
         const int nrows = P - 1, nunits = (nrows + 1) / 2;
-        for (int u = tid; u < nunits; u += NT) {
+        const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+        for (int u = warp; u < nunits; u += nwarps) {
             for (int half = 0; half < 2; ++half) {
                 const int i = half == 0 ? u : nrows - 1 - u;
                 if (half == 1 && i == u) break;
                 const rmcv_lightblob bi = sblob[i];
                 int cnt = 0;
-                for (int j = i + 1; j < P; ++j) cnt += pair_passes(bi, sblob[j], p.prm) ? 1 : 0;
-                s_rowpos[i] = cnt;
+                for (int j0 = i + 1; j0 < P; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool pass = j < P && pair_passes(bi, sblob[j], p.prm);
+                    cnt += __popc(__ballot_sync(0xffffffffu, pass));
+                }
+                if (lane == 0) s_rowpos[i] = cnt;
             }
         }
         __syncthreads();
@@ -749,28 +755,37 @@ __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
             base += total;
         }
         __syncthreads();
-        for (int u = tid; u < nunits; u += NT) {
+        for (int u = warp; u < nunits; u += nwarps) {
             for (int half = 0; half < 2; ++half) {
                 const int i = half == 0 ? u : nrows - 1 - u;
                 if (half == 1 && i == u) break;
                 const rmcv_lightblob bi = sblob[i];
-                float gates[6];
                 int pos = s_rowpos[i];
-                for (int j = i + 1; j < P; ++j) {
-                    if (!pair_passes(bi, sblob[j], p.prm)) continue;
-                    pair_gates(bi, sblob[j], p.prm, gates);
-                    if (pos < A) {
-                        rmcv_armour a;
-                        make_armour(bi, sblob[j], &a);
-                        a.i = i; a.j = j;
-                        for (int t = 0; t < 6; ++t) a.gates[t] = gates[t];
-                        oa[pos] = a;
-                    } else {
-                        atomicOr(&s_flags, RMCV_FRAME_OVERFLOW_ARMOURS);
+                for (int j0 = i + 1; j0 < P; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool pass = j < P && pair_passes(bi, sblob[j], p.prm);
+                    const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+                    if (pass) {
+                        const int my = pos + __popc(bal & ((1u << lane) - 1u));
+                        if (my < A) { oa[my].i = i; oa[my].j = j; }   // the pair; the armour is built below by all threads
+                        else atomicOr(&s_flags, RMCV_FRAME_OVERFLOW_ARMOURS);
                     }
-                    ++pos;
+                    pos += __popc(bal);
                 }
             }
+        }
+        __syncthreads();
+        // the armours themselves (double-precision trigonometry): one per thread and round, no divergence
+        const int n_pass = min(base, A);
+        for (int k = tid; k < n_pass; k += NT) {
+            const int i = oa[k].i, j = oa[k].j;
+            float gates[6];
+            pair_gates(sblob[i], sblob[j], p.prm, gates);
+            rmcv_armour a;
+            make_armour(sblob[i], sblob[j], &a);
+            a.i = i; a.j = j;
+            for (int t = 0; t < 6; ++t) a.gates[t] = gates[t];
+            oa[k] = a;
         }
     }
     const int n_arm = min(base, A);
@@ -793,11 +808,35 @@ __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
         fi.contour_offset = (int32_t)base_c; fi.blob_offset = (int32_t)base_b; fi.armour_offset = (int32_t)base_a;
         fi.flags = s_flags;
         p.o_frames[p.frame_base + frame] = fi;
-        sb.arm_offset[frame] = (int32_t)base_a;
+        sb.arm_offset[4 * frame] = (int32_t)base_a;
+        sb.arm_offset[4 * frame + 1] = (int32_t)base_c;
+        sb.arm_offset[4 * frame + 2] = (int32_t)base_b;
     }
+    if (p.defer_copy) return;
     copy_words(p.o_contours + base_c, oc, (size_t)s_nc * sizeof(rmcv_contour_info), tid, NT);
     copy_words(p.o_blobs + base_b, ob, (size_t)P * sizeof(rmcv_lightblob), tid, NT);
     copy_words(p.o_armours + base_a, oa, (size_t)n_arm * sizeof(rmcv_armour), tid, NT);
+}
+
+// Dense write-out of a large frame's records into the pinned result arrays, kWriteSplit CTAs per frame: with a handful of
+// frames per chunk the single order CTA of a frame would be the only one posting its ~130 KB over PCIe.
+constexpr int kWriteSplit = 16;
+__global__ void __launch_bounds__(256) writeout_kernel(const OrderParams p) {
+    const int frame = blockIdx.y, part = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+    const SlotBuffers& sb = p.sb;
+    const FrameCounters& fc = sb.counters[frame];
+    const int C = p.g.C, A = p.g.A;
+    auto slice = [&](uint8_t* dst, const uint8_t* src, size_t records, size_t rec_bytes) {
+        const size_t per = (records + kWriteSplit - 1) / kWriteSplit;
+        const size_t r0 = (size_t)part * per, r1 = r0 + per < records ? r0 + per : records;
+        if (r0 < r1) copy_words(dst + r0 * rec_bytes, src + r0 * rec_bytes, (r1 - r0) * rec_bytes, tid, NT);
+    };
+    slice(reinterpret_cast<uint8_t*>(p.o_armours + sb.arm_offset[4 * frame]), reinterpret_cast<const uint8_t*>(sb.s_armours + (size_t)frame * A),
+          (size_t)fc.n_armours, sizeof(rmcv_armour));
+    slice(reinterpret_cast<uint8_t*>(p.o_contours + sb.arm_offset[4 * frame + 1]), reinterpret_cast<const uint8_t*>(sb.s_contours + (size_t)frame * C),
+          (size_t)fc.n_contours, sizeof(rmcv_contour_info));
+    slice(reinterpret_cast<uint8_t*>(p.o_blobs + sb.arm_offset[4 * frame + 2]), reinterpret_cast<const uint8_t*>(sb.s_blobs + (size_t)frame * C),
+          (size_t)fc.n_positive, sizeof(rmcv_lightblob));
 }
 
 // Enqueues the labelling stages of one chunk.  stage_done(i) is called after each kernel (profiling events).
@@ -886,8 +925,14 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
                     : cudaFuncSetAttribute(order_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
+        p.defer_copy = (L.g.R > 65535 || L.g.C > 512) ? 1 : 0;
         if (big) order_kernel<512><<<L.frames, 512, smem, so>>>(p);
         else order_kernel<128><<<L.frames, 128, smem, so>>>(p);
+        if (p.defer_copy) {
+            if (launches) ++*launches;
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            writeout_kernel<<<dim3(kWriteSplit, L.frames), 256, 0, so>>>(p);
+        }
         if (launches) ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (L.o_poses && L.camera) {   // f1 fused: rm::solve_PnP for every armour of the chunk

@@ -45,7 +45,7 @@ struct ChunkPoseParams {
 __global__ void __launch_bounds__(64) chunk_pose_kernel(const ChunkPoseParams p) {
     const int frame = blockIdx.x;
     const int n = p.counters[frame].n_armours;
-    const size_t base = (size_t)p.arm_offset[frame];
+    const size_t base = (size_t)p.arm_offset[4 * frame];
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
         const rmcv_armour& a = p.armours[(size_t)frame * p.A + k];
         float pts[4][2];
