@@ -20,7 +20,8 @@ __global__ void __launch_bounds__(256) filter_armours_kernel(const rmcv_lightblo
         float gates[6];
         if (k < npairs) {
             pair_from_index(k, P, &i, &j);
-            pass = pair_gates(blobs[i], blobs[j], prm, gates);
+            pass = pair_passes(blobs[i], blobs[j], prm);       // cheap gates first; the gate values only for survivors
+            if (pass) pair_gates(blobs[i], blobs[j], prm, gates);
         }
         int total;
         const int pos = base + block_excl_scan(pass ? 1 : 0, &total, sh_scan);
