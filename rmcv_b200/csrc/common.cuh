@@ -153,8 +153,8 @@ struct PixelLaunch {
 cudaError_t launch_pixel_stage(const PixelLaunch& p, int sm_count, cudaStream_t st, int64_t* launches);
 // Bayer fast path (bayer_strip.cu); cudaErrorNotSupported when the call does not qualify for it
 cudaError_t launch_bayer_strip(const PixelLaunch& p, int sm_count, cudaStream_t st, int64_t* launches);
-// BGR fast path (bgr_strip.cu), same convention
-cudaError_t launch_bgr_strip(const PixelLaunch& p, int sm_count, cudaStream_t st, int64_t* launches);
+// BGR alternative: TMA-fed bands consumed by register-resident lanes (bgr_bandstrip.cu, RMCV_BGR_STRIP=1), same convention
+cudaError_t launch_bgr_bandstrip(const PixelLaunch& p, int sm_count, cudaStream_t st, int64_t* launches);
 
 struct CameraSetup { double K[9], dist[5], M[16]; int has_M; float w, h; };
 

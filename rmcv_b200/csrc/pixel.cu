@@ -516,11 +516,12 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
 
     if (L.bayer_layout == 0) {
-        // ---- BGR.  The register-resident strip kernel (bgr_strip.cu) needs 2.5x fewer instructions per pixel but, with its
-        // many small copies in flight, it lengthens the memory latency the labelling kernels beside it see: the whole path
-        // is faster with the band kernel below.  RMCV_BGR_STRIP=1 selects the strip kernel.
+        // ---- BGR.  The band-strip kernel (bgr_bandstrip.cu: TMA-fed bands consumed by register-resident lanes) needs half the
+        // instructions per pixel, but as it draws more bandwidth per unit of time in the pipeline it lengthens the memory
+        // latency the labelling kernels beside it see, and the whole path is faster with the band kernel below
+        // (DESIGN.md 4.3).  RMCV_BGR_STRIP=1 selects the band-strip kernel.
         if (env_int("RMCV_BGR_STRIP", 0) != 0) {
-            const cudaError_t se = launch_bgr_strip(L, sm_count, st, launches);
+            const cudaError_t se = launch_bgr_bandstrip(L, sm_count, st, launches);
             if (se != cudaErrorNotSupported) return se;
         }
         int a, b;  // plus / minus channel (src/imgproc.cpp:56-65)

@@ -1,4 +1,4 @@
-// Building blocks of the register-resident pixel kernels (bgr_strip.cu; bayer_strip.cu follows the same scheme):
+// Building blocks of the register-resident pixel kernels (bayer_strip.cu, bgr_bandstrip.cu):
 // a lane owns 16 pixels of a row, walks down a segment of rows, receives the threshold words of its two neighbours by warp
 // shuffle and runs the 3x3 close of rm::extract_color (src/imgproc.cpp:67-69, OpenCV MORPH_CLOSE borders: dilate pads 0,
 // erode pads 1) on a 20-bit window in registers.
@@ -11,10 +11,6 @@ namespace strip {
 // ---- cp.async (LDGSTS) ring helpers: a lane only reads back bytes it asked for itself, so groups need no barrier
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
-}
-// same through L1: the three 16-byte pieces of a lane's 48 bytes share 32-byte sectors with its neighbours' pieces
-__device__ __forceinline__ void cp_async16_ca(uint32_t saddr, const void* g) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -29,6 +25,33 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
     return v;
 }
+// ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk, UBLKCP in SASS): bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 __device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) { return (a & m) | (b & ~m); }
 
 // ---- bits -> bytes table: 256 entries of 8 bytes (0x00 / 0xFF per mask bit) on a 2 KB boundary of the shared window, so
@@ -36,8 +59,8 @@ __device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) {
 __device__ __forceinline__ uint32_t lut_base(const void* raw) {
     return ((uint32_t)__cvta_generic_to_shared(raw) + 2047u) & ~2047u;
 }
-__device__ __forceinline__ void lut_init(const void* raw, uint32_t tid) {
-    if (tid < 256u) {
+__device__ __forceinline__ void lut_init(const void* raw, uint32_t tid0) {
+    for (uint32_t tid = tid0; tid < 256u; tid += blockDim.x) {
         auto expand4 = [](uint32_t nib) {   // 4 bits -> 4 bytes: bits to the byte MSBs, PRMT sign-replicate
             uint32_t r;
             asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(nib * 0x10204080u));

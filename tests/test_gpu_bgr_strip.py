@@ -1,5 +1,5 @@
-"""Row a1, alternative pixel kernel (opt-in, RMCV_BGR_STRIP=1): the register-resident BGR strip kernel
-(rmcv_b200/csrc/bgr_strip.cu) against the oracle's restatement
+"""Row a1, alternative pixel kernel (opt-in, RMCV_BGR_STRIP=1): the TMA-fed, register-resident BGR band-strip kernel
+(rmcv_b200/csrc/bgr_bandstrip.cu) against the oracle's restatement
 of rm::extract_color's mask (src/imgproc.cpp:52-69: split, saturating difference, inRange, 3x3 MORPH_CLOSE) and against
 the shared-memory band kernel.  Bit-exact on the byte mask and on the bit mask the labelling stages read."""
 import os
@@ -12,6 +12,7 @@ from rmcv_b200 import synth
 from oracle import rm_oracle as O
 
 pytestmark = pytest.mark.gpu
+VARIANT = "1"
 
 
 @pytest.fixture(scope="module")
@@ -26,9 +27,9 @@ def run(ctx, frames, target, lb, pitch=None, band=False, env=None):
     buf = np.zeros((B, H, pitch), np.uint8)
     buf[:, :, :W * 3] = frames.reshape(B, H, W * 3)
     d_in = ctx.device_buffer(buf.nbytes); d_out = ctx.device_buffer(B * H * W)
-    saved = {k: os.environ.get(k) for k in ("RMCV_BGR_STRIP", "RMCV_STRIP_SEG")}
+    saved = {k: os.environ.get(k) for k in ("RMCV_BGR_STRIP", "RMCV_BANDSTRIP_RC")}
     if not band:
-        os.environ["RMCV_BGR_STRIP"] = "1"
+        os.environ["RMCV_BGR_STRIP"] = VARIANT
     for k, v in (env or {}).items():
         os.environ[k] = v
     try:
@@ -60,7 +61,8 @@ def check(ctx, frames, target, lb, pitch=None, what="", env=None):
 @pytest.mark.parametrize("shape", [(1, 32), (2, 48), (3, 32), (5, 480), (37, 496), (64, 1296), (130, 976), (200, 2048), (21, 1280)])
 def test_random_frames(ctx, shape):
     """Uniform random bytes; widths of exactly one warp strip (480), one group more (496), W % 32 == 16 (1296, 976), two
-    groups (32); heights of 1..5 rows and heights that cut segments; all three targets."""
+    groups (32); heights of 1..5 rows and heights that cut bands; batches that do not fill a CTA's frame group; all three
+    targets."""
     H, W = shape
     rng = np.random.default_rng(H * 131 + W * 7)
     frames = rng.integers(0, 256, (3, H, W, 3), dtype=np.uint8)
@@ -68,12 +70,13 @@ def test_random_frames(ctx, shape):
         check(ctx, frames, target, lb, what="random")
 
 
-def test_segment_heights(ctx):
-    """Every segment height cuts the frame differently (last segment partial, one-row segments, whole frame)."""
+def test_rows_per_stage_and_band_edges(ctx):
+    """Every ring-stage height (rows per TMA chunk) cuts the 32-row bands differently; heights around the band size."""
     rng = np.random.default_rng(5)
-    frames = rng.integers(0, 256, (2, 50, 160, 3), dtype=np.uint8)
-    for seg in (1, 2, 3, 7, 16, 49, 50, 64):
-        check(ctx, frames, rb.CAMP_BLUE, 60, what=f"seg {seg}", env={"RMCV_STRIP_SEG": str(seg)})
+    for H in (31, 32, 33, 63, 65):
+        frames = rng.integers(0, 256, (4, H, 160, 3), dtype=np.uint8)
+        for rc in (1, 2, 3, 5):
+            check(ctx, frames, rb.CAMP_BLUE, 60, what=f"H {H} rc {rc}", env={"RMCV_BANDSTRIP_RC": str(rc)})
 
 
 def test_degenerate_bounds_and_extremes(ctx):
