@@ -1,5 +1,5 @@
 // C ABI of rmcv_b200 (include/rmcv_b200.h): context, memory helpers, the batched entry points and the
-// chunked two-slot pipeline that overlaps copies and kernels.  No CPU fallback: every compute entry point
+// chunked multi-slot pipeline that overlaps copies and kernels.  No CPU fallback: every compute entry point
 // launches the CUDA kernels in pixel.cu / ccl.cu / blob.cu / armour.cu or fails with an error code.
 #include <math.h>
 #include <stdlib.h>
@@ -44,11 +44,14 @@ struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
     void* tmp_host = nullptr; size_t tmp_host_bytes = 0;
     int last_nchunks = 0;
     int last_kind = 0;  // 0 none, 1 extract, 2 detect
-    cudaEvent_t t_start[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, t_stop[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t t_start[4 + kSlots] = {}, t_stop[4 + kSlots] = {};
     // Streams of the ctx.  The pixel kernels of consecutive chunks run back to back on `pix`; the labelling kernels of
     // chunk i run on the high-priority stream `lab` behind an event, so that they overlap the pixel kernel of chunk
     // i+1; host<->device staging copies have their own streams (both copy engines stay busy).
-    cudaStream_t pix = nullptr, lab = nullptr, lab2 = nullptr, out = nullptr, h2d = nullptr, d2h = nullptr;   // lab2: slot 1
+    cudaStream_t pix = nullptr, lab = nullptr, out = nullptr, h2d = nullptr, d2h = nullptr;
+    cudaStream_t labs[kSlots] = {};   // labelling stream of each slot (labs[0] == lab)
+    long long chunk_counter = 0;      // chunks enqueued over the life of the ctx
+    int last_first_slot = 0;          // slot of chunk 0 of the last call
     bool own_pix = false;
     CameraSetup camera;      // f1 fused: pose of every armour behind the write-out kernel
     bool have_camera = false;
@@ -175,7 +178,7 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
     CtxExtra* ex = extra(ctx);
     // each slot has its own labelling stream: the labelling kernels of consecutive chunks are latency-bound and overlap
     // each other as well as the pixel kernels
-    cudaStream_t sp = ex->pix, sl = (&sb == &ctx->slot[1]) ? ex->lab2 : ex->lab;
+    cudaStream_t sp = ex->pix, sl = ex->labs[&sb - ctx->slot];
     // the slot's scratch is free once the labelling stages (and the mask download) of its previous chunk are done
     RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, sb.ev_lab, 0));
     RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, sb.ev_d2h, 0));
@@ -244,8 +247,9 @@ int run_device_batch(rmcv_ctx* ctx, const uint8_t* d_src, size_t pitch, size_t f
     if (full) begin_call(ctx);
     const int CF = ctx->CF;
     int nchunks = 0;
+    extra(ctx)->last_first_slot = (int)(extra(ctx)->chunk_counter % kSlots);
     for (int f0 = 0; f0 < batch; f0 += CF, ++nchunks) {
-        SlotBuffers& sb = ctx->slot[nchunks & 1];
+        SlotBuffers& sb = ctx->slot[extra(ctx)->chunk_counter++ % kSlots];
         const int frames = batch - f0 < CF ? batch - f0 : CF;
         rc = enqueue_chunk(ctx, sb, d_src + (size_t)f0 * frame_stride, pitch, frame_stride, W, H, frames, f0, bayer_layout,
                            prm, d_mask ? d_mask + (size_t)f0 * mask_frame_stride : nullptr, mask_pitch, mask_frame_stride, full);
@@ -264,8 +268,7 @@ int sync_all(rmcv_ctx* ctx) {
     CtxExtra* ex = extra(ctx);
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->h2d));
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->pix));
-    RMCV_CUDA(ctx, cudaStreamSynchronize(ex->lab));
-    RMCV_CUDA(ctx, cudaStreamSynchronize(ex->lab2));
+    for (int i = 0; i < kSlots; ++i) RMCV_CUDA(ctx, cudaStreamSynchronize(ex->labs[i]));
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->out));
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->d2h));
     prof_collect(ctx);
@@ -312,9 +315,9 @@ int fetch_oldest(rmcv_ctx* ctx, rmcv_results* out) {
 SlotBuffers* resident_slot(rmcv_ctx* ctx, int frame, int* local) {
     if (frame < 0 || frame >= ctx->last_batch) return nullptr;
     const int chunk = frame / ctx->CF;
-    if (chunk + 2 < extra(ctx)->last_nchunks) return nullptr;
+    if (chunk + kSlots < extra(ctx)->last_nchunks) return nullptr;
     *local = frame - chunk * ctx->CF;
-    return &ctx->slot[chunk & 1];
+    return &ctx->slot[(extra(ctx)->last_first_slot + chunk) % kSlots];
 }
 
 }  // namespace
@@ -415,20 +418,25 @@ int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
         cudaError_t se = cudaSuccess;
         if (cfg->stream) { ex->pix = reinterpret_cast<cudaStream_t>(cfg->stream); ex->own_pix = false; }
         else { se = cudaStreamCreateWithPriority(&ex->pix, cudaStreamNonBlocking, least); ex->own_pix = true; }
-        if (getenv("RMCV_SERIAL")) { ex->lab = ex->pix; ex->lab2 = ex->pix; ex->out = ex->pix; }   // debug aid: every kernel on one stream
-        else {
+        if (getenv("RMCV_SERIAL")) {   // debug aid: every kernel on one stream
+            ex->lab = ex->pix; ex->out = ex->pix;
+            for (int i = 0; i < kSlots; ++i) ex->labs[i] = ex->pix;
+        } else {
             if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&ex->lab, cudaStreamNonBlocking, greatest);
-            const char* e1 = getenv("RMCV_LAB_STREAMS");
-            if (e1 && atoi(e1) == 1) ex->lab2 = ex->lab;
-            else if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&ex->lab2, cudaStreamNonBlocking, greatest);
+            ex->labs[0] = ex->lab;
+            const char* e1 = getenv("RMCV_LAB_STREAMS");   // 1: all slots share one labelling stream (experiments)
+            for (int i = 1; i < kSlots; ++i) {
+                if (e1 && atoi(e1) == 1) ex->labs[i] = ex->lab;
+                else if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&ex->labs[i], cudaStreamNonBlocking, greatest);
+            }
             if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&ex->out, cudaStreamNonBlocking, greatest);
         }
         if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&ex->h2d, cudaStreamNonBlocking);
         if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&ex->d2h, cudaStreamNonBlocking);
         if (se != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "stream creation failed: %s", cudaGetErrorString(se)); return fail(RMCV_ERR_CUDA); }
     }
-    int rc = alloc_slot(ctx, ctx->slot[0], true);
-    if (rc == RMCV_OK) rc = alloc_slot(ctx, ctx->slot[1], false);
+    int rc = RMCV_OK;
+    for (int i = 0; i < kSlots && rc == RMCV_OK; ++i) rc = alloc_slot(ctx, ctx->slot[i], i == 0);
     if (rc != RMCV_OK) return fail(rc);
     const size_t B = cfg->max_batch;
     const unsigned hflags = cudaHostAllocMapped | cudaHostAllocPortable;
@@ -458,8 +466,7 @@ int rmcv_ctx_destroy(rmcv_ctx* ctx) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    free_slot(ctx->slot[0]);
-    free_slot(ctx->slot[1]);
+    for (int i = 0; i < kSlots; ++i) free_slot(ctx->slot[i]);
     CtxExtra* ex = extra(ctx);
     if (ex) {
         for (int i = 0; i < 2; ++i) {
@@ -475,8 +482,8 @@ int rmcv_ctx_destroy(rmcv_ctx* ctx) {
             for (int i = 0; i < 2; ++i) cudaEventDestroy(ps.pix[i]);
             for (int i = 0; i < RMCV_STAGE_COUNT; ++i) cudaEventDestroy(ps.lab[i]);
         }
-        for (int i = 0; i < 6; ++i) { if (ex->t_start[i]) cudaEventDestroy(ex->t_start[i]); if (ex->t_stop[i]) cudaEventDestroy(ex->t_stop[i]); }
-        if (ex->lab2 && ex->lab2 != ex->pix && ex->lab2 != ex->lab) cudaStreamDestroy(ex->lab2);
+        for (int i = 0; i < 4 + kSlots; ++i) { if (ex->t_start[i]) cudaEventDestroy(ex->t_start[i]); if (ex->t_stop[i]) cudaEventDestroy(ex->t_stop[i]); }
+        for (int i = 1; i < kSlots; ++i) if (ex->labs[i] && ex->labs[i] != ex->pix && ex->labs[i] != ex->lab) cudaStreamDestroy(ex->labs[i]);
         if (ex->lab && ex->lab != ex->pix) cudaStreamDestroy(ex->lab);
         if (ex->out && ex->out != ex->pix) cudaStreamDestroy(ex->out);
         if (ex->pix && ex->own_pix) cudaStreamDestroy(ex->pix);
@@ -599,8 +606,9 @@ int rmcv_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, si
     const int CF = ctx->CF;
     const size_t dev_frame = (size_t)height * rowbytes, dev_mask = (size_t)height * width;
     int nchunks = 0;
+    extra(ctx)->last_first_slot = (int)(extra(ctx)->chunk_counter % kSlots);
     for (int f0 = 0; f0 < batch; f0 += CF, ++nchunks) {
-        SlotBuffers& sb = ctx->slot[nchunks & 1];
+        SlotBuffers& sb = ctx->slot[extra(ctx)->chunk_counter++ % kSlots];
         const int frames = batch - f0 < CF ? batch - f0 : CF;
         const size_t need = (size_t)CF * (size_t)ctx->cfg.max_height * ctx->cfg.max_width * 3;
         if (sb.frames_bytes < need) {
@@ -1296,8 +1304,9 @@ int rmcv_timer_start(rmcv_ctx* ctx) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
     CtxExtra* ex = extra(ctx);
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st[6] = {ex->pix, ex->lab, ex->out, ex->h2d, ex->d2h, ex->lab2};
-    for (int i = 0; i < 6; ++i) {
+    cudaStream_t st[4 + kSlots] = {ex->pix, ex->out, ex->h2d, ex->d2h};
+    for (int i = 0; i < kSlots; ++i) st[4 + i] = ex->labs[i];
+    for (int i = 0; i < 4 + kSlots; ++i) {
         if (!ex->t_start[i]) { RMCV_CUDA(ctx, cudaEventCreate(&ex->t_start[i])); RMCV_CUDA(ctx, cudaEventCreate(&ex->t_stop[i])); }
         RMCV_CUDA(ctx, cudaEventRecord(ex->t_start[i], st[i]));
     }
@@ -1308,13 +1317,14 @@ int rmcv_timer_stop(rmcv_ctx* ctx, double* ms) {
     if (!ctx || !ms) return RMCV_ERR_INVALID_ARG;
     CtxExtra* ex = extra(ctx);
     if (!ex->t_start[0]) return set_err(ctx, RMCV_ERR_STATE, "rmcv_timer_stop without rmcv_timer_start");
-    cudaStream_t st[6] = {ex->pix, ex->lab, ex->out, ex->h2d, ex->d2h, ex->lab2};
-    for (int i = 0; i < 6; ++i) RMCV_CUDA(ctx, cudaEventRecord(ex->t_stop[i], st[i]));
+    cudaStream_t st[4 + kSlots] = {ex->pix, ex->out, ex->h2d, ex->d2h};
+    for (int i = 0; i < kSlots; ++i) st[4 + i] = ex->labs[i];
+    for (int i = 0; i < 4 + kSlots; ++i) RMCV_CUDA(ctx, cudaEventRecord(ex->t_stop[i], st[i]));
     int rc = sync_all(ctx);
     if (rc != RMCV_OK) return rc;
     float best = 0.f;
-    for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) {
+    for (int i = 0; i < 4 + kSlots; ++i)
+        for (int j = 0; j < 4 + kSlots; ++j) {
             float t = 0.f;
             RMCV_CUDA(ctx, cudaEventElapsedTime(&t, ex->t_start[i], ex->t_stop[j]));
             if (t > best) best = t;

@@ -58,6 +58,10 @@ struct Geometry {           // frame geometry + derived sizes, shared by all ker
     int SC;                 // entries per frame of the global bucket array (>= R+2 and >= PC)
 };
 
+// Scratch slots of a ctx: chunk n (counted over the life of the ctx) uses slot n % kSlots, so up to kSlots chunks are in
+// flight between the start of their pixel kernel and the end of their write-out.
+constexpr int kSlots = 3;
+
 struct SlotBuffers {
     // pixel stage outputs
     uint32_t* bits;         // [CF][H][WB]   final mask, bit-packed
@@ -88,7 +92,7 @@ struct SlotBuffers {
     uint8_t* frames;        // [CF][H][W*3] (allocated lazily)
     uint8_t* masks;         // [CF][H][W]   (allocated lazily)
     size_t frames_bytes, masks_bytes;
-    // chunk i of a call uses slot i&1; the events order the ctx streams (api.cu) around the slot's scratch
+    // the events order the ctx streams (api.cu) around the slot's scratch
     cudaEvent_t ev_pix;     // pixel kernel done  (bits written; staging frames read)
     cudaEvent_t ev_fit;     // fit kernel done (the order kernel runs on its own stream behind it)
     cudaEvent_t ev_lab;     // labelling stages done (scratch free again)
@@ -105,7 +109,7 @@ struct rmcv_ctx {
     int max_smem_optin;
     int CF;                 // chunk frames
     rmcv::Geometry cap;     // capacities at max_width x max_height
-    rmcv::SlotBuffers slot[2];
+    rmcv::SlotBuffers slot[rmcv::kSlots];
     // pinned, device-mapped result arrays of the most recent detect call (one of the two sets kept in api.cu)
     rmcv_frame_info* h_frames;      // [max_batch]
     rmcv_contour_info* h_contours;  // [max_batch][C]  (chunk-dense)
