@@ -247,9 +247,9 @@ int run_device_batch(rmcv_ctx* ctx, const uint8_t* d_src, size_t pitch, size_t f
     if (full) begin_call(ctx);
     const int CF = ctx->CF;
     int nchunks = 0;
-    extra(ctx)->last_first_slot = (int)(extra(ctx)->chunk_counter % kSlots);
+    extra(ctx)->last_first_slot = (int)(extra(ctx)->chunk_counter % ctx->n_slots);
     for (int f0 = 0; f0 < batch; f0 += CF, ++nchunks) {
-        SlotBuffers& sb = ctx->slot[extra(ctx)->chunk_counter++ % kSlots];
+        SlotBuffers& sb = ctx->slot[extra(ctx)->chunk_counter++ % ctx->n_slots];
         const int frames = batch - f0 < CF ? batch - f0 : CF;
         rc = enqueue_chunk(ctx, sb, d_src + (size_t)f0 * frame_stride, pitch, frame_stride, W, H, frames, f0, bayer_layout,
                            prm, d_mask ? d_mask + (size_t)f0 * mask_frame_stride : nullptr, mask_pitch, mask_frame_stride, full);
@@ -315,9 +315,9 @@ int fetch_oldest(rmcv_ctx* ctx, rmcv_results* out) {
 SlotBuffers* resident_slot(rmcv_ctx* ctx, int frame, int* local) {
     if (frame < 0 || frame >= ctx->last_batch) return nullptr;
     const int chunk = frame / ctx->CF;
-    if (chunk + kSlots < extra(ctx)->last_nchunks) return nullptr;
+    if (chunk + ctx->n_slots < extra(ctx)->last_nchunks) return nullptr;
     *local = frame - chunk * ctx->CF;
-    return &ctx->slot[(extra(ctx)->last_first_slot + chunk) % kSlots];
+    return &ctx->slot[(extra(ctx)->last_first_slot + chunk) % ctx->n_slots];
 }
 
 }  // namespace
@@ -408,6 +408,11 @@ int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
     if (CF > cfg->max_batch) CF = cfg->max_batch;
     ctx->CF = CF;
     {
+        const char* es = getenv("RMCV_SLOTS");
+        int ns = es ? atoi(es) : 3;
+        ctx->n_slots = ns < 2 ? 2 : (ns > kSlots ? kSlots : ns);
+    }
+    {
         CtxExtra* ex = extra(ctx);
         int least = 0, greatest = 0;
         cudaDeviceGetStreamPriorityRange(&least, &greatest);
@@ -436,7 +441,7 @@ int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
         if (se != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "stream creation failed: %s", cudaGetErrorString(se)); return fail(RMCV_ERR_CUDA); }
     }
     int rc = RMCV_OK;
-    for (int i = 0; i < kSlots && rc == RMCV_OK; ++i) rc = alloc_slot(ctx, ctx->slot[i], i == 0);
+    for (int i = 0; i < ctx->n_slots && rc == RMCV_OK; ++i) rc = alloc_slot(ctx, ctx->slot[i], i == 0);
     if (rc != RMCV_OK) return fail(rc);
     const size_t B = cfg->max_batch;
     const unsigned hflags = cudaHostAllocMapped | cudaHostAllocPortable;
@@ -466,7 +471,7 @@ int rmcv_ctx_destroy(rmcv_ctx* ctx) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < kSlots; ++i) free_slot(ctx->slot[i]);
+    for (int i = 0; i < ctx->n_slots; ++i) free_slot(ctx->slot[i]);
     CtxExtra* ex = extra(ctx);
     if (ex) {
         for (int i = 0; i < 2; ++i) {
@@ -606,9 +611,9 @@ int rmcv_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, si
     const int CF = ctx->CF;
     const size_t dev_frame = (size_t)height * rowbytes, dev_mask = (size_t)height * width;
     int nchunks = 0;
-    extra(ctx)->last_first_slot = (int)(extra(ctx)->chunk_counter % kSlots);
+    extra(ctx)->last_first_slot = (int)(extra(ctx)->chunk_counter % ctx->n_slots);
     for (int f0 = 0; f0 < batch; f0 += CF, ++nchunks) {
-        SlotBuffers& sb = ctx->slot[extra(ctx)->chunk_counter++ % kSlots];
+        SlotBuffers& sb = ctx->slot[extra(ctx)->chunk_counter++ % ctx->n_slots];
         const int frames = batch - f0 < CF ? batch - f0 : CF;
         const size_t need = (size_t)CF * (size_t)ctx->cfg.max_height * ctx->cfg.max_width * 3;
         if (sb.frames_bytes < need) {

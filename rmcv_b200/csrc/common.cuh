@@ -58,9 +58,9 @@ struct Geometry {           // frame geometry + derived sizes, shared by all ker
     int SC;                 // entries per frame of the global bucket array (>= R+2 and >= PC)
 };
 
-// Scratch slots of a ctx: chunk n (counted over the life of the ctx) uses slot n % kSlots, so up to kSlots chunks are in
+// Scratch slots of a ctx: chunk n (counted over the life of the ctx) uses slot n % n_slots, so up to n_slots chunks are in
 // flight between the start of their pixel kernel and the end of their write-out.
-constexpr int kSlots = 3;
+constexpr int kSlots = 8;          // upper bound; a ctx uses n_slots of them (default 3, RMCV_SLOTS)
 
 struct SlotBuffers {
     // pixel stage outputs
@@ -110,6 +110,7 @@ struct rmcv_ctx {
     int CF;                 // chunk frames
     rmcv::Geometry cap;     // capacities at max_width x max_height
     rmcv::SlotBuffers slot[rmcv::kSlots];
+    int n_slots;
     // pinned, device-mapped result arrays of the most recent detect call (one of the two sets kept in api.cu)
     rmcv_frame_info* h_frames;      // [max_batch]
     rmcv_contour_info* h_contours;  // [max_batch][C]  (chunk-dense)

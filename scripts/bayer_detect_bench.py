@@ -6,7 +6,8 @@ import rmcv_b200 as rb
 from rmcv_b200 import synth
 W, H, B = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (1280, 1024, 1024)
 raw = np.stack([synth.bgr_to_bayer(synth.make_frame(s, W, H, synth.plates_for_seed(s)), synth.BAYER_BG) for s in range(32)] * (B // 32))
-c = rb.Context(max_width=W, max_height=H, max_batch=B)
+import os
+c = rb.Context(max_width=W, max_height=H, max_batch=B, chunk_frames=int(os.environ.get("CHUNK", "0")))
 d = c.device_buffer(raw.nbytes); m = c.device_buffer(B * H * W); d.upload(raw)
 p = rb.default_params()
 for _ in range(3):
