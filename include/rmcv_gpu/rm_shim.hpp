@@ -34,6 +34,7 @@ namespace cv {
 struct Point { int x = 0, y = 0; };
 struct Point2f { float x = 0, y = 0; };
 struct Size2f { float width = 0, height = 0; };
+struct Size { int width = 0, height = 0; };
 struct Rect2f { float x = 0, y = 0, width = 0, height = 0; };
 struct RotatedRect { Point2f center; Size2f size; float angle = 0; };
 // 8-bit image view/owner with cv::Mat's field names for the members the shim touches
@@ -356,6 +357,37 @@ inline bool LightBlobOverlap(const std::vector<lightblob>& lightBlobs, int leftI
     int res = 0;
     gc.check(rmcv_lightblob_overlap(ctx, in.data(), (int)in.size(), leftIndex, rightIndex, &res), "rmcv_lightblob_overlap");
     return res != 0;
+}
+
+// rm::affine_correction — include/imgproc.h:19, src/imgproc.cpp:9-35 (next row f2): the icon crop of one armour, bit-exact
+// against OpenCV's getAffineTransform / warpAffine / resize.  The four vertices are clamped into the frame in place like the
+// reference does.  The frame is uploaded for this call; rmcv_icon_batch / rmcv_identify_batch take a device-resident frame
+// and all armours of it at once.
+inline cv::Mat affine_correction(const cv::Mat& source, cv::Point2f vertices[4], const cv::Size outSize) {
+    gpu::context& gc = gpu::default_context();
+    rmcv_ctx* ctx = gc.get(source.cols, source.rows);
+    rmcv_armour a;
+    std::memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 4; ++i) { a.icon[i][0] = vertices[i].x; a.icon[i][1] = vertices[i].y; }
+    const size_t bytes = (size_t)source.step * (size_t)source.rows;
+    void* d_frame = nullptr;
+    gc.check(rmcv_device_alloc(ctx, bytes, &d_frame), "rmcv_device_alloc");
+    std::vector<uint8_t> icon((size_t)outSize.width * outSize.height * 3);
+    int rc = rmcv_memcpy_h2d(ctx, d_frame, source.data, bytes);
+    if (rc == RMCV_OK)
+        rc = rmcv_icon_batch(ctx, static_cast<const uint8_t*>(d_frame), (size_t)source.step, source.cols, source.rows, &a, 1, outSize.width,
+                             outSize.height, icon.data(), nullptr);
+    rmcv_device_free(ctx, d_frame);
+    gc.check(rc, "rmcv_icon_batch");
+    for (int i = 0; i < 4; ++i) { vertices[i].x = a.icon[i][0]; vertices[i].y = a.icon[i][1]; }
+#if defined(RMCV_SHIM_WITH_REFERENCE)
+    cv::Mat out(outSize.height, outSize.width, CV_8UC3);
+#else
+    cv::Mat out(outSize.height, outSize.width, 3);
+#endif
+    for (int y = 0; y < outSize.height; ++y)
+        std::memcpy(out.data + (size_t)y * out.step, icon.data() + (size_t)y * outSize.width * 3, (size_t)outSize.width * 3);
+    return out;
 }
 
 #if defined(RMCV_SHIM_WITH_REFERENCE)

@@ -30,6 +30,15 @@ int main(int argc, char** argv) {
         cv::RotatedRect one;
         const bool matched0 = !contours.empty() && rm::MatchLightBlob(contours[0], 1.5f, 80.f, 70.f, 10.f, 99999.f, one, true);
         const bool overlap = legacy.size() >= 3 && rm::LightBlobOverlap(legacy, 0, (int)legacy.size() - 1);
+        // next row f2: the icon crop of every armour (src/imgproc.cpp:9-35) through the shim; FNV-1a of the 20x20x3 bytes
+        std::vector<unsigned long long> icon_hash;
+        for (auto& arm : armours) {
+            cv::Mat icon = rm::affine_correction(image, arm.icon, cv::Size{20, 20});
+            unsigned long long h = 1469598103934665603ull;
+            for (int y = 0; y < icon.rows; ++y)
+                for (int x = 0; x < icon.cols * 3; ++x) { h ^= icon.data[(size_t)y * icon.step + x]; h *= 1099511628211ull; }
+            icon_hash.push_back(h);
+        }
         unsigned long long fg = 0;
         for (int y = 0; y < binary.rows; ++y)
             for (int x = 0; x < binary.cols; ++x) fg += binary.data[(size_t)y * binary.step + x] == 255;
@@ -46,6 +55,8 @@ int main(int argc, char** argv) {
         for (size_t k = 0; k < armours.size(); ++k)
             printf("%s[%.1f,%.1f,%.1f,%.1f]", k ? "," : "", armours[k].bounding_box.x, armours[k].bounding_box.y, armours[k].bounding_box.width,
                    armours[k].bounding_box.height);
+        printf("],\n \"icon_hashes\": [");
+        for (size_t k = 0; k < icon_hash.size(); ++k) printf("%s\"%llu\"", k ? "," : "", icon_hash[k]);
         printf("]}\n");
     } catch (const rm::gpu::error& e) {
         fprintf(stderr, "rm::gpu::error %d: %s\n", e.status, e.what());

@@ -42,3 +42,12 @@ def test_cpp_call_site_matches_oracle():
     for g, b in zip(got["blob_centers"], ref.positive):
         assert abs(g[0] - b.center[0]) <= 0.5 and abs(g[1] - b.center[1]) <= 0.5  # rng-band tolerant; exactness is tested elsewhere
     assert [tuple(x) for x in got["armour_boxes"]] == [a.bounding_box for a in ref.armours] or len(got["armour_boxes"]) == len(ref.armours)
+    # next row f2 through the shim: rm::affine_correction of every armour, FNV-1a of the icon bytes
+    def fnv(b):
+        h = 1469598103934665603
+        for v in b.tobytes():
+            h = ((h ^ v) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+    assert len(got["icon_hashes"]) == len(ref.armours)
+    for g, a in zip(got["icon_hashes"], ref.armours):
+        assert int(g) == fnv(np.ascontiguousarray(O.affine_correction(frame, a.icon)[0]))
