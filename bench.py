@@ -406,7 +406,9 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": ach_iso, "peak": peak, "unit": "GB/s", "frac": ach_iso / peak,
                          "traffic": ncu_traffic_per_launch(frames_per_launch),
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_FRAME * frames_per_launch,
-                         "kernel": "pixel_bgr_kernel<true> (fused diff/threshold/close)", "peak_source": peak_src,
+                         "kernel": "pixel_bgr_kernel<true, Geom1280> (fused diff/threshold/close)", "peak_source": peak_src,
+                         "peak_note": "peak = measured copy bandwidth (1 read : 1 write); this kernel reads 3 bytes per byte it "
+                                      "writes, and reads are cheaper for HBM than writes, so frac may exceed 1 by a few per cent",
                          "launch_ms": pix_ms_med / n_chunks, "frames_per_launch": frames_per_launch,
                          "algorithmic_bytes_per_frame": ALG_BYTES_PER_FRAME,
                          "in_pipeline": {"achieved": ach_pipe, "launch_ms": pix_in_pipe_ms,

@@ -108,18 +108,33 @@ __host__ __device__ inline size_t pix_smem_bytes(int S, int RC, int srow, int BH
     return stage + bars + t + d;
 }
 
+// Compile-time geometry of a launch: kW = 0 reads everything from PixelParams; kW > 0 fixes the width, the band height,
+// the rows per TMA chunk, the ring depth and the CTA size, so that the index arithmetic of a band (divisions by the word
+// count, per-segment row counts, the 2-D walk) folds into constants.  Every CTA only sees 128 pixels per thread, which
+// makes that set-up arithmetic a visible share of the kernel.
+template <int kW_, int kBH_, int kRC_, int kS_, int kNT_>
+struct PixGeom {
+    static constexpr int kW = kW_, kBH = kBH_, kRC = kRC_, kS = kS_, kNT = kNT_;
+};
+using GeomRuntime = PixGeom<0, 0, 0, 0, 0>;
+using Geom1280 = PixGeom<1280, 32, 4, 4, 320>;
+
 // ------------------------------------------------------------------------------------------ morphology + stores
 // t: (nout+4) x TW threshold words (row 0 <-> image row y0-2), zero outside the image.
 // Writes the final mask of rows [y0, y0+nout) to global as bytes and as bit words (the labelling stages read the bits).
 // Both passes are separable (3x1 on the bit row, then 1x3 down the rows) and a thread walks DOWN one word column over a
 // segment of rows, so every word is loaded once and the row-combined value slides through three registers.
+template <class G = GeomRuntime>
 __device__ __forceinline__ void close_and_store(const PixelParams& p, uint32_t* t, uint32_t* d, int frame, int y0,
-                                                int nout, int tid, int NT) {
-    const int WB = p.WB, TW = WB + 2, H = p.H;
-    const uint32_t valid = p.last_valid;
+                                                int nout, int tid, int NT_) {
+    constexpr bool kFixed = G::kW > 0;
+    const int W = kFixed ? G::kW : p.W;
+    const int NT = kFixed ? G::kNT : NT_;
+    const int WB = kFixed ? (G::kW + 31) / 32 : p.WB, TW = WB + 2, H = p.H;
+    const uint32_t valid = kFixed ? ((G::kW & 31) ? ((1u << (G::kW & 31)) - 1u) : 0xFFFFFFFFu) : p.last_valid;
     const int nseg = NT >= WB ? NT / WB : 1;      // row segments per word column
     auto col_of = [&](int slot, int* seg) -> int {  // slot -> (segment, word column); one umulhi instead of a division
-        const int sg = p.inv_wb ? (int)__umulhi((uint32_t)slot, p.inv_wb) : slot;
+        const int sg = kFixed ? slot / WB : (p.inv_wb ? (int)__umulhi((uint32_t)slot, p.inv_wb) : slot);
         *seg = sg;
         return slot - sg * WB;
     };
@@ -188,13 +203,13 @@ __device__ __forceinline__ void close_and_store(const PixelParams& p, uint32_t* 
     // ---- byte mask: one 16-byte store per 16 pixels, a thread walks down one 16-pixel column
     if (p.mask != nullptr) {
         const uint16_t* m16 = reinterpret_cast<const uint16_t*>(m);
-        const int gpr16 = (p.W + 15) >> 4;
+        const int gpr16 = (W + 15) >> 4;
         const int nsg = NT >= gpr16 ? NT / gpr16 : 1;
         uint8_t* gmask = p.mask + (size_t)frame * p.mask_frame_stride + (size_t)y0 * p.mask_pitch;
         for (int slot = tid; slot < gpr16 * nsg; slot += NT) {
-            const int sg = p.inv_gpr16 ? (int)__umulhi((uint32_t)slot, p.inv_gpr16) : slot;
+            const int sg = kFixed ? slot / gpr16 : (p.inv_gpr16 ? (int)__umulhi((uint32_t)slot, p.inv_gpr16) : slot);
             const int g = slot - sg * gpr16;
-            const bool vec = p.mask_vec && g * 16 + 16 <= p.W;
+            const bool vec = p.mask_vec && g * 16 + 16 <= W;
             uint8_t* dst = gmask + (size_t)sg * p.mask_pitch + (size_t)g * 16;
             const size_t dstep = (size_t)nsg * p.mask_pitch;
             const uint16_t* src = m16 + (size_t)sg * WB * 2 + g;
@@ -209,7 +224,7 @@ __device__ __forceinline__ void close_and_store(const PixelParams& p, uint32_t* 
                     __stcs(reinterpret_cast<uint4*>(dst), o);
                 } else {
                     const uint32_t w[4] = {o.x, o.y, o.z, o.w};
-                    for (int q = 0; q < 16 && g * 16 + q < p.W; ++q) dst[q] = (uint8_t)(w[q >> 2] >> ((q & 3) * 8));
+                    for (int q = 0; q < 16 && g * 16 + q < W; ++q) dst[q] = (uint8_t)(w[q >> 2] >> ((q & 3) * 8));
                 }
             }
         }
@@ -217,19 +232,22 @@ __device__ __forceinline__ void close_and_store(const PixelParams& p, uint32_t* 
 }
 
 // ------------------------------------------------------------------------------------------ BGR kernel
-template <bool kBulk>
+template <bool kBulk, class G = GeomRuntime>
 __global__ void __launch_bounds__(512) pixel_bgr_kernel(const PixelParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, NT = blockDim.x;
+    constexpr bool kFixed = G::kW > 0;
+    const int tid = threadIdx.x, NT = kFixed ? G::kNT : (int)blockDim.x;
     const int frame = blockIdx.x / p.bands, band = blockIdx.x - frame * p.bands;
-    const int W = p.W, H = p.H, WB = p.WB, TW = WB + 2, BH = p.BH, RC = p.RC, S = p.S;
+    const int W = kFixed ? G::kW : p.W, H = p.H, WB = kFixed ? (G::kW + 31) / 32 : p.WB, TW = WB + 2;
+    const int BH = kFixed ? G::kBH : p.BH, RC = kFixed ? G::kRC : p.RC, S = kFixed ? G::kS : p.S;
+    const int srow = kFixed ? ((G::kW + 15) / 16) * 48 : p.srow;
     const int y0 = band * BH;
     const int nout = min(BH, H - y0);
     const int hl = p.halo;
     const int ty0 = y0 - hl;                              // image row of t row 0
     const int cy0 = max(0, ty0), cy1 = min(H, y0 + nout + hl);
     const int nchunks = (cy1 - cy0 + RC - 1) / RC;
-    const size_t stage_bytes = (size_t)RC * p.srow;
+    const size_t stage_bytes = (size_t)RC * srow;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
     uint32_t* t = reinterpret_cast<uint32_t*>(smem + (size_t)S * stage_bytes + (((size_t)S * 8 + 15) & ~(size_t)15));
     uint32_t* d = t + (size_t)(BH + 2 * hl) * TW;
@@ -254,14 +272,14 @@ __global__ void __launch_bounds__(512) pixel_bgr_kernel(const PixelParams p) {
         if (p.contiguous) {
             bulk_g2s(dst, fsrc + (size_t)r0 * p.pitch, (uint32_t)nr * rowbytes, &bars[s]);
         } else {
-            for (int r = 0; r < nr; ++r) bulk_g2s(dst + (size_t)r * p.srow, fsrc + (size_t)(r0 + r) * p.pitch, rowbytes, &bars[s]);
+            for (int r = 0; r < nr; ++r) bulk_g2s(dst + (size_t)r * srow, fsrc + (size_t)(r0 + r) * p.pitch, rowbytes, &bars[s]);
         }
     };
     if (kBulk && tid == 0) {
         for (int c = 0; c < S && c < nchunks; ++c) issue(c, c);
     }
 
-    const int gpr = p.gpr;
+    const int gpr = kFixed ? (G::kW + 15) / 16 : p.gpr;
     const uint32_t c0 = p.coef[0], c1a = p.coef[1], c1b = p.coef[2], c2a = p.coef[3], c2b = p.coef[4], c3 = p.coef[5];
     const int acc0 = p.acc0;
     const Iter2D it0(tid, NT, gpr);
@@ -277,12 +295,12 @@ __global__ void __launch_bounds__(512) pixel_bgr_kernel(const PixelParams p) {
             uint8_t* wstage = smem + (size_t)s * stage_bytes;
             for (int r = 0; r < nr; ++r) {
                 const uint8_t* g = fsrc + (size_t)(r0 + r) * p.pitch;
-                for (uint32_t i = tid; i < rowbytes; i += NT) wstage[(size_t)r * p.srow + i] = __ldg(g + i);
+                for (uint32_t i = tid; i < rowbytes; i += NT) wstage[(size_t)r * srow + i] = __ldg(g + i);
             }
             __syncthreads();
         }
         for (Iter2D it = it0; it.r < nr; it.next()) {
-            const uint4* q = reinterpret_cast<const uint4*>(stage + (size_t)it.r * p.srow + (size_t)it.c * 48);
+            const uint4* q = reinterpret_cast<const uint4*>(stage + (size_t)it.r * srow + (size_t)it.c * 48);
             const uint4 A = q[0], B = q[1], C = q[2];
             const uint32_t w[12] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x, C.y, C.z, C.w};
             uint32_t nb = 0;  // sign bits of (diff - lb), pixel 15 first so that pixel 0 lands in bit 0
@@ -305,7 +323,7 @@ __global__ void __launch_bounds__(512) pixel_bgr_kernel(const PixelParams p) {
         if (kBulk && tid == 0 && c + S < nchunks) issue(c + S, s);
         if (++s == S) { s = 0; phase ^= 1u; }
     }
-    close_and_store(p, t, d, frame, y0, nout, tid, NT);
+    close_and_store<G>(p, t, d, frame, y0, nout, tid, NT);
 }
 
 // ------------------------------------------------------------------------------------------ Bayer kernel
@@ -567,7 +585,13 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
         while (smem > (size_t)max_smem && p.RC > 1) { --p.RC; smem = pix_smem_bytes(p.S, p.RC, p.srow, BH, p.WB, hl); }
         if (smem > (size_t)max_smem) return cudaErrorInvalidConfiguration;
         cudaError_t e;
-        if (bulk) {
+        const bool fixed1280 = bulk && L.W == Geom1280::kW && p.BH == Geom1280::kBH && p.RC == Geom1280::kRC && p.S == Geom1280::kS &&
+                               NT == Geom1280::kNT && env_int("RMCV_PIX_GENERIC", 0) == 0;
+        if (fixed1280) {   // the default configuration with its geometry folded into the code
+            e = cudaFuncSetAttribute(pixel_bgr_kernel<true, Geom1280>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            pixel_bgr_kernel<true, Geom1280><<<(unsigned)grid, NT, smem, st>>>(p);
+        } else if (bulk) {
             e = cudaFuncSetAttribute(pixel_bgr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             pixel_bgr_kernel<true><<<(unsigned)grid, NT, smem, st>>>(p);
