@@ -324,9 +324,25 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
         for (int r = tid; r < n_runs; r += NT) {
             const int y = f.run_y[r];
             const int2 rr = row(y);
-            if (r == rr.x || y <= hy0 || y >= hy1) { f.glink[r + 1] = 0; continue; }  // border gap, or outside the box
+            if (r == rr.x) { f.glink[r + 1] = 0; continue; }   // left border gap (the gaps above it test for it themselves)
             const int a = (int)(f.run_x[r - 1] >> 16) + 1, b = (int)(f.run_x[r] & 0xffffu) - 1;
-            if (a <= hx0 || b >= hx1) { f.glink[r + 1] = 0; continue; }
+            if (y <= hy0 || y >= hy1 || a <= hx0 || b >= hx1) {
+                // not strictly inside the box: outer background without any search.  The gaps of the row above that it
+                // touches and that do lie inside the box are connected to it, and nothing else tells them so.
+                f.glink[r + 1] = 0;
+                if (y - 1 > hy0 && y - 1 < hy1 && b > hx0 && a < hx1) {
+                    const int2 pr = row(y - 1);
+                    const int lo = pr.x, hi = pr.y;
+                    for (int k = upper_bound_xs(f.run_x, lo, hi, a);; ++k) {
+                        const int ga = (k == lo) ? 0 : (int)(f.run_x[k - 1] >> 16) + 1;
+                        if (ga > b) break;
+                        const int gb = (k == hi) ? W - 1 : (int)(f.run_x[k] & 0xffffu) - 1;
+                        if (gb >= a && ga <= gb && k != lo && k != hi) f.jo[k + 1] = 1;
+                        if (k == hi) break;
+                    }
+                }
+                continue;
+            }
             bool outer = false;
             int first = -1;
             {   // row above: every overlapped gap is connected to this one (and so to each other)

@@ -144,6 +144,31 @@ def test_random_masks(ctx, seed):
     detect_and_compare(ctx, mask_to_bgr(m)[None], p, what=f"random {seed} {W}x{H}")
 
 
+def test_concavity_next_to_holed_components(ctx):
+    """Regression (found by scripts/fuzz_gpu.py): a small component in a concavity of a larger one, where the concavity
+    opens across the edge of the bounding box of the frame's holed components — the background gap just inside the box
+    must inherit "outer" from the gap below it that lies outside the box, or the small component is taken for a nested
+    one and dropped.  The mask (a closed 832x37 noise mask with 52 holes, 324 external contours) is a committed fixture."""
+    path = os.path.join(os.path.dirname(__file__), "golden", "mask_concavity_next_to_holes_37x832.npy")
+    m = np.unpackbits(np.load(path), axis=1)[:, :832].astype(bool)
+    p = CMP.oracle_params(dict(area_range=(10.0, 99999.0)))
+    rep = detect_and_compare(ctx, mask_to_bgr(m)[None], p, check_points=False, what="concavity fixture")
+    assert rep.contours == 324
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_wide_noise_masks_with_many_holes(ctx, seed):
+    """Closed noise masks, wide and flat (hundreds of components and dozens of holes per frame): every concavity /
+    hole / bounding-box configuration of the gap labelling shows up somewhere."""
+    rng = np.random.default_rng(7000 + seed)
+    H, W = int(rng.integers(24, 60)), int(rng.integers(500, 1000))
+    from oracle import cv_restate as R
+    m = R.close3x3(rng.random((H, W)) < rng.uniform(0.3, 0.45))
+    p = CMP.oracle_params(dict(area_range=(10.0, 99999.0)))
+    with rb.Context(max_width=W, max_height=H, max_batch=1, max_blobs_per_frame=2048) as c:
+        detect_and_compare(c, mask_to_bgr(m)[None], p, check_points=False, what=f"noise {seed} {W}x{H}")
+
+
 def test_nested_levels(ctx):
     """Component inside a hole inside a component inside a hole ...: only the outermost is external."""
     m = np.zeros((60, 60), bool)
