@@ -650,6 +650,7 @@ struct OrderParams {
     rmcv_armour* o_armours;
     int frames;  // frames in this chunk (index of the allocator entry in sb.counters)
     int defer_copy;  // the records are posted by writeout_kernel (large frames: many CTAs per frame share the PCIe writes)
+    int stage_blobs; // the positives are staged in shared memory for the pair loops (wide variant, when they fit)
 };
 
 // NTMAX: 128 threads for ordinary frames; 512 for frames with large capacities (stress frames: hundreds of blobs, ~125k
@@ -705,7 +706,7 @@ __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
     // ---- pairs in lexicographic (i,j) order (src/objdetect.cpp:122-163)
     const int P = s_np;
     const rmcv_lightblob* sblob = ob;            // ordinary frames: ~25 positives, read in place (L1/L2)
-    if (NTMAX > 128) {                           // large capacities: staged in shared memory for the O(P^2) loops
+    if (p.stage_blobs) {                         // large capacities: staged in shared memory for the O(P^2) loops
         rmcv_lightblob* st = reinterpret_cast<rmcv_lightblob*>(s_status + C);
         copy_words(st, ob, (size_t)P * sizeof(rmcv_lightblob), tid, NT);
         sblob = st;
@@ -935,7 +936,10 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         p.o_frames = L.o_frames; p.o_contours = L.o_contours; p.o_blobs = L.o_blobs; p.o_armours = L.o_armours;
         p.frames = L.frames;
         const bool big = L.g.R > 65535 || L.g.C > 512 || L.frames <= small_batch;
-        const size_t smem = (size_t)2 * L.g.C * 4 + 16 + (big ? (size_t)L.g.C * sizeof(rmcv_lightblob) : 0);   // keys, status (+ staged blobs)
+        size_t smem = (size_t)2 * L.g.C * 4 + 16;   // keys, status
+        p.stage_blobs = big && smem + (size_t)L.g.C * sizeof(rmcv_lightblob) <= (size_t)max_smem_optin ? 1 : 0;
+        if (p.stage_blobs) smem += (size_t)L.g.C * sizeof(rmcv_lightblob);
+        if (smem > (size_t)max_smem_optin) return cudaErrorInvalidConfiguration;
         if (smem > 48 * 1024) {
             e = big ? cudaFuncSetAttribute(order_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                     : cudaFuncSetAttribute(order_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

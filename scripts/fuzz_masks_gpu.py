@@ -1,0 +1,52 @@
+"""GPU aid: closed noise masks of many sizes and densities (hundreds to thousands of components, holes, nesting, concavities)
+through the whole path; external contours (count, first pixel, size, ordered points of a sample) and the label map against
+cv2.  usage: fuzz_masks_gpu.py [cases] [seed]"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import cv2
+import rmcv_b200 as rb
+from oracle import cv_restate as R
+
+cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+bad = 0
+for n in range(cases):
+    W = int(rng.integers(16, 900)); H = int(rng.integers(8, 500))
+    dens = rng.uniform(0.2, 0.6)
+    m = rng.random((H, W)) < dens
+    kind = int(rng.integers(0, 3))
+    if kind == 1:
+        m = cv2.GaussianBlur(m.astype(np.float32), (0, 0), float(rng.uniform(1.0, 3.0))) > dens * rng.uniform(0.8, 1.1)
+    elif kind == 2:
+        m = cv2.dilate(m.astype(np.uint8), np.ones((2, 2), np.uint8)).astype(bool) & (rng.random((H, W)) < 0.9)
+    m = R.close3x3(m)
+    frame = np.zeros((H, W, 3), np.uint8); frame[..., 0] = np.where(m, 200, 0)
+    contours, _ = cv2.findContours(m.astype(np.uint8) * 255, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
+    if len(contours) > 8000:
+        continue
+    prm = rb.default_params(area_range=(0.0, 1e300))
+    with rb.Context(max_width=W, max_height=H, max_batch=1, max_blobs_per_frame=8192, max_armours_per_frame=16384) as c:
+        try:
+            res = c.detect_batch_host(frame[None], prm)
+        except rb.RmcvError as e:
+            if "capacity" in str(e):
+                continue
+            raise
+        det = c.frame_detections(res, 0)
+        got = [(tuple(ci.first), ci.n_points) for ci in det.contours]
+        want = [((int(p[0][0][0]), int(p[0][0][1])), len(p)) for p in contours]
+        ok = got == want
+        if ok and len(contours):
+            pts = c.get_contours(0)
+            for k in range(0, len(contours), max(1, len(contours) // 16)):
+                ok = ok and np.array_equal(pts[k], contours[k].reshape(-1, 2))
+        if not ok:
+            bad += 1
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            np.save(os.path.join(ROOT, "gpurun_out", "fuzz_mask_fail_%d.npy" % bad), np.packbits(m, axis=1))
+            print("MISMATCH", dict(W=W, H=H, kind=kind, dens=round(dens, 3)), len(got), len(want),
+                  sorted(set(want) - set(got))[:3], sorted(set(got) - set(want))[:3])
+print("fuzz_masks: %d cases, %d mismatches" % (cases, bad))
+sys.exit(1 if bad else 0)

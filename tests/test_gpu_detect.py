@@ -169,6 +169,17 @@ def test_wide_noise_masks_with_many_holes(ctx, seed):
         detect_and_compare(c, mask_to_bgr(m)[None], p, check_points=False, what=f"noise {seed} {W}x{H}")
 
 
+def test_large_capacities(ctx):
+    """Capacities far above the defaults (8192 blobs, 16384 armours per frame): the wide order kernel cannot stage that
+    many light blobs in shared memory and reads them in place."""
+    rng = np.random.default_rng(77)
+    from oracle import cv_restate as R
+    m = R.close3x3(rng.random((120, 400)) < 0.35)
+    p = CMP.oracle_params(dict(area_range=(10.0, 99999.0)))
+    with rb.Context(max_width=400, max_height=120, max_batch=2, max_blobs_per_frame=8192, max_armours_per_frame=16384) as c:
+        detect_and_compare(c, np.stack([mask_to_bgr(m), mask_to_bgr(m[::-1].copy())]), p, check_points=False, what="large capacities")
+
+
 def test_nested_levels(ctx):
     """Component inside a hole inside a component inside a hole ...: only the outermost is external."""
     m = np.zeros((60, 60), bool)
