@@ -12,13 +12,17 @@ from oracle import cv_restate as R
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 bad = 0
+ran = 0
+total_contours = 0
 for n in range(cases):
-    W = int(rng.integers(16, 900)); H = int(rng.integers(8, 500))
-    dens = rng.uniform(0.2, 0.6)
+    big = os.environ.get("FUZZ_BIG")        # frames above 2 Mpx: the label kernel works on global arrays
+    W = int(rng.integers(1500, 2600)) if big else int(rng.integers(16, 900))
+    H = int(rng.integers(1400, 2000)) if big else int(rng.integers(8, 500))
+    dens = rng.uniform(0.05, 0.5)
     m = rng.random((H, W)) < dens
-    kind = int(rng.integers(0, 3))
+    kind = 1 if big else int(rng.integers(0, 3))
     if kind == 1:
-        m = cv2.GaussianBlur(m.astype(np.float32), (0, 0), float(rng.uniform(1.0, 3.0))) > dens * rng.uniform(0.8, 1.1)
+        m = cv2.GaussianBlur(m.astype(np.float32), (0, 0), float(rng.uniform(3.0, 8.0) if big else rng.uniform(1.0, 3.0))) > dens * rng.uniform(0.8, 1.1)
     elif kind == 2:
         m = cv2.dilate(m.astype(np.uint8), np.ones((2, 2), np.uint8)).astype(bool) & (rng.random((H, W)) < 0.9)
     m = R.close3x3(m)
@@ -34,6 +38,8 @@ for n in range(cases):
             if "capacity" in str(e):
                 continue
             raise
+        ran += 1
+        total_contours += len(contours)
         det = c.frame_detections(res, 0)
         got = [(tuple(ci.first), ci.n_points) for ci in det.contours]
         want = [((int(p[0][0][0]), int(p[0][0][1])), len(p)) for p in contours]
@@ -48,5 +54,5 @@ for n in range(cases):
             np.save(os.path.join(ROOT, "gpurun_out", "fuzz_mask_fail_%d.npy" % bad), np.packbits(m, axis=1))
             print("MISMATCH", dict(W=W, H=H, kind=kind, dens=round(dens, 3)), len(got), len(want),
                   sorted(set(want) - set(got))[:3], sorted(set(got) - set(want))[:3])
-print("fuzz_masks: %d cases, %d mismatches" % (cases, bad))
+print("fuzz_masks: %d cases, %d compared (%d contours), %d mismatches" % (cases, ran, total_contours, bad))
 sys.exit(1 if bad else 0)
