@@ -946,9 +946,11 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
             if (e != cudaSuccess) return e;
         }
         p.defer_copy = (L.g.R > 65535 || L.g.C > 512) ? 1 : 0;
+        static const int exp_nocopy = getenv("RMCV_EXP_NOCOPY") ? atoi(getenv("RMCV_EXP_NOCOPY")) : 0;   // experiment only: records not posted
+        if (exp_nocopy) p.defer_copy = 2;
         if (big) order_kernel<512><<<L.frames, 512, smem, so>>>(p);
         else order_kernel<128><<<L.frames, 128, smem, so>>>(p);
-        if (p.defer_copy) {
+        if (p.defer_copy == 1) {
             if (launches) ++*launches;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             writeout_kernel<<<dim3(kWriteSplit, L.frames), 256, 0, so>>>(p);
