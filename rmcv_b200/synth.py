@@ -149,3 +149,37 @@ def bgr_to_bayer(img: np.ndarray, layout: int = BAYER_BG) -> np.ndarray:
     yy, xx = np.mgrid[0:H, 0:W]
     idx = ch[yy & 1, xx & 1]
     return np.take_along_axis(img, idx[..., None], axis=2)[..., 0].copy()
+
+
+def shape_mask(rng, W: int, H: int) -> np.ndarray:
+    """Boolean mask of drawn outlines — rings in rings, C-shaped arcs holding other shapes in their concavity, box
+    outlines, spirals, combs, dots, a little noise; some strokes erase and cut earlier shapes open.  Exercises holes,
+    nesting and concavities of the external-contour discovery (the reference's contour call at src/imgproc.cpp:72) far more densely than light bars do."""
+    import cv2
+    img = np.zeros((H, W), np.uint8)
+    for _ in range(int(rng.integers(3, 60))):
+        cx, cy = int(rng.integers(0, W)), int(rng.integers(0, H))
+        r = int(rng.integers(3, max(4, min(W, H) // 3)))
+        th = int(rng.integers(1, 6))
+        what = int(rng.integers(0, 6))
+        col = 255 if rng.random() < 0.8 else 0
+        if what == 0:
+            cv2.circle(img, (cx, cy), r, col, th)
+        elif what == 1:
+            a0 = float(rng.uniform(0, 360))
+            cv2.ellipse(img, (cx, cy), (r, max(2, int(r * rng.uniform(0.3, 1.0)))), float(rng.uniform(0, 180)), a0,
+                        a0 + float(rng.uniform(180, 340)), col, th)
+        elif what == 2:
+            cv2.rectangle(img, (cx - r, cy - r // 2), (cx + r, cy + r // 2), col, th)
+        elif what == 3:
+            t = np.linspace(0, float(rng.uniform(2, 8)) * np.pi, 400)
+            pts = np.stack([cx + r * t / t[-1] * np.cos(t), cy + r * t / t[-1] * np.sin(t)], 1).astype(np.int32)
+            cv2.polylines(img, [pts.reshape(-1, 1, 2)], False, col, th)
+        elif what == 4:
+            step = int(rng.integers(3, 9))
+            cv2.line(img, (cx - r, cy), (cx + r, cy), col, th)
+            for x in range(cx - r, cx + r, step):
+                cv2.line(img, (x, cy), (x, cy + int(rng.integers(-r, r + 1))), col, 1)
+        else:
+            cv2.circle(img, (cx, cy), int(rng.integers(1, 8)), col, -1)
+    return (img > 0) | (rng.random((H, W)) < float(rng.uniform(0.0, 0.01)))

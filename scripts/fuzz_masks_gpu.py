@@ -1,4 +1,5 @@
 """GPU aid: closed noise masks of many sizes and densities (hundreds to thousands of components, holes, nesting, concavities)
+and, with FUZZ_SHAPES=1, drawn shapes (rings in rings, C-shapes holding components in their concavity, spirals, combs)
 through the whole path; external contours (count, first pixel, size, ordered points of a sample) and the label map against
 cv2.  usage: fuzz_masks_gpu.py [cases] [seed]"""
 import os, sys
@@ -7,6 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import cv2
 import rmcv_b200 as rb
+from rmcv_b200 import synth
 from oracle import cv_restate as R
 
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
@@ -21,6 +23,11 @@ for n in range(cases):
     dens = rng.uniform(0.05, 0.5)
     m = rng.random((H, W)) < dens
     kind = 1 if big else int(rng.integers(0, 3))
+    if os.environ.get("FUZZ_SHAPES"):
+        kind = 3
+        W = int(rng.integers(200, 1400)); H = int(rng.integers(150, 1100))
+        m = synth.shape_mask(rng, W, H)
+        dens = 0.0
     if kind == 1:
         m = cv2.GaussianBlur(m.astype(np.float32), (0, 0), float(rng.uniform(3.0, 8.0) if big else rng.uniform(1.0, 3.0))) > dens * rng.uniform(0.8, 1.1)
     elif kind == 2:

@@ -169,6 +169,19 @@ def test_wide_noise_masks_with_many_holes(ctx, seed):
         detect_and_compare(c, mask_to_bgr(m)[None], p, check_points=False, what=f"noise {seed} {W}x{H}")
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_drawn_shapes(ctx, seed):
+    """Rings in rings, arcs holding other shapes in their concavity, spirals, combs (synth.shape_mask): the external
+    contours, their order and the blob pixel sets against cv2."""
+    rng = np.random.default_rng(9100 + seed)
+    W, H = int(rng.integers(200, 900)), int(rng.integers(150, 600))
+    from oracle import cv_restate as R
+    m = R.close3x3(synth.shape_mask(rng, W, H))
+    p = CMP.oracle_params(dict(area_range=(10.0, 99999.0)))
+    with rb.Context(max_width=W, max_height=H, max_batch=1, max_blobs_per_frame=4096) as c:
+        detect_and_compare(c, mask_to_bgr(m)[None], p, check_points=(seed < 3), what=f"shapes {seed} {W}x{H}")
+
+
 def test_large_capacities(ctx):
     """Capacities far above the defaults (8192 blobs, 16384 armours per frame): the wide order kernel cannot stage that
     many light blobs in shared memory and reads them in place."""
