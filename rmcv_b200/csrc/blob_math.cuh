@@ -302,7 +302,11 @@ RMCV_HD void nodirect_fit(const Moments& m, double scale, float c32x, float c32y
     box->cx = fadd((float)(rx / scale), c32x);
     box->cy = fadd((float)(ry / scale), c32y);
     float wd = (float)(rp2 * 2.0 / scale), ht = (float)(rp3 * 2.0 / scale);
-    float ang = (float)(rp4 * 180.0 / RMCV_PI);
+    // cv::fitEllipseNoDirect assigns box.angle only when it swaps the axes, so the angle of an unswapped box stays at
+    // cv::RotatedRect's default 0.  With |g2[2]| > min_eps t = hypot(g2[2], g2[1] - g2[0]) > 0 and the swap always happens;
+    // the unswapped case is the axis-aligned ellipse taller than wide (t = g2[1] - g2[0] < 0), e.g. an exactly
+    // mirror-symmetric upright light bar.
+    float ang = 0.f;
     if (wd > ht) {
         const float tmp = wd; wd = ht; ht = tmp;
         ang = (float)(90.0 + rp4 * 180.0 / RMCV_PI);

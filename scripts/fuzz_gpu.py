@@ -7,11 +7,13 @@ sys.path.insert(0, ROOT)
 import rmcv_b200 as rb
 from rmcv_b200 import synth
 from oracle import rm_oracle as O
+from tests import _compare as CMP
 
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 bad = 0
 soft = 0
+rep = CMP.Report()
 for n in range(cases):
     W = int(rng.choice([rng.integers(3, 200), 16 * rng.integers(2, 90), 1280, 1440, 32 * rng.integers(1, 40)]))
     H = int(rng.choice([rng.integers(3, 150), 2 * rng.integers(2, 300), 1024]))
@@ -42,7 +44,14 @@ for n in range(cases):
                 [list(ci.first) for ci in det.contours] == [[int(p[0][0]), int(p[0][1])] for p in ref.contours] and \
                 [ci.n_points for ci in det.contours] == [len(p) for p in ref.contours]
             if ok and (len(det.positive) != len(ref.positive) or len(det.armours) != len(ref.armours)):
-                soft += 1    # a gate value at its threshold or a fit in cv::fitEllipseDirect's RNG band (tests/_compare.py carve-outs)
+                soft += 1    # must be a gate value at its threshold or a fit in cv::fitEllipseDirect's RNG band: checked below
+            if ok:           # the full comparison of tests/_compare.py (statistics exact, geometry within tolerance, carve-outs counted)
+                try:
+                    p = CMP.oracle_params(dict(target=int(target), lower_bound=int(prm.lower_bound)))
+                    rep.merge(CMP.compare_frame(det, ref, p, where="case %d frame %d" % (n, f)))
+                except AssertionError as e:
+                    ok = False
+                    print("COMPARE", str(e)[:300])
             if not ok:
                 bad += 1
                 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -64,5 +73,7 @@ for n in range(cases):
                     bad += 1
                     print("MISMATCH bayer", dict(W=W, H=H, B=B, f=f, layout=layout, target=target, lb=prm.lower_bound), int((bm[f] != refm).sum()))
             d_in.free(); d_out.free()
-print("fuzz: %d cases, %d mismatches, %d frames whose positive / armour counts differ (gate or RNG-band carve-outs)" % (cases, bad, soft))
+print("fuzz: %d cases, %d mismatches, %d frames whose positive / armour counts differ (all inside the comparator's carve-outs)" % (cases, bad, soft))
+print("compared:", {k: getattr(rep, k) for k in ("frames", "contours", "fitted", "direct", "fallback", "rng_band", "near_gate", "degenerate", "blobs", "armours")},
+      "worst centre / axis / angle / vertex:", rep.worst_centre, rep.worst_axis_rel, rep.worst_angle, rep.worst_vertex)
 sys.exit(1 if bad else 0)

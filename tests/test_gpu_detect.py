@@ -182,6 +182,29 @@ def test_drawn_shapes(ctx, seed):
         detect_and_compare(c, mask_to_bgr(m)[None], p, check_points=(seed < 3), what=f"shapes {seed} {W}x{H}")
 
 
+def test_upright_symmetric_bars(ctx):
+    """Exactly mirror-symmetric upright / level bars (rectangles, ellipses, diamonds of many sizes): the xy coefficient of
+    the fitted conic is zero and cv::fitEllipseNoDirect leaves the angle of an unswapped box at 0 — the fallback branch of a
+    singular direct fit must report 0, not -90 (found by scripts/fuzz_gpu.py: the blob flipped from positive to negative)."""
+    import cv2
+    img = np.zeros((1024, 1280), np.uint8)
+    x = 12
+    for k, (w, h) in enumerate([(20, 93), (19, 92), (10, 60), (11, 61), (24, 120), (18, 88), (21, 95), (16, 75), (22, 101), (14, 66),
+                                 (20, 94), (20, 92), (23, 110), (17, 80), (12, 57)]):
+        for row, kind in enumerate(("rect", "ellipse", "diamond")):
+            y = 40 + row * 300
+            if kind == "rect":
+                img[y:y + h, x:x + w] = 255
+            elif kind == "ellipse":
+                cv2.ellipse(img, (x + w // 2, y + h // 2), (w // 2, h // 2), 0, 0, 360, 255, -1)
+            else:
+                cv2.fillConvexPoly(img, np.array([[x + w // 2, y], [x + 2 * (w // 2), y + h // 2], [x + w // 2, y + 2 * (h // 2)], [x, y + h // 2]], np.int32), 255)
+        img[940:940 + w, x:x + min(h, 70)] = 255      # level bars
+        x += max(w, min(h, 70)) + 14
+    rep = detect_and_compare(ctx, mask_to_bgr(img > 0)[None], what="upright symmetric bars")
+    assert rep.fallback > 0 and rep.direct > 0
+
+
 def test_large_capacities(ctx):
     """Capacities far above the defaults (8192 blobs, 16384 armours per frame): the wide order kernel cannot stage that
     many light blobs in shared memory and reads them in place."""

@@ -73,6 +73,31 @@ def test_ellipse_lightblob_armour_math_matches_oracle(hm):
     assert branches[1] > 50 and branches[2] > 5 and n_arm > 50
 
 
+def _outline(w, h, x0=100, y0=200):
+    pts = [(x0 + i, y0) for i in range(w)] + [(x0 + w - 1, y0 + j) for j in range(1, h)] + \
+          [(x0 + w - 1 - i, y0 + h - 1) for i in range(1, w)] + [(x0, y0 + h - 1 - j) for j in range(1, h - 1)]
+    return np.array(pts, np.int32)
+
+
+@pytest.mark.parametrize("wh", [(20, 93), (93, 20), (19, 92), (10, 60), (60, 10), (11, 61), (24, 120), (120, 24), (7, 7), (30, 31)])
+def test_mirror_symmetric_outlines_both_fit_branches(hm, wh):
+    """Axis-aligned, exactly mirror-symmetric contours: the conic's xy coefficient is zero, so both fits take their
+    special branches (cv::fitEllipseDirect: theta from the sign of a - c; cv::fitEllipseNoDirect: t = g1 - g0 and an angle
+    that is only assigned when the axes are swapped, i.e. 0 for an upright ellipse).  Some of the sizes are singular for
+    the direct fit (|det| < 1e-10) and go through the fallback."""
+    import cv2
+    c = _outline(*wh)
+    br, box, det = fit(hm, c)
+    cv2.setRNGSeed(0)
+    (cx, cy), (w, h), ang = cv2.fitEllipseDirect(c.reshape(-1, 1, 2))
+    if 0.7e-10 <= det <= 1.0e-10 * (1 + 1e-6):
+        pytest.skip("RNG band")
+    assert abs(box.cx - cx) <= 1e-3 and abs(box.cy - cy) <= 1e-3
+    assert abs(box.w - w) <= 1e-5 * w + 1e-4 and abs(box.h - h) <= 1e-5 * h + 1e-4
+    if h / w > 1.0001:
+        assert abs(((box.angle - ang) + 90) % 180 - 90) <= 1e-3, (br, box.angle, ang)   # modulo 180 like tests/_compare.py
+
+
 def test_extend_cord_special_cases(hm):
     """Vertical / horizontal cords take the exact branches of rm::utils::ExtendCord (src/core.cpp:298-331)."""
     def blob(cx, verts):
