@@ -6,7 +6,9 @@ compared for near-isotropic blobs); light-blob and armour vertices <= 2e-3 px; g
 Carve-outs (counted, returned in the report):
   * `rng_band`: contours whose first direct-fit |det M| lies in [0.7e-10, 1e-10*(1+1e-6)]: cv::fitEllipseDirect
     itself is non-deterministic there (jittered retry from the global RNG) -> loose tolerance
-    0.5 px / 0.5 % / 0.1 deg and no exact gate membership;
+    0.5 px / 0.5 % / 0.1 deg and no exact gate membership; when the oracle's draw landed on a jittered direct fit that
+    is further away than that (thin ragged blobs), the GPU's answer must equal the reference's other possible outcome,
+    cv::fitEllipseNoDirect on the same contour, to the full tolerance;
   * `near_gate`: contours / pairs whose gate quantity is within tolerance of its threshold;
   * `degenerate`: contours whose oracle ellipse is thinner than 2 px (or not finite): the contour points lie on two
     parallel lines, the conic through them is a line pair, cv::fitEllipse's least-squares systems are singular and its
@@ -115,7 +117,18 @@ def compare_frame(det, ref: O.FrameResult, params, where="") -> Report:
         ds = max(abs(ew - e.w) / max(e.w, 1e-9), abs(eh - e.h) / max(e.h, 1e-9))
         da = angle_diff(ea, e.angle) if e.h / max(e.w, 1e-9) >= 1 + 1e-4 else 0.0
         if band:
-            assert dc <= LOOSE["centre"] and ds <= LOOSE["rel"] and da <= LOOSE["angle"], f"{w}: rng-band ellipse off: {c.ellipse} vs {e}"
+            if not (dc <= LOOSE["centre"] and ds <= LOOSE["rel"] and da <= LOOSE["angle"]):
+                # The reference's answer depends on its RNG here: a jittered retry of the direct fit when one succeeds, else
+                # cv::fitEllipseNoDirect.  The two can be far apart for thin ragged blobs, so the GPU's (deterministic)
+                # answer must then be the other outcome the reference can produce — the plain fallback — to full tolerance.
+                import cv2
+                (fx, fy), (fw, fh), fa = cv2.fitEllipse(np.ascontiguousarray(rc, np.int32).reshape(-1, 1, 2))
+                ulp = float(np.spacing(np.float32(max(abs(fx), abs(fy), 1.0))))
+                assert max(abs(cx - fx), abs(cy - fy)) <= max(TOL_CENTRE, 2 * ulp) and \
+                    max(abs(ew - fw) / max(fw, 1e-9), abs(eh - fh) / max(fh, 1e-9)) <= TOL_AXIS_REL + TOL_AXIS_ABS / max(fw, 1e-9) and \
+                    (angle_diff(ea, fa) <= TOL_ANGLE or fh / max(fw, 1e-9) < 1 + 1e-4), \
+                    f"{w}: rng-band ellipse matches neither outcome of the reference: {c.ellipse} vs {e} / fallback {(fx, fy, fw, fh, fa)}"
+                flips += 1      # the oracle's lists were built from its other outcome: not comparable for this frame
         else:
             # tolerance floor: one fp32 ulp of the coordinate
             ulp = float(np.spacing(np.float32(max(abs(e.cx), abs(e.cy), 1.0))))

@@ -205,6 +205,17 @@ def test_upright_symmetric_bars(ctx):
     assert rep.fallback > 0 and rep.direct > 0
 
 
+def test_rng_band_blob_whose_jittered_fit_is_far_away():
+    """A 17-row noise frame (committed fixture, found by scripts/fuzz_gpu.py) with a thin ragged blob whose direct fit is
+    singular inside cv::fitEllipseDirect's RNG band: with the oracle's seed the reference returns a jittered direct fit that
+    is 3 px away from its own fallback; the GPU must then equal the fallback exactly (tests/_compare.py)."""
+    fr = np.load(os.path.join(os.path.dirname(__file__), "golden", "rng_band_thin_blob.npz"))["frame"]
+    p = CMP.oracle_params(dict(target=0, lower_bound=120))
+    with rb.Context(max_width=fr.shape[1], max_height=fr.shape[0], max_batch=1) as c:
+        rep = detect_and_compare(c, fr[None], p, what="rng band fixture")
+    assert rep.rng_band >= 1
+
+
 def test_large_capacities(ctx):
     """Capacities far above the defaults (8192 blobs, 16384 armours per frame): the wide order kernel cannot stage that
     many light blobs in shared memory and reads them in place."""
