@@ -306,7 +306,7 @@ def nodirect_fit_from_moments(m: Dict[str, float], scale: float, c32x: float, c3
     by = f32(f32(ry / scale) + f32(c32y))
     wd = f32(rp2 * 2 / scale)
     ht = f32(rp3 * 2 / scale)
-    ang = f32(rp4 * 180 / math.pi)
+    ang = f32(0.0)   # cv::fitEllipseNoDirect assigns box.angle only in the swap below: an unswapped box keeps RotatedRect's 0
     if wd > ht:
         wd, ht = ht, wd
         ang = f32(90 + rp4 * 180 / math.pi)

@@ -123,6 +123,25 @@ def test_fit_ellipse_restatement_both_branches():
     assert n_direct > 50 and n_fallback > 5
 
 
+@pytest.mark.parametrize("wh", [(20, 93), (93, 20), (19, 92), (10, 60), (60, 10), (24, 120), (120, 24), (18, 88), (22, 101)])
+def test_fit_ellipse_restatement_on_mirror_symmetric_outlines(wh):
+    """Exactly axis-aligned contours (xy coefficient zero): cv::fitEllipseNoDirect only assigns the angle when it swaps the
+    axes, so an upright box keeps angle 0.  (20, 93) and its neighbours are singular for the direct fit -> fallback."""
+    w, h = wh
+    x0, y0 = 100, 200
+    pts = [(x0 + i, y0) for i in range(w)] + [(x0 + w - 1, y0 + j) for j in range(1, h)] + \
+          [(x0 + w - 1 - i, y0 + h - 1) for i in range(1, w)] + [(x0, y0 + h - 1 - j) for j in range(1, h - 1)]
+    c = np.array(pts, np.int32)
+    e = O.fit_ellipse_direct(c)
+    r = R.fit_ellipse_direct(c)
+    if 0.7e-10 <= r["det0"] <= 1.0e-10:
+        pytest.skip("RNG band")
+    b = r["box"]
+    assert max(abs(b[0] - e.cx), abs(b[1] - e.cy)) <= 1e-3
+    assert max(abs(b[2] - e.w) / e.w, abs(b[3] - e.h) / e.h) <= 1e-5
+    assert abs(((b[4] - e.angle) + 90) % 180 - 90) <= 1e-3, (r["branch"], b[4], e.angle)
+
+
 def test_fit_ellipse_direct_is_rng_dependent_only_inside_the_band():
     """The oracle seeds cv::theRNG() before each fit; outside the band the result does not depend on the seed."""
     img = synth.make_frame(2, 1280, 1024, 12)
