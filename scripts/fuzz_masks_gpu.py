@@ -10,12 +10,16 @@ import cv2
 import rmcv_b200 as rb
 from rmcv_b200 import synth
 from oracle import cv_restate as R
+from oracle import rm_oracle as O
+from tests import _compare as CMP
 
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 bad = 0
 ran = 0
 total_contours = 0
+rep = CMP.Report()
+FULL = os.environ.get("FUZZ_FULL")   # also every contour's statistics, fit, blob and armour through tests/_compare.py
 for n in range(cases):
     big = os.environ.get("FUZZ_BIG")        # frames above 2 Mpx: the label kernel works on global arrays
     W = int(rng.integers(1500, 2600)) if big else int(rng.integers(16, 900))
@@ -55,6 +59,16 @@ for n in range(cases):
             pts = c.get_contours(0)
             for k in range(0, len(contours), max(1, len(contours) // 16)):
                 ok = ok and np.array_equal(pts[k], contours[k].reshape(-1, 2))
+        if ok and FULL:
+            p = CMP.oracle_params(dict(area_range=(10.0, 99999.0)))
+            prm2 = rb.default_params()
+            try:
+                res2 = c.detect_batch_host(frame[None], prm2)
+                ref = O.detect_frame(frame)
+                rep.merge(CMP.compare_frame(c.frame_detections(res2, 0), ref, p, where="case %d" % n))
+            except AssertionError as e:
+                ok = False
+                print("COMPARE", str(e)[:300])
         if not ok:
             bad += 1
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -62,4 +76,7 @@ for n in range(cases):
             print("MISMATCH", dict(W=W, H=H, kind=kind, dens=round(dens, 3)), len(got), len(want),
                   sorted(set(want) - set(got))[:3], sorted(set(got) - set(want))[:3])
 print("fuzz_masks: %d cases, %d compared (%d contours), %d mismatches" % (cases, ran, total_contours, bad))
+if FULL:
+    print("compared:", {k: getattr(rep, k) for k in ("frames", "contours", "fitted", "direct", "fallback", "rng_band", "near_gate", "degenerate", "blobs", "armours")},
+          "worst centre / axis / angle / vertex:", rep.worst_centre, rep.worst_axis_rel, rep.worst_angle, rep.worst_vertex)
 sys.exit(1 if bad else 0)
