@@ -21,11 +21,12 @@ def ctx():
 def rect_equal(got, ref, tol=2e-3):
     """Same rectangle: cv2 convention (angle in [-90, 0), width along it); near-square ties may swap the edge."""
     (cx, cy, w, h, a), ((rx, ry), (rw, rh), ra) = got, ref
-    if max(abs(cx - rx), abs(cy - ry)) > tol * 10:
-        return False
-    if abs(w - rw) <= tol * max(1, rw) and abs(h - rh) <= tol * max(1, rh) and abs(a - ra) <= 0.02:
+    if max(abs(cx - rx), abs(cy - ry)) <= tol * 10 and abs(w - rw) <= tol * max(1, rw) and abs(h - rh) <= tol * max(1, rh) \
+            and abs(a - ra) <= 0.02:
         return True
-    return abs(w * h - rw * rh) <= 1e-5 * max(1.0, rw * rh)   # an equal-area tie between two hull edges (SURVEY A.9)
+    # an equal-area tie between two hull edges (SURVEY A.9): another minimum-area rectangle of the same points, whose
+    # centre then differs too (by less than the rectangle's own size)
+    return abs(w * h - rw * rh) <= 1e-5 * max(1.0, rw * rh) and max(abs(cx - rx), abs(cy - ry)) <= max(rw, rh)
 
 
 def test_min_area_rect_matches_cv2(ctx):
