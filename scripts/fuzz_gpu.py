@@ -14,6 +14,7 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 bad = 0
 soft = 0
 rep = CMP.Report()
+repb = CMP.Report()
 for n in range(cases):
     W = int(rng.choice([rng.integers(3, 200), 16 * rng.integers(2, 90), 1280, 1440, 32 * rng.integers(1, 40)]))
     H = int(rng.choice([rng.integers(3, 150), 2 * rng.integers(2, 300), 1024]))
@@ -72,8 +73,28 @@ for n in range(cases):
                 if not np.array_equal(bm[f], refm):
                     bad += 1
                     print("MISMATCH bayer", dict(W=W, H=H, B=B, f=f, layout=layout, target=target, lb=prm.lower_bound), int((bm[f] != refm).sum()))
+            # the same mosaics through the Bayer full-detect entry point, every frame through the comparator
+            c.bayer_detect_batch(d_in.ptr, W, H, B, layout, prm, d_out.ptr)
+            try:
+                resb = c.fetch_results()
+            except rb.RmcvError as e:
+                if "capacity" not in str(e):
+                    raise
+                resb = None
+            if resb is not None:
+                bm = d_out.download((B, H, W))
+                for f in range(min(B, 3)):
+                    refd = O.detect_frame(O.bayer_to_bgr(raw[f], layout), target=target, lower_bound=prm.lower_bound)
+                    try:
+                        assert np.array_equal(bm[f], refd.binary), "bayer detect mask differs"
+                        p = CMP.oracle_params(dict(target=int(target), lower_bound=int(prm.lower_bound)))
+                        repb.merge(CMP.compare_frame(c.frame_detections(resb, f), refd, p, where="case %d bayer frame %d" % (n, f)))
+                    except AssertionError as e:
+                        bad += 1
+                        print("MISMATCH bayer detect", dict(W=W, H=H, B=B, f=f, layout=layout, target=target, lb=prm.lower_bound), str(e)[:300])
             d_in.free(); d_out.free()
 print("fuzz: %d cases, %d mismatches, %d frames whose positive / armour counts differ (all inside the comparator's carve-outs)" % (cases, bad, soft))
 print("compared:", {k: getattr(rep, k) for k in ("frames", "contours", "fitted", "direct", "fallback", "rng_band", "near_gate", "degenerate", "blobs", "armours")},
       "worst centre / axis / angle / vertex:", rep.worst_centre, rep.worst_axis_rel, rep.worst_angle, rep.worst_vertex)
+print("bayer detect compared:", {k: getattr(repb, k) for k in ("frames", "contours", "fitted", "direct", "fallback", "rng_band", "near_gate", "degenerate", "blobs", "armours")})
 sys.exit(1 if bad else 0)
