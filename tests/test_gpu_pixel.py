@@ -1,5 +1,7 @@
 """GPU parity of the pixel stage (rm::extract_color up to the binary mask, src/imgproc.cpp:52-69) and of the Bayer
 front, through the C ABI, against the cv2 oracle.  Bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -9,6 +11,7 @@ from oracle import rm_oracle as O
 from rmcv_b200 import synth
 
 pytestmark = pytest.mark.gpu
+SEED_OFFSET = int(os.environ.get("RMCV_TEST_SEED", "0"))   # other random cases: RMCV_TEST_SEED=n pytest -m gpu ...
 
 
 def run_mask(ctx, frames, target, lb, pitch=None):
@@ -92,7 +95,7 @@ def test_random_noise_shapes(ctx, shape):
 
 
 def test_pitched_rows_and_unaligned(ctx):
-    rng = np.random.default_rng(7)
+    rng = np.random.default_rng(7 + SEED_OFFSET)
     frames = rng.integers(0, 256, (2, 40, 320, 3), dtype=np.uint8)
     check(ctx, frames, rb.CAMP_BLUE, 70, pitch=320 * 3 + 64, what="pitch +64 (16-B aligned rows, bulk per-row copies)")
     check(ctx, frames, rb.CAMP_BLUE, 70, pitch=320 * 3 + 7, what="pitch +7 (unaligned rows, generic loader)")
