@@ -6,11 +6,17 @@ reference pins `opencv4 >= 4.8.0#21`, vcpkg.json:26-33).  The reference's C++
 cannot be built in this image (no OpenCV C++ headers/libs), so every rm::
 function is restated line by line and the OpenCV calls are made through cv2.
 
-PARITY UNPINNED BY THE REFERENCE: /root/reference ships no tests, golden
-vectors or fixtures for this path.  What pins this oracle
-instead is (i) that its arithmetic *is* OpenCV's, the un-vendored dependency
-that holds all the arithmetic of the path, and (ii) the hand-checkable
-micro-masks and invariants in tests/test_oracle.py and tests/golden/.
+PINNING: /root/reference ships no tests, golden vectors or fixtures for this
+path, so the oracle is pinned against OUTPUTS OF THE
+REFERENCE ITSELF RUN HERE: oracle/_ref/librmcv_ref.so is the reference's own
+src/core.cpp, src/objdetect.cpp, src/imgproc.cpp, src/mobility.cpp compiled
+unmodified against a types-only OpenCV stub whose cv:: calls are served by
+this image's cv2 (oracle/Makefile, oracle/ref_bridge.py).  tests/test_ref_pin.py
+holds every rm:: restatement below bit-equal to that build (1e5 random boxes,
+1e5 pairs, whole synthetic frames, legacy/next rows), and tests/golden/*.json
+are that build's outputs ("source": "_ref").  What stays unpinnable: the
+OpenCV version (cv2 4.13.0 here vs the pinned >= 4.8.0) and the closed Daheng
+SDK behind the Bayer front (row a0).
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
 `--impl reference` legs may import this module.
