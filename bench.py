@@ -2,7 +2,7 @@
 """Benchmark of the rmcv detection hot path on B200 (BASELINE.json metric: frames/s @1280x1024 full detect).
 
     python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (cv2 oracle), host cores
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own C++ (oracle/_ref) on the host cores
 
 One "step" = one pass of the whole path (rm::extract_color -> rm::filter_lightblobs -> rm::filter_armours,
 executable/main.cpp:172-176) over one batch of synthetic 1280x1024 BGR frames per GPU.  Weak scaling: every rank owns
@@ -14,7 +14,9 @@ Prints ONE JSON line on rank 0 (see the contract in the task statement):
             library's streams, max over ranks), results written to pinned host memory inside the timed region
   e2e       frames/s through rmcv_detect_batch_host with HOST (pinned) buffers: H2D of the frames, kernels, results
   roofline  the pixel-stage kernel: algorithmic bytes (3 B/px read + 1 B/px mask written) / its CUDA-event duration
-  cpu_baseline  the cv2 oracle timed on this box's host cores on a bounded sample (reported baseline, not the target)
+  cpu_baseline  the reference's CPU path (oracle/_ref: its own rm:: C++ over this image's OpenCV) on this box's host cores,
+            one worker process per core, single-core and all-core figures (reported baseline, not the target)
+  strong    (N > 1) BASELINE config 3 as written: ONE 1024-frame batch cut into N contiguous slices, one per rank
 """
 from __future__ import annotations
 
@@ -128,21 +130,29 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_path_fps(frames, passes, threads):
-    """The reference's CPU path (cv2 oracle, oracle/rm_oracle.py) frame-parallel on `threads` host threads."""
-    import cv2
-    from oracle import rm_oracle as O
-    cv2.setNumThreads(1)
-    n = len(frames)
+def cpu_arm_measure(n_frames, procs, steps, warmup=1):
+    """The reference's CPU path on `procs` worker processes over frames of seeds 0..n_frames-1 (oracle/cpu_arm.py)."""
+    from oracle import cpu_arm
+    return cpu_arm.measure(n_frames, procs, steps, warmup)
 
-    def one(i):
-        fr = O.detect_frame(frames[i % n])
-        return len(fr.armours)
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        tot = sum(ex.map(one, range(passes)))
-    dt = time.perf_counter() - t0
-    return passes / dt, dt, tot
+
+def cpu_side_configs():
+    """Single-process CPU figures for BASELINE configs 2, 4, 5 + trampoline overhead, in a fresh interpreter."""
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "cpu_arm.py"), "--side-configs"], capture_output=True, text=True,
+                             timeout=300, cwd=ROOT)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
+def cpu_description(m, cores):
+    import cv2
+    what = ("the reference's own rm:: C++ (oracle/_ref: src/core.cpp, objdetect.cpp, imgproc.cpp compiled unmodified), its cv:: calls served "
+            f"by this image's OpenCV {cv2.__version__} through cv2" if m["kind"] == "reference" else f"Python port oracle/rm_oracle.py over cv2 {cv2.__version__}")
+    return (f"{m['frames_per_step']} synthetic 1280x1024 frames (seeds 0..{m['frames_per_step'] - 1}) x {m['steps']} steps, one worker process per core "
+            f"({m['procs']} of {cores} host threads, cv2.setNumThreads(1) each); {what}; {m['seconds']:.1f} s wall; "
+            f"OpenCV's share of the workers' busy time {100 * (m['opencv_share'] or 0):.0f} %")
 
 
 def run_reference(args):
@@ -150,25 +160,20 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = args.cpu_sample
-    frames = np.empty((n, H_, W_, 3), np.uint8)
-    make_frames(n, 0, frames)
-    for _ in range(args.warmup):
-        cpu_path_fps(frames, min(n, 2 * cores), cores)
-    times = []
-    for _ in range(args.steps):
-        fps, dt, _ = cpu_path_fps(frames, n, cores)
-        times.append(dt)
-    total = sum(times)
-    fps = n * args.steps / total
-    sample = f"{n} synthetic 1280x1024 frames per step, frame-parallel over {cores} host threads, cv2 {__import__('cv2').__version__} oracle"
+    n = args.batch
+    m = cpu_arm_measure(n, cores, args.steps, max(1, args.warmup))
+    single = cpu_arm_measure(min(n, 48), 1, 1, 1)
+    fps = m["fps"]
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * m["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload_name(n), "frames_per_step": n,
-                   "note": "reference CPU path = the cv2 oracle (same OpenCV kernels as the C++ reference, which cannot be built on this image: no OpenCV C++)"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(n), "frames_per_step": n, "frames_per_gpu": n,
+                   "note": "reference arm = the reference's CPU implementation of the path on the host cores; one step = the whole "
+                           f"{n}-frame batch of config 3, frame-parallel over all host threads (the reference itself is single-threaded, main.cpp:55)"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": m["kind"], "sample": cpu_description(m, cores),
+                         "single_core": {"value": single["fps"], "frames": single["frames_per_step"]},
+                         "scaling_vs_cores": fps / (single["fps"] * cores), "cv_calls_per_frame": m["cv_calls_per_frame"]},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -283,45 +288,99 @@ def run_gpu(args):
     frames_per_launch = B / n_chunks
     ach_pipe = ALG_BYTES_PER_FRAME * frames_per_launch / (pix_in_pipe_ms * 1e-3) / 1e9 if pix_in_pipe_ms > 0 else None
 
-    # ---- end to end through the host-buffer entry point (H2D + kernels + results), wall clock, max over ranks
-    for _ in range(2):
-        ctx.detect_batch_host(pinned.array, params)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        ctx.detect_batch_host(pinned.array, params)
-    e2e_ms = 1e3 * (time.perf_counter() - t0)
-    barrier()
-    e2e_max, e2e_units = shard.reduce_timing(e2e_ms, B * args.e2e_steps, dist, device=None if dist is None else f"cuda:{local_rank}")
-    e2e_value = e2e_units / (e2e_max * 1e-3)
-    d2h_bytes = 32 * B + 72 * n_contours + 56 * n_blobs + 112 * n_armours  # frame infos + dense records actually written
+    # ---- end to end through the host-buffer entry point: H2D of the frames, kernels, D2H of the masks (rm::extract_color
+    # returns `binary`, src/imgproc.cpp:74, and the caller uses it, main.cpp:200-204) and of the result records; wall
+    # clock, max over ranks.  The figure without the mask download is reported beside it.
+    h_masks = ctx.pinned((B, H_, W_))
+
+    def e2e_run(masks, steps):
+        for _ in range(2):
+            ctx.detect_batch_host(pinned.array, params, masks)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ctx.detect_batch_host(pinned.array, params, masks)
+        ms = 1e3 * (time.perf_counter() - t0)
+        barrier()
+        mx, units = shard.reduce_timing(ms, B * steps, dist, device=None if dist is None else f"cuda:{local_rank}")
+        return units / (mx * 1e-3)
+    e2e_value = e2e_run(h_masks.array, args.e2e_steps)
+    e2e_nomask = e2e_run(None, max(3, args.e2e_steps // 2))
+    rec_bytes = 32 * B + 72 * n_contours + 56 * n_blobs + 112 * n_armours  # frame infos + dense records actually written
+    d2h_bytes = rec_bytes + B * H_ * W_
+
+    # ---- BASELINE config 3 as written (N > 1): ONE 1024-frame batch cut into N contiguous slices, one per rank / GPU
+    strong = None
+    if world > 1:
+        lo, hi = shard.frame_slice(args.batch, world, rank)
+        nb = hi - lo
+        for _ in range(3):
+            ctx.detect_batch(d_frames.ptr, W_, H_, nb, params, d_mask.ptr); ctx.fetch_results()
+        barrier()
+        ctx.timer_start()
+        ctx.detect_batch(d_frames.ptr, W_, H_, nb, params, d_mask.ptr)
+        for _ in range(1, args.steps):
+            ctx.detect_batch(d_frames.ptr, W_, H_, nb, params, d_mask.ptr)
+            ctx.fetch_results()
+        ctx.fetch_results()
+        s_ms = ctx.timer_stop()
+        barrier()
+        s_max, s_units = shard.reduce_timing(s_ms, nb * args.steps, dist, device=f"cuda:{local_rank}")
+        for _ in range(2):
+            ctx.detect_batch_host(pinned.array[:nb], params, h_masks.array[:nb])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            ctx.detect_batch_host(pinned.array[:nb], params, h_masks.array[:nb])
+        se_ms = 1e3 * (time.perf_counter() - t0)
+        barrier()
+        se_max, se_units = shard.reduce_timing(se_ms, nb * args.e2e_steps, dist, device=f"cuda:{local_rank}")
+        strong = {"scaling": "strong", "frames_total": args.batch, "frames_per_gpu": nb, "value": s_units / (s_max * 1e-3), "unit": UNIT,
+                  "ms_per_step": s_max / args.steps, "e2e": se_units / (se_max * 1e-3),
+                  "note": "BASELINE config 3 as written: one batch of frames_total frames, contiguous slice per rank, device time max over ranks; "
+                          "a slice below one 592-frame chunk is one launch of each kernel per step"}
 
     # ---- extras on rank 0: BASELINE config 5 (batch-1 latency) and config 2 (Bayer pixel stage)
     extras = None
     if rank == 0 and not args.no_extras:
         extras = {}
         lat = []
-        n_lat = 2000
-        for i in range(200 + n_lat):
+        n_lat, n_warm = args.latency_frames, 1000
+        for i in range(n_warm + n_lat):
             t0 = time.perf_counter()
             ctx.detect_batch(d_frames.ptr + (i % B) * H_ * W_ * 3, W_, H_, 1, params, d_mask.ptr)
             ctx.fetch_results()
-            if i >= 200:
+            if i >= n_warm:
                 lat.append(1e6 * (time.perf_counter() - t0))
         lat.sort()
-        extras["latency_batch1"] = {"p50_us": lat[len(lat) // 2], "p99_us": lat[int(len(lat) * 0.99)], "frames": n_lat,
-                                    "what": "1280x1024 frame resident in HBM; enqueue (6 launches) -> results readable in pinned host memory; host wall clock"}
+        extras["latency_batch1"] = {"p50_us": lat[len(lat) // 2], "p99_us": lat[int(len(lat) * 0.99)], "frames": n_lat, "warmup_frames": n_warm,
+                                    "what": "stream of single 1280x1024 frames (seeds 0..B-1 round robin) resident in HBM; enqueue -> results readable in pinned host memory; host wall clock (BASELINE config 5)"}
+        lath = []
+        for i in range(200 + 2000):
+            t0 = time.perf_counter()
+            ctx.detect_batch_host(pinned.array[i % B:i % B + 1], params)
+            if i >= 200:
+                lath.append(1e6 * (time.perf_counter() - t0))
+        lath.sort()
+        extras["latency_batch1_from_host"] = {"p50_us": lath[len(lath) // 2], "p99_us": lath[int(len(lath) * 0.99)], "frames": len(lath),
+                                              "what": "the same from pinned host memory: H2D of 3.9 MB inside the timed region (rmcv_detect_batch_host)"}
         WB_, HB_, NB_ = 1440, 1080, 64
         raw = np.stack([synth.bgr_to_bayer(synth.make_frame(s, WB_, HB_, 10), synth.BAYER_BG) for s in range(8)] * (NB_ // 8))
         ctxb = rb.Context(max_width=WB_, max_height=HB_, max_batch=NB_, device=dev_index)
-        d_raw = ctxb.device_buffer(raw.nbytes); d_mb = ctxb.device_buffer(NB_ * HB_ * WB_)
-        d_raw.upload(raw)
+        # COLD measurement: four distinct input batches and four distinct mask buffers are rotated, so that between two uses
+        # of the same 199 MB working set 597 MB of other traffic has gone through the 126 MB L2 (an HBM number, not an L2 one)
+        n_rot = 4
+        d_raws = [ctxb.device_buffer(raw.nbytes) for _ in range(n_rot)]
+        d_mbs = [ctxb.device_buffer(NB_ * HB_ * WB_) for _ in range(n_rot)]
+        for k, d in enumerate(d_raws):
+            d.upload(np.roll(raw, k, axis=0))
+        d_raw, d_mb = d_raws[0], d_mbs[0]
         bms = []
         rep_b = 20   # launches per timed window (the event pair itself costs ~15 us of host enqueue time)
         for i in range(8):
             ctxb.timer_start()
-            for _ in range(rep_b):
-                ctxb.bayer_extract_color_batch(d_raw.ptr, WB_, HB_, NB_, synth.BAYER_BG, params.target, params.lower_bound, d_mb.ptr)
+            for r_ in range(rep_b):
+                ctxb.bayer_extract_color_batch(d_raws[r_ % n_rot].ptr, WB_, HB_, NB_, synth.BAYER_BG, params.target, params.lower_bound, d_mbs[r_ % n_rot].ptr)
             ms = ctxb.timer_stop() / rep_b
             if i >= 3:
                 bms.append(ms)
@@ -330,8 +389,10 @@ def run_gpu(args):
                                        "ms": bm, "algorithmic_bytes": NB_ * HB_ * WB_ * 2, "achieved_gbs": NB_ * HB_ * WB_ * 2 / (bm * 1e-3) / 1e9,
                                        "frac_of_peak": NB_ * HB_ * WB_ * 2 / (bm * 1e-3) / 1e9 / peak,
                                        "launches_per_timed_window": rep_b,
-                                       "note": "average launch duration over back-to-back launches; 199 MB working set, partly L2-resident between repetitions"}
-        d_raw.free(); d_mb.free(); ctxb.close()
+                                       "note": "average launch duration over back-to-back launches rotating 4 distinct 199 MB working sets (cold: every byte comes from / goes to HBM)"}
+        for d in d_raws + d_mbs:
+            d.free()
+        ctxb.close()
         # the whole path from raw Bayer frames at the size of config 3 (1024 x 1280x1024 mosaics, two calls in flight)
         WF_, HF_, NF_ = 1280, 1024, 1024
         rawf = np.stack([synth.bgr_to_bayer(pinned.array[i], synth.BAYER_BG) for i in range(64)] * (NF_ // 64))
@@ -351,6 +412,18 @@ def run_gpu(args):
                                        "ms_per_step": fms, "frames_per_s": NF_ / (fms * 1e-3), "blobs_per_frame": fres.total_blobs / NF_,
                                        "full_path_frac_of_hbm_peak": NF_ * HF_ * WF_ * 2 / (fms * 1e-3) / 1e9 / peak,
                                        "note": "2 B/px algorithmic (1 raw in, 1 mask out)"}
+        # the same from HOST mosaics (what the camera delivers): 1 B/px crosses PCIe instead of 3
+        p_raw = ctxf.pinned(rawf.shape); p_raw.array[:] = rawf
+        p_rm = ctxf.pinned(rawf.shape)
+        for _ in range(2):
+            ctxf.bayer_detect_batch_host(p_raw.array, synth.BAYER_BG, params, p_rm.array)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ctxf.bayer_detect_batch_host(p_raw.array, synth.BAYER_BG, params, p_rm.array)
+        bh_s = (time.perf_counter() - t0) / 5
+        extras["bayer_full_detect"]["e2e_from_host_frames_per_s"] = NF_ / bh_s
+        extras["bayer_full_detect"]["e2e_note"] = "rmcv_bayer_detect_batch_host: H2D of 1 B/px raw mosaics + kernels + D2H of masks and records, wall clock"
+        p_raw.free(); p_rm.free()
         d_rf.free(); d_mf.free(); ctxf.close()
         # BASELINE config 4: 4096x3072 stress frames (250 plates -> ~500 light blobs, ~125k pairs per frame), batch 16
         WS_, HS_, NS_ = 4096, 3072, 16
@@ -379,15 +452,35 @@ def run_gpu(args):
                                       "note": "two calls in flight; 4 B/px algorithmic (3 in, 1 mask out)"}
         d_sf.free(); d_sm.free(); ctxs.close()
 
+    # ---- the library's own partition of ONE host batch across every visible GPU (one process; rmcv_multi_*)
+    if extras is not None and world == 1:
+        try:
+            import ctypes as C_
+            nvis = C_.c_int(0)
+            rb.load_library().rmcv_device_count(C_.byref(nvis))
+            if nvis.value > 1:
+                with rb.MultiContext(None, max_width=W_, max_height=H_, max_batch=B) as mc:
+                    for _ in range(2):
+                        mc.detect_batch_host(pinned.array, params, h_masks.array)
+                    t0 = time.perf_counter()
+                    for _ in range(5):
+                        mc.detect_batch_host(pinned.array, params, h_masks.array)
+                    dt = (time.perf_counter() - t0) / 5
+                    extras["multi_gpu_one_process"] = {"devices": mc.n_devices, "frames": B, "e2e_frames_per_s": B / dt,
+                                                       "what": "rmcv_multi_detect_batch_host: one host batch, contiguous slice per device, one host thread + ctx per device"}
+        except Exception as e:  # noqa: BLE001
+            extras["multi_gpu_one_process"] = {"error": repr(e)}
+
     # ---- CPU baseline on rank 0 at N == 1
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        passes = args.cpu_sample
-        fps, dt, _ = cpu_path_fps(pinned.array[:min(B, 256)], passes, cores)
-        cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{passes} frame passes over the first {min(B, 256)} frames of the same batch, frame-parallel on {cores} host threads, "
-                         f"cv2 oracle (OpenCV {__import__('cv2').__version__}); {dt:.1f} s wall"}
+        m = cpu_arm_measure(B, cores, args.cpu_steps, 1)          # the same batch (seeds 0..B-1), all cores
+        single = cpu_arm_measure(min(B, 48), 1, 1, 1)             # one core, bounded sample
+        cpu = {"value": m["fps"], "unit": UNIT, "cores": cores, "kind": m["kind"], "sample": cpu_description(m, cores),
+               "single_core": {"value": single["fps"], "frames": single["frames_per_step"]},
+               "scaling_vs_cores": m["fps"] / (single["fps"] * cores), "cv_calls_per_frame": m["cv_calls_per_frame"],
+               "side_configs": cpu_side_configs()}
 
     if rank == 0:
         stage_ms = {k: v[0] / args.steps for k, v in prof.items()}
@@ -401,7 +494,9 @@ def run_gpu(args):
                        "steps_in_flight": 1 if args.no_pipeline else 2,
                        "contours_per_frame": n_contours / B, "blobs_per_frame": n_blobs / B, "armours_per_frame": n_armours / B},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * H_ * W_ * 3, "d2h_bytes_per_step": d2h_bytes,
-                    "steps": args.e2e_steps, "note": "rmcv_detect_batch_host from pinned host frames; wall clock; mask kept on device"},
+                    "steps": args.e2e_steps, "without_mask_download": e2e_nomask,
+                    "note": "rmcv_detect_batch_host from pinned host frames into pinned host masks + result records; wall clock, max over ranks"},
+            "strong": strong,
             "gpu_launches": tot_launches,
             "roofline": {"bound": "hbm", "achieved": ach_iso, "peak": peak, "unit": "GB/s", "frac": ach_iso / peak,
                          "traffic": ncu_traffic_per_launch(frames_per_launch),
@@ -422,7 +517,7 @@ def run_gpu(args):
             "frame_generation_s": t_gen,
         }
         emit(line)
-    pinned.free(); d_frames.free(); d_mask.free()
+    h_masks.free(); pinned.free(); d_frames.free(); d_mask.free()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -453,16 +548,13 @@ def main():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="frames per GPU per step")
     ap.add_argument("--chunk", type=int, default=0, help="frames per internal pipeline chunk (0 = library default)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="frame passes of the CPU baseline (0 = auto)")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-steps", type=int, default=2, help="steps of the cpu_baseline leg (each = the whole batch on all cores)")
+    ap.add_argument("--latency-frames", type=int, default=10000, help="timed frames of the batch-1 latency extra (config 5)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the latency (config 5) and Bayer (config 2) side measurements")
     ap.add_argument("--no-pipeline", action="store_true", help="fetch every step's results before enqueueing the next step")
     args = ap.parse_args()
-    cores = os.cpu_count() or 1
-    if args.cpu_sample <= 0:
-        # ~10-30 s of CPU work at ~6 ms per frame pass, at least 4 passes per core
-        args.cpu_sample = max(256, min(4096, 64 * cores)) if args.impl == "graft" else max(128, min(1024, 16 * cores))
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -221,6 +221,14 @@ int rmcv_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, si
                            uint8_t* h_mask, size_t mask_pitch, size_t mask_frame_stride,
                            rmcv_results* out);
 
+/* The same from raw 8-bit Bayer mosaics in HOST memory — what the camera actually delivers (hardware/src/daheng.cpp:
+ * 74-89: GXGetImage hands back the raw frame; DxRaw8toRGB24 at :136-151 is what this path replaces).  1 B/px crosses PCIe
+ * instead of 3.  Synchronous. */
+int rmcv_bayer_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_raw, size_t pitch, size_t frame_stride,
+                                 int width, int height, int batch, int bayer_layout, const rmcv_params* params,
+                                 uint8_t* h_mask, size_t mask_pitch, size_t mask_frame_stride,
+                                 rmcv_results* out);
+
 /* Waits for the oldest detect call whose results have not been fetched yet and exposes them
  * (with one call in flight: the last call).  Without an unfetched call it re-exposes the
  * results fetched last.  An unfetched call is dropped when a third call is enqueued. */
@@ -245,6 +253,30 @@ int rmcv_get_label_map(rmcv_ctx* ctx, int frame, int32_t* labels, size_t pitch_e
 /* Bit-packed mask (1 bit per pixel, LSB = lowest x, rows padded to 32-pixel words) of frame
  * `frame` of the last extract/detect call.  Host pointer, synchronous. */
 int rmcv_get_bitmask(rmcv_ctx* ctx, int frame, uint32_t* words, int words_per_row);
+
+/* ---- one batch across the GPUs of one box ------------------------------------ */
+/* The reference's only caller (executable/main.cpp:163-209) processes frames one after the other on one thread and keeps no
+ * cross-frame state, so a batch is partitioned BY FRAME: contiguous slices of batch / n_devices frames (+1 for the first
+ * batch % n_devices slices), slice g on
+ * device devices[g], one persistent host thread + one rmcv_ctx per device, no collective, results concatenated on the
+ * host in frame order (identical, byte for byte, to one device running the whole batch).
+ * cfg->max_batch is the largest WHOLE batch; cfg->device is ignored; devices == NULL with n_devices == 0 means every
+ * visible device.  For full upload bandwidth the frames should sit in pinned host memory (rmcv_host_alloc allocates it
+ * portable, i.e. usable from every device). */
+typedef struct rmcv_multi rmcv_multi;
+int rmcv_multi_create(const rmcv_config* cfg, const int* devices, int n_devices, rmcv_multi** out);
+int rmcv_multi_destroy(rmcv_multi* m);
+int rmcv_multi_device_count(const rmcv_multi* m);
+const char* rmcv_multi_last_error(const rmcv_multi* m);
+/* frames [*first, *first + *count) of a batch belong to device index g */
+void rmcv_multi_slice(int batch, int n_devices, int g, int* first, int* count);
+/* Synchronous.  Results (frame order, offsets into the merged dense arrays) stay valid until the next call on `m`. */
+int rmcv_multi_detect_batch_host(rmcv_multi* m, const uint8_t* h_bgr, size_t pitch, size_t frame_stride,
+                                 int width, int height, int batch, const rmcv_params* params,
+                                 uint8_t* h_mask, size_t mask_pitch, size_t mask_frame_stride, rmcv_results* out);
+int rmcv_multi_bayer_detect_batch_host(rmcv_multi* m, const uint8_t* h_raw, size_t pitch, size_t frame_stride,
+                                       int width, int height, int batch, int bayer_layout, const rmcv_params* params,
+                                       uint8_t* h_mask, size_t mask_pitch, size_t mask_frame_stride, rmcv_results* out);
 
 /* ---- a2/a3 standalone: rm::filter_lightblobs on caller-supplied contours --------------------- */
 /* xy = concatenated (x,y) int32 pairs, offsets[n_contours+1] in points.  Host pointers,

@@ -106,7 +106,23 @@ struct error : std::runtime_error {
     error(int s, const std::string& what) : std::runtime_error(what), status(s) {}
 };
 
-// Owns one rmcv_ctx sized for single-frame calls; grows on demand.
+// What rm::extract_color leaves behind for the two calls that follow it at the reference's call site
+// (executable/main.cpp:172-176): the device already ran the whole path on the frame, so rm::filter_lightblobs /
+// rm::filter_armours hand back those results when they are called with the very contours / light blobs the previous
+// call returned and with the parameters it ran with ("hidden handle").  Anything else — foreign contours,
+// other thresholds — goes through the standalone kernels.
+struct last_frame {
+    bool valid = false;
+    rmcv_params prm;                          // parameters the device ran with
+    std::vector<int32_t> xy, off;             // the contours handed to the caller (exact copy)
+    std::vector<rmcv_contour_info> infos;     // per contour: verdict, ellipse, blob index
+    std::vector<rmcv_lightblob> blobs;        // positives in contour order
+    std::vector<rmcv_armour> armours;
+    bool blobs_handed_out = false;            // filter_lightblobs returned `blobs` unchanged
+    long long reused_lightblobs = 0, reused_armours = 0;   // diagnostics (tests/cpp/call_site.cpp)
+};
+
+// Owns one rmcv_ctx sized for single-frame calls; grows on demand (frame size and per-frame capacities).
 class context {
    public:
     context() = default;
@@ -116,28 +132,53 @@ class context {
 
     rmcv_ctx* get(int width, int height) {
         if (!ctx_ || width > w_ || height > h_) {
-            if (ctx_) rmcv_ctx_destroy(ctx_);
-            ctx_ = nullptr;
-            rmcv_config cfg;
-            rmcv_default_config(&cfg);
             w_ = width > w_ ? width : w_;
             h_ = height > h_ ? height : h_;
-            cfg.max_width = w_ < 1280 ? 1280 : w_;
-            cfg.max_height = h_ < 1024 ? 1024 : h_;
-            cfg.max_batch = 1;
-            const int rc = rmcv_ctx_create(&cfg, &ctx_);
-            if (rc != RMCV_OK) throw error(rc, std::string("rmcv_ctx_create: ") + rmcv_status_string(rc) + " (no CPU fallback exists)");
-            w_ = cfg.max_width; h_ = cfg.max_height;
+            if (w_ < 1280) w_ = 1280;
+            if (h_ < 1024) h_ = 1024;
+            rebuild();
         }
         return ctx_;
     }
+    // A frame overflowed a per-frame capacity (RMCV_FRAME_OVERFLOW_*): double what overflowed and rebuild the ctx.
+    // false when the capacities are already at their ceilings (a frame cannot hold more runs than pixels / 2).
+    bool grow(int flags) {
+        const long long px = (long long)w_ * h_;
+        bool grew = false;
+        if (flags & (RMCV_FRAME_OVERFLOW_RUNS | RMCV_FRAME_OVERFLOW_POINTS)) {
+            long long cur = runs_ > 0 ? runs_ : (px / 32 > 16384 ? px / 32 : 16384);
+            if (cur < px / 2 + h_) { runs_ = (int)(cur * 4 < px / 2 + h_ ? cur * 4 : px / 2 + h_); grew = true; }
+        }
+        if (flags & RMCV_FRAME_OVERFLOW_BLOBS) {
+            const int cur = blobs_ > 0 ? blobs_ : 512;
+            if (cur < (1 << 15) - 1) { blobs_ = cur * 4 < (1 << 15) - 1 ? cur * 4 : (1 << 15) - 1; grew = true; }   // component ids are 16 bit
+        }
+        if (flags & RMCV_FRAME_OVERFLOW_ARMOURS) {
+            const int cur = armours_ > 0 ? armours_ : 1024;
+            if (cur < (1 << 22)) { armours_ = cur * 4; grew = true; }
+        }
+        if (grew) rebuild();
+        return grew;
+    }
+    last_frame last;
     void check(int rc, const char* where) {
         if (rc != RMCV_OK) throw error(rc, std::string(where) + ": " + rmcv_status_string(rc) + " - " + (ctx_ ? rmcv_last_error(ctx_) : ""));
     }
 
    private:
+    void rebuild() {
+        if (ctx_) rmcv_ctx_destroy(ctx_);
+        ctx_ = nullptr;
+        last.valid = false;
+        rmcv_config cfg;
+        rmcv_default_config(&cfg);
+        cfg.max_width = w_; cfg.max_height = h_; cfg.max_batch = 1;
+        cfg.max_runs_per_frame = runs_; cfg.max_blobs_per_frame = blobs_; cfg.max_armours_per_frame = armours_;
+        const int rc = rmcv_ctx_create(&cfg, &ctx_);
+        if (rc != RMCV_OK) throw error(rc, std::string("rmcv_ctx_create: ") + rmcv_status_string(rc) + " (no CPU fallback exists)");
+    }
     rmcv_ctx* ctx_ = nullptr;
-    int w_ = 0, h_ = 0;
+    int w_ = 0, h_ = 0, runs_ = 0, blobs_ = 0, armours_ = 0;
 };
 
 inline context& default_context() {
@@ -199,9 +240,21 @@ inline std::tuple<std::vector<contour>, cv::Mat> extract_color(cv::InputArray im
     prm.target = static_cast<int32_t>(target);
     prm.lower_bound = lower_bound;
     rmcv_results res;
-    int rc = rmcv_detect_batch_host(ctx, image.data, image.step, image.step * (size_t)image.rows, image.cols, image.rows, 1, &prm,
+    int rc = RMCV_OK;
+    for (;;) {
+        rc = rmcv_detect_batch_host(ctx, image.data, image.step, image.step * (size_t)image.rows, image.cols, image.rows, 1, &prm,
                                     binary.data, bstep, bstep * (size_t)image.rows, &res);
+        if (rc != RMCV_ERR_CAPACITY) break;
+        // The reference returns EVERY external contour (src/imgproc.cpp:71-72).  A frame that overflows the ctx's run /
+        // component / boundary-point capacities would come back truncated, so the ctx is rebuilt with larger ones and the
+        // frame runs again; an armour overflow does not touch the contours (filter_armours below re-runs those pairs).
+        const int flags = res.frames[0].flags;
+        if (!(flags & (RMCV_FRAME_OVERFLOW_RUNS | RMCV_FRAME_OVERFLOW_BLOBS | RMCV_FRAME_OVERFLOW_POINTS))) break;
+        if (!gc.grow(flags)) throw gpu::error(rc, "rm::extract_color: frame exceeds the largest per-frame capacities (contour list would be truncated)");
+        ctx = gc.get(image.cols, image.rows);
+    }
     if (rc != RMCV_OK && rc != RMCV_ERR_CAPACITY) gc.check(rc, "rmcv_detect_batch_host");
+    const bool armour_overflow = rc == RMCV_ERR_CAPACITY;
     int nc = 0, np = 0;
     rc = rmcv_get_contours(ctx, 0, nullptr, 0, nullptr, 0, &nc, &np);
     if (rc != RMCV_OK && rc != RMCV_ERR_CAPACITY) gc.check(rc, "rmcv_get_contours");
@@ -212,6 +265,17 @@ inline std::tuple<std::vector<contour>, cv::Mat> extract_color(cv::InputArray im
         contours[k].resize((size_t)(off[k + 1] - off[k]));
         for (int i = off[k]; i < off[k + 1]; ++i) { contours[k][i - off[k]].x = xy[2 * i]; contours[k][i - off[k]].y = xy[2 * i + 1]; }
     }
+    // keep what the device computed for this frame: the two calls that follow at the reference's call site reuse it
+    gpu::last_frame& lf = gc.last;
+    const rmcv_frame_info& fi = res.frames[0];
+    lf.prm = prm;
+    xy.resize((size_t)np * 2);
+    lf.xy.swap(xy); lf.off.swap(off);
+    lf.infos.assign(res.contours + fi.contour_offset, res.contours + fi.contour_offset + fi.n_contours);
+    lf.blobs.assign(res.blobs + fi.blob_offset, res.blobs + fi.blob_offset + fi.n_positive);
+    lf.armours.assign(res.armours + fi.armour_offset, res.armours + fi.armour_offset + fi.n_armours);
+    lf.blobs_handed_out = false;
+    lf.valid = !armour_overflow && (int)lf.infos.size() == nc;
     return {contours, binary};
 }
 
@@ -235,6 +299,23 @@ inline auto filter_lightblobs(const std::vector<contour>& contours, const float 
     prm.tilt_max = tilt_max;
     prm.ratio_min = ratio_range.lower_bound; prm.ratio_max = ratio_range.upper_bound;
     prm.area_min = area_range.lower_bound; prm.area_max = area_range.upper_bound;
+    {   // the contours rm::extract_color just returned, with the parameters the device ran with: its results are the answer
+        gpu::last_frame& lf = gc.last;
+        const size_t nxy = (size_t)off.back() * 2;
+        if (lf.valid && lf.off == off && lf.xy.size() == nxy && std::memcmp(lf.xy.data(), xy.data(), nxy * sizeof(int32_t)) == 0 &&
+            lf.prm.target == prm.target && lf.prm.tilt_max == prm.tilt_max && lf.prm.ratio_min == prm.ratio_min &&
+            lf.prm.ratio_max == prm.ratio_max && lf.prm.area_min == prm.area_min && lf.prm.area_max == prm.area_max) {
+            for (size_t k = 0; k < contours.size(); ++k) {
+                if (lf.infos[k].status == RMCV_CONTOUR_NEGATIVE) negative.push_back(contours[k]);                       // :82
+                else if (lf.infos[k].status == RMCV_CONTOUR_POSITIVE)
+                    positive.push_back(gpu::to_lightblob(lf.blobs[(size_t)lf.infos[k].blob_index], &lf.infos[k].ellipse));   // :83
+            }
+            lf.blobs_handed_out = true;
+            ++lf.reused_lightblobs;
+            return {positive, negative};
+        }
+        lf.blobs_handed_out = false;
+    }
     std::vector<rmcv_contour_info> infos(contours.size());
     std::vector<rmcv_lightblob> blobs(contours.size());
     int nb = 0;
@@ -262,12 +343,25 @@ inline std::vector<armour> filter_armours(std::vector<lightblob>& lightblobs, co
     prm.angle_difference_max = angle_difference_max; prm.shear_max = shear_max; prm.lenght_ratio_max = lenght_ratio_max;
     int cap = 256, n = 0;
     std::vector<rmcv_armour> out((size_t)cap);
-    int rc = rmcv_filter_armours(ctx, in.data(), (int)in.size(), &prm, out.data(), cap, &n);
-    if (rc == RMCV_ERR_CAPACITY) {
-        cap = n; out.resize((size_t)cap);
+    int rc = RMCV_OK;
+    gpu::last_frame& lf = gc.last;
+    // the light blobs rm::filter_lightblobs just handed out (field for field), with the pair parameters the device ran with
+    const bool reuse = lf.valid && lf.blobs_handed_out && lf.blobs.size() == in.size() && lf.prm.target == prm.target &&
+                       lf.prm.angle_difference_max == prm.angle_difference_max && lf.prm.shear_max == prm.shear_max &&
+                       lf.prm.lenght_ratio_max == prm.lenght_ratio_max &&
+                       std::memcmp(lf.blobs.data(), in.data(), in.size() * sizeof(rmcv_lightblob)) == 0;
+    if (reuse) {
+        out = lf.armours;
+        n = (int)out.size();
+        ++lf.reused_armours;
+    } else {
         rc = rmcv_filter_armours(ctx, in.data(), (int)in.size(), &prm, out.data(), cap, &n);
+        if (rc == RMCV_ERR_CAPACITY) {
+            cap = n; out.resize((size_t)cap);
+            rc = rmcv_filter_armours(ctx, in.data(), (int)in.size(), &prm, out.data(), cap, &n);
+        }
+        gc.check(rc, "rmcv_filter_armours");
     }
-    gc.check(rc, "rmcv_filter_armours");
     for (int k = 0; k < n; ++k) {
 #if defined(RMCV_SHIM_WITH_REFERENCE)
         armours.push_back(armour({lightblobs[out[k].i], lightblobs[out[k].j]}));  // the reference's own ctor, :161

@@ -65,12 +65,15 @@ struct rmcv_ref_arr {   // a dense 2-D array handed across the callback: rows x 
     void* data;
     int32_t rows, cols, type;
     int64_t step;
+    int64_t owner;      // out arrays: non-zero = the callee keeps `data` alive until rmcv_ref_release(owner) is called
 };
 // op: the cv:: function name.  in/out: arrays; params: scalar arguments.  The callee fills out[i].data with a pointer
 // that stays valid until the next call (the stub copies it).  Returns 0 on success.
 typedef int (*rmcv_ref_cvcall_t)(const char* op, const rmcv_ref_arr* in, int n_in, const double* params, int n_params,
                                  rmcv_ref_arr* out, int n_out);
+typedef void (*rmcv_ref_release_t)(int64_t owner);
 extern rmcv_ref_cvcall_t rmcv_ref_cvcall;
+extern rmcv_ref_release_t rmcv_ref_release;
 extern double rmcv_ref_tick_frequency;
 }
 
@@ -193,7 +196,9 @@ public:
     Mat() {}
     Mat(int r, int c, int type) { create(r, c, type); }
     Mat(Size s, int type) { create(s.height, s.width, type); }
-    Mat(int r, int c, int type, void* ext) { create(r, c, type); std::memcpy(data_ptr(), ext, (size_t)r * step_); }
+    Mat(int r, int c, int type, void* ext) {   // a header over the caller's buffer, like cv::Mat(rows, cols, type, data)
+        rows = r; cols = c; type_ = type; step_ = (int64_t)c * elem_size_of(type); ext_ = static_cast<uchar*>(ext);
+    }
     Mat(const MatExpr& e);
     template <typename T> Mat(const MatCommaInitializer_<T>& ci);
 
@@ -201,7 +206,7 @@ public:
         rows = r; cols = c; type_ = type;
         step_ = (int64_t)c * elem_size_of(type);
         buf_ = std::make_shared<std::vector<uchar>>((size_t)std::max<int64_t>(1, (int64_t)r * step_), (uchar)0);
-        off_ = 0;
+        off_ = 0; ext_ = nullptr; hold_.reset();
     }
     static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
     static Mat eye(int r, int c, int type) {
@@ -212,7 +217,7 @@ public:
     int type() const { return type_; }
     int depth() const { return CV_MAT_DEPTH(type_); }
     int channels() const { return CV_MAT_CN(type_); }
-    bool empty() const { return rows == 0 || cols == 0 || !buf_; }
+    bool empty() const { return rows == 0 || cols == 0 || (!buf_ && !ext_); }
     size_t total() const { return (size_t)rows * cols; }
     Size size() const { return Size(cols, rows); }
     int64_t step() const { return step_; }
@@ -241,7 +246,7 @@ public:
         return m;
     }
     void copyTo(Mat& dst) const {
-        if (dst.rows != rows || dst.cols != cols || dst.type_ != type_ || !dst.buf_) dst.create(rows, cols, type_);
+        if (dst.rows != rows || dst.cols != cols || dst.type_ != type_ || (!dst.buf_ && !dst.ext_)) dst.create(rows, cols, type_);
         for (int r = 0; r < rows; ++r) std::memcpy(dst.ptr(r), ptr(r), (size_t)cols * elem_size_of(type_));
     }
     void copyTo(const Mat& dst_view) const {   // cv::OutputArray built from a temporary header (a ROI)
@@ -282,12 +287,22 @@ public:
     }
     rmcv_ref_arr as_arr() const {
         rmcv_ref_arr a;
-        a.data = const_cast<uchar*>(data_ptr()); a.rows = rows; a.cols = cols; a.type = type_; a.step = step_;
+        a.data = const_cast<uchar*>(data_ptr()); a.rows = rows; a.cols = cols; a.type = type_; a.step = step_; a.owner = 0;
         return a;
     }
-    static Mat from_arr(const rmcv_ref_arr& a) {   // deep copy of a callback result
+    static Mat from_arr(const rmcv_ref_arr& a) {   // a callback result: adopted without a copy when the callee owns it
         Mat m;
-        if (a.rows <= 0 || a.cols <= 0 || a.data == nullptr) { m.type_ = a.type; return m; }
+        if (a.rows <= 0 || a.cols <= 0 || a.data == nullptr) {
+            m.type_ = a.type;
+            if (a.owner && rmcv_ref_release) rmcv_ref_release(a.owner);
+            return m;
+        }
+        if (a.owner && rmcv_ref_release) {   // like a cv::Mat the real function would have allocated: one buffer, no extra copy
+            m.rows = a.rows; m.cols = a.cols; m.type_ = a.type; m.step_ = a.step; m.ext_ = static_cast<uchar*>(a.data);
+            const int64_t owner = a.owner;
+            m.hold_ = std::shared_ptr<void>(nullptr, [owner](void*) { if (rmcv_ref_release) rmcv_ref_release(owner); });
+            return m;
+        }
         m.create(a.rows, a.cols, a.type);
         for (int r = 0; r < a.rows; ++r)
             std::memcpy(m.ptr(r), static_cast<const uchar*>(a.data) + (int64_t)r * a.step, (size_t)a.cols * elem_size_of(a.type));
@@ -295,8 +310,10 @@ public:
     }
 
 private:
-    uchar* data_ptr() const { return buf_ ? const_cast<uchar*>(buf_->data()) + off_ : nullptr; }
+    uchar* data_ptr() const { return ext_ ? ext_ + off_ : (buf_ ? const_cast<uchar*>(buf_->data()) + off_ : nullptr); }
     std::shared_ptr<std::vector<uchar>> buf_;
+    std::shared_ptr<void> hold_;   // keeps a callee-owned buffer (ext_) alive
+    uchar* ext_ = nullptr;
     int64_t off_ = 0, step_ = 0;
     int type_ = 0;
 };

@@ -26,6 +26,7 @@
 
 extern "C" {
 rmcv_ref_cvcall_t rmcv_ref_cvcall = nullptr;
+rmcv_ref_release_t rmcv_ref_release = nullptr;
 double rmcv_ref_tick_frequency = 1e9;   // cv::getTickFrequency() on Linux (std::chrono::steady_clock, ns)
 
 struct ref_blob {      // public fields of rm::lightblob (include/core.h:92-96); same layout as rmcv_lightblob
@@ -80,6 +81,7 @@ template <class F> int guarded(F&& f) {
 extern "C" {
 
 void rmcv_ref_set_callback(rmcv_ref_cvcall_t cb) { rmcv_ref_cvcall = cb; }
+void rmcv_ref_set_release(rmcv_ref_release_t cb) { rmcv_ref_release = cb; }
 void rmcv_ref_set_tick_frequency(double f) { rmcv_ref_tick_frequency = f; }
 const char* rmcv_ref_last_error() { return g_err.c_str(); }
 int rmcv_ref_with_math_h() {
@@ -232,6 +234,23 @@ int rmcv_ref_extract_color(const uint8_t* bgr, int rows, int cols, int channels,
             }
             off[k + 1] = at;
         }
+    });
+}
+
+// ---- the per-frame hot loop of the reference's only caller (executable/main.cpp:172-176): the three calls back to back
+// with that call site's argument order, results kept in C++ like process_function keeps them.  counts = {contours,
+// positive, negative, armours}.  This is what bench.py's CPU arm times (kind "reference").
+int rmcv_ref_process_frame(const uint8_t* bgr, int rows, int cols, int target, int lower_bound, float tilt_max, float ratio_min,
+                           float ratio_max, double area_min, double area_max, float angle_difference_max, float shear_max,
+                           float lenght_ratio_max, int32_t counts[4]) {
+    return guarded([&] {
+        cv::Mat img(rows, cols, CV_8UC3, const_cast<uint8_t*>(bgr));
+        auto [contours, binary] = rm::extract_color(img, (rm::camp)target, lower_bound);
+        auto [positive, negative] = rm::filter_lightblobs(contours, tilt_max, rm::range<float>(ratio_min, ratio_max),
+                                                          rm::range<double>(area_min, area_max), (rm::camp)target);
+        auto armours = rm::filter_armours(positive, angle_difference_max, shear_max, lenght_ratio_max, (rm::camp)target);
+        counts[0] = (int32_t)contours.size(); counts[1] = (int32_t)positive.size(); counts[2] = (int32_t)negative.size();
+        counts[3] = (int32_t)armours.size();
     });
 }
 

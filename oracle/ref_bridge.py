@@ -30,9 +30,11 @@ _DEPTH_OF = {np.dtype(v): k for k, v in _DEPTH.items()}
 
 
 class _Arr(C.Structure):
-    _fields_ = [("data", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32), ("type", C.c_int32), ("step", C.c_int64)]
+    _fields_ = [("data", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32), ("type", C.c_int32), ("step", C.c_int64),
+                ("owner", C.c_int64)]
 
 
+_REL = C.CFUNCTYPE(None, C.c_int64)
 _CB = C.CFUNCTYPE(C.c_int, C.c_char_p, C.POINTER(_Arr), C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(_Arr), C.c_int)
 
 
@@ -64,12 +66,15 @@ class RefLibrary:
         if not os.path.exists(path):
             raise FileNotFoundError(f"{path} missing: run `make -C oracle` where /root/reference exists")
         self.lib = C.CDLL(path)
-        self._keep: List[np.ndarray] = []
-        self._kf = None
+        self._owned = {}          # results the C++ side still references (released through _release)
+        self._next_owner = 1
         self._cb = _CB(self._cvcall)
+        self._rel = _REL(self._release)
         L = self.lib
         L.rmcv_ref_set_callback.argtypes = [_CB]
         L.rmcv_ref_set_callback(self._cb)
+        L.rmcv_ref_set_release.argtypes = [_REL]
+        L.rmcv_ref_set_release(self._rel)
         L.rmcv_ref_last_error.restype = C.c_char_p
         L.rmcv_ref_armour_new.restype = C.c_void_p
         L.rmcv_ref_armour_new.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int, C.c_longlong]
@@ -85,21 +90,30 @@ class RefLibrary:
             ins = [_to_np(ain[i]) for i in range(n_in)]
             p = [params[i] for i in range(n_params)]
             outs = self._dispatch(op.decode(), ins, p)
-            self._keep = []
             for i in range(n_out):
                 o = np.ascontiguousarray(outs[i])
                 if o.ndim == 1:
                     o = o.reshape(1, -1)
-                self._keep.append(o)
+                if op in (b"kalmanPredict", b"kalmanCorrect"):   # attributes of a cv2.KalmanFilter that dies with this call
+                    o = o.copy()
                 cn = 1 if o.ndim == 2 else o.shape[2]
                 aout[i].data = o.ctypes.data if o.size else None
                 aout[i].rows, aout[i].cols = (o.shape[0], o.shape[1]) if o.size else (0, 0)
                 aout[i].type = _DEPTH_OF[o.dtype] + ((cn - 1) << 3)
                 aout[i].step = o.strides[0] if o.size else 0
+                aout[i].owner = 0
+                if o.size:          # the stub adopts the buffer (no copy) and releases it when its cv::Mat dies
+                    owner = self._next_owner
+                    self._next_owner += 1
+                    self._owned[owner] = o
+                    aout[i].owner = owner
             return 0
         except Exception as e:  # noqa: BLE001 — reported through the C side as a failed call
             self._cb_error = repr(e)
             return 1
+
+    def _release(self, owner: int) -> None:
+        self._owned.pop(owner, None)
 
     def _dispatch(self, op: str, a: List[np.ndarray], p: List[float]):
         if op == "boxPoints":

@@ -5,7 +5,7 @@ The product is the CUDA library `librmcv_b200.so` behind the C ABI in include/rm
 Python host mirror used by the tests and the benchmark.  Nothing here computes on the CPU.
 """
 from . import _abi as abi
-from .api import (Armour, Context, Tracker, SvmModel, ContourInfo, FrameDetections, LightBlob, RmcvError, default_params, extract_color,
+from .api import (Armour, Context, MultiContext, Tracker, SvmModel, ContourInfo, FrameDetections, LightBlob, RmcvError, default_params, extract_color,
                   filter_armours, filter_lightblobs, lib_path, load_library)
 from ._abi import (BAYER_BG, BAYER_GB, BAYER_GR, BAYER_RG, CAMP_BLUE, CAMP_GUIDELIGHT, CAMP_NEUTRAL, CAMP_RED,
                    CONTOUR_NEGATIVE, CONTOUR_POSITIVE, CONTOUR_SKIPPED, FIT_DIRECT, FIT_FALLBACK, FIT_NONE)

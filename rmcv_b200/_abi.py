@@ -113,6 +113,17 @@ PROTOTYPES = {
     "rmcv_bayer_detect_batch": (C.c_int, [_vp, _u8p, _sz, _sz, _i, _i, _i, _i, C.POINTER(Params), _u8p, _sz, _sz]),
     "rmcv_detect_batch_host": (C.c_int, [_vp, _u8p, _sz, _sz, _i, _i, _i, C.POINTER(Params), _u8p, _sz, _sz,
                                          C.POINTER(Results)]),
+    "rmcv_bayer_detect_batch_host": (C.c_int, [_vp, _u8p, _sz, _sz, _i, _i, _i, _i, C.POINTER(Params), _u8p, _sz, _sz,
+                                               C.POINTER(Results)]),
+    "rmcv_multi_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_int), _i, C.POINTER(_vp)]),
+    "rmcv_multi_destroy": (C.c_int, [_vp]),
+    "rmcv_multi_device_count": (C.c_int, [_vp]),
+    "rmcv_multi_last_error": (C.c_char_p, [_vp]),
+    "rmcv_multi_slice": (None, [_i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rmcv_multi_detect_batch_host": (C.c_int, [_vp, _u8p, _sz, _sz, _i, _i, _i, C.POINTER(Params), _u8p, _sz, _sz,
+                                               C.POINTER(Results)]),
+    "rmcv_multi_bayer_detect_batch_host": (C.c_int, [_vp, _u8p, _sz, _sz, _i, _i, _i, _i, C.POINTER(Params), _u8p, _sz, _sz,
+                                                     C.POINTER(Results)]),
     "rmcv_fetch_results": (C.c_int, [_vp, C.POINTER(Results)]),
     "rmcv_get_contour": (C.c_int, [_vp, _i, _i, _vp, _i, C.POINTER(C.c_int)]),
     "rmcv_get_contours": (C.c_int, [_vp, _i, _vp, _i, _vp, _i, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

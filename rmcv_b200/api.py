@@ -329,6 +329,16 @@ class Context:
                                                     mptr, W, W * H, C.byref(res)), "rmcv_detect_batch_host")
         return res
 
+    def bayer_detect_batch_host(self, raw: np.ndarray, layout: int, params: A.Params, masks: Optional[np.ndarray] = None) -> A.Results:
+        """raw: B×H×W uint8 host mosaics (what the camera delivers, hardware/src/daheng.cpp:74-89); 1 B/px crosses PCIe."""
+        assert raw.dtype == np.uint8 and raw.ndim == 3 and raw.flags.c_contiguous
+        B, H, W = raw.shape
+        res = A.Results()
+        mptr = masks.ctypes.data if masks is not None else None
+        self._check(self.lib.rmcv_bayer_detect_batch_host(self.h, raw.ctypes.data, W, W * H, W, H, B, int(layout), C.byref(params),
+                                                          mptr, W, W * H, C.byref(res)), "rmcv_bayer_detect_batch_host")
+        return res
+
     # -- result helpers
     @staticmethod
     def frame_detections(res: A.Results, f: int) -> FrameDetections:
@@ -543,6 +553,68 @@ class Context:
                                             float(exact_size[0]), float(exact_size[1]), float(roi[0]), float(roi[1]),
                                             None if M is None else M.ctypes.data, out), "rmcv_solve_pnp")
         return [(np.array(o.rvec[:]), np.array(o.tvec[:]), np.array(o.position[:]), bool(o.ok)) for o in out]
+
+
+class MultiContext:
+    """rmcv_multi wrapper: ONE batch partitioned by frame across the GPUs of one box; one host thread and
+    one rmcv_ctx per device inside the library, no collective, results concatenated in frame order."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None, max_width=1280, max_height=1024, max_batch=64, chunk_frames=0,
+                 max_runs_per_frame=0, max_blobs_per_frame=0, max_armours_per_frame=0):
+        self.lib = load_library()
+        cfg = A.Config()
+        self.lib.rmcv_default_config(C.byref(cfg))
+        cfg.max_width, cfg.max_height, cfg.max_batch = max_width, max_height, max_batch
+        cfg.chunk_frames, cfg.max_runs_per_frame = chunk_frames, max_runs_per_frame
+        cfg.max_blobs_per_frame, cfg.max_armours_per_frame = max_blobs_per_frame, max_armours_per_frame
+        h = C.c_void_p()
+        n = len(devices) if devices is not None else 0
+        arr = (C.c_int * max(1, n))(*(devices or [0]))
+        rc = self.lib.rmcv_multi_create(C.byref(cfg), arr if devices is not None else None, n, C.byref(h))
+        if rc != A.RMCV_OK:
+            raise RmcvError(rc, "rmcv_multi_create", "(is a CUDA device present? this library has no CPU path)")
+        self.h = h
+        self.n_devices = int(self.lib.rmcv_multi_device_count(self.h))
+
+    def _check(self, rc: int, where: str):
+        if rc != A.RMCV_OK:
+            raise RmcvError(rc, where, self.lib.rmcv_multi_last_error(self.h).decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rmcv_multi_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def slice(self, batch: int, g: int) -> Tuple[int, int]:
+        first, count = C.c_int(0), C.c_int(0)
+        self.lib.rmcv_multi_slice(int(batch), self.n_devices, int(g), C.byref(first), C.byref(count))
+        return first.value, count.value
+
+    def detect_batch_host(self, frames: np.ndarray, params: A.Params, masks: Optional[np.ndarray] = None) -> A.Results:
+        assert frames.dtype == np.uint8 and frames.ndim == 4 and frames.shape[3] == 3 and frames.flags.c_contiguous
+        B, H, W, _ = frames.shape
+        res = A.Results()
+        mptr = masks.ctypes.data if masks is not None else None
+        self._check(self.lib.rmcv_multi_detect_batch_host(self.h, frames.ctypes.data, W * 3, W * 3 * H, W, H, B, C.byref(params),
+                                                          mptr, W, W * H, C.byref(res)), "rmcv_multi_detect_batch_host")
+        return res
+
+    def bayer_detect_batch_host(self, raw: np.ndarray, layout: int, params: A.Params, masks: Optional[np.ndarray] = None) -> A.Results:
+        assert raw.dtype == np.uint8 and raw.ndim == 3 and raw.flags.c_contiguous
+        B, H, W = raw.shape
+        res = A.Results()
+        mptr = masks.ctypes.data if masks is not None else None
+        self._check(self.lib.rmcv_multi_bayer_detect_batch_host(self.h, raw.ctypes.data, W, W * H, W, H, B, int(layout), C.byref(params),
+                                                                mptr, W, W * H, C.byref(res)), "rmcv_multi_bayer_detect_batch_host")
+        return res
+
+    frame_detections = staticmethod(Context.frame_detections)
 
 
 class SvmModel:

@@ -11,6 +11,10 @@
 
 using namespace rmcv;
 
+namespace rmcv {
+const Tuning& tuning();
+}
+
 namespace {
 
 struct ProfSet {      // events of one chunk: pixel begin/end on the pixel stream, one mark per labelling stage on its stream
@@ -58,6 +62,25 @@ struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
 };
 
 CtxExtra* extra(rmcv_ctx* c) { return static_cast<CtxExtra*>(c->extra); }
+
+int env_or(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+Tuning read_tuning() {
+    Tuning t;
+    t.slots = env_or("RMCV_SLOTS", -1); t.prio = env_or("RMCV_PRIO", -1); t.serial = env_or("RMCV_SERIAL", -1) > 0 ? 1 : 0;
+    t.lab_streams = env_or("RMCV_LAB_STREAMS", -1);
+    t.small_batch = env_or("RMCV_SMALL_BATCH", -1); t.frame_rs = env_or("RMCV_FRAME_RS", -1);
+    t.label_minsmem = env_or("RMCV_LABEL_MINSMEM", -1); t.label_small = env_or("RMCV_LABEL_SMALL", -1) > 0 ? 1 : 0;
+    t.contour_gy = env_or("RMCV_CONTOUR_GY", -1); t.emit_bh = env_or("RMCV_EMIT_BH", -1);
+    t.pix_bh = env_or("RMCV_PIX_BH", -1); t.pix_rc = env_or("RMCV_PIX_RC", -1); t.pix_s = env_or("RMCV_PIX_S", -1);
+    t.pix_nt = env_or("RMCV_PIX_NT", -1); t.pix_nobulk = env_or("RMCV_PIX_NOBULK", 0); t.pix_generic = env_or("RMCV_PIX_GENERIC", 0);
+    t.bgr_strip = env_or("RMCV_BGR_STRIP", 0); t.bandstrip_rc = env_or("RMCV_BANDSTRIP_RC", -1);
+    t.bayer_generic = env_or("RMCV_BAYER_GENERIC", 0); t.strip_seg = env_or("RMCV_STRIP_SEG", -1); t.strip_minb = env_or("RMCV_STRIP_MINB", -1);
+    t.fused_emit = env_or("RMCV_FUSED_EMIT", -1); t.wide_label = env_or("RMCV_WIDE_LABEL", -1); t.graph = env_or("RMCV_GRAPH", -1);
+    return t;
+}
 
 template <class T>
 cudaError_t dalloc(T** p, size_t count) { return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)); }
@@ -308,6 +331,12 @@ int fetch_oldest(rmcv_ctx* ctx, rmcv_results* out) {
     RMCV_CUDA(ctx, cudaEventSynchronize(r.done[1]));
     r.pending = false;
     ex->last_fetched = pick;
+    // profiling events of finished chunks are collected here too: an async detect/fetch loop never reaches sync_all, and
+    // without this the event pool would grow with every call
+    bool any_pending = false;
+    for (int i = 0; i < 2; ++i) any_pending |= ex->rs[i].pending;
+    if (ctx->profiling && !any_pending) prof_collect(ctx);
+    else if (ctx->profiling && ex->prof_used > 4096) { ex->prof_used = 0; }   // bounded: drop the oldest marks
     return fill_results(ctx, r, out);
 }
 
@@ -321,6 +350,13 @@ SlotBuffers* resident_slot(rmcv_ctx* ctx, int frame, int* local) {
 }
 
 }  // namespace
+
+namespace rmcv {
+const Tuning& tuning() {
+    static const Tuning t = read_tuning();   // thread-safe one-time initialisation
+    return t;
+}
+}  // namespace rmcv
 
 // =============================================================================================== ABI
 extern "C" {
@@ -373,6 +409,8 @@ int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
     ctx->cfg = *cfg;
     ctx->device = cfg->device;
     ctx->extra = new (std::nothrow) CtxExtra();
+    if (!ctx->extra) { free(ctx); return RMCV_ERR_INVALID_ARG; }
+    const Tuning& tune = tuning();
     auto fail = [&](int code) {
         static thread_local char keep[512];
         snprintf(keep, sizeof(keep), "%s", ctx->err);
@@ -408,30 +446,26 @@ int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
     if (CF > cfg->max_batch) CF = cfg->max_batch;
     ctx->CF = CF;
     {
-        const char* es = getenv("RMCV_SLOTS");
-        int ns = es ? atoi(es) : 3;
+        const int ns = tune.slots > 0 ? tune.slots : 3;
         ctx->n_slots = ns < 2 ? 2 : (ns > kSlots ? kSlots : ns);
     }
     {
         CtxExtra* ex = extra(ctx);
         int least = 0, greatest = 0;
         cudaDeviceGetStreamPriorityRange(&least, &greatest);
-        if (const char* pe = getenv("RMCV_PRIO")) {   // experiment: 1 = equal priorities, 2 = pixel stream first
-            if (atoi(pe) == 1) greatest = least;
-            else if (atoi(pe) == 2) { const int t = least; least = greatest; greatest = t; }
-        }
+        if (tune.prio == 1) greatest = least;          // experiment: 1 = equal priorities, 2 = pixel stream first
+        else if (tune.prio == 2) { const int t = least; least = greatest; greatest = t; }
         cudaError_t se = cudaSuccess;
         if (cfg->stream) { ex->pix = reinterpret_cast<cudaStream_t>(cfg->stream); ex->own_pix = false; }
         else { se = cudaStreamCreateWithPriority(&ex->pix, cudaStreamNonBlocking, least); ex->own_pix = true; }
-        if (getenv("RMCV_SERIAL")) {   // debug aid: every kernel on one stream
+        if (tune.serial) {   // debug aid: every kernel on one stream
             ex->lab = ex->pix; ex->out = ex->pix;
             for (int i = 0; i < kSlots; ++i) ex->labs[i] = ex->pix;
         } else {
             if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&ex->lab, cudaStreamNonBlocking, greatest);
             ex->labs[0] = ex->lab;
-            const char* e1 = getenv("RMCV_LAB_STREAMS");   // 1: all slots share one labelling stream (experiments)
             for (int i = 1; i < kSlots; ++i) {
-                if (e1 && atoi(e1) == 1) ex->labs[i] = ex->lab;
+                if (tune.lab_streams == 1) ex->labs[i] = ex->lab;   // all slots share one labelling stream (experiments)
                 else if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&ex->labs[i], cudaStreamNonBlocking, greatest);
             }
             if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&ex->out, cudaStreamNonBlocking, greatest);
@@ -598,14 +632,17 @@ int rmcv_bayer_detect_batch(rmcv_ctx* ctx, const uint8_t* d_raw, size_t pitch, s
                             mask_frame_stride, true);
 }
 
-int rmcv_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, size_t frame_stride, int width, int height,
-                           int batch, const rmcv_params* params, uint8_t* h_mask, size_t mask_pitch, size_t mask_frame_stride,
-                           rmcv_results* out) {
+// Host-buffer entry points: frames are staged chunk by chunk (upload on the copy stream, kernels, mask download), so the
+// copies of one chunk overlap the kernels of the other.  bayer_layout == 0: interleaved BGR, else a raw 8-bit mosaic.
+static int run_host_batch(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, size_t frame_stride, int width, int height,
+                          int batch, int bayer_layout, const rmcv_params* params, uint8_t* h_mask, size_t mask_pitch,
+                          size_t mask_frame_stride, rmcv_results* out) {
     if (!ctx || !params || !h_bgr) return RMCV_ERR_INVALID_ARG;
     int rc = check_geometry(ctx, width, height, batch);
     if (rc != RMCV_OK) return rc;
-    const size_t rowbytes = (size_t)width * 3;
+    const size_t rowbytes = bayer_layout ? (size_t)width : (size_t)width * 3;
     if (pitch < rowbytes) return set_err(ctx, RMCV_ERR_INVALID_ARG, "pitch smaller than a row");
+    if (h_mask && mask_pitch < (size_t)width) return set_err(ctx, RMCV_ERR_INVALID_ARG, "mask pitch smaller than a row");
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
     begin_call(ctx);
     const int CF = ctx->CF;
@@ -615,18 +652,19 @@ int rmcv_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, si
     for (int f0 = 0; f0 < batch; f0 += CF, ++nchunks) {
         SlotBuffers& sb = ctx->slot[extra(ctx)->chunk_counter++ % ctx->n_slots];
         const int frames = batch - f0 < CF ? batch - f0 : CF;
-        const size_t need = (size_t)CF * (size_t)ctx->cfg.max_height * ctx->cfg.max_width * 3;
+        const size_t need_px = (size_t)CF * (size_t)ctx->cfg.max_height * ctx->cfg.max_width;
+        const size_t need = bayer_layout ? need_px : need_px * 3;   // a ctx that only ever sees mosaics stages 1 B/px
         if (sb.frames_bytes < need) {
             if (sb.frames) cudaFree(sb.frames);
             sb.frames = nullptr; sb.frames_bytes = 0;
             RMCV_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&sb.frames), need));
             sb.frames_bytes = need;
         }
-        if (h_mask && sb.masks_bytes < need / 3) {
+        if (h_mask && sb.masks_bytes < need_px) {
             if (sb.masks) cudaFree(sb.masks);
             sb.masks = nullptr; sb.masks_bytes = 0;
-            RMCV_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&sb.masks), need / 3));
-            sb.masks_bytes = need / 3;
+            RMCV_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&sb.masks), need_px));
+            sb.masks_bytes = need_px;
         }
         const uint8_t* hsrc = h_bgr + (size_t)f0 * frame_stride;
         CtxExtra* ex = extra(ctx);
@@ -641,7 +679,7 @@ int rmcv_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, si
         }
         RMCV_CUDA(ctx, cudaEventRecord(sb.ev_h2d, ex->h2d));
         RMCV_CUDA(ctx, cudaStreamWaitEvent(ex->pix, sb.ev_h2d, 0));
-        rc = enqueue_chunk(ctx, sb, sb.frames, rowbytes, dev_frame, width, height, frames, f0, 0, *params,
+        rc = enqueue_chunk(ctx, sb, sb.frames, rowbytes, dev_frame, width, height, frames, f0, bayer_layout, *params,
                            h_mask ? sb.masks : nullptr, width, dev_mask, true);
         if (rc != RMCV_OK) return rc;
         if (h_mask) {
@@ -669,6 +707,22 @@ int rmcv_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, si
     extra(ctx)->rs[set].pending = false;
     extra(ctx)->last_fetched = set;
     return fill_results(ctx, extra(ctx)->rs[set], out);
+}
+
+int rmcv_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, size_t frame_stride, int width, int height,
+                           int batch, const rmcv_params* params, uint8_t* h_mask, size_t mask_pitch, size_t mask_frame_stride,
+                           rmcv_results* out) {
+    return run_host_batch(ctx, h_bgr, pitch, frame_stride, width, height, batch, 0, params, h_mask, mask_pitch, mask_frame_stride, out);
+}
+
+int rmcv_bayer_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_raw, size_t pitch, size_t frame_stride, int width, int height,
+                                 int batch, int bayer_layout, const rmcv_params* params, uint8_t* h_mask, size_t mask_pitch,
+                                 size_t mask_frame_stride, rmcv_results* out) {
+    if (!ctx) return RMCV_ERR_INVALID_ARG;
+    if (bayer_layout < RMCV_BAYER_RG || bayer_layout > RMCV_BAYER_BG) return set_err(ctx, RMCV_ERR_INVALID_ARG, "bad bayer layout");
+    if (width < 3 || height < 3) return set_err(ctx, RMCV_ERR_INVALID_ARG, "bayer frames must be at least 3x3");
+    return run_host_batch(ctx, h_raw, pitch, frame_stride, width, height, batch, bayer_layout, params, h_mask, mask_pitch,
+                          mask_frame_stride, out);
 }
 
 int rmcv_fetch_results(rmcv_ctx* ctx, rmcv_results* out) {
@@ -788,11 +842,20 @@ int rmcv_get_bitmask(rmcv_ctx* ctx, int frame, uint32_t* words, int words_per_ro
     return RMCV_OK;
 }
 
+// offsets of caller-supplied contours: offsets[0] == 0, non-decreasing (the kernels index xy and their scratch with them)
+static int check_offsets(rmcv_ctx* ctx, const int32_t* offsets, int n) {
+    if (offsets[0] != 0) return set_err(ctx, RMCV_ERR_INVALID_ARG, "contour offsets must start at 0");
+    for (int k = 0; k < n; ++k)
+        if (offsets[k + 1] < offsets[k]) return set_err(ctx, RMCV_ERR_INVALID_ARG, "contour offsets must be non-decreasing");
+    return RMCV_OK;
+}
+
 int rmcv_filter_lightblobs(rmcv_ctx* ctx, const int32_t* xy, const int32_t* offsets, int n_contours, const rmcv_params* params,
                            rmcv_contour_info* infos, rmcv_lightblob* blobs, int blob_cap, int* n_blobs) {
     if (!ctx || !params || !offsets || n_contours < 0 || !n_blobs || (n_contours > 0 && !infos)) return RMCV_ERR_INVALID_ARG;
     *n_blobs = 0;
     if (n_contours == 0) return RMCV_OK;
+    if (int orc = check_offsets(ctx, offsets, n_contours)) return orc;
     const size_t npts = (size_t)offsets[n_contours];
     if (npts > 0 && !xy) return RMCV_ERR_INVALID_ARG;
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -879,6 +942,7 @@ static int run_legacy(rmcv_ctx* ctx, const int32_t* xy, const int32_t* offsets, 
                       int width, int height, int32_t* matched, rmcv_rotated_rect* boxes, int32_t* camps, rmcv_lightblob* blobs) {
     if (!ctx || !offsets || n < 0) return RMCV_ERR_INVALID_ARG;
     if (n == 0) return RMCV_OK;
+    if (int orc = check_offsets(ctx, offsets, n)) return orc;
     const size_t npts = (size_t)offsets[n];
     if (npts > 0 && !xy) return RMCV_ERR_INVALID_ARG;
     if (h_src && (width <= 0 || height <= 0 || pitch < (size_t)width * 3)) return set_err(ctx, RMCV_ERR_INVALID_ARG, "bad source image geometry");

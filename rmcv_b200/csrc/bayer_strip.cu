@@ -253,10 +253,8 @@ cudaError_t launch_bayer_strip(const PixelLaunch& L, int sm_count, cudaStream_t 
     // segment height: tall segments amortise the six halo rows, but the warps of a launch should fill whole waves of the
     // resident warp slots (3 CTAs of 8 warps per SM): pick the even height with the least waves x (rows + halo)
     int seg = 0;
-    const char* eb1 = getenv("RMCV_STRIP_MINB");
-    const int eb0 = eb1 ? atoi(eb1) : 3;
-    const char* es = getenv("RMCV_STRIP_SEG");
-    if (es && atoi(es) > 0) seg = atoi(es) & ~1;
+    const int eb0 = tuning().strip_minb > 0 ? tuning().strip_minb : 3;
+    if (tuning().strip_seg > 0) seg = tuning().strip_seg & ~1;
     else {
         const long long slots = (eb0 >= 4 ? 32LL : 24LL) * sm_count;
         long long best = -1;
@@ -286,8 +284,7 @@ cudaError_t launch_bayer_strip(const PixelLaunch& L, int sm_count, cudaStream_t 
     const int wpb = 8;
     const unsigned grid = (unsigned)((total + wpb - 1) / wpb);
     const int which = (py * 2 + px) * 2 + (L.mask ? 1 : 0);
-    const char* eb = getenv("RMCV_STRIP_MINB");
-    const int minb = eb ? atoi(eb) : 3;
+    const int minb = eb0;
 #define RMCV_STRIP_CASE(n, PY_, PX_, M_)                                                                     \
     case n:                                                                                                  \
         if (minb >= 4) bayer_strip_kernel<PY_, PX_, M_, 4><<<grid, wpb * 32, 0, st>>>(p);                    \

@@ -178,8 +178,7 @@ cudaError_t launch_bgr_bandstrip(const PixelLaunch& L, int sm_count, cudaStream_
         else if (L.lower_bound > 255) { for (int i = 0; i < 6; ++i) p.coef[i] = 0; p.acc0 = -1; }
         else p.acc0 = -L.lower_bound;
     }
-    const char* erc = getenv("RMCV_BANDSTRIP_RC");
-    p.rc = erc ? atoi(erc) : 2;
+    p.rc = tuning().bandstrip_rc > 0 ? tuning().bandstrip_rc : 2;
     if (p.rc < 1) p.rc = 1;
     p.frame_stage_bytes = (uint32_t)p.rc * (uint32_t)L.W * 3u;
     p.stage_bytes = (uint32_t)p.fpc * p.frame_stage_bytes;

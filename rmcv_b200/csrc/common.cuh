@@ -234,6 +234,17 @@ cudaError_t launch_track_update(rmcv_track* d_tracks, int32_t* d_n_tracks, int c
                                 const double* d_positions, const int32_t* d_identities, int n, int32_t* d_remaining, long long timestamp,
                                 double freq, double q, double r, double err, int32_t* d_status, cudaStream_t st, int64_t* launches);
 
-void upload_luts();  // copies the arc LUT to constant memory (once per process/device)
+void upload_luts();
+
+// Tuning knobs for experiments and debugging.  The environment is read ONCE per process — when the first
+// ctx is created — and never on a launch path; -1 = not set (the launcher's own default applies).
+struct Tuning {
+    int slots, prio, serial, lab_streams;                            // ctx: scratch slots, stream priorities, one stream
+    int small_batch, frame_rs, label_minsmem, label_small, contour_gy, emit_bh;   // labelling stages
+    int pix_bh, pix_rc, pix_s, pix_nt, pix_nobulk, pix_generic;      // BGR band kernel geometry
+    int bgr_strip, bandstrip_rc, bayer_generic, strip_seg, strip_minb;   // alternative pixel kernels
+    int fused_emit, wide_label, graph;                               // round-2 paths (emit inside the pixel kernel, ...)
+};
+const Tuning& tuning();  // copies the arc LUT to constant memory (once per process/device)
 
 }  // namespace rmcv

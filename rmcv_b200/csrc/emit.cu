@@ -239,8 +239,7 @@ cudaError_t launch_emit(const EmitLaunch& L, cudaStream_t st, int64_t* launches)
     // indices within 16 bits; taller bands amortise the scan / claim / row-table steps
     const int bh_max = 4096 / p.WB - 2;
     int BH = 32;
-    const char* env = getenv("RMCV_EMIT_BH");
-    if (env) BH = atoi(env);
+    if (tuning().emit_bh > 0) BH = tuning().emit_bh;
     if (BH > bh_max) BH = bh_max;
     if (BH < 1) BH = 1;
     if (BH > L.H) BH = L.H;

@@ -861,8 +861,8 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
                           void (*stage_done)(void*, int, cudaStream_t), void* stage_arg) {
     cudaError_t e;
     auto done = [&](int stage) { if (stage_done) stage_done(stage_arg, stage, st); };
-    const char* esb = getenv("RMCV_SMALL_BATCH");
-    const int small_batch = esb ? atoi(esb) : 16;   // at most this many frames: per-frame kernels take their wide variants
+    const Tuning& tune = tuning();
+    const int small_batch = tune.small_batch >= 0 ? tune.small_batch : 16;   // at most this many frames: per-frame kernels take their wide variants
     {   // K_E
         EmitLaunch el;
         el.bits = L.sb->bits; el.W = L.g.W; el.H = L.g.H; el.batch = L.frames;
@@ -875,20 +875,19 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
     {   // K_L
         LabelParams p;
         p.g = L.g; p.sb = *L.sb;
-        const char* env = getenv("RMCV_FRAME_RS");
-        int Rs = env ? atoi(env) : 3072;  // four CTAs per SM at 1280x1024 (gpurun_out/exp_rs*.json)
+        int Rs = tune.frame_rs >= 0 ? tune.frame_rs : 3072;  // four CTAs per SM at 1280x1024 (gpurun_out/exp_rs*.json)
         if (Rs > L.g.R) Rs = L.g.R;
         size_t smem = label_smem_bytes(L.g.H, Rs, L.g.C);
         while (smem > (size_t)max_smem_optin && Rs > 0) { Rs = Rs > 1024 ? Rs - 1024 : 0; smem = label_smem_bytes(L.g.H, Rs, L.g.C); }
         if (smem > (size_t)max_smem_optin) return cudaErrorInvalidConfiguration;
         p.Rs = Rs;
-        if (const char* pad = getenv("RMCV_LABEL_MINSMEM")) {   // experiment: cap the CTAs per SM by padding shared memory
-            const size_t m = (size_t)atoi(pad);
+        if (tune.label_minsmem > 0) {   // experiment: cap the CTAs per SM by padding shared memory
+            const size_t m = (size_t)tune.label_minsmem;
             if (m > smem && m <= (size_t)max_smem_optin) smem = m;
         }
         // 1024 threads: frames whose runs stay in global memory (run indices beyond 16 bits), and small batches, where a
         // frame's latency matters and the SMs are idle anyway
-        const bool big = (L.g.R > 65535 || L.frames <= small_batch) && !getenv("RMCV_LABEL_SMALL");
+        const bool big = (L.g.R > 65535 || L.frames <= small_batch) && !tune.label_small;
         if (big) {
             e = cudaFuncSetAttribute(label_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
@@ -905,8 +904,7 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
     {   // K_C
         ContourParams p;
         p.g = L.g; p.sb = *L.sb; p.prm = prm;
-        const char* env = getenv("RMCV_CONTOUR_GY");
-        int gy = env ? atoi(env) : 8;                      // 8 blocks x 4 warps per frame
+        int gy = tune.contour_gy > 0 ? tune.contour_gy : 8;                      // 8 blocks x 4 warps per frame
         if (gy * 4 > L.g.C) gy = (L.g.C + 3) / 4;
         if (gy < 1) gy = 1;
         dim3 grid(L.frames, gy);
@@ -946,8 +944,6 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
             if (e != cudaSuccess) return e;
         }
         p.defer_copy = (L.g.R > 65535 || L.g.C > 512) ? 1 : 0;
-        static const int exp_nocopy = getenv("RMCV_EXP_NOCOPY") ? atoi(getenv("RMCV_EXP_NOCOPY")) : 0;   // experiment only: records not posted
-        if (exp_nocopy) p.defer_copy = 2;
         if (big) order_kernel<512><<<L.frames, 512, smem, so>>>(p);
         else order_kernel<128><<<L.frames, 128, smem, so>>>(p);
         if (p.defer_copy == 1) {

@@ -493,11 +493,6 @@ __global__ void __launch_bounds__(512) pixel_bayer_kernel(const PixelParams p, c
 }
 
 // ------------------------------------------------------------------------------------------ host launcher
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
-
 cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t st, int64_t* launches) {
     PixelParams p;
     memset(&p, 0, sizeof(p));
@@ -518,7 +513,8 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
     }
 
     // band height: tall bands amortise the 4 halo rows; small batches need more, shorter bands to fill 148 SMs
-    int BH = env_int("RMCV_PIX_BH", 0);
+    const Tuning& tune = tuning();
+    int BH = tune.pix_bh > 0 ? tune.pix_bh : 0;
     if (BH <= 0) {
         BH = 32;
         while (BH > 8 && (long long)L.batch * ((L.H + BH - 1) / BH) < 4LL * sm_count) BH >>= 1;
@@ -538,7 +534,7 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
         // instructions per pixel, but as it draws more bandwidth per unit of time in the pipeline it lengthens the memory
         // latency the labelling kernels beside it see, and the whole path is faster with the band kernel below
         // (DESIGN.md 4.3).  RMCV_BGR_STRIP=1 selects the band-strip kernel.
-        if (env_int("RMCV_BGR_STRIP", 0) != 0) {
+        if (tune.bgr_strip != 0) {
             const cudaError_t se = launch_bgr_bandstrip(L, sm_count, st, launches);
             if (se != cudaErrorNotSupported) return se;
         }
@@ -568,13 +564,13 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
         p.gpr = (L.W + 15) / 16;
         p.srow = p.gpr * 48;
         const bool bulk = ((L.W & 15) == 0) && ((L.pitch & 15) == 0) && ((L.frame_stride & 15) == 0) &&
-                          ((((size_t)L.src) & 15) == 0) && env_int("RMCV_PIX_NOBULK", 0) == 0;
+                          ((((size_t)L.src) & 15) == 0) && tune.pix_nobulk == 0;
         p.contiguous = (L.pitch == (size_t)L.W * 3) ? 1 : 0;
-        int RC = env_int("RMCV_PIX_RC", 0);
+        int RC = tune.pix_rc > 0 ? tune.pix_rc : 0;
         if (RC <= 0) RC = max(1, min(16, 16384 / p.srow));  // ~16 KB per TMA chunk (sweep: gpurun_out/sweep.log)
         if (RC > BH + 2 * hl) RC = BH + 2 * hl;
-        int S = env_int("RMCV_PIX_S", 4);
-        int NT = env_int("RMCV_PIX_NT", 0);
+        int S = tune.pix_s > 0 ? tune.pix_s : 4;
+        int NT = tune.pix_nt > 0 ? tune.pix_nt : 0;
         if (NT <= 0) {  // one 16-pixel group per thread per chunk, rounded up to whole warps
             NT = ((RC * p.gpr + 31) / 32) * 32;
             NT = max(128, min(512, NT));
@@ -586,7 +582,7 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
         if (smem > (size_t)max_smem) return cudaErrorInvalidConfiguration;
         cudaError_t e;
         const bool fixed1280 = bulk && L.W == Geom1280::kW && p.BH == Geom1280::kBH && p.RC == Geom1280::kRC && p.S == Geom1280::kS &&
-                               NT == Geom1280::kNT && env_int("RMCV_PIX_GENERIC", 0) == 0;
+                               NT == Geom1280::kNT && tune.pix_generic == 0;
         if (fixed1280) {   // the default configuration with its geometry folded into the code
             e = cudaFuncSetAttribute(pixel_bgr_kernel<true, Geom1280>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
@@ -605,7 +601,7 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
     }
 
     // ---- Bayer: blue / red targets on 16-pixel-aligned frames take the register-resident strip kernel (bayer_strip.cu)
-    if (env_int("RMCV_BAYER_GENERIC", 0) == 0) {
+    if (tune.bayer_generic == 0) {
         const cudaError_t se = launch_bayer_strip(L, sm_count, st, launches);
         if (se != cudaErrorNotSupported) return se;
     }
@@ -690,7 +686,7 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
     p.srow = (L.W + 15) & ~15;
     if ((L.W & 15) == 0) p.srow = L.W;
     p.contiguous = 0;
-    int NT = env_int("RMCV_PIX_NT", 256);
+    int NT = tune.pix_nt > 0 ? tune.pix_nt : 256;
     if (L.W < 3 || L.H < 3) return cudaErrorInvalidValue;
     size_t raw_bytes = ((size_t)(BH + 2 * hl + 2) * p.srow + 15) & ~(size_t)15;
     size_t smem = raw_bytes + 128 + (size_t)(BH + 2 * hl) * (p.WB + 2) * 4 + (size_t)(BH + 2 * hl - 2) * (p.WB + 2) * 4 + 256;

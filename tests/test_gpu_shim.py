@@ -38,6 +38,13 @@ def test_cpp_call_site_matches_oracle():
     assert got["matched0"] == int(O.match_lightblob(ref.contours[0], 1.5, 80.0, 70.0, 10.0, 99999.0, True)[0])
     assert got["overlap"] == int(O.lightblob_overlap(legacy, 0, len(legacy) - 1))
     assert got["contour_sizes"] == [len(c) for c in ref.contours]
+    # the three-call path hands back the device results of rm::extract_color (no second fit, no re-upload of the points) ...
+    assert got["reused_lightblobs"] == 1 and got["reused_armours"] == 1
+    # ... but only for the parameters the device ran with: tilt_max = 60 went through the standalone kernels
+    assert got["reused_after_foreign_params"] == 0
+    p60 = [v for v in ref.verdicts if v.status != O.STATUS_SKIPPED and v.tilt <= 60.0 and v.status == O.STATUS_POSITIVE]
+    assert got["n_positive_tilt60"] == len(p60)
+    print("three-call path %.3f ms, fused rm::gpu::detect %.3f ms per frame (host wall clock, incl. H2D of the frame)" % (got["three_call_ms"], got["fused_ms"]))
     assert got["first_points"] == [[int(c[0][0]), int(c[0][1])] for c in ref.contours]
     for g, b in zip(got["blob_centers"], ref.positive):
         assert abs(g[0] - b.center[0]) <= 0.5 and abs(g[1] - b.center[1]) <= 0.5  # rng-band tolerant; exactness is tested elsewhere
@@ -51,3 +58,29 @@ def test_cpp_call_site_matches_oracle():
     assert len(got["icon_hashes"]) == len(ref.armours)
     for g, a in zip(got["icon_hashes"], ref.armours):
         assert int(g) == fnv(np.ascontiguousarray(O.affine_correction(frame, a.icon)[0]))
+
+
+def test_shim_extract_color_grows_capacities_instead_of_truncating():
+    """A frame with more components than the ctx's default per-frame capacity (512): the reference returns every external
+    contour (src/imgproc.cpp:71-72), so the shim must rebuild its ctx with larger capacities rather than hand back a
+    truncated list."""
+    rng = np.random.default_rng(3)
+    frame = np.zeros((480, 640, 3), np.uint8)
+    for _ in range(2500):
+        x, y = int(rng.integers(0, 636)), int(rng.integers(0, 476))
+        frame[y:y + int(rng.integers(1, 4)), x:x + int(rng.integers(1, 4)), 0] = 220
+    ref = O.detect_frame(frame)
+    assert len(ref.contours) > 600
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as fh:
+        fh.write(np.array([640, 480], np.int32).tobytes())
+        fh.write(frame.tobytes())
+        path = fh.name
+    try:
+        out = subprocess.run([EXE, path], check=True, capture_output=True, text=True, timeout=300).stdout
+    finally:
+        os.unlink(path)
+    got = json.loads(out)
+    assert got["n_contours"] == len(ref.contours)
+    assert got["contour_sizes"] == [len(c) for c in ref.contours]
+    assert got["first_points"] == [[int(c[0][0]), int(c[0][1])] for c in ref.contours]
+    assert got["n_positive"] == len(ref.positive) and got["n_armours"] == len(ref.armours)
