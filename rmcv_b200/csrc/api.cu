@@ -29,6 +29,14 @@ struct ResultSet {  // pinned, device-mapped result arrays of one detect call (t
     rmcv_lightblob* blobs = nullptr;        // [max_batch][C]
     rmcv_armour* armours = nullptr;         // [max_batch][A]
     rmcv_pose* poses = nullptr;             // [max_batch][A], allocated by the first rmcv_set_camera
+    // Device-side mirrors for large batches: the write-out kernel fills these (dense, same layout) and the records travel
+    // to the pinned arrays above as a few DMA copies sized from the per-frame counts once the call is fetched, instead of
+    // as posted stores over PCIe from inside the kernel (which stall the kernel and, with eight GPUs behind one host
+    // bridge, each other).  Small batches keep the zero-copy stores: lowest latency.
+    rmcv_frame_info* d_frames = nullptr; rmcv_contour_info* d_contours = nullptr; rmcv_lightblob* d_blobs = nullptr;
+    rmcv_armour* d_armours = nullptr;
+    bool staged = false, materialised = true;
+    int cf = 0;                             // frames per chunk of the call (dense regions are per chunk)
     bool with_poses = false;                // the call that filled this set had a camera
     int batch = 0;
     bool pending = false;                   // enqueued, not fetched yet
@@ -47,6 +55,7 @@ struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
     void* tmp_dev = nullptr; size_t tmp_dev_bytes = 0;
     void* tmp_host = nullptr; size_t tmp_host_bytes = 0;
     int last_nchunks = 0;
+    int last_cf = 0;     // frames per chunk of the last call (host-input calls use shorter chunks)
     int last_kind = 0;  // 0 none, 1 extract, 2 detect
     cudaEvent_t t_start[4 + kSlots] = {}, t_stop[4 + kSlots] = {};
     // Streams of the ctx.  The pixel kernels of consecutive chunks run back to back on `pix`; the labelling kernels of
@@ -57,6 +66,9 @@ struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
     long long chunk_counter = 0;      // chunks enqueued over the life of the ctx
     int last_first_slot = 0;          // slot of chunk 0 of the last call
     bool own_pix = false;
+    // where the write-out kernels of the current call put their records (pinned host arrays or the device mirrors)
+    rmcv_frame_info* o_frames = nullptr; rmcv_contour_info* o_contours = nullptr; rmcv_lightblob* o_blobs = nullptr;
+    rmcv_armour* o_armours = nullptr;
     CameraSetup camera;      // f1 fused: pose of every armour behind the write-out kernel
     bool have_camera = false;
 };
@@ -78,6 +90,7 @@ Tuning read_tuning() {
     t.pix_nt = env_or("RMCV_PIX_NT", -1); t.pix_nobulk = env_or("RMCV_PIX_NOBULK", 0); t.pix_generic = env_or("RMCV_PIX_GENERIC", 0);
     t.bgr_strip = env_or("RMCV_BGR_STRIP", 0); t.bandstrip_rc = env_or("RMCV_BANDSTRIP_RC", -1);
     t.bayer_generic = env_or("RMCV_BAYER_GENERIC", 0); t.strip_seg = env_or("RMCV_STRIP_SEG", -1); t.strip_minb = env_or("RMCV_STRIP_MINB", -1);
+    t.host_chunk = env_or("RMCV_HOST_CHUNK", -1); t.staged_out = env_or("RMCV_STAGED_OUT", -1);
     t.fused_emit = env_or("RMCV_FUSED_EMIT", -1); t.wide_label = env_or("RMCV_WIDE_LABEL", -1); t.graph = env_or("RMCV_GRAPH", -1);
     return t;
 }
@@ -224,7 +237,7 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
     FrameLaunch fl;
     fl.g = call_geometry(ctx, W, H); fl.frames = frames; fl.sb = &sb; fl.frame_base = frame_base;
     fl.st_out = ex->out;
-    fl.o_frames = ctx->h_frames; fl.o_contours = ctx->h_contours; fl.o_blobs = ctx->h_blobs; fl.o_armours = ctx->h_armours;
+    fl.o_frames = ex->o_frames; fl.o_contours = ex->o_contours; fl.o_blobs = ex->o_blobs; fl.o_armours = ex->o_armours;
     fl.o_poses = ex->have_camera ? ctx->h_poses : nullptr; fl.camera = ex->have_camera ? &ex->camera : nullptr;
     struct Mark { ProfSet* ps; rmcv_ctx* ctx; };
     Mark mk{ps, ctx};
@@ -240,17 +253,33 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
 
 // A detect call writes into result set (call number & 1); the previous call's set stays readable, so the host can fetch
 // call n while call n+1 is already running (rmcv_fetch_results returns the oldest unfetched call).
-void begin_call(rmcv_ctx* ctx) {
+int begin_call(rmcv_ctx* ctx, int batch = 0, int cf = 0) {
     CtxExtra* ex = extra(ctx);
     ResultSet& r = ex->rs[ex->n_calls & 1];
     r.pending = false;  // an unfetched call two calls back is dropped
     ctx->h_frames = r.frames; ctx->h_contours = r.contours; ctx->h_blobs = r.blobs; ctx->h_armours = r.armours;
     ctx->h_poses = r.poses;
     r.with_poses = ex->have_camera && r.poses;
+    const int mode = tuning().staged_out;      // -1 auto, 0 never, 1 always
+    r.staged = mode > 0 || (mode < 0 && batch > 64);
+    r.materialised = !r.staged;
+    r.cf = cf;
+    if (r.staged && !r.d_frames) {
+        const size_t B = ctx->cfg.max_batch, C = ctx->cap.C, A = ctx->cap.A;
+        RMCV_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&r.d_frames), B * sizeof(rmcv_frame_info)));
+        RMCV_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&r.d_contours), B * C * sizeof(rmcv_contour_info)));
+        RMCV_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&r.d_blobs), B * C * sizeof(rmcv_lightblob)));
+        RMCV_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&r.d_armours), B * A * sizeof(rmcv_armour)));
+    }
+    ex->o_frames = r.staged ? r.d_frames : r.frames; ex->o_contours = r.staged ? r.d_contours : r.contours;
+    ex->o_blobs = r.staged ? r.d_blobs : r.blobs; ex->o_armours = r.staged ? r.d_armours : r.armours;
+    return RMCV_OK;
 }
 int end_call(rmcv_ctx* ctx, int batch) {
     CtxExtra* ex = extra(ctx);
     ResultSet& r = ex->rs[ex->n_calls & 1];
+    if (r.staged)   // the per-frame counts and offsets travel first; the dense records follow when the call is fetched
+        RMCV_CUDA(ctx, cudaMemcpyAsync(r.frames, r.d_frames, (size_t)batch * sizeof(rmcv_frame_info), cudaMemcpyDeviceToHost, ex->out));
     RMCV_CUDA(ctx, cudaEventRecord(r.done[0], ex->out));
     RMCV_CUDA(ctx, cudaEventRecord(r.done[1], ex->pix));
     r.batch = batch; r.pending = true; r.call_id = ex->n_calls++;
@@ -267,8 +296,8 @@ int run_device_batch(rmcv_ctx* ctx, const uint8_t* d_src, size_t pitch, size_t f
     if (pitch < rowbytes) return set_err(ctx, RMCV_ERR_INVALID_ARG, "pitch smaller than a row");
     if (d_mask && mask_pitch < (size_t)W) return set_err(ctx, RMCV_ERR_INVALID_ARG, "mask pitch smaller than a row");
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (full) begin_call(ctx);
     const int CF = ctx->CF;
+    if (full) { rc = begin_call(ctx, batch, CF); if (rc != RMCV_OK) return rc; }
     int nchunks = 0;
     extra(ctx)->last_first_slot = (int)(extra(ctx)->chunk_counter % ctx->n_slots);
     for (int f0 = 0; f0 < batch; f0 += CF, ++nchunks) {
@@ -281,8 +310,30 @@ int run_device_batch(rmcv_ctx* ctx, const uint8_t* d_src, size_t pitch, size_t f
     ctx->last_batch = batch; ctx->last_W = W; ctx->last_H = H;
     ctx->have_results = full;
     extra(ctx)->last_nchunks = nchunks;
+    extra(ctx)->last_cf = CF;
     extra(ctx)->last_kind = full ? 2 : 1;
     if (full) return end_call(ctx, batch);
+    return RMCV_OK;
+}
+
+// Brings the dense records of a staged call into its pinned arrays: one DMA copy per array and chunk, sized from the
+// per-frame counts (which came over with the frame infos).  Idempotent.
+int materialise(rmcv_ctx* ctx, ResultSet& r) {
+    if (!r.staged || r.materialised || r.batch <= 0) return RMCV_OK;
+    CtxExtra* ex = extra(ctx);
+    RMCV_CUDA(ctx, cudaEventSynchronize(r.done[0]));
+    const size_t C = ctx->cap.C, A = ctx->cap.A;
+    const int cf = r.cf > 0 ? r.cf : r.batch;
+    for (int f0 = 0; f0 < r.batch; f0 += cf) {
+        const int f1 = f0 + cf < r.batch ? f0 + cf : r.batch;
+        size_t nc = 0, nb = 0, na = 0;
+        for (int f = f0; f < f1; ++f) { nc += (size_t)r.frames[f].n_contours; nb += (size_t)r.frames[f].n_positive; na += (size_t)r.frames[f].n_armours; }
+        if (nc) RMCV_CUDA(ctx, cudaMemcpyAsync(r.contours + (size_t)f0 * C, r.d_contours + (size_t)f0 * C, nc * sizeof(rmcv_contour_info), cudaMemcpyDeviceToHost, ex->d2h));
+        if (nb) RMCV_CUDA(ctx, cudaMemcpyAsync(r.blobs + (size_t)f0 * C, r.d_blobs + (size_t)f0 * C, nb * sizeof(rmcv_lightblob), cudaMemcpyDeviceToHost, ex->d2h));
+        if (na) RMCV_CUDA(ctx, cudaMemcpyAsync(r.armours + (size_t)f0 * A, r.d_armours + (size_t)f0 * A, na * sizeof(rmcv_armour), cudaMemcpyDeviceToHost, ex->d2h));
+    }
+    RMCV_CUDA(ctx, cudaStreamSynchronize(ex->d2h));
+    r.materialised = true;
     return RMCV_OK;
 }
 
@@ -295,6 +346,10 @@ int sync_all(rmcv_ctx* ctx) {
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->out));
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->d2h));
     prof_collect(ctx);
+    if (ex->n_calls > 0) {   // the on-demand getters read the most recent call's records on the host
+        ResultSet& r = ex->rs[(ex->n_calls - 1) & 1];
+        if (r.call_id == ex->n_calls - 1) { const int rc = materialise(ctx, r); if (rc != RMCV_OK) return rc; }
+    }
     return RMCV_OK;
 }
 
@@ -329,6 +384,7 @@ int fetch_oldest(rmcv_ctx* ctx, rmcv_results* out) {
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
     RMCV_CUDA(ctx, cudaEventSynchronize(r.done[0]));
     RMCV_CUDA(ctx, cudaEventSynchronize(r.done[1]));
+    if (int mrc = materialise(ctx, r)) return mrc;
     r.pending = false;
     ex->last_fetched = pick;
     // profiling events of finished chunks are collected here too: an async detect/fetch loop never reaches sync_all, and
@@ -343,9 +399,10 @@ int fetch_oldest(rmcv_ctx* ctx, rmcv_results* out) {
 // slot and local index of frame f of the last call, or null when its scratch has been recycled
 SlotBuffers* resident_slot(rmcv_ctx* ctx, int frame, int* local) {
     if (frame < 0 || frame >= ctx->last_batch) return nullptr;
-    const int chunk = frame / ctx->CF;
+    const int cf = extra(ctx)->last_cf > 0 ? extra(ctx)->last_cf : ctx->CF;
+    const int chunk = frame / cf;
     if (chunk + ctx->n_slots < extra(ctx)->last_nchunks) return nullptr;
-    *local = frame - chunk * ctx->CF;
+    *local = frame - chunk * cf;
     return &ctx->slot[(extra(ctx)->last_first_slot + chunk) % ctx->n_slots];
 }
 
@@ -515,6 +572,10 @@ int rmcv_ctx_destroy(rmcv_ctx* ctx) {
             if (r.blobs) cudaFreeHost(r.blobs);
             if (r.armours) cudaFreeHost(r.armours);
             if (r.poses) cudaFreeHost(r.poses);
+            if (r.d_frames) cudaFree(r.d_frames);
+            if (r.d_contours) cudaFree(r.d_contours);
+            if (r.d_blobs) cudaFree(r.d_blobs);
+            if (r.d_armours) cudaFree(r.d_armours);
             for (int k = 0; k < 2; ++k) if (r.done[k]) cudaEventDestroy(r.done[k]);
         }
         for (auto& ps : ex->prof) {
@@ -644,15 +705,22 @@ static int run_host_batch(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, siz
     if (pitch < rowbytes) return set_err(ctx, RMCV_ERR_INVALID_ARG, "pitch smaller than a row");
     if (h_mask && mask_pitch < (size_t)width) return set_err(ctx, RMCV_ERR_INVALID_ARG, "mask pitch smaller than a row");
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
-    begin_call(ctx);
-    const int CF = ctx->CF;
+    // Host-input calls are bound by the PCIe copies, not by the kernels: short chunks keep both copy engines busy (the
+    // upload of chunk i+1 overlaps the mask download of chunk i) and leave only a short download tail behind the last upload.
+    int CF = ctx->CF;
+    {
+        const int hc = tuning().host_chunk > 0 ? tuning().host_chunk : 64;
+        if (CF > hc) CF = hc;
+    }
+    rc = begin_call(ctx, batch, CF);
+    if (rc != RMCV_OK) return rc;
     const size_t dev_frame = (size_t)height * rowbytes, dev_mask = (size_t)height * width;
     int nchunks = 0;
     extra(ctx)->last_first_slot = (int)(extra(ctx)->chunk_counter % ctx->n_slots);
     for (int f0 = 0; f0 < batch; f0 += CF, ++nchunks) {
         SlotBuffers& sb = ctx->slot[extra(ctx)->chunk_counter++ % ctx->n_slots];
         const int frames = batch - f0 < CF ? batch - f0 : CF;
-        const size_t need_px = (size_t)CF * (size_t)ctx->cfg.max_height * ctx->cfg.max_width;
+        const size_t need_px = (size_t)(ctx->CF < 64 ? ctx->CF : 64) * (size_t)ctx->cfg.max_height * ctx->cfg.max_width;
         const size_t need = bayer_layout ? need_px : need_px * 3;   // a ctx that only ever sees mosaics stages 1 B/px
         if (sb.frames_bytes < need) {
             if (sb.frames) cudaFree(sb.frames);
@@ -698,6 +766,7 @@ static int run_host_batch(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, siz
     ctx->last_batch = batch; ctx->last_W = width; ctx->last_H = height;
     ctx->have_results = true;
     extra(ctx)->last_nchunks = nchunks;
+    extra(ctx)->last_cf = CF;
     extra(ctx)->last_kind = 2;
     const int set = (int)(extra(ctx)->n_calls & 1);
     rc = end_call(ctx, batch);
@@ -948,7 +1017,7 @@ static int run_legacy(rmcv_ctx* ctx, const int32_t* xy, const int32_t* offsets, 
     if (h_src && (width <= 0 || height <= 0 || pitch < (size_t)width * 3)) return set_err(ctx, RMCV_ERR_INVALID_ARG, "bad source image geometry");
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
     auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    const size_t b_xy = up16(npts * 8 + 8), b_off = up16(((size_t)n + 1) * 4), b_hull = up16(npts * 8 + 8);
+    const size_t b_xy = up16(npts * 8 + 8), b_off = up16(((size_t)n + 1) * 4), b_hull = up16(npts * 24 + 24);
     const size_t b_m = up16((size_t)n * 4), b_box = up16((size_t)n * sizeof(rmcv_rotated_rect)), b_c = up16((size_t)n * 4);
     const size_t b_blob = up16((size_t)n * sizeof(rmcv_lightblob));
     const size_t b_src = h_src ? up16((size_t)height * width * 3) : 0;

@@ -206,7 +206,7 @@ struct LegacyLaunch {   // rm::MatchLightBlob / rm::FindLightBlobs / cv::minArea
     float min_ratio, max_ratio, tilt_angle, min_area, max_area;
     int fit_ellipse;          // 1 = box from the ellipse, 0 = box from cv::minAreaRect, -1 = cv::minAreaRect only (no gates)
     const uint8_t* src; size_t pitch; int W, H;   // device BGR image for the camp vote, or null
-    int32_t* hull;            // scratch, 2 ints per contour point
+    int32_t* hull;            // scratch, 6 ints per contour point
     int32_t* matched; rmcv_rotated_rect* boxes; int32_t* camps; rmcv_lightblob* blobs;   // [n_contours] each
 };
 cudaError_t launch_legacy(const LegacyLaunch& p, cudaStream_t st, int64_t* launches);
@@ -243,6 +243,8 @@ struct Tuning {
     int small_batch, frame_rs, label_minsmem, label_small, contour_gy, emit_bh;   // labelling stages
     int pix_bh, pix_rc, pix_s, pix_nt, pix_nobulk, pix_generic;      // BGR band kernel geometry
     int bgr_strip, bandstrip_rc, bayer_generic, strip_seg, strip_minb;   // alternative pixel kernels
+    int staged_out;                                                  // result write-out through device staging: -1 auto, 0 never, 1 always
+    int host_chunk;                                                  // frames per chunk of the host-input entry points
     int fused_emit, wide_label, graph;                               // round-2 paths (emit inside the pixel kernel, ...)
 };
 const Tuning& tuning();  // copies the arc LUT to constant memory (once per process/device)

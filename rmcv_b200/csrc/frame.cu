@@ -17,12 +17,51 @@
 //        rm::armour geometry (reference: src/objdetect.cpp:114-166, src/core.cpp:21-49) with an order-preserving block
 //        compaction, dense write-out straight into pinned, device-mapped host memory.
 // Each kernel has a homogeneous resource profile, so each fills the SMs on its own.
+#include <cooperative_groups.h>
+
 #include "blob_math.cuh"
 #include "common.cuh"
 #include "pairs.cuh"
 #include "warp_fit.cuh"
 
 namespace rmcv {
+
+namespace cg = cooperative_groups;
+
+// A frame is labelled by ONE CTA (CS == 1) or, when a chunk holds fewer frames than the GPU has SMs (4096x3072 stress
+// frames, batch-1 latency), by a thread-block CLUSTER of CS CTAs: the per-frame phases are bound by memory latency, so
+// CS times the threads mean CS times the loads in flight.  The cluster works on the frame's global arrays; what a single
+// CTA keeps in shared-memory scalars lives in the shared memory of cluster rank 0 (distributed shared memory), block-wide
+// barriers become cluster barriers (barrier.cluster, release/acquire at cluster scope).
+template <int CS>
+struct Team {
+    int rank, k_or;
+    __device__ __forceinline__ Team() : rank(0), k_or(0) {
+        if (CS > 1) rank = (int)cg::this_cluster().block_rank();
+    }
+    __device__ __forceinline__ void sync() const {
+        if (CS > 1) cg::this_cluster().sync(); else __syncthreads();
+    }
+    template <class T>
+    __device__ __forceinline__ T* on0(T* p) const {      // the same shared-memory object in cluster rank 0
+        if (CS > 1) return cg::this_cluster().map_shared_rank(p, 0);
+        return p;
+    }
+    // cluster-wide OR of a per-thread flag; flags3 = three ints of shared memory (rank 0's are used), zero at kernel start
+    __device__ __forceinline__ int any(int v, int* flags3) {
+        if (CS == 1) return __syncthreads_or(v);
+        const int mine = __syncthreads_or(v);
+        int* f0 = on0(flags3);
+        const int slot = k_or % 3;
+        if (threadIdx.x == 0) {
+            if (rank == 0) f0[(slot + 1) % 3] = 0;        // the slot of the next call; last read two barriers ago
+            if (mine) atomicOr(f0 + slot, 1);
+        }
+        sync();
+        ++k_or;
+        return *reinterpret_cast<volatile int*>(f0 + slot);
+    }
+};
 
 // Arc table indexed by  NW | N<<1 | NE<<2 | W<<3 | E<<4 | SW<<5 | S<<6 | SE<<7  (bit set = foreground).
 // Entry: bits 0-2 arc count m; arc i at bits 3+5i: low 2 bits = 4-neighbour to test for "hole" (0=E,1=N,2=W,3=S),
@@ -119,7 +158,8 @@ __device__ __forceinline__ int upper_bound_xs(const uint32_t* run_x, int lo, int
 
 // Collapses a forest of links (every node points at an ancestor or at itself) until every node points at its root.
 // Block-wide; reads may see values written in the same round, which are ancestors too.
-__device__ __forceinline__ void pointer_jump(int32_t* link, int first, int end, int tid, int NT) {
+template <class TeamT>
+__device__ __forceinline__ void pointer_jump(int32_t* link, int first, int end, int tid, int NT, TeamT& team, int* flags3) {
     volatile int32_t* v = link;
     while (true) {
         int changed = 0;
@@ -133,7 +173,7 @@ __device__ __forceinline__ void pointer_jump(int32_t* link, int first, int end, 
             for (int u = 0; u < 4; ++u)
                 if (ll[u] != l[u]) { v[r0 + u * NT] = ll[u]; changed = 1; }
         }
-        if (!__syncthreads_or(changed)) break;
+        if (!team.any(changed, flags3)) break;
     }
 }
 
@@ -169,15 +209,20 @@ __host__ __device__ inline size_t label_smem_bytes(int H, int Rs, int C) {
 // NTMAX / MINB: 256 threads, four CTAs per SM for ordinary frames (the runs fit in shared memory); 1024 threads, one CTA per
 // SM for frames whose run arrays stay in global memory (4096x3072 stress frames), where the phases are bound by L2 latency
 // and more threads per frame mean more loads in flight.
-template <int NTMAX, int MINB>
+template <int NTMAX, int MINB, int CS>
 __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int sh_scan[33];
-    __shared__ int s_ncomp, s_nadj, s_flags, s_hb[4];
+    __shared__ int s_ncomp_, s_nadj_, s_flags_, s_hb_[4], s_or_[3];
+    Team<CS> team;
+    // shared scalars of the frame: rank 0's copies (CS == 1: this CTA's)
+    int& s_ncomp = *team.on0(&s_ncomp_); int& s_nadj = *team.on0(&s_nadj_); int& s_flags = *team.on0(&s_flags_);
+    int* s_hb = team.on0(s_hb_);
     const Geometry& g = p.g;
     const int W = g.W, H = g.H, R = g.R, C = g.C, Rs = p.Rs;
-    const int frame = blockIdx.x;
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+    const int frame = blockIdx.x / CS;
+    const int ltid = threadIdx.x, LNT = blockDim.x;               // within this CTA
+    const int tid = team.rank * LNT + ltid, NT = LNT * CS, lane = ltid & 31;   // within the frame's team
     const SlotBuffers& sb = p.sb;
     FrameCounters& fc = sb.counters[frame];
 
@@ -186,8 +231,8 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
     uint32_t* s_run_x = reinterpret_cast<uint32_t*>(q); q += (size_t)Rs * sizeof(uint32_t);
     int32_t* s_link = reinterpret_cast<int32_t*>(q);
     int32_t* s_hole = reinterpret_cast<int32_t*>(q + (((size_t)2 * (Rs + 2) + 3) & ~(size_t)3));  // per-component hole flags (gap phase)
-    int32_t* s_cnt = s_link;                       // record counts / start offsets (after the gap phase)
-    int32_t* s_start = s_link + C;
+    int32_t* s_cnt = team.on0(s_link);             // record counts / start offsets (after the gap phase): rank 0's
+    int32_t* s_start = s_cnt + C;
     q += label_link_bytes(Rs, C);
     int32_t* s_glink = reinterpret_cast<int32_t*>(q); q += ((size_t)Rs + 2) * sizeof(int32_t);
     uint16_t* s_run_y = reinterpret_cast<uint16_t*>(q); q += (size_t)Rs * sizeof(uint16_t);
@@ -195,7 +240,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
 
     const int raw_runs = fc.n_runs;
     const int n_runs = min(raw_runs, R);
-    const bool in_smem = n_runs <= Rs;
+    const bool in_smem = CS == 1 && n_runs <= Rs;   // a team works on the global arrays
     const uint32_t* g_run_x = sb.run_x + (size_t)frame * R;
     const uint16_t* g_run_y = sb.run_y + (size_t)frame * R;
     int32_t* g_parent = sb.parent + (size_t)frame * R;
@@ -224,6 +269,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
     if (tid == 0) {
         s_ncomp = 0; s_nadj = 0;
         s_flags = raw_runs > R ? RMCV_FRAME_OVERFLOW_RUNS : 0;
+        s_or_[0] = s_or_[1] = s_or_[2] = 0;
     }
     for (int y = tid; y < H; y += NT) {
         int2 rr = g_rows[y];
@@ -237,7 +283,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
         if (in_smem) { s_run_x[r] = g_run_x[r]; s_run_y[r] = g_run_y[r]; }
         f.cid[r] = 0;
     }
-    __syncthreads();
+    team.sync();
     // ---- foreground links (8-connectivity): the first run of row y-1 overlapping [xs-1, xe+1] becomes the parent;
     // every further touched run is flagged "joined with the run before it" (they are consecutive in their row)
     {
@@ -263,11 +309,11 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
         }
         if (adj) atomicAdd(&s_nadj, adj);
     }
-    __syncthreads();
-    pointer_jump(f.link, 0, n_runs, tid, NT);
+    team.sync();
+    pointer_jump(f.link, 0, n_runs, tid, NT, team, s_or_);
     for (int r = tid; r < n_runs; r += NT)
         if (f.cid[r]) uf_union(f.link, r, r - 1);
-    __syncthreads();
+    team.sync();
     // ---- flatten, enumerate components
     for (int r = tid; r < n_runs; r += NT) {
         const int root = uf_find(f.link, r);
@@ -284,7 +330,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
             f.link[r] = root;
         }
     }
-    __syncthreads();
+    team.sync();
     const int n_comps = min(s_ncomp, C);
     const int n_holes = s_ncomp - n_runs + s_nadj;  // Euler relation on the run graph
     const bool has_holes = n_holes > 0;
@@ -302,15 +348,15 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
         adj = __reduce_add_sync(peers, adj);
         if (c >= 0 && lane == __ffs(peers) - 1) atomicAdd(&g_comp_cnt[c], adj);
     }
-    __syncthreads();
+    team.sync();
     // ---- background gaps (4-connectivity), only when the frame has a hole
     if (has_holes) {
         // A hole lies strictly inside the bounding box of the component that encloses it, so a gap that is not strictly
         // inside the union of the bounding boxes of the components with holes is outer background without any search.
         if (tid == 0) { s_hb[0] = INT32_MAX; s_hb[1] = INT32_MAX; s_hb[2] = -1; s_hb[3] = -1; f.glink[0] = 0; }
         for (int i = tid; i < (2 * (n_runs + 2) + 3) / 4; i += NT) reinterpret_cast<uint32_t*>(f.jp)[i] = 0u;
-        for (int c = tid; c < n_comps; c += NT) s_hole[c] = g_comp_cnt[c];
-        __syncthreads();
+        for (int c = ltid; c < n_comps; c += LNT) s_hole[c] = g_comp_cnt[c];   // every CTA of the team keeps its own copy
+        team.sync();
         for (int r = tid; r < n_runs; r += NT) {
             const int c = f.cid[r];
             if (c >= 0 && s_hole[c] > 0) {
@@ -319,7 +365,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
                 atomicMin(&s_hb[1], (int)f.run_y[r]); atomicMax(&s_hb[3], (int)f.run_y[r]);
             }
         }
-        __syncthreads();
+        team.sync();
         const int hx0 = s_hb[0], hy0 = s_hb[1], hx1 = s_hb[2], hy1 = s_hb[3];
         for (int r = tid; r < n_runs; r += NT) {
             const int y = f.run_y[r];
@@ -381,20 +427,20 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
             if (outer && first >= 0) f.jo[first] = 1;
             f.glink[r + 1] = outer ? 0 : (first >= 0 ? first : r + 1);
         }
-        __syncthreads();
-        pointer_jump(f.glink, 1, n_runs + 1, tid, NT);
+        team.sync();
+        pointer_jump(f.glink, 1, n_runs + 1, tid, NT, team, s_or_);
         for (int gnode = 1 + tid; gnode <= n_runs; gnode += NT) {
             if (f.jp[gnode]) uf_union(f.glink, gnode, gnode - 1);
             if (f.jo[gnode]) uf_union(f.glink, gnode, 0);
         }
-        __syncthreads();
+        team.sync();
         for (int gnode = tid; gnode <= n_runs; gnode += NT) {
             const int root = gnode == 0 ? 0 : uf_find(f.glink, gnode);
             f.glink[gnode] = root;
             if (in_smem) g_glink[gnode] = root;  // read by the contour kernel's hole tests
         }
     }
-    __syncthreads();
+    team.sync();
     for (int c = tid; c < n_comps; c += NT) { g_comp_cnt[c] = g_comp_cnt[c] > 0; s_cnt[c] = 0; }  // has holes of its own
     // ---- boundary-pixel records -> components (through the run each record is tagged with): the records are counted
     // per component, start = exclusive scan of the counts, and a warp-aggregated scatter writes them
@@ -405,7 +451,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
     uint2* recs2 = sb.recs2 + (size_t)frame * g.PC;
     int32_t* g_start = sb.comp_start + (size_t)frame * (C + 1);
     if (tid == 0 && raw_recs > g.PC) s_flags |= RMCV_FRAME_OVERFLOW_POINTS;
-    __syncthreads();
+    team.sync();
     auto comp_of = [&](const uint2 rec) -> int {  // the emit kernel tagged the record with its run
         const int r = (int)(rec.y >> 8);
         return r < n_runs ? (int)f.cid[r] : -1;
@@ -421,20 +467,20 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
             if (c >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[c], __popc(peers));
         }
     }
-    __syncthreads();
-    {
+    team.sync();
+    if (team.rank == 0) {   // block-wide scan by the first CTA of the team
         int carry = 0;
-        for (int c0 = 0; c0 < n_comps; c0 += NT) {
-            const int c = c0 + tid;
+        for (int c0 = 0; c0 < n_comps; c0 += LNT) {
+            const int c = c0 + ltid;
             const int v = c < n_comps ? s_cnt[c] : 0;
             int total;
             const int ex = block_excl_scan(v, &total, sh_scan);
             if (c < n_comps) { s_start[c] = carry + ex; g_start[c] = carry + ex; s_cnt[c] = 0; }
             carry += total;
         }
-        if (tid == 0) g_start[n_comps] = carry;
+        if (ltid == 0) g_start[n_comps] = carry;
     }
-    __syncthreads();
+    team.sync();
     for (int i0 = 0; i0 < n_recs; i0 += 4 * NT) {
         uint2 rec[4];
 #pragma unroll
@@ -451,6 +497,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
         }
     }
     if (tid == 0) { fc.n_comps = n_comps; fc.n_holes = n_holes; fc.flags = s_flags; }
+    if (CS > 1) team.sync();   // rank 0's shared memory is read by the whole team until here
 }
 
 // ------------------------------------------------------------------------------------------ K_C: contour sums
@@ -654,100 +701,116 @@ struct OrderParams {
 };
 
 // NTMAX: 128 threads for ordinary frames; 512 for frames with large capacities (stress frames: hundreds of blobs, ~125k
-// pairs, ~130 KB of records to post over PCIe per frame from a handful of CTAs).
-template <int NTMAX>
+// pairs, ~130 KB of records to post over PCIe per frame from a handful of CTAs).  CS > 1: a cluster of CS CTAs per frame
+// (Team, above) shares the O(n^2) ordering and the O(P^2) pair loops when the chunk leaves most SMs idle.
+template <int NTMAX, int CS>
 __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int sh_scan[33];
-    __shared__ int s_np, s_nc, s_nn, s_flags, s_off[3];
+    __shared__ int s_np_, s_nc_, s_nn_, s_flags_, s_total_, s_off_[3];
+    Team<CS> team;
+    int& s_np = *team.on0(&s_np_); int& s_nc = *team.on0(&s_nc_); int& s_nn = *team.on0(&s_nn_);
+    int& s_flags = *team.on0(&s_flags_); int& s_total = *team.on0(&s_total_);
+    int* s_off = team.on0(s_off_);
     const Geometry& g = p.g;
     const int W = g.W, C = g.C, A = g.A;
-    const int frame = blockIdx.x;
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int frame = blockIdx.x / CS;
+    const int ltid = threadIdx.x, LNT = blockDim.x;               // within this CTA
+    const int tid = team.rank * LNT + ltid, NT = LNT * CS;        // within the frame's team
     const SlotBuffers& sb = p.sb;
     FrameCounters& fc = sb.counters[frame];
     const int n_comps = fc.n_comps;
-    int32_t* s_keys = reinterpret_cast<int32_t*>(smem);
+    int32_t* s_keys = reinterpret_cast<int32_t*>(smem);          // every CTA of a team keeps its own copy
     int32_t* s_status = s_keys + C;
     const CompRec* comps = sb.comps + (size_t)frame * C;
-    if (tid == 0) { s_np = 0; s_nc = 0; s_nn = 0; s_flags = fc.flags; }
-    for (int c = tid; c < n_comps; c += NT) { s_keys[c] = comps[c].firstkey; s_status[c] = comps[c].status; }
-    __syncthreads();
+    if (tid == 0) { s_np = 0; s_nc = 0; s_nn = 0; s_total = 0; s_flags = fc.flags; }
+    for (int c = ltid; c < n_comps; c += LNT) { s_keys[c] = comps[c].firstkey; s_status[c] = comps[c].status; }
+    team.sync();
     // ---- order: rank = number of external components with a larger first-pixel key (reverse raster order)
     rmcv_contour_info* oc = sb.s_contours + (size_t)frame * C;
     rmcv_lightblob* ob = sb.s_blobs + (size_t)frame * C;
     rmcv_armour* oa = sb.s_armours + (size_t)frame * A;
-    for (int i = tid; i < n_comps; i += NT) {
-        const int key = s_keys[i];
-        if (key < 0) continue;
-        const int stt = s_status[i];
-        int rank = 0, prank = 0;
-        for (int j = 0; j < n_comps; ++j) {
-            if (s_keys[j] > key) { ++rank; prank += (s_status[j] == RMCV_CONTOUR_POSITIVE); }
+    {
+        int nc = 0, np = 0, nn = 0;
+        for (int i = tid; i < n_comps; i += NT) {
+            const int key = s_keys[i];
+            if (key < 0) continue;
+            const int stt = s_status[i];
+            int rank = 0, prank = 0;
+            for (int j = 0; j < n_comps; ++j) {
+                if (s_keys[j] > key) { ++rank; prank += (s_status[j] == RMCV_CONTOUR_POSITIVE); }
+            }
+            const CompRec& c = comps[i];
+            rmcv_contour_info info;
+            info.first_x = key % W; info.first_y = key / W;
+            info.n_points = c.n_points;
+            info.status = stt;
+            info.area2 = c.area2;
+            info.bbox[0] = c.bbox[0]; info.bbox[1] = c.bbox[1];
+            info.bbox[2] = c.bbox[2] - c.bbox[0] + 1; info.bbox[3] = c.bbox[3] - c.bbox[1] + 1;
+            info.ellipse = c.ellipse;
+            info.fit_branch = c.fit_branch;
+            info.det0 = c.det0;
+            info.blob_index = stt == RMCV_CONTOUR_POSITIVE ? prank : -1;
+            oc[rank] = info;
+            ++nc;
+            if (stt == RMCV_CONTOUR_POSITIVE) { ob[prank] = c.blob; ++np; }
+            else if (stt == RMCV_CONTOUR_NEGATIVE) ++nn;
         }
-        const CompRec& c = comps[i];
-        rmcv_contour_info info;
-        info.first_x = key % W; info.first_y = key / W;
-        info.n_points = c.n_points;
-        info.status = stt;
-        info.area2 = c.area2;
-        info.bbox[0] = c.bbox[0]; info.bbox[1] = c.bbox[1];
-        info.bbox[2] = c.bbox[2] - c.bbox[0] + 1; info.bbox[3] = c.bbox[3] - c.bbox[1] + 1;
-        info.ellipse = c.ellipse;
-        info.fit_branch = c.fit_branch;
-        info.det0 = c.det0;
-        info.blob_index = stt == RMCV_CONTOUR_POSITIVE ? prank : -1;
-        oc[rank] = info;
-        atomicAdd(&s_nc, 1);
-        if (stt == RMCV_CONTOUR_POSITIVE) { ob[prank] = c.blob; atomicAdd(&s_np, 1); }
-        else if (stt == RMCV_CONTOUR_NEGATIVE) atomicAdd(&s_nn, 1);
+        if (nc) atomicAdd(&s_nc, nc);
+        if (np) atomicAdd(&s_np, np);
+        if (nn) atomicAdd(&s_nn, nn);
     }
-    __syncthreads();
+    team.sync();
     // ---- pairs in lexicographic (i,j) order (src/objdetect.cpp:122-163)
     const int P = s_np;
     const rmcv_lightblob* sblob = ob;            // ordinary frames: ~25 positives, read in place (L1/L2)
     if (p.stage_blobs) {                         // large capacities: staged in shared memory for the O(P^2) loops
         rmcv_lightblob* st = reinterpret_cast<rmcv_lightblob*>(s_status + C);
-        copy_words(st, ob, (size_t)P * sizeof(rmcv_lightblob), tid, NT);
+        copy_words(st, ob, (size_t)P * sizeof(rmcv_lightblob), ltid, LNT);
         sblob = st;
         __syncthreads();
     }
     const long long npairs = (long long)P * (P - 1) / 2;
-    int base = 0;
-    if (npairs <= 8 * NT) {
-        // few pairs (an ordinary frame): one pair per thread and round, order-preserving block compaction
-        for (long long k0 = 0; k0 < npairs; k0 += NT) {
-            const long long k = k0 + tid;
-            bool pass = false;
-            int i = 0, j = 0;
-            float gates[6];
-            if (k < npairs) {
-                pair_from_index(k, P, &i, &j);
-                pass = pair_passes(sblob[i], sblob[j], p.prm);
-                if (pass) pair_gates(sblob[i], sblob[j], p.prm, gates);
-            }
-            int total;
-            const int pos = base + block_excl_scan(pass ? 1 : 0, &total, sh_scan);
-            if (pass) {
-                if (pos < A) {
-                    rmcv_armour a;
-                    make_armour(sblob[i], sblob[j], &a);
-                    a.i = i; a.j = j;
-                    for (int t = 0; t < 6; ++t) a.gates[t] = gates[t];
-                    oa[pos] = a;
-                } else {
-                    atomicOr(&s_flags, RMCV_FRAME_OVERFLOW_ARMOURS);
+    if (npairs <= 8 * LNT) {
+        // few pairs (an ordinary frame): one pair per thread and round, order-preserving block compaction (first CTA)
+        if (team.rank == 0) {
+            int base = 0;
+            for (long long k0 = 0; k0 < npairs; k0 += LNT) {
+                const long long k = k0 + ltid;
+                bool pass = false;
+                int i = 0, j = 0;
+                float gates[6];
+                if (k < npairs) {
+                    pair_from_index(k, P, &i, &j);
+                    pass = pair_passes(sblob[i], sblob[j], p.prm);
+                    if (pass) pair_gates(sblob[i], sblob[j], p.prm, gates);
                 }
+                int total;
+                const int pos = base + block_excl_scan(pass ? 1 : 0, &total, sh_scan);
+                if (pass) {
+                    if (pos < A) {
+                        rmcv_armour a;
+                        make_armour(sblob[i], sblob[j], &a);
+                        a.i = i; a.j = j;
+                        for (int t = 0; t < 6; ++t) a.gates[t] = gates[t];
+                        oa[pos] = a;
+                    } else {
+                        atomicOr(&s_flags, RMCV_FRAME_OVERFLOW_ARMOURS);
+                    }
+                }
+                base += total;
             }
-            base += total;
+            if (ltid == 0) s_total = base;
         }
+        team.sync();
     } else {
         // many pairs (stress frames, ~125k): no barrier inside the O(P^2) loop.  A warp takes rows i and P-2-i of the pair
         // triangle together (P-1 pairs per unit) with its lanes over j; pass 1 counts the pairs of a row that pass the gates,
         // a scan of the counts gives every row its first output slot, pass 2 records the passing pairs there in j order.
-        int* s_rowpos = s_keys;                  // the ordering keys are no longer needed
+        int* s_rowpos = team.on0(s_keys);        // the ordering keys are no longer needed; rank 0's array
         const int nrows = P - 1, nunits = (nrows + 1) / 2;
-        const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+        const int lane = ltid & 31, warp = tid >> 5, nwarps = NT >> 5;
         for (int u = warp; u < nunits; u += nwarps) {
             for (int half = 0; half < 2; ++half) {
                 const int i = half == 0 ? u : nrows - 1 - u;
@@ -762,16 +825,20 @@ __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
                 if (lane == 0) s_rowpos[i] = cnt;
             }
         }
-        __syncthreads();
-        for (int r0 = 0; r0 < nrows; r0 += NT) {
-            const int r = r0 + tid;
-            const int v = r < nrows ? s_rowpos[r] : 0;
-            int total;
-            const int ex = block_excl_scan(v, &total, sh_scan);
-            if (r < nrows) s_rowpos[r] = base + ex;
-            base += total;
+        team.sync();
+        if (team.rank == 0) {
+            int base = 0;
+            for (int r0 = 0; r0 < nrows; r0 += LNT) {
+                const int r = r0 + ltid;
+                const int v = r < nrows ? s_rowpos[r] : 0;
+                int total;
+                const int ex = block_excl_scan(v, &total, sh_scan);
+                if (r < nrows) s_rowpos[r] = base + ex;
+                base += total;
+            }
+            if (ltid == 0) s_total = base;
         }
-        __syncthreads();
+        team.sync();
         for (int u = warp; u < nunits; u += nwarps) {
             for (int half = 0; half < 2; ++half) {
                 const int i = half == 0 ? u : nrows - 1 - u;
@@ -791,9 +858,9 @@ __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
                 }
             }
         }
-        __syncthreads();
+        team.sync();
         // the armours themselves (double-precision trigonometry): one per thread and round, no divergence
-        const int n_pass = min(base, A);
+        const int n_pass = min(s_total, A);
         for (int k = tid; k < n_pass; k += NT) {
             const int i = oa[k].i, j = oa[k].j;
             float gates[6];
@@ -805,7 +872,7 @@ __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
             oa[k] = a;
         }
     }
-    const int n_arm = min(base, A);
+    const int n_arm = min(s_total, A);
     // ---- claim dense space in the chunk's region of the pinned result arrays, write out
     if (tid == 0) {
         FrameCounters& al = sb.counters[p.frames];
@@ -815,13 +882,14 @@ __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
         fc.flags = s_flags;
         fc.n_contours = s_nc; fc.n_positive = P; fc.n_negative = s_nn; fc.n_armours = n_arm;
     }
-    __syncthreads();
+    team.sync();
+    const int nc_all = s_nc;
     const size_t base_c = (size_t)p.frame_base * C + s_off[0];
     const size_t base_b = (size_t)p.frame_base * C + s_off[1];
     const size_t base_a = (size_t)p.frame_base * A + s_off[2];
     if (tid == 0) {
         rmcv_frame_info fi;
-        fi.n_contours = s_nc; fi.n_positive = P; fi.n_negative = s_nn; fi.n_armours = n_arm;
+        fi.n_contours = nc_all; fi.n_positive = P; fi.n_negative = s_nn; fi.n_armours = n_arm;
         fi.contour_offset = (int32_t)base_c; fi.blob_offset = (int32_t)base_b; fi.armour_offset = (int32_t)base_a;
         fi.flags = s_flags;
         p.o_frames[p.frame_base + frame] = fi;
@@ -829,10 +897,12 @@ __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
         sb.arm_offset[4 * frame + 1] = (int32_t)base_c;
         sb.arm_offset[4 * frame + 2] = (int32_t)base_b;
     }
-    if (p.defer_copy) return;
-    copy_words(p.o_contours + base_c, oc, (size_t)s_nc * sizeof(rmcv_contour_info), tid, NT);
-    copy_words(p.o_blobs + base_b, ob, (size_t)P * sizeof(rmcv_lightblob), tid, NT);
-    copy_words(p.o_armours + base_a, oa, (size_t)n_arm * sizeof(rmcv_armour), tid, NT);
+    if (!p.defer_copy) {
+        copy_words(p.o_contours + base_c, oc, (size_t)nc_all * sizeof(rmcv_contour_info), tid, NT);
+        copy_words(p.o_blobs + base_b, ob, (size_t)P * sizeof(rmcv_lightblob), tid, NT);
+        copy_words(p.o_armours + base_a, oa, (size_t)n_arm * sizeof(rmcv_armour), tid, NT);
+    }
+    if (CS > 1) team.sync();   // rank 0's shared memory is read by the whole team until here
 }
 
 // Dense write-out of a large frame's records into the pinned result arrays, kWriteSplit CTAs per frame: with a handful of
@@ -888,14 +958,30 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         // 1024 threads: frames whose runs stay in global memory (run indices beyond 16 bits), and small batches, where a
         // frame's latency matters and the SMs are idle anyway
         const bool big = (L.g.R > 65535 || L.frames <= small_batch) && !tune.label_small;
-        if (big) {
-            e = cudaFuncSetAttribute(label_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // a team of 8 CTAs per frame: frames whose runs live in global memory anyway (above 2 Mpx), when the chunk leaves
+        // most SMs idle.  RMCV_WIDE_LABEL=0 switches it off, =1 forces it for every global-memory frame.
+        const bool team8 = L.g.R > 65535 && tune.wide_label != 0 && (tune.wide_label > 0 || L.frames * 8 <= 2 * 148);
+        if (team8) {
+            p.Rs = 0;
+            smem = label_smem_bytes(L.g.H, 0, L.g.C);
+            e = cudaFuncSetAttribute(label_kernel<1024, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            label_kernel<1024, 1><<<L.frames, 1024, smem, st>>>(p);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)L.frames * 8); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, label_kernel<1024, 1, 8>, p);
+            if (e != cudaSuccess) return e;
+        } else if (big) {
+            e = cudaFuncSetAttribute(label_kernel<1024, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            label_kernel<1024, 1, 1><<<L.frames, 1024, smem, st>>>(p);
         } else {
-            e = cudaFuncSetAttribute(label_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaFuncSetAttribute(label_kernel<256, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            label_kernel<256, 4><<<L.frames, 256, smem, st>>>(p);
+            label_kernel<256, 4, 1><<<L.frames, 256, smem, st>>>(p);
         }
         if (launches) ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -938,14 +1024,26 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         p.stage_blobs = big && smem + (size_t)L.g.C * sizeof(rmcv_lightblob) <= (size_t)max_smem_optin ? 1 : 0;
         if (p.stage_blobs) smem += (size_t)L.g.C * sizeof(rmcv_lightblob);
         if (smem > (size_t)max_smem_optin) return cudaErrorInvalidConfiguration;
+        p.defer_copy = (L.g.R > 65535 || L.g.C > 512) ? 1 : 0;
+        // a team of 8 CTAs per frame for frames with large capacities when the chunk leaves most SMs idle (see label)
+        const bool team8 = p.defer_copy && tune.wide_label != 0 && (tune.wide_label > 0 || L.frames * 8 <= 2 * 148);
         if (smem > 48 * 1024) {
-            e = big ? cudaFuncSetAttribute(order_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                    : cudaFuncSetAttribute(order_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = team8 ? cudaFuncSetAttribute(order_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                : big ? cudaFuncSetAttribute(order_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                      : cudaFuncSetAttribute(order_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        p.defer_copy = (L.g.R > 65535 || L.g.C > 512) ? 1 : 0;
-        if (big) order_kernel<512><<<L.frames, 512, smem, so>>>(p);
-        else order_kernel<128><<<L.frames, 128, smem, so>>>(p);
+        if (team8) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)L.frames * 8); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = so;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, order_kernel<512, 8>, p);
+            if (e != cudaSuccess) return e;
+        } else if (big) order_kernel<512, 1><<<L.frames, 512, smem, so>>>(p);
+        else order_kernel<128, 1><<<L.frames, 128, smem, so>>>(p);
         if (p.defer_copy == 1) {
             if (launches) ++*launches;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;

@@ -4,11 +4,12 @@
 //   rm::FindLightBlobs   src/objdetect.cpp:30-53   MatchLightBlob + camp vote from the mean colour of the contour's
 //                                                  bounding rect in the source image + rm::lightblob ctor
 //   rm::LightBlobOverlap src/objdetect.cpp:89-112
-//   cv::minAreaRect                                convex hull + the minimum-area enclosing rectangle over all hull-edge
-//                                                  directions (what OpenCV's rotating calipers find)
-// One warp per contour.  The hull is a warp-cooperative gift wrapping with exact integer cross products; every lane
-// then evaluates one hull edge direction against all hull vertices.  The camp vote compares exact integer channel sums
+//   cv::minAreaRect                                convex hull in cv::convexHull's vertex order + OpenCV's float32 rotating
+//                                                  calipers restated literally, tie rules included (calipers.cuh)
+// One warp per contour.  The hull is a warp-cooperative gift wrapping with exact integer cross products; one lane then
+// runs the calipers (O(hull) steps of a few flops).  The camp vote compares exact integer channel sums
 // over the bounding rect (the same decision as comparing the means).
+#include "calipers.cuh"
 #include "common.cuh"
 #include "warp_fit.cuh"
 
@@ -19,110 +20,67 @@ struct LegacyParams {
     float min_ratio, max_ratio, tilt_angle, min_area, max_area;
     int fit_ellipse;          // box = ellipse (1) or minAreaRect (0); -1 = minAreaRect only, no gates (rmcv_min_area_rects)
     const uint8_t* src; size_t pitch; int W, H;   // BGR source image for the camp vote, or null
-    int32_t* hull;            // scratch: 2 ints per contour point
+    int32_t* hull;            // scratch: 6 ints per contour point
     int32_t* matched; rmcv_rotated_rect* boxes; int32_t* camps; rmcv_lightblob* blobs;
 };
 
-// next hull vertex candidate: is p "more clockwise" than q as seen from cur (y down: negative cross), or equally
-// oriented and farther?
-__device__ __forceinline__ bool better_wrap(int cx, int cy, int qx, int qy, int px, int py) {
-    const long long cr = (long long)(qx - cx) * (py - cy) - (long long)(qy - cy) * (px - cx);
-    if (cr != 0) return cr < 0;
-    const long long dq = (long long)(qx - cx) * (qx - cx) + (long long)(qy - cy) * (qy - cy);
-    const long long dp = (long long)(px - cx) * (px - cx) + (long long)(py - cy) * (py - cy);
-    return dp > dq;
-}
-
-// cv::minAreaRect of the n points at pts (warp-cooperative).  hull: scratch for up to n vertices.  All lanes return
-// the same box.  Degenerate hulls (a point or a segment) give (length, 0) like OpenCV.
+// cv::minAreaRect of the n points at pts (warp-cooperative hull, then OpenCV's own float32 rotating calipers on one lane:
+// calipers.cuh).  hull: scratch for 6 ints per point (hull triples x, y, contour index + the same again for the reorder).
+// All lanes return the same box.  Degenerate hulls (a point or a segment) give (length, 0) like OpenCV.
 __device__ void min_area_rect_warp(const int32_t* pts, int n, int32_t* hull, int lane, rmcv_rotated_rect* out) {
     out->cx = out->cy = out->w = out->h = out->angle = 0.f;
     if (n <= 0) return;
-    // start vertex: lowest y, then lowest x
+    // start vertex: lowest y, then lowest x, then lowest contour index (coincident points: a contour revisits pixels)
     long long key = 0x7fffffffffffffffLL;
+    int kidx = 0x7fffffff;
     for (int i = lane; i < n; i += 32) {
         const long long k = ((long long)pts[2 * i + 1] << 32) | (unsigned)pts[2 * i];
-        key = k < key ? k : key;
+        if (k < key) { key = k; kidx = i; }
     }
-    for (int o = 16; o > 0; o >>= 1) { const long long k = __shfl_xor_sync(0xffffffffu, key, o); key = k < key ? k : key; }
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long k = __shfl_xor_sync(0xffffffffu, key, o);
+        const int ki = __shfl_xor_sync(0xffffffffu, kidx, o);
+        if (k < key || (k == key && ki < kidx)) { key = k; kidx = ki; }
+    }
     const int sx = (int)(key & 0xffffffffLL), sy = (int)(key >> 32);
-    int h = 0, cx = sx, cy = sy;
+    int h = 0, cx = sx, cy = sy, ci = kidx;
     while (h < n) {
-        if (lane == 0) { hull[2 * h] = cx; hull[2 * h + 1] = cy; }
+        if (lane == 0) { hull[3 * h] = cx; hull[3 * h + 1] = cy; hull[3 * h + 2] = ci; }
         ++h;
-        int bx = cx, by = cy;  // candidate (cur itself = none yet)
+        int bx = cx, by = cy, bi = 0x7fffffff;  // candidate (none yet)
         for (int i = lane; i < n; i += 32) {
             const int px = pts[2 * i], py = pts[2 * i + 1];
             if (px == cx && py == cy) continue;
-            if ((bx == cx && by == cy) || better_wrap(cx, cy, bx, by, px, py)) { bx = px; by = py; }
+            if (bi == 0x7fffffff || ((px != bx || py != by) && hull_better_wrap(cx, cy, bx, by, px, py))) { bx = px; by = py; bi = i; }
         }
         for (int o = 16; o > 0; o >>= 1) {
             const int ox = __shfl_xor_sync(0xffffffffu, bx, o), oy = __shfl_xor_sync(0xffffffffu, by, o);
-            const bool mine_none = bx == cx && by == cy, other_none = ox == cx && oy == cy;
-            // deterministic choice on both sides of the exchange: prefer the better wrap, break exact ties by coordinates
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            // deterministic choice on both sides of the exchange: the better wrap, coincident points by the lower index
             bool take = false;
-            if (!other_none) {
-                if (mine_none) take = true;
-                else if (ox != bx || oy != by) take = better_wrap(cx, cy, bx, by, ox, oy);
+            if (oi != 0x7fffffff) {
+                if (bi == 0x7fffffff) take = true;
+                else if (ox != bx || oy != by) take = hull_better_wrap(cx, cy, bx, by, ox, oy);
+                else take = oi < bi;
             }
-            if (take) { bx = ox; by = oy; }
+            if (take) { bx = ox; by = oy; bi = oi; }
         }
-        if ((bx == cx && by == cy) || (bx == sx && by == sy)) break;  // single point, or wrapped around
-        cx = bx; cy = by;
+        if (bi == 0x7fffffff || (bx == sx && by == sy)) break;  // single point, or wrapped around
+        cx = bx; cy = by; ci = bi;
     }
     __syncwarp();
-    if (h == 1) { out->cx = (float)sx; out->cy = (float)sy; return; }
-    // every hull edge direction: extents of the hull along it and across it
-    double best_area = 1e300;
-    int best_k = -1;
-    for (int k = lane; k < h; k += 32) {
-        const int k1 = k + 1 == h ? 0 : k + 1;
-        const double ax = hull[2 * k], ay = hull[2 * k + 1];
-        double ux = hull[2 * k1] - ax, uy = hull[2 * k1 + 1] - ay;
-        const double len = sqrt(ux * ux + uy * uy);
-        ux /= len; uy /= len;
-        double umin = 1e300, umax = -1e300, vmin = 1e300, vmax = -1e300;
-        for (int j = 0; j < h; ++j) {
-            const double px = hull[2 * j], py = hull[2 * j + 1];
-            const double pu = px * ux + py * uy, pv = -px * uy + py * ux;
-            umin = fmin(umin, pu); umax = fmax(umax, pu); vmin = fmin(vmin, pv); vmax = fmax(vmax, pv);
+    rmcv_rotated_rect box;
+    box.cx = box.cy = box.w = box.h = box.angle = 0.f;
+    if (lane == 0) {
+        if (h >= 3) hull_to_cv_order(hull, h, hull + 3 * (size_t)n);
+        else if (h == 2 && (hull[3] > hull[0] || (hull[3] == hull[0] && hull[4] > hull[1]))) {   // OpenCV: (max x, max y) first
+            for (int q = 0; q < 3; ++q) { const int32_t t = hull[q]; hull[q] = hull[3 + q]; hull[3 + q] = t; }
         }
-        const double area = (umax - umin) * (vmax - vmin);
-        if (area < best_area) { best_area = area; best_k = k; }
+        min_area_rect_from_hull(hull, h, &box);
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        const double oa = __shfl_xor_sync(0xffffffffu, best_area, o);
-        const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
-        if (ok >= 0 && (best_k < 0 || oa < best_area || (oa == best_area && ok < best_k))) { best_area = oa; best_k = ok; }
-    }
-    {
-        const int k = best_k, k1 = k + 1 == h ? 0 : k + 1;
-        const double ax = hull[2 * k], ay = hull[2 * k + 1];
-        double ux = hull[2 * k1] - ax, uy = hull[2 * k1 + 1] - ay;
-        const double len = sqrt(ux * ux + uy * uy);
-        ux /= len; uy /= len;
-        double umin = 1e300, umax = -1e300, vmin = 1e300, vmax = -1e300;
-        for (int j = 0; j < h; ++j) {
-            const double px = hull[2 * j], py = hull[2 * j + 1];
-            const double pu = px * ux + py * uy, pv = -px * uy + py * ux;
-            umin = fmin(umin, pu); umax = fmax(umax, pu); vmin = fmin(vmin, pv); vmax = fmax(vmax, pv);
-        }
-        const double eu = umax - umin, ev = vmax - vmin;
-        const double cu = 0.5 * (umax + umin), cv = 0.5 * (vmax + vmin);
-        out->cx = (float)(cu * ux - cv * uy);
-        out->cy = (float)(cu * uy + cv * ux);
-        // OpenCV 4.13 convention: angle in [-90, 0), width = extent along that direction
-        const double dirs[4][2] = {{ux, uy}, {-uy, ux}, {-ux, -uy}, {uy, -ux}};
-        for (int d = 0; d < 4; ++d) {
-            const double ang = atan2(dirs[d][1], dirs[d][0]) * 180.0 / RMCV_PI;
-            if (ang >= -90.0 && ang < 0.0) {
-                out->angle = (float)ang;
-                out->w = (float)((d & 1) ? ev : eu);
-                out->h = (float)((d & 1) ? eu : ev);
-                break;
-            }
-        }
-    }
+    out->cx = __shfl_sync(0xffffffffu, box.cx, 0); out->cy = __shfl_sync(0xffffffffu, box.cy, 0);
+    out->w = __shfl_sync(0xffffffffu, box.w, 0); out->h = __shfl_sync(0xffffffffu, box.h, 0);
+    out->angle = __shfl_sync(0xffffffffu, box.angle, 0);
 }
 
 __global__ void __launch_bounds__(128) legacy_kernel(const LegacyParams p) {
@@ -131,7 +89,7 @@ __global__ void __launch_bounds__(128) legacy_kernel(const LegacyParams p) {
     if (gw >= p.n_contours) return;
     const int p0 = p.off[gw], p1 = p.off[gw + 1], n = p1 - p0;
     const int32_t* pts = p.xy + 2 * (size_t)p0;
-    int32_t* hull = p.hull + 2 * (size_t)p0;
+    int32_t* hull = p.hull + 6 * (size_t)p0;
     rmcv_rotated_rect box;
     if (p.fit_ellipse < 0) {  // cv::minAreaRect only
         min_area_rect_warp(pts, n, hull, lane, &box);

@@ -4,6 +4,8 @@
 #include <cstring>
 #include "../../rmcv_b200/csrc/blob_math.cuh"
 #include "../../rmcv_b200/csrc/pnp_math.cuh"
+#include "../../rmcv_b200/csrc/calipers.cuh"
+#include <vector>
 
 using namespace rmcv;
 
@@ -70,5 +72,35 @@ int hm_solve_pnp(const float* pts, const double* K, const double* dist, float w,
     const bool ok = solve_pnp_square(reinterpret_cast<const float (*)[2]>(pts), K, dist, w, h, rx, ry, &r);
     for (int i = 0; i < 3; ++i) { rvec[i] = r.rvec[i]; tvec[i] = r.tvec[i]; }
     return ok ? 1 : 0;
+}
+
+// cv::minAreaRect the way legacy.cu evaluates it: gift-wrapped hull (smallest contour index among coincident points),
+// OpenCV's hull order, literal float32 rotating calipers (calipers.cuh).
+void hm_min_area_rect(const int32_t* xy, int n, rmcv_rotated_rect* box) {
+    memset(box, 0, sizeof(*box));
+    if (n <= 0) return;
+    std::vector<int32_t> hull((size_t)3 * n + 3), tmp((size_t)3 * n + 3);
+    int s = 0;
+    for (int i = 1; i < n; ++i)
+        if (xy[2 * i + 1] < xy[2 * s + 1] || (xy[2 * i + 1] == xy[2 * s + 1] && xy[2 * i] < xy[2 * s])) s = i;
+    const int sx = xy[2 * s], sy = xy[2 * s + 1];
+    int h = 0, cx = sx, cy = sy, ci = s;
+    while (h < n) {
+        hull[3 * h] = cx; hull[3 * h + 1] = cy; hull[3 * h + 2] = ci;
+        ++h;
+        int bx = cx, by = cy, bi = -1;
+        for (int i = 0; i < n; ++i) {
+            const int px = xy[2 * i], py = xy[2 * i + 1];
+            if (px == cx && py == cy) continue;
+            if (bi < 0 || (px == bx && py == by ? false : hull_better_wrap(cx, cy, bx, by, px, py))) { bx = px; by = py; bi = i; }
+        }
+        if (bi < 0 || (bx == sx && by == sy)) break;
+        cx = bx; cy = by; ci = bi;
+    }
+    if (h >= 3) hull_to_cv_order(hull.data(), h, tmp.data());
+    else if (h == 2 && (hull[3] > hull[0] || (hull[3] == hull[0] && hull[4] > hull[1]))) {   // OpenCV: (max x, max y) first
+        for (int q = 0; q < 3; ++q) { const int32_t t = hull[q]; hull[q] = hull[3 + q]; hull[3 + q] = t; }
+    }
+    min_area_rect_from_hull(hull.data(), h, box);
 }
 }
