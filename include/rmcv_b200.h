@@ -59,13 +59,22 @@ enum { RMCV_BAYER_RG = 1, RMCV_BAYER_GB = 2, RMCV_BAYER_GR = 3, RMCV_BAYER_BG = 
 enum { RMCV_CONTOUR_SKIPPED = 0, RMCV_CONTOUR_POSITIVE = 1, RMCV_CONTOUR_NEGATIVE = 2 };
 
 /* which branch cv::fitEllipseDirect took for a contour */
-enum { RMCV_FIT_NONE = 0, RMCV_FIT_DIRECT = 1, RMCV_FIT_FALLBACK = 2 };
+enum {
+    RMCV_FIT_NONE = 0, RMCV_FIT_DIRECT = 1, RMCV_FIT_FALLBACK = 2,
+    /* the fallback (cv::fitEllipseNoDirect) for a contour whose coordinate sum reaches 2^24: OpenCV accumulates the centre
+     * as a float Point2f point by point there, so ITS centre depends on the contour's point order by up to ~0.05 px; the
+     * order-free sums used here give the exactly rounded centre instead (only long contours far from the origin:
+     * n * x >= 16.7 M, e.g. 4100 points at x = 4090) */
+    RMCV_FIT_FALLBACK_LONG = 3
+};
 
 enum {
     RMCV_FRAME_OVERFLOW_RUNS = 1,
     RMCV_FRAME_OVERFLOW_BLOBS = 2,
     RMCV_FRAME_OVERFLOW_ARMOURS = 4,
-    RMCV_FRAME_OVERFLOW_POINTS = 8  /* boundary pixels above 4 * max_runs_per_frame */
+    RMCV_FRAME_OVERFLOW_POINTS = 8, /* boundary pixels above 4 * max_runs_per_frame */
+    RMCV_FRAME_OVERFLOW_MOMENTS = 16 /* a fitted contour too large for the exact 64-bit moment sums (n * extent^4 > 2^62; only
+                                        reachable with area_max far above the reference's 99999): its ellipse is not reliable */
 };
 
 /* ---- PODs --------------------------------------------------------------------------------- */

@@ -10,7 +10,8 @@ RMCV_ERR_INVALID_ARG, RMCV_ERR_CUDA, RMCV_ERR_CAPACITY, RMCV_ERR_NO_DEVICE, RMCV
 CAMP_RED, CAMP_BLUE, CAMP_GUIDELIGHT, CAMP_NEUTRAL = 0, 1, 2, -1
 BAYER_RG, BAYER_GB, BAYER_GR, BAYER_BG = 1, 2, 3, 4
 CONTOUR_SKIPPED, CONTOUR_POSITIVE, CONTOUR_NEGATIVE = 0, 1, 2
-FIT_NONE, FIT_DIRECT, FIT_FALLBACK = 0, 1, 2
+FIT_NONE, FIT_DIRECT, FIT_FALLBACK, FIT_FALLBACK_LONG = 0, 1, 2, 3
+FRAME_OVERFLOW_MOMENTS = 16
 STAGE_NAMES = ("pixel", "emit", "label", "contour", "fit", "order")
 
 

@@ -597,7 +597,8 @@ RMCV_HD void fit_from_moments(long long n_i, long long sum_x, long long sum_y, l
         const float c32x = fdiv((float)sum_x, (float)n_i), c32y = fdiv((float)sum_y, (float)n_i);
         shift_moments(R, (double)c32x - Ox, (double)c32y - Oy, &m);
         nodirect_fit(m, scale, c32x, c32y, ell);
-        *branch = RMCV_FIT_FALLBACK;
+        // beyond 2^24 OpenCV's own float accumulation of the centre rounds point by point (order dependent): flagged
+        *branch = (sum_x >= (1LL << 24) || sum_y >= (1LL << 24)) ? RMCV_FIT_FALLBACK_LONG : RMCV_FIT_FALLBACK;
     }
     *status = blob_gates(*ell, prm);
     if (*status == RMCV_CONTOUR_POSITIVE) make_lightblob(*ell, prm.target, blob);

@@ -678,6 +678,12 @@ __global__ void __launch_bounds__(64) fit_kernel(const FitParams p) {
         cs.xxxx = a.xxxx; cs.xxxy = a.xxxy; cs.xxyy = a.xxyy; cs.xyyy = a.xyyy; cs.yyyy = a.yyyy;
         cs.s_int = a.s_int; cs.ox = a.ox; cs.oy = a.oy;
         fit_contour(cs, p.prm, &rec.status, &rec.fit_branch, &rec.det0, &rec.ellipse, &rec.blob);
+        // the 4th-order sums are exact 64-bit integers about the component's root pixel: n * extent^4 must stay below 2^62
+        // (never reached with the reference's area_max = 99999; a caller who raises it gets the frame flagged, not a wrong fit)
+        if (a.fitted) {
+            const double ext = (double)max(a.bbox[2] - a.bbox[0], a.bbox[3] - a.bbox[1]) + 1.0;
+            if ((double)a.n * ext * ext * ext * ext > 4.6e18) atomicOr(&p.sb.counters[frame].flags, RMCV_FRAME_OVERFLOW_MOMENTS);
+        }
     }
     p.sb.comps[(size_t)frame * C + c] = rec;
 }

@@ -382,3 +382,37 @@ def test_pitched_device_frames_full_path(ctx):
         assert np.array_equal(got, ref.binary)
         CMP.compare_frame(ctx.frame_detections(res, f), ref, PRM, where=f"pitched frame {f}")
     d_in.free(); d_mask.free()
+
+
+def test_long_contour_fallback_centre_beyond_2_pow_24():
+    """cv::fitEllipseNoDirect sums its centre as a float Point2f point by point (the fallback every contour of >~ 200 points
+    takes): once n * x reaches 2^24 that sum rounds in contour order.  The order-free path returns the exactly rounded
+    centre and says so (RMCV_FIT_FALLBACK_LONG); below the bound the result is the reference's, float for float."""
+    W, H = 4096, 1200
+    frame = np.zeros((H, W, 3), np.uint8)
+    # a long thin serpentine near the right border: ~6000 contour points at x ~ 3900  ->  n * x ~ 2.3e7 > 2^24
+    for k, y in enumerate(range(100, 1100, 40)):
+        frame[y:y + 6, 3700:4090, 0] = 230
+        x = 4084 if k % 2 == 0 else 3700
+        frame[y:y + 46, x:x + 6, 0] = 230
+    # the same shape near the origin stays below the bound
+    small = np.zeros_like(frame)
+    small[:, :400] = frame[:, 3696:4096]
+    prm = CMP.oracle_params(dict(area_range=(10.0, 1e9)))
+    with rb.Context(max_width=W, max_height=H, max_batch=1) as c:
+        for img, expect_long in ((frame, True), (small, False)):
+            masks = np.empty((1, H, W), np.uint8)
+            res = c.detect_batch_host(img[None], c_params(prm), masks)
+            ref = O.detect_frame(img, **oracle_kwargs(prm))
+            det = c.frame_detections(res, 0)
+            assert np.array_equal(masks[0], ref.binary) and len(det.contours) == len(ref.contours) == 1
+            ci = det.contours[0]
+            assert ci.n_points == len(ref.contours[0]) > 5000
+            sx = int(ref.contours[0][:, 0].sum())
+            assert (sx >= 1 << 24) == expect_long
+            assert ci.fit_branch == (rb.abi.FIT_FALLBACK_LONG if expect_long else rb.abi.FIT_FALLBACK)
+            rep = CMP.compare_frame(det, ref, prm, where="long contour")
+            assert rep.long_fallback == (1 if expect_long else 0)
+            if not expect_long:
+                e = ref.verdicts[0].ellipse
+                assert np.float32(ci.ellipse).tobytes() == np.float32([e.cx, e.cy, e.w, e.h, e.angle]).tobytes()

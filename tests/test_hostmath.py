@@ -194,3 +194,33 @@ def test_solve_pnp_ippe_square_matches_cv2(hm):
         n += 1
     assert n > 200
     assert worst_r <= 1e-8 and worst_t <= 1e-8, (worst_r, worst_t)
+
+
+def test_min_area_rect_literal_calipers_bit_equal_to_cv2():
+    """a6: cv::minAreaRect (src/objdetect.cpp:16) as legacy.cu evaluates it — gift-wrapped hull put into cv::convexHull's
+    vertex order, OpenCV's float32 rotating calipers restated literally (calipers.cuh) — compiled for the host and
+    compared with cv2.minAreaRect: every float identical, no equal-area ties left."""
+    import cv2
+
+    class RR(C.Structure):
+        _fields_ = [("cx", C.c_float), ("cy", C.c_float), ("w", C.c_float), ("h", C.c_float), ("angle", C.c_float)]
+    lib = C.CDLL(LIB)
+    rng = np.random.default_rng(3)
+    tot = 0
+    extra = [np.array([[5, 5]], np.int32), np.array([[5, 5], [9, 5]], np.int32), np.array([[3, 3], [4, 4], [5, 5]], np.int32),
+             np.array([[0, 0], [0, 7], [0, 3]], np.int32), np.array([[2, 9], [2, 9]], np.int32),
+             np.array([[0, 0], [10, 0], [10, 10], [0, 10]], np.int32), np.array([[0, 0], [10, 0], [10, 10], [0, 10]][::-1], np.int32)]
+    for t in range(40):
+        W, H = int(rng.integers(60, 500)), int(rng.integers(60, 400))
+        m = (cv2.GaussianBlur((rng.random((H, W)) < 0.3).astype(np.float32), (0, 0), float(rng.uniform(1.2, 5))) > 0.33).astype(np.uint8) * 255
+        cs, _ = cv2.findContours(m, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
+        for c in [c.reshape(-1, 2) for c in cs] + (extra if t == 0 else []):
+            xy = np.ascontiguousarray(c, np.int32)
+            b = RR()
+            lib.hm_min_area_rect(xy.ctypes.data_as(C.POINTER(C.c_int32)), len(xy), C.byref(b))
+            r = cv2.minAreaRect(xy.reshape(-1, 1, 2))
+            got = np.array([b.cx, b.cy, b.w, b.h, b.angle], np.float32)
+            ref = np.array([r[0][0], r[0][1], r[1][0], r[1][1], r[2]], np.float32)
+            assert got.tobytes() == ref.tobytes(), (len(xy), got, ref)
+            tot += 1
+    assert tot > 5000
