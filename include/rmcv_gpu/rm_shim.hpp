@@ -255,9 +255,8 @@ inline std::tuple<std::vector<contour>, cv::Mat> extract_color(cv::InputArray im
     }
     if (rc != RMCV_OK && rc != RMCV_ERR_CAPACITY) gc.check(rc, "rmcv_detect_batch_host");
     const bool armour_overflow = rc == RMCV_ERR_CAPACITY;
-    int nc = 0, np = 0;
-    rc = rmcv_get_contours(ctx, 0, nullptr, 0, nullptr, 0, &nc, &np);
-    if (rc != RMCV_OK && rc != RMCV_ERR_CAPACITY) gc.check(rc, "rmcv_get_contours");
+    int nc = res.frames[0].n_contours, np = 0;       // sizes straight from the frame's records: one tracing call below
+    for (int k = 0; k < nc; ++k) np += res.contours[res.frames[0].contour_offset + k].n_points;
     std::vector<int32_t> xy((size_t)np * 2 + 2), off((size_t)nc + 1);
     if (nc > 0) gc.check(rmcv_get_contours(ctx, 0, xy.data(), np, off.data(), nc, &nc, &np), "rmcv_get_contours");
     std::vector<contour> contours((size_t)nc);

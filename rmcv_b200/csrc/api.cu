@@ -227,6 +227,15 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
     pl.mask = mask; pl.mask_pitch = mask_pitch; pl.mask_frame_stride = mask_frame_stride;
     pl.bits = sb.bits; pl.W = W; pl.H = H; pl.batch = frames;
     pl.target = prm.target; pl.lower_bound = prm.lower_bound; pl.bayer_layout = bayer_layout;
+    EmitLaunch el;
+    int emit_done = 0;
+    if (full) {   // the fixed-geometry BGR kernel can cut the runs / boundary records itself
+        const Geometry cg = call_geometry(ctx, W, H);
+        el.bits = sb.bits; el.W = W; el.H = H; el.batch = frames;
+        el.rows = sb.rows; el.run_x = sb.run_x; el.run_y = sb.run_y; el.counters = sb.counters; el.R = cg.R;
+        el.recs = sb.recs; el.PC = cg.PC;
+        pl.emit = &el; pl.emit_done = &emit_done;
+    }
     RMCV_CUDA(ctx, launch_pixel_stage(pl, ctx->sm_count, sp, &ctx->kernel_launches));
     if (ps) cudaEventRecord(ps->pix[1], sp);
     RMCV_CUDA(ctx, cudaEventRecord(sb.ev_pix, sp));
@@ -237,6 +246,7 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
     FrameLaunch fl;
     fl.g = call_geometry(ctx, W, H); fl.frames = frames; fl.sb = &sb; fl.frame_base = frame_base;
     fl.st_out = ex->out;
+    fl.emit_done = emit_done;
     fl.o_frames = ex->o_frames; fl.o_contours = ex->o_contours; fl.o_blobs = ex->o_blobs; fl.o_armours = ex->o_armours;
     fl.o_poses = ex->have_camera ? ctx->h_poses : nullptr; fl.camera = ex->have_camera ? &ex->camera : nullptr;
     struct Mark { ProfSet* ps; rmcv_ctx* ctx; };
@@ -394,6 +404,21 @@ int fetch_oldest(rmcv_ctx* ctx, rmcv_results* out) {
     if (ctx->profiling && !any_pending) prof_collect(ctx);
     else if (ctx->profiling && ex->prof_used > 4096) { ex->prof_used = 0; }   // bounded: drop the oldest marks
     return fill_results(ctx, r, out);
+}
+
+// The on-demand getters refer to the most recent detect call: wait for THAT call (its two done events) and bring its records
+// to the host, instead of synchronising every stream of the ctx (a dozen cudaStreamSynchronize calls, ~50 us when idle).
+int wait_latest_call(rmcv_ctx* ctx) {
+    CtxExtra* ex = extra(ctx);
+    if (ex->n_calls <= 0 || ex->last_kind != 2) return sync_all(ctx);
+    ResultSet& r = ex->rs[(ex->n_calls - 1) & 1];
+    if (r.call_id != ex->n_calls - 1) return sync_all(ctx);
+    RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (r.pending) {
+        RMCV_CUDA(ctx, cudaEventSynchronize(r.done[0]));
+        RMCV_CUDA(ctx, cudaEventSynchronize(r.done[1]));
+    }
+    return materialise(ctx, r);
 }
 
 // slot and local index of frame f of the last call, or null when its scratch has been recycled
@@ -801,7 +826,7 @@ int rmcv_fetch_results(rmcv_ctx* ctx, rmcv_results* out) {
 
 int rmcv_get_contour(rmcv_ctx* ctx, int frame, int contour_index, int32_t* xy, int cap, int* n_points) {
     if (!ctx || !n_points || cap < 0 || (cap > 0 && !xy)) return RMCV_ERR_INVALID_ARG;
-    int rc = sync_all(ctx);
+    int rc = wait_latest_call(ctx);
     if (rc != RMCV_OK) return rc;
     if (!ctx->have_results) return set_err(ctx, RMCV_ERR_STATE, "rmcv_get_contour needs a detect call first");
     int local = 0;
@@ -832,7 +857,7 @@ int rmcv_get_contour(rmcv_ctx* ctx, int frame, int contour_index, int32_t* xy, i
 int rmcv_get_contours(rmcv_ctx* ctx, int frame, int32_t* xy, int cap_points, int32_t* offsets, int cap_contours, int* n_contours,
                       int* n_points) {
     if (!ctx || !n_contours || !n_points || cap_points < 0 || cap_contours < 0) return RMCV_ERR_INVALID_ARG;
-    int rc = sync_all(ctx);
+    int rc = wait_latest_call(ctx);
     if (rc != RMCV_OK) return rc;
     if (!ctx->have_results) return set_err(ctx, RMCV_ERR_STATE, "rmcv_get_contours needs a detect call first");
     int local = 0;
@@ -875,7 +900,7 @@ int rmcv_get_contours(rmcv_ctx* ctx, int frame, int32_t* xy, int cap_points, int
 
 int rmcv_get_label_map(rmcv_ctx* ctx, int frame, int32_t* labels, size_t pitch_elems) {
     if (!ctx || !labels) return RMCV_ERR_INVALID_ARG;
-    int rc = sync_all(ctx);
+    int rc = wait_latest_call(ctx);
     if (rc != RMCV_OK) return rc;
     if (!ctx->have_results) return set_err(ctx, RMCV_ERR_STATE, "rmcv_get_label_map needs a detect call first");
     int local = 0;

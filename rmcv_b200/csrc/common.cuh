@@ -147,6 +147,11 @@ inline int set_err(rmcv_ctx* ctx, int code, const char* msg) {
 }
 
 // ---- launchers implemented in the .cu files -----------------------------------------------
+struct EmitLaunch {
+    const uint32_t* bits; int W, H, batch;
+    int2* rows; uint32_t* run_x; uint16_t* run_y; FrameCounters* counters; int R;
+    uint2* recs; int PC;
+};
 struct PixelLaunch {
     const uint8_t* src; size_t pitch, frame_stride;
     uint8_t* mask; size_t mask_pitch, mask_frame_stride;
@@ -154,6 +159,8 @@ struct PixelLaunch {
     int W, H, batch;
     int target, lower_bound;
     int bayer_layout;   // 0 = BGR input
+    const EmitLaunch* emit = nullptr;   // full calls: where the labelling stage's runs / records go, if the pixel kernel can emit them
+    int* emit_done = nullptr;           // set to 1 when it did (the separate emit launch is then skipped)
 };
 cudaError_t launch_pixel_stage(const PixelLaunch& p, int sm_count, cudaStream_t st, int64_t* launches);
 // Bayer fast path (bayer_strip.cu); cudaErrorNotSupported when the call does not qualify for it
@@ -173,17 +180,13 @@ struct FrameLaunch {
     rmcv_armour* o_armours;
     rmcv_pose* o_poses;           // null unless a camera is set
     const CameraSetup* camera;
+    int emit_done = 0;            // the pixel kernel already emitted the runs / records (fused pixel+emit kernel)
 };
 // everything after the pixel stage for one chunk (five launches: emit, label, contour sums, fits, order/pairs/write-out);
 // stage_done(arg, RMCV_STAGE_*, stream) is called after each launch (profiling events), may be null
 cudaError_t launch_frames(const FrameLaunch& p, const rmcv_params& prm, int max_smem_optin, cudaStream_t st, int64_t* launches,
                           void (*stage_done)(void*, int, cudaStream_t), void* stage_arg);
 
-struct EmitLaunch {
-    const uint32_t* bits; int W, H, batch;
-    int2* rows; uint32_t* run_x; uint16_t* run_y; FrameCounters* counters; int R;
-    uint2* recs; int PC;
-};
 cudaError_t launch_emit(const EmitLaunch& p, cudaStream_t st, int64_t* launches);
 
 cudaError_t launch_trace_contour(const Geometry& g, const uint32_t* bits, int x0, int y0, int32_t* d_xy, int cap,

@@ -932,6 +932,38 @@ __global__ void __launch_bounds__(256) writeout_kernel(const OrderParams p) {
           (size_t)fc.n_positive, sizeof(rmcv_lightblob));
 }
 
+// Team launches: a thread-block cluster of CS CTAs per frame.  All clusters of a launch should be co-resident (a second
+// wave doubles the kernel's time), and a cluster lives inside one GPC, so the largest CS in {8, 4, 2} whose clusters all
+// fit at once is chosen (cudaOccupancyMaxActiveClusters); 0 = no team.
+template <class Params>
+static int pick_team(void (*k8)(Params), void (*k4)(Params), void (*k2)(Params), int frames, int threads, size_t smem) {
+    void (*ks[3])(Params) = {k8, k4, k2};
+    const int cs[3] = {8, 4, 2};
+    for (int i = 0; i < 3; ++i) {
+        if (cudaFuncSetAttribute(ks[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)frames * cs[i]); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs[i]; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, ks[i], &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (n >= frames) return cs[i];
+    }
+    return 0;
+}
+template <class Params>
+static cudaError_t launch_team(void (*k)(Params), int cs, int frames, int threads, size_t smem, cudaStream_t st, const Params& p) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)frames * cs); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k, p);
+}
+
 // Enqueues the labelling stages of one chunk.  stage_done(i) is called after each kernel (profiling events).
 cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_smem_optin, cudaStream_t st, int64_t* launches,
                           void (*stage_done)(void*, int, cudaStream_t), void* stage_arg) {
@@ -939,13 +971,15 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
     auto done = [&](int stage) { if (stage_done) stage_done(stage_arg, stage, st); };
     const Tuning& tune = tuning();
     const int small_batch = tune.small_batch >= 0 ? tune.small_batch : 16;   // at most this many frames: per-frame kernels take their wide variants
-    {   // K_E
+    if (!L.emit_done) {   // K_E (unless the pixel kernel emitted the runs / records itself)
         EmitLaunch el;
         el.bits = L.sb->bits; el.W = L.g.W; el.H = L.g.H; el.batch = L.frames;
         el.rows = L.sb->rows; el.run_x = L.sb->run_x; el.run_y = L.sb->run_y; el.counters = L.sb->counters; el.R = L.g.R;
         el.recs = L.sb->recs; el.PC = L.g.PC;
         e = launch_emit(el, st, launches);
         if (e != cudaSuccess) return e;
+        done(RMCV_STAGE_EMIT);
+    } else {
         done(RMCV_STAGE_EMIT);
     }
     {   // K_L
@@ -966,19 +1000,14 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         const bool big = (L.g.R > 65535 || L.frames <= small_batch) && !tune.label_small;
         // a team of 8 CTAs per frame: frames whose runs live in global memory anyway (above 2 Mpx), when the chunk leaves
         // most SMs idle.  RMCV_WIDE_LABEL=0 switches it off, =1 forces it for every global-memory frame.
-        const bool team8 = L.g.R > 65535 && tune.wide_label != 0 && (tune.wide_label > 0 || L.frames * 8 <= 2 * 148);
-        if (team8) {
+        int cs = 0;
+        const size_t smem_team = label_smem_bytes(L.g.H, 0, L.g.C);
+        if (L.g.R > 65535 && tune.wide_label != 0 && L.frames < 148)
+            cs = pick_team<LabelParams>(label_kernel<1024, 1, 8>, label_kernel<1024, 1, 4>, label_kernel<1024, 1, 2>, L.frames, 1024, smem_team);
+        if (cs) {
             p.Rs = 0;
-            smem = label_smem_bytes(L.g.H, 0, L.g.C);
-            e = cudaFuncSetAttribute(label_kernel<1024, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)L.frames * 8); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            e = cudaLaunchKernelEx(&cfg, label_kernel<1024, 1, 8>, p);
+            e = launch_team<LabelParams>(cs == 8 ? label_kernel<1024, 1, 8> : cs == 4 ? label_kernel<1024, 1, 4> : label_kernel<1024, 1, 2>,
+                                         cs, L.frames, 1024, smem_team, st, p);
             if (e != cudaSuccess) return e;
         } else if (big) {
             e = cudaFuncSetAttribute(label_kernel<1024, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1032,21 +1061,17 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         if (smem > (size_t)max_smem_optin) return cudaErrorInvalidConfiguration;
         p.defer_copy = (L.g.R > 65535 || L.g.C > 512) ? 1 : 0;
         // a team of 8 CTAs per frame for frames with large capacities when the chunk leaves most SMs idle (see label)
-        const bool team8 = p.defer_copy && tune.wide_label != 0 && (tune.wide_label > 0 || L.frames * 8 <= 2 * 148);
-        if (smem > 48 * 1024) {
-            e = team8 ? cudaFuncSetAttribute(order_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                : big ? cudaFuncSetAttribute(order_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                      : cudaFuncSetAttribute(order_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int cs = 0;
+        if (p.defer_copy && tune.wide_label != 0 && L.frames < 148)
+            cs = pick_team<OrderParams>(order_kernel<512, 8>, order_kernel<512, 4>, order_kernel<512, 2>, L.frames, 512, smem);
+        if (!cs && smem > 48 * 1024) {
+            e = big ? cudaFuncSetAttribute(order_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                    : cudaFuncSetAttribute(order_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        if (team8) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)L.frames * 8); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = so;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            e = cudaLaunchKernelEx(&cfg, order_kernel<512, 8>, p);
+        if (cs) {
+            e = launch_team<OrderParams>(cs == 8 ? order_kernel<512, 8> : cs == 4 ? order_kernel<512, 4> : order_kernel<512, 2>, cs, L.frames, 512,
+                                         smem, so, p);
             if (e != cudaSuccess) return e;
         } else if (big) order_kernel<512, 1><<<L.frames, 512, smem, so>>>(p);
         else order_kernel<128, 1><<<L.frames, 128, smem, so>>>(p);

@@ -14,6 +14,7 @@
 //   * every input byte is read from HBM once (band halo rows are re-read through L2), every mask byte is
 //     written once with 16-byte stores.
 #include "common.cuh"
+#include "emit_core.cuh"
 #include "pairs.cuh"
 
 namespace rmcv {
@@ -83,6 +84,7 @@ struct PixelParams {
     int px, py;          // parity (x&1, y&1) of the site that samples channel `plus`... see kernel
     int plus_is_site;    // layout helpers, see bayer kernel
     int lb;
+    EmitParams em;       // fused pixel+emit kernel only: where the band's runs and boundary-pixel records go
 };
 
 struct Iter2D {  // walks idx = tid, tid+NT, ... over a [rows][cols] grid without divisions in the loop
@@ -231,9 +233,165 @@ __device__ __forceinline__ void close_and_store(const PixelParams& p, uint32_t* 
     }
 }
 
+// ------------------------------------------------------------------------------------------ fused close + emit
+// The fixed-geometry band kernel with the emission of the labelling stage folded in (emit.cu's work without its launch and
+// without re-reading the bit mask): the band computes its final mask rows y0-1 .. y0+nout (one more threshold row on each
+// side than the plain kernel: halo 3), stores rows y0 .. y0+nout-1 as before, and cuts the runs and boundary-pixel records
+// of its own rows straight from shared memory (emit_core.cuh).
+// t: (nout+6) x TW threshold words (row 0 <-> image row y0-3).  work: the TMA ring, free once the last chunk is consumed.
+template <class G>
+__device__ __forceinline__ void close_store_emit(const PixelParams& p, uint32_t* t, uint32_t* d, uint8_t* work, int frame, int y0,
+                                                 int nout, int tid) {
+    constexpr int W = G::kW, NT = G::kNT, WB = (G::kW + 31) / 32, TW = WB + 2;
+    constexpr uint32_t valid = (G::kW & 31) ? ((1u << (G::kW & 31)) - 1u) : 0xFFFFFFFFu;
+    constexpr int nseg = NT >= WB ? NT / WB : 1;
+    static_assert((WB & 3) == 0 && NT % 32 == 0, "fused emit: 16-byte groups of bit words, whole warps");
+    const int H = p.H;
+    // ---- dilate: rows y0-2 .. y0+nout+1 (outside the image: all ones so that the erode ignores them)
+    {
+        const int nd = nout + 4, per = (nd + nseg - 1) / nseg;
+        for (int slot = tid; slot < WB * nseg; slot += NT) {
+            const int seg = slot / WB, k = slot - seg * WB;
+            const int i0 = seg * per, i1 = min(nd, i0 + per);
+            if (i0 >= i1) continue;
+            const bool last = k == WB - 1, prelast = k + 1 == WB - 1;
+            auto hrow = [&](int ti) -> uint32_t {
+                const uint32_t* a = t + (size_t)ti * TW + k;
+                uint32_t left = a[0], mid = a[1], right = a[2];
+                if (last) mid &= valid;
+                if (prelast) right &= valid;
+                return mid | (mid << 1) | (left >> 31) | (mid >> 1) | (right << 31);
+            };
+            uint32_t h0 = hrow(i0), h1 = hrow(i0 + 1);
+            uint32_t* dp = d + (size_t)i0 * TW + k + 1;
+            for (int i = i0; i < i1; ++i, dp += TW) {
+                const uint32_t h2 = hrow(i + 2);
+                const int y = y0 - 2 + i;
+                uint32_t dv = h0 | h1 | h2;
+                if (last) dv |= ~valid;
+                if (y < 0 || y >= H) dv = 0xFFFFFFFFu;
+                dp[0] = dv;
+                if (k == 0) dp[-1] = 0xFFFFFFFFu;
+                if (last) dp[1] = 0xFFFFFFFFu;
+                h0 = h1; h1 = h2;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- erode: rows y0-1 .. y0+nout into mm (compact [nout+2][WB], aliases t); own rows also go to the global bit mask
+    uint32_t* mm = t;
+    {
+        uint32_t* gbits = p.bits + ((size_t)frame * H + y0) * WB;
+        const int ne = nout + 2, per = (ne + nseg - 1) / nseg;
+        for (int slot = tid; slot < WB * nseg; slot += NT) {
+            const int seg = slot / WB, k = slot - seg * WB;
+            const int j0 = seg * per, j1 = min(ne, j0 + per);
+            if (j0 >= j1) continue;
+            const bool last = k == WB - 1;
+            auto hrow = [&](int di) -> uint32_t {
+                const uint32_t* a = d + (size_t)di * TW + k;
+                const uint32_t left = a[0], mid = a[1], right = a[2];
+                return mid & ((mid << 1) | (left >> 31)) & ((mid >> 1) | (right << 31));
+            };
+            uint32_t h0 = hrow(j0), h1 = hrow(j0 + 1);
+            uint32_t* mp = mm + (size_t)j0 * WB + k;
+            for (int j = j0; j < j1; ++j, mp += WB) {
+                const uint32_t h2 = hrow(j + 2);
+                uint32_t mv = h0 & h1 & h2;
+                if (last) mv &= valid;
+                const int y = y0 - 1 + j;
+                if (y < 0 || y >= H) mv = 0u;                    // rows outside the image are background for the emission
+                mp[0] = mv;
+                if (j >= 1 && j <= nout) gbits[(size_t)(j - 1) * WB + k] = mv;
+                h0 = h1; h1 = h2;
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t* m = mm + WB;   // row 0 of m <-> image row y0
+    // ---- byte mask: one 16-byte store per 16 pixels, a thread walks down one 16-pixel column
+    if (p.mask != nullptr) {
+        const uint16_t* m16 = reinterpret_cast<const uint16_t*>(m);
+        constexpr int gpr16 = (W + 15) >> 4;
+        constexpr int nsg = NT >= gpr16 ? NT / gpr16 : 1;
+        uint8_t* gmask = p.mask + (size_t)frame * p.mask_frame_stride + (size_t)y0 * p.mask_pitch;
+        for (int slot = tid; slot < gpr16 * nsg; slot += NT) {
+            const int sg = slot / gpr16, g = slot - sg * gpr16;
+            const bool vec = p.mask_vec && g * 16 + 16 <= W;
+            uint8_t* dst = gmask + (size_t)sg * p.mask_pitch + (size_t)g * 16;
+            const size_t dstep = (size_t)nsg * p.mask_pitch;
+            const uint16_t* src = m16 + (size_t)sg * WB * 2 + g;
+            for (int j = sg; j < nout; j += nsg, dst += dstep, src += (size_t)nsg * WB * 2) {
+                const uint32_t b = *src;
+                uint4 o;
+                o.x = expand4(b & 15u);
+                o.y = expand4((b >> 4) & 15u);
+                o.z = expand4((b >> 8) & 15u);
+                o.w = expand4(b >> 12);
+                if (vec) {
+                    __stcs(reinterpret_cast<uint4*>(dst), o);
+                } else {
+                    for (int q = 0; q < 16 && g * 16 + q < W; ++q) {
+                        const uint32_t w4 = q < 4 ? o.x : q < 8 ? o.y : q < 12 ? o.z : o.w;
+                        dst[q] = (uint8_t)(w4 >> ((q & 3) * 8));
+                    }
+                }
+            }
+        }
+    }
+    // ---- emission of the band's own rows (the stage ring is free: every chunk has been consumed)
+    __shared__ int s_wtot[NT / 32], s_base[2];
+    constexpr int nwarps = NT / 32, cap = G::kBH * WB;
+    long long* scratch = reinterpret_cast<long long*>(work);
+    int* erun = reinterpret_cast<int*>(scratch + 36);
+    int* erec = erun + cap + 1;
+    uint16_t* list = reinterpret_cast<uint16_t*>(erec + cap + 1);
+    const int lane = tid & 31, warp = tid >> 5;
+    int pos = 0, n_ent = 0;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(mm);
+        const int own_lo = WB >> 2, own_hi = ((nout + 1) * WB) >> 2;
+        constexpr int per_w = ((((G::kBH * WB) >> 2) + nwarps - 1) / nwarps + 31) & ~31;
+        static_assert(per_w <= 256, "eight rounds of nibbles per warp");
+        const int q0 = min(own_hi, own_lo + warp * per_w), q1 = min(own_hi, q0 + per_w);
+        uint32_t nibs = 0;
+        int mine = 0, it = 0;
+        for (int i = q0 + lane; i < q1; i += 32, ++it) {
+            const uint4 v = src[i];
+            const uint32_t nib = (v.x != 0u) | ((v.y != 0u) << 1) | ((v.z != 0u) << 2) | ((v.w != 0u) << 3);
+            nibs |= nib << (4 * it);
+            mine += __popc(nib);
+        }
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if (lane == 0) s_wtot[warp] = mine;
+        __syncthreads();
+        for (int w = 0; w < nwarps; ++w) { if (w < warp) pos += s_wtot[w]; n_ent += s_wtot[w]; }
+        it = 0;
+        for (int i0 = q0; i0 < q1; i0 += 32, ++it) {
+            uint32_t nib = (nibs >> (4 * it)) & 15u;
+            const int c = __popc(nib);
+            int incl = c;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            int at = pos + incl - c;
+            const int wbase = ((i0 + lane) << 2) - WB;   // word index relative to the band's first own row
+            while (nib) {
+                const int b = __ffs(nib) - 1;
+                nib &= nib - 1;
+                list[at++] = (uint16_t)(wbase + b);
+            }
+            pos += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    emit_tail<NT>(p.em, frame, y0, nout, n_ent, m, list, erun, erec, scratch, s_base, tid);
+}
+
 // ------------------------------------------------------------------------------------------ BGR kernel
-template <bool kBulk, class G = GeomRuntime>
+template <bool kBulk, class G = GeomRuntime, bool kEmit = false>
 __global__ void __launch_bounds__(512) pixel_bgr_kernel(const PixelParams p) {
+    static_assert(!kEmit || G::kW > 0, "the fused emission needs the fixed geometry");
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr bool kFixed = G::kW > 0;
     const int tid = threadIdx.x, NT = kFixed ? G::kNT : (int)blockDim.x;
@@ -243,7 +401,7 @@ __global__ void __launch_bounds__(512) pixel_bgr_kernel(const PixelParams p) {
     const int srow = kFixed ? ((G::kW + 15) / 16) * 48 : p.srow;
     const int y0 = band * BH;
     const int nout = min(BH, H - y0);
-    const int hl = p.halo;
+    const int hl = kEmit ? 3 : p.halo;                    // the fused emission needs the final rows y0-1 and y0+nout too
     const int ty0 = y0 - hl;                              // image row of t row 0
     const int cy0 = max(0, ty0), cy1 = min(H, y0 + nout + hl);
     const int nchunks = (cy1 - cy0 + RC - 1) / RC;
@@ -323,7 +481,8 @@ __global__ void __launch_bounds__(512) pixel_bgr_kernel(const PixelParams p) {
         if (kBulk && tid == 0 && c + S < nchunks) issue(c + S, s);
         if (++s == S) { s = 0; phase ^= 1u; }
     }
-    close_and_store<G>(p, t, d, frame, y0, nout, tid, NT);
+    if constexpr (kEmit) close_store_emit<G>(p, t, d, smem, frame, y0, nout, tid);
+    else close_and_store<G>(p, t, d, frame, y0, nout, tid, NT);
 }
 
 // ------------------------------------------------------------------------------------------ Bayer kernel
@@ -583,6 +742,24 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
         cudaError_t e;
         const bool fixed1280 = bulk && L.W == Geom1280::kW && p.BH == Geom1280::kBH && p.RC == Geom1280::kRC && p.S == Geom1280::kS &&
                                NT == Geom1280::kNT && tune.pix_generic == 0;
+        if (fixed1280 && L.emit != nullptr && tune.fused_emit != 0 && L.H >= 3) {
+            // the same band kernel with the labelling stage's emission folded in (halo 3): one launch less per chunk and the bit
+            // mask is not read back
+            const EmitLaunch& E = *L.emit;
+            p.em.bits = L.bits; p.em.W = L.W; p.em.H = L.H; p.em.WB = p.WB; p.em.BH = p.BH; p.em.bands = p.bands;
+            p.em.inv_wb = p.inv_wb;
+            p.em.rows = E.rows; p.em.run_x = E.run_x; p.em.run_y = E.run_y; p.em.counters = E.counters; p.em.R = E.R;
+            p.em.recs = E.recs; p.em.PC = E.PC;
+            const size_t smem_e = pix_smem_bytes(S, RC, p.srow, BH, p.WB, 3);
+            if (smem_e <= (size_t)max_smem) {
+                e = cudaFuncSetAttribute(pixel_bgr_kernel<true, Geom1280, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
+                if (e != cudaSuccess) return e;
+                pixel_bgr_kernel<true, Geom1280, true><<<(unsigned)grid, NT, smem_e, st>>>(p);
+                if (launches) ++*launches;
+                if (L.emit_done) *L.emit_done = 1;
+                return cudaGetLastError();
+            }
+        }
         if (fixed1280) {   // the default configuration with its geometry folded into the code
             e = cudaFuncSetAttribute(pixel_bgr_kernel<true, Geom1280>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;

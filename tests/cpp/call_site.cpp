@@ -37,9 +37,11 @@ int main(int argc, char** argv) {
             auto a3 = rm::filter_armours(p3, 12, 22, 0.4, rm::CAMP_BLUE);
         }
         const double three_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / 20;
-        cv::Mat bin2(image.rows, image.cols, 1);
         t0 = std::chrono::steady_clock::now();
-        for (int rep = 0; rep < 20; ++rep) rm::gpu::detect(image, prm, &bin2);
+        for (int rep = 0; rep < 20; ++rep) {
+            cv::Mat bin2(image.rows, image.cols, 1);   // a fresh mask per frame, like rm::extract_color has to return
+            rm::gpu::detect(image, prm, &bin2);
+        }
         const double fused_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / 20;
         // legacy entry points (include/objdetect.h:22-37,62) over the same contours
         std::vector<rm::lightblob> legacy;
