@@ -92,6 +92,7 @@ Tuning read_tuning() {
     t.bayer_generic = env_or("RMCV_BAYER_GENERIC", 0); t.strip_seg = env_or("RMCV_STRIP_SEG", -1); t.strip_minb = env_or("RMCV_STRIP_MINB", -1);
     t.host_chunk = env_or("RMCV_HOST_CHUNK", -1); t.staged_out = env_or("RMCV_STAGED_OUT", -1);
     t.fused_emit = env_or("RMCV_FUSED_EMIT", -1); t.wide_label = env_or("RMCV_WIDE_LABEL", -1); t.graph = env_or("RMCV_GRAPH", -1);
+    t.chain_pad = env_or("RMCV_CHAIN_PAD", -1);
     return t;
 }
 

@@ -263,6 +263,11 @@ cudaError_t launch_bayer_strip(const PixelLaunch& L, int sm_count, cudaStream_t 
             const long long cost = ((warps + slots - 1) / slots) * (sg + 8);
             if (best < 0 || cost < best) { best = cost; seg = sg; }
         }
+        // With enough work for two waves and more, short segments win although they re-read more halo rows: the CTAs of a
+        // multi-wave launch overlap each other's ramp-up and drain, and the labelling kernels of a detect call get SM slots
+        // sooner (cold sweep on 64 x 1440x1080: 24-row segments 4.21 TB/s, the one-wave choice of ~60 rows 3.99 TB/s).
+        const long long warps24 = ((long long)L.batch * ((L.H + 23) / 24) * p.NC + 29) / 30;
+        if (warps24 >= 2 * slots) seg = 24;
     }
     if (seg > L.H) seg = L.H;
     if (seg < 2) seg = 2;

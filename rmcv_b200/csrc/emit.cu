@@ -129,14 +129,16 @@ cudaError_t launch_emit(const EmitLaunch& L, cudaStream_t st, int64_t* launches)
     const size_t cap = (size_t)BH * p.WB;
     const size_t smem = 36 * 8 + 2 * (cap + 1) * 4 + 16 + (size_t)(BH + 2) * p.WB * 4 + cap * 2 + 16;
     const bool vec = (p.WB & 3) == 0;
-    if (smem > 48 * 1024) {
-        cudaError_t e = vec ? cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                            : cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    size_t smem_l = smem;
+    if (tuning().chain_pad > 0 && (size_t)tuning().chain_pad > smem_l) smem_l = (size_t)tuning().chain_pad;
+    if (smem_l > 48 * 1024) {
+        cudaError_t e = vec ? cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l)
+                            : cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
         if (e != cudaSuccess) return e;
     }
     dim3 grid(p.bands, L.batch);
-    if (vec) emit_kernel<true><<<grid, 128, smem, st>>>(p);
-    else emit_kernel<false><<<grid, 128, smem, st>>>(p);
+    if (vec) emit_kernel<true><<<grid, 128, smem_l, st>>>(p);
+    else emit_kernel<false><<<grid, 128, smem_l, st>>>(p);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -991,6 +991,7 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         while (smem > (size_t)max_smem_optin && Rs > 0) { Rs = Rs > 1024 ? Rs - 1024 : 0; smem = label_smem_bytes(L.g.H, Rs, L.g.C); }
         if (smem > (size_t)max_smem_optin) return cudaErrorInvalidConfiguration;
         p.Rs = Rs;
+        if (tune.chain_pad > 0 && (size_t)tune.chain_pad > smem && tune.chain_pad <= max_smem_optin) smem = (size_t)tune.chain_pad;
         if (tune.label_minsmem > 0) {   // experiment: cap the CTAs per SM by padding shared memory
             const size_t m = (size_t)tune.label_minsmem;
             if (m > smem && m <= (size_t)max_smem_optin) smem = m;
@@ -1029,7 +1030,9 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         if (gy * 4 > L.g.C) gy = (L.g.C + 3) / 4;
         if (gy < 1) gy = 1;
         dim3 grid(L.frames, gy);
-        contour_kernel<<<grid, 128, 0, st>>>(p);
+        const size_t pad = tune.chain_pad > 0 ? (size_t)tune.chain_pad : 0;
+        if (pad > 48 * 1024) cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+        contour_kernel<<<grid, 128, pad, st>>>(p);
         if (launches) ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         done(RMCV_STAGE_CONTOUR);
@@ -1038,7 +1041,9 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         FitParams p;
         p.g = L.g; p.sb = *L.sb; p.prm = prm;
         dim3 grid((L.g.C + 63) / 64, L.frames);
-        fit_kernel<<<grid, 64, 0, st>>>(p);
+        const size_t pad = tune.chain_pad > 0 ? (size_t)tune.chain_pad : 0;
+        if (pad > 48 * 1024) cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+        fit_kernel<<<grid, 64, pad, st>>>(p);
         if (launches) ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         done(RMCV_STAGE_FIT);
@@ -1059,6 +1064,7 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         p.stage_blobs = big && smem + (size_t)L.g.C * sizeof(rmcv_lightblob) <= (size_t)max_smem_optin ? 1 : 0;
         if (p.stage_blobs) smem += (size_t)L.g.C * sizeof(rmcv_lightblob);
         if (smem > (size_t)max_smem_optin) return cudaErrorInvalidConfiguration;
+        if (tune.chain_pad > 0 && (size_t)tune.chain_pad > smem) smem = (size_t)tune.chain_pad;
         p.defer_copy = (L.g.R > 65535 || L.g.C > 512) ? 1 : 0;
         // a team of 8 CTAs per frame for frames with large capacities when the chunk leaves most SMs idle (see label)
         int cs = 0;

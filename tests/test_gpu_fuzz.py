@@ -48,3 +48,10 @@ def test_fuzz_legacy_rows():
 def test_fuzz_stress_frames():
     """frames up to 4096x3072 with hundreds of light blobs, every frame through the comparator."""
     run_script("fuzz_stress_gpu.py", [4, 9])
+
+
+def test_fused_pixel_emit_kernel_opt_in():
+    """RMCV_FUSED_EMIT=1 (the band kernel with the labelling stage's emission folded in; tuning is read once per process, so
+    the check runs in its own interpreter): five launches per chunk and the same results, frame for frame."""
+    out = run_script("fused_emit_parity_gpu.py", [])
+    assert " 0 mismatches" in out
