@@ -161,8 +161,8 @@ typedef struct rmcv_pose {
 } rmcv_pose;
 
 /* View of the results of one detect call.  Pointers are ctx-owned pinned host memory, valid
- * until the second next detect call on the ctx (two result sets alternate).  Dense arrays are
- * indexed through frames[f].*_offset. */
+ * until the fourth next detect call on the ctx (four result sets rotate, so up to three calls can
+ * be in flight behind the one being fetched).  Dense arrays are indexed through frames[f].*_offset. */
 typedef struct rmcv_results {
     int32_t batch;
     int32_t total_contours, total_blobs, total_armours;
@@ -240,7 +240,7 @@ int rmcv_bayer_detect_batch_host(rmcv_ctx* ctx, const uint8_t* h_raw, size_t pit
 
 /* Waits for the oldest detect call whose results have not been fetched yet and exposes them
  * (with one call in flight: the last call).  Without an unfetched call it re-exposes the
- * results fetched last.  An unfetched call is dropped when a third call is enqueued. */
+ * results fetched last.  An unfetched call is dropped when a fifth call is enqueued. */
 int rmcv_fetch_results(rmcv_ctx* ctx, rmcv_results* out);
 
 /* The on-demand getters below refer to the MOST RECENT detect call and wait for it.

@@ -44,8 +44,12 @@ struct ResultSet {  // pinned, device-mapped result arrays of one detect call (t
     cudaEvent_t done[2] = {nullptr, nullptr};  // recorded on the write-out stream and on the pixel stream
 };
 
+// Result sets of a ctx: up to kResultSets - 1 detect calls can be in flight behind the one being fetched (short calls — a few
+// frames, or one slice of a batch split over several GPUs — need more than one call ahead to keep the GPU busy).
+constexpr int kResultSets = 4;
+
 struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
-    ResultSet rs[2];
+    ResultSet rs[kResultSets];
     long long n_calls = 0;
     int last_fetched = -1;
     std::vector<ProfSet> prof;
@@ -264,10 +268,27 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
 
 // A detect call writes into result set (call number & 1); the previous call's set stays readable, so the host can fetch
 // call n while call n+1 is already running (rmcv_fetch_results returns the oldest unfetched call).
+cudaError_t alloc_result_set(rmcv_ctx* ctx, ResultSet& r) {
+    const size_t B = ctx->cfg.max_batch, C = ctx->cap.C, A = ctx->cap.A;
+    const unsigned hflags = cudaHostAllocMapped | cudaHostAllocPortable;
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&r.frames), B * sizeof(rmcv_frame_info), hflags);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&r.contours), B * C * sizeof(rmcv_contour_info), hflags);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&r.blobs), B * C * sizeof(rmcv_lightblob), hflags);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&r.armours), B * A * sizeof(rmcv_armour), hflags);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.done[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.done[1], cudaEventDisableTiming);
+    if (e == cudaSuccess) memset(r.frames, 0, B * sizeof(rmcv_frame_info));
+    return e;
+}
+
 int begin_call(rmcv_ctx* ctx, int batch = 0, int cf = 0) {
     CtxExtra* ex = extra(ctx);
-    ResultSet& r = ex->rs[ex->n_calls & 1];
-    r.pending = false;  // an unfetched call two calls back is dropped
+    ResultSet& r = ex->rs[ex->n_calls % kResultSets];
+    if (!r.frames) RMCV_CUDA(ctx, alloc_result_set(ctx, r));
+    if (ex->have_camera && !r.poses)
+        RMCV_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&r.poses), (size_t)ctx->cfg.max_batch * ctx->cap.A * sizeof(rmcv_pose),
+                                     cudaHostAllocMapped | cudaHostAllocPortable));
+    r.pending = false;  // an unfetched call kResultSets calls back is dropped
     ctx->h_frames = r.frames; ctx->h_contours = r.contours; ctx->h_blobs = r.blobs; ctx->h_armours = r.armours;
     ctx->h_poses = r.poses;
     r.with_poses = ex->have_camera && r.poses;
@@ -288,7 +309,7 @@ int begin_call(rmcv_ctx* ctx, int batch = 0, int cf = 0) {
 }
 int end_call(rmcv_ctx* ctx, int batch) {
     CtxExtra* ex = extra(ctx);
-    ResultSet& r = ex->rs[ex->n_calls & 1];
+    ResultSet& r = ex->rs[ex->n_calls % kResultSets];
     if (r.staged)   // the per-frame counts and offsets travel first; the dense records follow when the call is fetched
         RMCV_CUDA(ctx, cudaMemcpyAsync(r.frames, r.d_frames, (size_t)batch * sizeof(rmcv_frame_info), cudaMemcpyDeviceToHost, ex->out));
     RMCV_CUDA(ctx, cudaEventRecord(r.done[0], ex->out));
@@ -358,7 +379,7 @@ int sync_all(rmcv_ctx* ctx) {
     RMCV_CUDA(ctx, cudaStreamSynchronize(ex->d2h));
     prof_collect(ctx);
     if (ex->n_calls > 0) {   // the on-demand getters read the most recent call's records on the host
-        ResultSet& r = ex->rs[(ex->n_calls - 1) & 1];
+        ResultSet& r = ex->rs[(ex->n_calls - 1) % kResultSets];
         if (r.call_id == ex->n_calls - 1) { const int rc = materialise(ctx, r); if (rc != RMCV_OK) return rc; }
     }
     return RMCV_OK;
@@ -385,7 +406,7 @@ int fill_results(rmcv_ctx* ctx, const ResultSet& r, rmcv_results* out) {
 int fetch_oldest(rmcv_ctx* ctx, rmcv_results* out) {
     CtxExtra* ex = extra(ctx);
     int pick = -1;
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < kResultSets; ++i)
         if (ex->rs[i].pending && (pick < 0 || ex->rs[i].call_id < ex->rs[pick].call_id)) pick = i;
     if (pick < 0) {
         if (ex->last_fetched < 0) return set_err(ctx, RMCV_ERR_STATE, "no detect call to fetch results from");
@@ -401,7 +422,7 @@ int fetch_oldest(rmcv_ctx* ctx, rmcv_results* out) {
     // profiling events of finished chunks are collected here too: an async detect/fetch loop never reaches sync_all, and
     // without this the event pool would grow with every call
     bool any_pending = false;
-    for (int i = 0; i < 2; ++i) any_pending |= ex->rs[i].pending;
+    for (int i = 0; i < kResultSets; ++i) any_pending |= ex->rs[i].pending;
     if (ctx->profiling && !any_pending) prof_collect(ctx);
     else if (ctx->profiling && ex->prof_used > 4096) { ex->prof_used = 0; }   // bounded: drop the oldest marks
     return fill_results(ctx, r, out);
@@ -412,7 +433,7 @@ int fetch_oldest(rmcv_ctx* ctx, rmcv_results* out) {
 int wait_latest_call(rmcv_ctx* ctx) {
     CtxExtra* ex = extra(ctx);
     if (ex->n_calls <= 0 || ex->last_kind != 2) return sync_all(ctx);
-    ResultSet& r = ex->rs[(ex->n_calls - 1) & 1];
+    ResultSet& r = ex->rs[(ex->n_calls - 1) % kResultSets];
     if (r.call_id != ex->n_calls - 1) return sync_all(ctx);
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
     if (r.pending) {
@@ -560,19 +581,8 @@ int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
     int rc = RMCV_OK;
     for (int i = 0; i < ctx->n_slots && rc == RMCV_OK; ++i) rc = alloc_slot(ctx, ctx->slot[i], i == 0);
     if (rc != RMCV_OK) return fail(rc);
-    const size_t B = cfg->max_batch;
-    const unsigned hflags = cudaHostAllocMapped | cudaHostAllocPortable;
     cudaError_t e = cudaSuccess;
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-        ResultSet& r = extra(ctx)->rs[i];
-        e = cudaHostAlloc(reinterpret_cast<void**>(&r.frames), B * sizeof(rmcv_frame_info), hflags);
-        if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&r.contours), B * g.C * sizeof(rmcv_contour_info), hflags);
-        if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&r.blobs), B * g.C * sizeof(rmcv_lightblob), hflags);
-        if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&r.armours), B * g.A * sizeof(rmcv_armour), hflags);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.done[0], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.done[1], cudaEventDisableTiming);
-        if (e == cudaSuccess) memset(r.frames, 0, B * sizeof(rmcv_frame_info));
-    }
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = alloc_result_set(ctx, extra(ctx)->rs[i]);   // sets 2.. on first use
     if (e != cudaSuccess) {
         snprintf(ctx->err, sizeof(ctx->err), "pinned result allocation failed: %s", cudaGetErrorString(e));
         return fail(RMCV_ERR_CUDA);
@@ -591,7 +601,7 @@ int rmcv_ctx_destroy(rmcv_ctx* ctx) {
     for (int i = 0; i < ctx->n_slots; ++i) free_slot(ctx->slot[i]);
     CtxExtra* ex = extra(ctx);
     if (ex) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kResultSets; ++i) {
             ResultSet& r = ex->rs[i];
             if (r.frames) cudaFreeHost(r.frames);
             if (r.contours) cudaFreeHost(r.contours);
@@ -794,7 +804,7 @@ static int run_host_batch(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, siz
     extra(ctx)->last_nchunks = nchunks;
     extra(ctx)->last_cf = CF;
     extra(ctx)->last_kind = 2;
-    const int set = (int)(extra(ctx)->n_calls & 1);
+    const int set = (int)(extra(ctx)->n_calls % kResultSets);
     rc = end_call(ctx, batch);
     if (rc != RMCV_OK) return rc;
     rc = sync_all(ctx);
@@ -1165,9 +1175,9 @@ int rmcv_set_camera(rmcv_ctx* ctx, const double camera_matrix[9], const double d
     if (exact_w != exact_h || !(exact_w > 0.f)) return set_err(ctx, RMCV_ERR_INVALID_ARG, "IPPE_SQUARE needs a square object of positive size");
     CtxExtra* ex = extra(ctx);
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
-    for (int i = 0; i < 2; ++i) {   // the pose arrays exist only for callers that ask for poses
+    for (int i = 0; i < kResultSets; ++i) {   // the pose arrays exist only for callers that ask for poses
         ResultSet& r = ex->rs[i];
-        if (!r.poses)
+        if (r.frames && !r.poses)
             RMCV_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&r.poses), (size_t)ctx->cfg.max_batch * ctx->cap.A * sizeof(rmcv_pose),
                                          cudaHostAllocMapped | cudaHostAllocPortable));
     }
