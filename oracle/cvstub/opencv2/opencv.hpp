@@ -190,23 +190,32 @@ class MatExpr;
 template <typename T> class Mat_;
 template <typename T> class MatCommaInitializer_;
 
+struct MatStep {   // cv::MatStep: bytes per row, converts to size_t
+    size_t v = 0;
+    operator size_t() const { return v; }
+    MatStep& operator=(size_t s) { v = s; return *this; }
+};
+
 class Mat {
 public:
     int rows = 0, cols = 0;
+    uchar* data = nullptr;   // first element (like cv::Mat::data)
+    MatStep step;            // bytes per row (like cv::Mat::step)
     Mat() {}
     Mat(int r, int c, int type) { create(r, c, type); }
     Mat(Size s, int type) { create(s.height, s.width, type); }
     Mat(int r, int c, int type, void* ext) {   // a header over the caller's buffer, like cv::Mat(rows, cols, type, data)
-        rows = r; cols = c; type_ = type; step_ = (int64_t)c * elem_size_of(type); ext_ = static_cast<uchar*>(ext);
+        rows = r; cols = c; type_ = type; step = (size_t)c * elem_size_of(type); data = static_cast<uchar*>(ext);
     }
     Mat(const MatExpr& e);
     template <typename T> Mat(const MatCommaInitializer_<T>& ci);
 
     void create(int r, int c, int type) {
         rows = r; cols = c; type_ = type;
-        step_ = (int64_t)c * elem_size_of(type);
-        buf_ = std::make_shared<std::vector<uchar>>((size_t)std::max<int64_t>(1, (int64_t)r * step_), (uchar)0);
-        off_ = 0; ext_ = nullptr; hold_.reset();
+        step = (size_t)c * elem_size_of(type);
+        auto buf = std::make_shared<std::vector<uchar>>((size_t)std::max<int64_t>(1, (int64_t)r * (int64_t)step.v), (uchar)0);
+        data = buf->data();
+        hold_ = buf;
     }
     static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
     static Mat eye(int r, int c, int type) {
@@ -217,15 +226,14 @@ public:
     int type() const { return type_; }
     int depth() const { return CV_MAT_DEPTH(type_); }
     int channels() const { return CV_MAT_CN(type_); }
-    bool empty() const { return rows == 0 || cols == 0 || (!buf_ && !ext_); }
+    bool empty() const { return rows == 0 || cols == 0 || data == nullptr; }
     size_t total() const { return (size_t)rows * cols; }
     Size size() const { return Size(cols, rows); }
-    int64_t step() const { return step_; }
-    bool isContinuous() const { return step_ == (int64_t)cols * elem_size_of(type_); }
-    uchar* ptr(int r = 0) { return data_ptr() + (int64_t)r * step_; }
-    const uchar* ptr(int r = 0) const { return data_ptr() + (int64_t)r * step_; }
-    template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data_ptr() + (int64_t)r * step_); }
-    template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data_ptr() + (int64_t)r * step_); }
+    bool isContinuous() const { return step.v == (size_t)cols * elem_size_of(type_); }
+    uchar* ptr(int r = 0) { return data + (size_t)r * step.v; }
+    const uchar* ptr(int r = 0) const { return data + (size_t)r * step.v; }
+    template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * step.v); }
+    template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * step.v); }
     template <typename T> T& at(int i) {
         return rows == 1 ? reinterpret_cast<T*>(ptr(0))[i] : (cols == 1 ? *reinterpret_cast<T*>(ptr(i)) : reinterpret_cast<T*>(ptr(i / cols))[i % cols]);
     }
@@ -234,7 +242,7 @@ public:
     template <typename T> const T& at(int i, int j) const { return reinterpret_cast<const T*>(ptr(i))[j]; }
     Mat operator()(const Rect& r) const {   // a view that shares storage
         Mat m = *this;
-        m.off_ = off_ + (int64_t)r.y * step_ + (int64_t)r.x * elem_size_of(type_);
+        m.data = data + (size_t)r.y * step.v + (size_t)r.x * elem_size_of(type_);
         m.rows = r.height; m.cols = r.width;
         return m;
     }
@@ -246,7 +254,7 @@ public:
         return m;
     }
     void copyTo(Mat& dst) const {
-        if (dst.rows != rows || dst.cols != cols || dst.type_ != type_ || (!dst.buf_ && !dst.ext_)) dst.create(rows, cols, type_);
+        if (dst.rows != rows || dst.cols != cols || dst.type_ != type_ || dst.data == nullptr) dst.create(rows, cols, type_);
         for (int r = 0; r < rows; ++r) std::memcpy(dst.ptr(r), ptr(r), (size_t)cols * elem_size_of(type_));
     }
     void copyTo(const Mat& dst_view) const {   // cv::OutputArray built from a temporary header (a ROI)
@@ -263,7 +271,7 @@ public:
         m.type_ = CV_MAKETYPE(depth(), cn);
         m.rows = new_rows;
         m.cols = (int)(elems / ((int64_t)new_rows * cn));
-        m.step_ = (int64_t)m.cols * elem_size_of(m.type_);
+        m.step = (size_t)m.cols * elem_size_of(m.type_);
         return m;
     }
     void convertTo(Mat& dst, int rtype, double alpha = 1.0, double beta = 0.0) const;
@@ -287,7 +295,7 @@ public:
     }
     rmcv_ref_arr as_arr() const {
         rmcv_ref_arr a;
-        a.data = const_cast<uchar*>(data_ptr()); a.rows = rows; a.cols = cols; a.type = type_; a.step = step_; a.owner = 0;
+        a.data = data; a.rows = rows; a.cols = cols; a.type = type_; a.step = (int64_t)step.v; a.owner = 0;
         return a;
     }
     static Mat from_arr(const rmcv_ref_arr& a) {   // a callback result: adopted without a copy when the callee owns it
@@ -298,7 +306,7 @@ public:
             return m;
         }
         if (a.owner && rmcv_ref_release) {   // like a cv::Mat the real function would have allocated: one buffer, no extra copy
-            m.rows = a.rows; m.cols = a.cols; m.type_ = a.type; m.step_ = a.step; m.ext_ = static_cast<uchar*>(a.data);
+            m.rows = a.rows; m.cols = a.cols; m.type_ = a.type; m.step = (size_t)a.step; m.data = static_cast<uchar*>(a.data);
             const int64_t owner = a.owner;
             m.hold_ = std::shared_ptr<void>(nullptr, [owner](void*) { if (rmcv_ref_release) rmcv_ref_release(owner); });
             return m;
@@ -310,11 +318,7 @@ public:
     }
 
 private:
-    uchar* data_ptr() const { return ext_ ? ext_ + off_ : (buf_ ? const_cast<uchar*>(buf_->data()) + off_ : nullptr); }
-    std::shared_ptr<std::vector<uchar>> buf_;
-    std::shared_ptr<void> hold_;   // keeps a callee-owned buffer (ext_) alive
-    uchar* ext_ = nullptr;
-    int64_t off_ = 0, step_ = 0;
+    std::shared_ptr<void> hold_;   // keeps the storage behind `data` alive (own allocation or a callee-owned buffer)
     int type_ = 0;
 };
 

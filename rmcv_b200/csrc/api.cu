@@ -281,6 +281,15 @@ cudaError_t alloc_result_set(rmcv_ctx* ctx, ResultSet& r) {
     return e;
 }
 
+cudaError_t alloc_result_mirror(rmcv_ctx* ctx, ResultSet& r) {
+    const size_t B = ctx->cfg.max_batch, C = ctx->cap.C, A = ctx->cap.A;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&r.d_frames), B * sizeof(rmcv_frame_info));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&r.d_contours), B * C * sizeof(rmcv_contour_info));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&r.d_blobs), B * C * sizeof(rmcv_lightblob));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&r.d_armours), B * A * sizeof(rmcv_armour));
+    return e;
+}
+
 int begin_call(rmcv_ctx* ctx, int batch = 0, int cf = 0) {
     CtxExtra* ex = extra(ctx);
     ResultSet& r = ex->rs[ex->n_calls % kResultSets];
@@ -296,13 +305,7 @@ int begin_call(rmcv_ctx* ctx, int batch = 0, int cf = 0) {
     r.staged = mode > 0 || (mode < 0 && batch > 64);
     r.materialised = !r.staged;
     r.cf = cf;
-    if (r.staged && !r.d_frames) {
-        const size_t B = ctx->cfg.max_batch, C = ctx->cap.C, A = ctx->cap.A;
-        RMCV_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&r.d_frames), B * sizeof(rmcv_frame_info)));
-        RMCV_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&r.d_contours), B * C * sizeof(rmcv_contour_info)));
-        RMCV_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&r.d_blobs), B * C * sizeof(rmcv_lightblob)));
-        RMCV_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&r.d_armours), B * A * sizeof(rmcv_armour)));
-    }
+    if (r.staged && !r.d_frames) RMCV_CUDA(ctx, alloc_result_mirror(ctx, r));
     ex->o_frames = r.staged ? r.d_frames : r.frames; ex->o_contours = r.staged ? r.d_contours : r.contours;
     ex->o_blobs = r.staged ? r.d_blobs : r.blobs; ex->o_armours = r.staged ? r.d_armours : r.armours;
     return RMCV_OK;
@@ -582,7 +585,14 @@ int rmcv_ctx_create(const rmcv_config* cfg, rmcv_ctx** out) {
     for (int i = 0; i < ctx->n_slots && rc == RMCV_OK; ++i) rc = alloc_slot(ctx, ctx->slot[i], i == 0);
     if (rc != RMCV_OK) return fail(rc);
     cudaError_t e = cudaSuccess;
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = alloc_result_set(ctx, extra(ctx)->rs[i]);   // sets 2.. on first use
+    // every result set (and, for ctxs that will see batches above 64 frames, its device mirror) up front: an allocation
+    // inside a detect call would stall that call by tens of milliseconds
+    for (int i = 0; i < kResultSets && e == cudaSuccess; ++i) {
+        ResultSet& r = extra(ctx)->rs[i];
+        e = alloc_result_set(ctx, r);
+        const int mode = tuning().staged_out;
+        if (e == cudaSuccess && (mode > 0 || (mode < 0 && cfg->max_batch > 64))) e = alloc_result_mirror(ctx, r);
+    }
     if (e != cudaSuccess) {
         snprintf(ctx->err, sizeof(ctx->err), "pinned result allocation failed: %s", cudaGetErrorString(e));
         return fail(RMCV_ERR_CUDA);

@@ -84,3 +84,34 @@ def test_shim_extract_color_grows_capacities_instead_of_truncating():
     assert got["contour_sizes"] == [len(c) for c in ref.contours]
     assert got["first_points"] == [[int(c[0][0]), int(c[0][1])] for c in ref.contours]
     assert got["n_positive"] == len(ref.positive) and got["n_armours"] == len(ref.armours)
+
+
+def test_cpp_call_site_in_reference_mode():
+    """The shim's RMCV_SHIM_WITH_REFERENCE mode: the call site compiled with the REFERENCE'S OWN include/core.h and
+    src/core.cpp (from /root/reference, against oracle/cvstub), so rm::lightblob / rm::armour are the reference's classes,
+    rebuilt through their own constructors from the GPU's ellipses and pair indices (oracle/_ref/call_site_ref, built where
+    /root/reference exists).  Every blob and armour field must equal the oracle's."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "call_site_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/call_site_ref not built (needs /root/reference)")
+    frame = synth.make_frame(21, 1280, 1024, 9)
+    ref = O.detect_frame(frame)
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as fh:
+        fh.write(np.array([1280, 1024], np.int32).tobytes())
+        fh.write(frame.tobytes())
+        path = fh.name
+    try:
+        out = subprocess.run([exe, path], check=True, capture_output=True, text=True, timeout=120).stdout
+    finally:
+        os.unlink(path)
+    got = json.loads(out)
+    assert got["n_contours"] == len(ref.contours) and got["n_positive"] == len(ref.positive)
+    assert got["n_negative"] == len(ref.negative) and got["n_armours"] == len(ref.armours) > 0
+    assert got["mask_fg"] == int((ref.binary == 255).sum())
+    assert got["identity0"] == -1 and got["lost0"] == 0          # the reference's default member initialisers (include/core.h:114-117)
+    for g, b in zip(got["blobs"], ref.positive):
+        want = [b.angle, b.target, b.center[0], b.center[1], b.size[0], b.size[1]] + [float(v) for v in np.asarray(b.vertices).ravel()]
+        assert np.abs(np.asarray(g, np.float64) - np.asarray(want, np.float64)).max() <= 2e-3, (g, want)
+    for g, a in zip(got["armours"], ref.armours):
+        want = list(a.bounding_box) + [float(v) for v in a.icon.ravel()] + [float(v) for v in a.vertices.ravel()]
+        assert np.abs(np.asarray(g, np.float64) - np.asarray(want, np.float64)).max() <= 2e-3, (g, want)
