@@ -125,6 +125,7 @@ int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
     const size_t CF = ctx->CF, H = g.H, WB = g.WB, R = g.R, C = g.C, A = g.A, PC = g.PC, SC = g.SC;
     memset(&sb, 0, sizeof(sb));
     RMCV_CUDA(ctx, dalloc(&sb.bits, CF * H * WB));
+    RMCV_CUDA(ctx, dalloc(&sb.band_flags, CF * ((H + 7) / 8)));
     RMCV_CUDA(ctx, dalloc(&sb.rows, CF * H));
     RMCV_CUDA(ctx, dalloc(&sb.run_x, CF * R));
     RMCV_CUDA(ctx, dalloc(&sb.run_y, CF * R));
@@ -155,7 +156,7 @@ int alloc_slot(rmcv_ctx* ctx, SlotBuffers& sb, bool first) {
 }
 
 void free_slot(SlotBuffers& sb) {
-    cudaFree(sb.bits); cudaFree(sb.rows); cudaFree(sb.run_x); cudaFree(sb.run_y);
+    cudaFree(sb.bits); cudaFree(sb.band_flags); cudaFree(sb.rows); cudaFree(sb.run_x); cudaFree(sb.run_y);
     cudaFree(sb.parent); cudaFree(sb.gparent); cudaFree(sb.run_cid); cudaFree(sb.sorted); cudaFree(sb.recs); cudaFree(sb.recs2); cudaFree(sb.comp_start); cudaFree(sb.acc); cudaFree(sb.comp_root); cudaFree(sb.comp_cnt); cudaFree(sb.comps);
     cudaFree(sb.counters); cudaFree(sb.s_contours); cudaFree(sb.s_blobs); cudaFree(sb.s_armours); cudaFree(sb.arm_offset);
     if (sb.frames) cudaFree(sb.frames);
@@ -233,13 +234,14 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
     pl.bits = sb.bits; pl.W = W; pl.H = H; pl.batch = frames;
     pl.target = prm.target; pl.lower_bound = prm.lower_bound; pl.bayer_layout = bayer_layout;
     EmitLaunch el;
-    int emit_done = 0;
+    int emit_done = 0, flags_bh = 0;
     if (full) {   // the fixed-geometry BGR kernel can cut the runs / boundary records itself
         const Geometry cg = call_geometry(ctx, W, H);
         el.bits = sb.bits; el.W = W; el.H = H; el.batch = frames;
         el.rows = sb.rows; el.run_x = sb.run_x; el.run_y = sb.run_y; el.counters = sb.counters; el.R = cg.R;
         el.recs = sb.recs; el.PC = cg.PC;
         pl.emit = &el; pl.emit_done = &emit_done;
+        pl.band_flags = sb.band_flags; pl.flags_bh = &flags_bh;
     }
     RMCV_CUDA(ctx, launch_pixel_stage(pl, ctx->sm_count, sp, &ctx->kernel_launches));
     if (ps) cudaEventRecord(ps->pix[1], sp);
@@ -252,6 +254,7 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
     fl.g = call_geometry(ctx, W, H); fl.frames = frames; fl.sb = &sb; fl.frame_base = frame_base;
     fl.st_out = ex->out;
     fl.emit_done = emit_done;
+    fl.flags_bh = flags_bh;
     fl.o_frames = ex->o_frames; fl.o_contours = ex->o_contours; fl.o_blobs = ex->o_blobs; fl.o_armours = ex->o_armours;
     fl.o_poses = ex->have_camera ? ctx->h_poses : nullptr; fl.camera = ex->have_camera ? &ex->camera : nullptr;
     struct Mark { ProfSet* ps; rmcv_ctx* ctx; };

@@ -65,6 +65,7 @@ constexpr int kSlots = 8;          // upper bound; a ctx uses n_slots of them (d
 struct SlotBuffers {
     // pixel stage outputs
     uint32_t* bits;         // [CF][H][WB]   final mask, bit-packed
+    uint8_t* band_flags;    // [CF][ceil(H/8)] 1 = the band's own rows hold foreground (written by the BGR band kernel, read by emit)
     // runs (emitted by the pixel kernel; rows of one band are contiguous, bands land in arrival order)
     int2* rows;             // [CF][H]       (first run, one-past-last run) of each row
     uint32_t* run_x;        // [CF][R]       xs | xe<<16
@@ -149,6 +150,7 @@ inline int set_err(rmcv_ctx* ctx, int code, const char* msg) {
 // ---- launchers implemented in the .cu files -----------------------------------------------
 struct EmitLaunch {
     const uint32_t* bits; int W, H, batch;
+    const uint8_t* band_flags = nullptr; int flag_bh = 0, flag_bands = 0;   // per-band "has foreground" flags of the pixel kernel, if it wrote them
     int2* rows; uint32_t* run_x; uint16_t* run_y; FrameCounters* counters; int R;
     uint2* recs; int PC;
 };
@@ -159,6 +161,8 @@ struct PixelLaunch {
     int W, H, batch;
     int target, lower_bound;
     int bayer_layout;   // 0 = BGR input
+    uint8_t* band_flags = nullptr;      // full calls: one byte per band, 1 = its own rows hold foreground
+    int* flags_bh = nullptr;            // receives the band height the flags were written for (0 = not written)
     const EmitLaunch* emit = nullptr;   // full calls: where the labelling stage's runs / records go, if the pixel kernel can emit them
     int* emit_done = nullptr;           // set to 1 when it did (the separate emit launch is then skipped)
 };
@@ -181,6 +185,7 @@ struct FrameLaunch {
     rmcv_pose* o_poses;           // null unless a camera is set
     const CameraSetup* camera;
     int emit_done = 0;            // the pixel kernel already emitted the runs / records (fused pixel+emit kernel)
+    int flags_bh = 0;             // band height of sb->band_flags as written by the pixel kernel of this chunk (0 = none)
 };
 // everything after the pixel stage for one chunk (five launches: emit, label, contour sums, fits, order/pairs/write-out);
 // stage_done(arg, RMCV_STAGE_*, stream) is called after each launch (profiling events), may be null

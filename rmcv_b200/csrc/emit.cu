@@ -28,6 +28,12 @@ __global__ void __launch_bounds__(128) emit_kernel(const EmitParams p) {
     const int H = p.H, WB = p.WB;
     const int y0 = band * p.BH;
     const int nout = min(p.BH, H - y0);
+    if (p.band_flags != nullptr && p.band_flags[(size_t)frame * p.bands + band] == 0) {
+        // the pixel kernel saw no foreground in this band's rows: no runs, no records, nothing to load
+        int2* rows = p.rows + (size_t)frame * H;
+        for (int j = threadIdx.x; j < nout; j += 128) rows[y0 + j] = make_int2(0, 0);
+        return;
+    }
     const int nwords = nout * WB, cap = p.BH * WB;
     auto row_of = [&](int idx) -> int { return p.inv_wb ? (int)__umulhi((uint32_t)idx, p.inv_wb) : idx; };  // idx / WB
     long long* scratch = reinterpret_cast<long long*>(smem);        // 34 long longs of scan scratch
@@ -125,6 +131,7 @@ cudaError_t launch_emit(const EmitLaunch& L, cudaStream_t st, int64_t* launches)
     if (BH > L.H) BH = L.H;
     p.BH = BH; p.bands = (L.H + BH - 1) / BH;
     p.inv_wb = p.WB > 1 ? (uint32_t)((1ull << 32) / (unsigned)p.WB) + 1u : 0u;   // 0: WB == 1
+    p.band_flags = (L.band_flags != nullptr && L.flag_bh == p.BH && L.flag_bands == p.bands) ? L.band_flags : nullptr;
     if (L.batch <= 0 || L.batch > 65535) return cudaErrorInvalidValue;
     const size_t cap = (size_t)BH * p.WB;
     const size_t smem = 36 * 8 + 2 * (cap + 1) * 4 + 16 + (size_t)(BH + 2) * p.WB * 4 + cap * 2 + 16;

@@ -12,6 +12,7 @@ struct EmitParams {
     uint32_t inv_wb;        // floor(2^32 / WB) + 1: idx / WB == umulhi(idx, inv_wb) for idx < 2^20; 0 when WB == 1
     int2* rows; uint32_t* run_x; uint16_t* run_y; FrameCounters* counters; int R;
     uint2* recs; int PC;
+    const uint8_t* band_flags;   // one byte per (frame, band) or null: 0 = the band's own rows are all background
 };
 
 

@@ -656,36 +656,39 @@ struct FitParams {
 
 __global__ void __launch_bounds__(64) fit_kernel(const FitParams p) {
     const int frame = blockIdx.y;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int C = p.g.C;
-    if (c >= p.sb.counters[frame].n_comps) return;
-    const CompAcc& a = p.sb.acc[(size_t)frame * C + c];
-    CompRec rec;
-    const int n = (int)a.n;
-    rec.firstkey = n > 0 ? a.firstkey : -1;
-    rec.n_points = n;
-    rec.area2 = a.cross < 0 ? -a.cross : a.cross;
-    rec.bbox[0] = a.bbox[0]; rec.bbox[1] = a.bbox[1]; rec.bbox[2] = a.bbox[2]; rec.bbox[3] = a.bbox[3];
-    rec.status = -1;
-    rec.fit_branch = RMCV_FIT_NONE;
-    rec.det0 = 0.f;
-    memset(&rec.blob, 0, sizeof(rec.blob));
-    memset(&rec.ellipse, 0, sizeof(rec.ellipse));
-    if (n > 0) {  // external component
-        ContourSums cs;
-        cs.n = a.n; cs.sx = a.sx; cs.sy = a.sy; cs.cross = a.cross;
-        cs.xx = a.xx; cs.xy = a.xy; cs.yy = a.yy; cs.xxx = a.xxx; cs.xxy = a.xxy; cs.xyy = a.xyy; cs.yyy = a.yyy;
-        cs.xxxx = a.xxxx; cs.xxxy = a.xxxy; cs.xxyy = a.xxyy; cs.xyyy = a.xyyy; cs.yyyy = a.yyyy;
-        cs.s_int = a.s_int; cs.ox = a.ox; cs.oy = a.oy;
-        fit_contour(cs, p.prm, &rec.status, &rec.fit_branch, &rec.det0, &rec.ellipse, &rec.blob);
-        // the 4th-order sums are exact 64-bit integers about the component's root pixel: n * extent^4 must stay below 2^62
-        // (never reached with the reference's area_max = 99999; a caller who raises it gets the frame flagged, not a wrong fit)
-        if (a.fitted) {
-            const double ext = (double)max(a.bbox[2] - a.bbox[0], a.bbox[3] - a.bbox[1]) + 1.0;
-            if ((double)a.n * ext * ext * ext * ext > 4.6e18) atomicOr(&p.sb.counters[frame].flags, RMCV_FRAME_OVERFLOW_MOMENTS);
+    const int n_comps = p.sb.counters[frame].n_comps;
+    // a frame has ~36 components: two CTAs of 64 threads per frame cover it in one round (a grid over the capacity C would
+    // launch C/64 CTAs per frame that find nothing to do)
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_comps; c += gridDim.x * blockDim.x) {
+        const CompAcc& a = p.sb.acc[(size_t)frame * C + c];
+        CompRec rec;
+        const int n = (int)a.n;
+        rec.firstkey = n > 0 ? a.firstkey : -1;
+        rec.n_points = n;
+        rec.area2 = a.cross < 0 ? -a.cross : a.cross;
+        rec.bbox[0] = a.bbox[0]; rec.bbox[1] = a.bbox[1]; rec.bbox[2] = a.bbox[2]; rec.bbox[3] = a.bbox[3];
+        rec.status = -1;
+        rec.fit_branch = RMCV_FIT_NONE;
+        rec.det0 = 0.f;
+        memset(&rec.blob, 0, sizeof(rec.blob));
+        memset(&rec.ellipse, 0, sizeof(rec.ellipse));
+        if (n > 0) {  // external component
+            ContourSums cs;
+            cs.n = a.n; cs.sx = a.sx; cs.sy = a.sy; cs.cross = a.cross;
+            cs.xx = a.xx; cs.xy = a.xy; cs.yy = a.yy; cs.xxx = a.xxx; cs.xxy = a.xxy; cs.xyy = a.xyy; cs.yyy = a.yyy;
+            cs.xxxx = a.xxxx; cs.xxxy = a.xxxy; cs.xxyy = a.xxyy; cs.xyyy = a.xyyy; cs.yyyy = a.yyyy;
+            cs.s_int = a.s_int; cs.ox = a.ox; cs.oy = a.oy;
+            fit_contour(cs, p.prm, &rec.status, &rec.fit_branch, &rec.det0, &rec.ellipse, &rec.blob);
+            // the 4th-order sums are exact 64-bit integers about the component's root pixel: n * extent^4 must stay below 2^62
+            // (never reached with the reference's area_max = 99999; a caller who raises it gets the frame flagged, not a wrong fit)
+            if (a.fitted) {
+                const double ext = (double)max(a.bbox[2] - a.bbox[0], a.bbox[3] - a.bbox[1]) + 1.0;
+                if ((double)a.n * ext * ext * ext * ext > 4.6e18) atomicOr(&p.sb.counters[frame].flags, RMCV_FRAME_OVERFLOW_MOMENTS);
+            }
         }
+        p.sb.comps[(size_t)frame * C + c] = rec;
     }
-    p.sb.comps[(size_t)frame * C + c] = rec;
 }
 
 // ------------------------------------------------------------------------------------------ K_O: order, pairs, output
@@ -976,6 +979,7 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         el.bits = L.sb->bits; el.W = L.g.W; el.H = L.g.H; el.batch = L.frames;
         el.rows = L.sb->rows; el.run_x = L.sb->run_x; el.run_y = L.sb->run_y; el.counters = L.sb->counters; el.R = L.g.R;
         el.recs = L.sb->recs; el.PC = L.g.PC;
+        if (L.flags_bh > 0) { el.band_flags = L.sb->band_flags; el.flag_bh = L.flags_bh; el.flag_bands = (L.g.H + L.flags_bh - 1) / L.flags_bh; }
         e = launch_emit(el, st, launches);
         if (e != cudaSuccess) return e;
         done(RMCV_STAGE_EMIT);
@@ -1026,7 +1030,9 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
     {   // K_C
         ContourParams p;
         p.g = L.g; p.sb = *L.sb; p.prm = prm;
-        int gy = tune.contour_gy > 0 ? tune.contour_gy : 8;                      // 8 blocks x 4 warps per frame
+        // CTAs of four warps per frame: eight for small chunks (a warp per component and round: latency), two for large ones
+        // (1024 frames: 2048 fat CTAs instead of 8192 thin ones, 1.188 -> 1.175 ms per step; gpu_exp_t.sh)
+        int gy = tune.contour_gy > 0 ? tune.contour_gy : (L.frames >= 128 ? 2 : 8);
         if (gy * 4 > L.g.C) gy = (L.g.C + 3) / 4;
         if (gy < 1) gy = 1;
         dim3 grid(L.frames, gy);
@@ -1040,7 +1046,9 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
     {   // K_F
         FitParams p;
         p.g = L.g; p.sb = *L.sb; p.prm = prm;
-        dim3 grid((L.g.C + 63) / 64, L.frames);
+        // ordinary frames: two CTAs per frame; large capacities (stress frames, ~510 components): one per 64 components
+        const int gx_full = (L.g.C + 63) / 64;
+        dim3 grid(L.g.C > 512 ? gx_full : (gx_full < 2 ? gx_full : 2), L.frames);
         const size_t pad = tune.chain_pad > 0 ? (size_t)tune.chain_pad : 0;
         if (pad > 48 * 1024) cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
         fit_kernel<<<grid, 64, pad, st>>>(p);

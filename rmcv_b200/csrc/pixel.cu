@@ -84,6 +84,7 @@ struct PixelParams {
     int px, py;          // parity (x&1, y&1) of the site that samples channel `plus`... see kernel
     int plus_is_site;    // layout helpers, see bayer kernel
     int lb;
+    uint8_t* band_flags; // one byte per (frame, band): 1 = the band's own rows hold foreground (null: not wanted)
     EmitParams em;       // fused pixel+emit kernel only: where the band's runs and boundary-pixel records go
 };
 
@@ -174,6 +175,7 @@ __device__ __forceinline__ void close_and_store(const PixelParams& p, uint32_t* 
     __syncthreads();
     // ---- erode: rows y0 .. y0+nout-1; result into m (compact [nout][WB]) and to the global bit mask
     uint32_t* m = t;   // t and m alias: every thread reads d only and writes m; t was last read before the barrier
+    uint32_t any_fg = 0u;
     {
         uint32_t* gbits = p.bits + ((size_t)frame * H + y0) * WB;
         const int per = (nout + nseg - 1) / nseg;
@@ -197,11 +199,15 @@ __device__ __forceinline__ void close_and_store(const PixelParams& p, uint32_t* 
                 if (last) mv &= valid;
                 mp[0] = mv;
                 gp[0] = mv;
+                any_fg |= mv;
                 h0 = h1; h1 = h2;
             }
         }
     }
-    __syncthreads();
+    {   // barrier + "does this band hold any foreground": lets the emit kernel skip empty bands without loading them
+        const int any = __syncthreads_or(any_fg != 0u);
+        if (tid == 0 && p.band_flags != nullptr) p.band_flags[(size_t)frame * p.bands + y0 / p.BH] = any ? 1 : 0;
+    }
     // ---- byte mask: one 16-byte store per 16 pixels, a thread walks down one 16-pixel column
     if (p.mask != nullptr) {
         const uint16_t* m16 = reinterpret_cast<const uint16_t*>(m);
@@ -722,6 +728,8 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
 
         p.gpr = (L.W + 15) / 16;
         p.srow = p.gpr * 48;
+        p.band_flags = L.band_flags;
+        if (L.flags_bh) *L.flags_bh = L.band_flags ? p.BH : 0;
         const bool bulk = ((L.W & 15) == 0) && ((L.pitch & 15) == 0) && ((L.frame_stride & 15) == 0) &&
                           ((((size_t)L.src) & 15) == 0) && tune.pix_nobulk == 0;
         p.contiguous = (L.pitch == (size_t)L.W * 3) ? 1 : 0;
