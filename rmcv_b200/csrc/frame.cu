@@ -1032,7 +1032,7 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         p.g = L.g; p.sb = *L.sb; p.prm = prm;
         // CTAs of four warps per frame: eight for small chunks (a warp per component and round: latency), two for large ones
         // (1024 frames: 2048 fat CTAs instead of 8192 thin ones, 1.188 -> 1.175 ms per step; gpu_exp_t.sh)
-        int gy = tune.contour_gy > 0 ? tune.contour_gy : (L.frames >= 128 ? 2 : 8);
+        int gy = tune.contour_gy > 0 ? tune.contour_gy : (L.frames >= 512 ? 1 : L.frames >= 128 ? 2 : 8);
         if (gy * 4 > L.g.C) gy = (L.g.C + 3) / 4;
         if (gy < 1) gy = 1;
         dim3 grid(L.frames, gy);

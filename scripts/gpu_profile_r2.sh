@@ -10,7 +10,7 @@ $BENCH_SMALL > $OUT/bench_small_$TAG.json 2> $OUT/bench_small_$TAG.err || { echo
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv $BENCH_SMALL > $OUT/ncu_launches_$TAG.log 2>&1
 echo "ncu launches rc=$?"
 for k in pixel_bgr_kernel emit_kernel label_kernel contour_kernel fit_kernel order_kernel; do
-  ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 1 -f -o $OUT/${k}_$TAG $BENCH_SMALL > $OUT/ncu_full_${k}_$TAG.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $OUT/${k}_$TAG $BENCH_SMALL > $OUT/ncu_full_${k}_$TAG.log 2>&1
   echo "ncu full $k rc=$?"
 done
 python scripts/bayer_bench.py > $OUT/bayer_bench_$TAG.log 2>&1 && \
