@@ -69,6 +69,7 @@ struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
     cudaStream_t labs[kSlots] = {};   // labelling stream of each slot (labs[0] == lab)
     long long chunk_counter = 0;      // chunks enqueued over the life of the ctx
     int last_first_slot = 0;          // slot of chunk 0 of the last call
+    cudaStream_t chain = nullptr;     // stream of the current call's chained chunk (small chunks), else null
     bool own_pix = false;
     // where the write-out kernels of the current call put their records (pinned host arrays or the device mirrors)
     rmcv_frame_info* o_frames = nullptr; rmcv_contour_info* o_contours = nullptr; rmcv_lightblob* o_blobs = nullptr;
@@ -95,7 +96,7 @@ Tuning read_tuning() {
     t.bgr_strip = env_or("RMCV_BGR_STRIP", 0); t.bandstrip_rc = env_or("RMCV_BANDSTRIP_RC", -1);
     t.bayer_generic = env_or("RMCV_BAYER_GENERIC", 0); t.strip_seg = env_or("RMCV_STRIP_SEG", -1); t.strip_minb = env_or("RMCV_STRIP_MINB", -1);
     t.host_chunk = env_or("RMCV_HOST_CHUNK", -1); t.staged_out = env_or("RMCV_STAGED_OUT", -1);
-    t.fused_emit = env_or("RMCV_FUSED_EMIT", -1); t.wide_label = env_or("RMCV_WIDE_LABEL", -1); t.graph = env_or("RMCV_GRAPH", -1);
+    t.fused_emit = env_or("RMCV_FUSED_EMIT", -1); t.wide_label = env_or("RMCV_WIDE_LABEL", -1); t.chained = env_or("RMCV_CHAINED", -1);
     t.chain_pad = env_or("RMCV_CHAIN_PAD", -1);
     return t;
 }
@@ -216,11 +217,25 @@ void prof_collect(rmcv_ctx* ctx) {  // after a sync
 // Enqueue all stages for `frames` frames whose pixels are at `src`, using the scratch of slot `sb`.
 int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pitch, size_t frame_stride, int W, int H,
                   int frames, int frame_base, int bayer_layout, const rmcv_params& prm, uint8_t* mask, size_t mask_pitch,
-                  size_t mask_frame_stride, bool full) {
+                  size_t mask_frame_stride, bool full, bool host_path = false) {
     CtxExtra* ex = extra(ctx);
     // each slot has its own labelling stream: the labelling kernels of consecutive chunks are latency-bound and overlap
     // each other as well as the pixel kernels
-    cudaStream_t sp = ex->pix, sl = ex->labs[&sb - ctx->slot];
+    // small chunks of ordinary frames (latency mode): all six kernels on the pixel stream, each a programmatic dependent of
+    // the one before (common.cuh: chain_begin / chain_wait) - no cross-stream hops, launch gaps hidden
+    // (the slot's own stream, so that consecutive small calls still overlap; a caller-supplied stream keeps everything)
+    const bool chained = full && frames <= small_batch_limit() && ctx->cap.R <= 65535 && tuning().chained != 0;
+    cudaStream_t sl = ex->labs[&sb - ctx->slot];
+    cudaStream_t sp = chained && ex->own_pix ? sl : ex->pix;
+    if (chained) {
+        sl = sp;
+        ex->chain = sp;
+        if (sp != ex->pix) {   // what the pixel stream would have been ordered after
+            ResultSet& r = ex->rs[ex->n_calls % kResultSets];   // the set's previous call (kResultSets calls back) must be done
+            if (r.done[0]) { RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, r.done[0], 0)); RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, r.done[1], 0)); }
+            if (host_path) RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, sb.ev_h2d, 0));
+        }
+    }
     // the slot's scratch is free once the labelling stages (and the mask download) of its previous chunk are done
     RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, sb.ev_lab, 0));
     RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, sb.ev_d2h, 0));
@@ -245,14 +260,16 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
     }
     RMCV_CUDA(ctx, launch_pixel_stage(pl, ctx->sm_count, sp, &ctx->kernel_launches));
     if (ps) cudaEventRecord(ps->pix[1], sp);
-    RMCV_CUDA(ctx, cudaEventRecord(sb.ev_pix, sp));
+    // (only the host path waits for ev_pix; an event between two kernels would undo the chained launch of the second)
+    if (!chained || host_path) RMCV_CUDA(ctx, cudaEventRecord(sb.ev_pix, sp));
     ctx->prof_launches[RMCV_STAGE_PIXEL] += ctx->kernel_launches - l0;
     if (!full) return RMCV_OK;
-    RMCV_CUDA(ctx, cudaStreamWaitEvent(sl, sb.ev_pix, 0));
+    if (sl != sp) RMCV_CUDA(ctx, cudaStreamWaitEvent(sl, sb.ev_pix, 0));
     if (ps) { ps->full = true; cudaEventRecord(ps->lab[0], sl); }
     FrameLaunch fl;
     fl.g = call_geometry(ctx, W, H); fl.frames = frames; fl.sb = &sb; fl.frame_base = frame_base;
-    fl.st_out = ex->out;
+    fl.st_out = chained ? nullptr : ex->out;
+    fl.chained = chained ? 1 : 0;
     fl.emit_done = emit_done;
     fl.flags_bh = flags_bh;
     fl.o_frames = ex->o_frames; fl.o_contours = ex->o_contours; fl.o_blobs = ex->o_blobs; fl.o_armours = ex->o_armours;
@@ -265,7 +282,7 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
         m->ctx->prof_launches[stage] += 1;
     };
     RMCV_CUDA(ctx, launch_frames(fl, prm, ctx->max_smem_optin, sl, &ctx->kernel_launches, stage_done, &mk));
-    RMCV_CUDA(ctx, cudaEventRecord(sb.ev_lab, ex->out));
+    RMCV_CUDA(ctx, cudaEventRecord(sb.ev_lab, chained ? sp : ex->out));
     return RMCV_OK;
 }
 
@@ -301,6 +318,9 @@ int begin_call(rmcv_ctx* ctx, int batch = 0, int cf = 0) {
         RMCV_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&r.poses), (size_t)ctx->cfg.max_batch * ctx->cap.A * sizeof(rmcv_pose),
                                      cudaHostAllocMapped | cudaHostAllocPortable));
     r.pending = false;  // an unfetched call kResultSets calls back is dropped
+    // that call wrote this set from the write-out stream or, chained, from a slot stream: this call's work comes after it
+    RMCV_CUDA(ctx, cudaStreamWaitEvent(ex->pix, r.done[0], 0));
+    RMCV_CUDA(ctx, cudaStreamWaitEvent(ex->pix, r.done[1], 0));
     ctx->h_frames = r.frames; ctx->h_contours = r.contours; ctx->h_blobs = r.blobs; ctx->h_armours = r.armours;
     ctx->h_poses = r.poses;
     r.with_poses = ex->have_camera && r.poses;
@@ -319,7 +339,8 @@ int end_call(rmcv_ctx* ctx, int batch) {
     if (r.staged)   // the per-frame counts and offsets travel first; the dense records follow when the call is fetched
         RMCV_CUDA(ctx, cudaMemcpyAsync(r.frames, r.d_frames, (size_t)batch * sizeof(rmcv_frame_info), cudaMemcpyDeviceToHost, ex->out));
     RMCV_CUDA(ctx, cudaEventRecord(r.done[0], ex->out));
-    RMCV_CUDA(ctx, cudaEventRecord(r.done[1], ex->pix));
+    RMCV_CUDA(ctx, cudaEventRecord(r.done[1], ex->chain ? ex->chain : ex->pix));
+    ex->chain = nullptr;
     r.batch = batch; r.pending = true; r.call_id = ex->n_calls++;
     return RMCV_OK;
 }
@@ -798,7 +819,7 @@ static int run_host_batch(rmcv_ctx* ctx, const uint8_t* h_bgr, size_t pitch, siz
         RMCV_CUDA(ctx, cudaEventRecord(sb.ev_h2d, ex->h2d));
         RMCV_CUDA(ctx, cudaStreamWaitEvent(ex->pix, sb.ev_h2d, 0));
         rc = enqueue_chunk(ctx, sb, sb.frames, rowbytes, dev_frame, width, height, frames, f0, bayer_layout, *params,
-                           h_mask ? sb.masks : nullptr, width, dev_mask, true);
+                           h_mask ? sb.masks : nullptr, width, dev_mask, true, true);
         if (rc != RMCV_OK) return rc;
         if (h_mask) {
             uint8_t* hdst = h_mask + (size_t)f0 * mask_frame_stride;

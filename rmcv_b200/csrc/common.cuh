@@ -186,13 +186,14 @@ struct FrameLaunch {
     const CameraSetup* camera;
     int emit_done = 0;            // the pixel kernel already emitted the runs / records (fused pixel+emit kernel)
     int flags_bh = 0;             // band height of sb->band_flags as written by the pixel kernel of this chunk (0 = none)
+    int chained = 0;              // small chunk on ONE stream: every kernel is launched as a programmatic dependent of the one before
 };
 // everything after the pixel stage for one chunk (five launches: emit, label, contour sums, fits, order/pairs/write-out);
 // stage_done(arg, RMCV_STAGE_*, stream) is called after each launch (profiling events), may be null
 cudaError_t launch_frames(const FrameLaunch& p, const rmcv_params& prm, int max_smem_optin, cudaStream_t st, int64_t* launches,
                           void (*stage_done)(void*, int, cudaStream_t), void* stage_arg);
 
-cudaError_t launch_emit(const EmitLaunch& p, cudaStream_t st, int64_t* launches);
+cudaError_t launch_emit(const EmitLaunch& p, cudaStream_t st, int64_t* launches, bool chained = false);
 
 cudaError_t launch_trace_contour(const Geometry& g, const uint32_t* bits, int x0, int y0, int32_t* d_xy, int cap,
                                  int32_t* d_n, cudaStream_t st, int64_t* launches);
@@ -253,9 +254,49 @@ struct Tuning {
     int bgr_strip, bandstrip_rc, bayer_generic, strip_seg, strip_minb;   // alternative pixel kernels
     int staged_out;                                                  // result write-out through device staging: -1 auto, 0 never, 1 always
     int host_chunk;                                                  // frames per chunk of the host-input entry points
-    int fused_emit, wide_label, graph;
+    int fused_emit, wide_label, chained;
     int chain_pad;                                                   // experiment: pad the labelling kernels' dynamic shared memory to this many bytes per CTA                               // round-2 paths (emit inside the pixel kernel, ...)
 };
 const Tuning& tuning();  // copies the arc LUT to constant memory (once per process/device)
+
+
+// Programmatic dependent launch (small chunks, latency mode): a chunk's six kernels sit on one stream and each is launched
+// with cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs become resident while its predecessor still runs and
+// the 3-4 us launch gap between dependent kernels shrinks to the wake-up out of griddepcontrol.wait.  Every kernel of the
+// chain calls chain_begin() first (lets ITS successor be scheduled) and chain_wait() before it touches global memory that a
+// predecessor reads or writes.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void chain_begin() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// at most this many frames: per-frame kernels take their wide variants and the chunk runs chained on one stream
+inline int small_batch_limit() { return tuning().small_batch >= 0 ? tuning().small_batch : 16; }
+
+template <class Params>
+inline cudaError_t launch_chained(void (*k)(Params), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool chained, const Params& p) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = chained ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k, p);
+}
+
+// Kernel begin / end stamps on the global timer, for the launch-gap anatomy of scripts/phase_stamps.py: only in a
+// -DRMCV_STAMPS build (the product library has none).  One array per translation unit (no relocatable device code).
+#ifdef RMCV_STAMPS
+#define RMCV_GSTAMP_ARRAY(name) __device__ unsigned long long name[8][2];
+__device__ __forceinline__ unsigned long long gstamp_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define RMCV_GSTAMP_BEGIN(arr, k) do { if (threadIdx.x == 0) atomicMin(&arr[k][0], gstamp_now()); } while (0)
+#define RMCV_GSTAMP_END(arr, k) do { __syncthreads(); if (threadIdx.x == 0) atomicMax(&arr[k][1], gstamp_now()); } while (0)
+#define RMCV_GSTAMP_GETTER(fn, arr) extern "C" int fn(unsigned long long* out, int reset) { \
+    cudaError_t e = cudaMemcpyFromSymbol(out, arr, sizeof(arr)); \
+    if (reset) { unsigned long long z[8][2]; for (int i = 0; i < 8; ++i) { z[i][0] = ~0ull; z[i][1] = 0ull; } e = cudaMemcpyToSymbol(arr, z, sizeof(z)); } \
+    return (int)e; }
+#else
+#define RMCV_GSTAMP_ARRAY(name)
+#define RMCV_GSTAMP_BEGIN(arr, k) do { } while (0)
+#define RMCV_GSTAMP_END(arr, k) do { } while (0)
+#define RMCV_GSTAMP_GETTER(fn, arr)
+#endif
 
 }  // namespace rmcv

@@ -18,9 +18,11 @@
 namespace rmcv {
 
 // kVec: WB % 4 == 0 -> the band is loaded with 128-bit loads and the non-zero test rides on the load.
+RMCV_GSTAMP_ARRAY(g_ns_emit)
 template <bool kVec>
 __global__ void __launch_bounds__(128) emit_kernel(const EmitParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
+    RMCV_GSTAMP_BEGIN(g_ns_emit, 0);
     __shared__ int s_wtot[4], s_base[2];
     constexpr int NT = 128, nwarps = 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -28,10 +30,13 @@ __global__ void __launch_bounds__(128) emit_kernel(const EmitParams p) {
     const int H = p.H, WB = p.WB;
     const int y0 = band * p.BH;
     const int nout = min(p.BH, H - y0);
+    chain_begin();
+    chain_wait();
     if (p.band_flags != nullptr && p.band_flags[(size_t)frame * p.bands + band] == 0) {
         // the pixel kernel saw no foreground in this band's rows: no runs, no records, nothing to load
         int2* rows = p.rows + (size_t)frame * H;
         for (int j = threadIdx.x; j < nout; j += 128) rows[y0 + j] = make_int2(0, 0);
+        RMCV_GSTAMP_END(g_ns_emit, 0);
         return;
     }
     const int nwords = nout * WB, cap = p.BH * WB;
@@ -114,9 +119,10 @@ __global__ void __launch_bounds__(128) emit_kernel(const EmitParams p) {
         }
     }
     emit_tail<NT>(p, frame, y0, nout, n_ent, m, list, erun, erec, scratch, s_base, tid);
+    RMCV_GSTAMP_END(g_ns_emit, 0);
 }
 
-cudaError_t launch_emit(const EmitLaunch& L, cudaStream_t st, int64_t* launches) {
+cudaError_t launch_emit(const EmitLaunch& L, cudaStream_t st, int64_t* launches, bool chained) {
     EmitParams p;
     p.bits = L.bits; p.W = L.W; p.H = L.H; p.WB = (L.W + 31) / 32;
     p.rows = L.rows; p.run_x = L.run_x; p.run_y = L.run_y; p.counters = L.counters; p.R = L.R;
@@ -144,10 +150,11 @@ cudaError_t launch_emit(const EmitLaunch& L, cudaStream_t st, int64_t* launches)
         if (e != cudaSuccess) return e;
     }
     dim3 grid(p.bands, L.batch);
-    if (vec) emit_kernel<true><<<grid, 128, smem_l, st>>>(p);
-    else emit_kernel<false><<<grid, 128, smem_l, st>>>(p);
+    const cudaError_t e = vec ? launch_chained<EmitParams>(emit_kernel<true>, grid, dim3(128), smem_l, st, chained, p)
+                              : launch_chained<EmitParams>(emit_kernel<false>, grid, dim3(128), smem_l, st, chained, p);
     if (launches) ++*launches;
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace rmcv
+RMCV_GSTAMP_GETTER(rmcv_debug_ns_emit, rmcv::g_ns_emit)

@@ -28,6 +28,15 @@ namespace rmcv {
 
 namespace cg = cooperative_groups;
 
+// Phase stamps for latency anatomy (scripts/phase_stamps.py builds a -DRMCV_STAMPS copy of the library; the product has none).
+#ifdef RMCV_STAMPS
+__device__ long long g_stamps[4][32];
+#define STAMP(k, i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_stamps[k][i] = clock64(); } while (0)
+#else
+#define STAMP(k, i) do { } while (0)
+#endif
+RMCV_GSTAMP_ARRAY(g_ns_frame)
+
 // A frame is labelled by ONE CTA (CS == 1) or, when a chunk holds fewer frames than the GPU has SMs (4096x3072 stress
 // frames, batch-1 latency), by a thread-block CLUSTER of CS CTAs: the per-frame phases are bound by memory latency, so
 // CS times the threads mean CS times the loads in flight.  The cluster works on the frame's global arrays; what a single
@@ -157,13 +166,34 @@ __device__ __forceinline__ int upper_bound_xs(const uint32_t* run_x, int lo, int
 }
 
 // Collapses a forest of links (every node points at an ancestor or at itself) until every node points at its root.
-// Block-wide; reads may see values written in the same round, which are ancestors too.
+// Reads may see values written concurrently, which are ancestors too, and a root never changes, so a single CTA needs no
+// barrier between rounds: every thread jumps its own nodes until their parent is a root (log2(depth) steps while the other
+// threads make the same progress).  A cluster keeps the lock-step rounds (its members see each other through L2).
 template <class TeamT>
-__device__ __forceinline__ void pointer_jump(int32_t* link, int first, int end, int tid, int NT, TeamT& team, int* flags3) {
+__device__ __forceinline__ void pointer_jump(int32_t* link, int first, int end, int tid, int NT, TeamT& team, int* flags3, bool lockstep) {
     volatile int32_t* v = link;
+    if (!lockstep) {
+        for (int r0 = first + tid; r0 < end; r0 += 4 * NT) {   // four independent chains per iteration (latency-bound)
+            int l[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int r = r0 + u * NT; l[u] = r < end ? v[r] : -1; }
+            bool busy = true;
+            while (busy) {
+                busy = false;
+                int ll[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ll[u] = l[u] >= 0 ? v[l[u]] : -1;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (ll[u] != l[u]) { l[u] = ll[u]; v[r0 + u * NT] = ll[u]; busy = true; }
+            }
+        }
+        team.sync();
+        return;
+    }
     while (true) {
         int changed = 0;
-        for (int r0 = first + tid; r0 < end; r0 += 4 * NT) {   // four independent chains per iteration (latency-bound)
+        for (int r0 = first + tid; r0 < end; r0 += 4 * NT) {
             int l[4], ll[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) { const int r = r0 + u * NT; l[u] = r < end ? v[r] : -1; }
@@ -203,18 +233,21 @@ __host__ __device__ inline size_t label_smem_bytes(int H, int Rs, int C) {
     b += ((size_t)Rs + 2) * sizeof(int32_t);       // glink
     b += (size_t)Rs * sizeof(uint16_t);            // run_y
     b += (size_t)Rs * sizeof(int16_t);             // cid
+    b = (b + 3) & ~(size_t)3;
+    b += (size_t)C * sizeof(int32_t);              // Euler term of every component (single-CTA frames)
     return b + 64;
 }
 
 // NTMAX / MINB: 256 threads, four CTAs per SM for ordinary frames (the runs fit in shared memory); 1024 threads, one CTA per
 // SM for frames whose run arrays stay in global memory (4096x3072 stress frames), where the phases are bound by L2 latency
 // and more threads per frame mean more loads in flight.
-template <int NTMAX, int MINB, int CS>
-__global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
+template <int CS>
+__device__ __forceinline__ void label_body(const LabelParams& p, uint8_t* smem) {
     __shared__ int sh_scan[33];
     __shared__ int s_ncomp_, s_nadj_, s_flags_, s_hb_[4], s_or_[3];
     Team<CS> team;
+    STAMP(0, 0);
+    RMCV_GSTAMP_BEGIN(g_ns_frame, 0);
     // shared scalars of the frame: rank 0's copies (CS == 1: this CTA's)
     int& s_ncomp = *team.on0(&s_ncomp_); int& s_nadj = *team.on0(&s_nadj_); int& s_flags = *team.on0(&s_flags_);
     int* s_hb = team.on0(s_hb_);
@@ -225,6 +258,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
     const int tid = team.rank * LNT + ltid, NT = LNT * CS, lane = ltid & 31;   // within the frame's team
     const SlotBuffers& sb = p.sb;
     FrameCounters& fc = sb.counters[frame];
+    chain_begin();
 
     uint8_t* q = smem;
     ushort2* s_rows16 = reinterpret_cast<ushort2*>(q); q += ((size_t)H * sizeof(ushort2) + 15) & ~(size_t)15;
@@ -236,8 +270,10 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
     q += label_link_bytes(Rs, C);
     int32_t* s_glink = reinterpret_cast<int32_t*>(q); q += ((size_t)Rs + 2) * sizeof(int32_t);
     uint16_t* s_run_y = reinterpret_cast<uint16_t*>(q); q += (size_t)Rs * sizeof(uint16_t);
-    int16_t* s_cid = reinterpret_cast<int16_t*>(q);
+    int16_t* s_cid = reinterpret_cast<int16_t*>(q); q += (size_t)Rs * sizeof(int16_t);
+    int32_t* s_euler = reinterpret_cast<int32_t*>(smem + (((size_t)(q - smem) + 3) & ~(size_t)3));
 
+    chain_wait();
     const int raw_runs = fc.n_runs;
     const int n_runs = min(raw_runs, R);
     const bool in_smem = CS == 1 && n_runs <= Rs;   // a team works on the global arrays
@@ -248,7 +284,10 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
     int16_t* g_cid = sb.run_cid + (size_t)frame * R;
     int2* g_rows = sb.rows + (size_t)frame * H;
     int32_t* g_comp_root = sb.comp_root + (size_t)frame * C;
-    int32_t* g_comp_cnt = sb.comp_cnt + (size_t)frame * C;     // runs per component, then (1 - runs + contacts) > 0
+    int32_t* g_comp_cnt = sb.comp_cnt + (size_t)frame * C;     // out: bit 0 = has holes of its own, bit 1 = lies in a hole
+    // Euler term 1 - runs + contacts of every component (> 0: it has holes): shared-memory atomics for a single CTA, the
+    // global array for a cluster
+    int32_t* ecnt = CS == 1 ? s_euler : g_comp_cnt;
 
     Runs f;
     f.rows = nullptr;
@@ -284,6 +323,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
         f.cid[r] = 0;
     }
     team.sync();
+    STAMP(0, 1);
     // ---- foreground links (8-connectivity): the first run of row y-1 overlapping [xs-1, xe+1] becomes the parent;
     // every further touched run is flagged "joined with the run before it" (they are consecutive in their row)
     {
@@ -310,17 +350,20 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
         if (adj) atomicAdd(&s_nadj, adj);
     }
     team.sync();
-    pointer_jump(f.link, 0, n_runs, tid, NT, team, s_or_);
+    STAMP(0, 2);
+    pointer_jump(f.link, 0, n_runs, tid, NT, team, s_or_, CS > 1);
+    STAMP(0, 3);
     for (int r = tid; r < n_runs; r += NT)
         if (f.cid[r]) uf_union(f.link, r, r - 1);
     team.sync();
+    STAMP(0, 4);
     // ---- flatten, enumerate components
     for (int r = tid; r < n_runs; r += NT) {
         const int root = uf_find(f.link, r);
         if (root == r) {
             const int c = atomicAdd(&s_ncomp, 1);
             if (c < C) {
-                g_comp_root[c] = r; g_comp_cnt[c] = 1;   // the Euler term 1 - runs + contacts, accumulated below
+                g_comp_root[c] = r; ecnt[c] = 1;   // the Euler term 1 - runs + contacts, accumulated below
                 f.cid[r] = (int16_t)c;
             } else {
                 f.cid[r] = -1;
@@ -331,6 +374,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
         }
     }
     team.sync();
+    STAMP(0, 5);
     const int n_comps = min(s_ncomp, C);
     const int n_holes = s_ncomp - n_runs + s_nadj;  // Euler relation on the run graph
     const bool has_holes = n_holes > 0;
@@ -346,26 +390,39 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
         }
         const unsigned peers = __match_any_sync(0xffffffffu, c);
         adj = __reduce_add_sync(peers, adj);
-        if (c >= 0 && lane == __ffs(peers) - 1) atomicAdd(&g_comp_cnt[c], adj);
+        if (c >= 0 && lane == __ffs(peers) - 1) atomicAdd(&ecnt[c], adj);
     }
     team.sync();
+    STAMP(0, 6);
     // ---- background gaps (4-connectivity), only when the frame has a hole
     if (has_holes) {
         // A hole lies strictly inside the bounding box of the component that encloses it, so a gap that is not strictly
         // inside the union of the bounding boxes of the components with holes is outer background without any search.
         if (tid == 0) { s_hb[0] = INT32_MAX; s_hb[1] = INT32_MAX; s_hb[2] = -1; s_hb[3] = -1; f.glink[0] = 0; }
         for (int i = tid; i < (2 * (n_runs + 2) + 3) / 4; i += NT) reinterpret_cast<uint32_t*>(f.jp)[i] = 0u;
-        for (int c = ltid; c < n_comps; c += LNT) s_hole[c] = g_comp_cnt[c];   // every CTA of the team keeps its own copy
+        for (int c = ltid; c < n_comps; c += LNT) s_hole[c] = ecnt[c];   // every CTA of the team keeps its own copy
         team.sync();
-        for (int r = tid; r < n_runs; r += NT) {
-            const int c = f.cid[r];
-            if (c >= 0 && s_hole[c] > 0) {
-                const uint32_t rx = f.run_x[r];
-                atomicMin(&s_hb[0], (int)(rx & 0xffffu)); atomicMax(&s_hb[2], (int)(rx >> 16));
-                atomicMin(&s_hb[1], (int)f.run_y[r]); atomicMax(&s_hb[3], (int)f.run_y[r]);
+        STAMP(0, 12);
+        {
+            int bx0 = INT32_MAX, by0 = INT32_MAX, bx1 = -1, by1 = -1;
+            for (int r = tid; r < n_runs; r += NT) {
+                const int c = f.cid[r];
+                if (c >= 0 && s_hole[c] > 0) {
+                    const uint32_t rx = f.run_x[r];
+                    const int y = (int)f.run_y[r];
+                    bx0 = min(bx0, (int)(rx & 0xffffu)); bx1 = max(bx1, (int)(rx >> 16));
+                    by0 = min(by0, y); by1 = max(by1, y);
+                }
+            }
+            bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
+            bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
+            if (lane == 0 && bx1 >= 0) {
+                atomicMin(&s_hb[0], bx0); atomicMax(&s_hb[2], bx1);
+                atomicMin(&s_hb[1], by0); atomicMax(&s_hb[3], by1);
             }
         }
         team.sync();
+        STAMP(0, 13);
         const int hx0 = s_hb[0], hy0 = s_hb[1], hx1 = s_hb[2], hy1 = s_hb[3];
         for (int r = tid; r < n_runs; r += NT) {
             const int y = f.run_y[r];
@@ -428,12 +485,15 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
             f.glink[r + 1] = outer ? 0 : (first >= 0 ? first : r + 1);
         }
         team.sync();
-        pointer_jump(f.glink, 1, n_runs + 1, tid, NT, team, s_or_);
+        STAMP(0, 14);
+        pointer_jump(f.glink, 1, n_runs + 1, tid, NT, team, s_or_, CS > 1);
+        STAMP(0, 15);
         for (int gnode = 1 + tid; gnode <= n_runs; gnode += NT) {
             if (f.jp[gnode]) uf_union(f.glink, gnode, gnode - 1);
             if (f.jo[gnode]) uf_union(f.glink, gnode, 0);
         }
         team.sync();
+        STAMP(0, 16);
         for (int gnode = tid; gnode <= n_runs; gnode += NT) {
             const int root = gnode == 0 ? 0 : uf_find(f.glink, gnode);
             f.glink[gnode] = root;
@@ -441,7 +501,25 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
         }
     }
     team.sync();
-    for (int c = tid; c < n_comps; c += NT) { g_comp_cnt[c] = g_comp_cnt[c] > 0; s_cnt[c] = 0; }  // has holes of its own
+    STAMP(0, 7);
+    // A component without holes faces ONE background region: outer, or a hole of another component (nested: RETR_EXTERNAL
+    // drops it).  The pixel above the first pixel of its root run is background of that region (a root run touches no run
+    // above), so one gap look-up decides; the contour kernel reads the verdict.
+    for (int c = tid; c < n_comps; c += NT) {
+        const int own = ecnt[c] > 0;
+        int nested = 0;
+        if (has_holes && !own) {
+            const int root = g_comp_root[c];
+            const int x = (int)(f.run_x[root] & 0xffffu), yy = (int)f.run_y[root] - 1;
+            if (x > 0 && yy > 0 && x < W - 1 && yy < H - 1) {
+                const int2 rr = row(yy);
+                const int k = upper_bound_xs(f.run_x, rr.x, rr.y, x);   // the gap between run k-1 and run k
+                if (k != rr.x && k != rr.y) nested = f.glink[k + 1] != 0;
+            }
+        }
+        g_comp_cnt[c] = own | (nested << 1);
+        s_cnt[c] = 0;
+    }
     // ---- boundary-pixel records -> components (through the run each record is tagged with): the records are counted
     // per component, start = exclusive scan of the counts, and a warp-aggregated scatter writes them
     // bucketed by component (so that the contour kernel streams each component's records linearly).
@@ -452,6 +530,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
     int32_t* g_start = sb.comp_start + (size_t)frame * (C + 1);
     if (tid == 0 && raw_recs > g.PC) s_flags |= RMCV_FRAME_OVERFLOW_POINTS;
     team.sync();
+    STAMP(0, 8);
     auto comp_of = [&](const uint2 rec) -> int {  // the emit kernel tagged the record with its run
         const int r = (int)(rec.y >> 8);
         return r < n_runs ? (int)f.cid[r] : -1;
@@ -468,6 +547,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
         }
     }
     team.sync();
+    STAMP(0, 9);
     if (team.rank == 0) {   // block-wide scan by the first CTA of the team
         int carry = 0;
         for (int c0 = 0; c0 < n_comps; c0 += LNT) {
@@ -481,6 +561,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
         if (ltid == 0) g_start[n_comps] = carry;
     }
     team.sync();
+    STAMP(0, 10);
     for (int i0 = 0; i0 < n_recs; i0 += 4 * NT) {
         uint2 rec[4];
 #pragma unroll
@@ -498,6 +579,17 @@ __global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p)
     }
     if (tid == 0) { fc.n_comps = n_comps; fc.n_holes = n_holes; fc.flags = s_flags; }
     if (CS > 1) team.sync();   // rank 0's shared memory is read by the whole team until here
+#ifdef RMCV_STAMPS
+    __syncthreads();
+    STAMP(0, 11);
+    RMCV_GSTAMP_END(g_ns_frame, 0);
+#endif
+}
+
+template <int NTMAX, int MINB, int CS>
+__global__ void __launch_bounds__(NTMAX, MINB) label_kernel(const LabelParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    label_body<CS>(p, smem);
 }
 
 // ------------------------------------------------------------------------------------------ K_C: contour sums
@@ -513,13 +605,6 @@ struct ContourParams {
 struct GRuns {  // read-only view of one frame's runs and gap labels in global memory
     const int2* rows; const uint32_t* run_x; const int32_t* glink; int W, H;
 };
-__device__ __forceinline__ int g_lower_bound_xe(const uint32_t* run_x, int lo, int hi, int x) {
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if ((int)(__ldg(run_x + mid) >> 16) < x) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
 __device__ __forceinline__ bool g_is_hole(const GRuns& f, int x, int yy) {
     if (x <= 0 || yy <= 0 || x >= f.W - 1 || yy >= f.H - 1) return false;
     const int2 rr = __ldg(f.rows + yy);
@@ -532,18 +617,20 @@ __device__ __forceinline__ bool g_is_hole(const GRuns& f, int x, int yy) {
     return __ldg(f.glink + lo + 1) != 0;
 }
 
-__global__ void __launch_bounds__(128) contour_kernel(const ContourParams p) {
+// c_first / c_stride: this warp's first component and the number of warps working on the frame
+__device__ __forceinline__ void contour_body(const Geometry& g, const SlotBuffers& sb, const rmcv_params& prm, int frame, int c_first, int c_stride) {
     __shared__ uint32_t s_lut[256];
-    const Geometry& g = p.g;
     const int W = g.W, H = g.H, R = g.R, C = g.C;
-    const int frame = blockIdx.x;
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
-    const SlotBuffers& sb = p.sb;
     const FrameCounters& fc = sb.counters[frame];
-    const int n_comps = fc.n_comps;
-    const bool has_holes = fc.n_holes > 0;
-    for (int i = tid; i < 256; i += NT) s_lut[i] = c_arc_lut[i];
+    chain_begin();
+    STAMP(1, 0);
+    RMCV_GSTAMP_BEGIN(g_ns_frame, 1);
+    for (int i = tid; i < 256; i += NT) s_lut[i] = c_arc_lut[i];   // (before the wait: overlaps the label kernel's tail)
     __syncthreads();
+    chain_wait();
+    const int n_comps = fc.n_comps;
+    STAMP(1, 1);
 
     GRuns f;
     f.rows = sb.rows + (size_t)frame * H;
@@ -558,17 +645,18 @@ __global__ void __launch_bounds__(128) contour_kernel(const ContourParams p) {
     // ---- per component (one warp each, claimed dynamically), lanes over its boundary pixels.  A pixel contributes one
     // contour point per arc of the 3x3 rule.
     CompAcc* accs = sb.acc + (size_t)frame * C;
-    const int warps_per_frame = gridDim.y * (NT >> 5);
-    for (int c = blockIdx.y * (NT >> 5) + (tid >> 5); c < n_comps; c += warps_per_frame) {
+    for (int c = c_first; c < n_comps; c += c_stride) {
         const int base = g_start[c], cnt = g_start[c + 1] - base;
         const int root = comp_root[c];
         const int ox = (int)(f.run_x[root] & 0xffffu), oy = (int)run_y[root];
         // A component without holes faces ONE background region: outer (all arcs count) or a hole of another component
         // (nested: RETR_EXTERNAL drops it).  The pixel above the first pixel of the root run is background of that region
         // (a root run touches no run above).  Only components with holes of their own test every arc.
-        const bool own_holes = comp_holes[c] != 0;
-        const bool nested = has_holes && !own_holes && g_is_hole(f, ox, oy - 1);
+        const int hole_flags = comp_holes[c];      // label kernel: bit 0 = holes of its own, bit 1 = lies in a hole
+        const bool own_holes = (hole_flags & 1) != 0;
+        const bool nested = (hole_flags & 2) != 0;
         const int ncnt = nested ? 0 : cnt;
+        STAMP(1, 2);
         // one record -> (multiplicity k, sum of the edge directions of its counted arcs)
         auto arcs_of = [&](uint32_t nb, int x, int y, int* dxs, int* dys) -> int {
             const uint32_t ent = s_lut[nb & 0xffu];
@@ -615,8 +703,9 @@ __global__ void __launch_bounds__(128) contour_kernel(const ContourParams p) {
         x1 = __reduce_max_sync(0xffffffffu, x1); y1 = __reduce_max_sync(0xffffffffu, y1);
         fk = __reduce_min_sync(0xffffffffu, fk);
         sx = warp_sum(sx); sy = warp_sum(sy); cross = warp_sum(cross);
+        STAMP(1, 3);
         long long s_int = 0;
-        const bool fitted = contour_is_fitted(n, cross, p.prm);  // warp-uniform
+        const bool fitted = contour_is_fitted(n, cross, prm);  // warp-uniform
         if (fitted) {
             m20 = warp_sum(m20); m11 = warp_sum(m11); m02 = warp_sum(m02);
             m30 = warp_sum(m30); m21 = warp_sum(m21); m12 = warp_sum(m12); m03 = warp_sum(m03);
@@ -631,6 +720,7 @@ __global__ void __launch_bounds__(128) contour_kernel(const ContourParams p) {
             }
             s_int = warp_sum(s_int);
         }
+        STAMP(1, 4);
         if (lane == 0) {
             CompAcc a;
             a.n = n; a.sx = sx; a.sy = sy; a.cross = cross;
@@ -642,7 +732,14 @@ __global__ void __launch_bounds__(128) contour_kernel(const ContourParams p) {
             a.firstkey = fk; a.fitted = fitted ? 1 : 0;
             accs[c] = a;
         }
+        STAMP(1, 5);
     }
+    RMCV_GSTAMP_END(g_ns_frame, 1);
+}
+
+__global__ void __launch_bounds__(128) contour_kernel(const ContourParams p) {
+    const int wpc = blockDim.x >> 5;
+    contour_body(p.g, p.sb, p.prm, blockIdx.x, blockIdx.y * wpc + (threadIdx.x >> 5), gridDim.y * wpc);
 }
 
 // ------------------------------------------------------------------------------------------ K_F: fits
@@ -654,16 +751,20 @@ struct FitParams {
     rmcv_params prm;
 };
 
-__global__ void __launch_bounds__(64) fit_kernel(const FitParams p) {
-    const int frame = blockIdx.y;
-    const int C = p.g.C;
-    const int n_comps = p.sb.counters[frame].n_comps;
+__device__ __forceinline__ void fit_body(const Geometry& g, const SlotBuffers& sb, const rmcv_params& prm, int frame, int c_first, int c_stride) {
+    const int C = g.C;
+    STAMP(2, 0);
+    RMCV_GSTAMP_BEGIN(g_ns_frame, 2);
+    chain_begin();
+    chain_wait();
+    const int n_comps = sb.counters[frame].n_comps;
     // a frame has ~36 components: two CTAs of 64 threads per frame cover it in one round (a grid over the capacity C would
     // launch C/64 CTAs per frame that find nothing to do)
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_comps; c += gridDim.x * blockDim.x) {
-        const CompAcc& a = p.sb.acc[(size_t)frame * C + c];
+    for (int c = c_first; c < n_comps; c += c_stride) {
+        const CompAcc& a = sb.acc[(size_t)frame * C + c];
         CompRec rec;
         const int n = (int)a.n;
+        STAMP(2, 1);
         rec.firstkey = n > 0 ? a.firstkey : -1;
         rec.n_points = n;
         rec.area2 = a.cross < 0 ? -a.cross : a.cross;
@@ -679,16 +780,23 @@ __global__ void __launch_bounds__(64) fit_kernel(const FitParams p) {
             cs.xx = a.xx; cs.xy = a.xy; cs.yy = a.yy; cs.xxx = a.xxx; cs.xxy = a.xxy; cs.xyy = a.xyy; cs.yyy = a.yyy;
             cs.xxxx = a.xxxx; cs.xxxy = a.xxxy; cs.xxyy = a.xxyy; cs.xyyy = a.xyyy; cs.yyyy = a.yyyy;
             cs.s_int = a.s_int; cs.ox = a.ox; cs.oy = a.oy;
-            fit_contour(cs, p.prm, &rec.status, &rec.fit_branch, &rec.det0, &rec.ellipse, &rec.blob);
+            fit_contour(cs, prm, &rec.status, &rec.fit_branch, &rec.det0, &rec.ellipse, &rec.blob);
             // the 4th-order sums are exact 64-bit integers about the component's root pixel: n * extent^4 must stay below 2^62
             // (never reached with the reference's area_max = 99999; a caller who raises it gets the frame flagged, not a wrong fit)
             if (a.fitted) {
                 const double ext = (double)max(a.bbox[2] - a.bbox[0], a.bbox[3] - a.bbox[1]) + 1.0;
-                if ((double)a.n * ext * ext * ext * ext > 4.6e18) atomicOr(&p.sb.counters[frame].flags, RMCV_FRAME_OVERFLOW_MOMENTS);
+                if ((double)a.n * ext * ext * ext * ext > 4.6e18) atomicOr(&sb.counters[frame].flags, RMCV_FRAME_OVERFLOW_MOMENTS);
             }
         }
-        p.sb.comps[(size_t)frame * C + c] = rec;
+        STAMP(2, 2);
+        sb.comps[(size_t)frame * C + c] = rec;
+        STAMP(2, 3);
     }
+    RMCV_GSTAMP_END(g_ns_frame, 2);
+}
+
+__global__ void __launch_bounds__(64) fit_kernel(const FitParams p) {
+    fit_body(p.g, p.sb, p.prm, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 // ------------------------------------------------------------------------------------------ K_O: order, pairs, output
@@ -712,12 +820,13 @@ struct OrderParams {
 // NTMAX: 128 threads for ordinary frames; 512 for frames with large capacities (stress frames: hundreds of blobs, ~125k
 // pairs, ~130 KB of records to post over PCIe per frame from a handful of CTAs).  CS > 1: a cluster of CS CTAs per frame
 // (Team, above) shares the O(n^2) ordering and the O(P^2) pair loops when the chunk leaves most SMs idle.
-template <int NTMAX, int CS>
-__global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
+template <int CS>
+__device__ __forceinline__ void order_body(const OrderParams& p, uint8_t* smem) {
     __shared__ int sh_scan[33];
     __shared__ int s_np_, s_nc_, s_nn_, s_flags_, s_total_, s_off_[3];
     Team<CS> team;
+    STAMP(3, 0);
+    RMCV_GSTAMP_BEGIN(g_ns_frame, 3);
     int& s_np = *team.on0(&s_np_); int& s_nc = *team.on0(&s_nc_); int& s_nn = *team.on0(&s_nn_);
     int& s_flags = *team.on0(&s_flags_); int& s_total = *team.on0(&s_total_);
     int* s_off = team.on0(s_off_);
@@ -728,6 +837,8 @@ __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
     const int tid = team.rank * LNT + ltid, NT = LNT * CS;        // within the frame's team
     const SlotBuffers& sb = p.sb;
     FrameCounters& fc = sb.counters[frame];
+    chain_begin();
+    chain_wait();
     const int n_comps = fc.n_comps;
     int32_t* s_keys = reinterpret_cast<int32_t*>(smem);          // every CTA of a team keeps its own copy
     int32_t* s_status = s_keys + C;
@@ -735,6 +846,7 @@ __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
     if (tid == 0) { s_np = 0; s_nc = 0; s_nn = 0; s_total = 0; s_flags = fc.flags; }
     for (int c = ltid; c < n_comps; c += LNT) { s_keys[c] = comps[c].firstkey; s_status[c] = comps[c].status; }
     team.sync();
+    STAMP(3, 1);
     // ---- order: rank = number of external components with a larger first-pixel key (reverse raster order)
     rmcv_contour_info* oc = sb.s_contours + (size_t)frame * C;
     rmcv_lightblob* ob = sb.s_blobs + (size_t)frame * C;
@@ -771,6 +883,7 @@ __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
         if (nn) atomicAdd(&s_nn, nn);
     }
     team.sync();
+    STAMP(3, 2);
     // ---- pairs in lexicographic (i,j) order (src/objdetect.cpp:122-163)
     const int P = s_np;
     const rmcv_lightblob* sblob = ob;            // ordinary frames: ~25 positives, read in place (L1/L2)
@@ -882,6 +995,7 @@ __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
         }
     }
     const int n_arm = min(s_total, A);
+    STAMP(3, 3);
     // ---- claim dense space in the chunk's region of the pinned result arrays, write out
     if (tid == 0) {
         FrameCounters& al = sb.counters[p.frames];
@@ -892,6 +1006,7 @@ __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
         fc.n_contours = s_nc; fc.n_positive = P; fc.n_negative = s_nn; fc.n_armours = n_arm;
     }
     team.sync();
+    STAMP(3, 4);
     const int nc_all = s_nc;
     const size_t base_c = (size_t)p.frame_base * C + s_off[0];
     const size_t base_b = (size_t)p.frame_base * C + s_off[1];
@@ -912,6 +1027,17 @@ __global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
         copy_words(p.o_armours + base_a, oa, (size_t)n_arm * sizeof(rmcv_armour), tid, NT);
     }
     if (CS > 1) team.sync();   // rank 0's shared memory is read by the whole team until here
+#ifdef RMCV_STAMPS
+    __syncthreads();
+    STAMP(3, 5);
+    RMCV_GSTAMP_END(g_ns_frame, 3);
+#endif
+}
+
+template <int NTMAX, int CS>
+__global__ void __launch_bounds__(NTMAX) order_kernel(const OrderParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    order_body<CS>(p, smem);
 }
 
 // Dense write-out of a large frame's records into the pinned result arrays, kWriteSplit CTAs per frame: with a handful of
@@ -922,6 +1048,7 @@ __global__ void __launch_bounds__(256) writeout_kernel(const OrderParams p) {
     const SlotBuffers& sb = p.sb;
     const FrameCounters& fc = sb.counters[frame];
     const int C = p.g.C, A = p.g.A;
+    chain_wait();
     auto slice = [&](uint8_t* dst, const uint8_t* src, size_t records, size_t rec_bytes) {
         const size_t per = (records + kWriteSplit - 1) / kWriteSplit;
         const size_t r0 = (size_t)part * per, r1 = r0 + per < records ? r0 + per : records;
@@ -973,14 +1100,15 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
     cudaError_t e;
     auto done = [&](int stage) { if (stage_done) stage_done(stage_arg, stage, st); };
     const Tuning& tune = tuning();
-    const int small_batch = tune.small_batch >= 0 ? tune.small_batch : 16;   // at most this many frames: per-frame kernels take their wide variants
+    const int small_batch = small_batch_limit();   // at most this many frames: per-frame kernels take their wide variants
+    const bool chained = L.chained != 0;
     if (!L.emit_done) {   // K_E (unless the pixel kernel emitted the runs / records itself)
         EmitLaunch el;
         el.bits = L.sb->bits; el.W = L.g.W; el.H = L.g.H; el.batch = L.frames;
         el.rows = L.sb->rows; el.run_x = L.sb->run_x; el.run_y = L.sb->run_y; el.counters = L.sb->counters; el.R = L.g.R;
         el.recs = L.sb->recs; el.PC = L.g.PC;
         if (L.flags_bh > 0) { el.band_flags = L.sb->band_flags; el.flag_bh = L.flags_bh; el.flag_bands = (L.g.H + L.flags_bh - 1) / L.flags_bh; }
-        e = launch_emit(el, st, launches);
+        e = launch_emit(el, st, launches, chained);
         if (e != cudaSuccess) return e;
         done(RMCV_STAGE_EMIT);
     } else {
@@ -1017,11 +1145,13 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         } else if (big) {
             e = cudaFuncSetAttribute(label_kernel<1024, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            label_kernel<1024, 1, 1><<<L.frames, 1024, smem, st>>>(p);
+            e = launch_chained<LabelParams>(label_kernel<1024, 1, 1>, dim3(L.frames), dim3(1024), smem, st, chained, p);
+            if (e != cudaSuccess) return e;
         } else {
             e = cudaFuncSetAttribute(label_kernel<256, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            label_kernel<256, 4, 1><<<L.frames, 256, smem, st>>>(p);
+            e = launch_chained<LabelParams>(label_kernel<256, 4, 1>, dim3(L.frames), dim3(256), smem, st, chained, p);
+            if (e != cudaSuccess) return e;
         }
         if (launches) ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -1032,13 +1162,14 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         p.g = L.g; p.sb = *L.sb; p.prm = prm;
         // CTAs of four warps per frame: eight for small chunks (a warp per component and round: latency), two for large ones
         // (1024 frames: 2048 fat CTAs instead of 8192 thin ones, 1.188 -> 1.175 ms per step; gpu_exp_t.sh)
-        int gy = tune.contour_gy > 0 ? tune.contour_gy : (L.frames >= 512 ? 1 : L.frames >= 128 ? 2 : 8);
+        // (a handful of frames: sixteen, so that every component of an ordinary frame has a warp in the first round)
+        int gy = tune.contour_gy > 0 ? tune.contour_gy : (L.frames >= 512 ? 1 : L.frames >= 128 ? 2 : L.frames <= 4 ? 16 : 8);
         if (gy * 4 > L.g.C) gy = (L.g.C + 3) / 4;
         if (gy < 1) gy = 1;
         dim3 grid(L.frames, gy);
         const size_t pad = tune.chain_pad > 0 ? (size_t)tune.chain_pad : 0;
         if (pad > 48 * 1024) cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
-        contour_kernel<<<grid, 128, pad, st>>>(p);
+        if ((e = launch_chained<ContourParams>(contour_kernel, grid, dim3(128), pad, st, chained, p)) != cudaSuccess) return e;
         if (launches) ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         done(RMCV_STAGE_CONTOUR);
@@ -1051,7 +1182,7 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         dim3 grid(L.g.C > 512 ? gx_full : (gx_full < 2 ? gx_full : 2), L.frames);
         const size_t pad = tune.chain_pad > 0 ? (size_t)tune.chain_pad : 0;
         if (pad > 48 * 1024) cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
-        fit_kernel<<<grid, 64, pad, st>>>(p);
+        if ((e = launch_chained<FitParams>(fit_kernel, grid, dim3(64), pad, st, chained, p)) != cudaSuccess) return e;
         if (launches) ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         done(RMCV_STAGE_FIT);
@@ -1087,8 +1218,11 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
             e = launch_team<OrderParams>(cs == 8 ? order_kernel<512, 8> : cs == 4 ? order_kernel<512, 4> : order_kernel<512, 2>, cs, L.frames, 512,
                                          smem, so, p);
             if (e != cudaSuccess) return e;
-        } else if (big) order_kernel<512, 1><<<L.frames, 512, smem, so>>>(p);
-        else order_kernel<128, 1><<<L.frames, 128, smem, so>>>(p);
+        } else if (big) {
+            if ((e = launch_chained<OrderParams>(order_kernel<512, 1>, dim3(L.frames), dim3(512), smem, so, chained && so == st, p)) != cudaSuccess) return e;
+        } else {
+            if ((e = launch_chained<OrderParams>(order_kernel<128, 1>, dim3(L.frames), dim3(128), smem, so, chained && so == st, p)) != cudaSuccess) return e;
+        }
         if (p.defer_copy == 1) {
             if (launches) ++*launches;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -1103,6 +1237,15 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
     }
     return cudaSuccess;
 }
+
+#ifdef RMCV_STAMPS
+}  // namespace rmcv
+extern "C" int rmcv_debug_stamps(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, rmcv::g_stamps, sizeof(rmcv::g_stamps));
+}
+RMCV_GSTAMP_GETTER(rmcv_debug_ns_frame, rmcv::g_ns_frame)
+namespace rmcv {
+#endif
 
 // ------------------------------------------------------------------------------------------ standalone a2 / a3
 // rm::filter_lightblobs on caller-supplied ordered contours: one warp per contour.

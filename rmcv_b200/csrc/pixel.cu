@@ -395,10 +395,13 @@ __device__ __forceinline__ void close_store_emit(const PixelParams& p, uint32_t*
 }
 
 // ------------------------------------------------------------------------------------------ BGR kernel
+RMCV_GSTAMP_ARRAY(g_ns_pixel)
 template <bool kBulk, class G = GeomRuntime, bool kEmit = false>
 __global__ void __launch_bounds__(512) pixel_bgr_kernel(const PixelParams p) {
     static_assert(!kEmit || G::kW > 0, "the fused emission needs the fixed geometry");
     extern __shared__ __align__(128) uint8_t smem[];
+    RMCV_GSTAMP_BEGIN(g_ns_pixel, 0);
+    chain_begin();   // a chained emit kernel (small chunks) may become resident now; it waits for this grid to complete
     constexpr bool kFixed = G::kW > 0;
     const int tid = threadIdx.x, NT = kFixed ? G::kNT : (int)blockDim.x;
     const int frame = blockIdx.x / p.bands, band = blockIdx.x - frame * p.bands;
@@ -489,6 +492,7 @@ __global__ void __launch_bounds__(512) pixel_bgr_kernel(const PixelParams p) {
     }
     if constexpr (kEmit) close_store_emit<G>(p, t, d, smem, frame, y0, nout, tid);
     else close_and_store<G>(p, t, d, frame, y0, nout, tid, NT);
+    RMCV_GSTAMP_END(g_ns_pixel, 0);
 }
 
 // ------------------------------------------------------------------------------------------ Bayer kernel
@@ -892,3 +896,4 @@ cudaError_t launch_pixel_stage(const PixelLaunch& L, int sm_count, cudaStream_t 
 }
 
 }  // namespace rmcv
+RMCV_GSTAMP_GETTER(rmcv_debug_ns_pixel, rmcv::g_ns_pixel)

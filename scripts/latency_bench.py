@@ -14,11 +14,12 @@ for f in frames:
 d_mask = ctx.device_buffer(H * W)
 p = rb.default_params()
 lat = []
-for i in range(3000):
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
+for i in range(N):
     t0 = time.perf_counter()
     ctx.detect_batch(bufs[i % 16].ptr, W, H, 1, p, d_mask.ptr)
     ctx.fetch_results()
-    if i >= 500:
+    if i >= N // 6:
         lat.append(1e6 * (time.perf_counter() - t0))
 lat.sort()
 ctx.profile(True); ctx.profile_read(reset=True)
