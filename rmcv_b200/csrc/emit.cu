@@ -130,7 +130,8 @@ cudaError_t launch_emit(const EmitLaunch& L, cudaStream_t st, int64_t* launches,
     // band height: (BH + 2) * WB <= 4096 words keeps the per-warp nibble register within eight rounds and the word
     // indices within 16 bits; taller bands amortise the scan / claim / row-table steps
     const int bh_max = 4096 / p.WB - 2;
-    int BH = 32;
+    // (chunks of a few frames: 8-row bands - four times the CTAs, each with a quarter of the scan / claim / write chain)
+    int BH = L.batch <= small_batch_limit() ? 8 : 32;
     if (tuning().emit_bh > 0) BH = tuning().emit_bh;
     if (BH > bh_max) BH = bh_max;
     if (BH < 1) BH = 1;

@@ -617,7 +617,39 @@ __device__ __forceinline__ bool g_is_hole(const GRuns& f, int x, int yy) {
     return __ldg(f.glink + lo + 1) != 0;
 }
 
+// One component's sums -> its record: cv::fitEllipseDirect incl. its fallback, the ratio/tilt gates and the rm::lightblob ctor
+// (reference: src/objdetect.cpp:62-84, src/core.cpp:9-19).  One thread.
+__device__ __forceinline__ void fit_component(const CompAcc& a, const rmcv_params& prm, int32_t* frame_flags, CompRec& rec) {
+    const int n = (int)a.n;
+    rec.firstkey = n > 0 ? a.firstkey : -1;
+    rec.n_points = n;
+    rec.area2 = a.cross < 0 ? -a.cross : a.cross;
+    rec.bbox[0] = a.bbox[0]; rec.bbox[1] = a.bbox[1]; rec.bbox[2] = a.bbox[2]; rec.bbox[3] = a.bbox[3];
+    rec.status = -1;
+    rec.fit_branch = RMCV_FIT_NONE;
+    rec.det0 = 0.f;
+    memset(&rec.blob, 0, sizeof(rec.blob));
+    memset(&rec.ellipse, 0, sizeof(rec.ellipse));
+    if (n > 0) {  // external component
+        ContourSums cs;
+        cs.n = a.n; cs.sx = a.sx; cs.sy = a.sy; cs.cross = a.cross;
+        cs.xx = a.xx; cs.xy = a.xy; cs.yy = a.yy; cs.xxx = a.xxx; cs.xxy = a.xxy; cs.xyy = a.xyy; cs.yyy = a.yyy;
+        cs.xxxx = a.xxxx; cs.xxxy = a.xxxy; cs.xxyy = a.xxyy; cs.xyyy = a.xyyy; cs.yyyy = a.yyyy;
+        cs.s_int = a.s_int; cs.ox = a.ox; cs.oy = a.oy;
+        fit_contour(cs, prm, &rec.status, &rec.fit_branch, &rec.det0, &rec.ellipse, &rec.blob);
+        // the 4th-order sums are exact 64-bit integers about the component's root pixel: n * extent^4 must stay below 2^62
+        // (never reached with the reference's area_max = 99999; a caller who raises it gets the frame flagged, not a wrong fit)
+        if (a.fitted) {
+            const double ext = (double)max(a.bbox[2] - a.bbox[0], a.bbox[3] - a.bbox[1]) + 1.0;
+            if ((double)a.n * ext * ext * ext * ext > 4.6e18) atomicOr(frame_flags, RMCV_FRAME_OVERFLOW_MOMENTS);
+        }
+    }
+}
+
 // c_first / c_stride: this warp's first component and the number of warps working on the frame
+// kFit: lane 0 goes straight on to the component's fit (chunks of a few frames: one kernel boundary less, and the fits of
+// the small components start while the long ones are still summing; the other lanes idle, so not for throughput)
+template <bool kFit>
 __device__ __forceinline__ void contour_body(const Geometry& g, const SlotBuffers& sb, const rmcv_params& prm, int frame, int c_first, int c_stride) {
     __shared__ uint32_t s_lut[256];
     const int W = g.W, H = g.H, R = g.R, C = g.C;
@@ -730,16 +762,23 @@ __device__ __forceinline__ void contour_body(const Geometry& g, const SlotBuffer
             a.ox = ox; a.oy = oy;
             a.bbox[0] = x0; a.bbox[1] = y0; a.bbox[2] = x1; a.bbox[3] = y1;
             a.firstkey = fk; a.fitted = fitted ? 1 : 0;
-            accs[c] = a;
+            if (kFit) {
+                CompRec rec;
+                fit_component(a, prm, &sb.counters[frame].flags, rec);
+                sb.comps[(size_t)frame * C + c] = rec;
+            } else {
+                accs[c] = a;
+            }
         }
         STAMP(1, 5);
     }
     RMCV_GSTAMP_END(g_ns_frame, 1);
 }
 
+template <bool kFit>
 __global__ void __launch_bounds__(128) contour_kernel(const ContourParams p) {
     const int wpc = blockDim.x >> 5;
-    contour_body(p.g, p.sb, p.prm, blockIdx.x, blockIdx.y * wpc + (threadIdx.x >> 5), gridDim.y * wpc);
+    contour_body<kFit>(p.g, p.sb, p.prm, blockIdx.x, blockIdx.y * wpc + (threadIdx.x >> 5), gridDim.y * wpc);
 }
 
 // ------------------------------------------------------------------------------------------ K_F: fits
@@ -763,31 +802,8 @@ __device__ __forceinline__ void fit_body(const Geometry& g, const SlotBuffers& s
     for (int c = c_first; c < n_comps; c += c_stride) {
         const CompAcc& a = sb.acc[(size_t)frame * C + c];
         CompRec rec;
-        const int n = (int)a.n;
         STAMP(2, 1);
-        rec.firstkey = n > 0 ? a.firstkey : -1;
-        rec.n_points = n;
-        rec.area2 = a.cross < 0 ? -a.cross : a.cross;
-        rec.bbox[0] = a.bbox[0]; rec.bbox[1] = a.bbox[1]; rec.bbox[2] = a.bbox[2]; rec.bbox[3] = a.bbox[3];
-        rec.status = -1;
-        rec.fit_branch = RMCV_FIT_NONE;
-        rec.det0 = 0.f;
-        memset(&rec.blob, 0, sizeof(rec.blob));
-        memset(&rec.ellipse, 0, sizeof(rec.ellipse));
-        if (n > 0) {  // external component
-            ContourSums cs;
-            cs.n = a.n; cs.sx = a.sx; cs.sy = a.sy; cs.cross = a.cross;
-            cs.xx = a.xx; cs.xy = a.xy; cs.yy = a.yy; cs.xxx = a.xxx; cs.xxy = a.xxy; cs.xyy = a.xyy; cs.yyy = a.yyy;
-            cs.xxxx = a.xxxx; cs.xxxy = a.xxxy; cs.xxyy = a.xxyy; cs.xyyy = a.xyyy; cs.yyyy = a.yyyy;
-            cs.s_int = a.s_int; cs.ox = a.ox; cs.oy = a.oy;
-            fit_contour(cs, prm, &rec.status, &rec.fit_branch, &rec.det0, &rec.ellipse, &rec.blob);
-            // the 4th-order sums are exact 64-bit integers about the component's root pixel: n * extent^4 must stay below 2^62
-            // (never reached with the reference's area_max = 99999; a caller who raises it gets the frame flagged, not a wrong fit)
-            if (a.fitted) {
-                const double ext = (double)max(a.bbox[2] - a.bbox[0], a.bbox[3] - a.bbox[1]) + 1.0;
-                if ((double)a.n * ext * ext * ext * ext > 4.6e18) atomicOr(&sb.counters[frame].flags, RMCV_FRAME_OVERFLOW_MOMENTS);
-            }
-        }
+        fit_component(a, prm, &sb.counters[frame].flags, rec);
         STAMP(2, 2);
         sb.comps[(size_t)frame * C + c] = rec;
         STAMP(2, 3);
@@ -1157,24 +1173,33 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         done(RMCV_STAGE_LABEL);
     }
+    // chunks of a few ordinary frames (latency mode): the fits ride on the contour kernel's warps
+    const int tiny = tune.fit_in_contour >= 0 ? tune.fit_in_contour : 4;   // frames; 0 = never
+    const bool fit_in_contour = L.frames <= tiny && L.g.C <= 512;
     {   // K_C
         ContourParams p;
         p.g = L.g; p.sb = *L.sb; p.prm = prm;
         // CTAs of four warps per frame: eight for small chunks (a warp per component and round: latency), two for large ones
         // (1024 frames: 2048 fat CTAs instead of 8192 thin ones, 1.188 -> 1.175 ms per step; gpu_exp_t.sh)
         // (a handful of frames: sixteen, so that every component of an ordinary frame has a warp in the first round)
-        int gy = tune.contour_gy > 0 ? tune.contour_gy : (L.frames >= 512 ? 1 : L.frames >= 128 ? 2 : L.frames <= 4 ? 16 : 8);
+        int gy = tune.contour_gy > 0 ? tune.contour_gy : (L.frames >= 512 ? 1 : L.frames >= 128 ? 2 : (L.frames <= 4 || fit_in_contour) ? 16 : 8);
         if (gy * 4 > L.g.C) gy = (L.g.C + 3) / 4;
         if (gy < 1) gy = 1;
         dim3 grid(L.frames, gy);
         const size_t pad = tune.chain_pad > 0 ? (size_t)tune.chain_pad : 0;
-        if (pad > 48 * 1024) cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
-        if ((e = launch_chained<ContourParams>(contour_kernel, grid, dim3(128), pad, st, chained, p)) != cudaSuccess) return e;
+        if (fit_in_contour) {
+            if ((e = launch_chained<ContourParams>(contour_kernel<true>, grid, dim3(128), 0, st, chained, p)) != cudaSuccess) return e;
+        } else {
+            if (pad > 48 * 1024) cudaFuncSetAttribute(contour_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+            if ((e = launch_chained<ContourParams>(contour_kernel<false>, grid, dim3(128), pad, st, chained, p)) != cudaSuccess) return e;
+        }
         if (launches) ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         done(RMCV_STAGE_CONTOUR);
     }
-    {   // K_F
+    if (fit_in_contour) {
+        done(RMCV_STAGE_FIT);
+    } else {   // K_F
         FitParams p;
         p.g = L.g; p.sb = *L.sb; p.prm = prm;
         // ordinary frames: two CTAs per frame; large capacities (stress frames, ~510 components): one per 64 components
