@@ -343,7 +343,7 @@ def run_gpu(args):
         strong = {"scaling": "strong", "frames_total": args.batch, "frames_per_gpu": nb, "value": s_units / (s_max * 1e-3), "unit": UNIT,
                   "ms_per_step": s_max / args.steps, "e2e": se_units / (se_max * 1e-3),
                   "note": "BASELINE config 3 as written: one batch of frames_total frames, contiguous slice per rank, device time max over ranks; "
-                          "a slice below one 592-frame chunk is one launch of each kernel per step; three calls in flight", "calls_in_flight": 3}
+                          "a slice is one launch of each kernel per step (a call is one chunk); three calls in flight", "calls_in_flight": 3}
 
     # ---- extras on rank 0: BASELINE config 5 (batch-1 latency) and config 2 (Bayer pixel stage)
     extras = None
