@@ -1174,7 +1174,7 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         done(RMCV_STAGE_LABEL);
     }
     // chunks of a few ordinary frames (latency mode): the fits ride on the contour kernel's warps
-    const int tiny = tune.fit_in_contour >= 0 ? tune.fit_in_contour : 4;   // frames; 0 = never
+    const int tiny = tune.fit_in_contour >= 0 ? tune.fit_in_contour : small_batch;   // frames; 0 = never
     const bool fit_in_contour = L.frames <= tiny && L.g.C <= 512;
     {   // K_C
         ContourParams p;
