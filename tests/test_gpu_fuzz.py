@@ -55,3 +55,13 @@ def test_fused_pixel_emit_kernel_opt_in():
     the check runs in its own interpreter): five launches per chunk and the same results, frame for frame."""
     out = run_script("fused_emit_parity_gpu.py", [])
     assert " 0 mismatches" in out
+
+
+def test_latency_mode_changes_no_result_bit():
+    """Small chunks run as a chain of programmatic dependent launches on the slot stream, with the fits on the contour kernel's
+    warps and 8-row emit bands.  The same batches with all of that switched off (tuning is read once per process,
+    hence two interpreters) must give the same digest over every record and mask byte."""
+    a = run_script("latency_mode_digest_gpu.py", [], tag="_default")
+    b = run_script("latency_mode_digest_gpu.py", [], env={"RMCV_CHAINED": "0", "RMCV_FIT_IN_CONTOUR": "0", "RMCV_EMIT_BH": "32"}, tag="_plain")
+    da, db = a.strip().splitlines()[-1], b.strip().splitlines()[-1]
+    assert "digest over" in da and da == db, (da, db)
