@@ -221,10 +221,10 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
     CtxExtra* ex = extra(ctx);
     // each slot has its own labelling stream: the labelling kernels of consecutive chunks are latency-bound and overlap
     // each other as well as the pixel kernels
-    // small chunks of ordinary frames (latency mode): all six kernels on the pixel stream, each a programmatic dependent of
-    // the one before (common.cuh: chain_begin / chain_wait) - no cross-stream hops, launch gaps hidden
+    // small chunks (latency mode; also the thread-block-cluster kernels of large frames): all kernels on one stream, each a
+    // programmatic dependent of the one before (common.cuh: chain_begin / chain_wait) - no cross-stream hops, launch gaps hidden
     // (the slot's own stream, so that consecutive small calls still overlap; a caller-supplied stream keeps everything)
-    const bool chained = full && frames <= small_batch_limit() && ctx->cap.R <= 65535 && tuning().chained != 0;
+    const bool chained = full && frames <= small_batch_limit() && tuning().chained != 0;
     cudaStream_t sl = ex->labs[&sb - ctx->slot];
     cudaStream_t sp = chained && ex->own_pix ? sl : ex->pix;
     if (chained) {

@@ -1064,6 +1064,7 @@ __global__ void __launch_bounds__(256) writeout_kernel(const OrderParams p) {
     const SlotBuffers& sb = p.sb;
     const FrameCounters& fc = sb.counters[frame];
     const int C = p.g.C, A = p.g.A;
+    chain_begin();
     chain_wait();
     auto slice = [&](uint8_t* dst, const uint8_t* src, size_t records, size_t rec_bytes) {
         const size_t per = (records + kWriteSplit - 1) / kWriteSplit;
@@ -1100,13 +1101,16 @@ static int pick_team(void (*k8)(Params), void (*k4)(Params), void (*k2)(Params),
     return 0;
 }
 template <class Params>
-static cudaError_t launch_team(void (*k)(Params), int cs, int frames, int threads, size_t smem, cudaStream_t st, const Params& p) {
+static cudaError_t launch_team(void (*k)(Params), int cs, int frames, int threads, size_t smem, cudaStream_t st, const Params& p,
+                               bool chained = false) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)frames * cs); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // a link of a small chunk's chain (common.cuh)
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = chained ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, k, p);
 }
 
@@ -1156,7 +1160,7 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         if (cs) {
             p.Rs = 0;
             e = launch_team<LabelParams>(cs == 8 ? label_kernel<1024, 1, 8> : cs == 4 ? label_kernel<1024, 1, 4> : label_kernel<1024, 1, 2>,
-                                         cs, L.frames, 1024, smem_team, st, p);
+                                         cs, L.frames, 1024, smem_team, st, p, chained);
             if (e != cudaSuccess) return e;
         } else if (big) {
             e = cudaFuncSetAttribute(label_kernel<1024, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1241,7 +1245,7 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         }
         if (cs) {
             e = launch_team<OrderParams>(cs == 8 ? order_kernel<512, 8> : cs == 4 ? order_kernel<512, 4> : order_kernel<512, 2>, cs, L.frames, 512,
-                                         smem, so, p);
+                                         smem, so, p, chained && so == st);
             if (e != cudaSuccess) return e;
         } else if (big) {
             if ((e = launch_chained<OrderParams>(order_kernel<512, 1>, dim3(L.frames), dim3(512), smem, so, chained && so == st, p)) != cudaSuccess) return e;
@@ -1251,7 +1255,7 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         if (p.defer_copy == 1) {
             if (launches) ++*launches;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
-            writeout_kernel<<<dim3(kWriteSplit, L.frames), 256, 0, so>>>(p);
+            if ((e = launch_chained<OrderParams>(writeout_kernel, dim3(kWriteSplit, L.frames), dim3(256), 0, so, chained && so == st, p)) != cudaSuccess) return e;
         }
         if (launches) ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
