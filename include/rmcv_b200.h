@@ -17,9 +17,18 @@
  * Threading: one rmcv_ctx per host thread and GPU.  All device work of a ctx is ordered on the
  * ctx's own streams (pixel kernels, labelling kernels, write-out and staging copies each have
  * one); entry points documented "async" return before the GPU has finished — call rmcv_sync()
- * (or a fetch/host entry point, which waits) before reading outputs.  Up to two detect calls may
- * be in flight: results are double-buffered and rmcv_fetch_results() returns the oldest
- * unfetched call, so call n+1 can be enqueued before call n is fetched.
+ * (or a fetch/host entry point, which waits) before reading outputs.  Up to three detect calls
+ * may be in flight: a ctx rotates four result sets and rmcv_fetch_results() returns the oldest
+ * unfetched call, so calls n+1 .. n+3 can be enqueued before call n is fetched.
+ *
+ * Ordering of a detect call against the pixel stream (rmcv_stream(), the "async, pixel stream"
+ * helpers): everything enqueued on that stream BEFORE the call is waited for by the call, and
+ * every helper of this library enqueued AFTER it runs after it.  A call of at most 16 frames
+ * runs on an internal stream of its own (so that consecutive small calls overlap), therefore
+ * (a) work the CALLER puts on rmcv_stream() after such a call is not ordered after it — fetch
+ * or rmcv_sync() first; (b) calls in flight at the same time must not share an output buffer
+ * (d_mask): which of them writes last is then unspecified.  With rmcv_config.stream set, all of
+ * a small call runs on that stream and neither caveat applies.
  *
  * There is no CPU fallback anywhere behind this ABI: without a CUDA device every entry point
  * that needs one returns RMCV_ERR_CUDA / RMCV_ERR_NO_DEVICE.

@@ -70,6 +70,8 @@ struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
     long long chunk_counter = 0;      // chunks enqueued over the life of the ctx
     int last_first_slot = 0;          // slot of chunk 0 of the last call
     cudaStream_t chain = nullptr;     // stream of the current call's chained chunk (small chunks), else null
+    cudaEvent_t ev_order = nullptr;   // "everything on the pixel stream so far", waited for by a chained chunk
+    bool slot_chained[kSlots] = {};   // the slot's last chunk ran chained on its own stream (its ev_lab marks the chain's end)
     bool own_pix = false;
     // where the write-out kernels of the current call put their records (pinned host arrays or the device mirrors)
     rmcv_frame_info* o_frames = nullptr; rmcv_contour_info* o_contours = nullptr; rmcv_lightblob* o_blobs = nullptr;
@@ -214,6 +216,19 @@ void prof_collect(rmcv_ctx* ctx) {  // after a sync
     cudaGetLastError();
 }
 
+// Small chunks run on their slot's stream, not on the pixel stream (enqueue_chunk).  Whatever the library itself enqueues on
+// the pixel stream afterwards - helper copies, a front-end pass, the pixel kernels of a large call - comes after them:
+// a mask is complete before it is copied, an input frame is not overwritten before it has been read.
+int order_pix_after_chains(rmcv_ctx* ctx) {
+    CtxExtra* ex = extra(ctx);
+    for (int i = 0; i < ctx->n_slots && i < kSlots; ++i)
+        if (ex->slot_chained[i]) {
+            RMCV_CUDA(ctx, cudaStreamWaitEvent(ex->pix, ctx->slot[i].ev_lab, 0));
+            ex->slot_chained[i] = false;
+        }
+    return RMCV_OK;
+}
+
 // Enqueue all stages for `frames` frames whose pixels are at `src`, using the scratch of slot `sb`.
 int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pitch, size_t frame_stride, int W, int H,
                   int frames, int frame_base, int bayer_layout, const rmcv_params& prm, uint8_t* mask, size_t mask_pitch,
@@ -230,11 +245,18 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
     if (chained) {
         sl = sp;
         ex->chain = sp;
-        if (sp != ex->pix) {   // what the pixel stream would have been ordered after
-            ResultSet& r = ex->rs[ex->n_calls % kResultSets];   // the set's previous call (kResultSets calls back) must be done
-            if (r.done[0]) { RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, r.done[0], 0)); RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, r.done[1], 0)); }
-            if (host_path) RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, sb.ev_h2d, 0));
+        if (sp != ex->pix) {
+            // everything enqueued on the pixel stream before this call comes first: the waits of begin_call (the result set's
+            // previous call), the frame upload of the host path, helper copies / a front-end pass, the caller's own work on
+            // rmcv_stream()
+            if (!ex->ev_order) RMCV_CUDA(ctx, cudaEventCreateWithFlags(&ex->ev_order, cudaEventDisableTiming));
+            RMCV_CUDA(ctx, cudaEventRecord(ex->ev_order, ex->pix));
+            RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, ex->ev_order, 0));
+            ex->slot_chained[&sb - ctx->slot] = true;
         }
+    } else {
+        const int rc_o = order_pix_after_chains(ctx);
+        if (rc_o != RMCV_OK) return rc_o;
     }
     // the slot's scratch is free once the labelling stages (and the mask download) of its previous chunk are done
     RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, sb.ev_lab, 0));
@@ -657,6 +679,7 @@ int rmcv_ctx_destroy(rmcv_ctx* ctx) {
         for (int i = 1; i < kSlots; ++i) if (ex->labs[i] && ex->labs[i] != ex->pix && ex->labs[i] != ex->lab) cudaStreamDestroy(ex->labs[i]);
         if (ex->lab && ex->lab != ex->pix) cudaStreamDestroy(ex->lab);
         if (ex->out && ex->out != ex->pix) cudaStreamDestroy(ex->out);
+        if (ex->ev_order) cudaEventDestroy(ex->ev_order);
         if (ex->pix && ex->own_pix) cudaStreamDestroy(ex->pix);
         if (ex->h2d) cudaStreamDestroy(ex->h2d);
         if (ex->d2h) cudaStreamDestroy(ex->d2h);
@@ -706,16 +729,19 @@ int rmcv_host_free(rmcv_ctx* ctx, void* hptr) {
 }
 int rmcv_memcpy_h2d(rmcv_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
+    if (order_pix_after_chains(ctx) != RMCV_OK) return RMCV_ERR_CUDA;
     RMCV_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, extra(ctx)->pix));
     return RMCV_OK;
 }
 int rmcv_memcpy_d2h(rmcv_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
+    if (order_pix_after_chains(ctx) != RMCV_OK) return RMCV_ERR_CUDA;
     RMCV_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, extra(ctx)->pix));
     return RMCV_OK;
 }
 int rmcv_memset_d(rmcv_ctx* ctx, void* dst, int value, size_t bytes) {
     if (!ctx) return RMCV_ERR_INVALID_ARG;
+    if (order_pix_after_chains(ctx) != RMCV_OK) return RMCV_ERR_CUDA;
     RMCV_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, extra(ctx)->pix));
     return RMCV_OK;
 }
@@ -1185,6 +1211,7 @@ int rmcv_raw_frontend_batch(rmcv_ctx* ctx, const void* d_raw, size_t pitch, size
     if (bits != 8 && bits != 10 && bits != 12) return set_err(ctx, RMCV_ERR_INVALID_ARG, "bits must be 8, 10 or 12");
     const size_t rowbytes = (size_t)width * (bits > 8 ? 2 : 1);
     if (pitch < rowbytes || out_pitch < (size_t)width) return set_err(ctx, RMCV_ERR_INVALID_ARG, "pitch smaller than a row");
+    if (order_pix_after_chains(ctx) != RMCV_OK) return RMCV_ERR_CUDA;   // d_raw8 may be the input of a small call still in flight
     if (bits > 8 && ((pitch | frame_stride | reinterpret_cast<size_t>(d_raw)) & 1)) return set_err(ctx, RMCV_ERR_INVALID_ARG, "16-bit rows must be 2-byte aligned");
     RMCV_CUDA(ctx, cudaSetDevice(ctx->device));
     RMCV_CUDA(ctx, launch_frontend(static_cast<const uint8_t*>(d_raw), pitch, frame_stride, d_raw8, out_pitch, out_frame_stride, width,

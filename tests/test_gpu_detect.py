@@ -416,3 +416,32 @@ def test_long_contour_fallback_centre_beyond_2_pow_24():
             if not expect_long:
                 e = ref.verdicts[0].ellipse
                 assert np.float32(ci.ellipse).tobytes() == np.float32([e.cx, e.cy, e.w, e.h, e.angle]).tobytes()
+
+
+def test_small_calls_are_ordered_against_the_pixel_stream():
+    """Calls of a few frames run on a slot stream of their own.  The ordering the header promises must still hold
+    without any host synchronisation in between: an async upload on the pixel stream before a call is seen by it, an async
+    overwrite of its input after it waits for it, an async mask download after it copies the finished mask."""
+    W, H = 1280, 1024
+    with rb.Context(max_width=W, max_height=H, max_batch=1) as c:
+        prm = rb.default_params(target=rb.CAMP_BLUE)
+        hs = [c.pinned((H, W, 3)) for _ in range(3)]
+        frames = [synth.make_frame(7100 + s, W, H, synth.plates_for_seed(7100 + s), blue=True) for s in range(3)]
+        for hbuf, f in zip(hs, frames):
+            hbuf.array[:] = f
+        d_frame = c.device_buffer(frames[0].nbytes)
+        d_masks = [c.device_buffer(H * W) for _ in range(3)]
+        h_masks = [c.pinned((H, W)) for _ in range(3)]
+        for rep in range(4):   # several rounds: slots and result sets rotate
+            for k in range(3):  # upload k -> detect k -> download mask k, nothing but stream order in between
+                c._check(c.lib.rmcv_memcpy_h2d(c.h, d_frame.ptr, hs[k].array.ctypes.data, frames[k].nbytes), "h2d")
+                c.detect_batch(d_frame.ptr, W, H, 1, prm, d_masks[k].ptr)
+                c._check(c.lib.rmcv_memcpy_d2h(c.h, h_masks[k].array.ctypes.data, d_masks[k].ptr, H * W), "d2h")
+            res = [c.fetch_results() for _ in range(3)]
+            c.sync()
+            for k in range(3):
+                ref = O.detect_frame(frames[k], target=rb.CAMP_BLUE)
+                assert np.array_equal(h_masks[k].array, ref.binary), "round %d frame %d: mask copied before it was complete" % (rep, k)
+                det = c.frame_detections(res[k], 0)
+                assert len(det.contours) == len(ref.contours) and len(det.armours) == len(ref.armours), (rep, k)
+                h_masks[k].array[:] = 0
