@@ -254,10 +254,11 @@ struct Tuning {
     int bgr_strip, bandstrip_rc, bayer_generic, strip_seg, strip_minb;   // alternative pixel kernels
     int staged_out;                                                  // result write-out through device staging: -1 auto, 0 never, 1 always
     int host_chunk;                                                  // frames per chunk of the host-input entry points
-    int fused_emit, wide_label, chained, fit_in_contour;
-    int chain_pad;                                                   // experiment: pad the labelling kernels' dynamic shared memory to this many bytes per CTA                               // round-2 paths (emit inside the pixel kernel, ...)
+    int fused_emit, wide_label;                                      // emit inside the pixel kernel; cluster kernels for large frames
+    int chained, fit_in_contour;                                     // small chunks: chained launches (0 = off); fits on the contour kernel's warps up to n frames
+    int chain_pad;                                                   // experiment: pad the labelling kernels' dynamic shared memory to this many bytes per CTA
 };
-const Tuning& tuning();  // copies the arc LUT to constant memory (once per process/device)
+const Tuning& tuning();
 
 
 // Programmatic dependent launch (small chunks, latency mode): a chunk's six kernels sit on one stream and each is launched
