@@ -72,6 +72,7 @@ struct CtxExtra {  // C++ side of the ctx (kept out of the POD part)
     cudaStream_t chain = nullptr;     // stream of the current call's chained chunk (small chunks), else null
     cudaEvent_t ev_order = nullptr;   // "everything on the pixel stream so far", waited for by a chained chunk
     bool slot_chained[kSlots] = {};   // the slot's last chunk ran chained on its own stream (its ev_lab marks the chain's end)
+    unsigned call_slots = 0;          // slots whose streams carried chained chunks of the call being enqueued
     bool own_pix = false;
     // where the write-out kernels of the current call put their records (pinned host arrays or the device mirrors)
     rmcv_frame_info* o_frames = nullptr; rmcv_contour_info* o_contours = nullptr; rmcv_lightblob* o_blobs = nullptr;
@@ -253,6 +254,7 @@ int enqueue_chunk(rmcv_ctx* ctx, SlotBuffers& sb, const uint8_t* src, size_t pit
             RMCV_CUDA(ctx, cudaEventRecord(ex->ev_order, ex->pix));
             RMCV_CUDA(ctx, cudaStreamWaitEvent(sp, ex->ev_order, 0));
             ex->slot_chained[&sb - ctx->slot] = true;
+            ex->call_slots |= 1u << (unsigned)(&sb - ctx->slot);
         }
     } else {
         const int rc_o = order_pix_after_chains(ctx);
@@ -360,6 +362,11 @@ int end_call(rmcv_ctx* ctx, int batch) {
     ResultSet& r = ex->rs[ex->n_calls % kResultSets];
     if (r.staged)   // the per-frame counts and offsets travel first; the dense records follow when the call is fetched
         RMCV_CUDA(ctx, cudaMemcpyAsync(r.frames, r.d_frames, (size_t)batch * sizeof(rmcv_frame_info), cudaMemcpyDeviceToHost, ex->out));
+    // a call of several small chunks ran them on several slot streams: the write-out stream, whose event ends the call, waits
+    // for the end of each (ev_lab: recorded behind a chunk's last kernel)
+    for (int i = 0; i < ctx->n_slots && i < kSlots; ++i)
+        if (ex->call_slots & (1u << i)) RMCV_CUDA(ctx, cudaStreamWaitEvent(ex->out, ctx->slot[i].ev_lab, 0));
+    ex->call_slots = 0;
     RMCV_CUDA(ctx, cudaEventRecord(r.done[0], ex->out));
     RMCV_CUDA(ctx, cudaEventRecord(r.done[1], ex->chain ? ex->chain : ex->pix));
     ex->chain = nullptr;
