@@ -449,29 +449,28 @@ def test_small_calls_are_ordered_against_the_pixel_stream():
 
 def test_call_of_several_small_chunks_is_complete_when_fetched():
     """A call cut into chunks of a few frames runs every chunk as a chain on its slot's stream (three slots, three streams);
-    rmcv_fetch_results must wait for all of them, not only for the stream of the last chunk.  Two different batches alternate
-    so that a record left over from the previous call would be noticed."""
-    W, H, B = 1280, 1024, 9
+    rmcv_fetch_results must wait for all of them, not only for the stream of the last chunk.  Four one-frame chunks land on
+    streams 0, 1, 2, 0: frames 0 and 3 are black (their chains are over at once), frames 1 and 2 are crowded, and two different
+    batches alternate so that a record left over from the previous call is noticed."""
+    W, H, B = 1280, 1024, 4
     prm = rb.default_params(target=rb.CAMP_BLUE)
-    batches = [np.stack([synth.make_frame(7300 + 50 * k + s, W, H, synth.plates_for_seed(7300 + 50 * k + s), blue=True) for s in range(B)])
+    black = np.zeros((H, W, 3), np.uint8)
+    batches = [np.stack([black, synth.make_frame(7300 + 50 * k, W, H, 40, blue=True), synth.make_frame(7301 + 50 * k, W, H, 40, blue=True), black])
                for k in range(2)]
+
+    def digest(res):
+        return [(res.frames[f].n_contours, res.frames[f].n_positive, res.frames[f].n_armours,
+                 [bytes(res.contours[res.frames[f].contour_offset + i]) for i in range(res.frames[f].n_contours)]) for f in range(B)]
+
     with rb.Context(max_width=W, max_height=H, max_batch=B, chunk_frames=1) as c:
-        want = []
-        for fr in batches:   # the host entry point synchronises every stream before it returns
-            res = c.detect_batch_host(fr, prm, np.empty((B, H, W), np.uint8))
-            want.append([(res.frames[f].n_contours, res.frames[f].n_positive, res.frames[f].n_armours,
-                          [bytes(res.contours[res.frames[f].contour_offset + i]) for i in range(res.frames[f].n_contours)])
-                         for f in range(B)])
-        assert want[0] != want[1]
+        # the host entry point synchronises every stream before it returns
+        want = [digest(c.detect_batch_host(fr, prm, np.empty((B, H, W), np.uint8))) for fr in batches]
+        assert want[0] != want[1] and want[0][1][0] > 40
         bufs = []
         for fr in batches:
             b = c.device_buffer(fr.nbytes); b.upload(fr); bufs.append(b)
         dm = c.device_buffer(B * H * W)
-        for it in range(40):
+        for it in range(60):
             k = it & 1
             c.detect_batch(bufs[k].ptr, W, H, B, prm, dm.ptr)
-            res = c.fetch_results()
-            got = [(res.frames[f].n_contours, res.frames[f].n_positive, res.frames[f].n_armours,
-                    [bytes(res.contours[res.frames[f].contour_offset + i]) for i in range(res.frames[f].n_contours)])
-                   for f in range(B)]
-            assert got == want[k], "iteration %d: results fetched before every chunk had finished" % it
+            assert digest(c.fetch_results()) == want[k], "iteration %d: results fetched before every chunk had finished" % it
