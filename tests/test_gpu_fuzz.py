@@ -65,3 +65,10 @@ def test_latency_mode_changes_no_result_bit():
     b = run_script("latency_mode_digest_gpu.py", [], env={"RMCV_CHAINED": "0", "RMCV_FIT_IN_CONTOUR": "0", "RMCV_EMIT_BH": "32"}, tag="_plain")
     da, db = a.strip().splitlines()[-1], b.strip().splitlines()[-1]
     assert "digest over" in da and da == db, (da, db)
+
+
+def test_fuzz_calls_in_flight():
+    """random sizes, batches, chunk sizes and depths: device-path calls with up to three in flight, each result and mask byte for
+    byte what the synchronising host entry point returns for the same batch."""
+    out = run_script("fuzz_inflight_gpu.py", [25, 4242])
+    assert " 0 mismatches" in out
