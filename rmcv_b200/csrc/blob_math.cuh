@@ -22,6 +22,18 @@
 #define RMCV_HD inline
 #endif
 
+// Section marks of the ellipse fit for scripts/phase_stamps.py (a -DRMCV_STAMPS build only; the product has none).
+#if defined(RMCV_STAMPS) && defined(__CUDACC__)
+static __device__ long long rmcv_fit_marks[16];
+#if defined(__CUDA_ARCH__)
+#define RMCV_FIT_MARK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) rmcv_fit_marks[i] = clock64(); } while (0)
+#else
+#define RMCV_FIT_MARK(i) do { } while (0)
+#endif
+#else
+#define RMCV_FIT_MARK(i) do { } while (0)
+#endif
+
 namespace rmcv {
 
 #if defined(__CUDA_ARCH__)
@@ -173,10 +185,12 @@ RMCV_HD bool direct_fit(const Moments& m, double scale, double cx, double cy, rm
     }
     const double det = fabs(det3(M));
     *det_out = det;
+    RMCV_FIT_MARK(2);
     if (!(det > 1.0e-10)) return false;
 
     double lam[3], pv[3] = {0, 0, 0};
     const int nl = eig3_values(M, lam);
+    RMCV_FIT_MARK(3);
     double best_cond = 0.0;
     for (int k = 0; k < nl; ++k) {
         double v[3];
@@ -184,6 +198,7 @@ RMCV_HD bool direct_fit(const Moments& m, double scale, double cx, double cy, rm
         const double cond = 4.0 * v[0] * v[2] - v[1] * v[1];
         if (k == 0 || cond > best_cond) { best_cond = cond; pv[0] = v[0]; pv[1] = v[1]; pv[2] = v[2]; }
     }
+    RMCV_FIT_MARK(4);
     double norm = sqrt(pv[0] * pv[0] + pv[1] * pv[1] + pv[2] * pv[2]);
     const int sg = (pv[0] < 0.0 ? -1 : 1) * (pv[1] < 0.0 ? -1 : 1) * (pv[2] < 0.0 ? -1 : 1);
     if (sg <= 0) norm = -norm;
@@ -214,6 +229,7 @@ RMCV_HD bool direct_fit(const Moments& m, double scale, double cx, double cy, rm
         ang = (float)fmod(theta * 180.0 / RMCV_PI, 180.0);
     }
     box->cx = (float)x0; box->cy = (float)y0; box->w = wd; box->h = ht; box->angle = ang;
+    RMCV_FIT_MARK(5);
     return true;
 }
 
@@ -585,6 +601,7 @@ RMCV_HD void fit_from_moments(long long n_i, long long sum_x, long long sum_y, l
     double scale = 100.0 / (s > RMCV_FLT_EPSILON ? s : RMCV_FLT_EPSILON);
     Moments m;
     shift_moments(R, cx - Ox, cy - Oy, &m);
+    RMCV_FIT_MARK(1);
     double det = 0.0;
     const bool ok = direct_fit(m, scale, cx, cy, ell, &det);
     *det0_out = (float)det;
@@ -601,12 +618,15 @@ RMCV_HD void fit_from_moments(long long n_i, long long sum_x, long long sum_y, l
         *branch = (sum_x >= (1LL << 24) || sum_y >= (1LL << 24)) ? RMCV_FIT_FALLBACK_LONG : RMCV_FIT_FALLBACK;
     }
     *status = blob_gates(*ell, prm);
+    RMCV_FIT_MARK(6);
     if (*status == RMCV_CONTOUR_POSITIVE) make_lightblob(*ell, prm.target, blob);
+    RMCV_FIT_MARK(7);
 }
 
 // Same, from the exact integer sums.
 RMCV_HD void fit_contour(const ContourSums& c, const rmcv_params& prm, int* status, int* branch, float* det0_out,
                          rmcv_rotated_rect* ell, rmcv_lightblob* blob) {
+    RMCV_FIT_MARK(0);
     Moments R;
     sums_to_moments(c, &R);
     const double s = c.n > 0 ? (double)c.s_int / (double)c.n : 0.0;

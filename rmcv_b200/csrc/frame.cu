@@ -1273,6 +1273,7 @@ extern "C" int rmcv_debug_stamps(long long* out) {
     return (int)cudaMemcpyFromSymbol(out, rmcv::g_stamps, sizeof(rmcv::g_stamps));
 }
 RMCV_GSTAMP_GETTER(rmcv_debug_ns_frame, rmcv::g_ns_frame)
+extern "C" int rmcv_debug_fit_marks(long long* out) { return (int)cudaMemcpyFromSymbol(out, rmcv_fit_marks, sizeof(rmcv_fit_marks)); }
 namespace rmcv {
 #endif
 

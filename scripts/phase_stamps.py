@@ -34,6 +34,8 @@ def read_ns(reset):
     # pixel, emit, label, contour, fit, order
     return np.stack([o[0, 0], o[1, 0], o[2, 0], o[2, 1], o[2, 2], o[2, 3]]).astype(np.int64)
 import time
+L.rmcv_debug_fit_marks.restype = ctypes.c_int; L.rmcv_debug_fit_marks.argtypes = [ctypes.c_void_p]
+fm = []
 rows = []; ns = []; wall = []
 read_ns(1)
 for i in range(400):
@@ -43,7 +45,8 @@ for i in range(400):
     st = np.zeros((4, 32), np.int64)
     assert L.rmcv_debug_stamps(st.ctypes.data) == 0
     k = read_ns(1)
-    if i >= 100: rows.append(st.copy()); ns.append(k)
+    marks = np.zeros(16, np.int64); assert L.rmcv_debug_fit_marks(marks.ctypes.data) == 0
+    if i >= 100: rows.append(st.copy()); ns.append(k); fm.append(marks)
 a = np.stack(rows)
 n = np.stack(ns)   # [iter][kernel][begin, end]
 kn = ["pixel", "emit", "label", "contour", "fit", "order"]
@@ -52,6 +55,9 @@ print("kernel us (first CTA begins -> last CTA ends):", {kn[j]: round(float(np.m
 print("gap us (end of previous -> begin of next):", {kn[j + 1]: round(float(np.median(n[:, j + 1, 0] - n[:, j, 1])) / 1e3, 2) for j in range(5)})
 print("pixel begin -> order end: %.2f us" % (float(np.median(n[:, 5, 1] - n[:, 0, 0])) / 1e3))
 names = {0: ("label", 12), 1: ("contour (last component of warp 0)", 6), 2: ("fit (last component of thread 0)", 4), 3: ("order", 6)}
+fm = np.stack(fm)
+print("fit sections, cycles (sums->moments+shift, scatter/M/det, eigenvalues, eigenvectors, ellipse, gates, lightblob):",
+      [int(np.median(fm[:, i + 1] - fm[:, i])) for i in range(7)], "total", int(np.median(fm[:, 7] - fm[:, 0])))
 h = a[:, 0, :]
 print("label hole phase cycles (init, bbox, classify, jump, unions, flatten):",
       [int(np.median(x)) for x in (h[:, 12] - h[:, 6], h[:, 13] - h[:, 12], h[:, 14] - h[:, 13], h[:, 15] - h[:, 14], h[:, 16] - h[:, 15], h[:, 7] - h[:, 16])])
