@@ -99,7 +99,7 @@ Tuning read_tuning() {
     t.bgr_strip = env_or("RMCV_BGR_STRIP", 0); t.bandstrip_rc = env_or("RMCV_BANDSTRIP_RC", -1);
     t.bayer_generic = env_or("RMCV_BAYER_GENERIC", 0); t.strip_seg = env_or("RMCV_STRIP_SEG", -1); t.strip_minb = env_or("RMCV_STRIP_MINB", -1);
     t.host_chunk = env_or("RMCV_HOST_CHUNK", -1); t.staged_out = env_or("RMCV_STAGED_OUT", -1);
-    t.fused_emit = env_or("RMCV_FUSED_EMIT", -1); t.wide_label = env_or("RMCV_WIDE_LABEL", -1); t.chained = env_or("RMCV_CHAINED", -1); t.fit_in_contour = env_or("RMCV_FIT_IN_CONTOUR", -1);
+    t.fused_emit = env_or("RMCV_FUSED_EMIT", -1); t.wide_label = env_or("RMCV_WIDE_LABEL", -1); t.chained = env_or("RMCV_CHAINED", -1); t.fit_in_contour = env_or("RMCV_FIT_IN_CONTOUR", -1); t.warp_fit = env_or("RMCV_WARP_FIT", -1);
     t.chain_pad = env_or("RMCV_CHAIN_PAD", -1);
     return t;
 }

@@ -233,6 +233,153 @@ RMCV_HD bool direct_fit(const Moments& m, double scale, double cx, double cy, rm
     return true;
 }
 
+#if defined(__CUDACC__)
+// Warp-cooperative twin of direct_fit for the latency path (contour kernel with the fit on board, frame.cu): ALL 32 lanes call
+// it with identical arguments and all return the identical result.  The independent pieces that are long fp64 dependency
+// chains run on different lanes - the nine divisions of M', the three eigenvalues (cos, Newton polish) with their
+// eigenvectors, the centre and axis pairs - and are exchanged with shuffles.  Every value is computed by the very expression
+// direct_fit uses, so the two agree bit for bit (scripts/latency_mode_digest_gpu.py under pytest -m gpu compares them).
+__device__ __forceinline__ bool direct_fit_warp(const Moments& m, double scale, double cx, double cy, rmcv_rotated_rect* box,
+                                                double* det_out) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const double n = m.n, s1 = scale, s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2;
+    const double inv_n = 1.0 / n;
+    const double X = m.x * s1 * inv_n, Y = m.y * s1 * inv_n;
+    const double XX = m.xx * s2 * inv_n, XY = m.xy * s2 * inv_n, YY = m.yy * s2 * inv_n;
+    const double XXX = m.xxx * s3 * inv_n, XXY = m.xxy * s3 * inv_n, XYY = m.xyy * s3 * inv_n, YYY = m.yyy * s3 * inv_n;
+    const double XXXX = m.xxxx * s4 * inv_n, XXXY = m.xxxy * s4 * inv_n, XXYY = m.xxyy * s4 * inv_n,
+                 XYYY = m.xyyy * s4 * inv_n, YYYY = m.yyyy * s4 * inv_n;
+    const double S1[3][3] = {{XXXX, XXXY, XXYY}, {XXXY, XXYY, XYYY}, {XXYY, XYYY, YYYY}};
+    const double S2[3][3] = {{XXX, XXY, XX}, {XXY, XYY, XY}, {XYY, YYY, YY}};
+    const double S3[3][3] = {{XX, XY, X}, {XY, YY, Y}, {X, Y, 1.0}};
+    const double Ts = det3(S3);
+    double adj[3][3];
+    adj[0][0] = S3[1][1] * S3[2][2] - S3[1][2] * S3[2][1];
+    adj[0][1] = S3[0][2] * S3[2][1] - S3[0][1] * S3[2][2];
+    adj[0][2] = S3[0][1] * S3[1][2] - S3[0][2] * S3[1][1];
+    adj[1][0] = adj[0][1];
+    adj[1][1] = S3[0][0] * S3[2][2] - S3[0][2] * S3[2][0];
+    adj[1][2] = S3[0][2] * S3[1][0] - S3[0][0] * S3[1][2];
+    adj[2][0] = adj[0][2];
+    adj[2][1] = adj[1][2];
+    adj[2][2] = S3[0][0] * S3[1][1] - S3[0][1] * S3[1][0];
+    double TM[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) TM[i][j] = -(adj[i][0] * S2[j][0] + adj[i][1] * S2[j][1] + adj[i][2] * S2[j][2]);
+    // M'[i][j] on lane 3 i + j
+    auto pick = [](double a0, double a1, double a2, int k) -> double { return k == 0 ? a0 : (k == 1 ? a1 : a2); };
+    double Mp[3][3];
+    {
+        const int e = lane < 9 ? lane : 0, ei = e / 3, ej = e - 3 * ei;
+        const double a0 = pick(S2[0][0], S2[1][0], S2[2][0], ei), a1 = pick(S2[0][1], S2[1][1], S2[2][1], ei),
+                     a2 = pick(S2[0][2], S2[1][2], S2[2][2], ei);
+        const double b0 = pick(TM[0][0], TM[0][1], TM[0][2], ej), b1 = pick(TM[1][0], TM[1][1], TM[1][2], ej),
+                     b2 = pick(TM[2][0], TM[2][1], TM[2][2], ej);
+        const double s1e = pick(pick(S1[0][0], S1[0][1], S1[0][2], ej), pick(S1[1][0], S1[1][1], S1[1][2], ej),
+                                pick(S1[2][0], S1[2][1], S1[2][2], ej), ei);
+        const double mine = s1e + (a0 * b0 + a1 * b1 + a2 * b2) / Ts;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Mp[i][j] = __shfl_sync(full, mine, 3 * i + j);
+    }
+    double M[3][3];
+    for (int j = 0; j < 3; ++j) {
+        M[0][j] = Mp[2][j] / 2.0;
+        M[1][j] = -Mp[1][j];
+        M[2][j] = Mp[0][j] / 2.0;
+    }
+    const double det = fabs(det3(M));
+    *det_out = det;
+    if (!(det > 1.0e-10)) return false;
+
+    // eigenvalue k, its Newton polish and its eigenvector on lane k (eig3_values / eig3_vector, one root per lane)
+    int nl;
+    double lam_k;
+    {
+        const double tr = M[0][0] + M[1][1] + M[2][2];
+        const double c1 = (M[0][0] * M[1][1] - M[0][1] * M[1][0]) + (M[0][0] * M[2][2] - M[0][2] * M[2][0]) +
+                          (M[1][1] * M[2][2] - M[1][2] * M[2][1]);
+        const double dt = det3(M);
+        const double a = -tr, b = c1, c = -dt;
+        const double p = b - a * a / 3.0;
+        const double q = 2.0 * a * a * a / 27.0 - a * b / 3.0 + c;
+        const double disc = q * q / 4.0 + p * p * p / 27.0;
+        const int k = lane < 3 ? lane : 0;
+        if (disc <= 0.0 && p < 0.0) {
+            const double r = sqrt(-p / 3.0);
+            double cosarg = -q / (2.0 * r * r * r);
+            cosarg = cosarg > 1.0 ? 1.0 : (cosarg < -1.0 ? -1.0 : cosarg);
+            const double phi = acos(cosarg);
+            lam_k = 2.0 * r * cos((phi - 2.0 * RMCV_PI * k) / 3.0) - a / 3.0;
+            nl = 3;
+        } else {
+            const double sq = sqrt(disc > 0.0 ? disc : 0.0);
+            const double u = cbrt(-q / 2.0 + sq), v = cbrt(-q / 2.0 - sq);
+            lam_k = u + v - a / 3.0;
+            nl = 1;
+        }
+        double l = lam_k;
+        for (int it = 0; it < 3; ++it) {
+            const double f = ((l + a) * l + b) * l + c;
+            const double fp = (3.0 * l + 2.0 * a) * l + b;
+            if (fp == 0.0) break;
+            const double step = f / fp;
+            if (!(fabs(step) < fabs(l) * 1e-3 + 1e-300)) break;
+            l -= step;
+        }
+        lam_k = l;
+    }
+    double pv[3] = {0, 0, 0};
+    {
+        double v[3];
+        eig3_vector(M, lam_k, v);
+        const double cond_k = 4.0 * v[0] * v[2] - v[1] * v[1];
+        double best_cond = 0.0;
+        for (int k = 0; k < nl; ++k) {
+            const double w0 = __shfl_sync(full, v[0], k), w1 = __shfl_sync(full, v[1], k), w2 = __shfl_sync(full, v[2], k);
+            const double cond = __shfl_sync(full, cond_k, k);
+            if (k == 0 || cond > best_cond) { best_cond = cond; pv[0] = w0; pv[1] = w1; pv[2] = w2; }
+        }
+    }
+    double norm = sqrt(pv[0] * pv[0] + pv[1] * pv[1] + pv[2] * pv[2]);
+    const int sg = (pv[0] < 0.0 ? -1 : 1) * (pv[1] < 0.0 ? -1 : 1) * (pv[2] < 0.0 ? -1 : 1);
+    if (sg <= 0) norm = -norm;
+    pv[0] /= norm; pv[1] /= norm; pv[2] /= norm;
+    const double Q0 = (TM[0][0] * pv[0] + TM[0][1] * pv[1] + TM[0][2] * pv[2]) / Ts;
+    const double Q1 = (TM[1][0] * pv[0] + TM[1][1] * pv[1] + TM[1][2] * pv[2]) / Ts;
+    const double Q2 = (TM[2][0] * pv[0] + TM[2][1] * pv[1] + TM[2][2] * pv[2]) / Ts;
+    const double a_ = pv[0], b_ = pv[1], c_ = pv[2];
+    const double u1 = c_ * Q0 * Q0 - b_ * Q0 * Q1 + a_ * Q1 * Q1 + b_ * b_ * Q2;
+    const double u2 = a_ * c_ * Q2;
+    const double l1 = sqrt(b_ * b_ + (a_ - c_) * (a_ - c_));
+    const double l2 = a_ + c_;
+    const double l3 = b_ * b_ - 4.0 * a_ * c_;
+    const double p1 = 2.0 * c_ * Q0 - b_ * Q1;
+    const double p2 = 2.0 * a_ * Q1 - b_ * Q0;
+    // centre: x0 on even lanes, y0 on odd lanes (the same chain of two divisions on different operands)
+    const bool odd = (lane & 1) != 0;
+    const double ctr = (odd ? p2 : p1) / l3 / scale + (odd ? cy : cx);
+    const double x0 = __shfl_sync(full, ctr, 0), y0 = __shfl_sync(full, ctr, 1);
+    // semi-axes: A on even lanes, B on odd lanes.  B = sqrt(2) * sqrt(-1.0 * (num / ((l1 + l2) * l3))) / scale
+    const double num = u1 - 4.0 * u2;
+    const double quo = num / ((odd ? (l1 + l2) : (l1 - l2)) * l3);
+    const double ax = sqrt(2.0) * sqrt(odd ? -1.0 * quo : quo) / scale;
+    const double A = __shfl_sync(full, ax, 0), B = __shfl_sync(full, ax, 1);
+    double theta;
+    if (b_ == 0.0) theta = (a_ < c_) ? 0.0 : RMCV_PI / 2.0;
+    else theta = RMCV_PI / 2.0 + 0.5 * atan2(b_, (a_ - c_));
+    float wd = (float)(2.0 * A), ht = (float)(2.0 * B), ang;
+    if (wd > ht) {
+        const float tmp = wd; wd = ht; ht = tmp;
+        ang = (float)fmod(90.0 + theta * 180.0 / RMCV_PI, 180.0);
+    } else {
+        ang = (float)fmod(theta * 180.0 / RMCV_PI, 180.0);
+    }
+    box->cx = (float)x0; box->cy = (float)y0; box->w = wd; box->h = ht; box->angle = ang;
+    return true;
+}
+#endif  // __CUDACC__
+
 // Solve A x = b (n <= 5) in place by Gaussian elimination with partial pivoting.
 template <int N>
 RMCV_HD void solve_n(double A[N][N], double b[N], double x[N]) {
@@ -587,9 +734,12 @@ RMCV_HD bool contour_is_fitted(long long n, long long cross, const rmcv_params& 
 //   n, sum_x, sum_y, cross  exact integers in absolute pixel coordinates,
 //   R                       moment sums about the origin (Ox, Oy),
 //   s                       L1 spread  sum |x-cx| + |y-cy|  about the double mean.
-RMCV_HD void fit_from_moments(long long n_i, long long sum_x, long long sum_y, long long cross, const Moments& R, double Ox,
-                              double Oy, double s, const rmcv_params& prm, int* status, int* branch, float* det0_out,
-                              rmcv_rotated_rect* ell, rmcv_lightblob* blob) {
+// kWarp (device only): all 32 lanes of a warp call it with identical arguments and the direct fit is the warp-cooperative
+// twin; every lane returns the same result.
+template <bool kWarp>
+RMCV_HD void fit_from_moments_t(long long n_i, long long sum_x, long long sum_y, long long cross, const Moments& R, double Ox,
+                                double Oy, double s, const rmcv_params& prm, int* status, int* branch, float* det0_out,
+                                rmcv_rotated_rect* ell, rmcv_lightblob* blob) {
     *status = RMCV_CONTOUR_SKIPPED;
     *branch = RMCV_FIT_NONE;
     *det0_out = 0.f;
@@ -603,7 +753,12 @@ RMCV_HD void fit_from_moments(long long n_i, long long sum_x, long long sum_y, l
     shift_moments(R, cx - Ox, cy - Oy, &m);
     RMCV_FIT_MARK(1);
     double det = 0.0;
-    const bool ok = direct_fit(m, scale, cx, cy, ell, &det);
+    bool ok;
+#if defined(__CUDA_ARCH__)
+    if (kWarp) ok = direct_fit_warp(m, scale, cx, cy, ell, &det);
+    else
+#endif
+        ok = direct_fit(m, scale, cx, cy, ell, &det);
     *det0_out = (float)det;
     if (ok) {
         *branch = RMCV_FIT_DIRECT;
@@ -623,14 +778,25 @@ RMCV_HD void fit_from_moments(long long n_i, long long sum_x, long long sum_y, l
     RMCV_FIT_MARK(7);
 }
 
+RMCV_HD void fit_from_moments(long long n_i, long long sum_x, long long sum_y, long long cross, const Moments& R, double Ox,
+                              double Oy, double s, const rmcv_params& prm, int* status, int* branch, float* det0_out,
+                              rmcv_rotated_rect* ell, rmcv_lightblob* blob) {
+    fit_from_moments_t<false>(n_i, sum_x, sum_y, cross, R, Ox, Oy, s, prm, status, branch, det0_out, ell, blob);
+}
+
 // Same, from the exact integer sums.
-RMCV_HD void fit_contour(const ContourSums& c, const rmcv_params& prm, int* status, int* branch, float* det0_out,
-                         rmcv_rotated_rect* ell, rmcv_lightblob* blob) {
+template <bool kWarp>
+RMCV_HD void fit_contour_t(const ContourSums& c, const rmcv_params& prm, int* status, int* branch, float* det0_out,
+                           rmcv_rotated_rect* ell, rmcv_lightblob* blob) {
     RMCV_FIT_MARK(0);
     Moments R;
     sums_to_moments(c, &R);
     const double s = c.n > 0 ? (double)c.s_int / (double)c.n : 0.0;
-    fit_from_moments(c.n, c.sx, c.sy, c.cross, R, (double)c.ox, (double)c.oy, s, prm, status, branch, det0_out, ell, blob);
+    fit_from_moments_t<kWarp>(c.n, c.sx, c.sy, c.cross, R, (double)c.ox, (double)c.oy, s, prm, status, branch, det0_out, ell, blob);
+}
+RMCV_HD void fit_contour(const ContourSums& c, const rmcv_params& prm, int* status, int* branch, float* det0_out,
+                         rmcv_rotated_rect* ell, rmcv_lightblob* blob) {
+    fit_contour_t<false>(c, prm, status, branch, det0_out, ell, blob);
 }
 
 }  // namespace rmcv

@@ -255,7 +255,7 @@ struct Tuning {
     int staged_out;                                                  // result write-out through device staging: -1 auto, 0 never, 1 always
     int host_chunk;                                                  // frames per chunk of the host-input entry points
     int fused_emit, wide_label;                                      // emit inside the pixel kernel; cluster kernels for large frames
-    int chained, fit_in_contour;                                     // small chunks: chained launches (0 = off); fits on the contour kernel's warps up to n frames
+    int chained, fit_in_contour, warp_fit;                           // small chunks: chained launches (0 = off); fits on the contour kernel's warps up to n frames; warp-cooperative fit there (0 = lane 0 alone)
     int chain_pad;                                                   // experiment: pad the labelling kernels' dynamic shared memory to this many bytes per CTA
 };
 const Tuning& tuning();

@@ -618,8 +618,10 @@ __device__ __forceinline__ bool g_is_hole(const GRuns& f, int x, int yy) {
 }
 
 // One component's sums -> its record: cv::fitEllipseDirect incl. its fallback, the ratio/tilt gates and the rm::lightblob ctor
-// (reference: src/objdetect.cpp:62-84, src/core.cpp:9-19).  One thread.
-__device__ __forceinline__ void fit_component(const CompAcc& a, const rmcv_params& prm, int32_t* frame_flags, CompRec& rec) {
+// (reference: src/objdetect.cpp:62-84, src/core.cpp:9-19).  One thread - or, kWarp, all 32 lanes of a warp with the same `a`
+// (the warp-cooperative direct fit of blob_math.cuh; every lane ends with the same record, `leader` raises the frame flag).
+template <bool kWarp>
+__device__ __forceinline__ void fit_component(const CompAcc& a, const rmcv_params& prm, int32_t* frame_flags, CompRec& rec, bool leader = true) {
     const int n = (int)a.n;
     rec.firstkey = n > 0 ? a.firstkey : -1;
     rec.n_points = n;
@@ -636,12 +638,12 @@ __device__ __forceinline__ void fit_component(const CompAcc& a, const rmcv_param
         cs.xx = a.xx; cs.xy = a.xy; cs.yy = a.yy; cs.xxx = a.xxx; cs.xxy = a.xxy; cs.xyy = a.xyy; cs.yyy = a.yyy;
         cs.xxxx = a.xxxx; cs.xxxy = a.xxxy; cs.xxyy = a.xxyy; cs.xyyy = a.xyyy; cs.yyyy = a.yyyy;
         cs.s_int = a.s_int; cs.ox = a.ox; cs.oy = a.oy;
-        fit_contour(cs, prm, &rec.status, &rec.fit_branch, &rec.det0, &rec.ellipse, &rec.blob);
+        fit_contour_t<kWarp>(cs, prm, &rec.status, &rec.fit_branch, &rec.det0, &rec.ellipse, &rec.blob);
         // the 4th-order sums are exact 64-bit integers about the component's root pixel: n * extent^4 must stay below 2^62
         // (never reached with the reference's area_max = 99999; a caller who raises it gets the frame flagged, not a wrong fit)
         if (a.fitted) {
             const double ext = (double)max(a.bbox[2] - a.bbox[0], a.bbox[3] - a.bbox[1]) + 1.0;
-            if ((double)a.n * ext * ext * ext * ext > 4.6e18) atomicOr(frame_flags, RMCV_FRAME_OVERFLOW_MOMENTS);
+            if (leader && (double)a.n * ext * ext * ext * ext > 4.6e18) atomicOr(frame_flags, RMCV_FRAME_OVERFLOW_MOMENTS);
         }
     }
 }
@@ -649,7 +651,7 @@ __device__ __forceinline__ void fit_component(const CompAcc& a, const rmcv_param
 // c_first / c_stride: this warp's first component and the number of warps working on the frame
 // kFit: lane 0 goes straight on to the component's fit (chunks of a few frames: one kernel boundary less, and the fits of
 // the small components start while the long ones are still summing; the other lanes idle, so not for throughput)
-template <bool kFit>
+template <int kFit>   // 0: sums only; 1: lane 0 fits; 2: the warp fits (warp-cooperative direct fit)
 __device__ __forceinline__ void contour_body(const Geometry& g, const SlotBuffers& sb, const rmcv_params& prm, int frame, int c_first, int c_stride) {
     __shared__ uint32_t s_lut[256];
     const int W = g.W, H = g.H, R = g.R, C = g.C;
@@ -753,7 +755,7 @@ __device__ __forceinline__ void contour_body(const Geometry& g, const SlotBuffer
             s_int = warp_sum(s_int);
         }
         STAMP(1, 4);
-        if (lane == 0) {
+        if (kFit || lane == 0) {   // (every lane holds the warp totals; with the fit on board all of them go on)
             CompAcc a;
             a.n = n; a.sx = sx; a.sy = sy; a.cross = cross;
             a.xx = m20; a.xy = m11; a.yy = m02; a.xxx = m30; a.xxy = m21; a.xyy = m12; a.yyy = m03;
@@ -764,8 +766,9 @@ __device__ __forceinline__ void contour_body(const Geometry& g, const SlotBuffer
             a.firstkey = fk; a.fitted = fitted ? 1 : 0;
             if (kFit) {
                 CompRec rec;
-                fit_component(a, prm, &sb.counters[frame].flags, rec);
-                sb.comps[(size_t)frame * C + c] = rec;
+                if (kFit == 2) fit_component<true>(a, prm, &sb.counters[frame].flags, rec, lane == 0);
+                else if (lane == 0) fit_component<false>(a, prm, &sb.counters[frame].flags, rec);
+                if (lane == 0) sb.comps[(size_t)frame * C + c] = rec;
             } else {
                 accs[c] = a;
             }
@@ -775,7 +778,7 @@ __device__ __forceinline__ void contour_body(const Geometry& g, const SlotBuffer
     RMCV_GSTAMP_END(g_ns_frame, 1);
 }
 
-template <bool kFit>
+template <int kFit>
 __global__ void __launch_bounds__(128) contour_kernel(const ContourParams p) {
     const int wpc = blockDim.x >> 5;
     contour_body<kFit>(p.g, p.sb, p.prm, blockIdx.x, blockIdx.y * wpc + (threadIdx.x >> 5), gridDim.y * wpc);
@@ -803,7 +806,7 @@ __device__ __forceinline__ void fit_body(const Geometry& g, const SlotBuffers& s
         const CompAcc& a = sb.acc[(size_t)frame * C + c];
         CompRec rec;
         STAMP(2, 1);
-        fit_component(a, prm, &sb.counters[frame].flags, rec);
+        fit_component<false>(a, prm, &sb.counters[frame].flags, rec);
         STAMP(2, 2);
         sb.comps[(size_t)frame * C + c] = rec;
         STAMP(2, 3);
@@ -1192,10 +1195,10 @@ cudaError_t launch_frames(const FrameLaunch& L, const rmcv_params& prm, int max_
         dim3 grid(L.frames, gy);
         const size_t pad = tune.chain_pad > 0 ? (size_t)tune.chain_pad : 0;
         if (fit_in_contour) {
-            if ((e = launch_chained<ContourParams>(contour_kernel<true>, grid, dim3(128), 0, st, chained, p)) != cudaSuccess) return e;
+            if ((e = launch_chained<ContourParams>(tune.warp_fit == 0 ? contour_kernel<1> : contour_kernel<2>, grid, dim3(128), 0, st, chained, p)) != cudaSuccess) return e;
         } else {
-            if (pad > 48 * 1024) cudaFuncSetAttribute(contour_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
-            if ((e = launch_chained<ContourParams>(contour_kernel<false>, grid, dim3(128), pad, st, chained, p)) != cudaSuccess) return e;
+            if (pad > 48 * 1024) cudaFuncSetAttribute(contour_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+            if ((e = launch_chained<ContourParams>(contour_kernel<0>, grid, dim3(128), pad, st, chained, p)) != cudaSuccess) return e;
         }
         if (launches) ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;

@@ -63,8 +63,9 @@ def test_latency_mode_changes_no_result_bit():
     hence two interpreters) must give the same digest over every record and mask byte."""
     a = run_script("latency_mode_digest_gpu.py", [], tag="_default")
     b = run_script("latency_mode_digest_gpu.py", [], env={"RMCV_CHAINED": "0", "RMCV_FIT_IN_CONTOUR": "0", "RMCV_EMIT_BH": "32"}, tag="_plain")
-    da, db = a.strip().splitlines()[-1], b.strip().splitlines()[-1]
-    assert "digest over" in da and da == db, (da, db)
+    c = run_script("latency_mode_digest_gpu.py", [], env={"RMCV_WARP_FIT": "0"}, tag="_lane0")   # fits on the contour warps, lane 0 alone
+    da, db, dc = a.strip().splitlines()[-1], b.strip().splitlines()[-1], c.strip().splitlines()[-1]
+    assert "digest over" in da and da == db == dc, (da, db, dc)
 
 
 def test_fuzz_calls_in_flight():
