@@ -924,8 +924,13 @@ __device__ __forceinline__ void order_body(const OrderParams& p, uint8_t* smem) 
                 float gates[6];
                 if (k < npairs) {
                     pair_from_index(k, P, &i, &j);
-                    pass = pair_passes(sblob[i], sblob[j], p.prm);
-                    if (pass) pair_gates(sblob[i], sblob[j], p.prm, gates);
+                    if (LNT >= 512) {   // a handful of frames, one pair per thread: the gate values at once (same verdict), not
+                                        // the cheap verdict first and the values, with a second atan2, for the survivors
+                        pass = pair_gates(sblob[i], sblob[j], p.prm, gates);
+                    } else {
+                        pass = pair_passes(sblob[i], sblob[j], p.prm);
+                        if (pass) pair_gates(sblob[i], sblob[j], p.prm, gates);
+                    }
                 }
                 int total;
                 const int pos = base + block_excl_scan(pass ? 1 : 0, &total, sh_scan);
